@@ -1,0 +1,465 @@
+#!/usr/bin/env python
+"""Benchmark of the ingest hot path (BASELINE.json metric: frame-sets/s, 8 x 1280x800).
+
+    python bench.py --gpus N --steps K --warmup W            # our arm (one process per GPU under torchrun)
+    python bench.py --impl reference --gpus N --steps K --warmup W   # the reference's CPU path (oracle port)
+
+Workload = BASELINE config 2: a 4 x OAK-D Pro stereo rig, 8 mono8 streams of 1280x800 per frame set,
+format conversion (mono8 pass-through) fused with the stereo-rectification remap.  One *step* is one
+pass of the hot path over a batch of ``--batch`` frame sets (default 64 = 524 MB in + 524 MB out per
+step, far larger than the 126 MB L2, so no step is served from cache).
+
+* ``value``   : frame-sets/s with inputs resident in HBM (CUDA events on the launch stream).
+* ``e2e``     : same metric through ``IngestContext.ingest_host`` - pinned HOST buffers in and out,
+                host->device and device->host copies inside the timed region.
+* ``roofline``: algorithmic bytes (2 B/px: 1 read + 1 written) of one launch
+                of the rectify kernel / its average duration, against MEASURED_PEAKS.json ``hbm_gbs``.
+* ``cpu_baseline``: the oracle (cv2.remap, all host threads) on a bounded sample, rank 0, N=1 only.
+
+With N > 1 every rank processes its own batch (weak scaling, no data-path collective - config 2 has no
+exchange step); ``extras.config5`` additionally times the 4 x (mono rectify + depth -> cloud) frame set
+and the NCCL gather of the clouds separately.
+"""
+
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+if str(ROOT) not in sys.path:
+    sys.path.insert(0, str(ROOT))
+
+W, H = 1280, 800
+N_CAMERAS = 4  # stereo sources -> 8 streams
+STREAMS = 2 * N_CAMERAS
+PX_PER_SET = STREAMS * W * H
+ALGO_BYTES_PER_PX = 2  # mono8 -> rectified mono8
+FALLBACK_HBM_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md fallback
+
+
+def measured_peak() -> tuple[float, str]:
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        try:
+            return float(json.loads(p.read_text())["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs"
+        except Exception:
+            pass
+    return FALLBACK_HBM_GBS, "fallback 6650 GB/s (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int) -> None:
+        self.index = index
+        self.proc: subprocess.Popen | None = None
+        self.lines: list[str] = []
+        self.thread: threading.Thread | None = None
+
+    def start(self) -> None:
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+            return
+
+        def pump() -> None:
+            assert self.proc and self.proc.stdout
+            for line in self.proc.stdout:
+                self.lines.append(line.strip())
+
+        self.thread = threading.Thread(target=pump, daemon=True)
+        self.thread.start()
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons, power = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            parts = [p.strip() for p in ln.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                smax.append(float(parts[1]))
+                power.append(float(parts[2]))
+            except ValueError:
+                continue
+            for nm, val in zip(names, parts[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        return {
+            "sm_mhz": float(np.median(sm)) if sm else None,
+            "sm_max_mhz": float(max(smax)) if smax else None,
+            "power_w_max": float(max(power)) if power else None,
+            "samples": len(sm),
+            "reasons": sorted(reasons),
+        }
+
+
+# ------------------------------------------------------------------------------------------------
+# workload construction (shared by both arms)
+# ------------------------------------------------------------------------------------------------
+def build_rig(seed: int = 1337):
+    """4 synthetic OAK-D Pro stereo sources + their rectification maps (host float32)."""
+    from thor_slam_b200.camera.synthetic import make_rig_sources
+    from thor_slam_b200.ingest.calib import stereo_rectify_maps
+
+    sources = make_rig_sources(N_CAMERAS, resolution=(W, H), pixel_format="mono8", seed=seed, pool=2)
+    maps = []
+    for s in sources:
+        maps.extend(stereo_rectify_maps(s.get_intrinsics(), s.get_extrinsics(), (W, H)))
+    return sources, maps  # maps[2*i + {0,1}] = (mapx, mapy) of source i left/right
+
+
+def host_frames(sources, n_sets: int) -> list[np.ndarray]:
+    """Per stream, ``n_sets`` frames [n_sets, H, W] u8 cycling through each source's seeded pool."""
+    out = []
+    for s in sources:
+        pool = s._pool
+        for cam in range(2):
+            out.append(np.stack([pool[b % len(pool)][cam] for b in range(n_sets)]))
+    return out
+
+
+def cpu_pass(frames: list[np.ndarray], maps, n_sets: int) -> None:
+    """The reference-side CPU path for this workload: cv2.remap per stream per frame set (oracle)."""
+    from oracle import rectify as orc
+
+    for b in range(n_sets):
+        for s in range(STREAMS):
+            orc.remap_cv(frames[s][b], maps[s][0], maps[s][1])
+
+
+def time_cpu(frames, maps, budget_s: float, max_sets: int) -> tuple[float, int, float]:
+    """(frame-sets/s, sets processed, seconds) on a bounded sample."""
+    cpu_pass(frames, maps, 1)  # warm OpenCV's thread pool
+    done, t0 = 0, time.perf_counter()
+    while done < max_sets and (time.perf_counter() - t0) < budget_s:
+        cpu_pass([f[done % f.shape[0]: done % f.shape[0] + 1] for f in frames], maps, 1)
+        done += 1
+    dt = time.perf_counter() - t0
+    return done / dt, done, dt
+
+
+# ------------------------------------------------------------------------------------------------
+def run_reference(args) -> None:
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import cv2
+
+    cores = os.cpu_count() or 1
+    cv2.setNumThreads(cores)
+    sources, maps = build_rig()
+    sets_per_step = max(1, args.ref_sets)
+    frames = host_frames(sources, min(sets_per_step, 4))
+    for _ in range(args.warmup):
+        cpu_pass([f[:1] for f in frames], maps, 1)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        for b in range(sets_per_step):
+            cpu_pass([f[b % f.shape[0]: b % f.shape[0] + 1] for f in frames], maps, 1)
+    dt = time.perf_counter() - t0
+    value = args.steps * sets_per_step / dt
+    line = {
+        "impl": "reference",
+        "metric": "frame_sets_per_sec",
+        "value": value,
+        "unit": "frame-sets/s",
+        "n_gpus": args.gpus,
+        "steps": args.steps,
+        "warmup": args.warmup,
+        "ms_per_step": dt / args.steps * 1e3,
+        "higher_is_better": True,
+        "scaling": "weak",
+        "vs_baseline": None,
+        "dtype": "u8",
+        "data": "synthetic",
+        "config": workload_config(sets_per_step, args.gpus) | {"note": "CPU path: cv2.remap INTER_LINEAR per stream (oracle port of the reference-side path), all host threads"},
+        "mpix_per_sec": value * PX_PER_SET / 1e6,
+        "cpu_baseline": {"value": value, "unit": "frame-sets/s", "cores": cv2.getNumThreads(), "kind": "port",
+                         "sample": f"{args.steps} steps x {sets_per_step} frame sets of 8 x 1280x800 mono8, cv2.remap"},
+        "e2e": {"value": value, "unit": "frame-sets/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def workload_config(batch: int, gpus: int) -> dict:
+    return {
+        "workload": "BASELINE config 2: 4x OAK-D Pro stereo rig, 8 mono8 streams 1280x800, convert+rectify (stereoRectify maps, rational-8 distortion)",
+        "streams": STREAMS,
+        "width": W,
+        "height": H,
+        "frame_sets_per_step": batch,
+        "sharding": f"frame-set batches per rank x{gpus} (no data-path collective)",
+        "l2_policy": "inputs larger than L2 (batch in+out >= 1 GB vs 126 MB L2); no flush needed",
+    }
+
+
+def run_ours(args) -> None:
+    import torch
+    import torch.distributed as dist
+
+    from thor_slam_b200.ingest import formats as F
+    from thor_slam_b200.ingest.context import IngestContext, StreamSpec
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local_rank)
+    distributed = world > 1
+    if distributed:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier() -> None:
+        if distributed:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    ctx = IngestContext(local_rank)
+    stream = torch.cuda.current_stream()
+    ctx.set_stream(stream.cuda_stream)
+
+    sources, maps = build_rig()
+    for cam, (mx, my) in enumerate(maps):
+        ctx.upload_rectify_map(cam, mx, my, (W, H))
+
+    B = args.batch
+    pool_frames = host_frames(sources, 2)  # two distinct frames per stream, tiled over the batch on device
+    d_src, d_dst = [], []
+    for s in range(STREAMS):
+        pf = torch.from_numpy(pool_frames[s]).cuda()
+        d_src.append(pf.repeat((B + 1) // 2, 1, 1)[:B].contiguous())
+        d_dst.append(torch.empty((B, H, W), dtype=torch.uint8, device="cuda"))
+    specs = [StreamSpec(F.KIND_RECTIFY, d_src[s], d_dst[s], F.MONO8, F.MONO8, camera=s) for s in range(STREAMS)]
+
+    # ---- device-resident throughput ("value") ---------------------------------------------------
+    for _ in range(args.warmup):
+        ctx.ingest(specs)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = ctx.launch_count
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record(stream)
+    for _ in range(args.steps):
+        ctx.ingest(specs)
+    ev1.record(stream)
+    barrier()
+    launches = ctx.launch_count - launches0
+    ms = ev0.elapsed_time(ev1)
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    if distributed:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    ms_per_step = ms_max / args.steps
+    value = world * B * args.steps / (ms_max * 1e-3)
+
+    # parity spot check inside the bench (rank 0, one frame of one stream) - the number is void otherwise
+    if rank == 0:
+        from oracle import rectify as orc
+
+        want = orc.remap_cv(pool_frames[3][1], maps[3][0], maps[3][1])
+        got = d_dst[3][1].cpu().numpy()
+        if not np.array_equal(got, want):
+            raise SystemExit("bench: GPU output differs from cv2.remap - refusing to report a number")
+
+    # ---- end to end through the host-buffer API ("e2e") -----------------------------------------
+    Be = min(B, args.e2e_batch)
+    h_src = [torch.from_numpy(np.ascontiguousarray(np.tile(pool_frames[s], ((Be + 1) // 2, 1, 1))[:Be])).pin_memory() for s in range(STREAMS)]
+    h_dst = [torch.empty((Be, H, W), dtype=torch.uint8).pin_memory() for _ in range(STREAMS)]
+    hspecs = [StreamSpec(F.KIND_RECTIFY, h_src[s], h_dst[s], F.MONO8, F.MONO8, camera=s) for s in range(STREAMS)]
+    e2e_steps = max(3, min(args.steps, 10))
+    for _ in range(2):
+        ctx.ingest_host(hspecs, chunk=args.chunk)
+    barrier()
+    launches_e2e0 = ctx.launch_count
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        ctx.ingest_host(hspecs, chunk=args.chunk)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    te = torch.tensor([dt], dtype=torch.float64, device="cuda")
+    if distributed:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = world * Be * e2e_steps / float(te.item())
+    launches_e2e = ctx.launch_count - launches_e2e0
+    if rank == 0:
+        from oracle import rectify as orc
+
+        if not np.array_equal(h_dst[5][0].numpy(), orc.remap_cv(pool_frames[5][0], maps[5][0], maps[5][1])):
+            raise SystemExit("bench: e2e output differs from cv2.remap - refusing to report a number")
+
+    extras: dict = {}
+    if args.extras:
+        extras = run_extras(args, ctx, sources, maps, rank, world, distributed, barrier)
+
+    # ---- CPU baseline (rank 0, N = 1 only) ---------------------------------------------------------
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        import cv2
+
+        cv2.setNumThreads(os.cpu_count() or 1)
+        cps, done, secs = time_cpu(pool_frames, maps, args.cpu_budget, 4096)
+        cpu_baseline = {"value": cps, "unit": "frame-sets/s", "cores": cv2.getNumThreads(), "kind": "port",
+                        "sample": f"{done} frame sets of 8 x 1280x800 mono8 in {secs:.1f} s, cv2.remap INTER_LINEAR (OpenCV {cv2.__version__})"}
+
+    if rank == 0:
+        peak, peak_src = measured_peak()
+        algo_bytes = B * PX_PER_SET * ALGO_BYTES_PER_PX
+        achieved = algo_bytes / (ms_per_step * 1e-3) / 1e9
+        line = {
+            "metric": "frame_sets_per_sec",
+            "value": value,
+            "unit": "frame-sets/s",
+            "n_gpus": world,
+            "steps": args.steps,
+            "warmup": args.warmup,
+            "ms_per_step": ms_per_step,
+            "higher_is_better": True,
+            "scaling": "weak",
+            "vs_baseline": None,
+            "dtype": "u8",
+            "data": "synthetic",
+            "config": workload_config(B, world),
+            "mpix_per_sec": value * PX_PER_SET / 1e6,
+            "e2e": {"value": e2e_value, "unit": "frame-sets/s", "h2d_bytes_per_step": Be * PX_PER_SET, "d2h_bytes_per_step": Be * PX_PER_SET,
+                    "frame_sets_per_step": Be, "steps": e2e_steps, "chunk": args.chunk, "gpu_launches": launches_e2e},
+            "gpu_launches": launches,
+            "clocks": clocks,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "kernel": "rectify_tile_kernel<1>", "algorithmic_bytes_per_launch": algo_bytes,
+                         "peak_source": peak_src, "frac_of_8000_datasheet": achieved / 8000.0,
+                         "note": "per-rank launch; duration = max-over-ranks ms_per_step (one launch per step)"},
+            "cpu_baseline": cpu_baseline,
+        }
+        if extras:
+            line["extras"] = extras
+        print(json.dumps(line))
+    ctx.close()
+    if distributed:
+        dist.destroy_process_group()
+
+
+def run_extras(args, ctx, sources, maps, rank, world, distributed, barrier) -> dict:
+    """Config 5 frame sets (4 mono rectify + 4 depth -> cloud) and, for N > 1, the cloud gather."""
+    import torch
+    import torch.distributed as dist
+
+    from thor_slam_b200.camera.synthetic import make_depth
+    from thor_slam_b200.ingest import formats as F
+    from thor_slam_b200.ingest.calib import body_T_camera
+    from thor_slam_b200.ingest.context import StreamSpec
+
+    B = max(1, args.batch // 4)
+    rng = np.random.default_rng(1337 + rank)
+    specs = []
+    keep = []
+    clouds = torch.empty((N_CAMERAS, B, H, W, 3), dtype=torch.float32, device="cuda")
+    for i, s in enumerate(sources):
+        left = torch.from_numpy(np.stack([s._pool[b % 2][0] for b in range(B)])).cuda()
+        out = torch.empty_like(left)
+        depth = torch.from_numpy(np.stack([make_depth(rng, W, H) for _ in range(2)]).view(np.int16)).cuda().view(torch.uint16)
+        depth = depth.repeat((B + 1) // 2, 1, 1)[:B].contiguous()
+        mask = torch.empty((B, H, W), dtype=torch.uint8, device="cuda")
+        count = torch.zeros((B,), dtype=torch.int32, device="cuda")
+        intr = s.get_intrinsics()[0]
+        ctx.upload_projection(2 * i, intr.matrix, body_T_camera(None, s.get_extrinsics()[0].to_4x4_matrix(), "rdf"), (W, H))
+        specs.append(StreamSpec(F.KIND_RECTIFY, left, out, F.MONO8, F.MONO8, camera=2 * i))
+        specs.append(StreamSpec(F.KIND_BACKPROJECT, depth, clouds[i], F.DEPTH16, F.XYZ32F, camera=2 * i, mask=mask, count=count))
+        keep.append((left, out, depth, mask, count))
+    stream = torch.cuda.current_stream()
+    for _ in range(3):
+        ctx.ingest(specs)
+    barrier()
+    steps = max(3, min(args.steps, 10))
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(steps):
+        ctx.ingest(specs)
+    e1.record(stream)
+    barrier()
+    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
+    if distributed:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item()) / steps
+    bytes_per_set = N_CAMERAS * W * H * (2 + 15)
+    peak, _ = measured_peak()
+    out = {"config5": {"frame_sets_per_step_per_rank": B, "ms_per_step": ms, "frame_sets_per_sec": world * B / (ms * 1e-3),
+                       "hbm_gbs": B * bytes_per_set / (ms * 1e-3) / 1e9, "frac": B * bytes_per_set / (ms * 1e-3) / 1e9 / peak,
+                       "algorithmic_bytes_per_frame_set": bytes_per_set}}
+    if distributed:
+        uid = [ctx.nccl_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        ctx.nccl_init(uid[0], rank, world)
+        nbytes = clouds.numel() * 4
+        gathered = torch.empty((world, *clouds.shape), dtype=torch.float32, device="cuda") if rank == 0 else None
+        sizes = [nbytes] * world
+        for _ in range(2):
+            ctx.gather_clouds(clouds, gathered, sizes, root=0)
+        barrier()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record(stream)
+        for _ in range(steps):
+            ctx.gather_clouds(clouds, gathered, sizes, root=0)
+        g1.record(stream)
+        barrier()
+        tg = torch.tensor([g0.elapsed_time(g1)], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tg, op=dist.ReduceOp.MAX)
+        gms = float(tg.item()) / steps
+        out["config5"]["gather"] = {"ms": gms, "bytes_into_root": nbytes * (world - 1), "root_ingress_gbs": nbytes * (world - 1) / (gms * 1e-3) / 1e9,
+                                    "kind": "grouped ncclSend/ncclRecv, dense clouds"}
+    return out
+
+
+def main() -> None:
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=64, help="frame sets per step (per rank)")
+    ap.add_argument("--e2e-batch", type=int, default=32, dest="e2e_batch")
+    ap.add_argument("--chunk", type=int, default=4, help="frame sets per H2D/compute/D2H pipeline stage")
+    ap.add_argument("--cpu-budget", type=float, default=10.0, dest="cpu_budget", help="seconds of CPU work for cpu_baseline")
+    ap.add_argument("--ref-sets", type=int, default=8, dest="ref_sets", help="frame sets per step of the reference arm")
+    ap.add_argument("--no-cpu", action="store_true", dest="no_cpu")
+    ap.add_argument("--extras", action="store_true", help="also time config 5 (rectify + back-projection) and the NCCL gather")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3  # timing rule: at least 3 warm-up steps
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

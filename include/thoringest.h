@@ -1,0 +1,181 @@
+/*
+ * thoringest.h - C ABI of the B200 ingest library (libthoringest.so).
+ *
+ * This is the drop-in boundary for ONE path of WT-MM/thor-slam: the per-frame-set
+ * ingest stage between CameraRig.get_synchronized_frames() and the SLAM / mapping
+ * consumers.  The reference is pure Python and has no FFI of its own; each entry
+ * point below names the reference code whose per-pixel work it takes over
+ * (paths relative to the reference repo root).  Host code binds these with ctypes
+ * (thor_slam_b200/ingest/_lib.py; the stub a reference maintainer would add is in
+ * INTEGRATION.md).
+ *
+ * Rules of the boundary
+ *  - plain C types only; every pointer argument is either a HOST pointer or a
+ *    DEVICE pointer as stated per argument - no torch / numpy types cross it;
+ *  - the library never allocates a buffer the caller sees, except the explicitly
+ *    named peer buffers (ti_peer_alloc); callers (PyTorch tensors in our host code)
+ *    own all image / cloud memory and keep it alive until ti_sync() returns;
+ *  - every function returns a ti_status; ti_last_error() gives the message;
+ *  - one ti_ctx per (process, GPU); a ctx is not thread-safe (the rig lock that
+ *    serialises CameraRig - thor_slam/camera/rig.py:114 - serialises it too);
+ *  - all kernels are enqueued on the stream given to ti_set_stream() (default: the
+ *    legacy NULL stream) and are asynchronous unless stated otherwise;
+ *  - there is NO CPU fallback: without a CUDA device ti_create() fails.
+ */
+#ifndef THORINGEST_H_
+#define THORINGEST_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TI_ABI_VERSION 1
+#define TI_MAX_CAMERAS 64 /* calibration slots per context                     */
+#define TI_MAX_STREAMS 32 /* streams of one kind per ti_ingest() call          */
+#define TI_MAX_DIM 2046   /* max source width/height addressable by the packed remap LUT */
+
+typedef struct ti_ctx ti_ctx;
+
+typedef enum ti_status {
+    TI_OK = 0,
+    TI_EINVAL = 1, /* bad argument (maps to ValueError on the Python side)      */
+    TI_ECUDA = 2,  /* a CUDA call failed (RuntimeError)                         */
+    TI_ENCCL = 3,  /* an NCCL call failed / NCCL not loadable (RuntimeError)    */
+    TI_ESTATE = 4, /* call order violated, e.g. camera slot not uploaded        */
+    TI_ENOMEM = 5
+} ti_status;
+
+/* Wire formats.  MONO8: HxW u8.  BGR8 / RGB8: HxWx3 u8 interleaved.  NV12: (H*3/2)xW u8,
+ * luma plane then interleaved U,V at half resolution.  DEPTH16: HxW u16 millimetres,
+ * 0 = invalid.  XYZ32F: HxWx3 f32 metres.  Rows are tightly packed. */
+typedef enum ti_format {
+    TI_FMT_MONO8 = 0,
+    TI_FMT_BGR8 = 1,
+    TI_FMT_RGB8 = 2,
+    TI_FMT_NV12 = 3,
+    TI_FMT_DEPTH16 = 4,
+    TI_FMT_XYZ32F = 5
+} ti_format;
+
+typedef enum ti_kind {
+    TI_KIND_CONVERT = 0,     /* format conversion only                                   */
+    TI_KIND_RECTIFY = 1,     /* format conversion fused with the undistort/rectify remap */
+    TI_KIND_BACKPROJECT = 2  /* depth -> body-frame xyz + valid mask + valid count       */
+} ti_kind;
+
+/* One stream of a frame-set batch.  Frame b of the batch lives at
+ * src + b*src_frame_stride / dst + b*dst_frame_stride (bytes). */
+typedef struct ti_stream {
+    int32_t kind;       /* ti_kind                                                         */
+    int32_t camera;     /* calibration slot (RECTIFY: remap LUT, BACKPROJECT: projection)   */
+    int32_t src_format; /* ti_format of src                                                */
+    int32_t dst_format; /* ti_format of dst                                                */
+    int32_t width;      /* source width in pixels                                          */
+    int32_t height;     /* source height in pixels (NV12: luma rows)                       */
+    const void* src;    /* DEVICE (ti_ingest) or HOST (ti_ingest_host) pointer, 16-B aligned */
+    void* dst;          /* likewise                                                        */
+    uint64_t src_frame_stride;
+    uint64_t dst_frame_stride;
+    void* mask;               /* BACKPROJECT: u8 HxW valid mask per frame, or NULL          */
+    uint64_t mask_frame_stride;
+    uint32_t* count;          /* BACKPROJECT: one u32 valid-pixel count per frame, or NULL  */
+} ti_stream;
+
+/* ---- context ------------------------------------------------------------------------- */
+int ti_abi_version(void);
+int ti_create(int device, ti_ctx** out);
+int ti_destroy(ti_ctx* ctx);
+/* Message of the last failing call on ctx (ctx == NULL: last failing ti_create). */
+const char* ti_last_error(const ti_ctx* ctx);
+/* cuda_stream: a cudaStream_t (e.g. torch.cuda.current_stream().cuda_stream). */
+int ti_set_stream(ti_ctx* ctx, void* cuda_stream);
+int ti_sync(ti_ctx* ctx);
+/* Kernel launches issued by this ctx since creation (for bench.py "gpu_launches"). */
+uint64_t ti_launch_count(const ti_ctx* ctx);
+int ti_device_sm_count(const ti_ctx* ctx);
+
+/* ---- calibration upload (one-off; replaces nothing per-frame in the reference:
+ *      Intrinsics/Extrinsics of thor_slam/camera/types.py:31-69 become device constants) */
+
+/* Remap LUT of calibration slot `camera` from OpenCV-style float maps (HOST pointers,
+ * dst_w*dst_h floats each, as produced by cv2.initUndistortRectifyMap(..., CV_32FC1)):
+ * output pixel (u,v) samples the source image at (mapx[v][u], mapy[v][u]).
+ * Quantised exactly like cv2.remap: ix = rint(mapx*32) (half-to-even), 1/32-px taps. */
+int ti_upload_rectify_map(ti_ctx* ctx, int camera, int dst_w, int dst_h, int src_w, int src_h,
+                          const float* mapx, const float* mapy);
+
+/* Pinhole projection + pose of calibration slot `camera` for back-projection.
+ * k = {fx, fy, cx, cy} of the DEPTH image (thor_slam/camera/drivers/luxonis.py:974-1066);
+ * body_T_cam = row-major 3x4 [R|t], metres, = M * world_T_camera with world_T_camera from
+ * RigCalibration.get_world_extrinsics (thor_slam/camera/rig.py:35-70) and M = RDF_TO_FLU
+ * (thor_slam/slam/adapters/isaac_ros.py:42-49) or identity.  float64 in, rounded once. */
+int ti_upload_projection(ti_ctx* ctx, int camera, int width, int height, const double k[4],
+                         const double body_T_cam[12]);
+
+/* u8 dst_h x dst_w mask of slot `camera`: 1 where all four bilinear taps are inside the
+ * source image.  Static per calibration.  dst: DEVICE pointer. */
+int ti_get_valid_mask(ti_ctx* ctx, int camera, uint8_t* dst);
+
+/* ---- per-frame work, DEVICE pointers --------------------------------------------------- */
+
+/* Format conversion of n_batch frames.  Takes over cv2.cvtColor(BGR2RGB)
+ * (thor_slam/slam/adapters/isaac_ros.py:357, scripts/run_pipeline.py:234) and the NV12 ->
+ * BGR/GRAY conversion inside dai.ImgFrame.getCvFrame() (thor_slam/camera/drivers/luxonis.py:773).
+ * Supported: BGR8->RGB8, BGR8->MONO8, NV12->MONO8, NV12->RGB8, NV12->BGR8, MONO8->MONO8. */
+int ti_convert(ti_ctx* ctx, int src_format, int dst_format, const void* src, void* dst, int width,
+               int height, int n_batch, uint64_t src_frame_stride, uint64_t dst_frame_stride);
+
+/* Conversion fused with the bilinear remap of slot `camera` (the undistortion the reference
+ * delegates to cuVSLAM with rectified_images:=false - isaac_ros.py:364-411, Makefile:77-80).
+ * src has the slot's src_w x src_h, dst its dst_w x dst_h.  Bit-exact with
+ * cv2.remap(cvtColor(src), INTER_LINEAR, BORDER_CONSTANT 0).  Supported: MONO8->MONO8,
+ * NV12->MONO8, BGR8->MONO8, BGR8->RGB8, NV12->RGB8. */
+int ti_rectify(ti_ctx* ctx, int camera, int src_format, int dst_format, const void* src, void* dst,
+               int n_batch, uint64_t src_frame_stride, uint64_t dst_frame_stride);
+
+/* depth (u16 mm) -> xyz (f32 x3, body frame, invalid = 0,0,0) + mask (u8) + per-frame count
+ * (u32, overwritten).  Takes over the back-projection the reference leaves to nvblox
+ * (scripts/run_pipeline.py:247-256) and examples/rgbd_stream.py:121-123,270-276 (mask/count).
+ * mask and count may be NULL. */
+int ti_backproject(ti_ctx* ctx, int camera, const uint16_t* depth, float* xyz, uint8_t* mask,
+                   uint32_t* count, int n_batch, uint64_t depth_frame_stride,
+                   uint64_t xyz_frame_stride, uint64_t mask_frame_stride);
+
+/* Whole frame-set batch in at most one launch per kind: every stream x every frame.
+ * This is the call behind CameraRig.get_synchronized_frames() (thor_slam/camera/rig.py:358-415)
+ * in the drop-in rig.  streams: HOST array, DEVICE image pointers inside. */
+int ti_ingest(ti_ctx* ctx, const ti_stream* streams, int n_streams, int n_batch);
+
+/* Same, but src/dst/mask/count inside `streams` are HOST pointers (pinned for overlap):
+ * host->device copy, kernels and device->host copy are pipelined over `chunk` frame sets at a
+ * time on internal streams; returns after everything has landed in the dst buffers. */
+int ti_ingest_host(ti_ctx* ctx, const ti_stream* streams, int n_streams, int n_batch, int chunk);
+
+/* ---- multi-GPU: one process per GPU ------------------------------------------------------ */
+
+/* NCCL is dlopen()ed on first use.  id: 128 bytes, created on rank 0, shipped by the caller
+ * (torch.distributed object broadcast in our host code). */
+int ti_nccl_unique_id(void* id128);
+int ti_nccl_init(ti_ctx* ctx, const void* id128, int rank, int world);
+/* Gather of per-GPU body-frame clouds to `root` over NVLink: rank r contributes
+ * bytes_per_rank[r] bytes from `local` (DEVICE); on root they land back to back in `gathered`
+ * (DEVICE, sum of bytes_per_rank) in rank order.  bytes_per_rank: HOST array of `world`. */
+int ti_gather_clouds(ti_ctx* ctx, const void* local, void* gathered, const uint64_t* bytes_per_rank,
+                     int root);
+int ti_nccl_barrier(ti_ctx* ctx);
+
+/* Peer-visible cloud buffer: allocated on this GPU, exported as a 64-byte IPC handle, opened
+ * on the other ranks so their back-projection kernels store straight into it over NVLink
+ * (gather fused into the producing kernel). */
+int ti_peer_alloc(ti_ctx* ctx, uint64_t bytes, void** dev_ptr, void* handle64);
+int ti_peer_open(ti_ctx* ctx, const void* handle64, void** dev_ptr);
+int ti_peer_close(ti_ctx* ctx, void* dev_ptr);
+int ti_peer_free(ti_ctx* ctx, void* dev_ptr);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* THORINGEST_H_ */

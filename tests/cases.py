@@ -1,0 +1,117 @@
+"""Parity cases shared by the CPU-emulation tests and the ``-m gpu`` tests.
+
+Every case drives the C ABI (through ``IngestContext``) on seeded inputs and compares with the
+oracle (``oracle/``) and/or the committed golden fixtures.  Bars: bit-exact for u8 / masks / counts;
+``|p - p_ref|_inf <= 1e-5 * max(|p_ref|_inf, 1e-3)`` for 3-D points (north_star tolerance).
+"""
+
+from __future__ import annotations
+
+import numpy as np
+
+from oracle import backproject as ob
+from oracle import conventions as conv
+from oracle import convert as oc
+from oracle import rectify as orc
+from thor_slam_b200.camera.synthetic import SyntheticCameraConfig, SyntheticCameraSource, make_depth, make_image
+from thor_slam_b200.ingest import formats as F
+from thor_slam_b200.ingest.context import StreamSpec
+
+POINT_RTOL = 1e-5
+POINT_FLOOR = 1e-3
+
+CONVERSIONS = [("bgr8", "rgb8"), ("bgr8", "mono8"), ("nv12", "mono8"), ("nv12", "rgb8"), ("nv12", "bgr8"), ("mono8", "mono8")]
+RECTIFY_CONVERSIONS = [("mono8", "mono8"), ("nv12", "mono8"), ("bgr8", "rgb8"), ("bgr8", "mono8"), ("nv12", "rgb8")]
+
+
+def oracle_convert(img: np.ndarray, s: str, d: str) -> np.ndarray:
+    if (s, d) == ("nv12", "bgr8"):
+        return oc.nv12_to_bgr_cv(img)
+    if (s, d) == ("mono8", "mono8"):
+        return img
+    return oc.convert(img, s, d)
+
+
+def make_batch(rng: np.random.Generator, fmt: str, w: int, h: int, n: int) -> np.ndarray:
+    if n == 0:
+        return np.zeros((0, *F.frame_shape(F.fmt(fmt), w, h)), dtype=np.uint8)
+    return np.stack([make_image(rng, fmt, w, h) for _ in range(n)])
+
+
+def check_convert(be, s: str, d: str, w: int, h: int, n: int = 2, seed: int = 0) -> None:
+    rng = np.random.default_rng(seed)
+    src = make_batch(rng, s, w, h, n)
+    if n and s == "nv12":  # full-range random chroma AND luma, so saturation paths are hit
+        src[0] = rng.integers(0, 256, size=src[0].shape, dtype=np.uint8)
+    dst = be.zeros((n, *F.frame_shape(F.fmt(d), w, h)), np.uint8)
+    be.ctx.convert(be.dev(src), dst, s, d, w, h)
+    got = be.host(dst)
+    for i in range(n):
+        want = oracle_convert(src[i], s, d)
+        assert np.array_equal(got[i], want), f"{s}->{d} {w}x{h} frame {i}: {(got[i] != want).sum()} bytes differ"
+
+
+def stereo_maps(w: int, h: int, seed: int = 3, distortion: str = "rational14"):
+    """(source, [(mapx, mapy) left, right]) from a synthetic stereo calibration via the oracle (cv2)."""
+    s = SyntheticCameraSource(SyntheticCameraConfig(name="oak0", resolution=(w, h), pool=1, seed=seed, distortion=distortion))
+    (il, ir), (el, er) = s.get_intrinsics(), s.get_extrinsics()
+    r1, r2, p1, p2 = orc.stereo_rectify_cv(il.matrix, il.coeffs, ir.matrix, ir.coeffs, (w, h), el.to_4x4_matrix(), er.to_4x4_matrix())
+    maps = [orc.undistort_rectify_map_cv(il.matrix, il.coeffs, r1, p1, (w, h)),
+            orc.undistort_rectify_map_cv(ir.matrix, ir.coeffs, r2, p2, (w, h))]
+    return s, maps
+
+
+def edge_maps(dst_w: int, dst_h: int) -> tuple[np.ndarray, np.ndarray]:
+    """An affine map that leaves the source on every side (border taps, fully-outside pixels)."""
+    yy, xx = np.mgrid[0:dst_h, 0:dst_w].astype(np.float32)
+    return (xx * 1.13 - 13.3 + 0.05 * yy).astype(np.float32), (yy * 1.21 - 14.7 - 0.03 * xx).astype(np.float32)
+
+
+def check_rectify(be, cam: int, mapx, mapy, s: str, d: str, src_w: int, src_h: int, n: int = 2, seed: int = 1) -> None:
+    rng = np.random.default_rng(seed)
+    dst_h, dst_w = mapx.shape
+    be.ctx.upload_rectify_map(cam, mapx, mapy, (src_w, src_h))
+    src = make_batch(rng, s, src_w, src_h, n)
+    if s != "mono8" and n:
+        src[0] = rng.integers(0, 256, size=src[0].shape, dtype=np.uint8)
+    dst = be.zeros((n, *F.frame_shape(F.fmt(d), dst_w, dst_h)), np.uint8)
+    be.ctx.rectify(cam, be.dev(src), dst, s, d)
+    got = be.host(dst)
+    for i in range(n):
+        want = orc.remap_cv(np.ascontiguousarray(oracle_convert(src[i], s, d)), mapx, mapy)
+        assert np.array_equal(got[i], want), f"rectify {s}->{d} frame {i}: {(got[i] != want).sum()} bytes differ"
+    mask = be.zeros((dst_h, dst_w), np.uint8)
+    be.ctx.get_valid_mask(cam, mask)
+    assert np.array_equal(be.host(mask), orc.valid_mask(mapx, mapy, (src_w, src_h)))
+
+
+def random_pose(rng: np.random.Generator) -> np.ndarray:
+    from scipy.spatial.transform import Rotation
+
+    t = np.eye(4)
+    t[:3, :3] = Rotation.from_rotvec(rng.uniform(-1.5, 1.5, 3)).as_matrix()
+    t[:3, 3] = rng.uniform(-0.5, 0.5, 3)
+    return t
+
+
+def check_backproject(be, cam: int, w: int, h: int, n: int = 2, seed: int = 2, rig_frame: str = "rdf", depth=None) -> None:
+    rng = np.random.default_rng(seed)
+    s = SyntheticCameraSource(SyntheticCameraConfig(name="oak0", resolution=(w, h), pool=1, seed=seed))
+    intr, ext = s.get_intrinsics()[0], s.get_extrinsics()[0]
+    m = conv.body_T_camera(random_pose(rng), ext.to_4x4_matrix(), rig_frame)
+    be.ctx.upload_projection(cam, intr.matrix, m, (w, h))
+    if depth is None:
+        depth = np.stack([make_depth(rng, w, h) for _ in range(n)]) if n else np.zeros((0, h, w), np.uint16)
+    n = depth.shape[0]
+    xyz = be.zeros((n, h, w, 3), np.float32)
+    mask = be.zeros((n, h, w), np.uint8)
+    count = be.dev(np.full(max(n, 1), 0xDEADBEEF, dtype=np.uint32))  # must be overwritten, not accumulated
+    be.ctx.backproject(cam, be.dev(depth), xyz, mask, count)
+    gx, gm, gc = be.host(xyz), be.host(mask), be.host(count)
+    for i in range(n):
+        pts, msk, cnt = ob.backproject(depth[i], intr.matrix, m)
+        ok, worst = ob.points_close(gx[i], pts, POINT_RTOL, POINT_FLOOR)
+        assert ok, f"points off by {worst:.3e} (> {POINT_RTOL})"
+        assert np.array_equal(gm[i], msk)
+        assert int(gc[i]) == cnt
+        assert not np.any(gx[i][msk == 0]), "invalid pixels must be written as (0,0,0)"

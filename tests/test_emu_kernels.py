@@ -1,0 +1,74 @@
+"""Kernel sources run thread-by-thread on the CPU (tests/emu) against the oracle - small sizes.
+
+This is a pre-flight for the ``-m gpu`` parity tests: same cases, same C ABI, same kernel source
+text, no GPU.  It is test infrastructure; the product library is the nvcc build only.
+"""
+
+from __future__ import annotations
+
+import numpy as np
+import pytest
+
+from tests import cases
+from thor_slam_b200.ingest import formats as F
+from thor_slam_b200.ingest.context import StreamSpec
+
+
+@pytest.mark.parametrize("s,d", cases.CONVERSIONS)
+@pytest.mark.parametrize("w,h", [(64, 32), (50, 22)])  # vector path / scalar path
+def test_convert(emu_backend, s, d, w, h):
+    cases.check_convert(emu_backend, s, d, w, h, n=2)
+
+
+def test_convert_empty_batch(emu_backend):
+    cases.check_convert(emu_backend, "bgr8", "rgb8", 64, 32, n=0)
+
+
+@pytest.mark.parametrize("s,d", cases.RECTIFY_CONVERSIONS)
+def test_rectify_stereo_maps(emu_backend, s, d):
+    _, maps = cases.stereo_maps(192, 96)
+    cases.check_rectify(emu_backend, 0, *maps[0], s, d, 192, 96)
+
+
+@pytest.mark.parametrize("s,d", cases.RECTIFY_CONVERSIONS)
+def test_rectify_border(emu_backend, s, d):
+    mx, my = cases.edge_maps(160, 64)
+    cases.check_rectify(emu_backend, 1, mx, my, s, d, 160, 64)
+
+
+def test_rectify_resize_and_ragged(emu_backend):
+    yy, xx = np.mgrid[0:51, 0:99].astype(np.float32)
+    cases.check_rectify(emu_backend, 2, xx * 1.1 + 0.3, yy * 1.05 + 0.7, "mono8", "mono8", 110, 60)  # direct kernel
+    yy, xx = np.mgrid[0:72, 0:200].astype(np.float32)
+    cases.check_rectify(emu_backend, 3, xx * 0.75 + 3.25, yy * 0.8 + 0.5, "mono8", "mono8", 160, 64)  # tiled, ragged tiles
+
+
+def test_rectify_all_outside(emu_backend):
+    mx = np.full((32, 128), -50.0, np.float32)
+    cases.check_rectify(emu_backend, 4, mx, mx.copy(), "mono8", "mono8", 128, 32)
+
+
+@pytest.mark.parametrize("w,h", [(64, 40), (50, 22)])
+@pytest.mark.parametrize("frame", ["rdf", "flu"])
+def test_backproject(emu_backend, w, h, frame):
+    cases.check_backproject(emu_backend, 5, w, h, rig_frame=frame)
+
+
+def test_backproject_extremes(emu_backend):
+    depth = np.zeros((3, 16, 64), np.uint16)
+    depth[1] = 65535
+    depth[2, ::2, 1::3] = 1
+    cases.check_backproject(emu_backend, 6, 64, 16, depth=depth)
+
+
+def test_errors(emu_backend):
+    ctx = emu_backend.ctx
+    a = np.zeros((1, 8, 16), np.uint8)
+    with pytest.raises(RuntimeError):  # TI_ESTATE: slot never uploaded
+        ctx.rectify(40, a, a.copy(), "mono8", "mono8")
+    with pytest.raises(ValueError):  # TI_EINVAL: unsupported conversion
+        ctx.convert(a, a.copy(), "mono8", "rgb8", 16, 8)
+    with pytest.raises(ValueError):
+        ctx.upload_rectify_map(99, np.zeros((4, 4), np.float32), np.zeros((4, 4), np.float32), (4, 4))
+    with pytest.raises(ValueError):
+        ctx.convert(np.zeros((1, 9, 6), np.uint8), np.zeros((1, 6, 6, 3), np.uint8), "nv12", "rgb8", 5, 6)  # odd NV12

@@ -1,0 +1,212 @@
+"""``-m gpu``: parity of the CUDA path (through the C ABI) against the oracle and golden fixtures."""
+
+from __future__ import annotations
+
+import numpy as np
+import pytest
+
+from oracle import backproject as ob
+from oracle import conventions as conv
+from oracle import rectify as orc
+from tests import cases
+from tests.conftest import GOLDEN
+from thor_slam_b200.camera.synthetic import make_depth
+from thor_slam_b200.ingest import formats as F
+from thor_slam_b200.ingest.context import StreamSpec
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("s,d", cases.CONVERSIONS)
+@pytest.mark.parametrize("w,h", [(64, 32), (50, 22), (1280, 800)])
+def test_convert(gpu_backend, s, d, w, h):
+    cases.check_convert(gpu_backend, s, d, w, h, n=3)
+
+
+def test_convert_1080p_bgr(gpu_backend):
+    cases.check_convert(gpu_backend, "bgr8", "rgb8", 1920, 1080, n=2)
+
+
+def test_convert_empty_batch(gpu_backend):
+    cases.check_convert(gpu_backend, "bgr8", "rgb8", 64, 32, n=0)
+
+
+def test_convert_golden(gpu_backend):
+    g = np.load(GOLDEN / "cv_arith.npz")
+    be = gpu_backend
+    for src_key, s, d, want_key in [("bgr", "bgr8", "rgb8", "bgr2rgb"), ("bgr", "bgr8", "mono8", "bgr2gray"),
+                                    ("nv12", "nv12", "rgb8", "nv122rgb"), ("nv12", "nv12", "bgr8", "nv122bgr"),
+                                    ("nv12", "nv12", "mono8", "nv122gray"), ("nv12lim", "nv12", "rgb8", "nv12lim2rgb")]:
+        src = g[src_key][None]
+        want = g[want_key]
+        dst = be.zeros((1, *want.shape), np.uint8)
+        be.ctx.convert(be.dev(src), dst, s, d, 48, 32)
+        assert np.array_equal(be.host(dst)[0], want), want_key
+
+
+@pytest.mark.parametrize("s,d", cases.RECTIFY_CONVERSIONS)
+def test_rectify_stereo_maps_small(gpu_backend, s, d):
+    _, maps = cases.stereo_maps(192, 96)
+    cases.check_rectify(gpu_backend, 0, *maps[1], s, d, 192, 96)
+
+
+@pytest.mark.parametrize("s,d", cases.RECTIFY_CONVERSIONS)
+def test_rectify_border(gpu_backend, s, d):
+    mx, my = cases.edge_maps(160, 64)
+    cases.check_rectify(gpu_backend, 1, mx, my, s, d, 160, 64)
+
+
+@pytest.mark.parametrize("distortion", ["rational14", "plumb_bob5", "fisheye4", "none"])
+def test_rectify_full_size_mono(gpu_backend, distortion):
+    """BASELINE config 2 stream shape, every distortion model the reference's CameraInfo rule knows."""
+    _, maps = cases.stereo_maps(1280, 800, seed=11, distortion=distortion)
+    for cam, (mx, my) in enumerate(maps):
+        cases.check_rectify(gpu_backend, 8 + cam, mx, my, "mono8", "mono8", 1280, 800, n=3)
+
+
+def test_rectify_full_size_colour(gpu_backend):
+    _, maps = cases.stereo_maps(1920, 1200, seed=5)
+    cases.check_rectify(gpu_backend, 10, *maps[0], "bgr8", "rgb8", 1920, 1200, n=2)
+    cases.check_rectify(gpu_backend, 10, *maps[0], "bgr8", "mono8", 1920, 1200, n=1)
+    cases.check_rectify(gpu_backend, 10, *maps[0], "nv12", "rgb8", 1920, 1200, n=1)
+
+
+def test_rectify_resize_ragged_outside(gpu_backend):
+    yy, xx = np.mgrid[0:51, 0:99].astype(np.float32)
+    cases.check_rectify(gpu_backend, 2, xx * 1.1 + 0.3, yy * 1.05 + 0.7, "mono8", "mono8", 110, 60)
+    yy, xx = np.mgrid[0:400, 0:640].astype(np.float32)
+    cases.check_rectify(gpu_backend, 3, xx * 2.0 + 0.25, yy * 2.0 + 0.75, "mono8", "mono8", 1280, 800)  # 2x downscale (slam_config.yaml:7)
+    mx = np.full((32, 128), -50.0, np.float32)
+    cases.check_rectify(gpu_backend, 4, mx, mx.copy(), "mono8", "mono8", 128, 32)
+
+
+def test_rectify_golden(gpu_backend):
+    g = np.load(GOLDEN / "cv_arith.npz")
+    be = gpu_backend
+    for side in "lr":
+        be.ctx.upload_rectify_map(20, g[f"mapx_{side}"], g[f"mapy_{side}"], (160, 100))
+        dst = be.zeros((1, 100, 160), np.uint8)
+        be.ctx.rectify(20, be.dev(g[f"img_{side}"][None]), dst, "mono8", "mono8")
+        assert np.array_equal(be.host(dst)[0], g[f"rect_{side}"])
+    be.ctx.upload_rectify_map(21, g["edge_mapx"], g["edge_mapy"], (48, 32))
+    dst = be.zeros((1, 32, 48), np.uint8)
+    be.ctx.rectify(21, be.dev(g["bgr2gray"][None]), dst, "mono8", "mono8")
+    assert np.array_equal(be.host(dst)[0], g["edge_rect_u8"])
+    dst3 = be.zeros((1, 32, 48, 3), np.uint8)
+    be.ctx.rectify(21, be.dev(g["bgr"][None]), dst3, "bgr8", "rgb8")
+    assert np.array_equal(be.host(dst3)[0], g["edge_rect_c3"][..., ::-1])
+
+
+def test_rectify_identity_is_copy(gpu_backend):
+    """Size-independent property: the identity map reproduces the input bit for bit."""
+    yy, xx = np.mgrid[0:800, 0:1280].astype(np.float32)
+    be = gpu_backend
+    be.ctx.upload_rectify_map(22, xx, yy, (1280, 800))
+    rng = np.random.default_rng(4)
+    src = rng.integers(0, 256, size=(4, 800, 1280), dtype=np.uint8)
+    dst = be.zeros(src.shape, np.uint8)
+    be.ctx.rectify(22, be.dev(src), dst, "mono8", "mono8")
+    assert np.array_equal(be.host(dst), src)
+
+
+@pytest.mark.parametrize("w,h", [(64, 40), (50, 22), (1280, 800)])
+@pytest.mark.parametrize("frame", ["rdf", "flu"])
+def test_backproject(gpu_backend, w, h, frame):
+    cases.check_backproject(gpu_backend, 30, w, h, n=2, rig_frame=frame)
+
+
+def test_backproject_extremes(gpu_backend):
+    depth = np.zeros((3, 16, 64), np.uint16)
+    depth[1] = 65535
+    depth[2, ::2, 1::3] = 1
+    cases.check_backproject(gpu_backend, 31, 64, 16, depth=depth)
+
+
+def test_backproject_golden_depth_and_readme_vector(gpu_backend):
+    """Pinned inputs: golden depth frame; README known answer rdf_to_flu @ [1,0,0,1] = [0,-1,0,1]."""
+    g = np.load(GOLDEN / "cv_arith.npz")
+    be = gpu_backend
+    # K = identity-ish so that pixel (u=1, v=0) at d = 1000 mm back-projects to RDF (1, 0, 1)
+    k = np.array([[1.0, 0, 0], [0, 1.0, 0], [0, 0, 1]])
+    be.ctx.upload_projection(32, k, conv.RDF_TO_FLU, (8, 1))
+    depth = np.zeros((1, 1, 8), np.uint16)
+    depth[0, 0, 1] = 1000
+    xyz = be.zeros((1, 1, 8, 3), np.float32)
+    be.ctx.backproject(32, be.dev(depth), xyz)
+    np.testing.assert_allclose(be.host(xyz)[0, 0, 1], [1.0, -1.0, 0.0], atol=1e-6)  # (x,y,z)_rdf=(1,0,1) -> flu (1,-1,0)
+    cases.check_backproject(gpu_backend, 33, 48, 32, depth=g["depth"][None])
+
+
+def test_ingest_fused_matches_single_calls(gpu_backend):
+    be = gpu_backend
+    w, h, n = 640, 400, 3
+    rng = np.random.default_rng(9)
+    s, maps = cases.stereo_maps(w, h, seed=9)
+    be.ctx.upload_rectify_map(40, *maps[0], (w, h))
+    be.ctx.upload_rectify_map(41, *maps[1], (w, h))
+    intr = s.get_intrinsics()[0]
+    m = conv.body_T_camera(cases.random_pose(rng), s.get_extrinsics()[0].to_4x4_matrix(), "rdf")
+    be.ctx.upload_projection(40, intr.matrix, m, (w, h))
+    left = cases.make_batch(rng, "mono8", w, h, n)
+    right = cases.make_batch(rng, "nv12", w, h, n)
+    bgr = cases.make_batch(rng, "bgr8", w, h, n)
+    depth = np.stack([make_depth(rng, w, h) for _ in range(n)])
+    o_l, o_r = be.zeros((n, h, w), np.uint8), be.zeros((n, h, w), np.uint8)
+    o_rgb = be.zeros((n, h, w, 3), np.uint8)
+    xyz, mask, count = be.zeros((n, h, w, 3), np.float32), be.zeros((n, h, w), np.uint8), be.zeros((n,), np.uint32)
+    be.ctx.ingest([
+        StreamSpec(F.KIND_RECTIFY, be.dev(left), o_l, F.MONO8, F.MONO8, camera=40),
+        StreamSpec(F.KIND_RECTIFY, be.dev(right), o_r, F.NV12, F.MONO8, camera=41),
+        StreamSpec(F.KIND_CONVERT, be.dev(bgr), o_rgb, F.BGR8, F.RGB8, width=w, height=h),
+        StreamSpec(F.KIND_BACKPROJECT, be.dev(depth), xyz, F.DEPTH16, F.XYZ32F, camera=40, mask=mask, count=count),
+    ])
+    gl, gr, grgb, gx, gm, gc = (be.host(x) for x in (o_l, o_r, o_rgb, xyz, mask, count))
+    for i in range(n):
+        assert np.array_equal(gl[i], orc.remap_cv(left[i], *maps[0]))
+        assert np.array_equal(gr[i], orc.remap_cv(np.ascontiguousarray(right[i, :h]), *maps[1]))
+        assert np.array_equal(grgb[i], bgr[i, ..., ::-1])
+        pts, msk, cnt = ob.backproject(depth[i], intr.matrix, m)
+        assert ob.points_close(gx[i], pts)[0] and np.array_equal(gm[i], msk) and int(gc[i]) == cnt
+
+
+def test_ingest_host_pipeline(gpu_backend):
+    """Host buffers in, host buffers out, chunked H2D / kernels / D2H; ragged last chunk."""
+    import torch
+
+    be = gpu_backend
+    w, h, n = 640, 400, 7
+    rng = np.random.default_rng(10)
+    s, maps = cases.stereo_maps(w, h, seed=10)
+    be.ctx.upload_rectify_map(42, *maps[0], (w, h))
+    intr = s.get_intrinsics()[0]
+    m = conv.body_T_camera(None, s.get_extrinsics()[0].to_4x4_matrix(), "rdf")
+    be.ctx.upload_projection(42, intr.matrix, m, (w, h))
+    left = torch.from_numpy(cases.make_batch(rng, "mono8", w, h, n)).pin_memory()
+    depth_np = np.stack([make_depth(rng, w, h) for _ in range(n)])
+    depth = torch.from_numpy(depth_np.view(np.int16)).pin_memory()
+    o_l = torch.zeros((n, h, w), dtype=torch.uint8).pin_memory()
+    xyz = torch.zeros((n, h, w, 3), dtype=torch.float32).pin_memory()
+    mask = torch.zeros((n, h, w), dtype=torch.uint8).pin_memory()
+    count = torch.zeros((n,), dtype=torch.int32).pin_memory()
+    be.ctx.ingest_host([
+        StreamSpec(F.KIND_RECTIFY, left, o_l, F.MONO8, F.MONO8, camera=42),
+        StreamSpec(F.KIND_BACKPROJECT, depth, xyz, F.DEPTH16, F.XYZ32F, camera=42, mask=mask, count=count),
+    ], chunk=3)
+    for i in range(n):
+        assert np.array_equal(o_l[i].numpy(), orc.remap_cv(left[i].numpy(), *maps[0]))
+        pts, msk, cnt = ob.backproject(depth_np[i], intr.matrix, m)
+        assert ob.points_close(xyz[i].numpy(), pts)[0]
+        assert np.array_equal(mask[i].numpy(), msk) and int(count[i]) == cnt
+
+
+def test_errors(gpu_backend):
+    import torch
+
+    ctx = gpu_backend.ctx
+    a = torch.zeros((1, 8, 16), dtype=torch.uint8, device="cuda")
+    with pytest.raises(RuntimeError):
+        ctx.rectify(60, a, a.clone(), "mono8", "mono8")  # slot never uploaded
+    with pytest.raises(ValueError):
+        ctx.convert(a, a.clone(), "mono8", "rgb8", 16, 8)  # unsupported conversion
+    with pytest.raises(ValueError):
+        ctx.convert(a.cpu(), a.clone(), "mono8", "mono8", 16, 8)  # host tensor on the device API

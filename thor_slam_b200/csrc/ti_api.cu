@@ -1,0 +1,422 @@
+// C ABI of libthoringest.so: context, calibration upload, per-frame entry points, host pipeline,
+// NCCL gather and peer buffers.  See include/thoringest.h for the contract.
+#include <dlfcn.h>
+#include <math.h>
+#include <stdarg.h>
+#include <string.h>
+
+#include <mutex>
+
+#include "ti_common.cuh"
+
+namespace ti {
+
+static std::mutex g_err_mu;
+static std::string g_err;
+
+void set_global_error(const char* msg) {
+    std::lock_guard<std::mutex> lk(g_err_mu);
+    g_err = msg;
+}
+
+int fail(ti_ctx* ctx, int code, const char* fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (ctx) ctx->err = buf; else set_global_error(buf);
+    return code;
+}
+
+static void free_camera(CameraSlot& c) {
+    if (c.d_lut) cudaFree(c.d_lut);
+    if (c.d_boxes) cudaFree(c.d_boxes);
+    if (c.d_valid) cudaFree(c.d_valid);
+    c = CameraSlot{};
+}
+
+// OpenCV's cvRound on float*32: round-half-to-even (SSE cvtss2si under the default MXCSR mode)
+static inline int round_half_even(float v) { return (int)lrintf(v); }
+
+}  // namespace ti
+
+using namespace ti;
+
+extern "C" {
+
+int ti_abi_version(void) { return TI_ABI_VERSION; }
+
+int ti_create(int device, ti_ctx** out) {
+    if (!out) return fail(nullptr, TI_EINVAL, "ti_create: out is NULL");
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0)
+        return fail(nullptr, TI_ECUDA, "ti_create: no CUDA device (%s) - this library has no CPU fallback",
+                    e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+    if (device < 0 || device >= n) return fail(nullptr, TI_EINVAL, "ti_create: device %d out of range [0,%d)", device, n);
+    e = cudaSetDevice(device);
+    if (e != cudaSuccess) return fail(nullptr, TI_ECUDA, "cudaSetDevice(%d): %s", device, cudaGetErrorString(e));
+    cudaDeviceProp prop;
+    e = cudaGetDeviceProperties(&prop, device);
+    if (e != cudaSuccess) return fail(nullptr, TI_ECUDA, "cudaGetDeviceProperties: %s", cudaGetErrorString(e));
+    if (prop.major != 10)
+        return fail(nullptr, TI_ECUDA, "ti_create: device %d is sm_%d%d; this library is built for sm_100a (B200) only",
+                    device, prop.major, prop.minor);
+    ti_ctx* ctx = new (std::nothrow) ti_ctx();
+    if (!ctx) return fail(nullptr, TI_ENOMEM, "ti_create: out of host memory");
+    ctx->device = device;
+    ctx->sm_count = prop.multiProcessorCount;
+    *out = ctx;
+    return TI_OK;
+}
+
+int ti_destroy(ti_ctx* ctx) {
+    if (!ctx) return TI_OK;
+    cudaSetDevice(ctx->device);
+    cudaDeviceSynchronize();
+    for (auto& c : ctx->cams) free_camera(c);
+    for (auto& h : ctx->hslot) {
+        for (void* p : h.d_src) if (p) cudaFree(p);
+        for (void* p : h.d_dst) if (p) cudaFree(p);
+        for (void* p : h.d_mask) if (p) cudaFree(p);
+        for (uint32_t* p : h.d_count) if (p) cudaFree(p);
+        if (h.h2d_done) cudaEventDestroy(h.h2d_done);
+        if (h.exec_done) cudaEventDestroy(h.exec_done);
+        if (h.d2h_done) cudaEventDestroy(h.d2h_done);
+    }
+    if (ctx->s_h2d) cudaStreamDestroy(ctx->s_h2d);
+    if (ctx->s_d2h) cudaStreamDestroy(ctx->s_d2h);
+    if (ctx->s_exec) cudaStreamDestroy(ctx->s_exec);
+    ti_nccl_teardown(ctx);
+    delete ctx;
+    return TI_OK;
+}
+
+const char* ti_last_error(const ti_ctx* ctx) {
+    if (ctx) return ctx->err.c_str();
+    std::lock_guard<std::mutex> lk(g_err_mu);
+    static thread_local std::string copy;
+    copy = g_err;
+    return copy.c_str();
+}
+
+int ti_set_stream(ti_ctx* ctx, void* cuda_stream) {
+    if (!ctx) return TI_EINVAL;
+    ctx->stream = (cudaStream_t)cuda_stream;
+    return TI_OK;
+}
+
+int ti_sync(ti_ctx* ctx) {
+    if (!ctx) return TI_EINVAL;
+    TI_CUDA(ctx, cudaSetDevice(ctx->device));
+    TI_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return TI_OK;
+}
+
+uint64_t ti_launch_count(const ti_ctx* ctx) { return ctx ? ctx->launches : 0; }
+int ti_device_sm_count(const ti_ctx* ctx) { return ctx ? ctx->sm_count : 0; }
+
+// ---- calibration ------------------------------------------------------------------------------
+
+int ti_upload_rectify_map(ti_ctx* ctx, int camera, int dst_w, int dst_h, int src_w, int src_h, const float* mapx,
+                          const float* mapy) {
+    if (!ctx) return TI_EINVAL;
+    if (camera < 0 || camera >= TI_MAX_CAMERAS) return fail(ctx, TI_EINVAL, "camera slot %d out of range", camera);
+    if (!mapx || !mapy) return fail(ctx, TI_EINVAL, "ti_upload_rectify_map: null map");
+    if (dst_w <= 0 || dst_h <= 0 || src_w <= 0 || src_h <= 0 || src_w > TI_MAX_DIM || src_h > TI_MAX_DIM)
+        return fail(ctx, TI_EINVAL, "ti_upload_rectify_map: sizes must be in [1,%d] (dst %dx%d, src %dx%d)", TI_MAX_DIM,
+                    dst_w, dst_h, src_w, src_h);
+    TI_CUDA(ctx, cudaSetDevice(ctx->device));
+    CameraSlot& C = ctx->cams[camera];
+    const bool keep_proj = C.has_proj;
+    CameraSlot saved = C;
+    if (C.d_lut) cudaFree(C.d_lut);
+    if (C.d_boxes) cudaFree(C.d_boxes);
+    if (C.d_valid) cudaFree(C.d_valid);
+    C.d_lut = nullptr; C.d_boxes = nullptr; C.d_valid = nullptr; C.has_map = false;
+    (void)keep_proj; (void)saved;
+
+    const int tiles_x = (dst_w + RT_W - 1) / RT_W, tiles_y = (dst_h + RT_H - 1) / RT_H;
+    const int lut_pitch = tiles_x * RT_W, lut_rows = tiles_y * RT_H;
+    std::vector<uint32_t> lut((size_t)lut_pitch * lut_rows, LUT_OUTSIDE);
+    std::vector<uint8_t> valid((size_t)dst_w * dst_h, 0);
+    std::vector<TileBox> boxes((size_t)tiles_x * tiles_y);
+    for (auto& b : boxes) { b.x0 = 32767; b.y0 = 32767; b.x1 = -32768; b.y1 = -32768; }
+
+    for (int v = 0; v < dst_h; ++v) {
+        for (int u = 0; u < dst_w; ++u) {
+            const float mx = mapx[(size_t)v * dst_w + u], my = mapy[(size_t)v * dst_w + u];
+            if (!(fabsf(mx) < 1e6f) || !(fabsf(my) < 1e6f)) continue;  // NaN / far away: no tap inside
+            const int ix = round_half_even(mx * 32.0f), iy = round_half_even(my * 32.0f);
+            const int x0 = ix >> 5, y0 = iy >> 5;  // arithmetic shift = floor
+            if (x0 < -1 || x0 > src_w - 1 || y0 < -1 || y0 > src_h - 1) continue;  // all four taps outside
+            lut[(size_t)v * lut_pitch + u] = (uint32_t)(x0 + 1) | ((uint32_t)(y0 + 1) << LUT_COORD_BITS) |
+                                             ((uint32_t)(ix & 31) << 22) | ((uint32_t)(iy & 31) << 27);
+            valid[(size_t)v * dst_w + u] = (x0 >= 0 && x0 + 1 <= src_w - 1 && y0 >= 0 && y0 + 1 <= src_h - 1) ? 1 : 0;
+            TileBox& b = boxes[(size_t)(v / RT_H) * tiles_x + (u / RT_W)];
+            b.x0 = std::min<int16_t>(b.x0, (int16_t)x0); b.y0 = std::min<int16_t>(b.y0, (int16_t)y0);
+            b.x1 = std::max<int16_t>(b.x1, (int16_t)(x0 + 2)); b.y1 = std::max<int16_t>(b.y1, (int16_t)(y0 + 2));
+        }
+    }
+    size_t smem1 = 0, smem3 = 0;
+    for (auto& b : boxes) {
+        if (b.x1 <= b.x0) { b.x0 = b.y0 = b.x1 = b.y1 = 0; continue; }
+        const int rows = b.y1 - b.y0;
+        const int p1 = ((b.x1 + 15) & ~15) - (b.x0 & ~15);
+        const int p3 = ((b.x1 * 3 + 15) & ~15) - ((b.x0 * 3) & ~15);
+        smem1 = std::max(smem1, (size_t)rows * p1);
+        smem3 = std::max(smem3, (size_t)rows * p3);
+    }
+    TI_CUDA(ctx, cudaMalloc(&C.d_lut, lut.size() * sizeof(uint32_t)));
+    TI_CUDA(ctx, cudaMalloc(&C.d_boxes, boxes.size() * sizeof(TileBox)));
+    TI_CUDA(ctx, cudaMalloc(&C.d_valid, valid.size()));
+    TI_CUDA(ctx, cudaMemcpy(C.d_lut, lut.data(), lut.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    TI_CUDA(ctx, cudaMemcpy(C.d_boxes, boxes.data(), boxes.size() * sizeof(TileBox), cudaMemcpyHostToDevice));
+    TI_CUDA(ctx, cudaMemcpy(C.d_valid, valid.data(), valid.size(), cudaMemcpyHostToDevice));
+    C.dst_w = dst_w; C.dst_h = dst_h; C.src_w = src_w; C.src_h = src_h;
+    C.tiles_x = tiles_x; C.tiles_y = tiles_y;
+    C.tile_smem[0] = smem1; C.tile_smem[1] = smem3;
+    C.has_map = true;
+    return TI_OK;
+}
+
+int ti_upload_projection(ti_ctx* ctx, int camera, int width, int height, const double k[4], const double body_T_cam[12]) {
+    if (!ctx) return TI_EINVAL;
+    if (camera < 0 || camera >= TI_MAX_CAMERAS) return fail(ctx, TI_EINVAL, "camera slot %d out of range", camera);
+    if (!k || !body_T_cam) return fail(ctx, TI_EINVAL, "ti_upload_projection: null argument");
+    if (width <= 0 || height <= 0 || width > 16384 || height > 16384)
+        return fail(ctx, TI_EINVAL, "ti_upload_projection: bad size %dx%d", width, height);
+    if (!(k[0] != 0.0) || !(k[1] != 0.0)) return fail(ctx, TI_EINVAL, "ti_upload_projection: fx and fy must be non-zero");
+    CameraSlot& C = ctx->cams[camera];
+    const double inv[3] = {1.0 / k[0], 1.0 / k[1], 1.0};
+    for (int r = 0; r < 3; ++r) {
+        for (int c = 0; c < 3; ++c) C.ray[3 * r + c] = (float)(body_T_cam[4 * r + c] * inv[c]);
+        C.trans[r] = (float)body_T_cam[4 * r + 3];
+    }
+    C.cx = (float)k[2]; C.cy = (float)k[3];
+    C.proj_w = width; C.proj_h = height;
+    C.has_proj = true;
+    return TI_OK;
+}
+
+int ti_get_valid_mask(ti_ctx* ctx, int camera, uint8_t* dst) {
+    if (!ctx) return TI_EINVAL;
+    if (camera < 0 || camera >= TI_MAX_CAMERAS || !ctx->cams[camera].has_map)
+        return fail(ctx, TI_ESTATE, "camera slot %d has no remap LUT", camera);
+    if (!dst) return fail(ctx, TI_EINVAL, "ti_get_valid_mask: null dst");
+    const CameraSlot& C = ctx->cams[camera];
+    TI_CUDA(ctx, cudaMemcpyAsync(dst, C.d_valid, (size_t)C.dst_w * C.dst_h, cudaMemcpyDeviceToDevice, ctx->stream));
+    return TI_OK;
+}
+
+// ---- per-frame entry points --------------------------------------------------------------------
+
+int ti_convert(ti_ctx* ctx, int src_format, int dst_format, const void* src, void* dst, int width, int height, int n_batch,
+               uint64_t src_frame_stride, uint64_t dst_frame_stride) {
+    if (!ctx) return TI_EINVAL;
+    if (n_batch < 0) return fail(ctx, TI_EINVAL, "n_batch must be >= 0");
+    TI_CUDA(ctx, cudaSetDevice(ctx->device));
+    ConvertJob J{(const uint8_t*)src, (uint8_t*)dst, src_frame_stride, dst_frame_stride, width, height, src_format, dst_format};
+    return launch_convert(ctx, &J, 1, n_batch);
+}
+
+int ti_rectify(ti_ctx* ctx, int camera, int src_format, int dst_format, const void* src, void* dst, int n_batch,
+               uint64_t src_frame_stride, uint64_t dst_frame_stride) {
+    if (!ctx) return TI_EINVAL;
+    if (n_batch < 0) return fail(ctx, TI_EINVAL, "n_batch must be >= 0");
+    TI_CUDA(ctx, cudaSetDevice(ctx->device));
+    RectifyJob J{(const uint8_t*)src, (uint8_t*)dst, src_frame_stride, dst_frame_stride, camera, src_format, dst_format};
+    return launch_rectify(ctx, &J, 1, n_batch);
+}
+
+int ti_backproject(ti_ctx* ctx, int camera, const uint16_t* depth, float* xyz, uint8_t* mask, uint32_t* count, int n_batch,
+                   uint64_t depth_frame_stride, uint64_t xyz_frame_stride, uint64_t mask_frame_stride) {
+    if (!ctx) return TI_EINVAL;
+    if (n_batch < 0) return fail(ctx, TI_EINVAL, "n_batch must be >= 0");
+    TI_CUDA(ctx, cudaSetDevice(ctx->device));
+    BackprojectJob J{depth, xyz, mask, count, depth_frame_stride, xyz_frame_stride, mask_frame_stride, camera};
+    return launch_backproject(ctx, &J, 1, n_batch);
+}
+
+static int split_streams(ti_ctx* ctx, const ti_stream* streams, int n_streams, std::vector<ConvertJob>& cv,
+                         std::vector<RectifyJob>& rc, std::vector<BackprojectJob>& bp) {
+    if (n_streams < 0 || (n_streams > 0 && !streams)) return fail(ctx, TI_EINVAL, "ti_ingest: bad stream array");
+    for (int i = 0; i < n_streams; ++i) {
+        const ti_stream& S = streams[i];
+        switch (S.kind) {
+            case TI_KIND_CONVERT:
+                cv.push_back({(const uint8_t*)S.src, (uint8_t*)S.dst, S.src_frame_stride, S.dst_frame_stride, S.width, S.height,
+                              S.src_format, S.dst_format});
+                break;
+            case TI_KIND_RECTIFY:
+                rc.push_back({(const uint8_t*)S.src, (uint8_t*)S.dst, S.src_frame_stride, S.dst_frame_stride, S.camera,
+                              S.src_format, S.dst_format});
+                break;
+            case TI_KIND_BACKPROJECT:
+                if (S.src_format != TI_FMT_DEPTH16 || S.dst_format != TI_FMT_XYZ32F)
+                    return fail(ctx, TI_EINVAL, "stream %d: BACKPROJECT needs DEPTH16 -> XYZ32F", i);
+                bp.push_back({(const uint16_t*)S.src, (float*)S.dst, (uint8_t*)S.mask, S.count, S.src_frame_stride,
+                              S.dst_frame_stride, S.mask_frame_stride, S.camera});
+                break;
+            default: return fail(ctx, TI_EINVAL, "stream %d: unknown kind %d", i, S.kind);
+        }
+    }
+    return TI_OK;
+}
+
+int ti_ingest(ti_ctx* ctx, const ti_stream* streams, int n_streams, int n_batch) {
+    if (!ctx) return TI_EINVAL;
+    if (n_batch < 0) return fail(ctx, TI_EINVAL, "n_batch must be >= 0");
+    TI_CUDA(ctx, cudaSetDevice(ctx->device));
+    std::vector<ConvertJob> cv; std::vector<RectifyJob> rc; std::vector<BackprojectJob> bp;
+    int r = split_streams(ctx, streams, n_streams, cv, rc, bp);
+    if (r != TI_OK) return r;
+    if ((r = launch_rectify(ctx, rc.data(), (int)rc.size(), n_batch)) != TI_OK) return r;
+    if ((r = launch_backproject(ctx, bp.data(), (int)bp.size(), n_batch)) != TI_OK) return r;
+    for (size_t i = 0; i < cv.size(); i += TI_MAX_STREAMS) {
+        const int n = (int)std::min<size_t>(TI_MAX_STREAMS, cv.size() - i);
+        if ((r = launch_convert(ctx, cv.data() + i, n, n_batch)) != TI_OK) return r;
+    }
+    return TI_OK;
+}
+
+// ---- host-buffer pipeline ----------------------------------------------------------------------
+// Frames arrive in (pinned) host memory; per chunk of `chunk` frame sets: H2D on one stream,
+// kernels on a second, D2H on a third, two chunk slots in flight so the three overlap.
+
+static uint64_t stream_src_bytes(const ti_ctx* ctx, const ti_stream& S) {
+    if (S.kind == TI_KIND_RECTIFY) { const CameraSlot& C = ctx->cams[S.camera]; return frame_bytes(S.src_format, C.src_w, C.src_h); }
+    if (S.kind == TI_KIND_BACKPROJECT) { const CameraSlot& C = ctx->cams[S.camera]; return frame_bytes(TI_FMT_DEPTH16, C.proj_w, C.proj_h); }
+    return frame_bytes(S.src_format, S.width, S.height);
+}
+static uint64_t stream_dst_bytes(const ti_ctx* ctx, const ti_stream& S) {
+    if (S.kind == TI_KIND_RECTIFY) { const CameraSlot& C = ctx->cams[S.camera]; return frame_bytes(S.dst_format, C.dst_w, C.dst_h); }
+    if (S.kind == TI_KIND_BACKPROJECT) { const CameraSlot& C = ctx->cams[S.camera]; return frame_bytes(TI_FMT_XYZ32F, C.proj_w, C.proj_h); }
+    return frame_bytes(S.dst_format, S.width, S.height);
+}
+static uint64_t stream_mask_bytes(const ti_ctx* ctx, const ti_stream& S) {
+    if (S.kind != TI_KIND_BACKPROJECT || !S.mask) return 0;
+    const CameraSlot& C = ctx->cams[S.camera];
+    return (uint64_t)C.proj_w * C.proj_h;
+}
+
+static int ensure_cap(ti_ctx* ctx, void** p, size_t* cap, size_t need) {
+    if (*cap >= need) return TI_OK;
+    if (*p) cudaFree(*p);
+    *p = nullptr; *cap = 0;
+    if (need == 0) return TI_OK;
+    TI_CUDA(ctx, cudaMalloc(p, need));
+    *cap = need;
+    return TI_OK;
+}
+
+int ti_ingest_host(ti_ctx* ctx, const ti_stream* streams, int n_streams, int n_batch, int chunk) {
+    if (!ctx) return TI_EINVAL;
+    if (n_batch < 0 || n_streams < 0 || (n_streams && !streams)) return fail(ctx, TI_EINVAL, "ti_ingest_host: bad arguments");
+    if (n_batch == 0 || n_streams == 0) return TI_OK;
+    if (chunk <= 0) chunk = 1;
+    chunk = std::min(chunk, n_batch);
+    TI_CUDA(ctx, cudaSetDevice(ctx->device));
+    for (int i = 0; i < n_streams; ++i) {
+        const ti_stream& S = streams[i];
+        if ((S.kind == TI_KIND_RECTIFY && (S.camera < 0 || S.camera >= TI_MAX_CAMERAS || !ctx->cams[S.camera].has_map)) ||
+            (S.kind == TI_KIND_BACKPROJECT && (S.camera < 0 || S.camera >= TI_MAX_CAMERAS || !ctx->cams[S.camera].has_proj)))
+            return fail(ctx, TI_ESTATE, "stream %d: camera slot %d not uploaded", i, S.camera);
+        if (!S.src || !S.dst) return fail(ctx, TI_EINVAL, "stream %d: null src/dst", i);
+    }
+    if (!ctx->s_h2d) {
+        TI_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->s_h2d, cudaStreamNonBlocking));
+        TI_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->s_d2h, cudaStreamNonBlocking));
+        TI_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->s_exec, cudaStreamNonBlocking));
+        for (auto& h : ctx->hslot) {
+            TI_CUDA(ctx, cudaEventCreateWithFlags(&h.h2d_done, cudaEventDisableTiming));
+            TI_CUDA(ctx, cudaEventCreateWithFlags(&h.exec_done, cudaEventDisableTiming));
+            TI_CUDA(ctx, cudaEventCreateWithFlags(&h.d2h_done, cudaEventDisableTiming));
+        }
+    }
+    // device staging: tightly packed frames, `chunk` per stream per slot
+    std::vector<uint64_t> sb(n_streams), db(n_streams), mb(n_streams);
+    for (int i = 0; i < n_streams; ++i) {
+        sb[i] = (stream_src_bytes(ctx, streams[i]) + 15) & ~15ull;
+        db[i] = (stream_dst_bytes(ctx, streams[i]) + 15) & ~15ull;
+        mb[i] = (stream_mask_bytes(ctx, streams[i]) + 15) & ~15ull;
+    }
+    for (auto& h : ctx->hslot) {
+        h.d_src.resize(n_streams, nullptr); h.d_dst.resize(n_streams, nullptr); h.d_mask.resize(n_streams, nullptr);
+        h.d_count.resize(n_streams, nullptr);
+        h.cap_src.resize(n_streams, 0); h.cap_dst.resize(n_streams, 0); h.cap_mask.resize(n_streams, 0); h.cap_count.resize(n_streams, 0);
+        for (int i = 0; i < n_streams; ++i) {
+            int r;
+            if ((r = ensure_cap(ctx, &h.d_src[i], &h.cap_src[i], sb[i] * chunk)) != TI_OK) return r;
+            if ((r = ensure_cap(ctx, &h.d_dst[i], &h.cap_dst[i], db[i] * chunk)) != TI_OK) return r;
+            if ((r = ensure_cap(ctx, &h.d_mask[i], &h.cap_mask[i], mb[i] * chunk)) != TI_OK) return r;
+            const size_t cb = (streams[i].kind == TI_KIND_BACKPROJECT && streams[i].count) ? sizeof(uint32_t) * chunk : 0;
+            if ((r = ensure_cap(ctx, (void**)&h.d_count[i], &h.cap_count[i], cb)) != TI_OK) return r;
+        }
+    }
+    cudaStream_t user_stream = ctx->stream;
+    int rc = TI_OK;
+    const int n_chunks = (n_batch + chunk - 1) / chunk;
+    for (int c = 0; c < n_chunks && rc == TI_OK; ++c) {
+        auto& h = ctx->hslot[c & 1];
+        const int b0 = c * chunk, nb = std::min(chunk, n_batch - b0);
+        // the slot's previous D2H must have drained before its buffers are overwritten
+        if (c >= 2) {
+            cudaStreamWaitEvent(ctx->s_h2d, h.d2h_done, 0);
+            cudaStreamWaitEvent(ctx->s_exec, h.d2h_done, 0);
+        }
+        std::vector<ti_stream> dev(streams, streams + n_streams);
+        for (int i = 0; i < n_streams; ++i) {
+            const ti_stream& S = streams[i];
+            const uint64_t raw = stream_src_bytes(ctx, S);
+            const uint64_t hs = S.src_frame_stride ? S.src_frame_stride : raw;
+            if (hs == raw && sb[i] == raw) {
+                cudaMemcpyAsync(h.d_src[i], (const uint8_t*)S.src + (uint64_t)b0 * hs, raw * nb, cudaMemcpyHostToDevice, ctx->s_h2d);
+            } else {
+                cudaMemcpy2DAsync(h.d_src[i], sb[i], (const uint8_t*)S.src + (uint64_t)b0 * hs, hs, raw, nb, cudaMemcpyHostToDevice, ctx->s_h2d);
+            }
+            dev[i].src = h.d_src[i]; dev[i].dst = h.d_dst[i];
+            dev[i].src_frame_stride = sb[i]; dev[i].dst_frame_stride = db[i];
+            dev[i].mask = mb[i] ? h.d_mask[i] : nullptr; dev[i].mask_frame_stride = mb[i];
+            dev[i].count = (S.kind == TI_KIND_BACKPROJECT && S.count) ? h.d_count[i] : nullptr;
+        }
+        cudaEventRecord(h.h2d_done, ctx->s_h2d);
+        cudaStreamWaitEvent(ctx->s_exec, h.h2d_done, 0);
+        ctx->stream = ctx->s_exec;
+        rc = ti_ingest(ctx, dev.data(), n_streams, nb);
+        ctx->stream = user_stream;
+        if (rc != TI_OK) break;
+        cudaEventRecord(h.exec_done, ctx->s_exec);
+        cudaStreamWaitEvent(ctx->s_d2h, h.exec_done, 0);
+        for (int i = 0; i < n_streams; ++i) {
+            const ti_stream& S = streams[i];
+            const uint64_t raw = stream_dst_bytes(ctx, S);
+            const uint64_t hs = S.dst_frame_stride ? S.dst_frame_stride : raw;
+            if (hs == raw && db[i] == raw) {
+                cudaMemcpyAsync((uint8_t*)S.dst + (uint64_t)b0 * hs, h.d_dst[i], raw * nb, cudaMemcpyDeviceToHost, ctx->s_d2h);
+            } else {
+                cudaMemcpy2DAsync((uint8_t*)S.dst + (uint64_t)b0 * hs, hs, h.d_dst[i], db[i], raw, nb, cudaMemcpyDeviceToHost, ctx->s_d2h);
+            }
+            if (mb[i]) {
+                const uint64_t mraw = stream_mask_bytes(ctx, S);
+                const uint64_t ms = S.mask_frame_stride ? S.mask_frame_stride : mraw;
+                cudaMemcpy2DAsync((uint8_t*)S.mask + (uint64_t)b0 * ms, ms, h.d_mask[i], mb[i], mraw, nb, cudaMemcpyDeviceToHost, ctx->s_d2h);
+            }
+            if (S.kind == TI_KIND_BACKPROJECT && S.count)
+                cudaMemcpyAsync(S.count + b0, h.d_count[i], sizeof(uint32_t) * nb, cudaMemcpyDeviceToHost, ctx->s_d2h);
+        }
+        cudaEventRecord(h.d2h_done, ctx->s_d2h);
+    }
+    cudaError_t e1 = cudaStreamSynchronize(ctx->s_d2h);
+    cudaError_t e2 = cudaStreamSynchronize(ctx->s_exec);
+    cudaError_t e3 = cudaStreamSynchronize(ctx->s_h2d);
+    if (rc != TI_OK) return rc;
+    cudaError_t e = e1 != cudaSuccess ? e1 : (e2 != cudaSuccess ? e2 : e3);
+    if (e == cudaSuccess) e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(ctx, TI_ECUDA, "ti_ingest_host: %s", cudaGetErrorString(e));
+    return TI_OK;
+}
+
+}  // extern "C"

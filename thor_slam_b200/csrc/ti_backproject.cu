@@ -1,0 +1,207 @@
+// depth (u16 mm) -> body-frame xyz (f32) + valid mask (u8) + per-frame valid count (u32).
+//
+// Restates, fused in one pass, what the reference leaves to nvblox (pinhole back-projection with
+// the depth image's K - scripts/run_pipeline.py:247-256), the rig pose composition
+// world_T_camera = rig_T_source @ source_T_camera (thor_slam/camera/rig.py:35-70), the RDF->FLU
+// rotation (thor_slam/slam/adapters/isaac_ros.py:42-49) and the viewer's `depth > 0` mask / count
+// (examples/rgbd_stream.py:121-123,270-276):
+//
+//     z = d * 1e-3 ;  ray = A * [u - cx, v - cy, 1] ,  A = R * diag(1/fx, 1/fy, 1)
+//     p = z * ray + t      (d == 0 -> p = 0, mask = 0)
+//
+// HBM-bound streaming kernel: 2 B/px in, 12 + 1 B/px out.  Each thread owns 8 consecutive pixels
+// (one 16-byte depth load, one 8-byte mask store); the 96 B of xyz per thread are transposed
+// through a warp-private shared-memory buffer so every global store instruction writes 512
+// contiguous bytes; counts are reduced with redux.sync and one atomic per warp.
+#include "ti_common.cuh"
+
+namespace ti {
+
+constexpr int BP_THREADS = 256;
+constexpr int BP_PX_PER_THREAD = 8;
+constexpr int BP_TILE = BP_THREADS * BP_PX_PER_THREAD;  // 2048 px
+constexpr int MAX_BP_JOBS = 16;
+constexpr int BP_LANE_STRIDE = 7;  // float4 slots per lane in the transpose buffer (6 used + 1 pad: conflict-free)
+
+struct BpCam {
+    float a[9];
+    float t[3];
+    float cx, cy;
+    int width, height;
+};
+
+struct BpJobDev {
+    const uint16_t* depth;
+    float* xyz;
+    uint8_t* mask;
+    uint32_t* count;
+    uint64_t depth_stride, xyz_stride, mask_stride;
+    BpCam cam;
+    uint32_t tile_begin;  // prefix of tiles per frame set
+};
+
+struct BpParams {
+    BpJobDev job[MAX_BP_JOBS];
+    uint32_t tiles_per_set;
+    int n_jobs;
+    int n_batch;
+};
+
+__device__ __forceinline__ void project(const BpCam& c, float bx, float by, float bz, int u, uint32_t d, float& x,
+                                        float& y, float& z) {
+    const float du = (float)u - c.cx;
+    const float rx = __fmaf_rn(c.a[0], du, bx);
+    const float ry = __fmaf_rn(c.a[3], du, by);
+    const float rz = __fmaf_rn(c.a[6], du, bz);
+    const float zz = (float)d * 0.001f;
+    const bool ok = d != 0;
+    x = ok ? __fmaf_rn(zz, rx, c.t[0]) : 0.f;
+    y = ok ? __fmaf_rn(zz, ry, c.t[1]) : 0.f;
+    z = ok ? __fmaf_rn(zz, rz, c.t[2]) : 0.f;
+}
+
+__global__ void __launch_bounds__(BP_THREADS) backproject_vec_kernel(const __grid_constant__ BpParams P) {
+    __shared__ float4 xbuf[BP_THREADS / 32][32 * BP_LANE_STRIDE];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint64_t total = (uint64_t)P.tiles_per_set * P.n_batch;
+    for (uint64_t t = blockIdx.x; t < total; t += gridDim.x) {
+        const uint32_t b = (uint32_t)(t / P.tiles_per_set);
+        const uint32_t r = (uint32_t)(t - (uint64_t)b * P.tiles_per_set);
+        int j = 0;
+        while (j + 1 < P.n_jobs && r >= P.job[j + 1].tile_begin) ++j;
+        const BpJobDev& J = P.job[j];
+        const uint32_t tile = r - J.tile_begin;
+        const uint32_t npx = (uint32_t)J.cam.width * J.cam.height;
+        const uint32_t warp_p0 = tile * BP_TILE + warp * (32 * BP_PX_PER_THREAD);
+        const uint32_t p0 = warp_p0 + lane * BP_PX_PER_THREAD;
+        uint32_t nvalid = 0;
+        if (p0 < npx) {  // width % 8 == 0 -> a thread's 8 pixels never straddle a row or the frame end
+            const uint16_t* dp = J.depth + (uint64_t)b * (J.depth_stride / 2) + p0;
+            const uint4 dv = ld_stream_u4(dp);
+            const uint32_t dw[4] = {dv.x, dv.y, dv.z, dv.w};
+            const int v = (int)(p0 / (uint32_t)J.cam.width), u0 = (int)(p0 - (uint32_t)v * J.cam.width);
+            const float fv = (float)v - J.cam.cy;
+            const float bx = __fmaf_rn(J.cam.a[1], fv, J.cam.a[2]);
+            const float by = __fmaf_rn(J.cam.a[4], fv, J.cam.a[5]);
+            const float bz = __fmaf_rn(J.cam.a[7], fv, J.cam.a[8]);
+            float f[24];
+            uint32_t m0 = 0, m1 = 0;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const uint32_t d = (dw[k >> 1] >> ((k & 1) * 16)) & 0xFFFFu;
+                project(J.cam, bx, by, bz, u0 + k, d, f[3 * k], f[3 * k + 1], f[3 * k + 2]);
+                const uint32_t ok = d != 0 ? 1u : 0u;
+                nvalid += ok;
+                if (k < 4) m0 |= ok << (8 * k); else m1 |= ok << (8 * (k - 4));
+            }
+            if (J.mask) st_stream_u2(J.mask + (uint64_t)b * J.mask_stride + p0, make_uint2(m0, m1));
+#pragma unroll
+            for (int q = 0; q < 6; ++q)
+                xbuf[warp][lane * BP_LANE_STRIDE + q] = make_float4(f[4 * q], f[4 * q + 1], f[4 * q + 2], f[4 * q + 3]);
+        }
+        __syncwarp();
+        // coalesced write-out: float4 slot q of the warp's 256-pixel span sits at lane (q / 6), sub-slot (q % 6)
+        if (warp_p0 < npx) {
+            const uint32_t live_px = min((uint32_t)(32 * BP_PX_PER_THREAD), npx - warp_p0);
+            const uint32_t live_q = live_px * 3 / 4;  // live_px is a multiple of 8
+            float4* out = reinterpret_cast<float4*>(J.xyz + (uint64_t)b * (J.xyz_stride / 4) + (uint64_t)warp_p0 * 3);
+#pragma unroll
+            for (int i = 0; i < 6; ++i) {
+                const uint32_t q = i * 32 + lane;
+                if (q < live_q) {
+                    const float4 val = xbuf[warp][(q / 6) * BP_LANE_STRIDE + (q % 6)];
+                    st_stream_u4(out + q, make_uint4(__float_as_uint(val.x), __float_as_uint(val.y),
+                                                     __float_as_uint(val.z), __float_as_uint(val.w)));
+                }
+            }
+        }
+        __syncwarp();
+        if (J.count) {
+            const uint32_t wsum = __reduce_add_sync(0xFFFFFFFFu, nvalid);
+            if (lane == 0 && wsum) atomicAdd(J.count + b, wsum);
+        }
+    }
+}
+
+// any width / alignment: one pixel per thread
+__global__ void __launch_bounds__(BP_THREADS) backproject_scalar_kernel(BpJobDev J, int n_batch) {
+    const uint32_t npx = (uint32_t)J.cam.width * J.cam.height;
+    const uint64_t total = (uint64_t)npx * n_batch;
+    // every thread takes part in every warp reduction, so the loop bound is uniform per warp
+    const uint64_t rounds = (total + (uint64_t)gridDim.x * BP_THREADS - 1) / ((uint64_t)gridDim.x * BP_THREADS);
+    for (uint64_t it = 0; it < rounds; ++it) {
+        const uint64_t t = it * gridDim.x * BP_THREADS + (uint64_t)blockIdx.x * BP_THREADS + threadIdx.x;
+        uint32_t ok = 0, b = 0;
+        if (t < total) {
+            b = (uint32_t)(t / npx);
+            const uint32_t p = (uint32_t)(t - (uint64_t)b * npx);
+            const int v = (int)(p / (uint32_t)J.cam.width), u = (int)(p - (uint32_t)v * J.cam.width);
+            const uint32_t d = J.depth[(uint64_t)b * (J.depth_stride / 2) + p];
+            const float fv = (float)v - J.cam.cy;
+            float x, y, z;
+            project(J.cam, __fmaf_rn(J.cam.a[1], fv, J.cam.a[2]), __fmaf_rn(J.cam.a[4], fv, J.cam.a[5]),
+                    __fmaf_rn(J.cam.a[7], fv, J.cam.a[8]), u, d, x, y, z);
+            float* o = J.xyz + (uint64_t)b * (J.xyz_stride / 4) + (uint64_t)p * 3;
+            o[0] = x; o[1] = y; o[2] = z;
+            ok = d != 0;
+            if (J.mask) J.mask[(uint64_t)b * J.mask_stride + p] = (uint8_t)ok;
+        }
+        if (J.count && ok) atomicAdd(J.count + b, 1u);
+    }
+}
+
+int launch_backproject(ti_ctx* ctx, const BackprojectJob* jobs, int n_jobs, int n_batch) {
+    if (n_jobs <= 0 || n_batch <= 0) return TI_OK;
+    int done = 0;
+    while (done < n_jobs) {
+        BpParams P{};
+        int nv = 0;
+        uint32_t tiles = 0;
+        for (; done < n_jobs && nv < MAX_BP_JOBS; ++done) {
+            const BackprojectJob& J = jobs[done];
+            if (J.camera < 0 || J.camera >= TI_MAX_CAMERAS || !ctx->cams[J.camera].has_proj)
+                return fail(ctx, TI_ESTATE, "backproject: camera slot %d has no projection (call ti_upload_projection)", J.camera);
+            if (!J.depth || !J.xyz) return fail(ctx, TI_EINVAL, "backproject: null depth/xyz pointer");
+            const CameraSlot& C = ctx->cams[J.camera];
+            BpJobDev D{};
+            D.depth = J.depth; D.xyz = J.xyz; D.mask = J.mask; D.count = J.count;
+            D.depth_stride = J.depth_stride; D.xyz_stride = J.xyz_stride; D.mask_stride = J.mask_stride;
+            for (int i = 0; i < 9; ++i) D.cam.a[i] = C.ray[i];
+            for (int i = 0; i < 3; ++i) D.cam.t[i] = C.trans[i];
+            D.cam.cx = C.cx; D.cam.cy = C.cy; D.cam.width = C.proj_w; D.cam.height = C.proj_h;
+            if (J.depth_stride % 2 || J.xyz_stride % 4)
+                return fail(ctx, TI_EINVAL, "backproject: frame strides must keep element alignment");
+            if (J.count) {
+#ifndef TI_EMULATE
+                TI_CUDA(ctx, cudaMemsetAsync(J.count, 0, sizeof(uint32_t) * (size_t)n_batch, ctx->stream));
+#else
+                for (int b = 0; b < n_batch; ++b) J.count[b] = 0;
+#endif
+            }
+            const bool aligned = (C.proj_w % 8 == 0) && ((uintptr_t)J.depth % 16 == 0) && ((uintptr_t)J.xyz % 16 == 0) &&
+                                 (J.depth_stride % 16 == 0) && (J.xyz_stride % 16 == 0) &&
+                                 (!J.mask || (((uintptr_t)J.mask | J.mask_stride) % 8 == 0));
+            if (!aligned) {
+                const uint64_t total = (uint64_t)C.proj_w * C.proj_h * n_batch;
+                const int grid = (int)std::min<uint64_t>((total + BP_THREADS - 1) / BP_THREADS, (uint64_t)ctx->sm_count * 8);
+                TI_LAUNCH(backproject_scalar_kernel, grid, BP_THREADS, 0, ctx->stream, D, n_batch);
+                TI_CHECK_LAUNCH(ctx);
+                continue;
+            }
+            D.tile_begin = tiles;
+            tiles += (uint32_t)(((uint64_t)C.proj_w * C.proj_h + BP_TILE - 1) / BP_TILE);
+            P.job[nv++] = D;
+        }
+        if (nv == 0) continue;
+        P.tiles_per_set = tiles;
+        P.n_jobs = nv;
+        P.n_batch = n_batch;
+        const uint64_t total = (uint64_t)tiles * n_batch;
+        const int grid = (int)std::min<uint64_t>(total, (uint64_t)ctx->sm_count * 8);
+        TI_LAUNCH(backproject_vec_kernel, grid, BP_THREADS, 0, ctx->stream, P);
+        TI_CHECK_LAUNCH(ctx);
+    }
+    return TI_OK;
+}
+
+}  // namespace ti

@@ -1,0 +1,229 @@
+// Shared definitions of libthoringest.so (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "../../include/thoringest.h"
+
+// TI_EMULATE is defined ONLY by tests/emu (a g++ build that runs these very kernel sources
+// thread-by-thread on the CPU so indexing bugs are found before GPU time is spent).  The
+// shipped library is always built by nvcc for sm_100a with TI_EMULATE undefined.
+#ifdef TI_EMULATE
+#include "cuda_emu.h"
+#define TI_DEVICE_CODE 1
+#else
+#ifdef __CUDACC__
+#define TI_DEVICE_CODE 1
+#endif
+#define TI_LAUNCH(kernel, grid, block, smem, stream, ...) kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
+#define TI_DYNAMIC_SMEM(type, name) extern __shared__ __align__(16) type name[]
+#endif
+
+namespace ti {
+
+// ---------------------------------------------------------------------------------------------
+// Remap LUT encoding.  One u32 per OUTPUT pixel, row-major:
+//   bits  0..10  x0 + 1   (x0 = floor(mapx) after 1/32-px quantisation; -1 <= x0 <= src_w-1)
+//   bits 11..21  y0 + 1
+//   bits 22..26  fx       (5-bit fractional part, units of 1/32 px)
+//   bits 27..31  fy
+// A pixel none of whose four taps touches the source image is LUT_OUTSIDE (x0+1 == 2047).
+// ---------------------------------------------------------------------------------------------
+constexpr uint32_t LUT_OUTSIDE = 0xFFFFFFFFu;
+constexpr int LUT_COORD_BITS = 11;
+constexpr uint32_t LUT_COORD_MASK = (1u << LUT_COORD_BITS) - 1u;
+
+// Rectify tile: one CTA produces RT_W x RT_H output pixels from a source box staged in smem.
+constexpr int RT_W = 128;
+constexpr int RT_H = 16;
+constexpr int RT_THREADS = 256;
+
+struct TileBox {  // source bounding box of one output tile, in source pixels
+    int16_t x0, y0;  // first column / row any tap touches (may be -1: zero border)
+    int16_t x1, y1;  // one past the last column / row any tap touches; x1 <= x0 means "all outside"
+};
+
+struct CameraSlot {
+    // rectification
+    bool has_map = false;
+    int dst_w = 0, dst_h = 0, src_w = 0, src_h = 0;
+    int tiles_x = 0, tiles_y = 0;
+    uint32_t* d_lut = nullptr;     // dst_h * dst_w
+    TileBox* d_boxes = nullptr;    // tiles_y * tiles_x
+    uint8_t* d_valid = nullptr;    // dst_h * dst_w
+    size_t tile_smem[2] = {0, 0};  // largest staged box in bytes for 1- and 3-channel sources
+    // projection
+    bool has_proj = false;
+    int proj_w = 0, proj_h = 0;
+    float ray[9];  // A = R * diag(1/fx, 1/fy, 1), row-major: p = z * (A * [u-cx, v-cy, 1]) + t
+    float trans[3];
+    float cx = 0.f, cy = 0.f;
+};
+
+}  // namespace ti
+
+struct ti_ctx {
+    int device = 0;
+    int sm_count = 148;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    uint64_t launches = 0;
+    ti::CameraSlot cams[TI_MAX_CAMERAS];
+    // host pipeline (ti_ingest_host)
+    cudaStream_t s_h2d = nullptr, s_d2h = nullptr, s_exec = nullptr;
+    struct HostSlot {
+        std::vector<void*> d_src, d_dst, d_mask;
+        std::vector<uint32_t*> d_count;
+        std::vector<size_t> cap_src, cap_dst, cap_mask, cap_count;
+        cudaEvent_t h2d_done = nullptr, exec_done = nullptr, d2h_done = nullptr;
+    } hslot[2];
+    // NCCL (dlopen)
+    void* nccl_comm = nullptr;
+    int rank = 0, world = 1;
+};
+
+void ti_nccl_teardown(ti_ctx* ctx);  // ti_nccl.cu
+
+namespace ti {
+
+int fail(ti_ctx* ctx, int code, const char* fmt, ...);
+void set_global_error(const char* msg);
+
+#define TI_CUDA(ctx, expr)                                                                     \
+    do {                                                                                       \
+        cudaError_t _e = (expr);                                                               \
+        if (_e != cudaSuccess)                                                                 \
+            return ti::fail((ctx), TI_ECUDA, "%s failed: %s (%s:%d)", #expr,                   \
+                            cudaGetErrorString(_e), __FILE__, __LINE__);                       \
+    } while (0)
+
+#ifdef TI_EMULATE
+#define TI_CHECK_LAUNCH(ctx) ((ctx)->launches++)
+#else
+#define TI_CHECK_LAUNCH(ctx)                                                                   \
+    do {                                                                                       \
+        cudaError_t _e = cudaGetLastError();                                                   \
+        if (_e != cudaSuccess)                                                                 \
+            return ti::fail((ctx), TI_ECUDA, "kernel launch failed: %s (%s:%d)",               \
+                            cudaGetErrorString(_e), __FILE__, __LINE__);                       \
+        (ctx)->launches++;                                                                     \
+    } while (0)
+#endif
+
+inline int channels_of(int fmt) {
+    switch (fmt) {
+        case TI_FMT_MONO8: return 1;
+        case TI_FMT_BGR8:
+        case TI_FMT_RGB8: return 3;
+        default: return 0;
+    }
+}
+
+// bytes of one frame in `fmt`
+inline uint64_t frame_bytes(int fmt, int w, int h) {
+    switch (fmt) {
+        case TI_FMT_MONO8: return (uint64_t)w * h;
+        case TI_FMT_BGR8:
+        case TI_FMT_RGB8: return (uint64_t)w * h * 3;
+        case TI_FMT_NV12: return (uint64_t)w * h * 3 / 2;
+        case TI_FMT_DEPTH16: return (uint64_t)w * h * 2;
+        case TI_FMT_XYZ32F: return (uint64_t)w * h * 12;
+        default: return 0;
+    }
+}
+
+// launchers implemented in the kernel translation units -------------------------------------
+struct ConvertJob {
+    const uint8_t* src;
+    uint8_t* dst;
+    uint64_t src_stride, dst_stride;
+    int width, height, src_fmt, dst_fmt;
+};
+int launch_convert(ti_ctx* ctx, const ConvertJob* jobs, int n_jobs, int n_batch);
+
+struct RectifyJob {
+    const uint8_t* src;
+    uint8_t* dst;
+    uint64_t src_stride, dst_stride;
+    int camera, src_fmt, dst_fmt;
+};
+int launch_rectify(ti_ctx* ctx, const RectifyJob* jobs, int n_jobs, int n_batch);
+
+struct BackprojectJob {
+    const uint16_t* depth;
+    float* xyz;
+    uint8_t* mask;
+    uint32_t* count;
+    uint64_t depth_stride, xyz_stride, mask_stride;
+    int camera;
+};
+int launch_backproject(ti_ctx* ctx, const BackprojectJob* jobs, int n_jobs, int n_batch);
+
+#if defined(TI_EMULATE)
+__device__ __forceinline__ uint4 ld_stream_u4(const void* p) { return *reinterpret_cast<const uint4*>(ti_emu::check_align(p, 16)); }
+__device__ __forceinline__ uint2 ld_stream_u2(const void* p) { return *reinterpret_cast<const uint2*>(ti_emu::check_align(p, 8)); }
+__device__ __forceinline__ void st_stream_u4(void* p, uint4 v) { *reinterpret_cast<uint4*>(ti_emu::check_align(p, 16)) = v; }
+__device__ __forceinline__ void st_stream_u2(void* p, uint2 v) { *reinterpret_cast<uint2*>(ti_emu::check_align(p, 8)) = v; }
+__device__ __forceinline__ void st_stream_u1(void* p, uint32_t v) { *reinterpret_cast<uint32_t*>(ti_emu::check_align(p, 4)) = v; }
+__device__ __forceinline__ uint4 ld_keep_u4(const void* p) { return *reinterpret_cast<const uint4*>(ti_emu::check_align(p, 16)); }
+#elif defined(__CUDACC__)
+// ---- device helpers ------------------------------------------------------------------------
+// L2 eviction policies (createpolicy is not volatile: the compiler hoists / CSEs it).
+__device__ __forceinline__ uint64_t policy_evict_first() {
+    uint64_t p;
+    asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ uint64_t policy_evict_last() {
+    uint64_t p;
+    asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+// Streaming accesses: inputs are read once, outputs written once -> keep them out of L1 and mark
+// them evict-first in L2 so the (re-used) remap LUT stays resident.
+__device__ __forceinline__ uint4 ld_stream_u4(const void* p) {
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.u32 {%0,%1,%2,%3}, [%4], %5;"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+                 : "l"(p), "l"(policy_evict_first()));
+    return r;
+}
+__device__ __forceinline__ uint2 ld_stream_u2(const void* p) {
+    uint2 r;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v2.u32 {%0,%1}, [%2], %3;"
+                 : "=r"(r.x), "=r"(r.y)
+                 : "l"(p), "l"(policy_evict_first()));
+    return r;
+}
+__device__ __forceinline__ void st_stream_u4(void* p, uint4 v) {
+    asm volatile("st.global.L1::no_allocate.L2::cache_hint.v4.u32 [%0], {%1,%2,%3,%4}, %5;" ::"l"(p),
+                 "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "l"(policy_evict_first())
+                 : "memory");
+}
+__device__ __forceinline__ void st_stream_u2(void* p, uint2 v) {
+    asm volatile("st.global.L1::no_allocate.L2::cache_hint.v2.u32 [%0], {%1,%2}, %3;" ::"l"(p),
+                 "r"(v.x), "r"(v.y), "l"(policy_evict_first())
+                 : "memory");
+}
+__device__ __forceinline__ void st_stream_u1(void* p, uint32_t v) {
+    asm volatile("st.global.L1::no_allocate.L2::cache_hint.u32 [%0], %1, %2;" ::"l"(p), "r"(v),
+                 "l"(policy_evict_first())
+                 : "memory");
+}
+// LUT reads: re-used by every frame of the batch -> prefer to keep in L2.
+__device__ __forceinline__ uint4 ld_keep_u4(const void* p) {
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.u32 {%0,%1,%2,%3}, [%4], %5;"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+                 : "l"(p), "l"(policy_evict_last()));
+    return r;
+}
+#endif
+
+}  // namespace ti

@@ -1,0 +1,219 @@
+// Format conversion kernels (u8, bit-exact with OpenCV 4.x cvtColor).
+//
+//   BGR8 -> RGB8   byte swap                                (isaac_ros.py:357, run_pipeline.py:234)
+//   BGR8 -> MONO8  Y = (B*3735 + G*19235 + R*9798 + 2^14) >> 15         (cv2.COLOR_BGR2GRAY)
+//   NV12 -> MONO8  copy of the luma plane                               (cv2.COLOR_YUV2GRAY_NV12)
+//   NV12 -> RGB8 / BGR8  BT.601 limited range, 20-bit fixed point       (cv2.COLOR_YUV2RGB_NV12)
+//   MONO8 -> MONO8 copy                                                 (isaac_ros.py:352-353)
+//
+// All of them are pure streaming: each thread moves whole 16-byte vectors, a warp covers a
+// contiguous span, nothing is re-read -> HBM-bound.  One launch covers every (stream, frame)
+// of the batch; the grid is a multiple of the SM count and CTAs stride over "units" of work.
+#include "ti_common.cuh"
+#include "ti_pixel.cuh"
+
+namespace ti {
+
+constexpr int CV_THREADS = 256;
+constexpr int MAX_CONVERT_JOBS = TI_MAX_STREAMS;
+
+struct ConvertParams {
+    ConvertJob job[MAX_CONVERT_JOBS];
+    uint32_t unit_begin[MAX_CONVERT_JOBS + 1];  // prefix sum of units per frame over jobs
+    int n_jobs;
+    int n_batch;
+};
+
+__device__ __forceinline__ uint32_t byte_of(const uint32_t* w, int i) {  // i-th byte of a small register array
+    return (w[i >> 2] >> ((i & 3) * 8)) & 0xFFu;
+}
+
+// ---- unit processors: one "unit" = 16 pixels (or 2 rows x 16 pixels for NV12 colour) --------
+
+// 16 BGR pixels (48 B) -> 16 RGB pixels (48 B)
+__device__ __forceinline__ void unit_bgr_to_rgb(const uint8_t* src, uint8_t* dst) {
+    uint32_t w[12], o[12];
+    const uint4 a = ld_stream_u4(src), b = ld_stream_u4(src + 16), c = ld_stream_u4(src + 32);
+    w[0] = a.x; w[1] = a.y; w[2] = a.z; w[3] = a.w;
+    w[4] = b.x; w[5] = b.y; w[6] = b.z; w[7] = b.w;
+    w[8] = c.x; w[9] = c.y; w[10] = c.z; w[11] = c.w;
+    // every 12-byte group holds 4 pixels: B0G0R0B1 G1R1B2G2 R2B3G3R3 -> R0G0B0R1 G1B1R2G2 B2R3G3B3
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+        const uint32_t w0 = w[3 * g], w1 = w[3 * g + 1], w2 = w[3 * g + 2];
+        o[3 * g] = __byte_perm(w0, w1, 0x5012);      // R0 G0 B0 R1   (bytes: w0.2, w0.1, w0.0, w1.1)
+        o[3 * g + 1] = __byte_perm(w1, __byte_perm(w0, w2, 0x0043), 0x3540);  // G1 B1 R2 G2
+        o[3 * g + 2] = __byte_perm(w2, w1, 0x1236);  // B2 R3 G3 B3   (bytes: w1.2, w2.3, w2.2, w2.1)
+    }
+    st_stream_u4(dst, make_uint4(o[0], o[1], o[2], o[3]));
+    st_stream_u4(dst + 16, make_uint4(o[4], o[5], o[6], o[7]));
+    st_stream_u4(dst + 32, make_uint4(o[8], o[9], o[10], o[11]));
+}
+
+// 16 BGR pixels (48 B) -> 16 gray pixels (16 B)
+__device__ __forceinline__ void unit_bgr_to_gray(const uint8_t* src, uint8_t* dst) {
+    uint32_t w[12], o[4];
+    const uint4 a = ld_stream_u4(src), b = ld_stream_u4(src + 16), c = ld_stream_u4(src + 32);
+    w[0] = a.x; w[1] = a.y; w[2] = a.z; w[3] = a.w;
+    w[4] = b.x; w[5] = b.y; w[6] = b.z; w[7] = b.w;
+    w[8] = c.x; w[9] = c.y; w[10] = c.z; w[11] = c.w;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        uint32_t out = 0;
+#pragma unroll
+        for (int p = 0; p < 4; ++p) {
+            const int px = q * 4 + p;
+            out |= gray_of(byte_of(w, 3 * px), byte_of(w, 3 * px + 1), byte_of(w, 3 * px + 2)) << (8 * p);
+        }
+        o[q] = out;
+    }
+    st_stream_u4(dst, make_uint4(o[0], o[1], o[2], o[3]));
+}
+
+// 2 rows x 16 luma + 16 B of UV -> 2 rows x 16 RGB (or BGR) pixels
+template <bool BGR_OUT>
+__device__ __forceinline__ void unit_nv12_to_color(const uint8_t* y0p, const uint8_t* y1p, const uint8_t* uvp,
+                                                   uint8_t* d0, uint8_t* d1) {
+    uint32_t y0[4], y1[4], uv[4];
+    {
+        const uint4 a = ld_stream_u4(y0p), b = ld_stream_u4(y1p), c = ld_stream_u4(uvp);
+        y0[0] = a.x; y0[1] = a.y; y0[2] = a.z; y0[3] = a.w;
+        y1[0] = b.x; y1[1] = b.y; y1[2] = b.z; y1[3] = b.w;
+        uv[0] = c.x; uv[1] = c.y; uv[2] = c.z; uv[3] = c.w;
+    }
+#pragma unroll
+    for (int row = 0; row < 2; ++row) {
+        const uint32_t* yy = row ? y1 : y0;
+        uint32_t o[12];
+#pragma unroll
+        for (int i = 0; i < 12; ++i) o[i] = 0;
+#pragma unroll
+        for (int px = 0; px < 16; ++px) {
+            const int u = (int)byte_of(uv, (px >> 1) * 2), v = (int)byte_of(uv, (px >> 1) * 2 + 1);
+            int r, g, b;
+            yuv_to_rgb((int)byte_of(yy, px), u, v, r, g, b);
+            const int c0 = BGR_OUT ? b : r, c2 = BGR_OUT ? r : b;
+            const int base = 3 * px;
+            o[base >> 2] |= (uint32_t)c0 << ((base & 3) * 8);
+            o[(base + 1) >> 2] |= (uint32_t)g << (((base + 1) & 3) * 8);
+            o[(base + 2) >> 2] |= (uint32_t)c2 << (((base + 2) & 3) * 8);
+        }
+        uint8_t* d = row ? d1 : d0;
+        st_stream_u4(d, make_uint4(o[0], o[1], o[2], o[3]));
+        st_stream_u4(d + 16, make_uint4(o[4], o[5], o[6], o[7]));
+        st_stream_u4(d + 32, make_uint4(o[8], o[9], o[10], o[11]));
+    }
+}
+
+// ---- vector kernel (width % 16 == 0, 16-byte aligned frames) ---------------------------------
+__global__ void __launch_bounds__(CV_THREADS) convert_vec_kernel(const __grid_constant__ ConvertParams P) {
+    const uint32_t units_per_set = P.unit_begin[P.n_jobs];
+    const uint64_t total = (uint64_t)units_per_set * P.n_batch;
+    for (uint64_t t = (uint64_t)blockIdx.x * CV_THREADS + threadIdx.x; t < total;
+         t += (uint64_t)gridDim.x * CV_THREADS) {
+        const uint32_t b = (uint32_t)(t / units_per_set);
+        const uint32_t r = (uint32_t)(t - (uint64_t)b * units_per_set);
+        int j = 0;
+        while (j + 1 < P.n_jobs && r >= P.unit_begin[j + 1]) ++j;
+        const ConvertJob& J = P.job[j];
+        const uint32_t unit = r - P.unit_begin[j];
+        const uint8_t* src = J.src + (uint64_t)b * J.src_stride;
+        uint8_t* dst = J.dst + (uint64_t)b * J.dst_stride;
+        const int w = J.width, h = J.height;
+        if (J.src_fmt == TI_FMT_BGR8 && J.dst_fmt == TI_FMT_RGB8) {
+            unit_bgr_to_rgb(src + (uint64_t)unit * 48, dst + (uint64_t)unit * 48);
+        } else if (J.src_fmt == TI_FMT_BGR8 && J.dst_fmt == TI_FMT_MONO8) {
+            unit_bgr_to_gray(src + (uint64_t)unit * 48, dst + (uint64_t)unit * 16);
+        } else if (J.dst_fmt == TI_FMT_MONO8) {  // MONO8 or NV12 luma: plain copy
+            st_stream_u4(dst + (uint64_t)unit * 16, ld_stream_u4(src + (uint64_t)unit * 16));
+        } else {  // NV12 -> colour: unit = 16 columns of a row PAIR
+            const uint32_t upr = (uint32_t)w / 16;
+            const uint32_t rp = unit / upr, cx = (unit - rp * upr) * 16;
+            const uint8_t* y0 = src + (uint64_t)(2 * rp) * w + cx;
+            const uint8_t* uv = src + (uint64_t)h * w + (uint64_t)rp * w + cx;
+            uint8_t* d0 = dst + ((uint64_t)(2 * rp) * w + cx) * 3;
+            if (J.dst_fmt == TI_FMT_BGR8)
+                unit_nv12_to_color<true>(y0, y0 + w, uv, d0, d0 + (uint64_t)w * 3);
+            else
+                unit_nv12_to_color<false>(y0, y0 + w, uv, d0, d0 + (uint64_t)w * 3);
+        }
+    }
+}
+
+// ---- scalar kernel (any width / alignment): one pixel per thread ----------------------------
+__global__ void __launch_bounds__(CV_THREADS) convert_scalar_kernel(ConvertJob J, int n_batch) {
+    const uint64_t npx = (uint64_t)J.width * J.height;
+    const uint64_t total = npx * n_batch;
+    for (uint64_t t = (uint64_t)blockIdx.x * CV_THREADS + threadIdx.x; t < total;
+         t += (uint64_t)gridDim.x * CV_THREADS) {
+        const uint64_t b = t / npx, p = t - b * npx;
+        const uint8_t* src = J.src + b * J.src_stride;
+        uint8_t* dst = J.dst + b * J.dst_stride;
+        if (J.src_fmt == TI_FMT_BGR8) {
+            const uint32_t bb = src[3 * p], gg = src[3 * p + 1], rr = src[3 * p + 2];
+            if (J.dst_fmt == TI_FMT_RGB8) {
+                dst[3 * p] = (uint8_t)rr; dst[3 * p + 1] = (uint8_t)gg; dst[3 * p + 2] = (uint8_t)bb;
+            } else {
+                dst[p] = (uint8_t)gray_of(bb, gg, rr);
+            }
+        } else if (J.dst_fmt == TI_FMT_MONO8) {
+            dst[p] = src[p];
+        } else {
+            const uint32_t y = (uint32_t)(p / J.width), x = (uint32_t)(p - (uint64_t)y * J.width);
+            const uint8_t* uv = src + npx + (uint64_t)(y >> 1) * J.width + (x & ~1u);
+            int r, g, bl;
+            yuv_to_rgb(src[p], uv[0], uv[1], r, g, bl);
+            const bool bgr = J.dst_fmt == TI_FMT_BGR8;
+            dst[3 * p] = (uint8_t)(bgr ? bl : r); dst[3 * p + 1] = (uint8_t)g; dst[3 * p + 2] = (uint8_t)(bgr ? r : bl);
+        }
+    }
+}
+
+static bool convert_supported(int s, int d) {
+    if (s == TI_FMT_BGR8) return d == TI_FMT_RGB8 || d == TI_FMT_MONO8;
+    if (s == TI_FMT_NV12) return d == TI_FMT_MONO8 || d == TI_FMT_RGB8 || d == TI_FMT_BGR8;
+    if (s == TI_FMT_MONO8) return d == TI_FMT_MONO8;
+    return false;
+}
+
+int launch_convert(ti_ctx* ctx, const ConvertJob* jobs, int n_jobs, int n_batch) {
+    if (n_jobs <= 0 || n_batch <= 0) return TI_OK;
+    if (n_jobs > MAX_CONVERT_JOBS) return fail(ctx, TI_EINVAL, "too many convert streams (%d > %d)", n_jobs, MAX_CONVERT_JOBS);
+    ConvertParams P{};
+    int nv = 0;
+    uint32_t units = 0;
+    for (int i = 0; i < n_jobs; ++i) {
+        const ConvertJob& J = jobs[i];
+        if (!convert_supported(J.src_fmt, J.dst_fmt))
+            return fail(ctx, TI_EINVAL, "unsupported conversion %d -> %d", J.src_fmt, J.dst_fmt);
+        if (J.width <= 0 || J.height <= 0 || !J.src || !J.dst)
+            return fail(ctx, TI_EINVAL, "convert: bad size or null pointer");
+        if (J.src_fmt == TI_FMT_NV12 && ((J.width | J.height) & 1))
+            return fail(ctx, TI_EINVAL, "NV12 needs even width and height (got %dx%d)", J.width, J.height);
+        const bool aligned = (J.width % 16 == 0) && (((uintptr_t)J.src | (uintptr_t)J.dst | J.src_stride | J.dst_stride) % 16 == 0);
+        if (!aligned) {
+            const uint64_t total = (uint64_t)J.width * J.height * n_batch;
+            const int grid = (int)std::min<uint64_t>((total + CV_THREADS - 1) / CV_THREADS, (uint64_t)ctx->sm_count * 8);
+            TI_LAUNCH(convert_scalar_kernel, grid, CV_THREADS, 0, ctx->stream, J, n_batch);
+            TI_CHECK_LAUNCH(ctx);
+            continue;
+        }
+        P.job[nv] = J;
+        P.unit_begin[nv] = units;
+        const bool pair = J.src_fmt == TI_FMT_NV12 && J.dst_fmt != TI_FMT_MONO8;
+        units += (uint32_t)((uint64_t)J.width * J.height / (pair ? 32 : 16));
+        ++nv;
+    }
+    if (nv == 0) return TI_OK;
+    P.unit_begin[nv] = units;
+    P.n_jobs = nv;
+    P.n_batch = n_batch;
+    const uint64_t total = (uint64_t)units * n_batch;
+    const uint64_t want = (total + CV_THREADS - 1) / CV_THREADS;
+    const int grid = (int)std::min<uint64_t>(want, (uint64_t)ctx->sm_count * 8);
+    TI_LAUNCH(convert_vec_kernel, grid, CV_THREADS, 0, ctx->stream, P);
+    TI_CHECK_LAUNCH(ctx);
+    return TI_OK;
+}
+
+}  // namespace ti

@@ -1,0 +1,197 @@
+// Multi-GPU exchange step of the ingest path: ONE gather of per-GPU body-frame clouds to the
+// fusing rank over NVLink 5 / NVSwitch (one process per GPU).
+//
+//  * ti_gather_clouds: grouped ncclSend / ncclRecv on the ctx stream (NCCL is dlopen()ed so the
+//    library has no link-time dependency and shares torch's libnccl when torch is loaded).
+//  * ti_peer_*: CUDA-IPC peer buffers, so a back-projection kernel on rank r can store its xyz
+//    output straight into the root GPU's memory through NVLink - the gather is then fused into
+//    the producing kernel (its `dst` simply is a peer pointer) and only a barrier remains.
+#include <dlfcn.h>
+#include <string.h>
+
+#include "ti_common.cuh"
+
+namespace {
+
+struct NcclId { char internal[128]; };
+typedef void* ncclComm_t;
+typedef int ncclResult_t;
+
+struct NcclApi {
+    void* handle = nullptr;
+    ncclResult_t (*GetUniqueId)(NcclId*) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, NcclId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    ncclResult_t (*Send)(const void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Recv)(void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+    std::string why;
+};
+
+NcclApi& nccl() {
+    static NcclApi api;
+    static bool tried = false;
+    if (tried) return api;
+    tried = true;
+    const char* names[] = {"libnccl.so.2", "libnccl.so"};
+    for (const char* n : names) {
+        api.handle = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+        if (api.handle) break;
+    }
+    if (!api.handle) {
+        api.why = std::string("dlopen(libnccl.so.2) failed: ") + (dlerror() ? dlerror() : "?");
+        return api;
+    }
+#define LOAD(field, sym)                                                     \
+    api.field = reinterpret_cast<decltype(api.field)>(dlsym(api.handle, sym)); \
+    if (!api.field) { api.why = std::string("missing NCCL symbol ") + sym; api.handle = nullptr; return api; }
+    LOAD(GetUniqueId, "ncclGetUniqueId")
+    LOAD(CommInitRank, "ncclCommInitRank")
+    LOAD(CommDestroy, "ncclCommDestroy")
+    LOAD(GroupStart, "ncclGroupStart")
+    LOAD(GroupEnd, "ncclGroupEnd")
+    LOAD(Send, "ncclSend")
+    LOAD(Recv, "ncclRecv")
+    LOAD(AllReduce, "ncclAllReduce")
+    LOAD(GetErrorString, "ncclGetErrorString")
+#undef LOAD
+    return api;
+}
+
+constexpr int NCCL_UINT8 = 1;   // ncclUint8
+constexpr int NCCL_INT32 = 2;   // ncclInt32
+constexpr int NCCL_SUM = 0;     // ncclSum
+
+#define TI_NCCL(ctx, expr)                                                                     \
+    do {                                                                                       \
+        ncclResult_t _r = (expr);                                                              \
+        if (_r != 0)                                                                           \
+            return ti::fail((ctx), TI_ENCCL, "%s failed: %s", #expr, nccl().GetErrorString(_r)); \
+    } while (0)
+
+}  // namespace
+
+void ti_nccl_teardown(ti_ctx* ctx) {
+    if (ctx->nccl_comm && nccl().handle) nccl().CommDestroy((ncclComm_t)ctx->nccl_comm);
+    ctx->nccl_comm = nullptr;
+}
+
+extern "C" {
+
+int ti_nccl_unique_id(void* id128) {
+    if (!id128) return ti::fail(nullptr, TI_EINVAL, "ti_nccl_unique_id: null buffer");
+    NcclApi& a = nccl();
+    if (!a.handle) return ti::fail(nullptr, TI_ENCCL, "%s", a.why.c_str());
+    NcclId id;
+    ncclResult_t r = a.GetUniqueId(&id);
+    if (r != 0) return ti::fail(nullptr, TI_ENCCL, "ncclGetUniqueId: %s", a.GetErrorString(r));
+    memcpy(id128, &id, sizeof id);
+    return TI_OK;
+}
+
+int ti_nccl_init(ti_ctx* ctx, const void* id128, int rank, int world) {
+    if (!ctx) return TI_EINVAL;
+    if (!id128 || world <= 0 || rank < 0 || rank >= world) return ti::fail(ctx, TI_EINVAL, "ti_nccl_init: bad rank/world");
+    NcclApi& a = nccl();
+    if (!a.handle) return ti::fail(ctx, TI_ENCCL, "%s", a.why.c_str());
+    TI_CUDA(ctx, cudaSetDevice(ctx->device));
+    ti_nccl_teardown(ctx);
+    NcclId id;
+    memcpy(&id, id128, sizeof id);
+    ncclComm_t comm = nullptr;
+    TI_NCCL(ctx, a.CommInitRank(&comm, world, id, rank));
+    ctx->nccl_comm = comm;
+    ctx->rank = rank;
+    ctx->world = world;
+    return TI_OK;
+}
+
+int ti_gather_clouds(ti_ctx* ctx, const void* local, void* gathered, const uint64_t* bytes_per_rank, int root) {
+    if (!ctx) return TI_EINVAL;
+    if (!ctx->nccl_comm) return ti::fail(ctx, TI_ESTATE, "ti_gather_clouds: call ti_nccl_init first");
+    if (!bytes_per_rank || root < 0 || root >= ctx->world) return ti::fail(ctx, TI_EINVAL, "ti_gather_clouds: bad arguments");
+    if (ctx->rank == root && !gathered) return ti::fail(ctx, TI_EINVAL, "ti_gather_clouds: root needs a gathered buffer");
+    NcclApi& a = nccl();
+    ncclComm_t comm = (ncclComm_t)ctx->nccl_comm;
+    TI_CUDA(ctx, cudaSetDevice(ctx->device));
+    const uint64_t mine = bytes_per_rank[ctx->rank];
+    if (mine && !local) return ti::fail(ctx, TI_EINVAL, "ti_gather_clouds: null local buffer");
+    if (ctx->rank == root) {
+        uint64_t off = 0;
+        for (int r = 0; r < root; ++r) off += bytes_per_rank[r];
+        if (mine)  // own slice: device-to-device copy, no NCCL self send
+            TI_CUDA(ctx, cudaMemcpyAsync((uint8_t*)gathered + off, local, mine, cudaMemcpyDeviceToDevice, ctx->stream));
+        TI_NCCL(ctx, a.GroupStart());
+        off = 0;
+        for (int r = 0; r < ctx->world; ++r) {
+            if (r != root && bytes_per_rank[r])
+                TI_NCCL(ctx, a.Recv((uint8_t*)gathered + off, bytes_per_rank[r], NCCL_UINT8, r, comm, ctx->stream));
+            off += bytes_per_rank[r];
+        }
+        TI_NCCL(ctx, a.GroupEnd());
+    } else if (mine) {
+        TI_NCCL(ctx, a.Send(local, mine, NCCL_UINT8, root, comm, ctx->stream));
+    }
+    return TI_OK;
+}
+
+int ti_nccl_barrier(ti_ctx* ctx) {
+    if (!ctx) return TI_EINVAL;
+    if (!ctx->nccl_comm) return ti::fail(ctx, TI_ESTATE, "ti_nccl_barrier: call ti_nccl_init first");
+    TI_CUDA(ctx, cudaSetDevice(ctx->device));
+    static thread_local int* d_flag = nullptr;
+    if (!d_flag) {
+        TI_CUDA(ctx, cudaMalloc(&d_flag, sizeof(int)));
+        TI_CUDA(ctx, cudaMemset(d_flag, 0, sizeof(int)));
+    }
+    TI_NCCL(ctx, nccl().AllReduce(d_flag, d_flag, 1, NCCL_INT32, NCCL_SUM, (ncclComm_t)ctx->nccl_comm, ctx->stream));
+    TI_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return TI_OK;
+}
+
+int ti_peer_alloc(ti_ctx* ctx, uint64_t bytes, void** dev_ptr, void* handle64) {
+    if (!ctx) return TI_EINVAL;
+    if (!dev_ptr || !handle64 || bytes == 0) return ti::fail(ctx, TI_EINVAL, "ti_peer_alloc: bad arguments");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle is 64 bytes");
+    TI_CUDA(ctx, cudaSetDevice(ctx->device));
+    void* p = nullptr;
+    TI_CUDA(ctx, cudaMalloc(&p, bytes));
+    cudaIpcMemHandle_t h;
+    cudaError_t e = cudaIpcGetMemHandle(&h, p);
+    if (e != cudaSuccess) {
+        cudaFree(p);
+        return ti::fail(ctx, TI_ECUDA, "cudaIpcGetMemHandle: %s", cudaGetErrorString(e));
+    }
+    memcpy(handle64, &h, sizeof h);
+    *dev_ptr = p;
+    return TI_OK;
+}
+
+int ti_peer_open(ti_ctx* ctx, const void* handle64, void** dev_ptr) {
+    if (!ctx) return TI_EINVAL;
+    if (!handle64 || !dev_ptr) return ti::fail(ctx, TI_EINVAL, "ti_peer_open: bad arguments");
+    TI_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, sizeof h);
+    TI_CUDA(ctx, cudaIpcOpenMemHandle(dev_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return TI_OK;
+}
+
+int ti_peer_close(ti_ctx* ctx, void* dev_ptr) {
+    if (!ctx) return TI_EINVAL;
+    TI_CUDA(ctx, cudaSetDevice(ctx->device));
+    TI_CUDA(ctx, cudaIpcCloseMemHandle(dev_ptr));
+    return TI_OK;
+}
+
+int ti_peer_free(ti_ctx* ctx, void* dev_ptr) {
+    if (!ctx) return TI_EINVAL;
+    TI_CUDA(ctx, cudaSetDevice(ctx->device));
+    TI_CUDA(ctx, cudaFree(dev_ptr));
+    return TI_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,296 @@
+// Format conversion fused with the undistort / rectify remap (u8, bit-exact with
+// cv2.remap(cvtColor(src), mapx, mapy, INTER_LINEAR, BORDER_CONSTANT 0)).
+//
+// The reference publishes raw images and lets cuVSLAM undistort them
+// (thor_slam/slam/adapters/isaac_ros.py:364-411, Makefile:77-80); here the remap runs on the GPU.
+//
+// Tiled kernel (rectify_tile_kernel): one CTA = RT_W x RT_H (128 x 16) output pixels.
+//   1. every thread fetches the packed LUT entries of its 8 consecutive output pixels (2 x 128-bit),
+//   2. the CTA copies the tile's source bounding box (precomputed per tile at upload time) into
+//      shared memory with coalesced 128-bit loads, zero-filling what lies outside the image
+//      (that is BORDER_CONSTANT 0),
+//   3. four bilinear taps per pixel are read from shared memory, blended in exact integer
+//      arithmetic, packed and written with one 64-bit store per channel-row.
+// Direct kernel (rectify_direct_kernel): one thread per output pixel, taps straight from global
+// memory, conversion applied per tap.  Used for sizes/alignments the tiled kernel does not take
+// and for the two-stage conversions (BGR->gray, NV12->rgb) before remap.
+#include "ti_common.cuh"
+#include "ti_pixel.cuh"
+
+namespace ti {
+
+constexpr int MAX_RECT_JOBS = 16;
+constexpr int RT_PX_PER_THREAD = 8;
+constexpr int RT_MAX_SMEM = 96 * 1024;  // per-CTA cap for the staged source box
+
+struct RectJobDev {
+    const uint8_t* src;
+    uint8_t* dst;
+    uint64_t src_stride, dst_stride;
+    const uint32_t* lut;  // padded: lut_rows x lut_pitch
+    const TileBox* boxes;
+    int lut_pitch;
+    int tiles_x, tiles_y;
+    int dst_w, dst_h, src_w, src_h;
+    uint32_t tile_begin;
+};
+
+struct RectParams {
+    RectJobDev job[MAX_RECT_JOBS];
+    uint32_t tiles_per_set;
+    int n_jobs;
+    int n_batch;
+};
+
+__device__ __forceinline__ uint4 ld_src_u4(const void* p) {
+#ifdef TI_EMULATE
+    return *reinterpret_cast<const uint4*>(ti_emu::check_align(p, 16));
+#else
+    uint4 r;  // source rows are re-read by neighbouring tiles (halo): default L2 policy, no L1
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+                 : "l"(p));
+    return r;
+#endif
+}
+
+// C = channels of the staged source (1: MONO8 / NV12 luma, 3: BGR8 written out as RGB8)
+template <int C>
+__global__ void __launch_bounds__(RT_THREADS) rectify_tile_kernel(const __grid_constant__ RectParams P) {
+    TI_DYNAMIC_SMEM(uint8_t, smem);
+    const int tid = threadIdx.x;
+    const int lx = (tid & 15) * RT_PX_PER_THREAD, ly = tid >> 4;
+    const uint64_t total = (uint64_t)P.tiles_per_set * P.n_batch;
+    for (uint64_t t = blockIdx.x; t < total; t += gridDim.x) {
+        const uint32_t b = (uint32_t)(t / P.tiles_per_set);
+        const uint32_t r = (uint32_t)(t - (uint64_t)b * P.tiles_per_set);
+        int j = 0;
+        while (j + 1 < P.n_jobs && r >= P.job[j + 1].tile_begin) ++j;
+        const RectJobDev& J = P.job[j];
+        const uint32_t tile = r - J.tile_begin;
+        const int ty = (int)(tile / (uint32_t)J.tiles_x), tx = (int)(tile - (uint32_t)ty * J.tiles_x);
+        const TileBox box = J.boxes[tile];
+        const int u = tx * RT_W + lx, v = ty * RT_H + ly;
+
+        // (1) LUT entries of this thread's 8 pixels (LUT is padded to whole tiles: no guards)
+        const uint32_t* lp = J.lut + (size_t)v * J.lut_pitch + u;
+        const uint4 l0 = ld_keep_u4(lp), l1 = ld_keep_u4(lp + 4);
+        const uint32_t e[8] = {l0.x, l0.y, l0.z, l0.w, l1.x, l1.y, l1.z, l1.w};
+
+        // (2) stage the source box
+        const int c0 = (box.x0 * C) & ~15;               // first staged byte column (may be negative)
+        const int c1 = (box.x1 * C + 15) & ~15;          // one past the last staged byte column
+        const int pitch = c1 - c0;
+        const int rows = box.y1 - box.y0;
+        const bool any = box.x1 > box.x0;
+        if (any) {
+            const uint8_t* src = J.src + (uint64_t)b * J.src_stride;
+            const int row_bytes = J.src_w * C;
+            const int nvec = pitch >> 4;
+            const int total_vec = nvec * rows;
+            for (int i = tid; i < total_vec; i += RT_THREADS) {
+                const int row = i / nvec, vc = i - row * nvec;
+                const int gy = box.y0 + row, gx = c0 + (vc << 4);
+                uint4 val = make_uint4(0u, 0u, 0u, 0u);
+                if (gy >= 0 && gy < J.src_h && gx >= 0 && gx + 16 <= row_bytes)
+                    val = ld_src_u4(src + (size_t)gy * row_bytes + gx);
+                *reinterpret_cast<uint4*>(smem + row * pitch + (vc << 4)) = val;
+            }
+        }
+        __syncthreads();
+
+        // (3) taps + blend
+        if (v < J.dst_h && u < J.dst_w) {
+            uint32_t o[C][2];
+#pragma unroll
+            for (int c = 0; c < C; ++c) o[c][0] = o[c][1] = 0u;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const uint32_t ek = e[k];
+                if (ek == LUT_OUTSIDE) continue;
+                const int sx = (int)(ek & LUT_COORD_MASK) - 1, sy = (int)((ek >> LUT_COORD_BITS) & LUT_COORD_MASK) - 1;
+                const uint32_t fx = (ek >> 22) & 31u, fy = ek >> 27;
+                const uint8_t* s = smem + (sy - box.y0) * pitch + (sx * C - c0);
+#pragma unroll
+                for (int c = 0; c < C; ++c) {
+                    const int sc = C == 3 ? 2 - c : c;  // BGR source -> RGB output
+                    const uint32_t val = bilinear_u8(s[sc], s[sc + C], s[sc + pitch], s[sc + pitch + C], fx, fy);
+                    o[c][k >> 2] |= val << ((k & 3) * 8);
+                }
+            }
+            uint8_t* dst = J.dst + (uint64_t)b * J.dst_stride + ((size_t)v * J.dst_w + u) * C;
+            if (u + 8 <= J.dst_w) {
+                if (C == 1) {
+                    st_stream_u2(dst, make_uint2(o[0][0], o[0][1]));
+                } else {
+                    // interleave 8 px x 3 channels = 24 bytes = 3 x 8-byte stores
+                    uint32_t w[6];
+#pragma unroll
+                    for (int i = 0; i < 6; ++i) w[i] = 0u;
+#pragma unroll
+                    for (int k = 0; k < 8; ++k)
+#pragma unroll
+                        for (int c = 0; c < C; ++c) {
+                            const uint32_t val = (o[c][k >> 2] >> ((k & 3) * 8)) & 0xFFu;
+                            const int bi = k * 3 + c;
+                            w[bi >> 2] |= val << ((bi & 3) * 8);
+                        }
+                    st_stream_u2(dst, make_uint2(w[0], w[1]));
+                    st_stream_u2(dst + 8, make_uint2(w[2], w[3]));
+                    st_stream_u2(dst + 16, make_uint2(w[4], w[5]));
+                }
+            } else {  // ragged right edge (dst_w % 8 != 0 is rejected by the launcher; kept for safety)
+                for (int k = 0; k < 8 && u + k < J.dst_w; ++k)
+                    for (int c = 0; c < C; ++c) dst[k * C + c] = (uint8_t)((o[c][k >> 2] >> ((k & 3) * 8)) & 0xFFu);
+            }
+        }
+        __syncthreads();  // the next tile's staging overwrites smem
+    }
+}
+
+// ---- direct kernel -----------------------------------------------------------------------------
+enum DirectMode { DM_MONO = 0, DM_BGR_TO_RGB = 1, DM_BGR_TO_GRAY = 2, DM_NV12_TO_RGB = 3 };
+
+struct DirectJob {
+    const uint8_t* src;
+    uint8_t* dst;
+    uint64_t src_stride, dst_stride;
+    const uint32_t* lut;
+    int lut_pitch;
+    int dst_w, dst_h, src_w, src_h;
+    int mode;
+};
+
+template <int MODE>
+__device__ __forceinline__ void fetch(const DirectJob& J, const uint8_t* src, int x, int y, uint32_t out[3]) {
+    out[0] = out[1] = out[2] = 0u;
+    if (x < 0 || x >= J.src_w || y < 0 || y >= J.src_h) return;  // BORDER_CONSTANT 0 (after conversion)
+    const size_t p = (size_t)y * J.src_w + x;
+    if (MODE == DM_MONO) {
+        out[0] = src[p];
+    } else if (MODE == DM_BGR_TO_RGB) {
+        out[0] = src[3 * p + 2]; out[1] = src[3 * p + 1]; out[2] = src[3 * p];
+    } else if (MODE == DM_BGR_TO_GRAY) {
+        out[0] = gray_of(src[3 * p], src[3 * p + 1], src[3 * p + 2]);
+    } else {
+        const uint8_t* uv = src + (size_t)J.src_h * J.src_w + (size_t)(y >> 1) * J.src_w + (x & ~1);
+        int r, g, b;
+        yuv_to_rgb(src[p], uv[0], uv[1], r, g, b);
+        out[0] = (uint32_t)r; out[1] = (uint32_t)g; out[2] = (uint32_t)b;
+    }
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(256) rectify_direct_kernel(DirectJob J, int n_batch) {
+    constexpr int C = (MODE == DM_BGR_TO_RGB || MODE == DM_NV12_TO_RGB) ? 3 : 1;
+    const uint64_t npx = (uint64_t)J.dst_w * J.dst_h;
+    const uint64_t total = npx * n_batch;
+    for (uint64_t t = (uint64_t)blockIdx.x * 256 + threadIdx.x; t < total; t += (uint64_t)gridDim.x * 256) {
+        const uint64_t b = t / npx;
+        const uint32_t p = (uint32_t)(t - b * npx);
+        const int v = (int)(p / (uint32_t)J.dst_w), u = (int)(p - (uint32_t)v * J.dst_w);
+        const uint32_t ek = J.lut[(size_t)v * J.lut_pitch + u];
+        uint8_t* dst = J.dst + b * J.dst_stride + (size_t)p * C;
+        if (ek == LUT_OUTSIDE) {
+            for (int c = 0; c < C; ++c) dst[c] = 0;
+            continue;
+        }
+        const int sx = (int)(ek & LUT_COORD_MASK) - 1, sy = (int)((ek >> LUT_COORD_BITS) & LUT_COORD_MASK) - 1;
+        const uint32_t fx = (ek >> 22) & 31u, fy = ek >> 27;
+        const uint8_t* src = J.src + b * J.src_stride;
+        uint32_t t00[3], t01[3], t10[3], t11[3];
+        fetch<MODE>(J, src, sx, sy, t00);
+        fetch<MODE>(J, src, sx + 1, sy, t01);
+        fetch<MODE>(J, src, sx, sy + 1, t10);
+        fetch<MODE>(J, src, sx + 1, sy + 1, t11);
+        for (int c = 0; c < C; ++c) dst[c] = (uint8_t)bilinear_u8(t00[c], t01[c], t10[c], t11[c], fx, fy);
+    }
+}
+
+static int direct_mode(int s, int d) {
+    if ((s == TI_FMT_MONO8 || s == TI_FMT_NV12) && d == TI_FMT_MONO8) return DM_MONO;
+    if (s == TI_FMT_BGR8 && d == TI_FMT_RGB8) return DM_BGR_TO_RGB;
+    if (s == TI_FMT_BGR8 && d == TI_FMT_MONO8) return DM_BGR_TO_GRAY;
+    if (s == TI_FMT_NV12 && d == TI_FMT_RGB8) return DM_NV12_TO_RGB;
+    return -1;
+}
+
+static int launch_direct(ti_ctx* ctx, const DirectJob& D, int n_batch) {
+    const uint64_t total = (uint64_t)D.dst_w * D.dst_h * n_batch;
+    const int grid = (int)std::min<uint64_t>((total + 255) / 256, (uint64_t)ctx->sm_count * 16);
+    switch (D.mode) {
+        case DM_MONO: TI_LAUNCH(rectify_direct_kernel<DM_MONO>, grid, 256, 0, ctx->stream, D, n_batch); break;
+        case DM_BGR_TO_RGB: TI_LAUNCH(rectify_direct_kernel<DM_BGR_TO_RGB>, grid, 256, 0, ctx->stream, D, n_batch); break;
+        case DM_BGR_TO_GRAY: TI_LAUNCH(rectify_direct_kernel<DM_BGR_TO_GRAY>, grid, 256, 0, ctx->stream, D, n_batch); break;
+        default: TI_LAUNCH(rectify_direct_kernel<DM_NV12_TO_RGB>, grid, 256, 0, ctx->stream, D, n_batch); break;
+    }
+    TI_CHECK_LAUNCH(ctx);
+    return TI_OK;
+}
+
+template <int C>
+static int launch_tiled(ti_ctx* ctx, RectParams& P, size_t smem_bytes) {
+    const uint64_t total = (uint64_t)P.tiles_per_set * P.n_batch;
+    if (total == 0) return TI_OK;
+#ifndef TI_EMULATE
+    static size_t configured[2] = {0, 0};
+    size_t& cfg = configured[C == 1 ? 0 : 1];
+    if (smem_bytes > 48 * 1024 && smem_bytes > cfg) {
+        TI_CUDA(ctx, cudaFuncSetAttribute(rectify_tile_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RT_MAX_SMEM));
+        cfg = RT_MAX_SMEM;
+    }
+#endif
+    // resident CTAs per SM are bounded by shared memory (228 KB/SM) and by 2048 threads/SM
+    int per_sm = (int)std::min<size_t>(8, (size_t)(220 * 1024) / std::max<size_t>(smem_bytes + 1024, 1));
+    per_sm = std::max(per_sm, 1);
+    const int grid = (int)std::min<uint64_t>(total, (uint64_t)ctx->sm_count * per_sm);
+    TI_LAUNCH(rectify_tile_kernel<C>, grid, RT_THREADS, smem_bytes, ctx->stream, P);
+    TI_CHECK_LAUNCH(ctx);
+    return TI_OK;
+}
+
+int launch_rectify(ti_ctx* ctx, const RectifyJob* jobs, int n_jobs, int n_batch) {
+    if (n_jobs <= 0 || n_batch <= 0) return TI_OK;
+    RectParams P1{}, P3{};  // tiled launches for 1-channel and 3-channel sources
+    size_t smem1 = 0, smem3 = 0;
+    for (int i = 0; i < n_jobs; ++i) {
+        const RectifyJob& J = jobs[i];
+        if (J.camera < 0 || J.camera >= TI_MAX_CAMERAS || !ctx->cams[J.camera].has_map)
+            return fail(ctx, TI_ESTATE, "rectify: camera slot %d has no remap LUT (call ti_upload_rectify_map)", J.camera);
+        const int mode = direct_mode(J.src_fmt, J.dst_fmt);
+        if (mode < 0) return fail(ctx, TI_EINVAL, "rectify: unsupported conversion %d -> %d", J.src_fmt, J.dst_fmt);
+        if (!J.src || !J.dst) return fail(ctx, TI_EINVAL, "rectify: null src/dst pointer");
+        const CameraSlot& C = ctx->cams[J.camera];
+        if (J.src_fmt == TI_FMT_NV12 && ((C.src_w | C.src_h) & 1))
+            return fail(ctx, TI_EINVAL, "NV12 needs even width and height (got %dx%d)", C.src_w, C.src_h);
+        const int lut_pitch = C.tiles_x * RT_W;
+        const int ch = (mode == DM_BGR_TO_RGB) ? 3 : 1;
+        const size_t need = C.tile_smem[ch == 1 ? 0 : 1];
+        const bool tiled_ok = (mode == DM_MONO || mode == DM_BGR_TO_RGB) && (C.src_w * ch) % 16 == 0 && C.dst_w % 8 == 0 &&
+                              ((uintptr_t)J.src % 16 == 0) && (J.src_stride % 16 == 0) && ((uintptr_t)J.dst % 8 == 0) &&
+                              (J.dst_stride % 8 == 0) && need <= (size_t)RT_MAX_SMEM;
+        RectParams& P = ch == 1 ? P1 : P3;
+        if (!tiled_ok || P.n_jobs == MAX_RECT_JOBS) {
+            DirectJob D{J.src, J.dst, J.src_stride, J.dst_stride, C.d_lut, lut_pitch, C.dst_w, C.dst_h, C.src_w, C.src_h, mode};
+            const int rc = launch_direct(ctx, D, n_batch);
+            if (rc != TI_OK) return rc;
+            continue;
+        }
+        RectJobDev D{};
+        D.src = J.src; D.dst = J.dst; D.src_stride = J.src_stride; D.dst_stride = J.dst_stride;
+        D.lut = C.d_lut; D.boxes = C.d_boxes; D.lut_pitch = lut_pitch;
+        D.tiles_x = C.tiles_x; D.tiles_y = C.tiles_y;
+        D.dst_w = C.dst_w; D.dst_h = C.dst_h; D.src_w = C.src_w; D.src_h = C.src_h;
+        D.tile_begin = P.tiles_per_set;
+        P.tiles_per_set += (uint32_t)(C.tiles_x * C.tiles_y);
+        P.job[P.n_jobs++] = D;
+        size_t& smem = ch == 1 ? smem1 : smem3;
+        smem = std::max(smem, need);
+    }
+    P1.n_batch = P3.n_batch = n_batch;
+    int rc = launch_tiled<1>(ctx, P1, smem1);
+    if (rc != TI_OK) return rc;
+    return launch_tiled<3>(ctx, P3, smem3);
+}
+
+}  // namespace ti

@@ -1,0 +1,246 @@
+"""``IngestContext`` - thin Python face of one ``ti_ctx`` (one per process and GPU).
+
+PyTorch tensors are only buffer carriers here: every call hands raw ``data_ptr()`` addresses to
+the C ABI.  Error mapping follows the reference's conventions:
+``TI_EINVAL`` -> ``ValueError``; everything else -> ``RuntimeError``.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Any, Sequence
+
+import numpy as np
+
+from thor_slam_b200.ingest import formats as F
+from thor_slam_b200.ingest._lib import TI_EINVAL, TI_OK, IngestLibrary, TiStream, default_library
+
+
+def _is_torch(x: Any) -> bool:
+    return hasattr(x, "data_ptr")
+
+
+@dataclass
+class StreamSpec:
+    """One stream of a frame-set batch (Python view of ``struct ti_stream``).
+
+    ``src`` / ``dst`` / ``mask`` / ``count`` are batched arrays whose first dimension is the
+    frame index; strides default to the tensors' own batch stride.
+    """
+
+    kind: int
+    src: Any
+    dst: Any
+    src_format: int
+    dst_format: int
+    camera: int = 0
+    width: int = 0
+    height: int = 0
+    mask: Any = None
+    count: Any = None
+
+
+class IngestContext:
+    def __init__(self, device: int = 0, library: IngestLibrary | None = None) -> None:
+        self.lib = library if library is not None else default_library()
+        self.device = device
+        handle = C.c_void_p()
+        rc = self.lib.ti_create(device, C.byref(handle))
+        if rc != TI_OK:
+            msg = self.lib.ti_last_error(None).decode()
+            raise (ValueError if rc == TI_EINVAL else RuntimeError)(msg)
+        self._h = handle
+        self._cams: dict[int, dict] = {}
+
+    # -- plumbing ------------------------------------------------------------
+    def close(self) -> None:
+        if getattr(self, "_h", None) is not None and self._h:
+            self.lib.ti_destroy(self._h)
+            self._h = None
+
+    def __del__(self) -> None:  # pragma: no cover - best effort
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self) -> "IngestContext":
+        return self
+
+    def __exit__(self, *exc: object) -> None:
+        self.close()
+
+    def _check(self, rc: int) -> None:
+        if rc == TI_OK:
+            return
+        msg = self.lib.ti_last_error(self._h).decode()
+        raise (ValueError if rc == TI_EINVAL else RuntimeError)(f"thoringest: {msg}")
+
+    def _ptr(self, x: Any, host_ok: bool = False) -> int | None:
+        """Raw address of a buffer carrier; device tensors only, unless ``host_ok``."""
+        if x is None:
+            return None
+        if _is_torch(x):
+            if not x.is_contiguous():
+                raise ValueError("buffers handed to the ingest library must be contiguous")
+            if not x.is_cuda and not (host_ok or self.lib.is_emulation):
+                raise ValueError("expected a CUDA tensor (the ingest stage has no CPU path)")
+            return x.data_ptr()
+        if isinstance(x, np.ndarray):
+            if not (host_ok or self.lib.is_emulation):
+                raise ValueError("numpy arrays are host memory; pass a CUDA tensor")
+            if not x.flags["C_CONTIGUOUS"]:
+                raise ValueError("buffers handed to the ingest library must be contiguous")
+            return x.ctypes.data
+        if isinstance(x, int):
+            return x
+        raise TypeError(f"unsupported buffer carrier {type(x).__name__}")
+
+    @staticmethod
+    def _batch_stride(x: Any) -> int:
+        """Bytes between consecutive frames (dimension 0) of a batched array."""
+        if _is_torch(x):
+            return x.stride(0) * x.element_size() if x.dim() > 0 and x.shape[0] > 1 else int(np.prod(x.shape[1:])) * x.element_size()
+        return x.strides[0] if x.ndim > 0 and x.shape[0] > 1 else int(np.prod(x.shape[1:])) * x.itemsize
+
+    def set_stream(self, cuda_stream: int | None) -> None:
+        """``cuda_stream``: e.g. ``torch.cuda.current_stream().cuda_stream`` (``None``/0: legacy default)."""
+        self._check(self.lib.ti_set_stream(self._h, C.c_void_p(cuda_stream or 0)))
+
+    def sync(self) -> None:
+        self._check(self.lib.ti_sync(self._h))
+
+    @property
+    def launch_count(self) -> int:
+        return int(self.lib.ti_launch_count(self._h))
+
+    @property
+    def sm_count(self) -> int:
+        return int(self.lib.ti_device_sm_count(self._h))
+
+    # -- calibration upload ----------------------------------------------------
+    def upload_rectify_map(self, camera: int, mapx: np.ndarray, mapy: np.ndarray, src_size: tuple[int, int]) -> None:
+        """``mapx``/``mapy``: float32 ``dst_h x dst_w`` (OpenCV convention); ``src_size`` = (w, h)."""
+        mapx = np.ascontiguousarray(mapx, dtype=np.float32)
+        mapy = np.ascontiguousarray(mapy, dtype=np.float32)
+        if mapx.shape != mapy.shape or mapx.ndim != 2:
+            raise ValueError(f"mapx/mapy must be equal-shaped 2-D arrays, got {mapx.shape} and {mapy.shape}")
+        dst_h, dst_w = mapx.shape
+        self._check(
+            self.lib.ti_upload_rectify_map(self._h, camera, dst_w, dst_h, int(src_size[0]), int(src_size[1]),
+                                           mapx.ctypes.data, mapy.ctypes.data)
+        )
+        self._cams.setdefault(camera, {}).update(dst=(dst_w, dst_h), src=(int(src_size[0]), int(src_size[1])))
+
+    def upload_projection(self, camera: int, k: np.ndarray, body_T_cam: np.ndarray, size: tuple[int, int]) -> None:
+        """``k``: 3x3 intrinsics of the depth image; ``body_T_cam``: 4x4 (or 3x4) float64; ``size`` = (w, h)."""
+        k = np.asarray(k, dtype=np.float64)
+        m = np.asarray(body_T_cam, dtype=np.float64)
+        if k.shape != (3, 3) or m.shape not in ((4, 4), (3, 4)):
+            raise ValueError("k must be 3x3 and body_T_cam 4x4 or 3x4")
+        kk = (C.c_double * 4)(k[0, 0], k[1, 1], k[0, 2], k[1, 2])
+        mm = (C.c_double * 12)(*m[:3, :4].reshape(-1))
+        self._check(self.lib.ti_upload_projection(self._h, camera, int(size[0]), int(size[1]), kk, mm))
+        self._cams.setdefault(camera, {}).update(proj=(int(size[0]), int(size[1])))
+
+    def camera_info(self, camera: int) -> dict:
+        return dict(self._cams.get(camera, {}))
+
+    def get_valid_mask(self, camera: int, out: Any) -> Any:
+        self._check(self.lib.ti_get_valid_mask(self._h, camera, self._ptr(out)))
+        return out
+
+    # -- per-frame calls (device buffers) ---------------------------------------
+    def convert(self, src: Any, dst: Any, src_format: int | str, dst_format: int | str, width: int, height: int) -> Any:
+        """Batched format conversion; ``src``/``dst``: ``[n_batch, ...frame shape...]``."""
+        n = int(src.shape[0])
+        self._check(
+            self.lib.ti_convert(self._h, F.fmt(src_format), F.fmt(dst_format), self._ptr(src), self._ptr(dst), width, height,
+                                n, self._batch_stride(src), self._batch_stride(dst))
+        )
+        return dst
+
+    def rectify(self, camera: int, src: Any, dst: Any, src_format: int | str, dst_format: int | str) -> Any:
+        n = int(src.shape[0])
+        self._check(
+            self.lib.ti_rectify(self._h, camera, F.fmt(src_format), F.fmt(dst_format), self._ptr(src), self._ptr(dst), n,
+                                self._batch_stride(src), self._batch_stride(dst))
+        )
+        return dst
+
+    def backproject(self, camera: int, depth: Any, xyz: Any, mask: Any = None, count: Any = None) -> Any:
+        n = int(depth.shape[0])
+        self._check(
+            self.lib.ti_backproject(self._h, camera, self._ptr(depth), self._ptr(xyz), self._ptr(mask), self._ptr(count), n,
+                                    self._batch_stride(depth), self._batch_stride(xyz),
+                                    self._batch_stride(mask) if mask is not None else 0)
+        )
+        return xyz
+
+    def _pack(self, streams: Sequence[StreamSpec], host: bool) -> tuple[Any, int]:
+        arr = (TiStream * len(streams))()
+        n_batch = None
+        for i, s in enumerate(streams):
+            nb = int(s.src.shape[0])
+            if n_batch is None:
+                n_batch = nb
+            elif nb != n_batch:
+                raise ValueError(f"stream {i} carries {nb} frames, earlier streams carry {n_batch}")
+            t = arr[i]
+            t.kind, t.camera = s.kind, s.camera
+            t.src_format, t.dst_format = F.fmt(s.src_format), F.fmt(s.dst_format)
+            t.width, t.height = s.width, s.height
+            t.src, t.dst = self._ptr(s.src, host), self._ptr(s.dst, host)
+            t.src_frame_stride, t.dst_frame_stride = self._batch_stride(s.src), self._batch_stride(s.dst)
+            t.mask = self._ptr(s.mask, host)
+            t.mask_frame_stride = self._batch_stride(s.mask) if s.mask is not None else 0
+            t.count = self._ptr(s.count, host)
+        return arr, (n_batch or 0)
+
+    def ingest(self, streams: Sequence[StreamSpec]) -> None:
+        """Whole frame-set batch, device buffers, at most one launch per stream kind."""
+        arr, n_batch = self._pack(streams, host=False)
+        self._check(self.lib.ti_ingest(self._h, arr, len(streams), n_batch))
+
+    def ingest_host(self, streams: Sequence[StreamSpec], chunk: int = 8) -> None:
+        """Same with (pinned) host buffers: H2D, kernels and D2H pipelined ``chunk`` frame sets at a time."""
+        arr, n_batch = self._pack(streams, host=True)
+        self._check(self.lib.ti_ingest_host(self._h, arr, len(streams), n_batch, chunk))
+
+    # -- multi-GPU ---------------------------------------------------------------
+    def nccl_unique_id(self) -> bytes:
+        buf = C.create_string_buffer(128)
+        rc = self.lib.ti_nccl_unique_id(buf)
+        if rc != TI_OK:
+            raise RuntimeError(self.lib.ti_last_error(None).decode())
+        return buf.raw
+
+    def nccl_init(self, unique_id: bytes, rank: int, world: int) -> None:
+        if len(unique_id) != 128:
+            raise ValueError("NCCL unique id must be 128 bytes")
+        self._check(self.lib.ti_nccl_init(self._h, C.create_string_buffer(unique_id, 128), rank, world))
+
+    def gather_clouds(self, local: Any, gathered: Any, bytes_per_rank: Sequence[int], root: int = 0) -> None:
+        arr = (C.c_uint64 * len(bytes_per_rank))(*[int(b) for b in bytes_per_rank])
+        self._check(self.lib.ti_gather_clouds(self._h, self._ptr(local), self._ptr(gathered), arr, root))
+
+    def nccl_barrier(self) -> None:
+        self._check(self.lib.ti_nccl_barrier(self._h))
+
+    def peer_alloc(self, nbytes: int) -> tuple[int, bytes]:
+        ptr = C.c_void_p()
+        handle = C.create_string_buffer(64)
+        self._check(self.lib.ti_peer_alloc(self._h, nbytes, C.byref(ptr), handle))
+        return int(ptr.value), handle.raw
+
+    def peer_open(self, handle: bytes) -> int:
+        ptr = C.c_void_p()
+        self._check(self.lib.ti_peer_open(self._h, C.create_string_buffer(handle, 64), C.byref(ptr)))
+        return int(ptr.value)
+
+    def peer_close(self, ptr: int) -> None:
+        self._check(self.lib.ti_peer_close(self._h, C.c_void_p(ptr)))
+
+    def peer_free(self, ptr: int) -> None:
+        self._check(self.lib.ti_peer_free(self._h, C.c_void_p(ptr)))
