@@ -95,6 +95,12 @@ int ti_set_stream(ti_ctx* ctx, void* cuda_stream);
 int ti_sync(ti_ctx* ctx);
 /* Kernel launches issued by this ctx since creation (for bench.py "gpu_launches"). */
 uint64_t ti_launch_count(const ti_ctx* ctx);
+/* Tuning / test switches (never change results). */
+typedef enum ti_option {
+    TI_OPT_FORCE_GENERIC_RECTIFY = 1, /* 1: skip the fast mono remap kernel, use the generic ones */
+    TI_OPT_CTAS_PER_SM = 2            /* >0: resident CTAs per SM the persistent grids are sized for */
+} ti_option;
+int ti_set_option(ti_ctx* ctx, int option, int value);
 int ti_device_sm_count(const ti_ctx* ctx);
 
 /* ---- calibration upload (one-off; replaces nothing per-frame in the reference:

@@ -33,6 +33,8 @@ static void free_camera(CameraSlot& c) {
     if (c.d_lut) cudaFree(c.d_lut);
     if (c.d_boxes) cudaFree(c.d_boxes);
     if (c.d_valid) cudaFree(c.d_valid);
+    if (c.d_lut2) cudaFree(c.d_lut2);
+    if (c.d_boxes2) cudaFree(c.d_boxes2);
     c = CameraSlot{};
 }
 
@@ -115,6 +117,15 @@ int ti_sync(ti_ctx* ctx) {
     return TI_OK;
 }
 
+int ti_set_option(ti_ctx* ctx, int option, int value) {
+    if (!ctx) return TI_EINVAL;
+    switch (option) {
+        case TI_OPT_FORCE_GENERIC_RECTIFY: ctx->force_generic_rectify = value != 0; return TI_OK;
+        case TI_OPT_CTAS_PER_SM: ctx->ctas_per_sm = value; return TI_OK;
+        default: return fail(ctx, TI_EINVAL, "ti_set_option: unknown option %d", option);
+    }
+}
+
 uint64_t ti_launch_count(const ti_ctx* ctx) { return ctx ? ctx->launches : 0; }
 int ti_device_sm_count(const ti_ctx* ctx) { return ctx ? ctx->sm_count : 0; }
 
@@ -130,13 +141,13 @@ int ti_upload_rectify_map(ti_ctx* ctx, int camera, int dst_w, int dst_h, int src
                     dst_w, dst_h, src_w, src_h);
     TI_CUDA(ctx, cudaSetDevice(ctx->device));
     CameraSlot& C = ctx->cams[camera];
-    const bool keep_proj = C.has_proj;
-    CameraSlot saved = C;
     if (C.d_lut) cudaFree(C.d_lut);
     if (C.d_boxes) cudaFree(C.d_boxes);
     if (C.d_valid) cudaFree(C.d_valid);
-    C.d_lut = nullptr; C.d_boxes = nullptr; C.d_valid = nullptr; C.has_map = false;
-    (void)keep_proj; (void)saved;
+    if (C.d_lut2) cudaFree(C.d_lut2);
+    if (C.d_boxes2) cudaFree(C.d_boxes2);
+    C.d_lut = nullptr; C.d_boxes = nullptr; C.d_valid = nullptr; C.d_lut2 = nullptr; C.d_boxes2 = nullptr;
+    C.has_map = false; C.has_fast_mono = false;
 
     const int tiles_x = (dst_w + RT_W - 1) / RT_W, tiles_y = (dst_h + RT_H - 1) / RT_H;
     const int lut_pitch = tiles_x * RT_W, lut_rows = tiles_y * RT_H;
@@ -179,6 +190,59 @@ int ti_upload_rectify_map(ti_ctx* ctx, int camera, int dst_w, int dst_h, int src
     C.tiles_x = tiles_x; C.tiles_y = tiles_y;
     C.tile_smem[0] = smem1; C.tile_smem[1] = smem3;
     C.has_map = true;
+
+    // ---- fast mono tables: tile-relative LUT ---------------------------------------------------
+    // entry = off << 16 | fy << 6 | fx ; off = byte address in shared memory of the (2-byte aligned)
+    // pair (src[y0][x0], src[y0][x0+1]): copy A holds the row as is (pairs with even x0 - c0), copy B
+    // holds it shifted by one byte (odd x0 - c0); the pair one row below sits M2_ROW_BYTES further.
+    // Pixels with no tap inside the image point at the zero block with fx = fy = 0.
+    if (src_w % 16 == 0) {
+        const int t2x = (dst_w + M2_TW - 1) / M2_TW, t2y = (dst_h + M2_TH - 1) / M2_TH;
+        std::vector<TileBox2> boxes2((size_t)t2x * t2y);
+        std::vector<uint32_t> lut2((size_t)t2x * t2y * M2_TW * M2_TH, 0u);
+        bool ok = true;
+        int rows_max = 0;
+        for (int ty = 0; ty < t2y && ok; ++ty)
+            for (int tx = 0; tx < t2x && ok; ++tx) {
+                int bx0 = 1 << 20, by0 = 1 << 20, bx1 = -(1 << 20), by1 = -(1 << 20);
+                for (int v = ty * M2_TH; v < std::min(dst_h, (ty + 1) * M2_TH); ++v)
+                    for (int u = tx * M2_TW; u < std::min(dst_w, (tx + 1) * M2_TW); ++u) {
+                        const uint32_t e = lut[(size_t)v * lut_pitch + u];
+                        if (e == LUT_OUTSIDE) continue;
+                        const int x0 = (int)(e & LUT_COORD_MASK) - 1, y0 = (int)((e >> LUT_COORD_BITS) & LUT_COORD_MASK) - 1;
+                        bx0 = std::min(bx0, x0); by0 = std::min(by0, y0);
+                        bx1 = std::max(bx1, x0 + 2); by1 = std::max(by1, y0 + 2);
+                    }
+                TileBox2& B = boxes2[(size_t)ty * t2x + tx];
+                B = TileBox2{0, 0, 0, 0, (int16_t)(tx * M2_TW), (int16_t)(ty * M2_TH), 0, 0};
+                if (bx1 <= bx0) continue;
+                const int c0 = bx0 & ~15;  // floor to 16 (two's complement: -1 -> -16)
+                const int span = bx1 - c0;
+                const int rows = by1 - by0;
+                if (span > M2_COPY_BYTES || rows > M2_MAX_ROWS) { ok = false; break; }
+                B.c0 = (int16_t)c0; B.y0 = (int16_t)by0; B.nvec = (int16_t)((span + 15) / 16); B.rows = (int16_t)rows;
+                rows_max = std::max(rows_max, rows);
+                uint32_t* tl = lut2.data() + ((size_t)ty * t2x + tx) * M2_TW * M2_TH;
+                for (int v = ty * M2_TH; v < std::min(dst_h, (ty + 1) * M2_TH); ++v)
+                    for (int u = tx * M2_TW; u < std::min(dst_w, (tx + 1) * M2_TW); ++u) {
+                        const uint32_t e = lut[(size_t)v * lut_pitch + u];
+                        if (e == LUT_OUTSIDE) continue;
+                        const int x0 = (int)(e & LUT_COORD_MASK) - 1, y0 = (int)((e >> LUT_COORD_BITS) & LUT_COORD_MASK) - 1;
+                        const uint32_t fx = (e >> 22) & 31u, fy = e >> 27;
+                        const int rel = x0 - c0;
+                        const int off = M2_ZERO_BYTES + (y0 - by0) * M2_ROW_BYTES + ((rel & 1) ? M2_COPY_BYTES + rel - 1 : rel);
+                        tl[(size_t)(v - ty * M2_TH) * M2_TW + (u - tx * M2_TW)] = ((uint32_t)off << 16) | (fy << 6) | fx;
+                    }
+            }
+        if (ok) {
+            TI_CUDA(ctx, cudaMalloc(&C.d_lut2, lut2.size() * sizeof(uint32_t)));
+            TI_CUDA(ctx, cudaMalloc(&C.d_boxes2, boxes2.size() * sizeof(TileBox2)));
+            TI_CUDA(ctx, cudaMemcpy(C.d_lut2, lut2.data(), lut2.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+            TI_CUDA(ctx, cudaMemcpy(C.d_boxes2, boxes2.data(), boxes2.size() * sizeof(TileBox2), cudaMemcpyHostToDevice));
+            C.tiles2_x = t2x; C.tiles2_y = t2y; C.rows2_max = rows_max;
+            C.has_fast_mono = true;
+        }
+    }
     return TI_OK;
 }
 

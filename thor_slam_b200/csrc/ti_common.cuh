@@ -49,9 +49,34 @@ struct TileBox {  // source bounding box of one output tile, in source pixels
     int16_t x1, y1;  // one past the last column / row any tap touches; x1 <= x0 means "all outside"
 };
 
+// Fast mono path ("v2"): tiles of M2_TW x M2_TH output pixels, LUT entries hold tile-relative
+// shared-memory byte offsets (see ti_rectify.cu).
+constexpr int M2_TW = 128;
+constexpr int M2_TH = 32;
+constexpr int M2_THREADS = 256;
+constexpr int M2_ROW_BYTES = 512;   // per staged source row: 256 B copy A + 256 B copy B (shifted by one byte)
+constexpr int M2_COPY_BYTES = 256;
+constexpr int M2_ZERO_BYTES = 128;  // always-zero block at the start of shared memory
+constexpr int M2_MAX_ROWS = 96;
+
+struct TileBox2 {
+    int16_t c0;    // first staged source column (multiple of 16, may be -16)
+    int16_t y0;    // first staged source row (may be -1)
+    int16_t nvec;  // 16-byte vectors staged per row (<= 16); 0 = nothing to stage
+    int16_t rows;  // staged rows
+    int16_t u0, v0;  // output pixel of the tile's top-left corner
+    int16_t pad0, pad1;
+};
+static_assert(sizeof(TileBox2) == 16, "TileBox2 is loaded as one 128-bit word");
+
 struct CameraSlot {
     // rectification
     bool has_map = false;
+    bool has_fast_mono = false;
+    uint32_t* d_lut2 = nullptr;     // tiles * M2_TH * M2_TW, tile-major
+    TileBox2* d_boxes2 = nullptr;   // tiles
+    int tiles2_x = 0, tiles2_y = 0;
+    int rows2_max = 0;
     int dst_w = 0, dst_h = 0, src_w = 0, src_h = 0;
     int tiles_x = 0, tiles_y = 0;
     uint32_t* d_lut = nullptr;     // dst_h * dst_w
@@ -74,6 +99,8 @@ struct ti_ctx {
     cudaStream_t stream = nullptr;
     std::string err;
     uint64_t launches = 0;
+    int ctas_per_sm = 0;
+    bool force_generic_rectify = false;  // tests: exercise the generic tiled / direct kernels
     ti::CameraSlot cams[TI_MAX_CAMERAS];
     // host pipeline (ti_ingest_host)
     cudaStream_t s_h2d = nullptr, s_d2h = nullptr, s_exec = nullptr;

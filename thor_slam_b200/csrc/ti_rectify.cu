@@ -148,6 +148,128 @@ __global__ void __launch_bounds__(RT_THREADS) rectify_tile_kernel(const __grid_c
     }
 }
 
+// ---- fast mono kernel ("v2") --------------------------------------------------------------------
+// One CTA = 128 x 32 output pixels; a warp owns 4 rows, a thread 4 consecutive pixels per row.
+//  * LUT entries are tile-relative: bits 31..16 = shared-memory byte address of the top tap pair,
+//    bits 10..6 = fy, bits 4..0 = fx (built at upload, see ti_upload_rectify_map).
+//  * The source box is staged twice per row: copy A as is, copy B shifted by one byte, so that the
+//    pair (p[x0], p[x0+1]) is always one 2-byte-aligned LDS.U16 whatever the parity of x0; the pair
+//    one source row below is +M2_ROW_BYTES (an immediate).  With 4 pixels per thread the lanes of a
+//    warp read consecutive 32-bit words of a copy: no bank conflicts.
+//  * blend: top/bot = dp2a((32-fx, fx), pair); out = ((32-fy)*top + fy*bot + 512) >> 10, evaluated
+//    as byte 2 of 64*(fy*(bot-top) + 32*top + 512) so that no shift is needed before packing.
+struct Rect2JobDev {
+    const uint8_t* src;
+    uint8_t* dst;
+    uint64_t src_stride, dst_stride;
+    const uint32_t* lut2;
+    const TileBox2* boxes2;
+    int tiles_x, n_tiles;
+    int dst_w, dst_h, src_w, src_h;
+    uint32_t tile_begin;
+};
+
+struct Rect2Params {
+    Rect2JobDev job[MAX_RECT_JOBS];
+    uint32_t tiles_per_set;
+    int n_jobs;
+    int n_batch;
+};
+
+__device__ __forceinline__ uint32_t lds_u16(const uint8_t* p) { return *reinterpret_cast<const uint16_t*>(p); }
+
+__device__ __forceinline__ uint32_t ld_src_u32(const void* p) {
+#ifdef TI_EMULATE
+    return *reinterpret_cast<const uint32_t*>(ti_emu::check_align(p, 4));
+#else
+    uint32_t r;
+    asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(r) : "l"(p));
+    return r;
+#endif
+}
+
+__device__ __forceinline__ uint32_t blend64(uint32_t e, const uint8_t* smem) {
+    const uint8_t* tap = smem + (e >> 16);
+    const uint32_t pt = lds_u16(tap), pb = lds_u16(tap + M2_ROW_BYTES);
+    const uint32_t fx = e & 31u;
+    const uint32_t aw = fx * 65535u + 32u;  // (32 - fx) | fx << 16
+    const uint32_t top = __dp2a_lo(aw, pt, 0u), bot = __dp2a_lo(aw, pb, 0u);
+    const uint32_t g = e & (31u << 6);      // 64 * fy
+    return g * (bot - top) + (top * 2048u + 32768u);  // 64 * S; result pixel = byte 2
+}
+
+__global__ void __launch_bounds__(M2_THREADS, 6) rectify_mono_kernel(const __grid_constant__ Rect2Params P) {
+    TI_DYNAMIC_SMEM(uint8_t, smem);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid < M2_ZERO_BYTES / 16) reinterpret_cast<uint4*>(smem)[tid] = make_uint4(0u, 0u, 0u, 0u);
+    // work item = (frame b, job j, tile): walked with a stride of gridDim.x, decoded incrementally
+    // (no divisions: every per-tile scalar instruction costs 1/16 instruction per pixel)
+    uint32_t r = blockIdx.x, b = 0;
+    int j = 0;
+    const int vc = tid & 15, row0 = tid >> 4;  // staging role: 16-byte column vc of rows row0, row0+16, ...
+    while (true) {
+        while (r >= P.tiles_per_set) { r -= P.tiles_per_set; ++b; j = 0; }
+        if (b >= (uint32_t)P.n_batch) break;
+        while (j + 1 < P.n_jobs && r >= P.job[j + 1].tile_begin) ++j;
+        const Rect2JobDev& J = P.job[j];
+        const uint32_t tile = r - J.tile_begin;
+        TileBox2 box;
+        {
+            const uint4 raw = *reinterpret_cast<const uint4*>(J.boxes2 + tile);
+            box.c0 = (int16_t)(raw.x & 0xFFFF); box.y0 = (int16_t)(raw.x >> 16);
+            box.nvec = (int16_t)(raw.y & 0xFFFF); box.rows = (int16_t)(raw.y >> 16);
+            box.u0 = (int16_t)(raw.z & 0xFFFF); box.v0 = (int16_t)(raw.z >> 16);
+        }
+
+        // (1) LUT: 4 rows x 4 px per thread, issued before the staging loads
+        const uint32_t* lp = J.lut2 + (size_t)tile * (M2_TW * M2_TH) + (warp * 4) * M2_TW + lane * 4;
+        uint4 l[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) l[q] = ld_keep_u4(lp + q * M2_TW);
+
+        // (2) stage rows [y0, y0 + rows) x columns [c0, c0 + 16 * nvec): copy A and copy B
+        if (vc < box.nvec) {
+            const int gx = box.c0 + (vc << 4);
+            const bool col_in = gx >= 0 && gx < J.src_w;   // gx is a multiple of 16 and src_w % 16 == 0
+            const bool col_left = gx == -16;                // copy B of the left-border vector needs p[0]
+            const bool has_next = gx + 16 < J.src_w;
+            const uint8_t* g = J.src + (uint64_t)b * J.src_stride + (int64_t)(box.y0 + row0) * J.src_w + gx;
+            uint8_t* d = smem + M2_ZERO_BYTES + row0 * M2_ROW_BYTES + (vc << 4);
+            for (int row = row0; row < box.rows; row += 16, g += (size_t)16 * J.src_w, d += 16 * M2_ROW_BYTES) {
+                const int gy = box.y0 + row;
+                const bool row_in = gy >= 0 && gy < J.src_h;
+                uint4 a = make_uint4(0u, 0u, 0u, 0u);
+                uint32_t nx = 0u;
+                if (row_in && col_in) {
+                    a = ld_src_u4(g);
+                    if (has_next) nx = ld_src_u32(g + 16);
+                } else if (row_in && col_left) {
+                    nx = ld_src_u32(g + 16);
+                }
+                *reinterpret_cast<uint4*>(d) = a;
+                *reinterpret_cast<uint4*>(d + M2_COPY_BYTES) =
+                    make_uint4(__funnelshift_r(a.x, a.y, 8), __funnelshift_r(a.y, a.z, 8), __funnelshift_r(a.z, a.w, 8),
+                               __funnelshift_r(a.w, nx, 8));
+            }
+        }
+        __syncthreads();
+
+        // (3) taps + blend + packed store
+        const int u = box.u0 + lane * 4, v = box.v0 + warp * 4;
+        uint8_t* dp = J.dst + (uint64_t)b * J.dst_stride + (size_t)v * J.dst_w + u;
+        const int live_rows = u < J.dst_w ? J.dst_h - v : 0;  // rows of this thread that exist in the image
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const uint32_t s0 = blend64(l[q].x, smem), s1 = blend64(l[q].y, smem);
+            const uint32_t s2 = blend64(l[q].z, smem), s3 = blend64(l[q].w, smem);
+            const uint32_t lo = __byte_perm(s0, s1, 0x0062), hi = __byte_perm(s2, s3, 0x0062);
+            if (q < live_rows) st_stream_u1(dp + (size_t)q * J.dst_w, __byte_perm(lo, hi, 0x5410));
+        }
+        __syncthreads();
+        r += gridDim.x;
+    }
+}
+
 // ---- direct kernel -----------------------------------------------------------------------------
 enum DirectMode { DM_MONO = 0, DM_BGR_TO_RGB = 1, DM_BGR_TO_GRAY = 2, DM_NV12_TO_RGB = 3 };
 
@@ -252,7 +374,8 @@ static int launch_tiled(ti_ctx* ctx, RectParams& P, size_t smem_bytes) {
 int launch_rectify(ti_ctx* ctx, const RectifyJob* jobs, int n_jobs, int n_batch) {
     if (n_jobs <= 0 || n_batch <= 0) return TI_OK;
     RectParams P1{}, P3{};  // tiled launches for 1-channel and 3-channel sources
-    size_t smem1 = 0, smem3 = 0;
+    Rect2Params P2{};       // fast mono launch
+    size_t smem1 = 0, smem3 = 0, smem2 = 0;
     for (int i = 0; i < n_jobs; ++i) {
         const RectifyJob& J = jobs[i];
         if (J.camera < 0 || J.camera >= TI_MAX_CAMERAS || !ctx->cams[J.camera].has_map)
@@ -269,6 +392,20 @@ int launch_rectify(ti_ctx* ctx, const RectifyJob* jobs, int n_jobs, int n_batch)
         const bool tiled_ok = (mode == DM_MONO || mode == DM_BGR_TO_RGB) && (C.src_w * ch) % 16 == 0 && C.dst_w % 8 == 0 &&
                               ((uintptr_t)J.src % 16 == 0) && (J.src_stride % 16 == 0) && ((uintptr_t)J.dst % 8 == 0) &&
                               (J.dst_stride % 8 == 0) && need <= (size_t)RT_MAX_SMEM;
+        const bool fast_ok = mode == DM_MONO && C.has_fast_mono && C.dst_w % 4 == 0 && ((uintptr_t)J.src % 16 == 0) &&
+                             (J.src_stride % 16 == 0) && ((uintptr_t)J.dst % 4 == 0) && (J.dst_stride % 4 == 0) &&
+                             P2.n_jobs < MAX_RECT_JOBS && !ctx->force_generic_rectify;
+        if (fast_ok) {
+            Rect2JobDev D{};
+            D.src = J.src; D.dst = J.dst; D.src_stride = J.src_stride; D.dst_stride = J.dst_stride;
+            D.lut2 = C.d_lut2; D.boxes2 = C.d_boxes2; D.tiles_x = C.tiles2_x; D.n_tiles = C.tiles2_x * C.tiles2_y;
+            D.dst_w = C.dst_w; D.dst_h = C.dst_h; D.src_w = C.src_w; D.src_h = C.src_h;
+            D.tile_begin = P2.tiles_per_set;
+            P2.tiles_per_set += (uint32_t)D.n_tiles;
+            P2.job[P2.n_jobs++] = D;
+            smem2 = std::max(smem2, (size_t)M2_ZERO_BYTES + (size_t)std::max(C.rows2_max, 2) * M2_ROW_BYTES);
+            continue;
+        }
         RectParams& P = ch == 1 ? P1 : P3;
         if (!tiled_ok || P.n_jobs == MAX_RECT_JOBS) {
             DirectJob D{J.src, J.dst, J.src_stride, J.dst_stride, C.d_lut, lut_pitch, C.dst_w, C.dst_h, C.src_w, C.src_h, mode};
@@ -287,7 +424,24 @@ int launch_rectify(ti_ctx* ctx, const RectifyJob* jobs, int n_jobs, int n_batch)
         size_t& smem = ch == 1 ? smem1 : smem3;
         smem = std::max(smem, need);
     }
-    P1.n_batch = P3.n_batch = n_batch;
+    P1.n_batch = P3.n_batch = P2.n_batch = n_batch;
+    if (P2.n_jobs) {
+        const uint64_t total = (uint64_t)P2.tiles_per_set * n_batch;
+#ifndef TI_EMULATE
+        static bool configured = false;
+        if (!configured) {
+            TI_CUDA(ctx, cudaFuncSetAttribute(rectify_mono_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                              M2_ZERO_BYTES + M2_MAX_ROWS * M2_ROW_BYTES));
+            configured = true;
+        }
+#endif
+        int per_sm = (int)std::min<size_t>(6, (size_t)(224 * 1024) / (smem2 + 1024));
+        per_sm = std::max(per_sm, 1);
+        if (ctx->ctas_per_sm > 0) per_sm = ctx->ctas_per_sm;
+        const int grid = (int)std::min<uint64_t>(total, (uint64_t)ctx->sm_count * per_sm);
+        TI_LAUNCH(rectify_mono_kernel, grid, M2_THREADS, smem2, ctx->stream, P2);
+        TI_CHECK_LAUNCH(ctx);
+    }
     int rc = launch_tiled<1>(ctx, P1, smem1);
     if (rc != TI_OK) return rc;
     return launch_tiled<3>(ctx, P3, smem3);

@@ -47,6 +47,7 @@ SIGNATURES: dict[str, tuple] = {
     "ti_set_stream": (C.c_int, [C.c_void_p, C.c_void_p]),
     "ti_sync": (C.c_int, [C.c_void_p]),
     "ti_launch_count": (C.c_uint64, [C.c_void_p]),
+    "ti_set_option": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
     "ti_device_sm_count": (C.c_int, [C.c_void_p]),
     "ti_upload_rectify_map": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "ti_upload_projection": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]),

@@ -111,6 +111,13 @@ class IngestContext:
     def sync(self) -> None:
         self._check(self.lib.ti_sync(self._h))
 
+    OPT_FORCE_GENERIC_RECTIFY = 1
+    OPT_CTAS_PER_SM = 2
+
+    def set_option(self, option: int, value: int) -> None:
+        """Tuning / test switches of the library; results never depend on them."""
+        self._check(self.lib.ti_set_option(self._h, option, value))
+
     @property
     def launch_count(self) -> int:
         return int(self.lib.ti_launch_count(self._h))

@@ -1,0 +1,116 @@
+#!/usr/bin/env python
+"""Kernel micro-benchmarks on one GPU (CUDA events, inputs >> L2): one line per kernel / variant.
+
+    python tools/kbench.py [--batch 32] [--iters 20]
+
+Prints achieved GB/s on the ALGORITHMIC bytes of each kernel and the
+fraction of MEASURED_PEAKS.json hbm_gbs.  Development tool; bench.py is the judged benchmark.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import sys
+from pathlib import Path
+
+import numpy as np
+import torch
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+from thor_slam_b200.camera.synthetic import SyntheticCameraConfig, SyntheticCameraSource, make_depth  # noqa: E402
+from thor_slam_b200.ingest import formats as F  # noqa: E402
+from thor_slam_b200.ingest.calib import body_T_camera, stereo_rectify_maps  # noqa: E402
+from thor_slam_b200.ingest.context import IngestContext, StreamSpec  # noqa: E402
+
+
+def timeit(fn, iters: int, warm: int = 3) -> float:
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters  # ms
+
+
+def main() -> None:
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--batch", type=int, default=32)
+    ap.add_argument("--iters", type=int, default=20)
+    ap.add_argument("--only", default="")
+    args = ap.parse_args()
+    peak = 6454.3
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        peak = float(json.loads(p.read_text())["hbm_gbs"])
+    torch.cuda.set_device(0)
+    ctx = IngestContext(0)
+    ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+    W, H, B = 1280, 800, args.batch
+    rows = []
+
+    def report(name: str, ms: float, algo_bytes: float, px: float) -> None:
+        gbs = algo_bytes / (ms * 1e-3) / 1e9
+        rows.append((name, ms, gbs, gbs / peak, px / (ms * 1e-3) / 1e9))
+        print(f"{name:44s} {ms:9.4f} ms  {gbs:8.1f} GB/s  frac {gbs / peak:6.3f}  {px / (ms * 1e-3) / 1e9:8.2f} GPix/s", flush=True)
+
+    rng = np.random.default_rng(0)
+    src = SyntheticCameraSource(SyntheticCameraConfig(name="oak0", resolution=(W, H), pool=2, enable_rgbd=False))
+    maps = stereo_rectify_maps(src.get_intrinsics(), src.get_extrinsics(), (W, H))
+    NS = 8
+    for cam in range(NS):
+        ctx.upload_rectify_map(cam, *maps[cam % 2], (W, H))
+    frames = [torch.from_numpy(np.stack([src._pool[b % 2][s % 2] for b in range(B)])).cuda() for s in range(NS)]
+    outs = [torch.empty_like(f) for f in frames]
+    specs = [StreamSpec(F.KIND_RECTIFY, frames[s], outs[s], F.MONO8, F.MONO8, camera=s) for s in range(NS)]
+    px = NS * B * W * H
+
+    if not args.only or "rect" in args.only:
+        for per_sm in (0, 2, 3, 4, 5, 6, 8):
+            ctx.set_option(ctx.OPT_CTAS_PER_SM, per_sm)
+            report(f"rectify mono fast  ctas/sm={per_sm or 'auto'}", timeit(lambda: ctx.ingest(specs), args.iters), 2 * px, px)
+        ctx.set_option(ctx.OPT_CTAS_PER_SM, 0)
+        ctx.set_option(ctx.OPT_FORCE_GENERIC_RECTIFY, 1)
+        report("rectify mono generic (v1 tiled)", timeit(lambda: ctx.ingest(specs), max(3, args.iters // 4)), 2 * px, px)
+        ctx.set_option(ctx.OPT_FORCE_GENERIC_RECTIFY, 0)
+        # plain device copy of the same bytes = what "1.0" looks like for this traffic
+        report("torch copy_ (same bytes)", timeit(lambda: [o.copy_(f) for o, f in zip(outs, frames)], args.iters), 2 * px, px)
+
+    if not args.only or "bp" in args.only:
+        intr = src.get_intrinsics()[0]
+        m = body_T_camera(None, src.get_extrinsics()[0].to_4x4_matrix(), "rdf")
+        ND = 4
+        for cam in range(ND):
+            ctx.upload_projection(cam, intr.matrix, m, (W, H))
+        d2 = np.stack([make_depth(rng, W, H) for _ in range(2)]).view(np.int16)
+        depth = [torch.from_numpy(d2).cuda().view(torch.uint16).repeat((B + 1) // 2, 1, 1)[:B].contiguous() for _ in range(ND)]
+        xyz = [torch.empty((B, H, W, 3), dtype=torch.float32, device="cuda") for _ in range(ND)]
+        mask = [torch.empty((B, H, W), dtype=torch.uint8, device="cuda") for _ in range(ND)]
+        cnt = [torch.zeros((B,), dtype=torch.int32, device="cuda") for _ in range(ND)]
+        bspecs = [StreamSpec(F.KIND_BACKPROJECT, depth[i], xyz[i], F.DEPTH16, F.XYZ32F, camera=i, mask=mask[i], count=cnt[i]) for i in range(ND)]
+        dpx = ND * B * W * H
+        report("backproject depth->xyz+mask+count", timeit(lambda: ctx.ingest(bspecs), args.iters), 15 * dpx, dpx)
+        report("torch copy_ xyz (24 B/px traffic)", timeit(lambda: [xyz[i].copy_(xyz[(i + 1) % ND]) for i in range(ND)], args.iters), 24 * dpx, dpx)
+        del xyz, mask, depth
+
+    if not args.only or "conv" in args.only:
+        CW, CH, NB = 1920, 1080, max(2, B // 4)
+        bgr = torch.randint(0, 256, (NB, CH, CW, 3), dtype=torch.uint8, device="cuda")
+        rgb = torch.empty_like(bgr)
+        gray = torch.empty((NB, CH, CW), dtype=torch.uint8, device="cuda")
+        nv = torch.randint(0, 256, (NB, CH * 3 // 2, CW), dtype=torch.uint8, device="cuda")
+        cpx = NB * CW * CH
+        report("convert bgr8->rgb8 1080p", timeit(lambda: ctx.convert(bgr, rgb, "bgr8", "rgb8", CW, CH), args.iters), 6 * cpx, cpx)
+        report("convert bgr8->mono8 1080p", timeit(lambda: ctx.convert(bgr, gray, "bgr8", "mono8", CW, CH), args.iters), 4 * cpx, cpx)
+        report("convert nv12->rgb8 1080p", timeit(lambda: ctx.convert(nv, rgb, "nv12", "rgb8", CW, CH), args.iters), 4.5 * cpx, cpx)
+        report("convert nv12->mono8 1080p", timeit(lambda: ctx.convert(nv, gray, "nv12", "mono8", CW, CH), args.iters), 2 * cpx, cpx)
+        report("torch copy_ bgr (6 B/px)", timeit(lambda: rgb.copy_(bgr), args.iters), 6 * cpx, cpx)
+    ctx.close()
+
+
+if __name__ == "__main__":
+    main()
