@@ -195,6 +195,8 @@ int ti_upload_rectify_map(ti_ctx* ctx, int camera, int dst_w, int dst_h, int src
     // entry = off << 16 | fy << 6 | fx ; off = byte address in shared memory of the (2-byte aligned)
     // pair (src[y0][x0], src[y0][x0+1]): copy A holds the row as is (pairs with even x0 - c0), copy B
     // holds it shifted by one byte (odd x0 - c0); the pair one row below sits M2_ROW_BYTES further.
+    // Within a tile row the entries are permuted so that lane L of a warp finds the entries of
+    // pixels L, L+32, L+64, L+96 in one 128-bit word (lanes then read consecutive source bytes).
     // Pixels with no tap inside the image point at the zero block with fx = fy = 0.
     if (src_w % 16 == 0) {
         const int t2x = (dst_w + M2_TW - 1) / M2_TW, t2y = (dst_h + M2_TH - 1) / M2_TH;
@@ -219,7 +221,7 @@ int ti_upload_rectify_map(ti_ctx* ctx, int camera, int dst_w, int dst_h, int src
                 const int c0 = bx0 & ~15;  // floor to 16 (two's complement: -1 -> -16)
                 const int span = bx1 - c0;
                 const int rows = by1 - by0;
-                if (span > M2_COPY_BYTES || rows > M2_MAX_ROWS) { ok = false; break; }
+                if (span > M2_SPAN_BYTES || rows > M2_MAX_ROWS) { ok = false; break; }
                 B.c0 = (int16_t)c0; B.y0 = (int16_t)by0; B.nvec = (int16_t)((span + 15) / 16); B.rows = (int16_t)rows;
                 rows_max = std::max(rows_max, rows);
                 uint32_t* tl = lut2.data() + ((size_t)ty * t2x + tx) * M2_TW * M2_TH;
@@ -231,7 +233,8 @@ int ti_upload_rectify_map(ti_ctx* ctx, int camera, int dst_w, int dst_h, int src
                         const uint32_t fx = (e >> 22) & 31u, fy = e >> 27;
                         const int rel = x0 - c0;
                         const int off = M2_ZERO_BYTES + (y0 - by0) * M2_ROW_BYTES + ((rel & 1) ? M2_COPY_BYTES + rel - 1 : rel);
-                        tl[(size_t)(v - ty * M2_TH) * M2_TW + (u - tx * M2_TW)] = ((uint32_t)off << 16) | (fy << 6) | fx;
+                        const int lu = u - tx * M2_TW;  // lane (lu % 32) owns pixels lu, lu+32, lu+64, lu+96: stored as its uint4
+                        tl[(size_t)(v - ty * M2_TH) * M2_TW + (lu & 31) * 4 + (lu >> 5)] = ((uint32_t)off << 16) | (fy << 6) | fx;
                     }
             }
         if (ok) {

@@ -54,8 +54,9 @@ struct TileBox {  // source bounding box of one output tile, in source pixels
 constexpr int M2_TW = 128;
 constexpr int M2_TH = 32;
 constexpr int M2_THREADS = 256;
-constexpr int M2_ROW_BYTES = 512;   // per staged source row: 256 B copy A + 256 B copy B (shifted by one byte)
-constexpr int M2_COPY_BYTES = 256;
+constexpr int M2_ROW_BYTES = 624;   // per staged source row: copy A at +0, copy B (shifted by one byte) at +320; 624 = 112 (mod 128) spreads consecutive rows over the banks
+constexpr int M2_COPY_BYTES = 320;  // = 64 (mod 128): copy B sits 16 banks away from copy A
+constexpr int M2_SPAN_BYTES = 256;  // staged bytes per row and copy
 constexpr int M2_ZERO_BYTES = 128;  // always-zero block at the start of shared memory
 constexpr int M2_MAX_ROWS = 96;
 
@@ -199,6 +200,7 @@ __device__ __forceinline__ void st_stream_u4(void* p, uint4 v) { *reinterpret_ca
 __device__ __forceinline__ void st_stream_u2(void* p, uint2 v) { *reinterpret_cast<uint2*>(ti_emu::check_align(p, 8)) = v; }
 __device__ __forceinline__ void st_stream_u1(void* p, uint32_t v) { *reinterpret_cast<uint32_t*>(ti_emu::check_align(p, 4)) = v; }
 __device__ __forceinline__ uint4 ld_keep_u4(const void* p) { return *reinterpret_cast<const uint4*>(ti_emu::check_align(p, 16)); }
+__device__ __forceinline__ void st_stream_b8(void* p, uint32_t v) { *reinterpret_cast<uint8_t*>(p) = (uint8_t)v; }
 #elif defined(__CUDACC__)
 // ---- device helpers ------------------------------------------------------------------------
 // L2 eviction policies (createpolicy is not volatile: the compiler hoists / CSEs it).
@@ -241,6 +243,10 @@ __device__ __forceinline__ void st_stream_u2(void* p, uint2 v) {
 __device__ __forceinline__ void st_stream_u1(void* p, uint32_t v) {
     asm volatile("st.global.L1::no_allocate.L2::cache_hint.u32 [%0], %1, %2;" ::"l"(p), "r"(v),
                  "l"(policy_evict_first())
+                 : "memory");
+}
+__device__ __forceinline__ void st_stream_b8(void* p, uint32_t v) {
+    asm volatile("st.global.L1::no_allocate.L2::cache_hint.u8 [%0], %1, %2;" ::"l"(p), "r"(v), "l"(policy_evict_first())
                  : "memory");
 }
 // LUT reads: re-used by every frame of the batch -> prefer to keep in L2.

@@ -149,13 +149,14 @@ __global__ void __launch_bounds__(RT_THREADS) rectify_tile_kernel(const __grid_c
 }
 
 // ---- fast mono kernel ("v2") --------------------------------------------------------------------
-// One CTA = 128 x 32 output pixels; a warp owns 4 rows, a thread 4 consecutive pixels per row.
+// One CTA = 128 x 32 output pixels; a warp owns 4 rows; in a row, lane L owns pixels L, L+32, L+64, L+96.
 //  * LUT entries are tile-relative: bits 31..16 = shared-memory byte address of the top tap pair,
 //    bits 10..6 = fy, bits 4..0 = fx (built at upload, see ti_upload_rectify_map).
 //  * The source box is staged twice per row: copy A as is, copy B shifted by one byte, so that the
 //    pair (p[x0], p[x0+1]) is always one 2-byte-aligned LDS.U16 whatever the parity of x0; the pair
-//    one source row below is +M2_ROW_BYTES (an immediate).  With 4 pixels per thread the lanes of a
-//    warp read consecutive 32-bit words of a copy: no bank conflicts.
+//    one source row below is +M2_ROW_BYTES (an immediate).  The 32 lanes of a warp read ~32
+//    consecutive source bytes (<= 9 words of copy A, <= 9 words of copy B, the copies 16 banks
+//    apart): no bank conflicts; stores are one byte per lane, 32 contiguous bytes per warp.
 //  * blend: top/bot = dp2a((32-fx, fx), pair); out = ((32-fy)*top + fy*bot + 512) >> 10, evaluated
 //    as byte 2 of 64*(fy*(bot-top) + 32*top + 512) so that no shift is needed before packing.
 struct Rect2JobDev {
@@ -255,15 +256,21 @@ __global__ void __launch_bounds__(M2_THREADS, 6) rectify_mono_kernel(const __gri
         __syncthreads();
 
         // (3) taps + blend + packed store
-        const int u = box.u0 + lane * 4, v = box.v0 + warp * 4;
+        const int u = box.u0 + lane, v = box.v0 + warp * 4;
         uint8_t* dp = J.dst + (uint64_t)b * J.dst_stride + (size_t)v * J.dst_w + u;
-        const int live_rows = u < J.dst_w ? J.dst_h - v : 0;  // rows of this thread that exist in the image
+        const int live_rows = J.dst_h - v;            // rows of this warp that exist in the image
+        const int live_cols = (J.dst_w - u + 31) >> 5;  // of this lane's 4 pixels, how many exist
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
             const uint32_t s0 = blend64(l[q].x, smem), s1 = blend64(l[q].y, smem);
             const uint32_t s2 = blend64(l[q].z, smem), s3 = blend64(l[q].w, smem);
-            const uint32_t lo = __byte_perm(s0, s1, 0x0062), hi = __byte_perm(s2, s3, 0x0062);
-            if (q < live_rows) st_stream_u1(dp + (size_t)q * J.dst_w, __byte_perm(lo, hi, 0x5410));
+            if (q < live_rows) {
+                uint8_t* o = dp + (size_t)q * J.dst_w;
+                if (live_cols > 0) st_stream_b8(o, s0 >> 16);
+                if (live_cols > 1) st_stream_b8(o + 32, s1 >> 16);
+                if (live_cols > 2) st_stream_b8(o + 64, s2 >> 16);
+                if (live_cols > 3) st_stream_b8(o + 96, s3 >> 16);
+            }
         }
         __syncthreads();
         r += gridDim.x;
@@ -392,9 +399,8 @@ int launch_rectify(ti_ctx* ctx, const RectifyJob* jobs, int n_jobs, int n_batch)
         const bool tiled_ok = (mode == DM_MONO || mode == DM_BGR_TO_RGB) && (C.src_w * ch) % 16 == 0 && C.dst_w % 8 == 0 &&
                               ((uintptr_t)J.src % 16 == 0) && (J.src_stride % 16 == 0) && ((uintptr_t)J.dst % 8 == 0) &&
                               (J.dst_stride % 8 == 0) && need <= (size_t)RT_MAX_SMEM;
-        const bool fast_ok = mode == DM_MONO && C.has_fast_mono && C.dst_w % 4 == 0 && ((uintptr_t)J.src % 16 == 0) &&
-                             (J.src_stride % 16 == 0) && ((uintptr_t)J.dst % 4 == 0) && (J.dst_stride % 4 == 0) &&
-                             P2.n_jobs < MAX_RECT_JOBS && !ctx->force_generic_rectify;
+        const bool fast_ok = mode == DM_MONO && C.has_fast_mono && ((uintptr_t)J.src % 16 == 0) &&
+                             (J.src_stride % 16 == 0) && P2.n_jobs < MAX_RECT_JOBS && !ctx->force_generic_rectify;
         if (fast_ok) {
             Rect2JobDev D{};
             D.src = J.src; D.dst = J.dst; D.src_stride = J.src_stride; D.dst_stride = J.dst_stride;
