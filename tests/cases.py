@@ -76,14 +76,21 @@ def check_rectify(be, cam: int, mapx, mapy, s: str, d: str, src_w: int, src_h: i
         src[0] = rng.integers(0, 256, size=src[0].shape, dtype=np.uint8)
     dst = be.zeros((n, *F.frame_shape(F.fmt(d), dst_w, dst_h)), np.uint8)
     wants = [orc.remap_cv(np.ascontiguousarray(oracle_convert(src[i], s, d)), mapx, mapy) for i in range(n)]
-    for generic in (0, 1):  # fast mono kernel (when eligible) and the generic tiled / direct kernels
-        be.ctx.set_option(be.ctx.OPT_FORCE_GENERIC_RECTIFY, generic)
-        dst = be.zeros((n, *F.frame_shape(F.fmt(d), dst_w, dst_h)), np.uint8)
-        be.ctx.rectify(cam, be.dev(src), dst, s, d)
-        got = be.host(dst)
-        for i in range(n):
-            assert np.array_equal(got[i], wants[i]), f"rectify {s}->{d} generic={generic} frame {i}: {(got[i] != wants[i]).sum()} bytes differ"
-    be.ctx.set_option(be.ctx.OPT_FORCE_GENERIC_RECTIFY, 0)
+    # every kernel variant must give the same bytes: TMA-pipelined (tile height 32 and 16), thread-staged, generic
+    variants = [(3, 32), (3, 16), (2, 32), (1, 32)] if d == "mono8" and s in ("mono8", "nv12") else [(3, 32), (1, 32)]
+    try:
+        for variant, th in variants:
+            be.ctx.set_option(be.ctx.OPT_MONO_VARIANT, variant)
+            be.ctx.set_option(be.ctx.OPT_TMA_TILE_H, th)
+            dst = be.zeros((n, *F.frame_shape(F.fmt(d), dst_w, dst_h)), np.uint8)
+            be.ctx.rectify(cam, be.dev(src), dst, s, d)
+            got = be.host(dst)
+            for i in range(n):
+                assert np.array_equal(got[i], wants[i]), (
+                    f"rectify {s}->{d} variant={variant} th={th} frame {i}: {(got[i] != wants[i]).sum()} bytes differ")
+    finally:
+        be.ctx.set_option(be.ctx.OPT_MONO_VARIANT, 3)
+        be.ctx.set_option(be.ctx.OPT_TMA_TILE_H, 32)
     mask = be.zeros((dst_h, dst_w), np.uint8)
     be.ctx.get_valid_mask(cam, mask)
     assert np.array_equal(be.host(mask), orc.valid_mask(mapx, mapy, (src_w, src_h)))

@@ -88,8 +88,8 @@ void run_grid(dim3 grid, dim3 block, size_t dyn_smem_bytes, F&& body) {
         abort();
     }
     const unsigned nwarps = nthreads / 32;
-    std::vector<uint8_t> smem(dyn_smem_bytes + 16);
-    uint8_t* smem_aligned = smem.data() + ((16 - reinterpret_cast<uintptr_t>(smem.data()) % 16) % 16);
+    std::vector<uint8_t> smem(dyn_smem_bytes + 128);
+    uint8_t* smem_aligned = smem.data() + ((128 - reinterpret_cast<uintptr_t>(smem.data()) % 128) % 128);
     for (unsigned bz = 0; bz < grid.z; ++bz)
         for (unsigned by = 0; by < grid.y; ++by)
             for (unsigned bx = 0; bx < grid.x; ++bx) {

@@ -35,6 +35,10 @@ static void free_camera(CameraSlot& c) {
     if (c.d_valid) cudaFree(c.d_valid);
     if (c.d_lut2) cudaFree(c.d_lut2);
     if (c.d_boxes2) cudaFree(c.d_boxes2);
+    for (int k = 0; k < 2; ++k) {
+        if (c.d_lut3[k]) cudaFree(c.d_lut3[k]);
+        if (c.d_boxes3[k]) cudaFree(c.d_boxes3[k]);
+    }
     c = CameraSlot{};
 }
 
@@ -122,6 +126,12 @@ int ti_set_option(ti_ctx* ctx, int option, int value) {
     switch (option) {
         case TI_OPT_FORCE_GENERIC_RECTIFY: ctx->force_generic_rectify = value != 0; return TI_OK;
         case TI_OPT_CTAS_PER_SM: ctx->ctas_per_sm = value; return TI_OK;
+        case TI_OPT_MONO_VARIANT:
+            if (value < 1 || value > 3) return fail(ctx, TI_EINVAL, "mono variant must be 1, 2 or 3");
+            ctx->mono_variant = value; return TI_OK;
+        case TI_OPT_TMA_TILE_H:
+            if (value != 16 && value != 32) return fail(ctx, TI_EINVAL, "tile height must be 16 or 32");
+            ctx->tma_tile_h = value; return TI_OK;
         default: return fail(ctx, TI_EINVAL, "ti_set_option: unknown option %d", option);
     }
 }
@@ -148,6 +158,11 @@ int ti_upload_rectify_map(ti_ctx* ctx, int camera, int dst_w, int dst_h, int src
     if (C.d_boxes2) cudaFree(C.d_boxes2);
     C.d_lut = nullptr; C.d_boxes = nullptr; C.d_valid = nullptr; C.d_lut2 = nullptr; C.d_boxes2 = nullptr;
     C.has_map = false; C.has_fast_mono = false;
+    for (int k = 0; k < 2; ++k) {
+        if (C.d_lut3[k]) cudaFree(C.d_lut3[k]);
+        if (C.d_boxes3[k]) cudaFree(C.d_boxes3[k]);
+        C.d_lut3[k] = nullptr; C.d_boxes3[k] = nullptr; C.has_tma_mono[k] = false;
+    }
 
     const int tiles_x = (dst_w + RT_W - 1) / RT_W, tiles_y = (dst_h + RT_H - 1) / RT_H;
     const int lut_pitch = tiles_x * RT_W, lut_rows = tiles_y * RT_H;
@@ -245,6 +260,60 @@ int ti_upload_rectify_map(ti_ctx* ctx, int camera, int dst_w, int dst_h, int src
             C.tiles2_x = t2x; C.tiles2_y = t2y; C.rows2_max = rows_max;
             C.has_fast_mono = true;
         }
+    }
+
+    // ---- TMA-pipelined mono tables (TH = 16 and TH = 32) ----------------------------------------
+    // Two passes per tile height: the tap offsets embed the camera's rows_alloc (start of copy B),
+    // which is only known once every tile's box has been measured.
+    for (int k = 0; k < 2 && src_w % 16 == 0; ++k) {
+        const int TH = k == 0 ? 16 : 32;
+        const int t3x = (dst_w + M3_TW - 1) / M3_TW, t3y = (dst_h + TH - 1) / TH;
+        std::vector<TileBox2> boxes3((size_t)t3x * t3y);
+        bool ok = true;
+        int rows_max = 0;
+        auto for_tile = [&](int tx, int ty, auto&& fn) {
+            for (int v = ty * TH; v < std::min(dst_h, (ty + 1) * TH); ++v)
+                for (int u = tx * M3_TW; u < std::min(dst_w, (tx + 1) * M3_TW); ++u) {
+                    const uint32_t e = lut[(size_t)v * lut_pitch + u];
+                    if (e == LUT_OUTSIDE) continue;
+                    fn(u, v, (int)(e & LUT_COORD_MASK) - 1, (int)((e >> LUT_COORD_BITS) & LUT_COORD_MASK) - 1, (e >> 22) & 31u, e >> 27);
+                }
+        };
+        for (int ty = 0; ty < t3y && ok; ++ty)
+            for (int tx = 0; tx < t3x && ok; ++tx) {
+                int bx0 = 1 << 20, by0 = 1 << 20, bx1 = -(1 << 20), by1 = -(1 << 20);
+                for_tile(tx, ty, [&](int, int, int x0, int y0, uint32_t, uint32_t) {
+                    bx0 = std::min(bx0, x0); by0 = std::min(by0, y0); bx1 = std::max(bx1, x0 + 2); by1 = std::max(by1, y0 + 2);
+                });
+                TileBox2& B = boxes3[(size_t)ty * t3x + tx];
+                B = TileBox2{0, 0, 0, 0, (int16_t)(tx * M3_TW), (int16_t)(ty * TH), 0, 0};
+                if (bx1 <= bx0) continue;
+                const int c0 = bx0 & ~15;
+                if (bx1 - c0 > M3_MAX_SPAN || by1 - by0 > M3_MAX_ROWS) { ok = false; break; }
+                B.c0 = (int16_t)c0; B.y0 = (int16_t)by0; B.nvec = (int16_t)((bx1 - c0 + 15) / 16); B.rows = (int16_t)(by1 - by0);
+                rows_max = std::max(rows_max, by1 - by0);
+            }
+        if (!ok) continue;
+        const int rows_alloc = std::max(M3_BOX_ROWS, (rows_max + M3_BOX_ROWS - 1) / M3_BOX_ROWS * M3_BOX_ROWS);
+        std::vector<uint32_t> lut3((size_t)t3x * t3y * M3_TW * TH, 0u);
+        for (int ty = 0; ty < t3y; ++ty)
+            for (int tx = 0; tx < t3x; ++tx) {
+                const TileBox2& B = boxes3[(size_t)ty * t3x + tx];
+                uint32_t* tl = lut3.data() + ((size_t)ty * t3x + tx) * M3_TW * TH;
+                for_tile(tx, ty, [&](int u, int v, int x0, int y0, uint32_t fx, uint32_t fy) {
+                    const int rel = x0 - B.c0, row = y0 - B.y0;
+                    const int off = (rel & 1) ? 128 + (rows_alloc + row) * M3_PITCH + (rel - 1 + M3_B_SHIFT + 1)
+                                              : 128 + row * M3_PITCH + rel;
+                    const int lu = u - tx * M3_TW;
+                    tl[(size_t)(v - ty * TH) * M3_TW + (lu & 31) * 4 + (lu >> 5)] = ((uint32_t)off << 16) | (fy << 6) | fx;
+                });
+            }
+        TI_CUDA(ctx, cudaMalloc(&C.d_lut3[k], lut3.size() * sizeof(uint32_t)));
+        TI_CUDA(ctx, cudaMalloc(&C.d_boxes3[k], boxes3.size() * sizeof(TileBox2)));
+        TI_CUDA(ctx, cudaMemcpy(C.d_lut3[k], lut3.data(), lut3.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+        TI_CUDA(ctx, cudaMemcpy(C.d_boxes3[k], boxes3.data(), boxes3.size() * sizeof(TileBox2), cudaMemcpyHostToDevice));
+        C.tiles3_x[k] = t3x; C.tiles3_y[k] = t3y; C.rows3_alloc[k] = rows_alloc;
+        C.has_tma_mono[k] = true;
     }
     return TI_OK;
 }

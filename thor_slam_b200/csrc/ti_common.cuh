@@ -22,7 +22,7 @@
 #define TI_DEVICE_CODE 1
 #endif
 #define TI_LAUNCH(kernel, grid, block, smem, stream, ...) kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
-#define TI_DYNAMIC_SMEM(type, name) extern __shared__ __align__(16) type name[]
+#define TI_DYNAMIC_SMEM(type, name) extern __shared__ __align__(128) type name[]
 #endif
 
 namespace ti {
@@ -70,8 +70,27 @@ struct TileBox2 {
 };
 static_assert(sizeof(TileBox2) == 16, "TileBox2 is loaded as one 128-bit word");
 
+// TMA-pipelined mono path ("v3"): tiles of M3_TW x TH (TH = 16 or 32); per stage of shared memory
+//   [128 B zeros | copy A: rows_alloc x 256 B | copy B: rows_alloc x 256 B | LUT tile | 128 B header]
+// copy A row r = source bytes [c0, c0+256) of source row y0+r; copy B = [c0-63, c0+193) (one byte
+// of pixel shift for odd x0, 64 bytes = 16 banks of bank shift).  Rows are TMA boxes of 256 x 8.
+constexpr int M3_TW = 128;
+constexpr int M3_BOX_ROWS = 8;
+constexpr int M3_PITCH = 256;
+constexpr int M3_B_SHIFT = 63;     // copy B starts at source column c0 - 63
+constexpr int M3_MAX_SPAN = 192;
+constexpr int M3_MAX_ROWS = 96;
+constexpr int M3_CONSUMER_WARPS = 8;
+constexpr int M3_THREADS = (M3_CONSUMER_WARPS + 1) * 32;  // + 1 producer warp
+constexpr int M3_STAGES = 2;
+
 struct CameraSlot {
     // rectification
+    bool has_tma_mono[2] = {false, false};   // [0]: TH = 16, [1]: TH = 32
+    uint32_t* d_lut3[2] = {nullptr, nullptr};
+    TileBox2* d_boxes3[2] = {nullptr, nullptr};
+    int tiles3_x[2] = {0, 0}, tiles3_y[2] = {0, 0};
+    int rows3_alloc[2] = {0, 0};
     bool has_map = false;
     bool has_fast_mono = false;
     uint32_t* d_lut2 = nullptr;     // tiles * M2_TH * M2_TW, tile-major
@@ -101,6 +120,8 @@ struct ti_ctx {
     std::string err;
     uint64_t launches = 0;
     int ctas_per_sm = 0;
+    int mono_variant = 3;   // 3: TMA-pipelined kernel, 2: thread-staged kernel, 1: generic only
+    int tma_tile_h = 32;    // 16 or 32
     bool force_generic_rectify = false;  // tests: exercise the generic tiled / direct kernels
     ti::CameraSlot cams[TI_MAX_CAMERAS];
     // host pipeline (ti_ingest_host)

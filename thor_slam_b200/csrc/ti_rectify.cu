@@ -16,6 +16,7 @@
 // and for the two-stage conversions (BGR->gray, NV12->rgb) before remap.
 #include "ti_common.cuh"
 #include "ti_pixel.cuh"
+#include "ti_tma.cuh"
 
 namespace ti {
 
@@ -189,9 +190,10 @@ __device__ __forceinline__ uint32_t ld_src_u32(const void* p) {
 #endif
 }
 
+template <int ROW_PITCH = M3_PITCH>
 __device__ __forceinline__ uint32_t blend64(uint32_t e, const uint8_t* smem) {
     const uint8_t* tap = smem + (e >> 16);
-    const uint32_t pt = lds_u16(tap), pb = lds_u16(tap + M2_ROW_BYTES);
+    const uint32_t pt = lds_u16(tap), pb = lds_u16(tap + ROW_PITCH);
     const uint32_t fx = e & 31u;
     const uint32_t aw = fx * 65535u + 32u;  // (32 - fx) | fx << 16
     const uint32_t top = __dp2a_lo(aw, pt, 0u), bot = __dp2a_lo(aw, pb, 0u);
@@ -262,8 +264,8 @@ __global__ void __launch_bounds__(M2_THREADS, 6) rectify_mono_kernel(const __gri
         const int live_cols = (J.dst_w - u + 31) >> 5;  // of this lane's 4 pixels, how many exist
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-            const uint32_t s0 = blend64(l[q].x, smem), s1 = blend64(l[q].y, smem);
-            const uint32_t s2 = blend64(l[q].z, smem), s3 = blend64(l[q].w, smem);
+            const uint32_t s0 = blend64<M2_ROW_BYTES>(l[q].x, smem), s1 = blend64<M2_ROW_BYTES>(l[q].y, smem);
+            const uint32_t s2 = blend64<M2_ROW_BYTES>(l[q].z, smem), s3 = blend64<M2_ROW_BYTES>(l[q].w, smem);
             if (q < live_rows) {
                 uint8_t* o = dp + (size_t)q * J.dst_w;
                 if (live_cols > 0) st_stream_b8(o, s0 >> 16);
@@ -274,6 +276,130 @@ __global__ void __launch_bounds__(M2_THREADS, 6) rectify_mono_kernel(const __gri
         }
         __syncthreads();
         r += gridDim.x;
+    }
+}
+
+// ---- TMA-pipelined mono kernel ("v3") --------------------------------------------------------------
+// Persistent, warp-specialised: warp 8 (one lane) is the producer - per tile it reads the tile's
+// source box descriptor, issues the TMA loads of copy A / copy B (256 x 8 byte boxes; coordinates
+// outside the image read as zero = BORDER_CONSTANT 0) and of the tile's LUT (one bulk copy), and
+// writes a small header (destination pointer, live rows / columns); warps 0..7 are consumers - they
+// wait on the stage's `full` mbarrier, blend exactly as the v2 kernel (aligned pair taps + dp2a),
+// store, and arrive on the stage's `empty` mbarrier.  No __syncthreads in the steady state; the
+// producer runs M3_STAGES tiles ahead, so global-memory latency is off the consumers' critical path
+// and no thread spends instructions on staging.
+struct Rect3JobDev {
+    const uint32_t* lut3;
+    const TileBox2* boxes3;
+    uint8_t* dst;
+    uint64_t dst_stride;
+    int dst_w, dst_h;
+    int rows_alloc;
+    uint32_t tile_begin;
+};
+
+struct Rect3Params {
+    TiTensorMap map[MAX_RECT_JOBS];
+    Rect3JobDev job[MAX_RECT_JOBS];
+    uint32_t tiles_per_set;
+    int n_jobs;
+    int n_batch;
+    int rows_alloc_max;  // launch-wide: fixes where the LUT sits inside a stage
+};
+
+struct Stage3Header {  // 32 bytes, written by the producer, read by every consumer thread
+    uint64_t dst;      // address of output pixel (u0, v0) of frame b
+    int32_t dst_w;
+    int32_t live_rows;  // dst_h - v0
+    int32_t live_cols;  // dst_w - u0
+    int32_t pad[3];
+};
+
+template <int TH>
+__global__ void __launch_bounds__(M3_THREADS) rectify_mono_tma_kernel(const __grid_constant__ Rect3Params P) {
+    TI_DYNAMIC_SMEM(uint8_t, smem);
+    constexpr int ROWS_PER_WARP = TH / M3_CONSUMER_WARPS;
+    constexpr uint32_t LUT_BYTES = TH * M3_TW * 4;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t ab_bytes = 2u * (uint32_t)P.rows_alloc_max * M3_PITCH;
+    const uint32_t stage_bytes = 128u + ab_bytes + LUT_BYTES + 128u;
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem);          // [M3_STAGES]
+    uint64_t* empty = full + M3_STAGES;                            // [M3_STAGES]
+    uint8_t* stage0 = smem + 128;
+
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < M3_STAGES; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, M3_CONSUMER_WARPS); }
+        mbar_fence_init();
+    }
+    for (int s = 0; s < M3_STAGES; ++s)  // the always-zero block of every stage
+        if (tid < 8) reinterpret_cast<uint4*>(stage0 + (size_t)s * stage_bytes)[tid] = make_uint4(0u, 0u, 0u, 0u);
+    __syncthreads();
+
+    const uint64_t total = (uint64_t)P.tiles_per_set * P.n_batch;
+    if (warp == M3_CONSUMER_WARPS) {
+        // ------------------------------------------------ producer ---------------------------------
+        if (lane != 0) return;
+        uint32_t r = blockIdx.x, b = 0;
+        int j = 0, s = 0;
+        uint32_t phase = 0;
+        for (uint64_t t = blockIdx.x; t < total; t += gridDim.x, r += gridDim.x) {
+            while (r >= P.tiles_per_set) { r -= P.tiles_per_set; ++b; j = 0; }
+            while (j + 1 < P.n_jobs && r >= P.job[j + 1].tile_begin) ++j;
+            const Rect3JobDev& J = P.job[j];
+            const uint32_t tile = r - J.tile_begin;
+            const uint4 raw = *reinterpret_cast<const uint4*>(J.boxes3 + tile);
+            const int c0 = (int16_t)(raw.x & 0xFFFF), y0 = (int16_t)(raw.x >> 16);
+            const int rows = (int16_t)(raw.y >> 16);
+            const int u0 = (int16_t)(raw.z & 0xFFFF), v0 = (int16_t)(raw.z >> 16);
+            uint8_t* sb = stage0 + (size_t)s * stage_bytes;
+            mbar_wait(empty + s, phase ^ 1u);  // every consumer warp is done with this stage
+            const int nblk = (rows + M3_BOX_ROWS - 1) / M3_BOX_ROWS;
+            uint8_t* a = sb + 128;
+            uint8_t* bq = a + (size_t)J.rows_alloc * M3_PITCH;
+            for (int k = 0; k < nblk; ++k) {
+                tma_load_3d(a + k * (M3_BOX_ROWS * M3_PITCH), &P.map[j], c0, y0 + k * M3_BOX_ROWS, (int)b, full + s);
+                tma_load_3d(bq + k * (M3_BOX_ROWS * M3_PITCH), &P.map[j], c0 - M3_B_SHIFT, y0 + k * M3_BOX_ROWS, (int)b, full + s);
+            }
+            bulk_load_1d(sb + 128 + ab_bytes, J.lut3 + (size_t)tile * (TH * M3_TW), LUT_BYTES, full + s);
+            Stage3Header* h = reinterpret_cast<Stage3Header*>(sb + 128 + ab_bytes + LUT_BYTES);
+            h->dst = (uint64_t)(uintptr_t)(J.dst + (uint64_t)b * J.dst_stride + (size_t)v0 * J.dst_w + u0);
+            h->dst_w = J.dst_w;
+            h->live_rows = J.dst_h - v0;
+            h->live_cols = J.dst_w - u0;
+            mbar_arrive_expect_tx(full + s, (uint32_t)nblk * (2u * M3_BOX_ROWS * M3_PITCH) + LUT_BYTES);
+            if (++s == M3_STAGES) { s = 0; phase ^= 1u; }
+        }
+        return;
+    }
+    // ---------------------------------------------------- consumers ---------------------------------
+    int s = 0;
+    uint32_t phase = 0;
+    for (uint64_t t = blockIdx.x; t < total; t += gridDim.x) {
+        const uint8_t* sb = stage0 + (size_t)s * stage_bytes;
+        mbar_wait(full + s, phase);
+        const uint4 hraw = *reinterpret_cast<const uint4*>(sb + 128 + ab_bytes + LUT_BYTES);
+        const uint32_t live_cols = *reinterpret_cast<const uint32_t*>(sb + 128 + ab_bytes + LUT_BYTES + 16);
+        uint8_t* dp = reinterpret_cast<uint8_t*>((uintptr_t)(((uint64_t)hraw.y << 32) | hraw.x));
+        const int dst_w = (int)hraw.z, live_rows = (int)hraw.w - warp * ROWS_PER_WARP;
+        const int my_cols = ((int)live_cols - lane + 31) >> 5;  // of this lane's 4 pixels, how many exist
+        const uint4* lut_s = reinterpret_cast<const uint4*>(sb + 128 + ab_bytes) + (warp * ROWS_PER_WARP) * 32 + lane;
+        dp += (size_t)(warp * ROWS_PER_WARP) * dst_w + lane;
+#pragma unroll
+        for (int q = 0; q < ROWS_PER_WARP; ++q) {
+            const uint4 e = lut_s[q * 32];
+            const uint32_t s0 = blend64(e.x, sb), s1 = blend64(e.y, sb), s2 = blend64(e.z, sb), s3 = blend64(e.w, sb);
+            if (q < live_rows) {
+                uint8_t* o = dp + (size_t)q * dst_w;
+                if (my_cols > 0) st_stream_b8(o, s0 >> 16);
+                if (my_cols > 1) st_stream_b8(o + 32, s1 >> 16);
+                if (my_cols > 2) st_stream_b8(o + 64, s2 >> 16);
+                if (my_cols > 3) st_stream_b8(o + 96, s3 >> 16);
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(empty + s);
+        if (++s == M3_STAGES) { s = 0; phase ^= 1u; }
     }
 }
 
@@ -381,7 +507,9 @@ static int launch_tiled(ti_ctx* ctx, RectParams& P, size_t smem_bytes) {
 int launch_rectify(ti_ctx* ctx, const RectifyJob* jobs, int n_jobs, int n_batch) {
     if (n_jobs <= 0 || n_batch <= 0) return TI_OK;
     RectParams P1{}, P3{};  // tiled launches for 1-channel and 3-channel sources
-    Rect2Params P2{};       // fast mono launch
+    Rect2Params P2{};       // fast mono launch (v2: thread-staged)
+    Rect3Params PT{};       // fast mono launch (v3: TMA-pipelined)
+    const int thk = ctx->tma_tile_h == 16 ? 0 : 1;
     size_t smem1 = 0, smem3 = 0, smem2 = 0;
     for (int i = 0; i < n_jobs; ++i) {
         const RectifyJob& J = jobs[i];
@@ -400,7 +528,22 @@ int launch_rectify(ti_ctx* ctx, const RectifyJob* jobs, int n_jobs, int n_batch)
                               ((uintptr_t)J.src % 16 == 0) && (J.src_stride % 16 == 0) && ((uintptr_t)J.dst % 8 == 0) &&
                               (J.dst_stride % 8 == 0) && need <= (size_t)RT_MAX_SMEM;
         const bool fast_ok = mode == DM_MONO && C.has_fast_mono && ((uintptr_t)J.src % 16 == 0) &&
-                             (J.src_stride % 16 == 0) && P2.n_jobs < MAX_RECT_JOBS && !ctx->force_generic_rectify;
+                             (J.src_stride % 16 == 0) && P2.n_jobs < MAX_RECT_JOBS && !ctx->force_generic_rectify && ctx->mono_variant >= 2;
+        const bool tma_ok = mode == DM_MONO && C.has_tma_mono[thk] && ((uintptr_t)J.src % 16 == 0) && (J.src_stride % 16 == 0) &&
+                            PT.n_jobs < MAX_RECT_JOBS && !ctx->force_generic_rectify && ctx->mono_variant == 3;
+        if (tma_ok) {
+            const int rc = tma_encode_u8_3d(ctx, &PT.map[PT.n_jobs], J.src, C.src_w, C.src_h, n_batch, (uint64_t)C.src_w,
+                                            J.src_stride, M3_PITCH, M3_BOX_ROWS);
+            if (rc != TI_OK) return rc;
+            Rect3JobDev D{};
+            D.lut3 = C.d_lut3[thk]; D.boxes3 = C.d_boxes3[thk]; D.dst = J.dst; D.dst_stride = J.dst_stride;
+            D.dst_w = C.dst_w; D.dst_h = C.dst_h; D.rows_alloc = C.rows3_alloc[thk];
+            D.tile_begin = PT.tiles_per_set;
+            PT.tiles_per_set += (uint32_t)(C.tiles3_x[thk] * C.tiles3_y[thk]);
+            PT.rows_alloc_max = std::max(PT.rows_alloc_max, C.rows3_alloc[thk]);
+            PT.job[PT.n_jobs++] = D;
+            continue;
+        }
         if (fast_ok) {
             Rect2JobDev D{};
             D.src = J.src; D.dst = J.dst; D.src_stride = J.src_stride; D.dst_stride = J.dst_stride;
@@ -430,7 +573,26 @@ int launch_rectify(ti_ctx* ctx, const RectifyJob* jobs, int n_jobs, int n_batch)
         size_t& smem = ch == 1 ? smem1 : smem3;
         smem = std::max(smem, need);
     }
-    P1.n_batch = P3.n_batch = P2.n_batch = n_batch;
+    P1.n_batch = P3.n_batch = P2.n_batch = PT.n_batch = n_batch;
+    if (PT.n_jobs) {
+        const int TH = thk == 0 ? 16 : 32;
+        const size_t stage = 128 + 2 * (size_t)PT.rows_alloc_max * M3_PITCH + (size_t)TH * M3_TW * 4 + 128;
+        const size_t smem = 128 + M3_STAGES * stage;
+        const uint64_t total = (uint64_t)PT.tiles_per_set * n_batch;
+#ifndef TI_EMULATE
+        if (thk == 0)
+            TI_CUDA(ctx, cudaFuncSetAttribute(rectify_mono_tma_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        else
+            TI_CUDA(ctx, cudaFuncSetAttribute(rectify_mono_tma_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+#endif
+        int per_sm = (int)std::min<size_t>(7, (size_t)(226 * 1024) / (smem + 1024));  // 7 x 288 threads <= 2048
+        per_sm = std::max(per_sm, 1);
+        if (ctx->ctas_per_sm > 0) per_sm = ctx->ctas_per_sm;
+        const int grid = (int)std::min<uint64_t>(total, (uint64_t)ctx->sm_count * per_sm);
+        if (thk == 0) TI_LAUNCH(rectify_mono_tma_kernel<16>, grid, M3_THREADS, smem, ctx->stream, PT);
+        else TI_LAUNCH(rectify_mono_tma_kernel<32>, grid, M3_THREADS, smem, ctx->stream, PT);
+        TI_CHECK_LAUNCH(ctx);
+    }
     if (P2.n_jobs) {
         const uint64_t total = (uint64_t)P2.tiles_per_set * n_batch;
 #ifndef TI_EMULATE

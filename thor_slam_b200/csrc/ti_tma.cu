@@ -1,0 +1,54 @@
+// Host side of the TMA wrappers: tensor-map encoding through the driver entry point
+// (cuTensorMapEncodeTiled is fetched with cudaGetDriverEntryPoint, so libcuda is not linked).
+#include "ti_tma.cuh"
+
+namespace ti {
+
+#ifdef TI_EMULATE
+int tma_encode_u8_3d(ti_ctx*, TiTensorMap* out, const void* base, int w, int h, int n, uint64_t pitch_y, uint64_t pitch_z,
+                     int box_x, int box_y) {
+    *out = TiTensorMap{};
+    out->base = static_cast<const uint8_t*>(base);
+    out->dim[0] = w; out->dim[1] = h; out->dim[2] = n;
+    out->stride[0] = 1; out->stride[1] = (int64_t)pitch_y; out->stride[2] = (int64_t)pitch_z;
+    out->box[0] = box_x; out->box[1] = box_y; out->box[2] = 1;
+    return TI_OK;
+}
+#else
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encoder() {
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+int tma_encode_u8_3d(ti_ctx* ctx, TiTensorMap* out, const void* base, int w, int h, int n, uint64_t pitch_y, uint64_t pitch_z,
+                     int box_x, int box_y) {
+    EncodeTiledFn fn = encoder();
+    if (!fn) return fail(ctx, TI_ECUDA, "cuTensorMapEncodeTiled is not available from this driver");
+    if (((uintptr_t)base % 16) || (pitch_y % 16) || (pitch_z % 16) || (box_x % 16) || box_x > 256 || box_y > 256)
+        return fail(ctx, TI_EINVAL, "tensor map: base/pitches/box must be 16-byte multiples, box <= 256");
+    const cuuint64_t dims[3] = {(cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)std::max(n, 1)};
+    const cuuint64_t strides[2] = {pitch_y, pitch_z ? pitch_z : pitch_y * (uint64_t)h};
+    const cuuint32_t box[3] = {(cuuint32_t)box_x, (cuuint32_t)box_y, 1u};
+    const cuuint32_t estr[3] = {1u, 1u, 1u};
+    const CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<void*>(base), dims, strides, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(ctx, TI_ECUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+    return TI_OK;
+}
+#endif
+
+}  // namespace ti

@@ -113,6 +113,8 @@ class IngestContext:
 
     OPT_FORCE_GENERIC_RECTIFY = 1
     OPT_CTAS_PER_SM = 2
+    OPT_MONO_VARIANT = 3
+    OPT_TMA_TILE_H = 4
 
     def set_option(self, option: int, value: int) -> None:
         """Tuning / test switches of the library; results never depend on them."""

@@ -70,10 +70,15 @@ def main() -> None:
     px = NS * B * W * H
 
     if not args.only or "rect" in args.only:
-        for per_sm in (0, 2, 3, 4, 5, 6, 8):
-            ctx.set_option(ctx.OPT_CTAS_PER_SM, per_sm)
-            report(f"rectify mono fast  ctas/sm={per_sm or 'auto'}", timeit(lambda: ctx.ingest(specs), args.iters), 2 * px, px)
+        for variant, th, sweep in ((3, 32, (0, 1, 2, 3)), (3, 16, (0, 2, 3, 4, 5)), (2, 32, (0,))):
+            ctx.set_option(ctx.OPT_MONO_VARIANT, variant)
+            ctx.set_option(ctx.OPT_TMA_TILE_H, th)
+            for per_sm in sweep:
+                ctx.set_option(ctx.OPT_CTAS_PER_SM, per_sm)
+                report(f"rectify mono v{variant} th={th} ctas/sm={per_sm or 'auto'}", timeit(lambda: ctx.ingest(specs), args.iters), 2 * px, px)
         ctx.set_option(ctx.OPT_CTAS_PER_SM, 0)
+        ctx.set_option(ctx.OPT_MONO_VARIANT, 3)
+        ctx.set_option(ctx.OPT_TMA_TILE_H, 32)
         ctx.set_option(ctx.OPT_FORCE_GENERIC_RECTIFY, 1)
         report("rectify mono generic (v1 tiled)", timeit(lambda: ctx.ingest(specs), max(3, args.iters // 4)), 2 * px, px)
         ctx.set_option(ctx.OPT_FORCE_GENERIC_RECTIFY, 0)
