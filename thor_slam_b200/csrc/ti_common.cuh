@@ -77,12 +77,12 @@ static_assert(sizeof(TileBox2) == 16, "TileBox2 is loaded as one 128-bit word");
 constexpr int M3_TW = 128;
 constexpr int M3_BOX_ROWS = 8;
 constexpr int M3_PITCH = 256;
-constexpr int M3_B_SHIFT = 63;     // copy B starts at source column c0 - 63
+constexpr int M3_B_SHIFT = 63;     // copy B[i] = source column c0 - 63 + i (built in shared memory from copy A)
 constexpr int M3_MAX_SPAN = 192;
 constexpr int M3_MAX_ROWS = 96;
 constexpr int M3_CONSUMER_WARPS = 8;
 constexpr int M3_THREADS = (M3_CONSUMER_WARPS + 1) * 32;  // + 1 producer warp
-constexpr int M3_STAGES = 2;
+constexpr int M3_STAGES = 3;
 
 struct CameraSlot {
     // rectification
@@ -120,6 +120,7 @@ struct ti_ctx {
     std::string err;
     uint64_t launches = 0;
     int ctas_per_sm = 0;
+    int debug = 0;
     int mono_variant = 3;   // 3: TMA-pipelined kernel, 2: thread-staged kernel, 1: generic only
     int tma_tile_h = 32;    // 16 or 32
     bool force_generic_rectify = false;  // tests: exercise the generic tiled / direct kernels

@@ -280,14 +280,17 @@ __global__ void __launch_bounds__(M2_THREADS, 6) rectify_mono_kernel(const __gri
 }
 
 // ---- TMA-pipelined mono kernel ("v3") --------------------------------------------------------------
-// Persistent, warp-specialised: warp 8 (one lane) is the producer - per tile it reads the tile's
-// source box descriptor, issues the TMA loads of copy A / copy B (256 x 8 byte boxes; coordinates
-// outside the image read as zero = BORDER_CONSTANT 0) and of the tile's LUT (one bulk copy), and
-// writes a small header (destination pointer, live rows / columns); warps 0..7 are consumers - they
-// wait on the stage's `full` mbarrier, blend exactly as the v2 kernel (aligned pair taps + dp2a),
-// store, and arrive on the stage's `empty` mbarrier.  No __syncthreads in the steady state; the
-// producer runs M3_STAGES tiles ahead, so global-memory latency is off the consumers' critical path
-// and no thread spends instructions on staging.
+// Persistent, warp-specialised, M3_STAGES-deep shared-memory ring, no __syncthreads in steady state.
+//  * Warp 8 is the producer.  Lane 0 reads the next tile's source-box descriptor and issues the TMA
+//    loads of copy A (256 x 8 byte boxes; coordinates outside the image read as zero = BORDER_CONSTANT
+//    0) and of the tile's LUT (one bulk copy) onto the stage's `raw` mbarrier - one tile ahead.
+//    TMA boxes must start on 16-byte boundaries, so the one-byte-shifted copy B cannot come from TMA:
+//    the 32 producer lanes build it from copy A in shared memory (LDS.128, funnel shifts, STS.128),
+//    lane 0 adds a small header (destination pointer, live rows / columns), and all 32 lanes arrive
+//    on the stage's `full` mbarrier.
+//  * Warps 0..7 are consumers: wait `full`, blend exactly as the v2 kernel (aligned pair taps +
+//    dp2a), store, arrive on `empty`.  They spend no instruction on staging and never wait on global
+//    memory.
 struct Rect3JobDev {
     const uint32_t* lut3;
     const TileBox2* boxes3;
@@ -305,14 +308,13 @@ struct Rect3Params {
     int n_jobs;
     int n_batch;
     int rows_alloc_max;  // launch-wide: fixes where the LUT sits inside a stage
+    int debug;           // bring-up switches (TI_OPT_DEBUG); 0 in production
 };
 
-struct Stage3Header {  // 32 bytes, written by the producer, read by every consumer thread
-    uint64_t dst;      // address of output pixel (u0, v0) of frame b
-    int32_t dst_w;
-    int32_t live_rows;  // dst_h - v0
-    int32_t live_cols;  // dst_w - u0
-    int32_t pad[3];
+struct Tile3 {  // what the producer keeps about a tile between "issue" and "finish"
+    uint64_t dst;
+    int dst_w, live_rows, live_cols;
+    int rows, nvec, rows_alloc;
 };
 
 template <int TH>
@@ -323,13 +325,18 @@ __global__ void __launch_bounds__(M3_THREADS) rectify_mono_tma_kernel(const __gr
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t ab_bytes = 2u * (uint32_t)P.rows_alloc_max * M3_PITCH;
     const uint32_t stage_bytes = 128u + ab_bytes + LUT_BYTES + 128u;
-    uint64_t* full = reinterpret_cast<uint64_t*>(smem);          // [M3_STAGES]
-    uint64_t* empty = full + M3_STAGES;                            // [M3_STAGES]
+    uint64_t* raw = reinterpret_cast<uint64_t*>(smem);  // [M3_STAGES] TMA landed
+    uint64_t* full = raw + M3_STAGES;                    // [M3_STAGES] copy B + header ready
+    uint64_t* empty = full + M3_STAGES;                  // [M3_STAGES] consumers done
     uint8_t* stage0 = smem + 128;
 
     if (tid == 0) {
 #pragma unroll
-        for (int s = 0; s < M3_STAGES; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, M3_CONSUMER_WARPS); }
+        for (int s = 0; s < M3_STAGES; ++s) {
+            mbar_init(raw + s, 1);
+            mbar_init(full + s, 32);
+            mbar_init(empty + s, M3_CONSUMER_WARPS);
+        }
         mbar_fence_init();
     }
     for (int s = 0; s < M3_STAGES; ++s)  // the always-zero block of every stage
@@ -337,47 +344,80 @@ __global__ void __launch_bounds__(M3_THREADS) rectify_mono_tma_kernel(const __gr
     __syncthreads();
 
     const uint64_t total = (uint64_t)P.tiles_per_set * P.n_batch;
+    const uint32_t n_mine = total > blockIdx.x ? (uint32_t)((total - blockIdx.x + gridDim.x - 1) / gridDim.x) : 0u;
+
     if (warp == M3_CONSUMER_WARPS) {
-        // ------------------------------------------------ producer ---------------------------------
-        if (lane != 0) return;
-        uint32_t r = blockIdx.x, b = 0;
-        int j = 0, s = 0;
-        uint32_t phase = 0;
-        for (uint64_t t = blockIdx.x; t < total; t += gridDim.x, r += gridDim.x) {
+        // ------------------------------------------------ producer warp ------------------------------
+        uint32_t r = blockIdx.x, b = 0;  // decode state of the next tile to issue (lane 0 only)
+        int j = 0;
+        Tile3 inflight[2];               // tile i sits in inflight[i & 1] between issue(i) and finish(i)
+
+        auto issue = [&](uint32_t i) {   // lane 0: TMA copy A + LUT of this CTA's i-th tile into stage i % S
             while (r >= P.tiles_per_set) { r -= P.tiles_per_set; ++b; j = 0; }
             while (j + 1 < P.n_jobs && r >= P.job[j + 1].tile_begin) ++j;
             const Rect3JobDev& J = P.job[j];
             const uint32_t tile = r - J.tile_begin;
-            const uint4 raw = *reinterpret_cast<const uint4*>(J.boxes3 + tile);
-            const int c0 = (int16_t)(raw.x & 0xFFFF), y0 = (int16_t)(raw.x >> 16);
-            const int rows = (int16_t)(raw.y >> 16);
-            const int u0 = (int16_t)(raw.z & 0xFFFF), v0 = (int16_t)(raw.z >> 16);
+            const uint4 bx = *reinterpret_cast<const uint4*>(J.boxes3 + tile);
+            const int c0 = (int16_t)(bx.x & 0xFFFF), y0 = (int16_t)(bx.x >> 16);
+            const int nvec = (int16_t)(bx.y & 0xFFFF), rows = (int16_t)(bx.y >> 16);
+            const int u0 = (int16_t)(bx.z & 0xFFFF), v0 = (int16_t)(bx.z >> 16);
+            const int s = (int)(i % M3_STAGES);
+            const uint32_t use = i / M3_STAGES;  // how many times this stage has been used before
             uint8_t* sb = stage0 + (size_t)s * stage_bytes;
-            mbar_wait(empty + s, phase ^ 1u);  // every consumer warp is done with this stage
+            mbar_wait(empty + s, (use & 1u) ^ 1u);  // consumers have released the stage's previous tile
             const int nblk = (rows + M3_BOX_ROWS - 1) / M3_BOX_ROWS;
-            uint8_t* a = sb + 128;
-            uint8_t* bq = a + (size_t)J.rows_alloc * M3_PITCH;
-            for (int k = 0; k < nblk; ++k) {
-                tma_load_3d(a + k * (M3_BOX_ROWS * M3_PITCH), &P.map[j], c0, y0 + k * M3_BOX_ROWS, (int)b, full + s);
-                tma_load_3d(bq + k * (M3_BOX_ROWS * M3_PITCH), &P.map[j], c0 - M3_B_SHIFT, y0 + k * M3_BOX_ROWS, (int)b, full + s);
+            for (int k = 0; k < nblk; ++k)
+                tma_load_3d(sb + 128 + k * (M3_BOX_ROWS * M3_PITCH), &P.map[j], c0, y0 + k * M3_BOX_ROWS, (int)b, raw + s);
+            bulk_load_1d(sb + 128 + ab_bytes, J.lut3 + (size_t)tile * (TH * M3_TW), LUT_BYTES, raw + s);
+            mbar_arrive_expect_tx(raw + s, (uint32_t)nblk * (M3_BOX_ROWS * M3_PITCH) + LUT_BYTES);
+            Tile3& T = inflight[i & 1];
+            T.dst = (uint64_t)(uintptr_t)(J.dst + (uint64_t)b * J.dst_stride + (size_t)v0 * J.dst_w + u0);
+            T.dst_w = J.dst_w; T.live_rows = J.dst_h - v0; T.live_cols = J.dst_w - u0;
+            T.rows = rows; T.nvec = nvec; T.rows_alloc = J.rows_alloc;
+            r += gridDim.x;
+        };
+
+        if (lane == 0 && n_mine > 0) issue(0);
+        for (uint32_t i = 0; i < n_mine; ++i) {
+            if (lane == 0 && i + 1 < n_mine) issue(i + 1);  // keep one tile of loads in flight
+            const int s = (int)(i % M3_STAGES);
+            const uint32_t use = i / M3_STAGES;
+            uint8_t* sb = stage0 + (size_t)s * stage_bytes;
+            const Tile3& T = inflight[i & 1];
+            const int rows = __shfl_sync(0xFFFFFFFFu, T.rows, 0), nvec = __shfl_sync(0xFFFFFFFFu, T.nvec, 0);
+            const int rows_alloc = __shfl_sync(0xFFFFFFFFu, T.rows_alloc, 0);
+            mbar_wait(raw + s, use & 1u);
+            // copy B[64 + i] = A[i + 1]: odd-x0 pairs become 2-byte aligned, 16 banks away from copy A
+            const uint8_t* a = sb + 128;
+            uint8_t* bq = sb + 128 + (size_t)rows_alloc * M3_PITCH + 64;
+            const int n = rows * 16;
+            for (int v = lane; v < n; v += 32) {
+                const int row = v >> 4, vc = v & 15;
+                if (vc < nvec) {
+                    const uint8_t* ap = a + row * M3_PITCH + (vc << 4);
+                    const uint4 x = *reinterpret_cast<const uint4*>(ap);
+                    const uint32_t nx = vc < 15 ? *reinterpret_cast<const uint32_t*>(ap + 16) : 0u;
+                    if (vc < 12)
+                        *reinterpret_cast<uint4*>(bq + row * M3_PITCH + (vc << 4)) =
+                            make_uint4(__funnelshift_r(x.x, x.y, 8), __funnelshift_r(x.y, x.z, 8),
+                                       __funnelshift_r(x.z, x.w, 8), __funnelshift_r(x.w, nx, 8));
+                }
             }
-            bulk_load_1d(sb + 128 + ab_bytes, J.lut3 + (size_t)tile * (TH * M3_TW), LUT_BYTES, full + s);
-            Stage3Header* h = reinterpret_cast<Stage3Header*>(sb + 128 + ab_bytes + LUT_BYTES);
-            h->dst = (uint64_t)(uintptr_t)(J.dst + (uint64_t)b * J.dst_stride + (size_t)v0 * J.dst_w + u0);
-            h->dst_w = J.dst_w;
-            h->live_rows = J.dst_h - v0;
-            h->live_cols = J.dst_w - u0;
-            mbar_arrive_expect_tx(full + s, (uint32_t)nblk * (2u * M3_BOX_ROWS * M3_PITCH) + LUT_BYTES);
-            if (++s == M3_STAGES) { s = 0; phase ^= 1u; }
+            if (lane == 0) {
+                uint4* h = reinterpret_cast<uint4*>(sb + 128 + ab_bytes + LUT_BYTES);
+                h[0] = make_uint4((uint32_t)(T.dst & 0xFFFFFFFFu), (uint32_t)(T.dst >> 32), (uint32_t)T.dst_w, (uint32_t)T.live_rows);
+                h[1] = make_uint4((uint32_t)T.live_cols, 0u, 0u, 0u);
+            }
+            mbar_arrive(full + s);  // all 32 lanes: each releases its own shared-memory writes
         }
         return;
     }
     // ---------------------------------------------------- consumers ---------------------------------
-    int s = 0;
-    uint32_t phase = 0;
-    for (uint64_t t = blockIdx.x; t < total; t += gridDim.x) {
+    for (uint32_t i = 0; i < n_mine; ++i) {
+        const int s = (int)(i % M3_STAGES);
+        const uint32_t use = i / M3_STAGES;
         const uint8_t* sb = stage0 + (size_t)s * stage_bytes;
-        mbar_wait(full + s, phase);
+        mbar_wait(full + s, use & 1u);
         const uint4 hraw = *reinterpret_cast<const uint4*>(sb + 128 + ab_bytes + LUT_BYTES);
         const uint32_t live_cols = *reinterpret_cast<const uint32_t*>(sb + 128 + ab_bytes + LUT_BYTES + 16);
         uint8_t* dp = reinterpret_cast<uint8_t*>((uintptr_t)(((uint64_t)hraw.y << 32) | hraw.x));
@@ -399,7 +439,6 @@ __global__ void __launch_bounds__(M3_THREADS) rectify_mono_tma_kernel(const __gr
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(empty + s);
-        if (++s == M3_STAGES) { s = 0; phase ^= 1u; }
     }
 }
 
@@ -574,6 +613,7 @@ int launch_rectify(ti_ctx* ctx, const RectifyJob* jobs, int n_jobs, int n_batch)
         smem = std::max(smem, need);
     }
     P1.n_batch = P3.n_batch = P2.n_batch = PT.n_batch = n_batch;
+    PT.debug = ctx->debug;
     if (PT.n_jobs) {
         const int TH = thk == 0 ? 16 : 32;
         const size_t stage = 128 + 2 * (size_t)PT.rows_alloc_max * M3_PITCH + (size_t)TH * M3_TW * 4 + 128;

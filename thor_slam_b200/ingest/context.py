@@ -115,6 +115,7 @@ class IngestContext:
     OPT_CTAS_PER_SM = 2
     OPT_MONO_VARIANT = 3
     OPT_TMA_TILE_H = 4
+    OPT_DEBUG = 5
 
     def set_option(self, option: int, value: int) -> None:
         """Tuning / test switches of the library; results never depend on them."""
