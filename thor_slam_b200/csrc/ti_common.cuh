@@ -81,7 +81,8 @@ constexpr int M3_B_SHIFT = 63;     // copy B[i] = source column c0 - 63 + i (bui
 constexpr int M3_MAX_SPAN = 192;
 constexpr int M3_MAX_ROWS = 96;
 constexpr int M3_CONSUMER_WARPS = 8;
-constexpr int M3_THREADS = (M3_CONSUMER_WARPS + 1) * 32;  // + 1 producer warp
+constexpr int M3_PRODUCER_WARPS = 2;
+constexpr int M3_THREADS = (M3_CONSUMER_WARPS + M3_PRODUCER_WARPS) * 32;
 constexpr int M3_STAGES = 3;
 
 struct CameraSlot {

@@ -311,10 +311,13 @@ struct Rect3Params {
     int debug;           // bring-up switches (TI_OPT_DEBUG); 0 in production
 };
 
-struct Tile3 {  // what the producer keeps about a tile between "issue" and "finish"
-    uint64_t dst;
-    int dst_w, live_rows, live_cols;
-    int rows, nvec, rows_alloc;
+struct Stage3Header {  // 48 bytes at the end of a stage: written by the TMA-issuing lane, read by everybody
+    uint32_t dst_lo, dst_hi;  // address of output pixel (u0, v0) of frame b
+    int32_t dst_w;
+    int32_t live_rows;        // dst_h - v0
+    int32_t live_cols;        // dst_w - u0
+    int32_t rows, nvec, rows_alloc;  // staged source rows, 16-byte vectors per row, start of copy B (rows)
+    int32_t pad[4];
 };
 
 template <int TH>
@@ -325,8 +328,9 @@ __global__ void __launch_bounds__(M3_THREADS) rectify_mono_tma_kernel(const __gr
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t ab_bytes = 2u * (uint32_t)P.rows_alloc_max * M3_PITCH;
     const uint32_t stage_bytes = 128u + ab_bytes + LUT_BYTES + 128u;
+    const uint32_t hdr_off = 128u + ab_bytes + LUT_BYTES;
     uint64_t* raw = reinterpret_cast<uint64_t*>(smem);  // [M3_STAGES] TMA landed
-    uint64_t* full = raw + M3_STAGES;                    // [M3_STAGES] copy B + header ready
+    uint64_t* full = raw + M3_STAGES;                    // [M3_STAGES] copy B ready
     uint64_t* empty = full + M3_STAGES;                  // [M3_STAGES] consumers done
     uint8_t* stage0 = smem + 128;
 
@@ -334,7 +338,7 @@ __global__ void __launch_bounds__(M3_THREADS) rectify_mono_tma_kernel(const __gr
 #pragma unroll
         for (int s = 0; s < M3_STAGES; ++s) {
             mbar_init(raw + s, 1);
-            mbar_init(full + s, 32);
+            mbar_init(full + s, M3_PRODUCER_WARPS * 32);
             mbar_init(empty + s, M3_CONSUMER_WARPS);
         }
         mbar_fence_init();
@@ -346,21 +350,24 @@ __global__ void __launch_bounds__(M3_THREADS) rectify_mono_tma_kernel(const __gr
     const uint64_t total = (uint64_t)P.tiles_per_set * P.n_batch;
     const uint32_t n_mine = total > blockIdx.x ? (uint32_t)((total - blockIdx.x + gridDim.x - 1) / gridDim.x) : 0u;
 
-    if (warp == M3_CONSUMER_WARPS) {
-        // ------------------------------------------------ producer warp ------------------------------
-        uint32_t r = blockIdx.x, b = 0;  // decode state of the next tile to issue (lane 0 only)
+    if (warp >= M3_CONSUMER_WARPS) {
+        // ------------------------------------------------ producer warps -----------------------------
+        const int ptid = tid - M3_CONSUMER_WARPS * 32;  // 0 .. 32 * M3_PRODUCER_WARPS - 1
+        // issuer state (ptid == 0): decode position of the next tile to issue and its prefetched box
+        uint32_t r = blockIdx.x, b = 0;
         int j = 0;
-        Tile3 inflight[2];               // tile i sits in inflight[i & 1] between issue(i) and finish(i)
-
-        auto issue = [&](uint32_t i) {   // lane 0: TMA copy A + LUT of this CTA's i-th tile into stage i % S
+        uint4 box = make_uint4(0u, 0u, 0u, 0u);
+        auto decode_and_prefetch = [&]() {
             while (r >= P.tiles_per_set) { r -= P.tiles_per_set; ++b; j = 0; }
             while (j + 1 < P.n_jobs && r >= P.job[j + 1].tile_begin) ++j;
+            box = *reinterpret_cast<const uint4*>(P.job[j].boxes3 + (r - P.job[j].tile_begin));
+        };
+        auto issue = [&](uint32_t i) {  // TMA copy A + LUT of this CTA's i-th tile into stage i % S
             const Rect3JobDev& J = P.job[j];
             const uint32_t tile = r - J.tile_begin;
-            const uint4 bx = *reinterpret_cast<const uint4*>(J.boxes3 + tile);
-            const int c0 = (int16_t)(bx.x & 0xFFFF), y0 = (int16_t)(bx.x >> 16);
-            const int nvec = (int16_t)(bx.y & 0xFFFF), rows = (int16_t)(bx.y >> 16);
-            const int u0 = (int16_t)(bx.z & 0xFFFF), v0 = (int16_t)(bx.z >> 16);
+            const int c0 = (int16_t)(box.x & 0xFFFF), y0 = (int16_t)(box.x >> 16);
+            const int nvec = (int16_t)(box.y & 0xFFFF), rows = (int16_t)(box.y >> 16);
+            const int u0 = (int16_t)(box.z & 0xFFFF), v0 = (int16_t)(box.z >> 16);
             const int s = (int)(i % M3_STAGES);
             const uint32_t use = i / M3_STAGES;  // how many times this stage has been used before
             uint8_t* sb = stage0 + (size_t)s * stage_bytes;
@@ -369,46 +376,55 @@ __global__ void __launch_bounds__(M3_THREADS) rectify_mono_tma_kernel(const __gr
             for (int k = 0; k < nblk; ++k)
                 tma_load_3d(sb + 128 + k * (M3_BOX_ROWS * M3_PITCH), &P.map[j], c0, y0 + k * M3_BOX_ROWS, (int)b, raw + s);
             bulk_load_1d(sb + 128 + ab_bytes, J.lut3 + (size_t)tile * (TH * M3_TW), LUT_BYTES, raw + s);
-            mbar_arrive_expect_tx(raw + s, (uint32_t)nblk * (M3_BOX_ROWS * M3_PITCH) + LUT_BYTES);
-            Tile3& T = inflight[i & 1];
-            T.dst = (uint64_t)(uintptr_t)(J.dst + (uint64_t)b * J.dst_stride + (size_t)v0 * J.dst_w + u0);
-            T.dst_w = J.dst_w; T.live_rows = J.dst_h - v0; T.live_cols = J.dst_w - u0;
-            T.rows = rows; T.nvec = nvec; T.rows_alloc = J.rows_alloc;
+            const uint64_t dst = (uint64_t)(uintptr_t)(J.dst + (uint64_t)b * J.dst_stride + (size_t)v0 * J.dst_w + u0);
+            uint4* h = reinterpret_cast<uint4*>(sb + hdr_off);
+            h[0] = make_uint4((uint32_t)(dst & 0xFFFFFFFFu), (uint32_t)(dst >> 32), (uint32_t)J.dst_w, (uint32_t)(J.dst_h - v0));
+            h[1] = make_uint4((uint32_t)(J.dst_w - u0), (uint32_t)rows, (uint32_t)nvec, (uint32_t)J.rows_alloc);
+            mbar_arrive_expect_tx(raw + s, (uint32_t)nblk * (M3_BOX_ROWS * M3_PITCH) + LUT_BYTES);  // releases the header too
             r += gridDim.x;
         };
 
-        if (lane == 0 && n_mine > 0) issue(0);
+        if (ptid == 0 && n_mine > 0) { decode_and_prefetch(); issue(0); if (n_mine > 1) decode_and_prefetch(); }
+        const int vc = ptid & 15, r0 = ptid >> 4;  // builder role: column vector vc of rows r0, r0 + RSTEP, ...
+        constexpr int RSTEP = M3_PRODUCER_WARPS * 2;
         for (uint32_t i = 0; i < n_mine; ++i) {
-            if (lane == 0 && i + 1 < n_mine) issue(i + 1);  // keep one tile of loads in flight
+            if (ptid == 0 && i + 1 < n_mine) {  // keep one tile of loads in flight, one box descriptor ahead of that
+                issue(i + 1);
+                if (i + 2 < n_mine) decode_and_prefetch();
+            }
             const int s = (int)(i % M3_STAGES);
             const uint32_t use = i / M3_STAGES;
             uint8_t* sb = stage0 + (size_t)s * stage_bytes;
-            const Tile3& T = inflight[i & 1];
-            const int rows = __shfl_sync(0xFFFFFFFFu, T.rows, 0), nvec = __shfl_sync(0xFFFFFFFFu, T.nvec, 0);
-            const int rows_alloc = __shfl_sync(0xFFFFFFFFu, T.rows_alloc, 0);
             mbar_wait(raw + s, use & 1u);
+            const uint4 h1 = *reinterpret_cast<const uint4*>(sb + hdr_off + 16);
+            const int rows = (int)h1.y, nvec = (int)h1.z, rows_alloc = (int)h1.w;
             // copy B[64 + i] = A[i + 1]: odd-x0 pairs become 2-byte aligned, 16 banks away from copy A
-            const uint8_t* a = sb + 128;
-            uint8_t* bq = sb + 128 + (size_t)rows_alloc * M3_PITCH + 64;
-            const int n = rows * 16;
-            for (int v = lane; v < n; v += 32) {
-                const int row = v >> 4, vc = v & 15;
-                if (vc < nvec) {
-                    const uint8_t* ap = a + row * M3_PITCH + (vc << 4);
+            if (vc < nvec && vc < 12) {
+                const uint8_t* ap = sb + 128 + r0 * M3_PITCH + (vc << 4);
+                uint8_t* bp = sb + 128 + (size_t)rows_alloc * M3_PITCH + 64 + r0 * M3_PITCH + (vc << 4);
+                int row = r0;
+                for (; row + 3 * RSTEP < rows; row += 4 * RSTEP, ap += 4 * RSTEP * M3_PITCH, bp += 4 * RSTEP * M3_PITCH) {
+                    uint4 x[4];
+                    uint32_t nx[4];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        x[k] = *reinterpret_cast<const uint4*>(ap + k * RSTEP * M3_PITCH);
+                        nx[k] = *reinterpret_cast<const uint32_t*>(ap + k * RSTEP * M3_PITCH + 16);
+                    }
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        *reinterpret_cast<uint4*>(bp + k * RSTEP * M3_PITCH) =
+                            make_uint4(__funnelshift_r(x[k].x, x[k].y, 8), __funnelshift_r(x[k].y, x[k].z, 8),
+                                       __funnelshift_r(x[k].z, x[k].w, 8), __funnelshift_r(x[k].w, nx[k], 8));
+                }
+                for (; row < rows; row += RSTEP, ap += RSTEP * M3_PITCH, bp += RSTEP * M3_PITCH) {
                     const uint4 x = *reinterpret_cast<const uint4*>(ap);
-                    const uint32_t nx = vc < 15 ? *reinterpret_cast<const uint32_t*>(ap + 16) : 0u;
-                    if (vc < 12)
-                        *reinterpret_cast<uint4*>(bq + row * M3_PITCH + (vc << 4)) =
-                            make_uint4(__funnelshift_r(x.x, x.y, 8), __funnelshift_r(x.y, x.z, 8),
-                                       __funnelshift_r(x.z, x.w, 8), __funnelshift_r(x.w, nx, 8));
+                    const uint32_t nx = *reinterpret_cast<const uint32_t*>(ap + 16);
+                    *reinterpret_cast<uint4*>(bp) = make_uint4(__funnelshift_r(x.x, x.y, 8), __funnelshift_r(x.y, x.z, 8),
+                                                               __funnelshift_r(x.z, x.w, 8), __funnelshift_r(x.w, nx, 8));
                 }
             }
-            if (lane == 0) {
-                uint4* h = reinterpret_cast<uint4*>(sb + 128 + ab_bytes + LUT_BYTES);
-                h[0] = make_uint4((uint32_t)(T.dst & 0xFFFFFFFFu), (uint32_t)(T.dst >> 32), (uint32_t)T.dst_w, (uint32_t)T.live_rows);
-                h[1] = make_uint4((uint32_t)T.live_cols, 0u, 0u, 0u);
-            }
-            mbar_arrive(full + s);  // all 32 lanes: each releases its own shared-memory writes
+            mbar_arrive(full + s);  // every producer thread: each releases its own shared-memory writes
         }
         return;
     }
@@ -418,8 +434,8 @@ __global__ void __launch_bounds__(M3_THREADS) rectify_mono_tma_kernel(const __gr
         const uint32_t use = i / M3_STAGES;
         const uint8_t* sb = stage0 + (size_t)s * stage_bytes;
         mbar_wait(full + s, use & 1u);
-        const uint4 hraw = *reinterpret_cast<const uint4*>(sb + 128 + ab_bytes + LUT_BYTES);
-        const uint32_t live_cols = *reinterpret_cast<const uint32_t*>(sb + 128 + ab_bytes + LUT_BYTES + 16);
+        const uint4 hraw = *reinterpret_cast<const uint4*>(sb + hdr_off);
+        const uint32_t live_cols = *reinterpret_cast<const uint32_t*>(sb + hdr_off + 16);
         uint8_t* dp = reinterpret_cast<uint8_t*>((uintptr_t)(((uint64_t)hraw.y << 32) | hraw.x));
         const int dst_w = (int)hraw.z, live_rows = (int)hraw.w - warp * ROWS_PER_WARP;
         const int my_cols = ((int)live_cols - lane + 31) >> 5;  // of this lane's 4 pixels, how many exist
@@ -625,7 +641,7 @@ int launch_rectify(ti_ctx* ctx, const RectifyJob* jobs, int n_jobs, int n_batch)
         else
             TI_CUDA(ctx, cudaFuncSetAttribute(rectify_mono_tma_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 #endif
-        int per_sm = (int)std::min<size_t>(7, (size_t)(226 * 1024) / (smem + 1024));  // 7 x 288 threads <= 2048
+        int per_sm = (int)std::min<size_t>(2048 / M3_THREADS, (size_t)(226 * 1024) / (smem + 1024));
         per_sm = std::max(per_sm, 1);
         if (ctx->ctas_per_sm > 0) per_sm = ctx->ctas_per_sm;
         const int grid = (int)std::min<uint64_t>(total, (uint64_t)ctx->sm_count * per_sm);
