@@ -67,7 +67,7 @@ def edge_maps(dst_w: int, dst_h: int) -> tuple[np.ndarray, np.ndarray]:
     return (xx * 1.13 - 13.3 + 0.05 * yy).astype(np.float32), (yy * 1.21 - 14.7 - 0.03 * xx).astype(np.float32)
 
 
-def check_rectify(be, cam: int, mapx, mapy, s: str, d: str, src_w: int, src_h: int, n: int = 2, seed: int = 1) -> None:
+def check_rectify(be, cam: int, mapx, mapy, s: str, d: str, src_w: int, src_h: int, n: int = 3, seed: int = 1) -> None:
     rng = np.random.default_rng(seed)
     dst_h, dst_w = mapx.shape
     be.ctx.upload_rectify_map(cam, mapx, mapy, (src_w, src_h))
@@ -77,11 +77,14 @@ def check_rectify(be, cam: int, mapx, mapy, s: str, d: str, src_w: int, src_h: i
     dst = be.zeros((n, *F.frame_shape(F.fmt(d), dst_w, dst_h)), np.uint8)
     wants = [orc.remap_cv(np.ascontiguousarray(oracle_convert(src[i], s, d)), mapx, mapy) for i in range(n)]
     # every kernel variant must give the same bytes: TMA-pipelined (tile height 32 and 16), thread-staged, generic
-    variants = [(3, 32), (3, 16), (2, 32), (1, 32)] if d == "mono8" and s in ("mono8", "nv12") else [(3, 32), (1, 32)]
+    # (the TMA kernel also with 1 and 2 frames of the batch per LUT fetch)
+    mono = d == "mono8" and s in ("mono8", "nv12")
+    variants = [(3, 32, 8), (3, 16, 2), (3, 32, 1), (2, 32, 8), (1, 32, 8)] if mono else [(3, 32, 8), (1, 32, 8)]
     try:
-        for variant, th in variants:
+        for variant, th, fpu in variants:
             be.ctx.set_option(be.ctx.OPT_MONO_VARIANT, variant)
             be.ctx.set_option(be.ctx.OPT_TMA_TILE_H, th)
+            be.ctx.set_option(be.ctx.OPT_FRAMES_PER_UNIT, fpu)
             dst = be.zeros((n, *F.frame_shape(F.fmt(d), dst_w, dst_h)), np.uint8)
             be.ctx.rectify(cam, be.dev(src), dst, s, d)
             got = be.host(dst)
@@ -91,6 +94,7 @@ def check_rectify(be, cam: int, mapx, mapy, s: str, d: str, src_w: int, src_h: i
     finally:
         be.ctx.set_option(be.ctx.OPT_MONO_VARIANT, 3)
         be.ctx.set_option(be.ctx.OPT_TMA_TILE_H, 32)
+        be.ctx.set_option(be.ctx.OPT_FRAMES_PER_UNIT, 8)
     mask = be.zeros((dst_h, dst_w), np.uint8)
     be.ctx.get_valid_mask(cam, mask)
     assert np.array_equal(be.host(mask), orc.valid_mask(mapx, mapy, (src_w, src_h)))

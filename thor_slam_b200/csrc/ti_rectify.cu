@@ -281,16 +281,20 @@ __global__ void __launch_bounds__(M2_THREADS, 6) rectify_mono_kernel(const __gri
 
 // ---- TMA-pipelined mono kernel ("v3") --------------------------------------------------------------
 // Persistent, warp-specialised, M3_STAGES-deep shared-memory ring, no __syncthreads in steady state.
-//  * Warp 8 is the producer.  Lane 0 reads the next tile's source-box descriptor and issues the TMA
-//    loads of copy A (256 x 8 byte boxes; coordinates outside the image read as zero = BORDER_CONSTANT
-//    0) and of the tile's LUT (one bulk copy) onto the stage's `raw` mbarrier - one tile ahead.
-//    TMA boxes must start on 16-byte boundaries, so the one-byte-shifted copy B cannot come from TMA:
-//    the 32 producer lanes build it from copy A in shared memory (LDS.128, funnel shifts, STS.128),
-//    lane 0 adds a small header (destination pointer, live rows / columns), and all 32 lanes arrive
-//    on the stage's `full` mbarrier.
+//
+// Work unit = (stream, output tile, chunk of up to M3_FRAMES frames of the batch).  The tile's LUT
+// (4 B per output pixel - twice the pixel payload) is fetched ONCE per unit into registers and reused
+// for every frame of the chunk, so per frame only the source box streams in.  Work item = one frame
+// of one unit = one ring stage.
+//  * Warps 8..9 are producers.  Thread 0 of warp 8 issues, one item ahead, the TMA loads of copy A
+//    (256 x 8 byte boxes; coordinates outside the image read as zero = BORDER_CONSTANT 0) onto the
+//    stage's `raw` mbarrier and writes the stage header (destination pointer, live rows / columns,
+//    LUT pointers).  TMA boxes must start on 16-byte boundaries, so the one-byte-shifted copy B cannot
+//    come from TMA: the 64 producer threads build it from copy A in shared memory (LDS.128, funnel
+//    shifts, STS.128) and arrive on the stage's `full` mbarrier.
 //  * Warps 0..7 are consumers: wait `full`, blend exactly as the v2 kernel (aligned pair taps +
-//    dp2a), store, arrive on `empty`.  They spend no instruction on staging and never wait on global
-//    memory.
+//    dp2a), store, arrive on `empty`.  They spend no instruction on staging, never wait on source
+//    pixels from global memory, and prefetch the next unit's LUT during the last frame of a unit.
 struct Rect3JobDev {
     const uint32_t* lut3;
     const TileBox2* boxes3;
@@ -307,28 +311,26 @@ struct Rect3Params {
     uint32_t tiles_per_set;
     int n_jobs;
     int n_batch;
-    int rows_alloc_max;  // launch-wide: fixes where the LUT sits inside a stage
+    int frames_per_unit;
+    int rows_alloc_max;  // launch-wide stage geometry
     int debug;           // bring-up switches (TI_OPT_DEBUG); 0 in production
 };
 
-struct Stage3Header {  // 48 bytes at the end of a stage: written by the TMA-issuing lane, read by everybody
-    uint32_t dst_lo, dst_hi;  // address of output pixel (u0, v0) of frame b
-    int32_t dst_w;
-    int32_t live_rows;        // dst_h - v0
-    int32_t live_cols;        // dst_w - u0
-    int32_t rows, nvec, rows_alloc;  // staged source rows, 16-byte vectors per row, start of copy B (rows)
-    int32_t pad[4];
-};
+// Stage header, 64 bytes at the end of a stage: written by the issuing thread, read by everybody.
+//  h0 = {dst_lo, dst_hi, dst_w, live_rows}   h1 = {live_cols, rows, nvec, rows_alloc}
+//  h2 = {lut_lo, lut_hi, next_lut_lo, next_lut_hi}   h3 = {flags, 0, 0, 0}
+constexpr uint32_t H3_FIRST = 1u;  // first frame of a unit: (re)load the LUT registers
+constexpr uint32_t H3_LAST_OF_UNIT = 2u;  // last frame of a unit: prefetch the next unit's LUT
+constexpr uint32_t H3_LAST_ITEM = 4u;     // last item of this CTA
 
 template <int TH>
 __global__ void __launch_bounds__(M3_THREADS) rectify_mono_tma_kernel(const __grid_constant__ Rect3Params P) {
     TI_DYNAMIC_SMEM(uint8_t, smem);
     constexpr int ROWS_PER_WARP = TH / M3_CONSUMER_WARPS;
-    constexpr uint32_t LUT_BYTES = TH * M3_TW * 4;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t ab_bytes = 2u * (uint32_t)P.rows_alloc_max * M3_PITCH;
-    const uint32_t stage_bytes = 128u + ab_bytes + LUT_BYTES + 128u;
-    const uint32_t hdr_off = 128u + ab_bytes + LUT_BYTES;
+    const uint32_t stage_bytes = 128u + ab_bytes + 128u;
+    const uint32_t hdr_off = 128u + ab_bytes;
     uint64_t* raw = reinterpret_cast<uint64_t*>(smem);  // [M3_STAGES] TMA landed
     uint64_t* full = raw + M3_STAGES;                    // [M3_STAGES] copy B ready
     uint64_t* empty = full + M3_STAGES;                  // [M3_STAGES] consumers done
@@ -347,56 +349,87 @@ __global__ void __launch_bounds__(M3_THREADS) rectify_mono_tma_kernel(const __gr
         if (tid < 8) reinterpret_cast<uint4*>(stage0 + (size_t)s * stage_bytes)[tid] = make_uint4(0u, 0u, 0u, 0u);
     __syncthreads();
 
-    const uint64_t total = (uint64_t)P.tiles_per_set * P.n_batch;
-    const uint32_t n_mine = total > blockIdx.x ? (uint32_t)((total - blockIdx.x + gridDim.x - 1) / gridDim.x) : 0u;
+    const uint32_t n_chunks = (uint32_t)((P.n_batch + P.frames_per_unit - 1) / P.frames_per_unit);
+    const uint64_t total_units = (uint64_t)P.tiles_per_set * n_chunks;
+    const uint32_t units_mine = total_units > blockIdx.x ? (uint32_t)((total_units - blockIdx.x + gridDim.x - 1) / gridDim.x) : 0u;
+    if (units_mine == 0) return;
 
     if (warp >= M3_CONSUMER_WARPS) {
         // ------------------------------------------------ producer warps -----------------------------
         const int ptid = tid - M3_CONSUMER_WARPS * 32;  // 0 .. 32 * M3_PRODUCER_WARPS - 1
-        // issuer state (ptid == 0): decode position of the next tile to issue and its prefetched box
-        uint32_t r = blockIdx.x, b = 0;
-        int j = 0;
-        uint4 box = make_uint4(0u, 0u, 0u, 0u);
-        auto decode_and_prefetch = [&]() {
-            while (r >= P.tiles_per_set) { r -= P.tiles_per_set; ++b; j = 0; }
+        const int vc = ptid & 15, r0 = ptid >> 4;       // builder role: column vector vc of rows r0, r0 + RSTEP, ...
+        constexpr int RSTEP = M3_PRODUCER_WARPS * 2;
+
+        // issuer state (ptid == 0): the unit being issued, the unit after it (for LUT prefetch), item counter
+        struct Unit { int j; uint32_t tile, b0, nb; uint4 box; uint64_t lut; };
+        Unit cur{}, nxt{};
+        uint32_t k_next = 0;   // index (among this CTA's units) of the unit held in `nxt`
+        uint32_t f = 0;        // next frame of `cur` to issue
+        uint32_t issued = 0;   // items issued so far
+        bool more = true;      // `cur` is valid
+        auto load_unit = [&](uint32_t k, Unit& U) {
+            const uint64_t ug = (uint64_t)blockIdx.x + (uint64_t)k * gridDim.x;
+            const uint32_t c = (uint32_t)(ug / P.tiles_per_set), r = (uint32_t)(ug - (uint64_t)c * P.tiles_per_set);
+            int j = 0;
             while (j + 1 < P.n_jobs && r >= P.job[j + 1].tile_begin) ++j;
-            box = *reinterpret_cast<const uint4*>(P.job[j].boxes3 + (r - P.job[j].tile_begin));
+            U.j = j; U.tile = r - P.job[j].tile_begin;
+            U.b0 = c * (uint32_t)P.frames_per_unit;
+            U.nb = min((uint32_t)P.frames_per_unit, (uint32_t)P.n_batch - U.b0);
+            U.box = *reinterpret_cast<const uint4*>(P.job[j].boxes3 + U.tile);
+            U.lut = (uint64_t)(uintptr_t)(P.job[j].lut3 + (size_t)U.tile * (TH * M3_TW));
         };
-        auto issue = [&](uint32_t i) {  // TMA copy A + LUT of this CTA's i-th tile into stage i % S
-            const Rect3JobDev& J = P.job[j];
-            const uint32_t tile = r - J.tile_begin;
-            const int c0 = (int16_t)(box.x & 0xFFFF), y0 = (int16_t)(box.x >> 16);
-            const int nvec = (int16_t)(box.y & 0xFFFF), rows = (int16_t)(box.y >> 16);
-            const int u0 = (int16_t)(box.z & 0xFFFF), v0 = (int16_t)(box.z >> 16);
-            const int s = (int)(i % M3_STAGES);
-            const uint32_t use = i / M3_STAGES;  // how many times this stage has been used before
+        auto issue_one = [&]() {  // TMA copy A of frame f of `cur` into stage issued % S, then advance
+            const Rect3JobDev& J = P.job[cur.j];
+            const int c0 = (int16_t)(cur.box.x & 0xFFFF), y0 = (int16_t)(cur.box.x >> 16);
+            const int nvec = (int16_t)(cur.box.y & 0xFFFF), rows = (int16_t)(cur.box.y >> 16);
+            const int u0 = (int16_t)(cur.box.z & 0xFFFF), v0 = (int16_t)(cur.box.z >> 16);
+            const uint32_t b = cur.b0 + f;
+            const int s = (int)(issued % M3_STAGES);
+            const uint32_t use = issued / M3_STAGES;  // how many times this stage has been used before
             uint8_t* sb = stage0 + (size_t)s * stage_bytes;
-            mbar_wait(empty + s, (use & 1u) ^ 1u);  // consumers have released the stage's previous tile
+            mbar_wait(empty + s, (use & 1u) ^ 1u);  // consumers have released the stage's previous item
             const int nblk = (rows + M3_BOX_ROWS - 1) / M3_BOX_ROWS;
             for (int k = 0; k < nblk; ++k)
-                tma_load_3d(sb + 128 + k * (M3_BOX_ROWS * M3_PITCH), &P.map[j], c0, y0 + k * M3_BOX_ROWS, (int)b, raw + s);
-            bulk_load_1d(sb + 128 + ab_bytes, J.lut3 + (size_t)tile * (TH * M3_TW), LUT_BYTES, raw + s);
+                tma_load_3d(sb + 128 + k * (M3_BOX_ROWS * M3_PITCH), &P.map[cur.j], c0, y0 + k * M3_BOX_ROWS, (int)b, raw + s);
+            const bool last_of_unit = f + 1 == cur.nb;
+            const bool have_next = k_next < units_mine;
+            uint32_t flags = (f == 0 ? H3_FIRST : 0u) | (last_of_unit ? H3_LAST_OF_UNIT : 0u) |
+                             (last_of_unit && !have_next ? H3_LAST_ITEM : 0u);
             const uint64_t dst = (uint64_t)(uintptr_t)(J.dst + (uint64_t)b * J.dst_stride + (size_t)v0 * J.dst_w + u0);
+            const uint64_t nlut = have_next ? nxt.lut : 0ull;
             uint4* h = reinterpret_cast<uint4*>(sb + hdr_off);
             h[0] = make_uint4((uint32_t)(dst & 0xFFFFFFFFu), (uint32_t)(dst >> 32), (uint32_t)J.dst_w, (uint32_t)(J.dst_h - v0));
             h[1] = make_uint4((uint32_t)(J.dst_w - u0), (uint32_t)rows, (uint32_t)nvec, (uint32_t)J.rows_alloc);
-            mbar_arrive_expect_tx(raw + s, (uint32_t)nblk * (M3_BOX_ROWS * M3_PITCH) + LUT_BYTES);  // releases the header too
-            r += gridDim.x;
+            h[2] = make_uint4((uint32_t)(cur.lut & 0xFFFFFFFFu), (uint32_t)(cur.lut >> 32), (uint32_t)(nlut & 0xFFFFFFFFu), (uint32_t)(nlut >> 32));
+            h[3] = make_uint4(flags, 0u, 0u, 0u);
+            mbar_arrive_expect_tx(raw + s, (uint32_t)nblk * (M3_BOX_ROWS * M3_PITCH));  // releases the header too
+            ++issued;
+            if (++f == cur.nb) {  // unit finished: move on
+                f = 0;
+                if (have_next) {
+                    cur = nxt;
+                    ++k_next;
+                    if (k_next < units_mine) load_unit(k_next, nxt);
+                } else {
+                    more = false;
+                }
+            }
         };
 
-        if (ptid == 0 && n_mine > 0) { decode_and_prefetch(); issue(0); if (n_mine > 1) decode_and_prefetch(); }
-        const int vc = ptid & 15, r0 = ptid >> 4;  // builder role: column vector vc of rows r0, r0 + RSTEP, ...
-        constexpr int RSTEP = M3_PRODUCER_WARPS * 2;
-        for (uint32_t i = 0; i < n_mine; ++i) {
-            if (ptid == 0 && i + 1 < n_mine) {  // keep one tile of loads in flight, one box descriptor ahead of that
-                issue(i + 1);
-                if (i + 2 < n_mine) decode_and_prefetch();
-            }
+        if (ptid == 0) {
+            load_unit(0, cur);
+            k_next = 1;
+            if (units_mine > 1) load_unit(1, nxt);
+            issue_one();
+        }
+        for (uint32_t i = 0;; ++i) {  // item i: its TMA was issued one iteration ago
+            if (ptid == 0 && more) issue_one();  // keep one item of loads in flight
             const int s = (int)(i % M3_STAGES);
             const uint32_t use = i / M3_STAGES;
             uint8_t* sb = stage0 + (size_t)s * stage_bytes;
             mbar_wait(raw + s, use & 1u);
             const uint4 h1 = *reinterpret_cast<const uint4*>(sb + hdr_off + 16);
+            const uint32_t flags = *reinterpret_cast<const uint32_t*>(sb + hdr_off + 48);
             const int rows = (int)h1.y, nvec = (int)h1.z, rows_alloc = (int)h1.w;
             // copy B[64 + i] = A[i + 1]: odd-x0 pairs become 2-byte aligned, 16 banks away from copy A
             if (vc < nvec && vc < 12) {
@@ -425,36 +458,69 @@ __global__ void __launch_bounds__(M3_THREADS) rectify_mono_tma_kernel(const __gr
                 }
             }
             mbar_arrive(full + s);  // every producer thread: each releases its own shared-memory writes
+            if (flags & H3_LAST_ITEM) break;
         }
         return;
     }
     // ---------------------------------------------------- consumers ---------------------------------
-    for (uint32_t i = 0; i < n_mine; ++i) {
+    uint4 l[ROWS_PER_WARP], ln[ROWS_PER_WARP];  // LUT of the current unit / prefetched LUT of the next unit
+#pragma unroll
+    for (int q = 0; q < ROWS_PER_WARP; ++q) ln[q] = make_uint4(0u, 0u, 0u, 0u);
+    const uint32_t lut_lane_off = (uint32_t)((warp * ROWS_PER_WARP) * M3_TW + lane * 4);  // in u32 entries
+    for (uint32_t i = 0;; ++i) {
         const int s = (int)(i % M3_STAGES);
         const uint32_t use = i / M3_STAGES;
         const uint8_t* sb = stage0 + (size_t)s * stage_bytes;
         mbar_wait(full + s, use & 1u);
-        const uint4 hraw = *reinterpret_cast<const uint4*>(sb + hdr_off);
+        const uint4 h0 = *reinterpret_cast<const uint4*>(sb + hdr_off);
+        const uint4 h2 = *reinterpret_cast<const uint4*>(sb + hdr_off + 32);
         const uint32_t live_cols = *reinterpret_cast<const uint32_t*>(sb + hdr_off + 16);
-        uint8_t* dp = reinterpret_cast<uint8_t*>((uintptr_t)(((uint64_t)hraw.y << 32) | hraw.x));
-        const int dst_w = (int)hraw.z, live_rows = (int)hraw.w - warp * ROWS_PER_WARP;
-        const int my_cols = ((int)live_cols - lane + 31) >> 5;  // of this lane's 4 pixels, how many exist
-        const uint4* lut_s = reinterpret_cast<const uint4*>(sb + 128 + ab_bytes) + (warp * ROWS_PER_WARP) * 32 + lane;
-        dp += (size_t)(warp * ROWS_PER_WARP) * dst_w + lane;
+        const uint32_t flags = *reinterpret_cast<const uint32_t*>(sb + hdr_off + 48);
+        if (flags & H3_FIRST) {
+            if (i == 0) {  // very first unit: nothing was prefetched
+                const uint32_t* lp = reinterpret_cast<const uint32_t*>((uintptr_t)(((uint64_t)h2.y << 32) | h2.x)) + lut_lane_off;
 #pragma unroll
-        for (int q = 0; q < ROWS_PER_WARP; ++q) {
-            const uint4 e = lut_s[q * 32];
-            const uint32_t s0 = blend64(e.x, sb), s1 = blend64(e.y, sb), s2 = blend64(e.z, sb), s3 = blend64(e.w, sb);
-            if (q < live_rows) {
-                uint8_t* o = dp + (size_t)q * dst_w;
-                if (my_cols > 0) st_stream_b8(o, s0 >> 16);
-                if (my_cols > 1) st_stream_b8(o + 32, s1 >> 16);
-                if (my_cols > 2) st_stream_b8(o + 64, s2 >> 16);
-                if (my_cols > 3) st_stream_b8(o + 96, s3 >> 16);
+                for (int q = 0; q < ROWS_PER_WARP; ++q) l[q] = ld_keep_u4(lp + q * M3_TW);
+            } else {
+#pragma unroll
+                for (int q = 0; q < ROWS_PER_WARP; ++q) l[q] = ln[q];
+            }
+        }
+        if ((flags & H3_LAST_OF_UNIT) && (h2.z | h2.w)) {  // prefetch the next unit's LUT behind this frame's work
+            const uint32_t* lp = reinterpret_cast<const uint32_t*>((uintptr_t)(((uint64_t)h2.w << 32) | h2.z)) + lut_lane_off;
+#pragma unroll
+            for (int q = 0; q < ROWS_PER_WARP; ++q) ln[q] = ld_keep_u4(lp + q * M3_TW);
+        }
+        uint8_t* dp = reinterpret_cast<uint8_t*>((uintptr_t)(((uint64_t)h0.y << 32) | h0.x));
+        const int dst_w = (int)h0.z, live_rows = (int)h0.w - warp * ROWS_PER_WARP;
+        dp += (size_t)(warp * ROWS_PER_WARP) * dst_w + lane;
+        if (live_rows >= ROWS_PER_WARP && live_cols >= (uint32_t)M3_TW) {  // whole tile inside the image (warp-uniform)
+#pragma unroll
+            for (int q = 0; q < ROWS_PER_WARP; ++q) {
+                const uint32_t s0 = blend64(l[q].x, sb), s1 = blend64(l[q].y, sb), s2 = blend64(l[q].z, sb), s3 = blend64(l[q].w, sb);
+                st_stream_b8(dp, s0 >> 16);
+                st_stream_b8(dp + 32, s1 >> 16);
+                st_stream_b8(dp + 64, s2 >> 16);
+                st_stream_b8(dp + 96, s3 >> 16);
+                dp += dst_w;
+            }
+        } else {
+            const int my_cols = ((int)live_cols - lane + 31) >> 5;  // of this lane's 4 pixels, how many exist
+#pragma unroll
+            for (int q = 0; q < ROWS_PER_WARP; ++q) {
+                const uint32_t s0 = blend64(l[q].x, sb), s1 = blend64(l[q].y, sb), s2 = blend64(l[q].z, sb), s3 = blend64(l[q].w, sb);
+                if (q < live_rows) {
+                    if (my_cols > 0) st_stream_b8(dp, s0 >> 16);
+                    if (my_cols > 1) st_stream_b8(dp + 32, s1 >> 16);
+                    if (my_cols > 2) st_stream_b8(dp + 64, s2 >> 16);
+                    if (my_cols > 3) st_stream_b8(dp + 96, s3 >> 16);
+                }
+                dp += dst_w;
             }
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(empty + s);
+        if (flags & H3_LAST_ITEM) break;
     }
 }
 
@@ -632,9 +698,10 @@ int launch_rectify(ti_ctx* ctx, const RectifyJob* jobs, int n_jobs, int n_batch)
     PT.debug = ctx->debug;
     if (PT.n_jobs) {
         const int TH = thk == 0 ? 16 : 32;
-        const size_t stage = 128 + 2 * (size_t)PT.rows_alloc_max * M3_PITCH + (size_t)TH * M3_TW * 4 + 128;
+        const size_t stage = 128 + 2 * (size_t)PT.rows_alloc_max * M3_PITCH + 128;
+        PT.frames_per_unit = std::max(1, std::min(n_batch, ctx->frames_per_unit));
         const size_t smem = 128 + M3_STAGES * stage;
-        const uint64_t total = (uint64_t)PT.tiles_per_set * n_batch;
+        const uint64_t total = (uint64_t)PT.tiles_per_set * ((n_batch + PT.frames_per_unit - 1) / PT.frames_per_unit);
 #ifndef TI_EMULATE
         if (thk == 0)
             TI_CUDA(ctx, cudaFuncSetAttribute(rectify_mono_tma_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

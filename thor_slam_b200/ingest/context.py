@@ -116,6 +116,7 @@ class IngestContext:
     OPT_MONO_VARIANT = 3
     OPT_TMA_TILE_H = 4
     OPT_DEBUG = 5
+    OPT_FRAMES_PER_UNIT = 6
 
     def set_option(self, option: int, value: int) -> None:
         """Tuning / test switches of the library; results never depend on them."""

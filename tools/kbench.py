@@ -70,13 +70,16 @@ def main() -> None:
     px = NS * B * W * H
 
     if not args.only or "rect" in args.only:
-        for variant, th, sweep in ((3, 32, (0, 1, 2, 3)), (3, 16, (0, 2, 3, 4, 5)), (2, 32, (0,))):
+        for variant, th, fpu, sweep in ((3, 32, 8, (0, 1, 2, 3)), (3, 32, 16, (0,)), (3, 32, 32, (0,)), (3, 32, 4, (0,)), (3, 32, 1, (0,)),
+                                        (3, 16, 8, (0, 3, 4)), (3, 16, 32, (0,)), (2, 32, 8, (0,))):
             ctx.set_option(ctx.OPT_MONO_VARIANT, variant)
             ctx.set_option(ctx.OPT_TMA_TILE_H, th)
+            ctx.set_option(ctx.OPT_FRAMES_PER_UNIT, fpu)
             for per_sm in sweep:
                 ctx.set_option(ctx.OPT_CTAS_PER_SM, per_sm)
-                report(f"rectify mono v{variant} th={th} ctas/sm={per_sm or 'auto'}", timeit(lambda: ctx.ingest(specs), args.iters), 2 * px, px)
+                report(f"rectify mono v{variant} th={th} fpu={fpu} ctas/sm={per_sm or 'auto'}", timeit(lambda: ctx.ingest(specs), args.iters), 2 * px, px)
         ctx.set_option(ctx.OPT_CTAS_PER_SM, 0)
+        ctx.set_option(ctx.OPT_FRAMES_PER_UNIT, 8)
         ctx.set_option(ctx.OPT_MONO_VARIANT, 3)
         ctx.set_option(ctx.OPT_TMA_TILE_H, 32)
         ctx.set_option(ctx.OPT_FORCE_GENERIC_RECTIFY, 1)
