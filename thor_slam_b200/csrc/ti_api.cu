@@ -127,6 +127,9 @@ int ti_set_option(ti_ctx* ctx, int option, int value) {
         case TI_OPT_FORCE_GENERIC_RECTIFY: ctx->force_generic_rectify = value != 0; return TI_OK;
         case TI_OPT_CTAS_PER_SM: ctx->ctas_per_sm = value; return TI_OK;
         case TI_OPT_DEBUG: ctx->debug = value; return TI_OK;
+        case TI_OPT_STAGES:
+            if (value < 3 || value > M3_MAX_STAGES) return fail(ctx, TI_EINVAL, "stages must be in [3,%d]", M3_MAX_STAGES);
+            ctx->stages = value; return TI_OK;
         case TI_OPT_FRAMES_PER_UNIT:
             if (value < 1) return fail(ctx, TI_EINVAL, "frames per unit must be >= 1");
             ctx->frames_per_unit = value; return TI_OK;

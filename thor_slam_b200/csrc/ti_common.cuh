@@ -83,7 +83,7 @@ constexpr int M3_MAX_ROWS = 96;
 constexpr int M3_CONSUMER_WARPS = 8;
 constexpr int M3_PRODUCER_WARPS = 2;
 constexpr int M3_THREADS = (M3_CONSUMER_WARPS + M3_PRODUCER_WARPS) * 32;
-constexpr int M3_STAGES = 3;
+constexpr int M3_MAX_STAGES = 8;
 
 struct CameraSlot {
     // rectification
@@ -124,6 +124,7 @@ struct ti_ctx {
     int debug = 0;
     int mono_variant = 3;   // 3: TMA-pipelined kernel, 2: thread-staged kernel, 1: generic only
     int tma_tile_h = 32;    // 16 or 32
+    int stages = 4;           // shared-memory ring depth of the TMA-pipelined kernel
     int frames_per_unit = 8;  // frames of the batch that share one LUT fetch in the TMA-pipelined kernel
     bool force_generic_rectify = false;  // tests: exercise the generic tiled / direct kernels
     ti::CameraSlot cams[TI_MAX_CAMERAS];

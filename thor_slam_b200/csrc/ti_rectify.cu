@@ -313,6 +313,7 @@ struct Rect3Params {
     int n_batch;
     int frames_per_unit;
     int rows_alloc_max;  // launch-wide stage geometry
+    int stages;          // ring depth (3 .. M3_MAX_STAGES)
     int debug;           // bring-up switches (TI_OPT_DEBUG); 0 in production
 };
 
@@ -331,21 +332,21 @@ __global__ void __launch_bounds__(M3_THREADS) rectify_mono_tma_kernel(const __gr
     const uint32_t ab_bytes = 2u * (uint32_t)P.rows_alloc_max * M3_PITCH;
     const uint32_t stage_bytes = 128u + ab_bytes + 128u;
     const uint32_t hdr_off = 128u + ab_bytes;
-    uint64_t* raw = reinterpret_cast<uint64_t*>(smem);  // [M3_STAGES] TMA landed
-    uint64_t* full = raw + M3_STAGES;                    // [M3_STAGES] copy B ready
-    uint64_t* empty = full + M3_STAGES;                  // [M3_STAGES] consumers done
-    uint8_t* stage0 = smem + 128;
+    const int S = P.stages;
+    uint64_t* raw = reinterpret_cast<uint64_t*>(smem);  // [S] TMA landed
+    uint64_t* full = raw + M3_MAX_STAGES;                // [S] copy B ready
+    uint64_t* empty = full + M3_MAX_STAGES;              // [S] consumers done
+    uint8_t* stage0 = smem + 256;
 
     if (tid == 0) {
-#pragma unroll
-        for (int s = 0; s < M3_STAGES; ++s) {
+        for (int s = 0; s < S; ++s) {
             mbar_init(raw + s, 1);
             mbar_init(full + s, M3_PRODUCER_WARPS * 32);
             mbar_init(empty + s, M3_CONSUMER_WARPS);
         }
         mbar_fence_init();
     }
-    for (int s = 0; s < M3_STAGES; ++s)  // the always-zero block of every stage
+    for (int s = 0; s < S; ++s)  // the always-zero block of every stage
         if (tid < 8) reinterpret_cast<uint4*>(stage0 + (size_t)s * stage_bytes)[tid] = make_uint4(0u, 0u, 0u, 0u);
     __syncthreads();
 
@@ -366,6 +367,8 @@ __global__ void __launch_bounds__(M3_THREADS) rectify_mono_tma_kernel(const __gr
         uint32_t k_next = 0;   // index (among this CTA's units) of the unit held in `nxt`
         uint32_t f = 0;        // next frame of `cur` to issue
         uint32_t issued = 0;   // items issued so far
+        int is = 0;            // stage of the next item to issue
+        uint32_t iphase = 1;   // parity to wait for on empty[is]: 1 on a stage's first use (passes at once)
         bool more = true;      // `cur` is valid
         auto load_unit = [&](uint32_t k, Unit& U) {
             const uint64_t ug = (uint64_t)blockIdx.x + (uint64_t)k * gridDim.x;
@@ -384,10 +387,9 @@ __global__ void __launch_bounds__(M3_THREADS) rectify_mono_tma_kernel(const __gr
             const int nvec = (int16_t)(cur.box.y & 0xFFFF), rows = (int16_t)(cur.box.y >> 16);
             const int u0 = (int16_t)(cur.box.z & 0xFFFF), v0 = (int16_t)(cur.box.z >> 16);
             const uint32_t b = cur.b0 + f;
-            const int s = (int)(issued % M3_STAGES);
-            const uint32_t use = issued / M3_STAGES;  // how many times this stage has been used before
+            const int s = is;
             uint8_t* sb = stage0 + (size_t)s * stage_bytes;
-            mbar_wait(empty + s, (use & 1u) ^ 1u);  // consumers have released the stage's previous item
+            mbar_wait(empty + s, iphase);  // consumers have released the stage's previous item
             const int nblk = (rows + M3_BOX_ROWS - 1) / M3_BOX_ROWS;
             for (int k = 0; k < nblk; ++k)
                 tma_load_3d(sb + 128 + k * (M3_BOX_ROWS * M3_PITCH), &P.map[cur.j], c0, y0 + k * M3_BOX_ROWS, (int)b, raw + s);
@@ -404,6 +406,7 @@ __global__ void __launch_bounds__(M3_THREADS) rectify_mono_tma_kernel(const __gr
             h[3] = make_uint4(flags, 0u, 0u, 0u);
             mbar_arrive_expect_tx(raw + s, (uint32_t)nblk * (M3_BOX_ROWS * M3_PITCH));  // releases the header too
             ++issued;
+            if (++is == S) { is = 0; iphase ^= 1u; }
             if (++f == cur.nb) {  // unit finished: move on
                 f = 0;
                 if (have_next) {
@@ -422,12 +425,19 @@ __global__ void __launch_bounds__(M3_THREADS) rectify_mono_tma_kernel(const __gr
             if (units_mine > 1) load_unit(1, nxt);
             issue_one();
         }
-        for (uint32_t i = 0;; ++i) {  // item i: its TMA was issued one iteration ago
-            if (ptid == 0 && more) issue_one();  // keep one item of loads in flight
-            const int s = (int)(i % M3_STAGES);
-            const uint32_t use = i / M3_STAGES;
+        int s = 0;
+        uint32_t phase = 0;
+        const uint32_t look = (uint32_t)(S - 2);  // items in flight beyond the one being built
+        for (uint32_t i = 0;; ++i) {  // item i: its TMA was issued `look` iterations ago
+            if (ptid == 0) {
+                // item i+1 must be issued now (blocking); items up to i+look only if their stage is already free
+                while (more && issued <= i + look) {
+                    if (issued > i + 1 && !mbar_test(empty + is, iphase)) break;
+                    issue_one();
+                }
+            }
             uint8_t* sb = stage0 + (size_t)s * stage_bytes;
-            mbar_wait(raw + s, use & 1u);
+            mbar_wait(raw + s, phase);
             const uint4 h1 = *reinterpret_cast<const uint4*>(sb + hdr_off + 16);
             const uint32_t flags = *reinterpret_cast<const uint32_t*>(sb + hdr_off + 48);
             const int rows = (int)h1.y, nvec = (int)h1.z, rows_alloc = (int)h1.w;
@@ -459,6 +469,7 @@ __global__ void __launch_bounds__(M3_THREADS) rectify_mono_tma_kernel(const __gr
             }
             mbar_arrive(full + s);  // every producer thread: each releases its own shared-memory writes
             if (flags & H3_LAST_ITEM) break;
+            if (++s == S) { s = 0; phase ^= 1u; }
         }
         return;
     }
@@ -467,11 +478,11 @@ __global__ void __launch_bounds__(M3_THREADS) rectify_mono_tma_kernel(const __gr
 #pragma unroll
     for (int q = 0; q < ROWS_PER_WARP; ++q) ln[q] = make_uint4(0u, 0u, 0u, 0u);
     const uint32_t lut_lane_off = (uint32_t)((warp * ROWS_PER_WARP) * M3_TW + lane * 4);  // in u32 entries
+    int s = 0;
+    uint32_t phase = 0;
     for (uint32_t i = 0;; ++i) {
-        const int s = (int)(i % M3_STAGES);
-        const uint32_t use = i / M3_STAGES;
         const uint8_t* sb = stage0 + (size_t)s * stage_bytes;
-        mbar_wait(full + s, use & 1u);
+        mbar_wait(full + s, phase);
         const uint4 h0 = *reinterpret_cast<const uint4*>(sb + hdr_off);
         const uint4 h2 = *reinterpret_cast<const uint4*>(sb + hdr_off + 32);
         const uint32_t live_cols = *reinterpret_cast<const uint32_t*>(sb + hdr_off + 16);
@@ -521,6 +532,7 @@ __global__ void __launch_bounds__(M3_THREADS) rectify_mono_tma_kernel(const __gr
         __syncwarp();
         if (lane == 0) mbar_arrive(empty + s);
         if (flags & H3_LAST_ITEM) break;
+        if (++s == S) { s = 0; phase ^= 1u; }
     }
 }
 
@@ -700,7 +712,8 @@ int launch_rectify(ti_ctx* ctx, const RectifyJob* jobs, int n_jobs, int n_batch)
         const int TH = thk == 0 ? 16 : 32;
         const size_t stage = 128 + 2 * (size_t)PT.rows_alloc_max * M3_PITCH + 128;
         PT.frames_per_unit = std::max(1, std::min(n_batch, ctx->frames_per_unit));
-        const size_t smem = 128 + M3_STAGES * stage;
+        PT.stages = std::max(3, std::min(ctx->stages, M3_MAX_STAGES));
+        const size_t smem = 256 + (size_t)PT.stages * stage;
         const uint64_t total = (uint64_t)PT.tiles_per_set * ((n_batch + PT.frames_per_unit - 1) / PT.frames_per_unit);
 #ifndef TI_EMULATE
         if (thk == 0)

@@ -54,6 +54,10 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     EmuMbar* m = reinterpret_cast<EmuMbar*>(bar);
     while ((__atomic_load_n(&m->completed, __ATOMIC_ACQUIRE) & 1u) == parity) std::this_thread::yield();
 }
+__device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
+    EmuMbar* m = reinterpret_cast<EmuMbar*>(bar);
+    return (__atomic_load_n(&m->completed, __ATOMIC_ACQUIRE) & 1u) != parity;
+}
 __device__ __forceinline__ void tma_load_3d(void* smem_dst, const TiTensorMap* map, int x, int y, int z, uint64_t*) {
     uint8_t* d = static_cast<uint8_t*>(smem_dst);
     ti_emu::check_align(smem_dst, 128);
@@ -94,6 +98,19 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         "}\n" ::"r"(smem_u32(bar)),
         "r"(parity)
         : "memory");
+}
+__device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {  // one non-blocking probe
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
 }
 __device__ __forceinline__ void tma_load_3d(void* smem_dst, const TiTensorMap* map, int x, int y, int z, uint64_t* bar) {
     asm volatile(
