@@ -82,7 +82,7 @@ constexpr int M3_MAX_SPAN = 192;
 constexpr int M3_MAX_ROWS = 96;
 constexpr int M3_CONSUMER_WARPS = 8;
 constexpr int M3_PRODUCER_WARPS = 2;
-constexpr int M3_THREADS = (M3_CONSUMER_WARPS + M3_PRODUCER_WARPS) * 32;
+constexpr int M3_THREADS = (M3_CONSUMER_WARPS + M3_PRODUCER_WARPS + 1) * 32;  // consumers, copy-B builders, TMA issuer
 constexpr int M3_MAX_STAGES = 8;
 
 struct CameraSlot {

@@ -355,11 +355,9 @@ __global__ void __launch_bounds__(M3_THREADS) rectify_mono_tma_kernel(const __gr
     const uint32_t units_mine = total_units > blockIdx.x ? (uint32_t)((total_units - blockIdx.x + gridDim.x - 1) / gridDim.x) : 0u;
     if (units_mine == 0) return;
 
-    if (warp >= M3_CONSUMER_WARPS) {
-        // ------------------------------------------------ producer warps -----------------------------
-        const int ptid = tid - M3_CONSUMER_WARPS * 32;  // 0 .. 32 * M3_PRODUCER_WARPS - 1
-        const int vc = ptid & 15, r0 = ptid >> 4;       // builder role: column vector vc of rows r0, r0 + RSTEP, ...
-        constexpr int RSTEP = M3_PRODUCER_WARPS * 2;
+    if (warp == M3_CONSUMER_WARPS + M3_PRODUCER_WARPS) {
+        // ------------------------------------------------ issuer (one thread) ------------------------
+        if (lane != 0) return;
 
         // issuer state (ptid == 0): the unit being issued, the unit after it (for LUT prefetch), item counter
         struct Unit { int j; uint32_t tile, b0, nb; uint4 box; uint64_t lut; };
@@ -390,9 +388,7 @@ __global__ void __launch_bounds__(M3_THREADS) rectify_mono_tma_kernel(const __gr
             const int s = is;
             uint8_t* sb = stage0 + (size_t)s * stage_bytes;
             mbar_wait(empty + s, iphase);  // consumers have released the stage's previous item
-            const int nblk = (rows + M3_BOX_ROWS - 1) / M3_BOX_ROWS;
-            for (int k = 0; k < nblk; ++k)
-                tma_load_3d(sb + 128 + k * (M3_BOX_ROWS * M3_PITCH), &P.map[cur.j], c0, y0 + k * M3_BOX_ROWS, (int)b, raw + s);
+            if (rows > 0) tma_load_3d(sb + 128, &P.map[cur.j], c0, y0, (int)b, raw + s);  // one box: 256 x rows_alloc bytes
             const bool last_of_unit = f + 1 == cur.nb;
             const bool have_next = k_next < units_mine;
             uint32_t flags = (f == 0 ? H3_FIRST : 0u) | (last_of_unit ? H3_LAST_OF_UNIT : 0u) |
@@ -404,7 +400,7 @@ __global__ void __launch_bounds__(M3_THREADS) rectify_mono_tma_kernel(const __gr
             h[1] = make_uint4((uint32_t)(J.dst_w - u0), (uint32_t)rows, (uint32_t)nvec, (uint32_t)J.rows_alloc);
             h[2] = make_uint4((uint32_t)(cur.lut & 0xFFFFFFFFu), (uint32_t)(cur.lut >> 32), (uint32_t)(nlut & 0xFFFFFFFFu), (uint32_t)(nlut >> 32));
             h[3] = make_uint4(flags, 0u, 0u, 0u);
-            mbar_arrive_expect_tx(raw + s, (uint32_t)nblk * (M3_BOX_ROWS * M3_PITCH));  // releases the header too
+            mbar_arrive_expect_tx(raw + s, rows > 0 ? (uint32_t)J.rows_alloc * M3_PITCH : 0u);  // releases the header too
             ++issued;
             if (++is == S) { is = 0; iphase ^= 1u; }
             if (++f == cur.nb) {  // unit finished: move on
@@ -419,23 +415,20 @@ __global__ void __launch_bounds__(M3_THREADS) rectify_mono_tma_kernel(const __gr
             }
         };
 
-        if (ptid == 0) {
-            load_unit(0, cur);
-            k_next = 1;
-            if (units_mine > 1) load_unit(1, nxt);
-            issue_one();
-        }
+        load_unit(0, cur);
+        k_next = 1;
+        if (units_mine > 1) load_unit(1, nxt);
+        while (more) issue_one();  // runs ahead of the builders / consumers by up to S stages
+        return;
+    }
+    if (warp >= M3_CONSUMER_WARPS) {
+        // ------------------------------------------------ builder warps ------------------------------
+        const int ptid = tid - M3_CONSUMER_WARPS * 32;  // 0 .. 32 * M3_PRODUCER_WARPS - 1
+        const int vc = ptid & 15, r0 = ptid >> 4;       // column vector vc of rows r0, r0 + RSTEP, ...
+        constexpr int RSTEP = M3_PRODUCER_WARPS * 2;
         int s = 0;
         uint32_t phase = 0;
-        const uint32_t look = (uint32_t)(S - 2);  // items in flight beyond the one being built
-        for (uint32_t i = 0;; ++i) {  // item i: its TMA was issued `look` iterations ago
-            if (ptid == 0) {
-                // item i+1 must be issued now (blocking); items up to i+look only if their stage is already free
-                while (more && issued <= i + look) {
-                    if (issued > i + 1 && !mbar_test(empty + is, iphase)) break;
-                    issue_one();
-                }
-            }
+        for (uint32_t i = 0;; ++i) {
             uint8_t* sb = stage0 + (size_t)s * stage_bytes;
             mbar_wait(raw + s, phase);
             const uint4 h1 = *reinterpret_cast<const uint4*>(sb + hdr_off + 16);
@@ -666,7 +659,7 @@ int launch_rectify(ti_ctx* ctx, const RectifyJob* jobs, int n_jobs, int n_batch)
                             PT.n_jobs < MAX_RECT_JOBS && !ctx->force_generic_rectify && ctx->mono_variant == 3;
         if (tma_ok) {
             const int rc = tma_encode_u8_3d(ctx, &PT.map[PT.n_jobs], J.src, C.src_w, C.src_h, n_batch, (uint64_t)C.src_w,
-                                            J.src_stride, M3_PITCH, M3_BOX_ROWS);
+                                            J.src_stride, M3_PITCH, C.rows3_alloc[thk]);
             if (rc != TI_OK) return rc;
             Rect3JobDev D{};
             D.lut3 = C.d_lut3[thk]; D.boxes3 = C.d_boxes3[thk]; D.dst = J.dst; D.dst_stride = J.dst_stride;
