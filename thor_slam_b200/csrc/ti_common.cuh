@@ -270,9 +270,8 @@ __device__ __forceinline__ void st_stream_u1(void* p, uint32_t v) {
                  "l"(policy_evict_first())
                  : "memory");
 }
-__device__ __forceinline__ void st_stream_b8(void* p, uint32_t v) {
-    asm volatile("st.global.L1::no_allocate.L2::cache_hint.u8 [%0], %1, %2;" ::"l"(p), "r"(v), "l"(policy_evict_first())
-                 : "memory");
+__device__ __forceinline__ void st_stream_b8(void* p, uint32_t v) {  // .cs = streaming (evict-first), no policy descriptor
+    asm volatile("st.global.cs.u8 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 // LUT reads: re-used by every frame of the batch -> prefer to keep in L2.
 __device__ __forceinline__ uint4 ld_keep_u4(const void* p) {

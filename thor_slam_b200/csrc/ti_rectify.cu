@@ -180,6 +180,23 @@ struct Rect2Params {
 
 __device__ __forceinline__ uint32_t lds_u16(const uint8_t* p) { return *reinterpret_cast<const uint16_t*>(p); }
 
+// Taps addressed in the 32-bit shared window: base + (entry >> 16) is ONE LEA.HI, the row below an immediate.
+#ifdef TI_EMULATE
+typedef const uint8_t* smem_base_t;
+__device__ __forceinline__ smem_base_t smem_base(const uint8_t* p) { return p; }
+template <int OFF>
+__device__ __forceinline__ uint32_t lds_u16_at(smem_base_t base, uint32_t e) { return lds_u16(base + (e >> 16) + OFF); }
+#else
+typedef uint32_t smem_base_t;
+__device__ __forceinline__ smem_base_t smem_base(const uint8_t* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+template <int OFF>
+__device__ __forceinline__ uint32_t lds_u16_at(smem_base_t base, uint32_t e) {
+    uint32_t v;
+    asm volatile("ld.shared.u16 %0, [%1+%2];" : "=r"(v) : "r"(base + (e >> 16)), "n"(OFF));
+    return v;
+}
+#endif
+
 __device__ __forceinline__ uint32_t ld_src_u32(const void* p) {
 #ifdef TI_EMULATE
     return *reinterpret_cast<const uint32_t*>(ti_emu::check_align(p, 4));
@@ -191,9 +208,8 @@ __device__ __forceinline__ uint32_t ld_src_u32(const void* p) {
 }
 
 template <int ROW_PITCH = M3_PITCH>
-__device__ __forceinline__ uint32_t blend64(uint32_t e, const uint8_t* smem) {
-    const uint8_t* tap = smem + (e >> 16);
-    const uint32_t pt = lds_u16(tap), pb = lds_u16(tap + ROW_PITCH);
+__device__ __forceinline__ uint32_t blend64(uint32_t e, smem_base_t smem) {
+    const uint32_t pt = lds_u16_at<0>(smem, e), pb = lds_u16_at<ROW_PITCH>(smem, e);
     const uint32_t fx = e & 31u;
     const uint32_t aw = fx * 65535u + 32u;  // (32 - fx) | fx << 16
     const uint32_t top = __dp2a_lo(aw, pt, 0u), bot = __dp2a_lo(aw, pb, 0u);
@@ -258,14 +274,15 @@ __global__ void __launch_bounds__(M2_THREADS, 6) rectify_mono_kernel(const __gri
         __syncthreads();
 
         // (3) taps + blend + packed store
+        const smem_base_t sm2 = smem_base(smem);
         const int u = box.u0 + lane, v = box.v0 + warp * 4;
         uint8_t* dp = J.dst + (uint64_t)b * J.dst_stride + (size_t)v * J.dst_w + u;
         const int live_rows = J.dst_h - v;            // rows of this warp that exist in the image
         const int live_cols = (J.dst_w - u + 31) >> 5;  // of this lane's 4 pixels, how many exist
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-            const uint32_t s0 = blend64<M2_ROW_BYTES>(l[q].x, smem), s1 = blend64<M2_ROW_BYTES>(l[q].y, smem);
-            const uint32_t s2 = blend64<M2_ROW_BYTES>(l[q].z, smem), s3 = blend64<M2_ROW_BYTES>(l[q].w, smem);
+            const uint32_t s0 = blend64<M2_ROW_BYTES>(l[q].x, sm2), s1 = blend64<M2_ROW_BYTES>(l[q].y, sm2);
+            const uint32_t s2 = blend64<M2_ROW_BYTES>(l[q].z, sm2), s3 = blend64<M2_ROW_BYTES>(l[q].w, sm2);
             if (q < live_rows) {
                 uint8_t* o = dp + (size_t)q * J.dst_w;
                 if (live_cols > 0) st_stream_b8(o, s0 >> 16);
@@ -496,12 +513,13 @@ __global__ void __launch_bounds__(M3_THREADS) rectify_mono_tma_kernel(const __gr
             for (int q = 0; q < ROWS_PER_WARP; ++q) ln[q] = ld_keep_u4(lp + q * M3_TW);
         }
         uint8_t* dp = reinterpret_cast<uint8_t*>((uintptr_t)(((uint64_t)h0.y << 32) | h0.x));
+        const smem_base_t sbase = smem_base(sb);
         const int dst_w = (int)h0.z, live_rows = (int)h0.w - warp * ROWS_PER_WARP;
         dp += (size_t)(warp * ROWS_PER_WARP) * dst_w + lane;
         if (live_rows >= ROWS_PER_WARP && live_cols >= (uint32_t)M3_TW) {  // whole tile inside the image (warp-uniform)
 #pragma unroll
             for (int q = 0; q < ROWS_PER_WARP; ++q) {
-                const uint32_t s0 = blend64(l[q].x, sb), s1 = blend64(l[q].y, sb), s2 = blend64(l[q].z, sb), s3 = blend64(l[q].w, sb);
+                const uint32_t s0 = blend64(l[q].x, sbase), s1 = blend64(l[q].y, sbase), s2 = blend64(l[q].z, sbase), s3 = blend64(l[q].w, sbase);
                 st_stream_b8(dp, s0 >> 16);
                 st_stream_b8(dp + 32, s1 >> 16);
                 st_stream_b8(dp + 64, s2 >> 16);
@@ -512,7 +530,7 @@ __global__ void __launch_bounds__(M3_THREADS) rectify_mono_tma_kernel(const __gr
             const int my_cols = ((int)live_cols - lane + 31) >> 5;  // of this lane's 4 pixels, how many exist
 #pragma unroll
             for (int q = 0; q < ROWS_PER_WARP; ++q) {
-                const uint32_t s0 = blend64(l[q].x, sb), s1 = blend64(l[q].y, sb), s2 = blend64(l[q].z, sb), s3 = blend64(l[q].w, sb);
+                const uint32_t s0 = blend64(l[q].x, sbase), s1 = blend64(l[q].y, sbase), s2 = blend64(l[q].z, sbase), s3 = blend64(l[q].w, sbase);
                 if (q < live_rows) {
                     if (my_cols > 0) st_stream_b8(dp, s0 >> 16);
                     if (my_cols > 1) st_stream_b8(dp + 32, s1 >> 16);
