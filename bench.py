@@ -57,62 +57,78 @@ def measured_peak() -> tuple[float, str]:
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    """SM clock / power / throttle reasons of one GPU, polled through NVML on a thread during the timed region."""
 
-    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    REASONS = {
+        "hw_slowdown": 0x8,            # nvmlClocksThrottleReasonHwSlowdown
+        "sw_power_cap": 0x4,           # nvmlClocksThrottleReasonSwPowerCap
+        "sw_thermal_slowdown": 0x20,   # nvmlClocksThrottleReasonSwThermalSlowdown
+        "hw_thermal_slowdown": 0x40,   # nvmlClocksThrottleReasonHwThermalSlowdown
+        "hw_power_brake_slowdown": 0x80,
+    }
 
-    def __init__(self, index: int) -> None:
-        self.index = index
-        self.proc: subprocess.Popen | None = None
-        self.lines: list[str] = []
-        self.thread: threading.Thread | None = None
+    def __init__(self, index: int, period_s: float = 0.004) -> None:
+        self.index, self.period = index, period_s
+        self.samples: list[tuple[float, int, float, int]] = []  # (t, sm_mhz, power_w, reasons)
+        self._stop = threading.Event()
+        self._thread: threading.Thread | None = None
+        self.sm_max = None
+        self.error: str | None = None
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            self._nv = pynvml
+            self._h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.sm_max = float(pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM))
+        except Exception as exc:  # pragma: no cover - depends on the box
+            self._nv = None
+            self.error = f"NVML unavailable: {exc}"
+
+    def _poll(self) -> None:
+        nv = self._nv
+        while not self._stop.is_set():
+            try:
+                mhz = nv.nvmlDeviceGetClockInfo(self._h, nv.NVML_CLOCK_SM)
+                pw = nv.nvmlDeviceGetPowerUsage(self._h) / 1000.0
+                try:
+                    rs = nv.nvmlDeviceGetCurrentClocksEventReasons(self._h)
+                except Exception:
+                    rs = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self._h)
+                self.samples.append((time.perf_counter(), int(mhz), float(pw), int(rs)))
+            except Exception as exc:  # pragma: no cover
+                self.error = str(exc)
+                return
+            self._stop.wait(self.period)
 
     def start(self) -> None:
-        try:
-            self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "100"],
-                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-        except Exception:
-            self.proc = None
+        if self._nv is None:
             return
+        self._thread = threading.Thread(target=self._poll, daemon=True)
+        self._thread.start()
 
-        def pump() -> None:
-            assert self.proc and self.proc.stdout
-            for line in self.proc.stdout:
-                self.lines.append(line.strip())
-
-        self.thread = threading.Thread(target=pump, daemon=True)
-        self.thread.start()
-
-    def stop(self) -> dict:
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
-        sm, smax, reasons, power = [], [], set(), []
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
-            parts = [p.strip() for p in ln.split(",")]
-            if len(parts) < 7:
-                continue
-            try:
-                sm.append(float(parts[0]))
-                smax.append(float(parts[1]))
-                power.append(float(parts[2]))
-            except ValueError:
-                continue
-            for nm, val in zip(names, parts[3:7]):
-                if val.lower().startswith("active"):
-                    reasons.add(nm)
+    def stop(self, t0: float | None = None, t1: float | None = None) -> dict:
+        """Summary over the samples taken in [t0, t1] (perf_counter times); all samples if the window holds none."""
+        if self._thread is not None:
+            self._stop.set()
+            self._thread.join(timeout=1.0)
+        if self._nv is None or not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.sm_max, "reasons": [self.error or "no samples"], "samples": 0}
+        inside = [x for x in self.samples if (t0 is None or x[0] >= t0) and (t1 is None or x[0] <= t1)]
+        window = "timed region"
+        if not inside:
+            inside, window = self.samples, "warm-up + timed region (timed region shorter than one NVML poll)"
+        reasons = set()
+        for _, _, _, rs in inside:
+            for name, bit in self.REASONS.items():
+                if rs & bit:
+                    reasons.add(name)
         return {
-            "sm_mhz": float(np.median(sm)) if sm else None,
-            "sm_max_mhz": float(max(smax)) if smax else None,
-            "power_w_max": float(max(power)) if power else None,
-            "samples": len(sm),
+            "sm_mhz": float(np.median([x[1] for x in inside])),
+            "sm_max_mhz": self.sm_max,
+            "power_w_max": max(x[2] for x in inside),
+            "samples": len(inside),
+            "window": window,
             "reasons": sorted(reasons),
         }
 
@@ -261,20 +277,24 @@ def run_ours(args) -> None:
     # ---- device-resident throughput ("value") ---------------------------------------------------
     for _ in range(args.warmup):
         ctx.ingest(specs)
-    barrier()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+    for _ in range(args.warmup):
+        ctx.ingest(specs)
+    barrier()
     launches0 = ctx.launch_count
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_begin = time.perf_counter()
     ev0.record(stream)
     for _ in range(args.steps):
         ctx.ingest(specs)
     ev1.record(stream)
     barrier()
+    t_end = time.perf_counter()
     launches = ctx.launch_count - launches0
     ms = ev0.elapsed_time(ev1)
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop(t_begin, t_end) if rank == 0 else None
     t = torch.tensor([ms], dtype=torch.float64, device="cuda")
     if distributed:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -355,7 +375,7 @@ def run_ours(args) -> None:
             "gpu_launches": launches,
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "kernel": "rectify_tile_kernel<1>", "algorithmic_bytes_per_launch": algo_bytes,
+                         "traffic": None, "kernel": "rectify_mono_tma_kernel<32>", "algorithmic_bytes_per_launch": algo_bytes,
                          "peak_source": peak_src, "frac_of_8000_datasheet": achieved / 8000.0,
                          "note": "per-rank launch; duration = max-over-ranks ms_per_step (one launch per step)"},
             "cpu_baseline": cpu_baseline,
@@ -442,8 +462,8 @@ def run_extras(args, ctx, sources, maps, rank, world, distributed, barrier) -> d
 def main() -> None:
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=400)
+    ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=64, help="frame sets per step (per rank)")
     ap.add_argument("--e2e-batch", type=int, default=32, dest="e2e_batch")

@@ -97,7 +97,7 @@ def check_rectify(be, cam: int, mapx, mapy, s: str, d: str, src_w: int, src_h: i
         be.ctx.set_option(be.ctx.OPT_MONO_VARIANT, 3)
         be.ctx.set_option(be.ctx.OPT_TMA_TILE_H, 32)
         be.ctx.set_option(be.ctx.OPT_FRAMES_PER_UNIT, 8)
-        be.ctx.set_option(be.ctx.OPT_STAGES, 4)
+        be.ctx.set_option(be.ctx.OPT_STAGES, 3)
     mask = be.zeros((dst_h, dst_w), np.uint8)
     be.ctx.get_valid_mask(cam, mask)
     assert np.array_equal(be.host(mask), orc.valid_mask(mapx, mapy, (src_w, src_h)))

@@ -124,7 +124,7 @@ struct ti_ctx {
     int debug = 0;
     int mono_variant = 3;   // 3: TMA-pipelined kernel, 2: thread-staged kernel, 1: generic only
     int tma_tile_h = 32;    // 16 or 32
-    int stages = 4;           // shared-memory ring depth of the TMA-pipelined kernel
+    int stages = 3;           // shared-memory ring depth of the TMA-pipelined kernel
     int frames_per_unit = 8;  // frames of the batch that share one LUT fetch in the TMA-pipelined kernel
     bool force_generic_rectify = false;  // tests: exercise the generic tiled / direct kernels
     ti::CameraSlot cams[TI_MAX_CAMERAS];
