@@ -451,30 +451,20 @@ __global__ void __launch_bounds__(M3_THREADS) rectify_mono_tma_kernel(const __gr
             const uint4 h1 = *reinterpret_cast<const uint4*>(sb + hdr_off + 16);
             const uint32_t flags = *reinterpret_cast<const uint32_t*>(sb + hdr_off + 48);
             const int rows = (int)h1.y, nvec = (int)h1.z, rows_alloc = (int)h1.w;
-            // copy B[64 + i] = A[i + 1]: odd-x0 pairs become 2-byte aligned, 16 banks away from copy A
-            if (vc < nvec && vc < 12) {
+            // copy B[64 + i] = A[i + 1]: odd-x0 pairs become 2-byte aligned, 16 banks away from copy A.
+            // Every lane loads its 16-byte vector; the first word of the NEXT vector comes from the next
+            // lane by shuffle (lanes 0..15 / 16..31 of a warp hold the 16 vectors of one row each).
+            {
+                const int nv = min(nvec, 12);
                 const uint8_t* ap = sb + 128 + r0 * M3_PITCH + (vc << 4);
                 uint8_t* bp = sb + 128 + (size_t)rows_alloc * M3_PITCH + 64 + r0 * M3_PITCH + (vc << 4);
-                int row = r0;
-                for (; row + 3 * RSTEP < rows; row += 4 * RSTEP, ap += 4 * RSTEP * M3_PITCH, bp += 4 * RSTEP * M3_PITCH) {
-                    uint4 x[4];
-                    uint32_t nx[4];
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        x[k] = *reinterpret_cast<const uint4*>(ap + k * RSTEP * M3_PITCH);
-                        nx[k] = *reinterpret_cast<const uint32_t*>(ap + k * RSTEP * M3_PITCH + 16);
-                    }
-#pragma unroll
-                    for (int k = 0; k < 4; ++k)
-                        *reinterpret_cast<uint4*>(bp + k * RSTEP * M3_PITCH) =
-                            make_uint4(__funnelshift_r(x[k].x, x[k].y, 8), __funnelshift_r(x[k].y, x[k].z, 8),
-                                       __funnelshift_r(x[k].z, x[k].w, 8), __funnelshift_r(x[k].w, nx[k], 8));
-                }
-                for (; row < rows; row += RSTEP, ap += RSTEP * M3_PITCH, bp += RSTEP * M3_PITCH) {
+                const int rows_pad = (rows + RSTEP - 1) / RSTEP * RSTEP;  // warp-uniform trip count (rows_alloc >= rows_pad)
+                for (int row = r0; row < rows_pad; row += RSTEP, ap += RSTEP * M3_PITCH, bp += RSTEP * M3_PITCH) {
                     const uint4 x = *reinterpret_cast<const uint4*>(ap);
-                    const uint32_t nx = *reinterpret_cast<const uint32_t*>(ap + 16);
-                    *reinterpret_cast<uint4*>(bp) = make_uint4(__funnelshift_r(x.x, x.y, 8), __funnelshift_r(x.y, x.z, 8),
-                                                               __funnelshift_r(x.z, x.w, 8), __funnelshift_r(x.w, nx, 8));
+                    const uint32_t nx = __shfl_down_sync(0xFFFFFFFFu, x.x, 1);
+                    if (vc < nv && row < rows)
+                        *reinterpret_cast<uint4*>(bp) = make_uint4(__funnelshift_r(x.x, x.y, 8), __funnelshift_r(x.y, x.z, 8),
+                                                                   __funnelshift_r(x.z, x.w, 8), __funnelshift_r(x.w, nx, 8));
                 }
             }
             mbar_arrive(full + s);  // every producer thread: each releases its own shared-memory writes
