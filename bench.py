@@ -436,26 +436,60 @@ def run_extras(args, ctx, sources, maps, rank, world, distributed, barrier) -> d
                        "hbm_gbs": B * bytes_per_set / (ms * 1e-3) / 1e9, "frac": B * bytes_per_set / (ms * 1e-3) / 1e9 / peak,
                        "algorithmic_bytes_per_frame_set": bytes_per_set}}
     if distributed:
-        uid = [ctx.nccl_unique_id() if rank == 0 else None]
-        dist.broadcast_object_list(uid, src=0)
-        ctx.nccl_init(uid[0], rank, world)
+        from thor_slam_b200.ingest.distributed import CloudGather, PeerCloudBuffer
+
+        # (a) compute, then ONE grouped ncclSend/ncclRecv gather of the dense clouds on rank 0
+        gat = CloudGather(ctx, rank, world, root=0)
         nbytes = clouds.numel() * 4
         gathered = torch.empty((world, *clouds.shape), dtype=torch.float32, device="cuda") if rank == 0 else None
-        sizes = [nbytes] * world
         for _ in range(2):
-            ctx.gather_clouds(clouds, gathered, sizes, root=0)
+            gat.gather(clouds, gathered)
         barrier()
         g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         g0.record(stream)
         for _ in range(steps):
-            ctx.gather_clouds(clouds, gathered, sizes, root=0)
+            gat.gather(clouds, gathered)
         g1.record(stream)
         barrier()
         tg = torch.tensor([g0.elapsed_time(g1)], dtype=torch.float64, device="cuda")
         dist.all_reduce(tg, op=dist.ReduceOp.MAX)
         gms = float(tg.item()) / steps
-        out["config5"]["gather"] = {"ms": gms, "bytes_into_root": nbytes * (world - 1), "root_ingress_gbs": nbytes * (world - 1) / (gms * 1e-3) / 1e9,
-                                    "kind": "grouped ncclSend/ncclRecv, dense clouds"}
+        out["config5"]["gather_nccl"] = {"ms": gms, "bytes_into_root": nbytes * (world - 1),
+                                         "root_ingress_gbs": nbytes * (world - 1) / (gms * 1e-3) / 1e9,
+                                         "kind": "grouped ncclSend/ncclRecv of dense clouds after the kernel (includes the count all-gather)"}
+        if rank == 0:
+            out["config5"]["gather_nccl"]["matches_local"] = bool(torch.equal(gathered[0], clouds))
+        # (b) gather fused into the kernel: xyz stores go straight into rank 0's buffer over NVLink
+        peer = PeerCloudBuffer(ctx, rank, world, tuple(clouds.shape), root=0)
+        mine = peer.slice_for(rank)
+        fused_specs = []
+        for i in range(len(specs)):
+            sp = specs[i]
+            if sp.kind == F.KIND_BACKPROJECT:
+                cam_i = i // 2
+                sp = StreamSpec(F.KIND_BACKPROJECT, sp.src, mine.slice0(cam_i, cam_i + 1).__class__(
+                    mine.ptr + cam_i * clouds[0].numel() * 4, tuple(clouds[0].shape), 4), F.DEPTH16, F.XYZ32F,
+                    camera=sp.camera, mask=sp.mask, count=sp.count)
+            fused_specs.append(sp)
+        for _ in range(2):
+            ctx.ingest(fused_specs)
+        barrier()
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        f0.record(stream)
+        for _ in range(steps):
+            ctx.ingest(fused_specs)
+        f1.record(stream)
+        barrier()
+        tf = torch.tensor([f0.elapsed_time(f1)], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tf, op=dist.ReduceOp.MAX)
+        fms = float(tf.item()) / steps
+        out["config5"]["fused_peer_store"] = {"ms_per_step": fms, "frame_sets_per_sec": world * B / (fms * 1e-3),
+                                              "kind": "back-projection kernels store xyz into rank 0's buffer through CUDA-IPC peer mapping (gather fused into the kernel); barrier only"}
+        if rank == 0:
+            fused = peer.as_tensor()
+            out["config5"]["fused_peer_store"]["matches_local"] = bool(torch.equal(fused[0], clouds))
+        barrier()
+        peer.close()
     return out
 
 

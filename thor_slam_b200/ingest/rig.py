@@ -1,0 +1,312 @@
+"""``IngestRig`` - the drop-in behind ``CameraRig.get_synchronized_frames()``.
+
+Same constructor, same methods, same ``None``/exception behaviour as the reference's ``CameraRig``
+(``thor_slam/camera/rig.py:73-520`` - it *is* a subclass of our API mirror), but every frame set
+that leaves the rig has been through the GPU ingest stage:
+
+* SLAM streams: format conversion (mono8 pass-through, BGR8 -> rgb8, NV12 -> mono8 / rgb8) fused with
+  the stereo-rectification / undistortion remap (what the reference leaves to cuVSLAM by publishing
+  raw images with ``rectified_images:=false``);
+* RGB-D sources (duck-typed like ``LuxonisCameraSource``, ``drivers/luxonis.py:871-1091``): BGR8 ->
+  rgb8, and depth (u16 mm) -> body-frame FLU point cloud + valid mask + valid count (what the
+  reference leaves to nvblox).
+
+What changes relative to the reference (BASELINE.json north_star, "subsystems that change"):
+
+* frame-set assembly: the per-source ``deque(maxlen=queue_size)`` (``rig.py:113``) becomes a ring of
+  ``queue_size`` pinned host slots paired with ``queue_size`` device slots per stream; a driver read
+  is copied once into its pinned slot and uploaded asynchronously on a copy stream, so by the time a
+  frame set is matched its pixels are already in HBM;
+* calibration: ``Intrinsics`` / ``Extrinsics`` (``camera/types.py``) are turned once into remap LUTs
+  and 3x4 body transforms on the device (re-done on ``load_rig_extrinsics``).
+
+``CameraFrame.image`` of a returned frame is a :class:`DeviceImage` (ndarray-compatible, lazy device
+-> host copy); ``SynchronizedFrameSet.clouds`` maps source name -> ``{"points", "mask", "count"}``.
+"""
+
+from __future__ import annotations
+
+import logging
+from dataclasses import dataclass, field
+from typing import Any, Sequence
+
+import numpy as np
+import torch
+
+from thor_slam_b200.camera.calibration import Extrinsics, IMUExtrinsics
+from thor_slam_b200.camera.frames import CameraFrame, CameraSource, DeviceImage, FrameSet, SynchronizedFrameSet
+from thor_slam_b200.camera.rig import CameraRig
+from thor_slam_b200.ingest import formats as F
+from thor_slam_b200.ingest.calib import body_T_camera, stereo_rectify_maps
+from thor_slam_b200.ingest.context import IngestContext, StreamSpec
+
+logger = logging.getLogger(__name__)
+
+_TORCH_DTYPE = {F.MONO8: torch.uint8, F.BGR8: torch.uint8, F.RGB8: torch.uint8, F.NV12: torch.uint8,
+                F.DEPTH16: torch.uint16, F.XYZ32F: torch.float32}
+
+
+@dataclass
+class _Stream:
+    """One stream of one source: its formats, calibration slot and slot rings."""
+
+    source: str
+    index: int            # position in the source's frame list (0 left / 1 right / 0 rgb)
+    camera: int           # calibration slot in the ingest context
+    src_format: int
+    dst_format: int
+    src_size: tuple[int, int]   # (w, h)
+    dst_size: tuple[int, int]
+    kind: int
+    host: Any = None      # [queue_size, ...] pinned
+    dev: Any = None       # [queue_size, ...] device
+    out: Any = None       # [queue_size, ...] device, ingest output
+    mask: Any = None
+    count: Any = None
+
+
+@dataclass
+class _SlotFrameSet(FrameSet):
+    """Queue entry that remembers which ring slot holds its pixels."""
+
+    slot: int = -1
+    uploaded: Any = field(default=None, repr=False)  # event: H2D of this slot finished
+
+
+class IngestRig(CameraRig):
+    def __init__(
+        self,
+        sources: Sequence[CameraSource],
+        queue_size: int = 30,
+        rig_extrinsics: dict[str, Extrinsics] | None = None,
+        imu_extrinsics: IMUExtrinsics | None = None,
+        imu_source: str | None = None,
+        *,
+        device: int = 0,
+        rectify: bool = True,
+        rig_frame: str = "rdf",
+        color_output: str = "rgb8",
+        context: IngestContext | None = None,
+    ) -> None:
+        """Extra (keyword-only) arguments over the reference constructor:
+
+        ``device``: CUDA device index; ``rectify``: remap SLAM streams (False = conversion only);
+        ``rig_frame``: ``"rdf"`` (rig poses in the Luxonis convention, clouds rotated to FLU with
+        ``RDF_TO_FLU_MATRIX``) or ``"flu"``; ``color_output``: ``"rgb8"`` (what the reference's adapter
+        publishes for 3-channel frames) or ``"mono8"``; ``context``: share an ``IngestContext``.
+        """
+        super().__init__(sources, queue_size, rig_extrinsics, imu_extrinsics, imu_source)
+        self._ctx = context if context is not None else IngestContext(device)
+        self._emulated = self._ctx.lib.is_emulation
+        self._device = torch.device("cpu") if self._emulated else torch.device("cuda", device)
+        self._rectify = rectify
+        self._rig_frame = rig_frame
+        self._color_output = F.fmt(color_output)
+        self._streams: dict[str, list[_Stream]] = {}
+        self._rgbd: dict[str, tuple[_Stream, _Stream]] = {}
+        self._next_camera = 0
+        self._copy_stream = None if self._emulated else torch.cuda.Stream(device=self._device)
+        self._build_streams()
+        self._upload_calibration()
+
+    # -- setup -----------------------------------------------------------------
+    def _alloc(self, shape: tuple[int, ...], fmt: int, pinned: bool = False) -> Any:
+        dt = _TORCH_DTYPE[fmt]
+        if pinned:
+            t = torch.zeros(shape, dtype=dt)
+            return t if self._emulated else t.pin_memory()
+        return torch.zeros(shape, dtype=dt, device=self._device)
+
+    def _new_camera(self) -> int:
+        cam = self._next_camera
+        self._next_camera += 1
+        return cam
+
+    def _build_streams(self) -> None:
+        q = self.queue_size
+        for name, src in self.sources.items():
+            intr = self._calibration.intrinsics[name]
+            fmts = getattr(src, "get_stream_formats", None)
+            names = fmts() if callable(fmts) else [None] * len(intr)
+            streams = []
+            for i, (it, fname) in enumerate(zip(intr, names)):
+                sfmt = F.fmt(fname) if fname is not None else None
+                size = (int(it.width), int(it.height))
+                st = _Stream(name, i, self._new_camera(), sfmt if sfmt is not None else -1, -1, size, size,
+                             F.KIND_RECTIFY if self._rectify else F.KIND_CONVERT)
+                streams.append(st)
+            self._streams[name] = streams
+            if getattr(src, "has_rgbd_streams", False):
+                ri, di = src.get_rgbd_intrinsics()
+                rgb = _Stream(name, 0, self._new_camera(), F.BGR8, F.RGB8, (ri.width, ri.height), (ri.width, ri.height), F.KIND_CONVERT)
+                dep = _Stream(name, 1, self._new_camera(), F.DEPTH16, F.XYZ32F, (di.width, di.height), (di.width, di.height), F.KIND_BACKPROJECT)
+                for st in (rgb, dep):
+                    self._alloc_stream(st, 2)
+                self._rgbd[name] = (rgb, dep)
+        del q
+
+    def _alloc_stream(self, st: _Stream, slots: int) -> None:
+        w, h = st.src_size
+        dw, dh = st.dst_size
+        st.host = self._alloc((slots, *F.frame_shape(st.src_format, w, h)), st.src_format, pinned=True)
+        st.dev = self._alloc((slots, *F.frame_shape(st.src_format, w, h)), st.src_format)
+        st.out = self._alloc((slots, *F.frame_shape(st.dst_format, dw, dh)), st.dst_format)
+        if st.kind == F.KIND_BACKPROJECT:
+            st.mask = self._alloc((slots, dh, dw), F.MONO8)
+            st.count = torch.zeros((slots,), dtype=torch.int32, device=self._device)
+
+    def _resolve_format(self, st: _Stream, image: np.ndarray) -> None:
+        """First frame of a stream: fix its wire format (the reference decides by ndim, isaac_ros.py:351-358)."""
+        if st.src_format < 0:
+            st.src_format = F.infer_format(image)
+        if st.src_format == F.MONO8 or (st.src_format == F.NV12 and self._color_output == F.MONO8):
+            st.dst_format = F.MONO8
+        elif st.src_format == F.NV12:
+            st.dst_format = self._color_output
+        else:
+            st.dst_format = self._color_output  # BGR8 -> rgb8 (reference) or mono8
+        self._alloc_stream(st, self.queue_size)
+
+    def _upload_calibration(self) -> None:
+        cal = self._calibration
+        for name, streams in self._streams.items():
+            intr, extr = cal.intrinsics[name], cal.extrinsics[name]
+            if self._rectify:
+                size = streams[0].src_size
+                maps = stereo_rectify_maps(intr, extr, size)
+                for st, (mx, my) in zip(streams, maps):
+                    self._ctx.upload_rectify_map(st.camera, mx, my, st.src_size)
+        for name, (_rgb, dep) in self._rgbd.items():
+            src = self.sources[name]
+            _ri, di = src.get_rgbd_intrinsics()
+            _re, de = src.get_rgbd_extrinsics()
+            rig_pose = cal.rig_extrinsics.get(name)
+            m = body_T_camera(None if rig_pose is None else rig_pose.to_4x4_matrix(), de.to_4x4_matrix(), self._rig_frame)
+            self._ctx.upload_projection(dep.camera, di.matrix, m, dep.src_size)
+
+    def _on_calibration_changed(self) -> None:
+        if hasattr(self, "_streams"):
+            self._upload_calibration()
+
+    # -- frame-set assembly: pinned ring + async upload -------------------------------
+    def _stage(self, st: _Stream, slot: int, image: np.ndarray) -> None:
+        host = st.host[slot]
+        src = torch.from_numpy(np.ascontiguousarray(image))
+        if src.dtype != host.dtype:
+            src = src.view(host.dtype)
+        if tuple(src.shape) != tuple(host.shape):
+            raise ValueError(f"{st.source}[{st.index}]: frame shape {tuple(src.shape)} does not match the calibrated {tuple(host.shape)}")
+        host.copy_(src)
+        if self._emulated:
+            st.dev[slot].copy_(host)
+        else:
+            with torch.cuda.stream(self._copy_stream):
+                st.dev[slot].copy_(host, non_blocking=True)
+
+    def _wrap_frames(self, name: str, frames: list) -> FrameSet:
+        streams = self._streams[name]
+        slot = self._frame_queues[name].next_slot()
+        staged = []
+        for st, fr in zip(streams, frames):
+            if st.host is None:
+                self._resolve_format(st, fr.image)
+            self._stage(st, slot, np.asarray(fr.image))
+            view = st.host[slot].numpy() if st.host.dtype != torch.uint16 else st.host[slot].view(torch.int16).numpy().view(np.uint16)
+            staged.append(CameraFrame(view, fr.timestamp, fr.sequence_num, fr.camera_name))
+        ev = None
+        if not self._emulated:
+            ev = torch.cuda.Event()
+            ev.record(self._copy_stream)
+        return _SlotFrameSet(timestamp=staged[0].timestamp, frames=staged, source_name=name, slot=slot, uploaded=ev)
+
+    # -- the ingest stage itself ------------------------------------------------------
+    def _finish(self, sync: SynchronizedFrameSet) -> SynchronizedFrameSet:
+        specs: list[StreamSpec] = []
+        outputs: dict[str, list[tuple[_Stream, int]]] = {}
+        if not self._emulated:
+            cur = torch.cuda.current_stream(self._device)
+            self._ctx.set_stream(cur.cuda_stream)
+        for name, fs in sync.frame_sets.items():
+            slot = getattr(fs, "slot", -1)
+            if slot < 0:
+                return sync  # not one of ours (e.g. injected by a test): pass through untouched
+            if fs.uploaded is not None:
+                torch.cuda.current_stream(self._device).wait_event(fs.uploaded)
+            for st in self._streams[name]:
+                specs.append(StreamSpec(st.kind, st.dev[slot:slot + 1], st.out[slot:slot + 1], st.src_format, st.dst_format,
+                                        camera=st.camera, width=st.src_size[0], height=st.src_size[1]))
+                outputs.setdefault(name, []).append((st, slot))
+        self._ctx.ingest(specs)
+        ready = None
+        if not self._emulated:
+            ready = torch.cuda.Event()
+            ready.record(torch.cuda.current_stream(self._device))
+        out_sets: dict[str, FrameSet] = {}
+        for name, fs in sync.frame_sets.items():
+            frames = [CameraFrame(DeviceImage(st.out[slot], ready), fr.timestamp, fr.sequence_num, fr.camera_name)
+                      for (st, slot), fr in zip(outputs[name], fs.frames)]
+            out_sets[name] = FrameSet(fs.timestamp, frames, fs.source_name, fs.sensor_data, fs.sensor_timestamp)
+        return SynchronizedFrameSet(sync.timestamp, out_sets, sync.max_time_delta, sync.sensor_data, sync.sensor_timestamp)
+
+    # -- RGB-D (bypasses the synchroniser in the reference too: run_pipeline.py:624-631) --------
+    def get_rgbd(self, source_name: str, blocking: bool = False) -> dict | None:
+        """Latest RGB-D pair of ``source_name`` through the ingest stage.
+
+        Returns ``{"rgb": CameraFrame(rgb8), "depth": CameraFrame(u16 mm, untouched), "points": DeviceImage
+        HxWx3 f32 body frame, "mask": DeviceImage HxW u8, "count": int tensor}`` or ``None`` when the
+        source has no new pair (or is not an RGB-D source / the rig is stopped).
+        """
+        if not self._running or source_name not in self._rgbd:
+            return None
+        src = self.sources[source_name]
+        pair = src.get_latest_rgbd_frames() if blocking else src.try_get_latest_rgbd_frames()
+        if pair is None:
+            return None
+        rgb_f, dep_f = pair
+        rgb, dep = self._rgbd[source_name]
+        slot = int(rgb_f.sequence_num) % 2
+        self._stage(rgb, slot, np.asarray(rgb_f.image))
+        self._stage(dep, slot, np.asarray(dep_f.image))
+        if not self._emulated:
+            ev = torch.cuda.Event()
+            ev.record(self._copy_stream)
+            cur = torch.cuda.current_stream(self._device)
+            cur.wait_event(ev)
+            self._ctx.set_stream(cur.cuda_stream)
+        self._ctx.ingest([
+            StreamSpec(F.KIND_CONVERT, rgb.dev[slot:slot + 1], rgb.out[slot:slot + 1], F.BGR8, F.RGB8, width=rgb.src_size[0], height=rgb.src_size[1]),
+            StreamSpec(F.KIND_BACKPROJECT, dep.dev[slot:slot + 1], dep.out[slot:slot + 1], F.DEPTH16, F.XYZ32F, camera=dep.camera,
+                       mask=dep.mask[slot:slot + 1], count=dep.count[slot:slot + 1]),
+        ])
+        ready = None
+        if not self._emulated:
+            ready = torch.cuda.Event()
+            ready.record(torch.cuda.current_stream(self._device))
+        return {
+            "rgb": CameraFrame(DeviceImage(rgb.out[slot], ready), rgb_f.timestamp, rgb_f.sequence_num, rgb_f.camera_name),
+            "depth": dep_f,
+            "points": DeviceImage(dep.out[slot], ready),
+            "mask": DeviceImage(dep.mask[slot], ready),
+            "count": dep.count[slot],
+        }
+
+    def get_synchronized_frames(self, max_wait_ms: float = 100.0, with_clouds: bool = False) -> SynchronizedFrameSet | None:
+        """Reference signature plus ``with_clouds``: attach the RGB-D clouds of every RGB-D source."""
+        sync = super().get_synchronized_frames(max_wait_ms)
+        if sync is not None and with_clouds and self._rgbd:
+            clouds = {}
+            for name in self._rgbd:
+                got = self.get_rgbd(name)
+                if got is not None:
+                    clouds[name] = got
+            sync.clouds = clouds or None
+        return sync
+
+    @property
+    def ingest_context(self) -> IngestContext:
+        return self._ctx
+
+    def stop(self) -> None:
+        super().stop()
+        if not self._emulated:
+            torch.cuda.synchronize(self._device)
