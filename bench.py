@@ -436,7 +436,7 @@ def run_extras(args, ctx, sources, maps, rank, world, distributed, barrier) -> d
                        "hbm_gbs": B * bytes_per_set / (ms * 1e-3) / 1e9, "frac": B * bytes_per_set / (ms * 1e-3) / 1e9 / peak,
                        "algorithmic_bytes_per_frame_set": bytes_per_set}}
     if distributed:
-        from thor_slam_b200.ingest.distributed import CloudGather, PeerCloudBuffer
+        from thor_slam_b200.ingest.distributed import CloudGather, PeerCloudBuffer, RawDeviceBuffer
 
         # (a) compute, then ONE grouped ncclSend/ncclRecv gather of the dense clouds on rank 0
         gat = CloudGather(ctx, rank, world, root=0)
@@ -467,9 +467,8 @@ def run_extras(args, ctx, sources, maps, rank, world, distributed, barrier) -> d
             sp = specs[i]
             if sp.kind == F.KIND_BACKPROJECT:
                 cam_i = i // 2
-                sp = StreamSpec(F.KIND_BACKPROJECT, sp.src, mine.slice0(cam_i, cam_i + 1).__class__(
-                    mine.ptr + cam_i * clouds[0].numel() * 4, tuple(clouds[0].shape), 4), F.DEPTH16, F.XYZ32F,
-                    camera=sp.camera, mask=sp.mask, count=sp.count)
+                dst = RawDeviceBuffer(mine.ptr + cam_i * clouds[0].numel() * 4, tuple(clouds[0].shape), 4)
+                sp = StreamSpec(F.KIND_BACKPROJECT, sp.src, dst, F.DEPTH16, F.XYZ32F, camera=sp.camera, mask=sp.mask, count=sp.count)
             fused_specs.append(sp)
         for _ in range(2):
             ctx.ingest(fused_specs)
