@@ -63,22 +63,34 @@ __device__ __forceinline__ void project(const BpCam& c, float bx, float by, floa
 __global__ void __launch_bounds__(BP_THREADS) backproject_vec_kernel(const __grid_constant__ BpParams P) {
     __shared__ float4 xbuf[BP_THREADS / 32][32 * BP_LANE_STRIDE];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const uint64_t total = (uint64_t)P.tiles_per_set * P.n_batch;
-    for (uint64_t t = blockIdx.x; t < total; t += gridDim.x) {
-        const uint32_t b = (uint32_t)(t / P.tiles_per_set);
-        const uint32_t r = (uint32_t)(t - (uint64_t)b * P.tiles_per_set);
-        int j = 0;
+    // tile walk with a stride of gridDim.x, decoded incrementally (no 64-bit divisions per 8 pixels);
+    // the depth vector of the NEXT tile is requested before the current one is processed.
+    struct Cur { int j; uint32_t b, p0, warp_p0, npx; bool live; uint4 dv; };
+    uint32_t r = blockIdx.x, b = 0;
+    int j = 0;
+    auto fetch = [&](Cur& c) {
+        while (r >= P.tiles_per_set) { r -= P.tiles_per_set; ++b; j = 0; }
+        c.live = b < (uint32_t)P.n_batch;
+        c.dv = make_uint4(0u, 0u, 0u, 0u);
+        if (!c.live) return;
         while (j + 1 < P.n_jobs && r >= P.job[j + 1].tile_begin) ++j;
         const BpJobDev& J = P.job[j];
-        const uint32_t tile = r - J.tile_begin;
-        const uint32_t npx = (uint32_t)J.cam.width * J.cam.height;
-        const uint32_t warp_p0 = tile * BP_TILE + warp * (32 * BP_PX_PER_THREAD);
-        const uint32_t p0 = warp_p0 + lane * BP_PX_PER_THREAD;
+        c.j = j; c.b = b;
+        c.npx = (uint32_t)J.cam.width * J.cam.height;
+        c.warp_p0 = (r - J.tile_begin) * BP_TILE + warp * (32 * BP_PX_PER_THREAD);
+        c.p0 = c.warp_p0 + lane * BP_PX_PER_THREAD;
+        if (c.p0 < c.npx) c.dv = ld_stream_u4(J.depth + (uint64_t)b * (J.depth_stride / 2) + c.p0);
+        r += gridDim.x;
+    };
+    Cur cur, nxt;
+    fetch(cur);
+    while (cur.live) {
+        fetch(nxt);
+        const BpJobDev& J = P.job[cur.j];
+        const uint32_t p0 = cur.p0, npx = cur.npx, warp_p0 = cur.warp_p0;
         uint32_t nvalid = 0;
         if (p0 < npx) {  // width % 8 == 0 -> a thread's 8 pixels never straddle a row or the frame end
-            const uint16_t* dp = J.depth + (uint64_t)b * (J.depth_stride / 2) + p0;
-            const uint4 dv = ld_stream_u4(dp);
-            const uint32_t dw[4] = {dv.x, dv.y, dv.z, dv.w};
+            const uint32_t dw[4] = {cur.dv.x, cur.dv.y, cur.dv.z, cur.dv.w};
             const int v = (int)(p0 / (uint32_t)J.cam.width), u0 = (int)(p0 - (uint32_t)v * J.cam.width);
             const float fv = (float)v - J.cam.cy;
             const float bx = __fmaf_rn(J.cam.a[1], fv, J.cam.a[2]);
@@ -94,7 +106,7 @@ __global__ void __launch_bounds__(BP_THREADS) backproject_vec_kernel(const __gri
                 nvalid += ok;
                 if (k < 4) m0 |= ok << (8 * k); else m1 |= ok << (8 * (k - 4));
             }
-            if (J.mask) st_stream_u2(J.mask + (uint64_t)b * J.mask_stride + p0, make_uint2(m0, m1));
+            if (J.mask) st_stream_u2(J.mask + (uint64_t)cur.b * J.mask_stride + p0, make_uint2(m0, m1));
 #pragma unroll
             for (int q = 0; q < 6; ++q)
                 xbuf[warp][lane * BP_LANE_STRIDE + q] = make_float4(f[4 * q], f[4 * q + 1], f[4 * q + 2], f[4 * q + 3]);
@@ -104,7 +116,7 @@ __global__ void __launch_bounds__(BP_THREADS) backproject_vec_kernel(const __gri
         if (warp_p0 < npx) {
             const uint32_t live_px = min((uint32_t)(32 * BP_PX_PER_THREAD), npx - warp_p0);
             const uint32_t live_q = live_px * 3 / 4;  // live_px is a multiple of 8
-            float4* out = reinterpret_cast<float4*>(J.xyz + (uint64_t)b * (J.xyz_stride / 4) + (uint64_t)warp_p0 * 3);
+            float4* out = reinterpret_cast<float4*>(J.xyz + (uint64_t)cur.b * (J.xyz_stride / 4) + (uint64_t)warp_p0 * 3);
 #pragma unroll
             for (int i = 0; i < 6; ++i) {
                 const uint32_t q = i * 32 + lane;
@@ -118,8 +130,9 @@ __global__ void __launch_bounds__(BP_THREADS) backproject_vec_kernel(const __gri
         __syncwarp();
         if (J.count) {
             const uint32_t wsum = __reduce_add_sync(0xFFFFFFFFu, nvalid);
-            if (lane == 0 && wsum) atomicAdd(J.count + b, wsum);
+            if (lane == 0 && wsum) atomicAdd(J.count + cur.b, wsum);
         }
+        cur = nxt;
     }
 }
 
@@ -197,7 +210,8 @@ int launch_backproject(ti_ctx* ctx, const BackprojectJob* jobs, int n_jobs, int 
         P.n_jobs = nv;
         P.n_batch = n_batch;
         const uint64_t total = (uint64_t)tiles * n_batch;
-        const int grid = (int)std::min<uint64_t>(total, (uint64_t)ctx->sm_count * 8);
+        static const int per_sm = resident_ctas(backproject_vec_kernel, BP_THREADS, 0, 4);
+        const int grid = (int)std::min<uint64_t>(total, (uint64_t)ctx->sm_count * (ctx->ctas_per_sm > 0 ? ctx->ctas_per_sm : per_sm));
         TI_LAUNCH(backproject_vec_kernel, grid, BP_THREADS, 0, ctx->stream, P);
         TI_CHECK_LAUNCH(ctx);
     }

@@ -169,6 +169,22 @@ void set_global_error(const char* msg);
     } while (0)
 #endif
 
+// Resident CTAs per SM of a persistent kernel (cached per kernel): grids are sized to exactly one wave.
+template <typename K>
+inline int resident_ctas(K kernel, int threads, size_t dyn_smem, int fallback) {
+#ifdef TI_EMULATE
+    (void)kernel; (void)threads; (void)dyn_smem;
+    return fallback > 2 ? 2 : fallback;
+#else
+    int n = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, threads, dyn_smem) != cudaSuccess || n <= 0) {
+        cudaGetLastError();
+        return fallback;
+    }
+    return n;
+#endif
+}
+
 inline int channels_of(int fmt) {
     switch (fmt) {
         case TI_FMT_MONO8: return 1;

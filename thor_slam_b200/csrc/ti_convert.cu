@@ -210,7 +210,8 @@ int launch_convert(ti_ctx* ctx, const ConvertJob* jobs, int n_jobs, int n_batch)
     P.n_batch = n_batch;
     const uint64_t total = (uint64_t)units * n_batch;
     const uint64_t want = (total + CV_THREADS - 1) / CV_THREADS;
-    const int grid = (int)std::min<uint64_t>(want, (uint64_t)ctx->sm_count * 8);
+    static const int per_sm = resident_ctas(convert_vec_kernel, CV_THREADS, 0, 4);
+    const int grid = (int)std::min<uint64_t>(want, (uint64_t)ctx->sm_count * per_sm);
     TI_LAUNCH(convert_vec_kernel, grid, CV_THREADS, 0, ctx->stream, P);
     TI_CHECK_LAUNCH(ctx);
     return TI_OK;

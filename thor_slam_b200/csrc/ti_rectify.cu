@@ -629,9 +629,7 @@ static int launch_tiled(ti_ctx* ctx, RectParams& P, size_t smem_bytes) {
         cfg = RT_MAX_SMEM;
     }
 #endif
-    // resident CTAs per SM are bounded by shared memory (228 KB/SM) and by 2048 threads/SM
-    int per_sm = (int)std::min<size_t>(8, (size_t)(220 * 1024) / std::max<size_t>(smem_bytes + 1024, 1));
-    per_sm = std::max(per_sm, 1);
+    const int per_sm = resident_ctas(rectify_tile_kernel<C>, RT_THREADS, smem_bytes, 4);
     const int grid = (int)std::min<uint64_t>(total, (uint64_t)ctx->sm_count * per_sm);
     TI_LAUNCH(rectify_tile_kernel<C>, grid, RT_THREADS, smem_bytes, ctx->stream, P);
     TI_CHECK_LAUNCH(ctx);
@@ -722,8 +720,8 @@ int launch_rectify(ti_ctx* ctx, const RectifyJob* jobs, int n_jobs, int n_batch)
         else
             TI_CUDA(ctx, cudaFuncSetAttribute(rectify_mono_tma_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 #endif
-        int per_sm = (int)std::min<size_t>(2048 / M3_THREADS, (size_t)(226 * 1024) / (smem + 1024));
-        per_sm = std::max(per_sm, 1);
+        int per_sm = thk == 0 ? resident_ctas(rectify_mono_tma_kernel<16>, M3_THREADS, smem, 3)
+                              : resident_ctas(rectify_mono_tma_kernel<32>, M3_THREADS, smem, 3);
         if (ctx->ctas_per_sm > 0) per_sm = ctx->ctas_per_sm;
         const int grid = (int)std::min<uint64_t>(total, (uint64_t)ctx->sm_count * per_sm);
         if (thk == 0) TI_LAUNCH(rectify_mono_tma_kernel<16>, grid, M3_THREADS, smem, ctx->stream, PT);
@@ -740,8 +738,7 @@ int launch_rectify(ti_ctx* ctx, const RectifyJob* jobs, int n_jobs, int n_batch)
             configured = true;
         }
 #endif
-        int per_sm = (int)std::min<size_t>(6, (size_t)(224 * 1024) / (smem2 + 1024));
-        per_sm = std::max(per_sm, 1);
+        int per_sm = resident_ctas(rectify_mono_kernel, M2_THREADS, smem2, 4);
         if (ctx->ctas_per_sm > 0) per_sm = ctx->ctas_per_sm;
         const int grid = (int)std::min<uint64_t>(total, (uint64_t)ctx->sm_count * per_sm);
         TI_LAUNCH(rectify_mono_kernel, grid, M2_THREADS, smem2, ctx->stream, P2);

@@ -105,10 +105,15 @@ def main() -> None:
         dpx = ND * B * W * H
         report("backproject depth->xyz+mask+count", timeit(lambda: ctx.ingest(bspecs), args.iters), 15 * dpx, dpx)
         report("torch copy_ xyz (24 B/px traffic)", timeit(lambda: [xyz[i].copy_(xyz[(i + 1) % ND]) for i in range(ND)], args.iters), 24 * dpx, dpx)
+        report("torch fill_ xyz (12 B/px, write only)", timeit(lambda: [xyz[i].fill_(1.0) for i in range(ND)], args.iters), 12 * dpx, dpx)
+        for per_sm in (2, 3, 4, 6, 8):
+            ctx.set_option(ctx.OPT_CTAS_PER_SM, per_sm)
+            report(f"backproject ctas/sm={per_sm}", timeit(lambda: ctx.ingest(bspecs), args.iters), 15 * dpx, dpx)
+        ctx.set_option(ctx.OPT_CTAS_PER_SM, 0)
         del xyz, mask, depth
 
     if not args.only or "conv" in args.only:
-        CW, CH, NB = 1920, 1080, max(2, B // 4)
+        CW, CH, NB = 1920, 1080, max(2, B)  # >= 32 frames: 199 MB in, far beyond L2
         bgr = torch.randint(0, 256, (NB, CH, CW, 3), dtype=torch.uint8, device="cuda")
         rgb = torch.empty_like(bgr)
         gray = torch.empty((NB, CH, CW), dtype=torch.uint8, device="cuda")
