@@ -63,16 +63,25 @@ __device__ __forceinline__ void project(const BpCam& c, float bx, float by, floa
 __global__ void __launch_bounds__(BP_THREADS) backproject_vec_kernel(const __grid_constant__ BpParams P) {
     __shared__ float4 xbuf[BP_THREADS / 32][32 * BP_LANE_STRIDE];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    // tile walk with a stride of gridDim.x, decoded incrementally (no 64-bit divisions per 8 pixels);
-    // the depth vector of the NEXT tile is requested before the current one is processed.
+    // Every CTA owns a CONTIGUOUS run of tiles (decoded incrementally: no divisions per 8 pixels), so a
+    // warp sees at most a couple of (frame, stream) changes and can keep the valid count in a register:
+    // one atomic per warp per frame instead of one per warp per tile (same-address atomics serialise in
+    // L2: per-tile atomics alone cost as much as the whole kernel).  The depth vector of the NEXT tile is
+    // requested before the current one is processed.
     struct Cur { int j; uint32_t b, p0, warp_p0, npx; bool live; uint4 dv; };
-    uint32_t r = blockIdx.x, b = 0;
+    const uint64_t total = (uint64_t)P.tiles_per_set * P.n_batch;
+    const uint64_t chunk = (total + gridDim.x - 1) / gridDim.x;
+    const uint64_t t_begin = (uint64_t)blockIdx.x * chunk;
+    uint64_t left = t_begin < total ? (total - t_begin < chunk ? total - t_begin : chunk) : 0;  // tiles still to fetch
+    uint32_t b = (uint32_t)(t_begin / P.tiles_per_set);
+    uint32_t r = (uint32_t)(t_begin - (uint64_t)b * P.tiles_per_set);
     int j = 0;
     auto fetch = [&](Cur& c) {
-        while (r >= P.tiles_per_set) { r -= P.tiles_per_set; ++b; j = 0; }
-        c.live = b < (uint32_t)P.n_batch;
+        c.live = left > 0;
         c.dv = make_uint4(0u, 0u, 0u, 0u);
         if (!c.live) return;
+        --left;
+        if (r >= P.tiles_per_set) { r = 0; ++b; j = 0; }
         while (j + 1 < P.n_jobs && r >= P.job[j + 1].tile_begin) ++j;
         const BpJobDev& J = P.job[j];
         c.j = j; c.b = b;
@@ -80,10 +89,17 @@ __global__ void __launch_bounds__(BP_THREADS) backproject_vec_kernel(const __gri
         c.warp_p0 = (r - J.tile_begin) * BP_TILE + warp * (32 * BP_PX_PER_THREAD);
         c.p0 = c.warp_p0 + lane * BP_PX_PER_THREAD;
         if (c.p0 < c.npx) c.dv = ld_stream_u4(J.depth + (uint64_t)b * (J.depth_stride / 2) + c.p0);
-        r += gridDim.x;
+        ++r;
     };
     Cur cur, nxt;
     fetch(cur);
+    uint32_t acc = 0, acc_b = cur.b;  // this lane's running valid count for (acc_j, acc_b)
+    int acc_j = cur.j;
+    auto flush = [&]() {
+        const uint32_t wsum = __reduce_add_sync(0xFFFFFFFFu, acc);
+        if (lane == 0 && wsum && P.job[acc_j].count) atomicAdd(P.job[acc_j].count + acc_b, wsum);
+        acc = 0;
+    };
     while (cur.live) {
         fetch(nxt);
         const BpJobDev& J = P.job[cur.j];
@@ -128,12 +144,14 @@ __global__ void __launch_bounds__(BP_THREADS) backproject_vec_kernel(const __gri
             }
         }
         __syncwarp();
-        if (J.count) {
-            const uint32_t wsum = __reduce_add_sync(0xFFFFFFFFu, nvalid);
-            if (lane == 0 && wsum) atomicAdd(J.count + cur.b, wsum);
+        if (cur.j != acc_j || cur.b != acc_b) {  // warp-uniform
+            flush();
+            acc_j = cur.j; acc_b = cur.b;
         }
+        acc += nvalid;
         cur = nxt;
     }
+    flush();
 }
 
 // any width / alignment: one pixel per thread
