@@ -109,10 +109,14 @@ __device__ __forceinline__ void unit_nv12_to_color(const uint8_t* y0p, const uin
 __global__ void __launch_bounds__(CV_THREADS) convert_vec_kernel(const __grid_constant__ ConvertParams P) {
     const uint32_t units_per_set = P.unit_begin[P.n_jobs];
     const uint64_t total = (uint64_t)units_per_set * P.n_batch;
-    for (uint64_t t = (uint64_t)blockIdx.x * CV_THREADS + threadIdx.x; t < total;
-         t += (uint64_t)gridDim.x * CV_THREADS) {
-        const uint32_t b = (uint32_t)(t / units_per_set);
-        const uint32_t r = (uint32_t)(t - (uint64_t)b * units_per_set);
+    const uint64_t stride = (uint64_t)gridDim.x * CV_THREADS;
+    // (frame b, unit r) advanced incrementally: one division up front instead of one per 16 pixels
+    uint64_t t = (uint64_t)blockIdx.x * CV_THREADS + threadIdx.x;
+    uint32_t b = (uint32_t)(t / units_per_set);
+    uint64_t r64 = t - (uint64_t)b * units_per_set;
+    for (; t < total; t += stride, r64 += stride) {
+        while (r64 >= units_per_set) { r64 -= units_per_set; ++b; }
+        const uint32_t r = (uint32_t)r64;
         int j = 0;
         while (j + 1 < P.n_jobs && r >= P.unit_begin[j + 1]) ++j;
         const ConvertJob& J = P.job[j];
