@@ -404,7 +404,7 @@ __global__ void __launch_bounds__(M3_THREADS) rectify_mono_tma_kernel(const __gr
             const uint32_t b = cur.b0 + f;
             const int s = is;
             uint8_t* sb = stage0 + (size_t)s * stage_bytes;
-            mbar_wait(empty + s, iphase);  // consumers have released the stage's previous item
+            mbar_wait_relaxed(empty + s, iphase);  // consumers have released the stage's previous item
             if (rows > 0) tma_load_3d(sb + 128, &P.map[cur.j], c0, y0, (int)b, raw + s);  // one box: 256 x rows_alloc bytes
             const bool last_of_unit = f + 1 == cur.nb;
             const bool have_next = k_next < units_mine;
@@ -447,7 +447,7 @@ __global__ void __launch_bounds__(M3_THREADS) rectify_mono_tma_kernel(const __gr
         uint32_t phase = 0;
         for (uint32_t i = 0;; ++i) {
             uint8_t* sb = stage0 + (size_t)s * stage_bytes;
-            mbar_wait(raw + s, phase);
+            mbar_wait_relaxed(raw + s, phase);
             const uint4 h1 = *reinterpret_cast<const uint4*>(sb + hdr_off + 16);
             const uint32_t flags = *reinterpret_cast<const uint32_t*>(sb + hdr_off + 48);
             const int rows = (int)h1.y, nvec = (int)h1.z, rows_alloc = (int)h1.w;

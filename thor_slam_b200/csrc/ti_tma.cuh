@@ -54,6 +54,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     EmuMbar* m = reinterpret_cast<EmuMbar*>(bar);
     while ((__atomic_load_n(&m->completed, __ATOMIC_ACQUIRE) & 1u) == parity) std::this_thread::yield();
 }
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity) { mbar_wait(bar, parity); }
 __device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
     EmuMbar* m = reinterpret_cast<EmuMbar*>(bar);
     return (__atomic_load_n(&m->completed, __ATOMIC_ACQUIRE) & 1u) != parity;
@@ -98,6 +99,23 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         "}\n" ::"r"(smem_u32(bar)),
         "r"(parity)
         : "memory");
+}
+// Wait used by the producer side (not latency critical): back off between probes so the spinning warp
+// does not eat issue slots the consumer warps need.
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(done)
+            : "r"(smem_u32(bar)), "r"(parity), "r"(2000u)   // suspend-time hint (ns)
+            : "memory");
+        if (!done) __nanosleep(200);
+    } while (!done);
 }
 __device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {  // one non-blocking probe
     uint32_t ok;
