@@ -79,14 +79,15 @@ def check_rectify(be, cam: int, mapx, mapy, s: str, d: str, src_w: int, src_h: i
     # every kernel variant must give the same bytes: TMA-pipelined (tile height 32 and 16), thread-staged, generic
     # (the TMA kernel also with 1 and 2 frames of the batch per LUT fetch)
     mono = d == "mono8" and s in ("mono8", "nv12")
-    variants = [(3, 32, 8), (3, 16, 2), (3, 32, 1), (2, 32, 8), (1, 32, 8)] if mono else [(3, 32, 8), (1, 32, 8)]
-    stages = {8: 4, 2: 3, 1: 6}
+    variants = [(3, 32, 8), (3, 16, 2), (3, 24, 3), (3, 32, 1), (2, 32, 8), (1, 32, 8)] if mono else [(3, 32, 8), (1, 32, 8)]
+    stages = {8: 4, 2: 3, 3: 2, 1: 6}
     try:
         for variant, th, fpu in variants:
             be.ctx.set_option(be.ctx.OPT_MONO_VARIANT, variant)
             be.ctx.set_option(be.ctx.OPT_TMA_TILE_H, th)
             be.ctx.set_option(be.ctx.OPT_FRAMES_PER_UNIT, fpu)
             be.ctx.set_option(be.ctx.OPT_STAGES, stages[fpu])
+            be.ctx.set_option(be.ctx.OPT_LUT_PREFETCH, 0 if fpu == 3 else 1)
             dst = be.zeros((n, *F.frame_shape(F.fmt(d), dst_w, dst_h)), np.uint8)
             be.ctx.rectify(cam, be.dev(src), dst, s, d)
             got = be.host(dst)
@@ -98,6 +99,7 @@ def check_rectify(be, cam: int, mapx, mapy, s: str, d: str, src_w: int, src_h: i
         be.ctx.set_option(be.ctx.OPT_TMA_TILE_H, 32)
         be.ctx.set_option(be.ctx.OPT_FRAMES_PER_UNIT, 8)
         be.ctx.set_option(be.ctx.OPT_STAGES, 3)
+        be.ctx.set_option(be.ctx.OPT_LUT_PREFETCH, 1)
     mask = be.zeros((dst_h, dst_w), np.uint8)
     be.ctx.get_valid_mask(cam, mask)
     assert np.array_equal(be.host(mask), orc.valid_mask(mapx, mapy, (src_w, src_h)))

@@ -35,7 +35,7 @@ static void free_camera(CameraSlot& c) {
     if (c.d_valid) cudaFree(c.d_valid);
     if (c.d_lut2) cudaFree(c.d_lut2);
     if (c.d_boxes2) cudaFree(c.d_boxes2);
-    for (int k = 0; k < 2; ++k) {
+    for (int k = 0; k < 3; ++k) {
         if (c.d_lut3[k]) cudaFree(c.d_lut3[k]);
         if (c.d_boxes3[k]) cudaFree(c.d_boxes3[k]);
     }
@@ -127,8 +127,9 @@ int ti_set_option(ti_ctx* ctx, int option, int value) {
         case TI_OPT_FORCE_GENERIC_RECTIFY: ctx->force_generic_rectify = value != 0; return TI_OK;
         case TI_OPT_CTAS_PER_SM: ctx->ctas_per_sm = value; return TI_OK;
         case TI_OPT_DEBUG: ctx->debug = value; return TI_OK;
+        case TI_OPT_LUT_PREFETCH: ctx->lut_prefetch = value != 0; return TI_OK;
         case TI_OPT_STAGES:
-            if (value < 3 || value > M3_MAX_STAGES) return fail(ctx, TI_EINVAL, "stages must be in [3,%d]", M3_MAX_STAGES);
+            if (value < 2 || value > M3_MAX_STAGES) return fail(ctx, TI_EINVAL, "stages must be in [2,%d]", M3_MAX_STAGES);
             ctx->stages = value; return TI_OK;
         case TI_OPT_FRAMES_PER_UNIT:
             if (value < 1) return fail(ctx, TI_EINVAL, "frames per unit must be >= 1");
@@ -137,7 +138,7 @@ int ti_set_option(ti_ctx* ctx, int option, int value) {
             if (value < 1 || value > 3) return fail(ctx, TI_EINVAL, "mono variant must be 1, 2 or 3");
             ctx->mono_variant = value; return TI_OK;
         case TI_OPT_TMA_TILE_H:
-            if (value != 16 && value != 32) return fail(ctx, TI_EINVAL, "tile height must be 16 or 32");
+            if (value != 16 && value != 24 && value != 32) return fail(ctx, TI_EINVAL, "tile height must be 16, 24 or 32");
             ctx->tma_tile_h = value; return TI_OK;
         default: return fail(ctx, TI_EINVAL, "ti_set_option: unknown option %d", option);
     }
@@ -165,7 +166,7 @@ int ti_upload_rectify_map(ti_ctx* ctx, int camera, int dst_w, int dst_h, int src
     if (C.d_boxes2) cudaFree(C.d_boxes2);
     C.d_lut = nullptr; C.d_boxes = nullptr; C.d_valid = nullptr; C.d_lut2 = nullptr; C.d_boxes2 = nullptr;
     C.has_map = false; C.has_fast_mono = false;
-    for (int k = 0; k < 2; ++k) {
+    for (int k = 0; k < 3; ++k) {
         if (C.d_lut3[k]) cudaFree(C.d_lut3[k]);
         if (C.d_boxes3[k]) cudaFree(C.d_boxes3[k]);
         C.d_lut3[k] = nullptr; C.d_boxes3[k] = nullptr; C.has_tma_mono[k] = false;
@@ -272,8 +273,8 @@ int ti_upload_rectify_map(ti_ctx* ctx, int camera, int dst_w, int dst_h, int src
     // ---- TMA-pipelined mono tables (TH = 16 and TH = 32) ----------------------------------------
     // Two passes per tile height: the tap offsets embed the camera's rows_alloc (start of copy B),
     // which is only known once every tile's box has been measured.
-    for (int k = 0; k < 2 && src_w % 16 == 0; ++k) {
-        const int TH = k == 0 ? 16 : 32;
+    for (int k = 0; k < 3 && src_w % 16 == 0; ++k) {
+        const int TH = M3_TILE_HEIGHTS[k];
         const int t3x = (dst_w + M3_TW - 1) / M3_TW, t3y = (dst_h + TH - 1) / TH;
         std::vector<TileBox2> boxes3((size_t)t3x * t3y);
         bool ok = true;

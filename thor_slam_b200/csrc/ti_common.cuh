@@ -75,6 +75,8 @@ static_assert(sizeof(TileBox2) == 16, "TileBox2 is loaded as one 128-bit word");
 // copy A row r = source bytes [c0, c0+256) of source row y0+r; copy B = [c0-63, c0+193) (one byte
 // of pixel shift for odd x0, 64 bytes = 16 banks of bank shift).  Rows are TMA boxes of 256 x 8.
 constexpr int M3_TW = 128;
+constexpr int M3_TILE_HEIGHTS[3] = {16, 32, 24};
+inline int m3_th_index(int th) { return th == 16 ? 0 : (th == 24 ? 2 : 1); }
 constexpr int M3_BOX_ROWS = 8;
 constexpr int M3_PITCH = 256;
 constexpr int M3_B_SHIFT = 63;     // copy B[i] = source column c0 - 63 + i (built in shared memory from copy A)
@@ -87,11 +89,11 @@ constexpr int M3_MAX_STAGES = 8;
 
 struct CameraSlot {
     // rectification
-    bool has_tma_mono[2] = {false, false};   // [0]: TH = 16, [1]: TH = 32
-    uint32_t* d_lut3[2] = {nullptr, nullptr};
-    TileBox2* d_boxes3[2] = {nullptr, nullptr};
-    int tiles3_x[2] = {0, 0}, tiles3_y[2] = {0, 0};
-    int rows3_alloc[2] = {0, 0};
+    bool has_tma_mono[3] = {false, false, false};   // tile height 16, 32, 24 (index = M3_TH_INDEX)
+    uint32_t* d_lut3[3] = {nullptr, nullptr, nullptr};
+    TileBox2* d_boxes3[3] = {nullptr, nullptr, nullptr};
+    int tiles3_x[3] = {0, 0, 0}, tiles3_y[3] = {0, 0, 0};
+    int rows3_alloc[3] = {0, 0, 0};
     bool has_map = false;
     bool has_fast_mono = false;
     uint32_t* d_lut2 = nullptr;     // tiles * M2_TH * M2_TW, tile-major
@@ -123,7 +125,8 @@ struct ti_ctx {
     int ctas_per_sm = 0;
     int debug = 0;
     int mono_variant = 3;   // 3: TMA-pipelined kernel, 2: thread-staged kernel, 1: generic only
-    int tma_tile_h = 32;    // 16 or 32
+    int tma_tile_h = 32;    // 16, 24 or 32
+    int lut_prefetch = 1;   // consumers prefetch the next unit's LUT into a second register set
     int stages = 3;           // shared-memory ring depth of the TMA-pipelined kernel
     int frames_per_unit = 8;  // frames of the batch that share one LUT fetch in the TMA-pipelined kernel
     bool force_generic_rectify = false;  // tests: exercise the generic tiled / direct kernels

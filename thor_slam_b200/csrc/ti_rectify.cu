@@ -341,8 +341,8 @@ constexpr uint32_t H3_FIRST = 1u;  // first frame of a unit: (re)load the LUT re
 constexpr uint32_t H3_LAST_OF_UNIT = 2u;  // last frame of a unit: prefetch the next unit's LUT
 constexpr uint32_t H3_LAST_ITEM = 4u;     // last item of this CTA
 
-template <int TH>
-__global__ void __launch_bounds__(M3_THREADS) rectify_mono_tma_kernel(const __grid_constant__ Rect3Params P) {
+template <int TH, bool PREFETCH>
+__global__ void __launch_bounds__(M3_THREADS, PREFETCH ? 3 : 4) rectify_mono_tma_kernel(const __grid_constant__ Rect3Params P) {
     TI_DYNAMIC_SMEM(uint8_t, smem);
     constexpr int ROWS_PER_WARP = TH / M3_CONSUMER_WARPS;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -474,9 +474,9 @@ __global__ void __launch_bounds__(M3_THREADS) rectify_mono_tma_kernel(const __gr
         return;
     }
     // ---------------------------------------------------- consumers ---------------------------------
-    uint4 l[ROWS_PER_WARP], ln[ROWS_PER_WARP];  // LUT of the current unit / prefetched LUT of the next unit
+    uint4 l[ROWS_PER_WARP], ln[PREFETCH ? ROWS_PER_WARP : 1];  // LUT of the current unit / prefetched LUT of the next unit
 #pragma unroll
-    for (int q = 0; q < ROWS_PER_WARP; ++q) ln[q] = make_uint4(0u, 0u, 0u, 0u);
+    for (int q = 0; q < (PREFETCH ? ROWS_PER_WARP : 1); ++q) ln[q] = make_uint4(0u, 0u, 0u, 0u);
     const uint32_t lut_lane_off = (uint32_t)((warp * ROWS_PER_WARP) * M3_TW + lane * 4);  // in u32 entries
     int s = 0;
     uint32_t phase = 0;
@@ -488,16 +488,16 @@ __global__ void __launch_bounds__(M3_THREADS) rectify_mono_tma_kernel(const __gr
         const uint32_t live_cols = *reinterpret_cast<const uint32_t*>(sb + hdr_off + 16);
         const uint32_t flags = *reinterpret_cast<const uint32_t*>(sb + hdr_off + 48);
         if (flags & H3_FIRST) {
-            if (i == 0) {  // very first unit: nothing was prefetched
+            if (i == 0 || !PREFETCH) {  // very first unit (or no prefetching): fetch now
                 const uint32_t* lp = reinterpret_cast<const uint32_t*>((uintptr_t)(((uint64_t)h2.y << 32) | h2.x)) + lut_lane_off;
 #pragma unroll
                 for (int q = 0; q < ROWS_PER_WARP; ++q) l[q] = ld_keep_u4(lp + q * M3_TW);
             } else {
 #pragma unroll
-                for (int q = 0; q < ROWS_PER_WARP; ++q) l[q] = ln[q];
+                for (int q = 0; q < ROWS_PER_WARP; ++q) l[q] = ln[PREFETCH ? q : 0];
             }
         }
-        if ((flags & H3_LAST_OF_UNIT) && (h2.z | h2.w)) {  // prefetch the next unit's LUT behind this frame's work
+        if (PREFETCH && (flags & H3_LAST_OF_UNIT) && (h2.z | h2.w)) {  // prefetch the next unit's LUT behind this frame's work
             const uint32_t* lp = reinterpret_cast<const uint32_t*>((uintptr_t)(((uint64_t)h2.w << 32) | h2.z)) + lut_lane_off;
 #pragma unroll
             for (int q = 0; q < ROWS_PER_WARP; ++q) ln[q] = ld_keep_u4(lp + q * M3_TW);
@@ -641,7 +641,7 @@ int launch_rectify(ti_ctx* ctx, const RectifyJob* jobs, int n_jobs, int n_batch)
     RectParams P1{}, P3{};  // tiled launches for 1-channel and 3-channel sources
     Rect2Params P2{};       // fast mono launch (v2: thread-staged)
     Rect3Params PT{};       // fast mono launch (v3: TMA-pipelined)
-    const int thk = ctx->tma_tile_h == 16 ? 0 : 1;
+    const int thk = m3_th_index(ctx->tma_tile_h);
     size_t smem1 = 0, smem3 = 0, smem2 = 0;
     for (int i = 0; i < n_jobs; ++i) {
         const RectifyJob& J = jobs[i];
@@ -708,24 +708,25 @@ int launch_rectify(ti_ctx* ctx, const RectifyJob* jobs, int n_jobs, int n_batch)
     P1.n_batch = P3.n_batch = P2.n_batch = PT.n_batch = n_batch;
     PT.debug = ctx->debug;
     if (PT.n_jobs) {
-        const int TH = thk == 0 ? 16 : 32;
+        const int TH = M3_TILE_HEIGHTS[thk];
         const size_t stage = 128 + 2 * (size_t)PT.rows_alloc_max * M3_PITCH + 128;
         PT.frames_per_unit = std::max(1, std::min(n_batch, ctx->frames_per_unit));
-        PT.stages = std::max(3, std::min(ctx->stages, M3_MAX_STAGES));
+        PT.stages = std::max(2, std::min(ctx->stages, M3_MAX_STAGES));
         const size_t smem = 256 + (size_t)PT.stages * stage;
         const uint64_t total = (uint64_t)PT.tiles_per_set * ((n_batch + PT.frames_per_unit - 1) / PT.frames_per_unit);
+        typedef void (*Kern)(const Rect3Params);
+        static const Kern kernels[3][2] = {{rectify_mono_tma_kernel<16, false>, rectify_mono_tma_kernel<16, true>},
+                                           {rectify_mono_tma_kernel<32, false>, rectify_mono_tma_kernel<32, true>},
+                                           {rectify_mono_tma_kernel<24, false>, rectify_mono_tma_kernel<24, true>}};
+        const Kern kern = kernels[thk][ctx->lut_prefetch ? 1 : 0];
+        (void)TH;
 #ifndef TI_EMULATE
-        if (thk == 0)
-            TI_CUDA(ctx, cudaFuncSetAttribute(rectify_mono_tma_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        else
-            TI_CUDA(ctx, cudaFuncSetAttribute(rectify_mono_tma_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        TI_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 #endif
-        int per_sm = thk == 0 ? resident_ctas(rectify_mono_tma_kernel<16>, M3_THREADS, smem, 3)
-                              : resident_ctas(rectify_mono_tma_kernel<32>, M3_THREADS, smem, 3);
+        int per_sm = resident_ctas(kern, M3_THREADS, smem, 3);
         if (ctx->ctas_per_sm > 0) per_sm = ctx->ctas_per_sm;
         const int grid = (int)std::min<uint64_t>(total, (uint64_t)ctx->sm_count * per_sm);
-        if (thk == 0) TI_LAUNCH(rectify_mono_tma_kernel<16>, grid, M3_THREADS, smem, ctx->stream, PT);
-        else TI_LAUNCH(rectify_mono_tma_kernel<32>, grid, M3_THREADS, smem, ctx->stream, PT);
+        TI_LAUNCH(kern, grid, M3_THREADS, smem, ctx->stream, PT);
         TI_CHECK_LAUNCH(ctx);
     }
     if (P2.n_jobs) {

@@ -118,6 +118,7 @@ class IngestContext:
     OPT_DEBUG = 5
     OPT_FRAMES_PER_UNIT = 6
     OPT_STAGES = 7
+    OPT_LUT_PREFETCH = 8
 
     def set_option(self, option: int, value: int) -> None:
         """Tuning / test switches of the library; results never depend on them."""

@@ -70,18 +70,18 @@ def main() -> None:
     px = NS * B * W * H
 
     if not args.only or "rect" in args.only:
-        for variant, th, fpu, stages, sweep in ((3, 32, 8, 3, (0,)), (3, 32, 8, 4, (0, 1)), (3, 32, 8, 5, (0,)), (3, 32, 8, 6, (0,)), (3, 32, 8, 8, (0,)),
-                                                (3, 32, 32, 5, (0,)), (3, 16, 8, 4, (0,)), (3, 16, 8, 6, (0,)), (3, 16, 8, 8, (0,)), (2, 32, 8, 4, (0,))):
+        for variant, th, fpu, stages, pf in ((3, 32, 8, 3, 1), (3, 32, 8, 3, 0), (3, 32, 8, 2, 1), (3, 32, 8, 2, 0), (3, 24, 8, 3, 1), (3, 24, 8, 3, 0),
+                                             (3, 24, 8, 2, 0), (3, 24, 8, 4, 0), (3, 16, 8, 4, 0), (3, 32, 32, 3, 0), (2, 32, 8, 3, 1)):
             ctx.set_option(ctx.OPT_MONO_VARIANT, variant)
             ctx.set_option(ctx.OPT_TMA_TILE_H, th)
             ctx.set_option(ctx.OPT_FRAMES_PER_UNIT, fpu)
             ctx.set_option(ctx.OPT_STAGES, stages)
-            for per_sm in sweep:
-                ctx.set_option(ctx.OPT_CTAS_PER_SM, per_sm)
-                report(f"rectify mono v{variant} th={th} fpu={fpu} S={stages} ctas/sm={per_sm or 'auto'}", timeit(lambda: ctx.ingest(specs), args.iters), 2 * px, px)
+            ctx.set_option(ctx.OPT_LUT_PREFETCH, pf)
+            report(f"rectify mono v{variant} th={th} fpu={fpu} S={stages} prefetch={pf}", timeit(lambda: ctx.ingest(specs), args.iters), 2 * px, px)
         ctx.set_option(ctx.OPT_CTAS_PER_SM, 0)
         ctx.set_option(ctx.OPT_FRAMES_PER_UNIT, 8)
-        ctx.set_option(ctx.OPT_STAGES, 4)
+        ctx.set_option(ctx.OPT_STAGES, 3)
+        ctx.set_option(ctx.OPT_LUT_PREFETCH, 1)
         ctx.set_option(ctx.OPT_MONO_VARIANT, 3)
         ctx.set_option(ctx.OPT_TMA_TILE_H, 32)
         ctx.set_option(ctx.OPT_FORCE_GENERIC_RECTIFY, 1)
