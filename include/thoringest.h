@@ -102,9 +102,9 @@ typedef enum ti_option {
     TI_OPT_MONO_VARIANT = 3,          /* mono remap kernel: 3 TMA-pipelined (default), 2 thread-staged, 1 generic */
     TI_OPT_TMA_TILE_H = 4,            /* output tile height of the TMA-pipelined kernel: 16, 24 or 32 (default) */
     TI_OPT_DEBUG = 5,                 /* bring-up switches; 0 in production (non-zero MAY change results) */
-    TI_OPT_FRAMES_PER_UNIT = 6,       /* frames of a batch sharing one LUT fetch in the TMA-pipelined kernel (default 8) */
-    TI_OPT_STAGES = 7,                /* shared-memory ring depth of the TMA-pipelined kernel, 2..8 (default 3) */
-    TI_OPT_LUT_PREFETCH = 8           /* 1 (default): consumers prefetch the next unit's LUT into a second register set */
+    TI_OPT_FRAMES_PER_UNIT = 6,       /* frames of a batch sharing one LUT fetch in the TMA-pipelined kernel (default 16) */
+    TI_OPT_STAGES = 7,                /* shared-memory ring depth of the TMA-pipelined kernel, 2..8 (default 2) */
+    TI_OPT_LUT_PREFETCH = 8           /* 1: consumers prefetch the next unit's LUT into a second register set (default 0) */
 } ti_option;
 int ti_set_option(ti_ctx* ctx, int option, int value);
 int ti_device_sm_count(const ti_ctx* ctx);

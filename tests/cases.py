@@ -87,7 +87,7 @@ def check_rectify(be, cam: int, mapx, mapy, s: str, d: str, src_w: int, src_h: i
             be.ctx.set_option(be.ctx.OPT_TMA_TILE_H, th)
             be.ctx.set_option(be.ctx.OPT_FRAMES_PER_UNIT, fpu)
             be.ctx.set_option(be.ctx.OPT_STAGES, stages[fpu])
-            be.ctx.set_option(be.ctx.OPT_LUT_PREFETCH, 0 if fpu == 3 else 1)
+            be.ctx.set_option(be.ctx.OPT_LUT_PREFETCH, 0 if fpu == 3 else 1)  # defaults (16 frames, 2 stages, no prefetch) run everywhere else
             dst = be.zeros((n, *F.frame_shape(F.fmt(d), dst_w, dst_h)), np.uint8)
             be.ctx.rectify(cam, be.dev(src), dst, s, d)
             got = be.host(dst)
@@ -97,9 +97,9 @@ def check_rectify(be, cam: int, mapx, mapy, s: str, d: str, src_w: int, src_h: i
     finally:
         be.ctx.set_option(be.ctx.OPT_MONO_VARIANT, 3)
         be.ctx.set_option(be.ctx.OPT_TMA_TILE_H, 32)
-        be.ctx.set_option(be.ctx.OPT_FRAMES_PER_UNIT, 8)
-        be.ctx.set_option(be.ctx.OPT_STAGES, 3)
-        be.ctx.set_option(be.ctx.OPT_LUT_PREFETCH, 1)
+        be.ctx.set_option(be.ctx.OPT_FRAMES_PER_UNIT, 16)
+        be.ctx.set_option(be.ctx.OPT_STAGES, 2)
+        be.ctx.set_option(be.ctx.OPT_LUT_PREFETCH, 0)
     mask = be.zeros((dst_h, dst_w), np.uint8)
     be.ctx.get_valid_mask(cam, mask)
     assert np.array_equal(be.host(mask), orc.valid_mask(mapx, mapy, (src_w, src_h)))

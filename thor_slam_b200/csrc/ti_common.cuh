@@ -126,9 +126,9 @@ struct ti_ctx {
     int debug = 0;
     int mono_variant = 3;   // 3: TMA-pipelined kernel, 2: thread-staged kernel, 1: generic only
     int tma_tile_h = 32;    // 16, 24 or 32
-    int lut_prefetch = 1;   // consumers prefetch the next unit's LUT into a second register set
-    int stages = 3;           // shared-memory ring depth of the TMA-pipelined kernel
-    int frames_per_unit = 8;  // frames of the batch that share one LUT fetch in the TMA-pipelined kernel
+    int lut_prefetch = 0;   // 1: consumers prefetch the next unit's LUT into a second register set (costs 16 registers)
+    int stages = 2;           // shared-memory ring depth of the TMA-pipelined kernel (2 stages -> 4 CTAs per SM)
+    int frames_per_unit = 16;  // frames of the batch that share one LUT fetch in the TMA-pipelined kernel
     bool force_generic_rectify = false;  // tests: exercise the generic tiled / direct kernels
     ti::CameraSlot cams[TI_MAX_CAMERAS];
     // host pipeline (ti_ingest_host)

@@ -70,8 +70,8 @@ def main() -> None:
     px = NS * B * W * H
 
     if not args.only or "rect" in args.only:
-        for variant, th, fpu, stages, pf in ((3, 32, 8, 3, 1), (3, 32, 8, 3, 0), (3, 32, 8, 2, 1), (3, 32, 8, 2, 0), (3, 24, 8, 3, 1), (3, 24, 8, 3, 0),
-                                             (3, 24, 8, 2, 0), (3, 24, 8, 4, 0), (3, 16, 8, 4, 0), (3, 32, 32, 3, 0), (2, 32, 8, 3, 1)):
+        for variant, th, fpu, stages, pf in ((3, 32, 8, 2, 0), (3, 32, 16, 2, 0), (3, 32, 32, 2, 0), (3, 32, 64, 2, 0), (3, 32, 16, 3, 0), (3, 32, 8, 3, 1),
+                                             (2, 32, 8, 3, 1)):
             ctx.set_option(ctx.OPT_MONO_VARIANT, variant)
             ctx.set_option(ctx.OPT_TMA_TILE_H, th)
             ctx.set_option(ctx.OPT_FRAMES_PER_UNIT, fpu)
@@ -79,9 +79,9 @@ def main() -> None:
             ctx.set_option(ctx.OPT_LUT_PREFETCH, pf)
             report(f"rectify mono v{variant} th={th} fpu={fpu} S={stages} prefetch={pf}", timeit(lambda: ctx.ingest(specs), args.iters), 2 * px, px)
         ctx.set_option(ctx.OPT_CTAS_PER_SM, 0)
-        ctx.set_option(ctx.OPT_FRAMES_PER_UNIT, 8)
-        ctx.set_option(ctx.OPT_STAGES, 3)
-        ctx.set_option(ctx.OPT_LUT_PREFETCH, 1)
+        ctx.set_option(ctx.OPT_FRAMES_PER_UNIT, 16)
+        ctx.set_option(ctx.OPT_STAGES, 2)
+        ctx.set_option(ctx.OPT_LUT_PREFETCH, 0)
         ctx.set_option(ctx.OPT_MONO_VARIANT, 3)
         ctx.set_option(ctx.OPT_TMA_TILE_H, 32)
         ctx.set_option(ctx.OPT_FORCE_GENERIC_RECTIFY, 1)
