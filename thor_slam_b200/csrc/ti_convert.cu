@@ -29,117 +29,154 @@ __device__ __forceinline__ uint32_t byte_of(const uint32_t* w, int i) {  // i-th
 }
 
 // ---- unit processors: one "unit" = 16 pixels (or 2 rows x 16 pixels for NV12 colour) --------
+// Each unit type is split into load() and emit() so that a thread can have the loads of several units
+// in flight before it converts and stores the first one (memory-level parallelism: one 16-byte load per
+// thread in flight cannot saturate HBM).
 
-// 16 BGR pixels (48 B) -> 16 RGB pixels (48 B)
-__device__ __forceinline__ void unit_bgr_to_rgb(const uint8_t* src, uint8_t* dst) {
-    uint32_t w[12], o[12];
-    const uint4 a = ld_stream_u4(src), b = ld_stream_u4(src + 16), c = ld_stream_u4(src + 32);
-    w[0] = a.x; w[1] = a.y; w[2] = a.z; w[3] = a.w;
-    w[4] = b.x; w[5] = b.y; w[6] = b.z; w[7] = b.w;
-    w[8] = c.x; w[9] = c.y; w[10] = c.z; w[11] = c.w;
-    // every 12-byte group holds 4 pixels: B0G0R0B1 G1R1B2G2 R2B3G3R3 -> R0G0B0R1 G1B1R2G2 B2R3G3B3
-#pragma unroll
-    for (int g = 0; g < 4; ++g) {
-        const uint32_t w0 = w[3 * g], w1 = w[3 * g + 1], w2 = w[3 * g + 2];
-        o[3 * g] = __byte_perm(w0, w1, 0x5012);      // R0 G0 B0 R1   (bytes: w0.2, w0.1, w0.0, w1.1)
-        o[3 * g + 1] = __byte_perm(w1, __byte_perm(w0, w2, 0x0043), 0x3540);  // G1 B1 R2 G2
-        o[3 * g + 2] = __byte_perm(w2, w1, 0x1236);  // B2 R3 G3 B3   (bytes: w1.2, w2.3, w2.2, w2.1)
+struct UnitCopy {  // MONO8 -> MONO8, NV12 luma -> MONO8: 16 bytes
+    uint4 v;
+    __device__ __forceinline__ void load(const uint8_t* src) { v = ld_stream_u4(src); }
+    __device__ __forceinline__ void emit(uint8_t* dst) const { st_stream_u4(dst, v); }
+};
+
+struct UnitBgr {  // 16 BGR pixels = 48 bytes
+    uint32_t w[12];
+    __device__ __forceinline__ void load(const uint8_t* src) {
+        const uint4 a = ld_stream_u4(src), b = ld_stream_u4(src + 16), c = ld_stream_u4(src + 32);
+        w[0] = a.x; w[1] = a.y; w[2] = a.z; w[3] = a.w;
+        w[4] = b.x; w[5] = b.y; w[6] = b.z; w[7] = b.w;
+        w[8] = c.x; w[9] = c.y; w[10] = c.z; w[11] = c.w;
     }
-    st_stream_u4(dst, make_uint4(o[0], o[1], o[2], o[3]));
-    st_stream_u4(dst + 16, make_uint4(o[4], o[5], o[6], o[7]));
-    st_stream_u4(dst + 32, make_uint4(o[8], o[9], o[10], o[11]));
-}
-
-// 16 BGR pixels (48 B) -> 16 gray pixels (16 B)
-__device__ __forceinline__ void unit_bgr_to_gray(const uint8_t* src, uint8_t* dst) {
-    uint32_t w[12], o[4];
-    const uint4 a = ld_stream_u4(src), b = ld_stream_u4(src + 16), c = ld_stream_u4(src + 32);
-    w[0] = a.x; w[1] = a.y; w[2] = a.z; w[3] = a.w;
-    w[4] = b.x; w[5] = b.y; w[6] = b.z; w[7] = b.w;
-    w[8] = c.x; w[9] = c.y; w[10] = c.z; w[11] = c.w;
+    __device__ __forceinline__ void emit_rgb(uint8_t* dst) const {
+        uint32_t o[12];
+        // every 12-byte group holds 4 pixels: B0G0R0B1 G1R1B2G2 R2B3G3R3 -> R0G0B0R1 G1B1R2G2 B2R3G3B3
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-        uint32_t out = 0;
-#pragma unroll
-        for (int p = 0; p < 4; ++p) {
-            const int px = q * 4 + p;
-            out |= gray_of(byte_of(w, 3 * px), byte_of(w, 3 * px + 1), byte_of(w, 3 * px + 2)) << (8 * p);
+        for (int g = 0; g < 4; ++g) {
+            const uint32_t w0 = w[3 * g], w1 = w[3 * g + 1], w2 = w[3 * g + 2];
+            o[3 * g] = __byte_perm(w0, w1, 0x5012);                               // R0 G0 B0 R1
+            o[3 * g + 1] = __byte_perm(w1, __byte_perm(w0, w2, 0x0043), 0x3540);  // G1 B1 R2 G2
+            o[3 * g + 2] = __byte_perm(w2, w1, 0x1236);                           // B2 R3 G3 B3
         }
-        o[q] = out;
+        st_stream_u4(dst, make_uint4(o[0], o[1], o[2], o[3]));
+        st_stream_u4(dst + 16, make_uint4(o[4], o[5], o[6], o[7]));
+        st_stream_u4(dst + 32, make_uint4(o[8], o[9], o[10], o[11]));
     }
-    st_stream_u4(dst, make_uint4(o[0], o[1], o[2], o[3]));
-}
+    __device__ __forceinline__ void emit_gray(uint8_t* dst) const {
+        uint32_t o[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            uint32_t out = 0;
+#pragma unroll
+            for (int p = 0; p < 4; ++p) {
+                const int px = q * 4 + p;
+                out |= gray_of(byte_of(w, 3 * px), byte_of(w, 3 * px + 1), byte_of(w, 3 * px + 2)) << (8 * p);
+            }
+            o[q] = out;
+        }
+        st_stream_u4(dst, make_uint4(o[0], o[1], o[2], o[3]));
+    }
+};
 
-// 2 rows x 16 luma + 16 B of UV -> 2 rows x 16 RGB (or BGR) pixels
-template <bool BGR_OUT>
-__device__ __forceinline__ void unit_nv12_to_color(const uint8_t* y0p, const uint8_t* y1p, const uint8_t* uvp,
-                                                   uint8_t* d0, uint8_t* d1) {
+struct UnitNv12 {  // 2 rows x 16 luma + 16 bytes of interleaved U,V
     uint32_t y0[4], y1[4], uv[4];
-    {
+    __device__ __forceinline__ void load(const uint8_t* y0p, const uint8_t* y1p, const uint8_t* uvp) {
         const uint4 a = ld_stream_u4(y0p), b = ld_stream_u4(y1p), c = ld_stream_u4(uvp);
         y0[0] = a.x; y0[1] = a.y; y0[2] = a.z; y0[3] = a.w;
         y1[0] = b.x; y1[1] = b.y; y1[2] = b.z; y1[3] = b.w;
         uv[0] = c.x; uv[1] = c.y; uv[2] = c.z; uv[3] = c.w;
     }
+    template <bool BGR_OUT>
+    __device__ __forceinline__ void emit(uint8_t* d0, uint8_t* d1) const {
 #pragma unroll
-    for (int row = 0; row < 2; ++row) {
-        const uint32_t* yy = row ? y1 : y0;
-        uint32_t o[12];
+        for (int row = 0; row < 2; ++row) {
+            const uint32_t* yy = row ? y1 : y0;
+            uint32_t o[12];
 #pragma unroll
-        for (int i = 0; i < 12; ++i) o[i] = 0;
+            for (int i = 0; i < 12; ++i) o[i] = 0;
 #pragma unroll
-        for (int px = 0; px < 16; ++px) {
-            const int u = (int)byte_of(uv, (px >> 1) * 2), v = (int)byte_of(uv, (px >> 1) * 2 + 1);
-            int r, g, b;
-            yuv_to_rgb((int)byte_of(yy, px), u, v, r, g, b);
-            const int c0 = BGR_OUT ? b : r, c2 = BGR_OUT ? r : b;
-            const int base = 3 * px;
-            o[base >> 2] |= (uint32_t)c0 << ((base & 3) * 8);
-            o[(base + 1) >> 2] |= (uint32_t)g << (((base + 1) & 3) * 8);
-            o[(base + 2) >> 2] |= (uint32_t)c2 << (((base + 2) & 3) * 8);
+            for (int px = 0; px < 16; ++px) {
+                const int u = (int)byte_of(uv, (px >> 1) * 2), v = (int)byte_of(uv, (px >> 1) * 2 + 1);
+                int r, g, b;
+                yuv_to_rgb((int)byte_of(yy, px), u, v, r, g, b);
+                const int c0 = BGR_OUT ? b : r, c2 = BGR_OUT ? r : b;
+                const int base = 3 * px;
+                o[base >> 2] |= (uint32_t)c0 << ((base & 3) * 8);
+                o[(base + 1) >> 2] |= (uint32_t)g << (((base + 1) & 3) * 8);
+                o[(base + 2) >> 2] |= (uint32_t)c2 << (((base + 2) & 3) * 8);
+            }
+            uint8_t* d = row ? d1 : d0;
+            st_stream_u4(d, make_uint4(o[0], o[1], o[2], o[3]));
+            st_stream_u4(d + 16, make_uint4(o[4], o[5], o[6], o[7]));
+            st_stream_u4(d + 32, make_uint4(o[8], o[9], o[10], o[11]));
         }
-        uint8_t* d = row ? d1 : d0;
-        st_stream_u4(d, make_uint4(o[0], o[1], o[2], o[3]));
-        st_stream_u4(d + 16, make_uint4(o[4], o[5], o[6], o[7]));
-        st_stream_u4(d + 32, make_uint4(o[8], o[9], o[10], o[11]));
     }
+};
+
+enum ConvMode { CM_COPY = 0, CM_BGR_RGB = 1, CM_BGR_GRAY = 2, CM_NV12_RGB = 3, CM_NV12_BGR = 4 };
+
+// where unit t of the launch lives
+struct UnitAddr {
+    const uint8_t* src;
+    uint8_t* dst;
+    int w, h;
+    uint32_t unit;
+};
+
+__device__ __forceinline__ UnitAddr locate(const ConvertParams& P, uint32_t units_per_set, uint64_t t) {
+    const uint32_t b = (uint32_t)(t / units_per_set);
+    const uint32_t r = (uint32_t)(t - (uint64_t)b * units_per_set);
+    int j = 0;
+    while (j + 1 < P.n_jobs && r >= P.unit_begin[j + 1]) ++j;
+    const ConvertJob& J = P.job[j];
+    return UnitAddr{J.src + (uint64_t)b * J.src_stride, J.dst + (uint64_t)b * J.dst_stride, J.width, J.height, r - P.unit_begin[j]};
 }
 
-// ---- vector kernel (width % 16 == 0, 16-byte aligned frames) ---------------------------------
+// ---- vector kernels (width % 16 == 0, 16-byte aligned frames): one per conversion, UNROLL units in flight ----
+template <int MODE, int UNROLL>
 __global__ void __launch_bounds__(CV_THREADS) convert_vec_kernel(const __grid_constant__ ConvertParams P) {
     const uint32_t units_per_set = P.unit_begin[P.n_jobs];
     const uint64_t total = (uint64_t)units_per_set * P.n_batch;
     const uint64_t stride = (uint64_t)gridDim.x * CV_THREADS;
-    // (frame b, unit r) advanced incrementally: one division up front instead of one per 16 pixels
-    uint64_t t = (uint64_t)blockIdx.x * CV_THREADS + threadIdx.x;
-    uint32_t b = (uint32_t)(t / units_per_set);
-    uint64_t r64 = t - (uint64_t)b * units_per_set;
-    for (; t < total; t += stride, r64 += stride) {
-        while (r64 >= units_per_set) { r64 -= units_per_set; ++b; }
-        const uint32_t r = (uint32_t)r64;
-        int j = 0;
-        while (j + 1 < P.n_jobs && r >= P.unit_begin[j + 1]) ++j;
-        const ConvertJob& J = P.job[j];
-        const uint32_t unit = r - P.unit_begin[j];
-        const uint8_t* src = J.src + (uint64_t)b * J.src_stride;
-        uint8_t* dst = J.dst + (uint64_t)b * J.dst_stride;
-        const int w = J.width, h = J.height;
-        if (J.src_fmt == TI_FMT_BGR8 && J.dst_fmt == TI_FMT_RGB8) {
-            unit_bgr_to_rgb(src + (uint64_t)unit * 48, dst + (uint64_t)unit * 48);
-        } else if (J.src_fmt == TI_FMT_BGR8 && J.dst_fmt == TI_FMT_MONO8) {
-            unit_bgr_to_gray(src + (uint64_t)unit * 48, dst + (uint64_t)unit * 16);
-        } else if (J.dst_fmt == TI_FMT_MONO8) {  // MONO8 or NV12 luma: plain copy
-            st_stream_u4(dst + (uint64_t)unit * 16, ld_stream_u4(src + (uint64_t)unit * 16));
-        } else {  // NV12 -> colour: unit = 16 columns of a row PAIR
-            const uint32_t upr = (uint32_t)w / 16;
-            const uint32_t rp = unit / upr, cx = (unit - rp * upr) * 16;
-            const uint8_t* y0 = src + (uint64_t)(2 * rp) * w + cx;
-            const uint8_t* uv = src + (uint64_t)h * w + (uint64_t)rp * w + cx;
-            uint8_t* d0 = dst + ((uint64_t)(2 * rp) * w + cx) * 3;
-            if (J.dst_fmt == TI_FMT_BGR8)
-                unit_nv12_to_color<true>(y0, y0 + w, uv, d0, d0 + (uint64_t)w * 3);
-            else
-                unit_nv12_to_color<false>(y0, y0 + w, uv, d0, d0 + (uint64_t)w * 3);
+    for (uint64_t t0 = (uint64_t)blockIdx.x * CV_THREADS + threadIdx.x; t0 < total; t0 += stride * UNROLL) {
+        UnitAddr A[UNROLL];
+        bool live[UNROLL];
+#pragma unroll
+        for (int k = 0; k < UNROLL; ++k) {
+            live[k] = t0 + k * stride < total;
+            if (live[k]) A[k] = locate(P, units_per_set, t0 + k * stride);
+        }
+        if (MODE == CM_COPY) {
+            UnitCopy U[UNROLL];
+#pragma unroll
+            for (int k = 0; k < UNROLL; ++k) if (live[k]) U[k].load(A[k].src + (uint64_t)A[k].unit * 16);
+#pragma unroll
+            for (int k = 0; k < UNROLL; ++k) if (live[k]) U[k].emit(A[k].dst + (uint64_t)A[k].unit * 16);
+        } else if (MODE == CM_BGR_RGB || MODE == CM_BGR_GRAY) {
+            UnitBgr U[UNROLL];
+#pragma unroll
+            for (int k = 0; k < UNROLL; ++k) if (live[k]) U[k].load(A[k].src + (uint64_t)A[k].unit * 48);
+#pragma unroll
+            for (int k = 0; k < UNROLL; ++k) if (live[k]) {
+                if (MODE == CM_BGR_RGB) U[k].emit_rgb(A[k].dst + (uint64_t)A[k].unit * 48);
+                else U[k].emit_gray(A[k].dst + (uint64_t)A[k].unit * 16);
+            }
+        } else {
+            UnitNv12 U[UNROLL];
+            uint8_t* d0[UNROLL];
+#pragma unroll
+            for (int k = 0; k < UNROLL; ++k) if (live[k]) {
+                const int w = A[k].w, h = A[k].h;
+                const uint32_t upr = (uint32_t)w / 16;  // unit = 16 columns of a row PAIR
+                const uint32_t rp = A[k].unit / upr, cx = (A[k].unit - rp * upr) * 16;
+                const uint8_t* y0 = A[k].src + (uint64_t)(2 * rp) * w + cx;
+                U[k].load(y0, y0 + w, A[k].src + (uint64_t)h * w + (uint64_t)rp * w + cx);
+                d0[k] = A[k].dst + ((uint64_t)(2 * rp) * w + cx) * 3;
+            }
+#pragma unroll
+            for (int k = 0; k < UNROLL; ++k) if (live[k]) {
+                if (MODE == CM_NV12_BGR) U[k].template emit<true>(d0[k], d0[k] + (uint64_t)A[k].w * 3);
+                else U[k].template emit<false>(d0[k], d0[k] + (uint64_t)A[k].w * 3);
+            }
         }
     }
 }
@@ -180,12 +217,28 @@ static bool convert_supported(int s, int d) {
     return false;
 }
 
+static int conv_mode(int s, int d) {
+    if (d == TI_FMT_MONO8 && (s == TI_FMT_MONO8 || s == TI_FMT_NV12)) return CM_COPY;
+    if (s == TI_FMT_BGR8) return d == TI_FMT_RGB8 ? CM_BGR_RGB : CM_BGR_GRAY;
+    return d == TI_FMT_BGR8 ? CM_NV12_BGR : CM_NV12_RGB;
+}
+
+template <int MODE, int UNROLL>
+static int launch_mode(ti_ctx* ctx, const ConvertParams& P, uint32_t units) {
+    const uint64_t total = (uint64_t)units * P.n_batch;
+    const uint64_t want = (total + (uint64_t)CV_THREADS * UNROLL - 1) / ((uint64_t)CV_THREADS * UNROLL);
+    static const int per_sm = resident_ctas(convert_vec_kernel<MODE, UNROLL>, CV_THREADS, 0, 4);
+    const int grid = (int)std::max<uint64_t>(1, std::min<uint64_t>(want, (uint64_t)ctx->sm_count * per_sm));
+    TI_LAUNCH((convert_vec_kernel<MODE, UNROLL>), grid, CV_THREADS, 0, ctx->stream, P);
+    TI_CHECK_LAUNCH(ctx);
+    return TI_OK;
+}
+
 int launch_convert(ti_ctx* ctx, const ConvertJob* jobs, int n_jobs, int n_batch) {
     if (n_jobs <= 0 || n_batch <= 0) return TI_OK;
     if (n_jobs > MAX_CONVERT_JOBS) return fail(ctx, TI_EINVAL, "too many convert streams (%d > %d)", n_jobs, MAX_CONVERT_JOBS);
-    ConvertParams P{};
-    int nv = 0;
-    uint32_t units = 0;
+    ConvertParams P[5] = {};
+    uint32_t units[5] = {0, 0, 0, 0, 0};
     for (int i = 0; i < n_jobs; ++i) {
         const ConvertJob& J = jobs[i];
         if (!convert_supported(J.src_fmt, J.dst_fmt))
@@ -202,22 +255,28 @@ int launch_convert(ti_ctx* ctx, const ConvertJob* jobs, int n_jobs, int n_batch)
             TI_CHECK_LAUNCH(ctx);
             continue;
         }
-        P.job[nv] = J;
-        P.unit_begin[nv] = units;
-        const bool pair = J.src_fmt == TI_FMT_NV12 && J.dst_fmt != TI_FMT_MONO8;
-        units += (uint32_t)((uint64_t)J.width * J.height / (pair ? 32 : 16));
-        ++nv;
+        const int m = conv_mode(J.src_fmt, J.dst_fmt);
+        ConvertParams& Q = P[m];
+        Q.job[Q.n_jobs] = J;
+        Q.unit_begin[Q.n_jobs] = units[m];
+        const bool pair = m == CM_NV12_RGB || m == CM_NV12_BGR;
+        units[m] += (uint32_t)((uint64_t)J.width * J.height / (pair ? 32 : 16));
+        ++Q.n_jobs;
     }
-    if (nv == 0) return TI_OK;
-    P.unit_begin[nv] = units;
-    P.n_jobs = nv;
-    P.n_batch = n_batch;
-    const uint64_t total = (uint64_t)units * n_batch;
-    const uint64_t want = (total + CV_THREADS - 1) / CV_THREADS;
-    static const int per_sm = resident_ctas(convert_vec_kernel, CV_THREADS, 0, 4);
-    const int grid = (int)std::min<uint64_t>(want, (uint64_t)ctx->sm_count * per_sm);
-    TI_LAUNCH(convert_vec_kernel, grid, CV_THREADS, 0, ctx->stream, P);
-    TI_CHECK_LAUNCH(ctx);
+    for (int m = 0; m < 5; ++m) {
+        if (!P[m].n_jobs) continue;
+        P[m].unit_begin[P[m].n_jobs] = units[m];
+        P[m].n_batch = n_batch;
+        int rc = TI_OK;
+        switch (m) {
+            case CM_COPY: rc = launch_mode<CM_COPY, 4>(ctx, P[m], units[m]); break;
+            case CM_BGR_RGB: rc = launch_mode<CM_BGR_RGB, 2>(ctx, P[m], units[m]); break;
+            case CM_BGR_GRAY: rc = launch_mode<CM_BGR_GRAY, 2>(ctx, P[m], units[m]); break;
+            case CM_NV12_RGB: rc = launch_mode<CM_NV12_RGB, 2>(ctx, P[m], units[m]); break;
+            default: rc = launch_mode<CM_NV12_BGR, 2>(ctx, P[m], units[m]); break;
+        }
+        if (rc != TI_OK) return rc;
+    }
     return TI_OK;
 }
 
