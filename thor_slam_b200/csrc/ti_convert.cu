@@ -28,6 +28,30 @@ __device__ __forceinline__ uint32_t byte_of(const uint32_t* w, int i) {  // i-th
     return (w[i >> 2] >> ((i & 3) * 8)) & 0xFFu;
 }
 
+// 48 bytes per lane (16 three-byte pixels) written so that every store instruction of the warp covers 512
+// contiguous bytes: strided 16-byte stores (lane stride 48 B) touch 12 lines and half-fill every sector.
+// Fast path when the 32 lanes' destinations are back to back (checked with a ballot); otherwise plain stores.
+__device__ __forceinline__ void store48(const uint32_t o[12], uint8_t* dst, bool live, uint4* wbuf) {
+    const int lane = threadIdx.x & 31;
+    uint8_t* base = reinterpret_cast<uint8_t*>(
+        ((uint64_t)__shfl_sync(0xFFFFFFFFu, (uint32_t)((uint64_t)(uintptr_t)dst >> 32), 0) << 32) |
+        __shfl_sync(0xFFFFFFFFu, (uint32_t)(uintptr_t)dst, 0));
+    const bool contiguous = __ballot_sync(0xFFFFFFFFu, live && dst == base + lane * 48) == 0xFFFFFFFFu;
+    if (contiguous) {
+        wbuf[lane * 3] = make_uint4(o[0], o[1], o[2], o[3]);
+        wbuf[lane * 3 + 1] = make_uint4(o[4], o[5], o[6], o[7]);
+        wbuf[lane * 3 + 2] = make_uint4(o[8], o[9], o[10], o[11]);
+        __syncwarp();
+#pragma unroll
+        for (int k = 0; k < 3; ++k) st_stream_u4(base + (k * 32 + lane) * 16, wbuf[k * 32 + lane]);
+        __syncwarp();
+    } else if (live) {
+        st_stream_u4(dst, make_uint4(o[0], o[1], o[2], o[3]));
+        st_stream_u4(dst + 16, make_uint4(o[4], o[5], o[6], o[7]));
+        st_stream_u4(dst + 32, make_uint4(o[8], o[9], o[10], o[11]));
+    }
+}
+
 // ---- unit processors: one "unit" = 16 pixels (or 2 rows x 16 pixels for NV12 colour) --------
 // Each unit type is split into load() and emit() so that a thread can have the loads of several units
 // in flight before it converts and stores the first one (memory-level parallelism: one 16-byte load per
@@ -47,7 +71,7 @@ struct UnitBgr {  // 16 BGR pixels = 48 bytes
         w[4] = b.x; w[5] = b.y; w[6] = b.z; w[7] = b.w;
         w[8] = c.x; w[9] = c.y; w[10] = c.z; w[11] = c.w;
     }
-    __device__ __forceinline__ void emit_rgb(uint8_t* dst) const {
+    __device__ __forceinline__ void emit_rgb(uint8_t* dst, bool live, uint4* wbuf) const {
         uint32_t o[12];
         // every 12-byte group holds 4 pixels: B0G0R0B1 G1R1B2G2 R2B3G3R3 -> R0G0B0R1 G1B1R2G2 B2R3G3B3
 #pragma unroll
@@ -57,9 +81,7 @@ struct UnitBgr {  // 16 BGR pixels = 48 bytes
             o[3 * g + 1] = __byte_perm(w1, __byte_perm(w0, w2, 0x0043), 0x3540);  // G1 B1 R2 G2
             o[3 * g + 2] = __byte_perm(w2, w1, 0x1236);                           // B2 R3 G3 B3
         }
-        st_stream_u4(dst, make_uint4(o[0], o[1], o[2], o[3]));
-        st_stream_u4(dst + 16, make_uint4(o[4], o[5], o[6], o[7]));
-        st_stream_u4(dst + 32, make_uint4(o[8], o[9], o[10], o[11]));
+        store48(o, dst, live, wbuf);
     }
     __device__ __forceinline__ void emit_gray(uint8_t* dst) const {
         uint32_t o[4];
@@ -86,7 +108,7 @@ struct UnitNv12 {  // 2 rows x 16 luma + 16 bytes of interleaved U,V
         uv[0] = c.x; uv[1] = c.y; uv[2] = c.z; uv[3] = c.w;
     }
     template <bool BGR_OUT>
-    __device__ __forceinline__ void emit(uint8_t* d0, uint8_t* d1) const {
+    __device__ __forceinline__ void emit(uint8_t* d0, uint8_t* d1, bool live, uint4* wbuf) const {
 #pragma unroll
         for (int row = 0; row < 2; ++row) {
             const uint32_t* yy = row ? y1 : y0;
@@ -104,10 +126,7 @@ struct UnitNv12 {  // 2 rows x 16 luma + 16 bytes of interleaved U,V
                 o[(base + 1) >> 2] |= (uint32_t)g << (((base + 1) & 3) * 8);
                 o[(base + 2) >> 2] |= (uint32_t)c2 << (((base + 2) & 3) * 8);
             }
-            uint8_t* d = row ? d1 : d0;
-            st_stream_u4(d, make_uint4(o[0], o[1], o[2], o[3]));
-            st_stream_u4(d + 16, make_uint4(o[4], o[5], o[6], o[7]));
-            st_stream_u4(d + 32, make_uint4(o[8], o[9], o[10], o[11]));
+            store48(o, row ? d1 : d0, live, wbuf);
         }
     }
 };
@@ -134,10 +153,14 @@ __device__ __forceinline__ UnitAddr locate(const ConvertParams& P, uint32_t unit
 // ---- vector kernels (width % 16 == 0, 16-byte aligned frames): one per conversion, UNROLL units in flight ----
 template <int MODE, int UNROLL>
 __global__ void __launch_bounds__(CV_THREADS) convert_vec_kernel(const __grid_constant__ ConvertParams P) {
+    __shared__ uint4 wbuf_all[(MODE == CM_COPY || MODE == CM_BGR_GRAY) ? 1 : CV_THREADS / 32][96];
+    uint4* wbuf = wbuf_all[(MODE == CM_COPY || MODE == CM_BGR_GRAY) ? 0 : threadIdx.x >> 5];
     const uint32_t units_per_set = P.unit_begin[P.n_jobs];
     const uint64_t total = (uint64_t)units_per_set * P.n_batch;
     const uint64_t stride = (uint64_t)gridDim.x * CV_THREADS;
-    for (uint64_t t0 = (uint64_t)blockIdx.x * CV_THREADS + threadIdx.x; t0 < total; t0 += stride * UNROLL) {
+    // warp-uniform trip count: the coalesced store path uses warp collectives
+    const uint64_t warp_t0 = (uint64_t)blockIdx.x * CV_THREADS + (threadIdx.x & ~31);
+    for (uint64_t t0 = warp_t0 + (threadIdx.x & 31); t0 - (threadIdx.x & 31) < total; t0 += stride * UNROLL) {
         UnitAddr A[UNROLL];
         bool live[UNROLL];
 #pragma unroll
@@ -156,13 +179,15 @@ __global__ void __launch_bounds__(CV_THREADS) convert_vec_kernel(const __grid_co
 #pragma unroll
             for (int k = 0; k < UNROLL; ++k) if (live[k]) U[k].load(A[k].src + (uint64_t)A[k].unit * 48);
 #pragma unroll
-            for (int k = 0; k < UNROLL; ++k) if (live[k]) {
-                if (MODE == CM_BGR_RGB) U[k].emit_rgb(A[k].dst + (uint64_t)A[k].unit * 48);
-                else U[k].emit_gray(A[k].dst + (uint64_t)A[k].unit * 16);
+            for (int k = 0; k < UNROLL; ++k) {
+                if (MODE == CM_BGR_RGB) U[k].emit_rgb(live[k] ? A[k].dst + (uint64_t)A[k].unit * 48 : nullptr, live[k], wbuf);
+                else if (live[k]) U[k].emit_gray(A[k].dst + (uint64_t)A[k].unit * 16);
             }
         } else {
             UnitNv12 U[UNROLL];
             uint8_t* d0[UNROLL];
+#pragma unroll
+            for (int k = 0; k < UNROLL; ++k) d0[k] = nullptr;
 #pragma unroll
             for (int k = 0; k < UNROLL; ++k) if (live[k]) {
                 const int w = A[k].w, h = A[k].h;
@@ -173,9 +198,10 @@ __global__ void __launch_bounds__(CV_THREADS) convert_vec_kernel(const __grid_co
                 d0[k] = A[k].dst + ((uint64_t)(2 * rp) * w + cx) * 3;
             }
 #pragma unroll
-            for (int k = 0; k < UNROLL; ++k) if (live[k]) {
-                if (MODE == CM_NV12_BGR) U[k].template emit<true>(d0[k], d0[k] + (uint64_t)A[k].w * 3);
-                else U[k].template emit<false>(d0[k], d0[k] + (uint64_t)A[k].w * 3);
+            for (int k = 0; k < UNROLL; ++k) {
+                uint8_t* d1 = live[k] ? d0[k] + (uint64_t)A[k].w * 3 : nullptr;
+                if (MODE == CM_NV12_BGR) U[k].template emit<true>(d0[k], d1, live[k], wbuf);
+                else U[k].template emit<false>(d0[k], d1, live[k], wbuf);
             }
         }
     }
