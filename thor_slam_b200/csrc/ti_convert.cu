@@ -109,22 +109,31 @@ struct UnitNv12 {  // 2 rows x 16 luma + 16 bytes of interleaved U,V
     }
     template <bool BGR_OUT>
     __device__ __forceinline__ void emit(uint8_t* d0, uint8_t* d1, bool live, uint4* wbuf) const {
+        // chroma terms once per (U,V) pair (shared by 2 columns x 2 rows); per pixel 3 x (add, shift) and
+        // saturate+pack two channels per instruction (cvt.pack.sat)
+        ChromaTerms ct[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) ct[i] = chroma_terms((int)byte_of(uv, 2 * i), (int)byte_of(uv, 2 * i + 1));
 #pragma unroll
         for (int row = 0; row < 2; ++row) {
             const uint32_t* yy = row ? y1 : y0;
             uint32_t o[12];
 #pragma unroll
-            for (int i = 0; i < 12; ++i) o[i] = 0;
+            for (int g = 0; g < 4; ++g) {  // 4 pixels -> 12 bytes -> 3 words
+                int v[12];
 #pragma unroll
-            for (int px = 0; px < 16; ++px) {
-                const int u = (int)byte_of(uv, (px >> 1) * 2), v = (int)byte_of(uv, (px >> 1) * 2 + 1);
-                int r, g, b;
-                yuv_to_rgb((int)byte_of(yy, px), u, v, r, g, b);
-                const int c0 = BGR_OUT ? b : r, c2 = BGR_OUT ? r : b;
-                const int base = 3 * px;
-                o[base >> 2] |= (uint32_t)c0 << ((base & 3) * 8);
-                o[(base + 1) >> 2] |= (uint32_t)g << (((base + 1) & 3) * 8);
-                o[(base + 2) >> 2] |= (uint32_t)c2 << (((base + 2) & 3) * 8);
+                for (int p = 0; p < 4; ++p) {
+                    const int px = 4 * g + p;
+                    const int l = luma_term((int)byte_of(yy, px));
+                    const ChromaTerms& c = ct[px >> 1];
+                    const int r = (l + c.r) >> 20, gg = (l + c.g) >> 20, b = (l + c.b) >> 20;
+                    v[3 * p] = BGR_OUT ? b : r;
+                    v[3 * p + 1] = gg;
+                    v[3 * p + 2] = BGR_OUT ? r : b;
+                }
+#pragma unroll
+                for (int q = 0; q < 3; ++q)
+                    o[3 * g + q] = pack_sat_u8(v[4 * q + 1], v[4 * q], pack_sat_u8(v[4 * q + 3], v[4 * q + 2], 0u));
             }
             store48(o, row ? d1 : d0, live, wbuf);
         }

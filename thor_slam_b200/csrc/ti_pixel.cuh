@@ -30,4 +30,27 @@ __host__ __device__ __forceinline__ uint32_t bilinear_u8(uint32_t t00, uint32_t 
     return (top * (32u - fy) + bot * fy + 512u) >> 10;
 }
 
+
+// Saturate two s32 to u8 and pack: result = { c[15:0], sat_u8(hi), sat_u8(lo) }  (one instruction on the GPU)
+__device__ __forceinline__ uint32_t pack_sat_u8(int hi, int lo, uint32_t c) {
+#if defined(TI_EMULATE) || !defined(__CUDACC__)
+    return (c << 16) | ((uint32_t)sat_u8(hi) << 8) | (uint32_t)sat_u8(lo);
+#else
+    uint32_t d;
+    asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(hi), "r"(lo), "r"(c));
+    return d;
+#endif
+}
+
+// NV12 chroma terms shared by the 2x2 pixels of one (U, V) pair (rounding constant folded in)
+struct ChromaTerms {
+    int r, g, b;
+};
+__device__ __forceinline__ ChromaTerms chroma_terms(int u, int v) {
+    u -= 128;
+    v -= 128;
+    return ChromaTerms{1673527 * v + (1 << 19), -852492 * v - 409993 * u + (1 << 19), 2116026 * u + (1 << 19)};
+}
+__device__ __forceinline__ int luma_term(int y) { return (y > 16 ? y - 16 : 0) * 1220542; }
+
 }  // namespace ti
