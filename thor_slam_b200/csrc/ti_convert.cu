@@ -307,8 +307,8 @@ int launch_convert(ti_ctx* ctx, const ConvertJob* jobs, int n_jobs, int n_batch)
             case CM_COPY: rc = launch_mode<CM_COPY, 4>(ctx, P[m], units[m]); break;
             case CM_BGR_RGB: rc = launch_mode<CM_BGR_RGB, 2>(ctx, P[m], units[m]); break;
             case CM_BGR_GRAY: rc = launch_mode<CM_BGR_GRAY, 2>(ctx, P[m], units[m]); break;
-            case CM_NV12_RGB: rc = launch_mode<CM_NV12_RGB, 2>(ctx, P[m], units[m]); break;
-            default: rc = launch_mode<CM_NV12_BGR, 2>(ctx, P[m], units[m]); break;
+            case CM_NV12_RGB: rc = launch_mode<CM_NV12_RGB, 1>(ctx, P[m], units[m]); break;
+            default: rc = launch_mode<CM_NV12_BGR, 1>(ctx, P[m], units[m]); break;
         }
         if (rc != TI_OK) return rc;
     }
