@@ -43,6 +43,14 @@ def test_rectify_resize_and_ragged(emu_backend):
     cases.check_rectify(emu_backend, 3, xx * 0.75 + 3.25, yy * 0.8 + 0.5, "mono8", "mono8", 160, 64)  # tiled, ragged tiles
 
 
+def test_rectify_odd_output_width_on_fast_kernels(emu_backend):
+    """dst_w odd (no 16-bit stores possible) while the source still qualifies for the TMA / thread-staged kernels."""
+    yy, xx = np.mgrid[0:51, 0:99].astype(np.float32)
+    cases.check_rectify(emu_backend, 7, xx * 1.1 + 0.3, yy * 1.05 + 0.7, "mono8", "mono8", 112, 60)
+    yy, xx = np.mgrid[0:40, 0:130].astype(np.float32)  # two tiles wide, second one 2 pixels
+    cases.check_rectify(emu_backend, 7, xx * 0.8 + 1.5, yy * 1.2 + 0.25, "mono8", "mono8", 112, 60)
+
+
 def test_rectify_all_outside(emu_backend):
     mx = np.full((32, 128), -50.0, np.float32)
     cases.check_rectify(emu_backend, 4, mx, mx.copy(), "mono8", "mono8", 128, 32)

@@ -80,6 +80,13 @@ def test_rectify_resize_ragged_outside(gpu_backend):
     cases.check_rectify(gpu_backend, 4, mx, mx.copy(), "mono8", "mono8", 128, 32)
 
 
+def test_rectify_odd_output_width_on_fast_kernels(gpu_backend):
+    yy, xx = np.mgrid[0:51, 0:99].astype(np.float32)
+    cases.check_rectify(gpu_backend, 7, xx * 1.1 + 0.3, yy * 1.05 + 0.7, "mono8", "mono8", 112, 60)
+    yy, xx = np.mgrid[0:40, 0:130].astype(np.float32)
+    cases.check_rectify(gpu_backend, 7, xx * 0.8 + 1.5, yy * 1.2 + 0.25, "mono8", "mono8", 112, 60)
+
+
 def test_rectify_golden(gpu_backend):
     g = np.load(GOLDEN / "cv_arith.npz")
     be = gpu_backend

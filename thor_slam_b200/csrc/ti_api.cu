@@ -312,8 +312,10 @@ int ti_upload_rectify_map(ti_ctx* ctx, int camera, int dst_w, int dst_h, int src
                     const int rel = x0 - B.c0, row = y0 - B.y0;
                     const int off = (rel & 1) ? 128 + (rows_alloc + row) * M3_PITCH + (rel - 1 + M3_B_SHIFT + 1)
                                               : 128 + row * M3_PITCH + rel;
+                    // lane L of a warp owns pixels 2L, 2L+1, 64+2L, 64+2L+1 of the 128-pixel tile row (its uint4)
                     const int lu = u - tx * M3_TW;
-                    tl[(size_t)(v - ty * TH) * M3_TW + (lu & 31) * 4 + (lu >> 5)] = ((uint32_t)off << 16) | (fy << 6) | fx;
+                    const int lane = (lu & 63) >> 1, slot = ((lu >> 6) << 1) | (lu & 1);
+                    tl[(size_t)(v - ty * TH) * M3_TW + lane * 4 + slot] = ((uint32_t)off << 16) | (fy << 6) | fx;
                 });
             }
         TI_CUDA(ctx, cudaMalloc(&C.d_lut3[k], lut3.size() * sizeof(uint32_t)));

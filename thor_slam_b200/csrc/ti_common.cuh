@@ -245,6 +245,7 @@ __device__ __forceinline__ void st_stream_u2(void* p, uint2 v) { *reinterpret_ca
 __device__ __forceinline__ void st_stream_u1(void* p, uint32_t v) { *reinterpret_cast<uint32_t*>(ti_emu::check_align(p, 4)) = v; }
 __device__ __forceinline__ uint4 ld_keep_u4(const void* p) { return *reinterpret_cast<const uint4*>(ti_emu::check_align(p, 16)); }
 __device__ __forceinline__ void st_stream_b8(void* p, uint32_t v) { *reinterpret_cast<uint8_t*>(p) = (uint8_t)v; }
+__device__ __forceinline__ void st_stream_b16(void* p, uint32_t v) { *reinterpret_cast<uint16_t*>(ti_emu::check_align(p, 2)) = (uint16_t)v; }
 #elif defined(__CUDACC__)
 // ---- device helpers ------------------------------------------------------------------------
 // L2 eviction policies (createpolicy is not volatile: the compiler hoists / CSEs it).
@@ -291,6 +292,9 @@ __device__ __forceinline__ void st_stream_u1(void* p, uint32_t v) {
 }
 __device__ __forceinline__ void st_stream_b8(void* p, uint32_t v) {  // .cs = streaming (evict-first), no policy descriptor
     asm volatile("st.global.cs.u8 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void st_stream_b16(void* p, uint32_t v) {
+    asm volatile("st.global.cs.u16 [%0], %1;" ::"l"(p), "h"((unsigned short)v) : "memory");
 }
 // LUT reads: re-used by every frame of the batch -> prefer to keep in L2.
 __device__ __forceinline__ uint4 ld_keep_u4(const void* p) {

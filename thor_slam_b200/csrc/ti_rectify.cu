@@ -340,6 +340,7 @@ struct Rect3Params {
 constexpr uint32_t H3_FIRST = 1u;  // first frame of a unit: (re)load the LUT registers
 constexpr uint32_t H3_LAST_OF_UNIT = 2u;  // last frame of a unit: prefetch the next unit's LUT
 constexpr uint32_t H3_LAST_ITEM = 4u;     // last item of this CTA
+constexpr uint32_t H3_ALIGNED2 = 8u;      // destination tile rows start on even addresses (16-bit stores allowed)
 
 template <int TH, bool PREFETCH>
 __global__ void __launch_bounds__(M3_THREADS, PREFETCH ? 3 : 4) rectify_mono_tma_kernel(const __grid_constant__ Rect3Params P) {
@@ -408,9 +409,10 @@ __global__ void __launch_bounds__(M3_THREADS, PREFETCH ? 3 : 4) rectify_mono_tma
             if (rows > 0) tma_load_3d(sb + 128, &P.map[cur.j], c0, y0, (int)b, raw + s);  // one box: 256 x rows_alloc bytes
             const bool last_of_unit = f + 1 == cur.nb;
             const bool have_next = k_next < units_mine;
-            uint32_t flags = (f == 0 ? H3_FIRST : 0u) | (last_of_unit ? H3_LAST_OF_UNIT : 0u) |
-                             (last_of_unit && !have_next ? H3_LAST_ITEM : 0u);
             const uint64_t dst = (uint64_t)(uintptr_t)(J.dst + (uint64_t)b * J.dst_stride + (size_t)v0 * J.dst_w + u0);
+            uint32_t flags = (f == 0 ? H3_FIRST : 0u) | (last_of_unit ? H3_LAST_OF_UNIT : 0u) |
+                             (last_of_unit && !have_next ? H3_LAST_ITEM : 0u) |
+                             (((dst | (uint64_t)J.dst_w) & 1ull) == 0 ? H3_ALIGNED2 : 0u);
             const uint64_t nlut = have_next ? nxt.lut : 0ull;
             uint4* h = reinterpret_cast<uint4*>(sb + hdr_off);
             h[0] = make_uint4((uint32_t)(dst & 0xFFFFFFFFu), (uint32_t)(dst >> 32), (uint32_t)J.dst_w, (uint32_t)(J.dst_h - v0));
@@ -477,7 +479,7 @@ __global__ void __launch_bounds__(M3_THREADS, PREFETCH ? 3 : 4) rectify_mono_tma
     uint4 l[ROWS_PER_WARP], ln[PREFETCH ? ROWS_PER_WARP : 1];  // LUT of the current unit / prefetched LUT of the next unit
 #pragma unroll
     for (int q = 0; q < (PREFETCH ? ROWS_PER_WARP : 1); ++q) ln[q] = make_uint4(0u, 0u, 0u, 0u);
-    const uint32_t lut_lane_off = (uint32_t)((warp * ROWS_PER_WARP) * M3_TW + lane * 4);  // in u32 entries
+    const uint32_t lut_lane_off = (uint32_t)((warp * ROWS_PER_WARP) * M3_TW + lane * 4);  // in u32 entries (lane's uint4)
     int s = 0;
     uint32_t phase = 0;
     for (uint32_t i = 0;; ++i) {
@@ -505,27 +507,26 @@ __global__ void __launch_bounds__(M3_THREADS, PREFETCH ? 3 : 4) rectify_mono_tma
         uint8_t* dp = reinterpret_cast<uint8_t*>((uintptr_t)(((uint64_t)h0.y << 32) | h0.x));
         const smem_base_t sbase = smem_base(sb);
         const int dst_w = (int)h0.z, live_rows = (int)h0.w - warp * ROWS_PER_WARP;
-        dp += (size_t)(warp * ROWS_PER_WARP) * dst_w + lane;
-        if (live_rows >= ROWS_PER_WARP && live_cols >= (uint32_t)M3_TW) {  // whole tile inside the image (warp-uniform)
+        dp += (size_t)(warp * ROWS_PER_WARP) * dst_w + 2 * lane;
+        // lane L owns pixels 2L, 2L+1, 64+2L, 64+2L+1 of the row: two 16-bit stores per row (64 B per warp store)
+        if (live_rows >= ROWS_PER_WARP && live_cols >= (uint32_t)M3_TW && (flags & H3_ALIGNED2)) {  // warp-uniform
 #pragma unroll
             for (int q = 0; q < ROWS_PER_WARP; ++q) {
                 const uint32_t s0 = blend64(l[q].x, sbase), s1 = blend64(l[q].y, sbase), s2 = blend64(l[q].z, sbase), s3 = blend64(l[q].w, sbase);
-                st_stream_b8(dp, s0 >> 16);
-                st_stream_b8(dp + 32, s1 >> 16);
-                st_stream_b8(dp + 64, s2 >> 16);
-                st_stream_b8(dp + 96, s3 >> 16);
+                st_stream_b16(dp, __byte_perm(s0, s1, 0x0062));
+                st_stream_b16(dp + 64, __byte_perm(s2, s3, 0x0062));
                 dp += dst_w;
             }
         } else {
-            const int my_cols = ((int)live_cols - lane + 31) >> 5;  // of this lane's 4 pixels, how many exist
+            const int c0 = 2 * lane, c2 = 64 + 2 * lane;
 #pragma unroll
             for (int q = 0; q < ROWS_PER_WARP; ++q) {
                 const uint32_t s0 = blend64(l[q].x, sbase), s1 = blend64(l[q].y, sbase), s2 = blend64(l[q].z, sbase), s3 = blend64(l[q].w, sbase);
                 if (q < live_rows) {
-                    if (my_cols > 0) st_stream_b8(dp, s0 >> 16);
-                    if (my_cols > 1) st_stream_b8(dp + 32, s1 >> 16);
-                    if (my_cols > 2) st_stream_b8(dp + 64, s2 >> 16);
-                    if (my_cols > 3) st_stream_b8(dp + 96, s3 >> 16);
+                    if (c0 < (int)live_cols) st_stream_b8(dp, s0 >> 16);
+                    if (c0 + 1 < (int)live_cols) st_stream_b8(dp + 1, s1 >> 16);
+                    if (c2 < (int)live_cols) st_stream_b8(dp + 64, s2 >> 16);
+                    if (c2 + 1 < (int)live_cols) st_stream_b8(dp + 65, s3 >> 16);
                 }
                 dp += dst_w;
             }
