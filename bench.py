@@ -43,6 +43,9 @@ N_CAMERAS = 4  # stereo sources -> 8 streams
 STREAMS = 2 * N_CAMERAS
 PX_PER_SET = STREAMS * W * H
 ALGO_BYTES_PER_PX = 2  # mono8 -> rectified mono8
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE rectify_mono_tma_kernel launch over 64 frame sets, from the
+# `ncu --set full` capture of this bench (profiles/r01_rect_ncu_raw.txt): 615.99 MB + 489.26 MB
+NCU_TRAFFIC_BYTES_PER_FRAME_SET = (615.985408e6 + 489.261312e6) / 64
 FALLBACK_HBM_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md fallback
 
 
@@ -375,7 +378,8 @@ def run_ours(args) -> None:
             "gpu_launches": launches,
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "kernel": "rectify_mono_tma_kernel<32>", "algorithmic_bytes_per_launch": algo_bytes,
+                         "traffic": NCU_TRAFFIC_BYTES_PER_FRAME_SET * B, "traffic_source": "ncu --set full, profiles/r01_rect_ncu_raw.txt (scaled per frame set)",
+                         "kernel": "rectify_mono_tma_kernel<32,false>", "algorithmic_bytes_per_launch": algo_bytes,
                          "peak_source": peak_src, "frac_of_8000_datasheet": achieved / 8000.0,
                          "note": "per-rank launch; duration = max-over-ranks ms_per_step (one launch per step)"},
             "cpu_baseline": cpu_baseline,

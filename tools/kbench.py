@@ -70,8 +70,7 @@ def main() -> None:
     px = NS * B * W * H
 
     if not args.only or "rect" in args.only:
-        for variant, th, fpu, stages, pf in ((3, 32, 8, 2, 0), (3, 32, 16, 2, 0), (3, 32, 32, 2, 0), (3, 32, 64, 2, 0), (3, 32, 16, 3, 0), (3, 32, 8, 3, 1),
-                                             (2, 32, 8, 3, 1)):
+        for variant, th, fpu, stages, pf in ((3, 32, 16, 2, 0), (3, 32, 8, 3, 1), (2, 32, 8, 3, 1)):
             ctx.set_option(ctx.OPT_MONO_VARIANT, variant)
             ctx.set_option(ctx.OPT_TMA_TILE_H, th)
             ctx.set_option(ctx.OPT_FRAMES_PER_UNIT, fpu)
