@@ -99,11 +99,11 @@ uint64_t ti_launch_count(const ti_ctx* ctx);
 typedef enum ti_option {
     TI_OPT_FORCE_GENERIC_RECTIFY = 1, /* 1: skip the fast mono remap kernel, use the generic ones */
     TI_OPT_CTAS_PER_SM = 2,           /* >0: resident CTAs per SM the persistent grids are sized for */
-    TI_OPT_MONO_VARIANT = 3,          /* mono remap kernel: 3 TMA-pipelined (default), 2 thread-staged, 1 generic */
+    TI_OPT_MONO_VARIANT = 3,          /* mono remap kernel: 4 pair-window TMA (default), 3 TMA + shifted copy, 2 thread-staged, 1 generic */
     TI_OPT_TMA_TILE_H = 4,            /* output tile height of the TMA-pipelined kernel: 16, 24 or 32 (default) */
     TI_OPT_DEBUG = 5,                 /* bring-up switches; 0 in production (non-zero MAY change results) */
-    TI_OPT_FRAMES_PER_UNIT = 6,       /* frames of a batch sharing one LUT fetch in the TMA-pipelined kernel (default 16) */
-    TI_OPT_STAGES = 7,                /* shared-memory ring depth of the TMA-pipelined kernel, 2..8 (default 2) */
+    TI_OPT_FRAMES_PER_UNIT = 6,       /* frames of a batch sharing one LUT fetch in the TMA kernels (default 16; pair-window: 0 = automatic) */
+    TI_OPT_STAGES = 7,                /* shared-memory ring depth of the TMA kernels, 2..8 (default 3 pair-window, 2 shifted-copy) */
     TI_OPT_LUT_PREFETCH = 8           /* 1: consumers prefetch the next unit's LUT into a second register set (default 0) */
 } ti_option;
 int ti_set_option(ti_ctx* ctx, int option, int value);
@@ -126,6 +126,13 @@ int ti_upload_rectify_map(ti_ctx* ctx, int camera, int dst_w, int dst_h, int src
  * (thor_slam/slam/adapters/isaac_ros.py:42-49) or identity.  float64 in, rounded once. */
 int ti_upload_projection(ti_ctx* ctx, int camera, int width, int height, const double k[4],
                          const double body_T_cam[12]);
+
+/* Which remap kernel ti_rectify()/ti_ingest() will run for MONO8/NV12 -> MONO8 on slot `camera`
+ * under the current options (diagnostic; tests use it to prove no silent fall-back to a slower
+ * kernel).  out[0] = kernel variant (4 pair-window, 3 TMA + shifted copy, 2 thread-staged,
+ * 1 generic), out[1] = output tile height, out[2] = source rows staged per tile,
+ * out[3] = exception-table entries per (tile, warp) of the pair-window kernel. */
+int ti_rectify_plan(ti_ctx* ctx, int camera, int32_t out[4]);
 
 /* u8 dst_h x dst_w mask of slot `camera`: 1 where all four bilinear taps are inside the
  * source image.  Static per calibration.  dst: DEVICE pointer. */

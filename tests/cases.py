@@ -67,7 +67,8 @@ def edge_maps(dst_w: int, dst_h: int) -> tuple[np.ndarray, np.ndarray]:
     return (xx * 1.13 - 13.3 + 0.05 * yy).astype(np.float32), (yy * 1.21 - 14.7 - 0.03 * xx).astype(np.float32)
 
 
-def check_rectify(be, cam: int, mapx, mapy, s: str, d: str, src_w: int, src_h: int, n: int = 3, seed: int = 1) -> None:
+def check_rectify(be, cam: int, mapx, mapy, s: str, d: str, src_w: int, src_h: int, n: int = 3, seed: int = 1,
+                  expect_variant: int | None = None, expect_exceptions: bool = False) -> None:
     rng = np.random.default_rng(seed)
     dst_h, dst_w = mapx.shape
     be.ctx.upload_rectify_map(cam, mapx, mapy, (src_w, src_h))
@@ -79,7 +80,8 @@ def check_rectify(be, cam: int, mapx, mapy, s: str, d: str, src_w: int, src_h: i
     # every kernel variant must give the same bytes: TMA-pipelined (tile height 32 and 16), thread-staged, generic
     # (the TMA kernel also with 1 and 2 frames of the batch per LUT fetch)
     mono = d == "mono8" and s in ("mono8", "nv12")
-    variants = [(3, 32, 8), (3, 16, 2), (3, 24, 3), (3, 32, 1), (2, 32, 8), (1, 32, 8)] if mono else [(3, 32, 8), (1, 32, 8)]
+    variants = ([(4, 32, 8), (4, 16, 2), (4, 32, 1), (3, 32, 8), (3, 16, 2), (3, 24, 3), (3, 32, 1), (2, 32, 8), (1, 32, 8)] if mono
+                else [(4, 32, 8), (1, 32, 8)])
     stages = {8: 4, 2: 3, 3: 2, 1: 6}
     try:
         for variant, th, fpu in variants:
@@ -88,6 +90,11 @@ def check_rectify(be, cam: int, mapx, mapy, s: str, d: str, src_w: int, src_h: i
             be.ctx.set_option(be.ctx.OPT_FRAMES_PER_UNIT, fpu)
             be.ctx.set_option(be.ctx.OPT_STAGES, stages[fpu])
             be.ctx.set_option(be.ctx.OPT_LUT_PREFETCH, 0 if fpu == 3 else 1)  # defaults (16 frames, 2 stages, no prefetch) run everywhere else
+            if mono and expect_variant is not None and variant == 4:
+                plan = be.ctx.rectify_plan(cam)
+                assert plan["variant"] == expect_variant, f"slot {cam} would run kernel variant {plan}"
+                if expect_exceptions:
+                    assert plan["exceptions_per_warp"] > 0, "this map was chosen to exercise the exception path"
             dst = be.zeros((n, *F.frame_shape(F.fmt(d), dst_w, dst_h)), np.uint8)
             be.ctx.rectify(cam, be.dev(src), dst, s, d)
             got = be.host(dst)
@@ -95,10 +102,11 @@ def check_rectify(be, cam: int, mapx, mapy, s: str, d: str, src_w: int, src_h: i
                 assert np.array_equal(got[i], wants[i]), (
                     f"rectify {s}->{d} variant={variant} th={th} frame {i}: {(got[i] != wants[i]).sum()} bytes differ")
     finally:
-        be.ctx.set_option(be.ctx.OPT_MONO_VARIANT, 3)
+        be.ctx.set_option(be.ctx.OPT_MONO_VARIANT, 4)
         be.ctx.set_option(be.ctx.OPT_TMA_TILE_H, 32)
         be.ctx.set_option(be.ctx.OPT_FRAMES_PER_UNIT, 16)
-        be.ctx.set_option(be.ctx.OPT_STAGES, 2)
+        be.ctx.set_option(be.ctx.OPT_FRAMES_PER_UNIT, 0)
+        be.ctx.set_option(be.ctx.OPT_STAGES, 4)
         be.ctx.set_option(be.ctx.OPT_LUT_PREFETCH, 0)
     mask = be.zeros((dst_h, dst_w), np.uint8)
     be.ctx.get_valid_mask(cam, mask)

@@ -65,6 +65,14 @@ inline uint32_t ballot(int pred) {
     syncwarp();
     return r;
 }
+inline uint32_t reduce_or(uint32_t v) {
+    tls.warp_scratch[lane()] = v;
+    syncwarp();
+    uint32_t r = 0;
+    for (int i = 0; i < 32; ++i) r |= tls.warp_scratch[i];
+    syncwarp();
+    return r;
+}
 inline uint32_t reduce_add(uint32_t v) {
     tls.warp_scratch[lane()] = v;
     syncwarp();
@@ -159,6 +167,7 @@ inline uint32_t __byte_perm(uint32_t x, uint32_t y, uint32_t s) {
 inline int __popc(uint32_t v) { return __builtin_popcount(v); }
 inline uint32_t __ballot_sync(uint32_t, int pred) { return ti_emu::ballot(pred); }
 inline uint32_t __reduce_add_sync(uint32_t, uint32_t v) { return ti_emu::reduce_add(v); }
+inline uint32_t __reduce_or_sync(uint32_t, uint32_t v) { return ti_emu::reduce_or(v); }
 template <typename T>
 inline T __shfl_sync(uint32_t, T v, int src) {
     static_assert(sizeof(T) == 4, "emu shuffles 32-bit values");

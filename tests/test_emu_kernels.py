@@ -27,13 +27,13 @@ def test_convert_empty_batch(emu_backend):
 @pytest.mark.parametrize("s,d", cases.RECTIFY_CONVERSIONS)
 def test_rectify_stereo_maps(emu_backend, s, d):
     _, maps = cases.stereo_maps(192, 96)
-    cases.check_rectify(emu_backend, 0, *maps[0], s, d, 192, 96)
+    cases.check_rectify(emu_backend, 0, *maps[0], s, d, 192, 96, expect_variant=4)
 
 
 @pytest.mark.parametrize("s,d", cases.RECTIFY_CONVERSIONS)
 def test_rectify_border(emu_backend, s, d):
     mx, my = cases.edge_maps(160, 64)
-    cases.check_rectify(emu_backend, 1, mx, my, s, d, 160, 64)
+    cases.check_rectify(emu_backend, 1, mx, my, s, d, 160, 64, expect_variant=4, expect_exceptions=True)
 
 
 def test_rectify_resize_and_ragged(emu_backend):

@@ -39,6 +39,7 @@ static void free_camera(CameraSlot& c) {
         if (c.d_lut3[k]) cudaFree(c.d_lut3[k]);
         if (c.d_boxes3[k]) cudaFree(c.d_boxes3[k]);
     }
+    free_pair_tables(c);
     c = CameraSlot{};
 }
 
@@ -130,12 +131,13 @@ int ti_set_option(ti_ctx* ctx, int option, int value) {
         case TI_OPT_LUT_PREFETCH: ctx->lut_prefetch = value != 0; return TI_OK;
         case TI_OPT_STAGES:
             if (value < 2 || value > M3_MAX_STAGES) return fail(ctx, TI_EINVAL, "stages must be in [2,%d]", M3_MAX_STAGES);
-            ctx->stages = value; return TI_OK;
+            ctx->stages = value; ctx->stages4 = value; return TI_OK;
         case TI_OPT_FRAMES_PER_UNIT:
-            if (value < 1) return fail(ctx, TI_EINVAL, "frames per unit must be >= 1");
-            ctx->frames_per_unit = value; return TI_OK;
+            if (value < 0) return fail(ctx, TI_EINVAL, "frames per unit must be >= 0 (0 = automatic, pair-window kernel only)");
+            if (value == 0) { ctx->frames_per_unit4 = 0; return TI_OK; }
+            ctx->frames_per_unit = value; ctx->frames_per_unit4 = value; return TI_OK;
         case TI_OPT_MONO_VARIANT:
-            if (value < 1 || value > 3) return fail(ctx, TI_EINVAL, "mono variant must be 1, 2 or 3");
+            if (value < 1 || value > 4) return fail(ctx, TI_EINVAL, "mono variant must be 1, 2, 3 or 4");
             ctx->mono_variant = value; return TI_OK;
         case TI_OPT_TMA_TILE_H:
             if (value != 16 && value != 24 && value != 32) return fail(ctx, TI_EINVAL, "tile height must be 16, 24 or 32");
@@ -166,6 +168,7 @@ int ti_upload_rectify_map(ti_ctx* ctx, int camera, int dst_w, int dst_h, int src
     if (C.d_boxes2) cudaFree(C.d_boxes2);
     C.d_lut = nullptr; C.d_boxes = nullptr; C.d_valid = nullptr; C.d_lut2 = nullptr; C.d_boxes2 = nullptr;
     C.has_map = false; C.has_fast_mono = false;
+    free_pair_tables(C);
     for (int k = 0; k < 3; ++k) {
         if (C.d_lut3[k]) cudaFree(C.d_lut3[k]);
         if (C.d_boxes3[k]) cudaFree(C.d_boxes3[k]);
@@ -325,7 +328,7 @@ int ti_upload_rectify_map(ti_ctx* ctx, int camera, int dst_w, int dst_h, int src
         C.tiles3_x[k] = t3x; C.tiles3_y[k] = t3y; C.rows3_alloc[k] = rows_alloc;
         C.has_tma_mono[k] = true;
     }
-    return TI_OK;
+    return build_pair_tables(ctx, C, lut, lut_pitch);
 }
 
 int ti_upload_projection(ti_ctx* ctx, int camera, int width, int height, const double k[4], const double body_T_cam[12]) {
@@ -344,6 +347,24 @@ int ti_upload_projection(ti_ctx* ctx, int camera, int width, int height, const d
     C.cx = (float)k[2]; C.cy = (float)k[3];
     C.proj_w = width; C.proj_h = height;
     C.has_proj = true;
+    return TI_OK;
+}
+
+int ti_rectify_plan(ti_ctx* ctx, int camera, int32_t out[4]) {
+    if (!ctx) return TI_EINVAL;
+    if (camera < 0 || camera >= TI_MAX_CAMERAS || !out) return fail(ctx, TI_EINVAL, "ti_rectify_plan: bad argument");
+    const CameraSlot& C = ctx->cams[camera];
+    if (!C.has_map) return fail(ctx, TI_ESTATE, "ti_rectify_plan: camera slot %d has no remap LUT", camera);
+    const int th4 = p4_th_index(ctx->tma_tile_h), thk = m3_th_index(ctx->tma_tile_h);
+    out[0] = 1; out[1] = RT_H; out[2] = 0; out[3] = 0;
+    if (ctx->force_generic_rectify) return TI_OK;
+    if (ctx->mono_variant == 4 && C.has_pair[th4]) {
+        out[0] = 4; out[1] = P4_TILE_HEIGHTS[th4]; out[2] = C.rows4_alloc[th4]; out[3] = C.exc4_per_warp[th4];
+    } else if (ctx->mono_variant >= 3 && C.has_tma_mono[thk]) {
+        out[0] = 3; out[1] = M3_TILE_HEIGHTS[thk]; out[2] = C.rows3_alloc[thk];
+    } else if (ctx->mono_variant >= 2 && C.has_fast_mono) {
+        out[0] = 2; out[1] = M2_TH; out[2] = C.rows2_max;
+    }
     return TI_OK;
 }
 

@@ -87,8 +87,29 @@ constexpr int M3_PRODUCER_WARPS = 2;
 constexpr int M3_THREADS = (M3_CONSUMER_WARPS + M3_PRODUCER_WARPS + 1) * 32;  // consumers, copy-B builders, TMA issuer
 constexpr int M3_MAX_STAGES = 8;
 
+// Pair-window mono path ("v4"): tiles of P4_TW x TH (TH = 16 or 32).  The TMA box of a tile lands
+// as is (pitch P4_PITCH, no shifted copy, no builder warps); two horizontally adjacent output pixels
+// share one 8-byte window per source row (see ti_rectify_pair.cu).
+constexpr int P4_TW = 128;
+constexpr int P4_TILE_HEIGHTS[2] = {16, 32};
+inline int p4_th_index(int th) { return th == 16 ? 0 : 1; }
+constexpr int P4_PITCH = 192;        // = 16 banks (mod 32): a lane group crossing into the next source row stays conflict-free
+constexpr int P4_MAX_ROWS = 96;
+constexpr int P4_CONSUMER_WARPS = 8;
+constexpr int P4_THREADS = (P4_CONSUMER_WARPS + 1) * 32;  // consumers + TMA issuer
+constexpr int P4_MAX_STAGES = 8;
+constexpr int P4_LUT_ROW_WORDS = 192;  // per tile row: 32 lanes x 2 pairs x {window word, pixel a word, pixel b word}
+constexpr int P4_MAX_EXC = 32;         // exception entries per (tile, warp): one lane each in the per-frame fix-up pass
+
 struct CameraSlot {
     // rectification
+    bool has_pair[2] = {false, false};              // tile height 16, 32
+    uint32_t* d_lut4[2] = {nullptr, nullptr};       // tiles * TH * P4_LUT_ROW_WORDS
+    TileBox2* d_boxes4[2] = {nullptr, nullptr};
+    uint32_t* d_exc4[2] = {nullptr, nullptr};       // tiles * P4_CONSUMER_WARPS * exc4_per_warp entries of 4 words
+    int tiles4_x[2] = {0, 0}, tiles4_y[2] = {0, 0};
+    int rows4_alloc[2] = {0, 0};
+    int exc4_per_warp[2] = {0, 0};
     bool has_tma_mono[3] = {false, false, false};   // tile height 16, 32, 24 (index = M3_TH_INDEX)
     uint32_t* d_lut3[3] = {nullptr, nullptr, nullptr};
     TileBox2* d_boxes3[3] = {nullptr, nullptr, nullptr};
@@ -124,11 +145,13 @@ struct ti_ctx {
     uint64_t launches = 0;
     int ctas_per_sm = 0;
     int debug = 0;
-    int mono_variant = 3;   // 3: TMA-pipelined kernel, 2: thread-staged kernel, 1: generic only
+    int mono_variant = 4;   // 4: pair-window TMA kernel, 3: TMA-pipelined kernel with shifted copy, 2: thread-staged kernel, 1: generic only
     int tma_tile_h = 32;    // 16, 24 or 32
     int lut_prefetch = 0;   // 1: consumers prefetch the next unit's LUT into a second register set (costs 16 registers)
     int stages = 2;           // shared-memory ring depth of the TMA-pipelined kernel (2 stages -> 4 CTAs per SM)
+    int stages4 = 4;          // ring depth of the pair-window kernel
     int frames_per_unit = 16;  // frames of the batch that share one LUT fetch in the TMA-pipelined kernel
+    int frames_per_unit4 = 0;  // same for the pair-window kernel; 0 = chosen per launch (least tail over the persistent grid)
     bool force_generic_rectify = false;  // tests: exercise the generic tiled / direct kernels
     ti::CameraSlot cams[TI_MAX_CAMERAS];
     // host pipeline (ti_ingest_host)
@@ -226,6 +249,9 @@ struct RectifyJob {
     int camera, src_fmt, dst_fmt;
 };
 int launch_rectify(ti_ctx* ctx, const RectifyJob* jobs, int n_jobs, int n_batch);
+// pair-window tables of one camera from its generic LUT (ti_rectify_pair.cu); frees / replaces the old ones
+int build_pair_tables(ti_ctx* ctx, CameraSlot& C, const std::vector<uint32_t>& lut, int lut_pitch);
+void free_pair_tables(CameraSlot& C);
 
 struct BackprojectJob {
     const uint16_t* depth;

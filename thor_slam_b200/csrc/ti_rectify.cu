@@ -17,6 +17,7 @@
 #include "ti_common.cuh"
 #include "ti_pixel.cuh"
 #include "ti_tma.cuh"
+#include "ti_rectify_pair.cuh"
 
 namespace ti {
 
@@ -642,7 +643,9 @@ int launch_rectify(ti_ctx* ctx, const RectifyJob* jobs, int n_jobs, int n_batch)
     RectParams P1{}, P3{};  // tiled launches for 1-channel and 3-channel sources
     Rect2Params P2{};       // fast mono launch (v2: thread-staged)
     Rect3Params PT{};       // fast mono launch (v3: TMA-pipelined)
+    Rect4Params PP{};       // fast mono launch (v4: pair windows)
     const int thk = m3_th_index(ctx->tma_tile_h);
+    const int th4 = p4_th_index(ctx->tma_tile_h);
     size_t smem1 = 0, smem3 = 0, smem2 = 0;
     for (int i = 0; i < n_jobs; ++i) {
         const RectifyJob& J = jobs[i];
@@ -663,7 +666,23 @@ int launch_rectify(ti_ctx* ctx, const RectifyJob* jobs, int n_jobs, int n_batch)
         const bool fast_ok = mode == DM_MONO && C.has_fast_mono && ((uintptr_t)J.src % 16 == 0) &&
                              (J.src_stride % 16 == 0) && P2.n_jobs < MAX_RECT_JOBS && !ctx->force_generic_rectify && ctx->mono_variant >= 2;
         const bool tma_ok = mode == DM_MONO && C.has_tma_mono[thk] && ((uintptr_t)J.src % 16 == 0) && (J.src_stride % 16 == 0) &&
-                            PT.n_jobs < MAX_RECT_JOBS && !ctx->force_generic_rectify && ctx->mono_variant == 3;
+                            PT.n_jobs < MAX_RECT_JOBS && !ctx->force_generic_rectify && ctx->mono_variant >= 3;
+        const bool pair_ok = mode == DM_MONO && C.has_pair[th4] && ((uintptr_t)J.src % 16 == 0) && (J.src_stride % 16 == 0) &&
+                             PP.n_jobs < MAX_PAIR_JOBS && !ctx->force_generic_rectify && ctx->mono_variant == 4;
+        if (pair_ok) {
+            const int rc = tma_encode_u8_3d(ctx, &PP.map[PP.n_jobs], J.src, C.src_w, C.src_h, n_batch, (uint64_t)C.src_w,
+                                            J.src_stride, P4_PITCH, C.rows4_alloc[th4]);
+            if (rc != TI_OK) return rc;
+            Rect4JobDev D{};
+            D.lut4 = C.d_lut4[th4]; D.boxes4 = C.d_boxes4[th4]; D.exc4 = C.d_exc4[th4]; D.dst = J.dst; D.dst_stride = J.dst_stride;
+            D.dst_w = C.dst_w; D.dst_h = C.dst_h; D.rows_alloc = C.rows4_alloc[th4]; D.exc_per_warp = C.exc4_per_warp[th4];
+            D.tile_begin = PP.tiles_per_set;
+            PP.tiles_per_set += (uint32_t)(C.tiles4_x[th4] * C.tiles4_y[th4]);
+            PP.rows_alloc_max = std::max(PP.rows_alloc_max, D.rows_alloc);
+            PP.exc_max = std::max(PP.exc_max, D.exc_per_warp);
+            PP.job[PP.n_jobs++] = D;
+            continue;
+        }
         if (tma_ok) {
             const int rc = tma_encode_u8_3d(ctx, &PT.map[PT.n_jobs], J.src, C.src_w, C.src_h, n_batch, (uint64_t)C.src_w,
                                             J.src_stride, M3_PITCH, C.rows3_alloc[thk]);
@@ -708,6 +727,11 @@ int launch_rectify(ti_ctx* ctx, const RectifyJob* jobs, int n_jobs, int n_batch)
     }
     P1.n_batch = P3.n_batch = P2.n_batch = PT.n_batch = n_batch;
     PT.debug = ctx->debug;
+    PP.n_batch = n_batch;
+    if (PP.n_jobs) {
+        const int rc = launch_rectify_pair(ctx, PP, th4);
+        if (rc != TI_OK) return rc;
+    }
     if (PT.n_jobs) {
         const int TH = M3_TILE_HEIGHTS[thk];
         const size_t stage = 128 + 2 * (size_t)PT.rows_alloc_max * M3_PITCH + 128;

@@ -1,0 +1,497 @@
+// Pair-window mono remap ("v4"), bit-exact with cv2.remap(INTER_LINEAR, BORDER_CONSTANT 0) on u8.
+//
+// Takes over the undistortion the reference leaves to cuVSLAM (thor_slam/slam/adapters/isaac_ros.py:364-411,
+// rectified_images:=false in Makefile:77-80).
+//
+// What changed against the v3 kernel (ti_rectify.cu): the 1-byte-shifted second copy of the source box,
+// the two builder warps that made it and the per-pixel fixed-point arithmetic are gone.
+//  * A tile's source box lands by ONE TMA load (pitch P4_PITCH, out-of-image bytes = 0 = BORDER_CONSTANT)
+//    and is used as it lies.
+//  * Two horizontally adjacent output pixels (a, b) share one WINDOW: the two aligned 32-bit words
+//    that contain source byte x0(a) of row y0, and the two words below them.  One PRMT per row picks
+//    the four bytes (a.left, a.right, b.left, b.right) out of the 8-byte window - the selector is
+//    precomputed per pair - so a pair costs 4 LDS.32 + 2 PRMT whatever the alignment of x0.
+//  * The whole bilinear blend of a pixel is two IDP.2A: the LUT holds the four 2-D weights
+//    64*(32-fx)(32-fy), 64*fx(32-fy), 64*(32-fx)fy, 64*fx*fy as two words of 16-bit halves, so
+//    R = dp2a(Wbot, bottom bytes, dp2a(Wtop, top bytes, 32768)) = 64*(S + 512) and the output pixel
+//    (S + 512) >> 10 is byte 2 of R.  The one weight that does not fit 16 bits (65536 when
+//    fx = fy = 0) is stored as 65535: byte 2 of 65535*p + 32768 is still p for every p <= 255.
+//  * Pairs whose pixel b does not lie in a's window (different source row, or more than 6 bytes to
+//    the right of the window start: ~0.5 % of the pairs of a stereo rectification map) are
+//    EXCEPTIONS.  The row loop does not know about them: it blends every pair the same way (the
+//    window word of an exception still serves pixel a; what it produces for pixel b is garbage).
+//    Afterwards each consumer warp runs ONE fix-up pass per frame: lane i takes entry i of the warp's
+//    exception list for the tile (window word, the two weight words, destination column / row),
+//    blends that single pixel from its own window and overwrites the byte (ordered behind the row
+//    loop's stores by __syncwarp).  The cost per frame is flat - one short pass whatever the number
+//    of exceptions - so the eight warps that share a stage stay in step.  Cameras with more than
+//    P4_MAX_EXC exceptions in one (tile, warp), or with source boxes wider than P4_PITCH, keep
+//    using the v3 / v2 kernels.
+//  * The LUT is 6 bytes per output pixel in memory (per pair: the window word and one word per pixel
+//    holding 32-fx, fy, fx and the fx = fy = 0 flag); a tile's 24 KB slice is prefetched into shared
+//    memory by a 1-D bulk copy one unit ahead (unit = tile x up to frames_per_unit frames of the
+//    batch), expanded ONCE per unit into the four 2-D weight words per pair, which then stay in
+//    registers for every frame of the unit.
+//
+// Shared memory: [full[8] | empty[8] | lut_full | lut_empty mbarriers, 256 B], `stages` boxes of
+// rows_alloc_max x P4_PITCH bytes, the LUT slice of the current / next unit (TH x P4_LUT_ROW_WORDS
+// words), two exception tables (8 warps x exc_max x 16 bytes; units alternate between them).
+#include "ti_rectify_pair.cuh"
+
+#include <cstring>
+
+namespace ti {
+
+#ifdef TI_EMULATE
+typedef const uint8_t* p4_addr_t;
+__device__ __forceinline__ p4_addr_t p4_addr(const uint8_t* p) { return p; }
+template <int OFF>
+__device__ __forceinline__ uint32_t p4_lds(p4_addr_t a) { return *reinterpret_cast<const uint32_t*>(ti_emu::check_align(a + OFF, 4)); }
+__device__ __forceinline__ uint2 ld_keep_u2(const void* p) { return *reinterpret_cast<const uint2*>(ti_emu::check_align(p, 8)); }
+#else
+typedef uint32_t p4_addr_t;
+__device__ __forceinline__ p4_addr_t p4_addr(const uint8_t* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+template <int OFF>
+__device__ __forceinline__ uint32_t p4_lds(p4_addr_t a) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1+%2];" : "=r"(v) : "r"(a), "n"(OFF));
+    return v;
+}
+__device__ __forceinline__ uint2 ld_keep_u2(const void* p) {
+    uint2 r;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v2.u32 {%0,%1}, [%2], %3;"
+                 : "=r"(r.x), "=r"(r.y)
+                 : "l"(p), "l"(policy_evict_last()));
+    return r;
+}
+#endif
+
+// mbarrier wait / arrive on a barrier named by its shared-window address (no generic->shared conversion per use)
+#ifdef TI_EMULATE
+__device__ __forceinline__ void p4_wait(p4_addr_t bar, uint32_t parity) {
+    mbar_wait(reinterpret_cast<uint64_t*>(const_cast<uint8_t*>(bar)), parity);
+}
+__device__ __forceinline__ void p4_arrive(p4_addr_t bar) { mbar_arrive(reinterpret_cast<uint64_t*>(const_cast<uint8_t*>(bar))); }
+#else
+__device__ __forceinline__ void p4_wait(p4_addr_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(bar),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void p4_arrive(p4_addr_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+#endif
+
+struct Taps { uint32_t t0, t1, b0, b1; };
+
+// Unit k of this CTA: which job / tile, which frames of the batch.  Issuer and consumers walk the same list.
+struct P4Unit { int j; uint32_t tile, b0, nb; };
+__device__ __forceinline__ P4Unit p4_unit(const Rect4Params& P, uint32_t k) {
+    const uint64_t ug = (uint64_t)blockIdx.x + (uint64_t)k * gridDim.x;
+    const uint32_t c = (uint32_t)(ug / P.tiles_per_set), r = (uint32_t)(ug - (uint64_t)c * P.tiles_per_set);
+    int j = 0;
+    while (j + 1 < P.n_jobs && r >= P.job[j + 1].tile_begin) ++j;
+    P4Unit U;
+    U.j = j; U.tile = r - P.job[j].tile_begin;
+    U.b0 = c * (uint32_t)P.frames_per_unit;
+    U.nb = min((uint32_t)P.frames_per_unit, (uint32_t)P.n_batch - U.b0);
+    return U;
+}
+
+// prmt.b32 with the selector taken as it is (CUDA's __byte_perm masks it with 0x7777 first - one more
+// instruction per window row; bit 3 of a nibble only matters in flagged window words, see below)
+__device__ __forceinline__ uint32_t p4_prmt(uint32_t lo, uint32_t hi, uint32_t sel) {
+#ifdef TI_EMULATE
+    return __byte_perm(lo, hi, sel);
+#else
+    uint32_t d;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(lo), "r"(hi), "r"(sel));
+    return d;
+#endif
+}
+
+__device__ __forceinline__ Taps p4_fetch(p4_addr_t base, uint32_t window_word) {
+    const p4_addr_t a = base + (window_word >> 16);
+    Taps T;
+    T.t0 = p4_lds<0>(a); T.t1 = p4_lds<4>(a); T.b0 = p4_lds<P4_PITCH>(a); T.b1 = p4_lds<P4_PITCH + 4>(a);
+    return T;
+}
+
+// LUT pixel word -> the two weight words of the pixel.  e = (32-fx) | fy << 6 | z << 11 | fx << 16 for a
+// pixel with a tap inside the image (z = 1 iff fx = fy = 0), 0 otherwise.
+//   Wtop = 64*(32-fy) * {32-fx, fx} - z      (16-bit halves; 65536 -> 65535 in the one case it occurs)
+//   Wbot = 64*fy      * {32-fx, fx}
+__device__ __forceinline__ void p4_expand(uint32_t e, uint32_t& wtop, uint32_t& wbot) {
+    const uint32_t pw = e & 0x001F003Fu, fy64 = e & (31u << 6);
+    wtop = (2048u - fy64) * pw - ((e >> 11) & 1u);
+    wbot = fy64 * pw;
+}
+
+// both pixels of a pair from the window `T`: 64 * (S + 512) of pixel a / pixel b (the pixel is byte 2).
+__device__ __forceinline__ void p4_blend(const Taps& T, const uint4& w, uint32_t m, uint32_t& ra, uint32_t& rb) {
+    const uint32_t wt = p4_prmt(T.t0, T.t1, m), wb = p4_prmt(T.b0, T.b1, m);
+    ra = __dp2a_lo(w.y, wb, __dp2a_lo(w.x, wt, 32768u));
+    rb = __dp2a_hi(w.w, wb, __dp2a_hi(w.z, wt, 32768u));
+}
+
+// One frame of one tile for one consumer warp: RPW rows x (2 pairs per lane).
+// WHOLE: every pixel of the warp's rows exists and rows start on even addresses (16-bit stores).
+template <int RPW, bool WHOLE>
+__device__ __forceinline__ void p4_rows(const uint4 (&w0)[RPW], const uint4 (&w1)[RPW], const uint2 (&mw)[RPW], p4_addr_t base,
+                                        uint8_t* dp, int dst_w, int live_rows, int live_cols, int lane) {
+    // software pipeline: the windows of row q+1 are in flight while row q is blended and stored
+    Taps A = p4_fetch(base, mw[0].x), B = p4_fetch(base, mw[0].y);
+#pragma unroll
+    for (int q = 0; q < RPW; ++q) {
+        Taps An = A, Bn = B;
+        if (q + 1 < RPW) { An = p4_fetch(base, mw[q + 1].x); Bn = p4_fetch(base, mw[q + 1].y); }
+        uint32_t ra0, rb0, ra1, rb1;
+        p4_blend(A, w0[q], mw[q].x, ra0, rb0);
+        p4_blend(B, w1[q], mw[q].y, ra1, rb1);
+        const uint32_t o0 = __byte_perm(ra0, rb0, 0x0062), o1 = __byte_perm(ra1, rb1, 0x0062);
+        if (WHOLE) {
+            st_stream_b16(dp, o0);
+            st_stream_b16(dp + 64, o1);
+        } else if (q < live_rows) {
+            const int c0 = 2 * lane, c1 = 64 + 2 * lane;
+            if (c0 < live_cols) st_stream_b8(dp, o0);
+            if (c0 + 1 < live_cols) st_stream_b8(dp + 1, o0 >> 8);
+            if (c1 < live_cols) st_stream_b8(dp + 64, o1);
+            if (c1 + 1 < live_cols) st_stream_b8(dp + 65, o1 >> 8);
+        }
+        dp += dst_w;
+        A = An; B = Bn;
+    }
+}
+
+// Fix-up pass: this lane's exception entry {window word, Wtop, Wbot, row << 16 | column} -> one pixel.
+__device__ __forceinline__ void p4_fixup(p4_addr_t entry, p4_addr_t base, uint8_t* warp_dst, int dst_w) {
+    const uint32_t ex = p4_lds<0>(entry), wt = p4_lds<4>(entry), wb = p4_lds<8>(entry), where = p4_lds<12>(entry);
+    const Taps X = p4_fetch(base, ex);
+    const uint32_t xt = p4_prmt(X.t0, X.t1, ex), xb = p4_prmt(X.b0, X.b1, ex);
+    const uint32_t r = __dp2a_lo(wb, xb, __dp2a_lo(wt, xt, 32768u));
+    st_stream_b8(warp_dst + (size_t)(where >> 16) * dst_w + (where & 0xFFFFu), r >> 16);
+}
+
+template <int TH>
+__global__ void __launch_bounds__(P4_THREADS, TH == 32 ? 3 : 4) rectify_mono_pair_kernel(const __grid_constant__ Rect4Params P) {
+    TI_DYNAMIC_SMEM(uint8_t, smem);
+    constexpr int RPW = TH / P4_CONSUMER_WARPS;  // tile rows per consumer warp
+    constexpr uint32_t LUT_BYTES = (uint32_t)TH * P4_LUT_ROW_WORDS * 4u;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t stage_bytes = (uint32_t)P.rows_alloc_max * P4_PITCH;  // rows_alloc is a multiple of 8: 128-byte granular
+    const uint32_t exc_buf_bytes = (uint32_t)P.exc_max * (P4_CONSUMER_WARPS * 16);
+    const int S = P.stages;
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem);  // [S] box landed
+    uint64_t* empty = full + P4_MAX_STAGES;              // [S] consumers done
+    uint64_t* lut_full = empty + P4_MAX_STAGES;          // LUT slice of the unit landed
+    uint64_t* lut_empty = lut_full + 1;                  // every consumer warp has expanded its part of the slice
+    uint8_t* stage0 = smem + 256;
+    uint8_t* lutbuf = stage0 + (size_t)S * stage_bytes;
+    uint8_t* excbuf = lutbuf + LUT_BYTES;  // two tables of exc_buf_bytes
+
+    if (tid == 0) {
+        for (int s = 0; s < S; ++s) {
+            mbar_init(full + s, 1);
+            mbar_init(empty + s, P4_CONSUMER_WARPS);
+        }
+        mbar_init(lut_full, 1);
+        mbar_init(lut_empty, P4_CONSUMER_WARPS);
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    const uint32_t n_chunks = (uint32_t)((P.n_batch + P.frames_per_unit - 1) / P.frames_per_unit);
+    const uint64_t total_units = (uint64_t)P.tiles_per_set * n_chunks;
+    const uint32_t units_mine = total_units > blockIdx.x ? (uint32_t)((total_units - blockIdx.x + gridDim.x - 1) / gridDim.x) : 0u;
+    if (units_mine == 0) return;
+
+    if (warp == P4_CONSUMER_WARPS) {
+        // ------------------------------------------------ issuer (one thread) ------------------------
+        if (lane != 0) return;
+        struct Unit { int j; uint32_t tile, b0, nb; uint4 box; };
+        auto load_unit = [&](uint32_t k, Unit& U) {
+            const P4Unit u = p4_unit(P, k);
+            U.j = u.j; U.tile = u.tile; U.b0 = u.b0; U.nb = u.nb;
+            U.box = *reinterpret_cast<const uint4*>(P.job[u.j].boxes4 + u.tile);
+        };
+        auto issue_lut = [&](const Unit& U, uint32_t k) {  // LUT slice + exception table of unit k
+            const Rect4JobDev& J = P.job[U.j];
+            const uint32_t eb = (uint32_t)J.exc_per_warp * (P4_CONSUMER_WARPS * 16);
+            bulk_load_1d(lutbuf, J.lut4 + (size_t)U.tile * (TH * P4_LUT_ROW_WORDS), LUT_BYTES, lut_full);
+            if (eb) bulk_load_1d(excbuf + (k & 1u) * exc_buf_bytes, J.exc4 + (size_t)U.tile * (eb / 4), eb, lut_full);
+            mbar_arrive_expect_tx(lut_full, LUT_BYTES + eb);
+        };
+        Unit cur{}, nxt{};
+        load_unit(0, cur);
+        issue_lut(cur, 0);
+        if (units_mine > 1) load_unit(1, nxt);
+        int s = 0;
+        uint32_t phase = 1;  // parity to wait for on empty[s]: 1 on a stage's first use (passes at once)
+        for (uint32_t k = 0; k < units_mine; ++k) {
+            const Rect4JobDev& J = P.job[cur.j];
+            const int c0 = (int16_t)(cur.box.x & 0xFFFF), y0 = (int16_t)(cur.box.x >> 16);
+            const int rows = (int16_t)(cur.box.y >> 16);
+            const uint32_t tx = rows > 0 ? (uint32_t)J.rows_alloc * P4_PITCH : 0u;
+            bool lut_pending = k + 1 < units_mine;  // the next unit's LUT slice still has to be requested
+            for (uint32_t f = 0; f < cur.nb; ++f) {
+                const uint32_t b = cur.b0 + f;
+                uint8_t* sb = stage0 + (size_t)s * stage_bytes;
+                mbar_wait_relaxed(empty + s, phase);  // consumers have released the stage's previous item
+                if (rows > 0 && !(P.debug & 2)) tma_load_3d(sb, &P.map[cur.j], c0, y0, (int)b, full + s);  // one box: P4_PITCH x rows_alloc bytes
+                mbar_arrive_expect_tx(full + s, (P.debug & 2) ? 0u : tx);
+                if (++s == S) { s = 0; phase ^= 1u; }
+                // the LUT buffer is free again once all consumer warps hold unit k in registers
+                if (lut_pending && mbar_test(lut_empty, k & 1u)) { issue_lut(nxt, k + 1); lut_pending = false; }
+            }
+            if (lut_pending) { mbar_wait_relaxed(lut_empty, k & 1u); issue_lut(nxt, k + 1); }
+            cur = nxt;
+            if (k + 2 < units_mine) load_unit(k + 2, nxt);
+        }
+        return;
+    }
+    // ---------------------------------------------------- consumers ---------------------------------
+    // Lane L owns, in each of its warp's RPW tile rows, pair 0 = pixels (2L, 2L+1) and pair 1 =
+    // pixels (64+2L, 65+2L): the 32 windows of one load instruction cover ~64 consecutive source
+    // bytes (17 words: conflict-free), stores are 64 contiguous bytes per warp instruction.
+    uint4 w0[RPW], w1[RPW];  // weights of pair 0 / pair 1: {Wtop(a), Wbot(a), Wtop(b), Wbot(b)}
+    uint2 mw[RPW];           // window words of pair 0 / pair 1
+    const p4_addr_t sm0 = p4_addr(smem);
+    const p4_addr_t stage_first = sm0 + 256;
+    const bool skip_blend = (P.debug & 1) != 0;
+    p4_addr_t base = stage_first, bar = sm0;  // current stage, its `full` barrier (`empty` is 64 bytes further)
+    int s = 0;
+    uint32_t phase = 0;
+    for (uint32_t k = 0; k < units_mine; ++k) {
+        const P4Unit U = p4_unit(P, k);
+        const Rect4JobDev& J = P.job[U.j];
+        const uint4 box = *reinterpret_cast<const uint4*>(J.boxes4 + U.tile);
+        const int u0 = (int16_t)(box.z & 0xFFFF), v0 = (int16_t)(box.z >> 16) + warp * RPW;
+        const int dst_w = J.dst_w, live_rows = J.dst_h - v0, live_cols = J.dst_w - u0;
+        const uint64_t dst_stride = J.dst_stride;
+        uint8_t* dp = J.dst + (uint64_t)U.b0 * dst_stride + (size_t)v0 * dst_w + u0 + 2 * lane;
+        const bool whole = live_rows >= RPW && live_cols >= P4_TW &&
+                           ((((uint64_t)(uintptr_t)J.dst | dst_stride | (uint64_t)dst_w) & 1ull) == 0);  // warp-uniform
+        uint8_t* const warp_dst0 = J.dst + (uint64_t)U.b0 * dst_stride + (size_t)v0 * dst_w + u0;  // fix-up pass: (row 0, column 0) of this warp
+
+        // expand this lane's part of the unit's LUT slice into weight registers
+        mbar_wait(lut_full, k & 1u);
+        {
+            const uint2* lp = reinterpret_cast<const uint2*>(lutbuf) + ((size_t)(warp * RPW) * 32 + lane) * 3;
+#pragma unroll
+            for (int q = 0; q < RPW; ++q) {
+                const uint2 e0 = lp[q * 96], e1 = lp[q * 96 + 1], e2 = lp[q * 96 + 2];  // {m0, a0}, {b0, m1}, {a1, b1}
+                mw[q] = make_uint2(e0.x, e1.y);
+                p4_expand(e0.y, w0[q].x, w0[q].y);
+                p4_expand(e1.x, w0[q].z, w0[q].w);
+                p4_expand(e2.x, w1[q].x, w1[q].y);
+                p4_expand(e2.y, w1[q].z, w1[q].w);
+            }
+        }
+        // this lane's exception entry (if any): entries are dense from 0, an unused one has all bits set in its last word
+        const p4_addr_t my_exc = sm0 + 256u + (uint32_t)S * stage_bytes + LUT_BYTES + (k & 1u) * exc_buf_bytes +
+                                 (uint32_t)(warp * J.exc_per_warp + lane) * 16u;
+        const bool i_fix = lane < J.exc_per_warp && p4_lds<12>(my_exc) != 0xFFFFFFFFu;
+        const bool warp_fixes = __ballot_sync(0xFFFFFFFFu, i_fix) != 0u;  // warp-uniform
+        __syncwarp();  // every lane's reads of the LUT slice are ordered before the release below
+        if (lane == 0) mbar_arrive(lut_empty);
+
+        for (uint32_t f = 0; f < U.nb; ++f) {
+            p4_wait(bar, phase);
+            if (!skip_blend) {
+                if (whole) p4_rows<RPW, true>(w0, w1, mw, base, dp, dst_w, live_rows, live_cols, lane);
+                else p4_rows<RPW, false>(w0, w1, mw, base, dp, dst_w, live_rows, live_cols, lane);
+                if (warp_fixes) {
+                    __syncwarp();  // the fix-up stores land behind the row loop's stores to the same bytes
+                    if (i_fix) p4_fixup(my_exc, base, warp_dst0 + (uint64_t)f * dst_stride, dst_w);
+                }
+            }
+            __syncwarp();
+            if (lane == 0) p4_arrive(bar + 64);
+            dp += dst_stride;
+            if (++s == S) { s = 0; phase ^= 1u; base = stage_first; bar = sm0; }
+            else { base += stage_bytes; bar += 8; }
+        }
+    }
+}
+
+// ---- launcher ------------------------------------------------------------------------------------
+int launch_rectify_pair(ti_ctx* ctx, Rect4Params& P, int th_index) {
+    if (P.n_jobs == 0 || P.n_batch <= 0) return TI_OK;
+    const int TH = P4_TILE_HEIGHTS[th_index];
+    const size_t stage = (size_t)P.rows_alloc_max * P4_PITCH;
+    const size_t lut_bytes = (size_t)TH * P4_LUT_ROW_WORDS * 4 + 2 * (size_t)P.exc_max * (P4_CONSUMER_WARPS * 16);
+    typedef void (*Kern)(const Rect4Params);
+    static const Kern kernels[2] = {rectify_mono_pair_kernel<16>, rectify_mono_pair_kernel<32>};
+    const Kern kern = kernels[th_index];
+    // ring depth: as asked, but never so deep that fewer CTAs fit an SM than the register budget allows
+    const int want_ctas = TH == 32 ? 3 : 4;
+    int stages = std::max(2, std::min(ctx->stages4, P4_MAX_STAGES));
+    while (stages > 2 && (256 + (size_t)stages * stage + lut_bytes + 1024) * want_ctas > 228 * 1024) --stages;
+    P.stages = stages;
+    P.debug = ctx->debug;
+    const size_t smem = 256 + (size_t)stages * stage + lut_bytes;
+#ifndef TI_EMULATE
+    TI_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+#endif
+    int per_sm = resident_ctas(kern, P4_THREADS, smem, 3);
+    if (ctx->ctas_per_sm > 0) per_sm = ctx->ctas_per_sm;
+    const uint64_t grid_max = (uint64_t)ctx->sm_count * per_sm;
+    // frames per unit: about 16 (one LUT expansion costs roughly one frame of work), the batch split evenly
+    int fpu = ctx->frames_per_unit4;
+    if (fpu <= 0) {
+        const int chunks = (P.n_batch + 15) / 16;
+        fpu = (P.n_batch + chunks - 1) / chunks;
+    }
+    P.frames_per_unit = std::max(1, std::min(P.n_batch, fpu));
+    const uint64_t total = (uint64_t)P.tiles_per_set * ((P.n_batch + P.frames_per_unit - 1) / P.frames_per_unit);
+    const int grid = (int)std::min<uint64_t>(total, grid_max);
+    TI_LAUNCH(kern, grid, P4_THREADS, smem, ctx->stream, P);
+    TI_CHECK_LAUNCH(ctx);
+    return TI_OK;
+}
+
+// ---- tables (host, at calibration upload) -----------------------------------------------------------
+void free_pair_tables(CameraSlot& C) {
+    for (int k = 0; k < 2; ++k) {
+        if (C.d_lut4[k]) cudaFree(C.d_lut4[k]);
+        if (C.d_boxes4[k]) cudaFree(C.d_boxes4[k]);
+        if (C.d_exc4[k]) cudaFree(C.d_exc4[k]);
+        C.d_lut4[k] = nullptr; C.d_boxes4[k] = nullptr; C.d_exc4[k] = nullptr;
+        C.has_pair[k] = false; C.exc4_per_warp[k] = 0; C.rows4_alloc[k] = 0;
+    }
+}
+
+namespace {
+struct Px {  // one output pixel decoded from the generic LUT
+    bool in;  // at least one tap inside the source image
+    int x0, y0;
+    uint32_t fx, fy;
+};
+inline Px decode(uint32_t e) {
+    Px p{};
+    p.in = e != LUT_OUTSIDE;
+    if (p.in) {
+        p.x0 = (int)(e & LUT_COORD_MASK) - 1; p.y0 = (int)((e >> LUT_COORD_BITS) & LUT_COORD_MASK) - 1;
+        p.fx = (e >> 22) & 31u; p.fy = e >> 27;
+    }
+    return p;
+}
+inline void host_expand(uint32_t e, uint32_t& wtop, uint32_t& wbot) {  // same arithmetic as p4_expand
+    const uint32_t pw = e & 0x001F003Fu, fy64 = e & (31u << 6);
+    wtop = (2048u - fy64) * pw - ((e >> 11) & 1u);
+    wbot = fy64 * pw;
+}
+inline uint32_t pixel_word(const Px& p) {  // see p4_expand
+    if (!p.in) return 0u;
+    return (32u - p.fx) | (p.fy << 6) | ((p.fx == 0 && p.fy == 0 ? 1u : 0u) << 11) | (p.fx << 16);
+}
+}  // namespace
+
+int build_pair_tables(ti_ctx* ctx, CameraSlot& C, const std::vector<uint32_t>& lut, int lut_pitch) {
+    free_pair_tables(C);
+    if (C.src_w % 16 != 0) return TI_OK;  // TMA row pitch must be a multiple of 16 bytes
+    const int dst_w = C.dst_w, dst_h = C.dst_h;
+    for (int k = 0; k < 2; ++k) {
+        const int TH = P4_TILE_HEIGHTS[k], RPW = TH / P4_CONSUMER_WARPS;
+        const int tx_n = (dst_w + P4_TW - 1) / P4_TW, ty_n = (dst_h + TH - 1) / TH;
+        const size_t n_tiles = (size_t)tx_n * ty_n;
+        std::vector<TileBox2> boxes(n_tiles);
+        auto entry = [&](int u, int v) -> uint32_t { return (u < dst_w && v < dst_h) ? lut[(size_t)v * lut_pitch + u] : LUT_OUTSIDE; };
+        bool ok = true;
+        int rows_max = 0;
+        for (int ty = 0; ty < ty_n && ok; ++ty)
+            for (int tx = 0; tx < tx_n && ok; ++tx) {
+                int bx0 = 1 << 20, by0 = 1 << 20, bx1 = -(1 << 20), by1 = -(1 << 20);
+                for (int v = ty * TH; v < std::min(dst_h, (ty + 1) * TH); ++v)
+                    for (int u = tx * P4_TW; u < std::min(dst_w, (tx + 1) * P4_TW); ++u) {
+                        const Px p = decode(entry(u, v));
+                        if (!p.in) continue;
+                        bx0 = std::min(bx0, p.x0); by0 = std::min(by0, p.y0); bx1 = std::max(bx1, p.x0 + 2); by1 = std::max(by1, p.y0 + 2);
+                    }
+                TileBox2& B = boxes[(size_t)ty * tx_n + tx];
+                B = TileBox2{0, 0, 0, 0, (int16_t)(tx * P4_TW), (int16_t)(ty * TH), 0, 0};
+                if (bx1 <= bx0) continue;
+                const int c0 = bx0 & ~15;  // floor to 16 (-1 -> -16): TMA boxes start on 16-byte columns
+                if (bx1 - c0 > P4_PITCH || by1 - by0 > P4_MAX_ROWS) { ok = false; break; }
+                B.c0 = (int16_t)c0; B.y0 = (int16_t)by0; B.nvec = (int16_t)((bx1 - c0 + 15) / 16); B.rows = (int16_t)(by1 - by0);
+                rows_max = std::max(rows_max, by1 - by0);
+            }
+        if (!ok) continue;
+        const int rows_alloc = std::max(8, (rows_max + 7) / 8 * 8);
+
+        std::vector<uint32_t> lut4(n_tiles * TH * P4_LUT_ROW_WORDS, 0u);
+        std::vector<std::vector<uint32_t>> exc(n_tiles * P4_CONSUMER_WARPS);  // 4 words per entry
+        for (int ty = 0; ty < ty_n && ok; ++ty)
+            for (int tx = 0; tx < tx_n && ok; ++tx) {
+                const size_t tile = (size_t)ty * tx_n + tx;
+                const TileBox2& B = boxes[tile];
+                for (int row = 0; row < TH && ok; ++row) {
+                    uint32_t* rw = lut4.data() + (tile * TH + row) * P4_LUT_ROW_WORDS;
+                    std::vector<uint32_t>& ex = exc[tile * P4_CONSUMER_WARPS + row / RPW];
+                    for (int lane = 0; lane < 32 && ok; ++lane)
+                        for (int p = 0; p < 2; ++p) {
+                            const int ua = tx * P4_TW + p * 64 + 2 * lane, v = ty * TH + row;
+                            const Px a = decode(entry(ua, v)), b = decode(entry(ua + 1, v));
+                            uint32_t* w = rw + (lane * 2 + p) * 3;  // {window word, pixel a, pixel b}
+                            w[1] = pixel_word(a);
+                            w[2] = pixel_word(b);
+                            uint32_t& m = w[0];
+                            m = 0x3210u;
+                            if (!a.in && !b.in) continue;
+                            const Px& anchor = a.in ? a : b;  // the window is placed for pixel a (for b when a has no tap inside)
+                            const int wordx = (anchor.x0 - B.c0) & ~3;
+                            const uint32_t off = (uint32_t)((anchor.y0 - B.y0) * P4_PITCH + wordx);
+                            const uint32_t sa = a.in ? (uint32_t)(a.x0 - B.c0 - wordx) : 0u;
+                            const int sb_rel = b.in ? b.x0 - B.c0 - wordx : (int)sa;
+                            const bool b_fits = !b.in || (b.y0 == anchor.y0 && sb_rel >= 0 && sb_rel <= 6);
+                            if (b_fits) {
+                                m = (off << 16) | sa | ((sa + 1) << 4) | ((uint32_t)sb_rel << 8) | ((uint32_t)(sb_rel + 1) << 12);
+                            } else {
+                                // pixel b gets an entry of the warp's exception list: its own window (bytes b.left, b.right
+                                // selected into bytes 0, 1), its weight words, where it goes (row of the warp << 16 | tile column)
+                                if (ex.size() / 4 >= (size_t)P4_MAX_EXC) { ok = false; break; }
+                                const int wordb = (b.x0 - B.c0) & ~3;
+                                const uint32_t offb = (uint32_t)((b.y0 - B.y0) * P4_PITCH + wordb);
+                                const uint32_t sb = (uint32_t)(b.x0 - B.c0 - wordb);
+                                m = (off << 16) | sa | ((sa + 1) << 4) | (sa << 8) | ((sa + 1) << 12);  // b reads a's bytes: harmless
+                                uint32_t wt, wb;
+                                host_expand(pixel_word(b), wt, wb);
+                                ex.push_back((offb << 16) | sb | ((sb + 1) << 4) | (sb << 8) | ((sb + 1) << 12));
+                                ex.push_back(wt);
+                                ex.push_back(wb);
+                                ex.push_back(((uint32_t)(row % RPW) << 16) | (uint32_t)(p * 64 + 2 * lane + 1));
+                            }
+                        }
+                }
+            }
+        if (!ok) continue;
+        size_t e_max = 0;
+        for (const auto& e : exc) e_max = std::max(e_max, e.size() / 4);
+        const int epw = (int)e_max;
+        std::vector<uint32_t> exc_flat(std::max<size_t>(4, n_tiles * P4_CONSUMER_WARPS * epw * 4), 0xFFFFFFFFu);  // unused entries: all ones
+        for (size_t i = 0; i < exc.size(); ++i)
+            if (!exc[i].empty()) std::memcpy(exc_flat.data() + i * epw * 4, exc[i].data(), exc[i].size() * sizeof(uint32_t));
+
+        TI_CUDA(ctx, cudaMalloc(&C.d_lut4[k], lut4.size() * sizeof(uint32_t)));
+        TI_CUDA(ctx, cudaMalloc(&C.d_boxes4[k], boxes.size() * sizeof(TileBox2)));
+        TI_CUDA(ctx, cudaMalloc(&C.d_exc4[k], exc_flat.size() * sizeof(uint32_t)));
+        TI_CUDA(ctx, cudaMemcpy(C.d_lut4[k], lut4.data(), lut4.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+        TI_CUDA(ctx, cudaMemcpy(C.d_boxes4[k], boxes.data(), boxes.size() * sizeof(TileBox2), cudaMemcpyHostToDevice));
+        TI_CUDA(ctx, cudaMemcpy(C.d_exc4[k], exc_flat.data(), exc_flat.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+        C.tiles4_x[k] = tx_n; C.tiles4_y[k] = ty_n; C.rows4_alloc[k] = rows_alloc; C.exc4_per_warp[k] = epw;
+        C.has_pair[k] = true;
+    }
+    return TI_OK;
+}
+
+}  // namespace ti

@@ -51,6 +51,7 @@ SIGNATURES: dict[str, tuple] = {
     "ti_device_sm_count": (C.c_int, [C.c_void_p]),
     "ti_upload_rectify_map": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "ti_upload_projection": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
+    "ti_rectify_plan": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_int32)]),
     "ti_get_valid_mask": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
     "ti_convert": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_uint64, C.c_uint64]),
     "ti_rectify": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_uint64, C.c_uint64]),

@@ -160,6 +160,14 @@ class IngestContext:
     def camera_info(self, camera: int) -> dict:
         return dict(self._cams.get(camera, {}))
 
+    def rectify_plan(self, camera: int) -> dict:
+        """Which mono remap kernel slot ``camera`` runs under the current options (``ti_rectify_plan``)."""
+        import ctypes
+
+        out = (ctypes.c_int32 * 4)()
+        self._check(self.lib.ti_rectify_plan(self._h, camera, out))
+        return {"variant": int(out[0]), "tile_h": int(out[1]), "rows": int(out[2]), "exceptions_per_warp": int(out[3])}
+
     def get_valid_mask(self, camera: int, out: Any) -> Any:
         self._check(self.lib.ti_get_valid_mask(self._h, camera, self._ptr(out)))
         return out

@@ -42,6 +42,7 @@ def main() -> None:
     ap.add_argument("--batch", type=int, default=32)
     ap.add_argument("--iters", type=int, default=20)
     ap.add_argument("--only", default="")
+    ap.add_argument("--one", action="store_true", help="rectify: first variant only (for ncu)")
     args = ap.parse_args()
     peak = 6454.3
     p = ROOT / "MEASURED_PEAKS.json"
@@ -70,7 +71,9 @@ def main() -> None:
     px = NS * B * W * H
 
     if not args.only or "rect" in args.only:
-        for variant, th, fpu, stages, pf in ((3, 32, 16, 2, 0), (3, 32, 8, 3, 1), (2, 32, 8, 3, 1)):
+        print("plan", ctx.rectify_plan(0), flush=True)
+        for variant, th, fpu, stages, pf in ((4, 32, 0, 4, 0), (4, 32, 16, 4, 0), (4, 32, 16, 3, 0), (4, 32, 16, 5, 0), (4, 32, 8, 4, 0), (4, 32, 32, 4, 0),
+                                             (4, 16, 0, 4, 0), (4, 16, 16, 6, 0), (3, 32, 16, 2, 0))[:1 if args.one else None]:
             ctx.set_option(ctx.OPT_MONO_VARIANT, variant)
             ctx.set_option(ctx.OPT_TMA_TILE_H, th)
             ctx.set_option(ctx.OPT_FRAMES_PER_UNIT, fpu)
@@ -79,10 +82,22 @@ def main() -> None:
             report(f"rectify mono v{variant} th={th} fpu={fpu} S={stages} prefetch={pf}", timeit(lambda: ctx.ingest(specs), args.iters), 2 * px, px)
         ctx.set_option(ctx.OPT_CTAS_PER_SM, 0)
         ctx.set_option(ctx.OPT_FRAMES_PER_UNIT, 16)
-        ctx.set_option(ctx.OPT_STAGES, 2)
+        ctx.set_option(ctx.OPT_FRAMES_PER_UNIT, 0)
+        ctx.set_option(ctx.OPT_STAGES, 4)
         ctx.set_option(ctx.OPT_LUT_PREFETCH, 0)
-        ctx.set_option(ctx.OPT_MONO_VARIANT, 3)
+        ctx.set_option(ctx.OPT_MONO_VARIANT, 4)
         ctx.set_option(ctx.OPT_TMA_TILE_H, 32)
+        if args.one:
+            ctx.close()
+            return
+        for dbg, what in ((1, "loads only (no blend)"), (2, "blend only (no loads)"), (3, "pipeline only")):
+            ctx.set_option(ctx.OPT_DEBUG, dbg)
+            report(f"rectify mono v4 DEBUG {what}", timeit(lambda: ctx.ingest(specs), args.iters), 2 * px, px)
+        ctx.set_option(ctx.OPT_DEBUG, 0)
+        for per_sm in (1, 2, 3):
+            ctx.set_option(ctx.OPT_CTAS_PER_SM, per_sm)
+            report(f"rectify mono v4 th=32 ctas/sm={per_sm}", timeit(lambda: ctx.ingest(specs), args.iters), 2 * px, px)
+        ctx.set_option(ctx.OPT_CTAS_PER_SM, 0)
         ctx.set_option(ctx.OPT_FORCE_GENERIC_RECTIFY, 1)
         report("rectify mono generic (v1 tiled)", timeit(lambda: ctx.ingest(specs), max(3, args.iters // 4)), 2 * px, px)
         ctx.set_option(ctx.OPT_FORCE_GENERIC_RECTIFY, 0)
