@@ -80,7 +80,7 @@ def check_rectify(be, cam: int, mapx, mapy, s: str, d: str, src_w: int, src_h: i
     # every kernel variant must give the same bytes: TMA-pipelined (tile height 32 and 16), thread-staged, generic
     # (the TMA kernel also with 1 and 2 frames of the batch per LUT fetch)
     mono = d == "mono8" and s in ("mono8", "nv12")
-    variants = ([(4, 32, 8), (4, 16, 2), (4, 32, 1), (3, 32, 8), (3, 16, 2), (3, 24, 3), (3, 32, 1), (2, 32, 8), (1, 32, 8)] if mono
+    variants = ([(4, 32, 8), (4, 16, 2), (4, 32, 1), (4, 24, 3), (3, 32, 8), (3, 16, 2), (3, 24, 3), (3, 32, 1), (2, 32, 8), (1, 32, 8)] if mono
                 else [(4, 32, 8), (1, 32, 8)])
     stages = {8: 4, 2: 3, 3: 2, 1: 6}
     try:

@@ -91,8 +91,9 @@ constexpr int M3_MAX_STAGES = 8;
 // as is (pitch P4_PITCH, no shifted copy, no builder warps); two horizontally adjacent output pixels
 // share one 8-byte window per source row (see ti_rectify_pair.cu).
 constexpr int P4_TW = 128;
-constexpr int P4_TILE_HEIGHTS[2] = {16, 32};
-inline int p4_th_index(int th) { return th == 16 ? 0 : 1; }
+constexpr int P4_N_TH = 3;
+constexpr int P4_TILE_HEIGHTS[P4_N_TH] = {16, 32, 24};
+inline int p4_th_index(int th) { return th == 16 ? 0 : (th == 24 ? 2 : 1); }
 constexpr int P4_PITCH = 192;        // = 16 banks (mod 32): a lane group crossing into the next source row stays conflict-free
 constexpr int P4_MAX_ROWS = 96;
 constexpr int P4_CONSUMER_WARPS = 8;
@@ -103,13 +104,13 @@ constexpr int P4_MAX_EXC = 32;         // exception entries per (tile, warp): on
 
 struct CameraSlot {
     // rectification
-    bool has_pair[2] = {false, false};              // tile height 16, 32
-    uint32_t* d_lut4[2] = {nullptr, nullptr};       // tiles * TH * P4_LUT_ROW_WORDS
-    TileBox2* d_boxes4[2] = {nullptr, nullptr};
-    uint32_t* d_exc4[2] = {nullptr, nullptr};       // tiles * P4_CONSUMER_WARPS * exc4_per_warp entries of 4 words
-    int tiles4_x[2] = {0, 0}, tiles4_y[2] = {0, 0};
-    int rows4_alloc[2] = {0, 0};
-    int exc4_per_warp[2] = {0, 0};
+    bool has_pair[P4_N_TH] = {false, false, false};              // tile height 16, 32, 24
+    uint32_t* d_lut4[P4_N_TH] = {nullptr, nullptr, nullptr};     // tiles * TH * P4_LUT_ROW_WORDS
+    TileBox2* d_boxes4[P4_N_TH] = {nullptr, nullptr, nullptr};
+    uint32_t* d_exc4[P4_N_TH] = {nullptr, nullptr, nullptr};     // tiles * P4_CONSUMER_WARPS * exc4_per_warp entries of 4 words
+    int tiles4_x[P4_N_TH] = {0, 0, 0}, tiles4_y[P4_N_TH] = {0, 0, 0};
+    int rows4_alloc[P4_N_TH] = {0, 0, 0};
+    int exc4_per_warp[P4_N_TH] = {0, 0, 0};
     bool has_tma_mono[3] = {false, false, false};   // tile height 16, 32, 24 (index = M3_TH_INDEX)
     uint32_t* d_lut3[3] = {nullptr, nullptr, nullptr};
     TileBox2* d_boxes3[3] = {nullptr, nullptr, nullptr};

@@ -48,6 +48,7 @@ __device__ __forceinline__ p4_addr_t p4_addr(const uint8_t* p) { return p; }
 template <int OFF>
 __device__ __forceinline__ uint32_t p4_lds(p4_addr_t a) { return *reinterpret_cast<const uint32_t*>(ti_emu::check_align(a + OFF, 4)); }
 __device__ __forceinline__ uint2 ld_keep_u2(const void* p) { return *reinterpret_cast<const uint2*>(ti_emu::check_align(p, 8)); }
+__device__ __forceinline__ uint4 p4_lds128(p4_addr_t a) { return *reinterpret_cast<const uint4*>(ti_emu::check_align(a, 16)); }
 #else
 typedef uint32_t p4_addr_t;
 __device__ __forceinline__ p4_addr_t p4_addr(const uint8_t* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -55,6 +56,11 @@ template <int OFF>
 __device__ __forceinline__ uint32_t p4_lds(p4_addr_t a) {
     uint32_t v;
     asm volatile("ld.shared.u32 %0, [%1+%2];" : "=r"(v) : "r"(a), "n"(OFF));
+    return v;
+}
+__device__ __forceinline__ uint4 p4_lds128(p4_addr_t a) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
     return v;
 }
 __device__ __forceinline__ uint2 ld_keep_u2(const void* p) {
@@ -143,17 +149,28 @@ __device__ __forceinline__ void p4_blend(const Taps& T, const uint4& w, uint32_t
     rb = __dp2a_hi(w.w, wb, __dp2a_hi(w.z, wt, 32768u));
 }
 
-// One frame of one tile for one consumer warp: RPW rows x (2 pairs per lane).
+// One frame of one tile for one consumer warp: RPW rows x (2 pairs per lane), then the fix-up pass.
 // WHOLE: every pixel of the warp's rows exists and rows start on even addresses (16-bit stores).
-template <int RPW, bool WHOLE>
+// PREFETCH: software pipeline, the windows of row q+1 are in flight while row q is blended and stored (8 more registers).
+// fixes (warp-uniform): some lane has an exception entry; i_fix: this lane has one, at shared address my_exc =
+// {window word, Wtop, Wbot, row << 16 | column}.  Its window is fetched ahead of the last row's blend so that the
+// latency of the dependent loads hides behind that row; its store follows the row loop's stores (__syncwarp).
+template <int RPW, bool WHOLE, bool PREFETCH>
 __device__ __forceinline__ void p4_rows(const uint4 (&w0)[RPW], const uint4 (&w1)[RPW], const uint2 (&mw)[RPW], p4_addr_t base,
-                                        uint8_t* dp, int dst_w, int live_rows, int live_cols, int lane) {
-    // software pipeline: the windows of row q+1 are in flight while row q is blended and stored
+                                        uint8_t* dp, int dst_w, int live_rows, int live_cols, int lane, bool fixes, bool i_fix,
+                                        p4_addr_t my_exc) {
     Taps A = p4_fetch(base, mw[0].x), B = p4_fetch(base, mw[0].y);
+    uint8_t* const warp_dst = dp - 2 * lane;  // (row 0, column 0) of this warp
+    uint4 fe = make_uint4(0u, 0u, 0u, 0u);
+    Taps X = A;
 #pragma unroll
     for (int q = 0; q < RPW; ++q) {
         Taps An = A, Bn = B;
-        if (q + 1 < RPW) { An = p4_fetch(base, mw[q + 1].x); Bn = p4_fetch(base, mw[q + 1].y); }
+        if (PREFETCH && q + 1 < RPW) { An = p4_fetch(base, mw[q + 1].x); Bn = p4_fetch(base, mw[q + 1].y); }
+        if (q == RPW - 1 && fixes && i_fix) {
+            fe = p4_lds128(my_exc);
+            X = p4_fetch(base, fe.x);
+        }
         uint32_t ra0, rb0, ra1, rb1;
         p4_blend(A, w0[q], mw[q].x, ra0, rb0);
         p4_blend(B, w1[q], mw[q].y, ra1, rb1);
@@ -169,20 +186,20 @@ __device__ __forceinline__ void p4_rows(const uint4 (&w0)[RPW], const uint4 (&w1
             if (c1 + 1 < live_cols) st_stream_b8(dp + 65, o1 >> 8);
         }
         dp += dst_w;
-        A = An; B = Bn;
+        if (PREFETCH) { A = An; B = Bn; }
+        else if (q + 1 < RPW) { A = p4_fetch(base, mw[q + 1].x); B = p4_fetch(base, mw[q + 1].y); }
+    }
+    if (fixes) {
+        __syncwarp();  // the fix-up stores land behind the row loop's stores to the same bytes
+        if (i_fix) {
+            const uint32_t xt = p4_prmt(X.t0, X.t1, fe.x), xb = p4_prmt(X.b0, X.b1, fe.x);
+            const uint32_t r = __dp2a_lo(fe.z, xb, __dp2a_lo(fe.y, xt, 32768u));
+            st_stream_b8(warp_dst + (size_t)(fe.w >> 16) * dst_w + (fe.w & 0xFFFFu), r >> 16);
+        }
     }
 }
 
-// Fix-up pass: this lane's exception entry {window word, Wtop, Wbot, row << 16 | column} -> one pixel.
-__device__ __forceinline__ void p4_fixup(p4_addr_t entry, p4_addr_t base, uint8_t* warp_dst, int dst_w) {
-    const uint32_t ex = p4_lds<0>(entry), wt = p4_lds<4>(entry), wb = p4_lds<8>(entry), where = p4_lds<12>(entry);
-    const Taps X = p4_fetch(base, ex);
-    const uint32_t xt = p4_prmt(X.t0, X.t1, ex), xb = p4_prmt(X.b0, X.b1, ex);
-    const uint32_t r = __dp2a_lo(wb, xb, __dp2a_lo(wt, xt, 32768u));
-    st_stream_b8(warp_dst + (size_t)(where >> 16) * dst_w + (where & 0xFFFFu), r >> 16);
-}
-
-template <int TH>
+template <int TH, bool DEBUG>
 __global__ void __launch_bounds__(P4_THREADS, TH == 32 ? 3 : 4) rectify_mono_pair_kernel(const __grid_constant__ Rect4Params P) {
     TI_DYNAMIC_SMEM(uint8_t, smem);
     constexpr int RPW = TH / P4_CONSUMER_WARPS;  // tile rows per consumer warp
@@ -246,9 +263,9 @@ __global__ void __launch_bounds__(P4_THREADS, TH == 32 ? 3 : 4) rectify_mono_pai
             for (uint32_t f = 0; f < cur.nb; ++f) {
                 const uint32_t b = cur.b0 + f;
                 uint8_t* sb = stage0 + (size_t)s * stage_bytes;
-                mbar_wait_relaxed(empty + s, phase);  // consumers have released the stage's previous item
-                if (rows > 0 && !(P.debug & 2)) tma_load_3d(sb, &P.map[cur.j], c0, y0, (int)b, full + s);  // one box: P4_PITCH x rows_alloc bytes
-                mbar_arrive_expect_tx(full + s, (P.debug & 2) ? 0u : tx);
+                mbar_wait_sleep(empty + s, phase, 300);  // consumers have released the stage's previous item
+                if (rows > 0 && !(DEBUG && (P.debug & 2))) tma_load_3d(sb, &P.map[cur.j], c0, y0, (int)b, full + s);  // one box: P4_PITCH x rows_alloc bytes
+                mbar_arrive_expect_tx(full + s, (DEBUG && (P.debug & 2)) ? 0u : tx);
                 if (++s == S) { s = 0; phase ^= 1u; }
                 // the LUT buffer is free again once all consumer warps hold unit k in registers
                 if (lut_pending && mbar_test(lut_empty, k & 1u)) { issue_lut(nxt, k + 1); lut_pending = false; }
@@ -267,9 +284,9 @@ __global__ void __launch_bounds__(P4_THREADS, TH == 32 ? 3 : 4) rectify_mono_pai
     uint2 mw[RPW];           // window words of pair 0 / pair 1
     const p4_addr_t sm0 = p4_addr(smem);
     const p4_addr_t stage_first = sm0 + 256;
-    const bool skip_blend = (P.debug & 1) != 0;
+    const bool skip_blend = DEBUG && (P.debug & 1) != 0;
     p4_addr_t base = stage_first, bar = sm0;  // current stage, its `full` barrier (`empty` is 64 bytes further)
-    int s = 0;
+    const p4_addr_t bar_end = sm0 + 8u * (uint32_t)S;
     uint32_t phase = 0;
     for (uint32_t k = 0; k < units_mine; ++k) {
         const P4Unit U = p4_unit(P, k);
@@ -281,8 +298,6 @@ __global__ void __launch_bounds__(P4_THREADS, TH == 32 ? 3 : 4) rectify_mono_pai
         uint8_t* dp = J.dst + (uint64_t)U.b0 * dst_stride + (size_t)v0 * dst_w + u0 + 2 * lane;
         const bool whole = live_rows >= RPW && live_cols >= P4_TW &&
                            ((((uint64_t)(uintptr_t)J.dst | dst_stride | (uint64_t)dst_w) & 1ull) == 0);  // warp-uniform
-        uint8_t* const warp_dst0 = J.dst + (uint64_t)U.b0 * dst_stride + (size_t)v0 * dst_w + u0;  // fix-up pass: (row 0, column 0) of this warp
-
         // expand this lane's part of the unit's LUT slice into weight registers
         mbar_wait(lut_full, k & 1u);
         {
@@ -308,18 +323,14 @@ __global__ void __launch_bounds__(P4_THREADS, TH == 32 ? 3 : 4) rectify_mono_pai
         for (uint32_t f = 0; f < U.nb; ++f) {
             p4_wait(bar, phase);
             if (!skip_blend) {
-                if (whole) p4_rows<RPW, true>(w0, w1, mw, base, dp, dst_w, live_rows, live_cols, lane);
-                else p4_rows<RPW, false>(w0, w1, mw, base, dp, dst_w, live_rows, live_cols, lane);
-                if (warp_fixes) {
-                    __syncwarp();  // the fix-up stores land behind the row loop's stores to the same bytes
-                    if (i_fix) p4_fixup(my_exc, base, warp_dst0 + (uint64_t)f * dst_stride, dst_w);
-                }
+                if (whole) p4_rows<RPW, true, TH == 32>(w0, w1, mw, base, dp, dst_w, live_rows, live_cols, lane, warp_fixes, i_fix, my_exc);
+                else p4_rows<RPW, false, false>(w0, w1, mw, base, dp, dst_w, live_rows, live_cols, lane, warp_fixes, i_fix, my_exc);
             }
             __syncwarp();
             if (lane == 0) p4_arrive(bar + 64);
             dp += dst_stride;
-            if (++s == S) { s = 0; phase ^= 1u; base = stage_first; bar = sm0; }
-            else { base += stage_bytes; bar += 8; }
+            bar += 8; base += stage_bytes;
+            if (bar == bar_end) { bar = sm0; base = stage_first; phase ^= 1u; }
         }
     }
 }
@@ -331,10 +342,12 @@ int launch_rectify_pair(ti_ctx* ctx, Rect4Params& P, int th_index) {
     const size_t stage = (size_t)P.rows_alloc_max * P4_PITCH;
     const size_t lut_bytes = (size_t)TH * P4_LUT_ROW_WORDS * 4 + 2 * (size_t)P.exc_max * (P4_CONSUMER_WARPS * 16);
     typedef void (*Kern)(const Rect4Params);
-    static const Kern kernels[2] = {rectify_mono_pair_kernel<16>, rectify_mono_pair_kernel<32>};
-    const Kern kern = kernels[th_index];
+    static const Kern kernels[2][P4_N_TH] = {
+        {rectify_mono_pair_kernel<16, false>, rectify_mono_pair_kernel<32, false>, rectify_mono_pair_kernel<24, false>},
+        {rectify_mono_pair_kernel<16, true>, rectify_mono_pair_kernel<32, true>, rectify_mono_pair_kernel<24, true>}};
+    const Kern kern = kernels[ctx->debug ? 1 : 0][th_index];
     // ring depth: as asked, but never so deep that fewer CTAs fit an SM than the register budget allows
-    const int want_ctas = TH == 32 ? 3 : 4;
+    const int want_ctas = TH == 32 ? 3 : 4;  // = the kernel's __launch_bounds__
     int stages = std::max(2, std::min(ctx->stages4, P4_MAX_STAGES));
     while (stages > 2 && (256 + (size_t)stages * stage + lut_bytes + 1024) * want_ctas > 228 * 1024) --stages;
     P.stages = stages;
@@ -346,11 +359,18 @@ int launch_rectify_pair(ti_ctx* ctx, Rect4Params& P, int th_index) {
     int per_sm = resident_ctas(kern, P4_THREADS, smem, 3);
     if (ctx->ctas_per_sm > 0) per_sm = ctx->ctas_per_sm;
     const uint64_t grid_max = (uint64_t)ctx->sm_count * per_sm;
-    // frames per unit: about 16 (one LUT expansion costs roughly one frame of work), the batch split evenly
+    // frames per unit: a unit costs one LUT expansion (about one frame of work) plus its frames; CTAs walk the
+    // unit list in rounds of `grid_max`, so pick the even split of the batch whose rounds x (frames + 1) is least
     int fpu = ctx->frames_per_unit4;
     if (fpu <= 0) {
-        const int chunks = (P.n_batch + 15) / 16;
-        fpu = (P.n_batch + chunks - 1) / chunks;
+        double best = 1e30;
+        for (int chunks = (P.n_batch + 31) / 32; chunks <= std::max(1, (P.n_batch + 7) / 8); ++chunks) {
+            const int c = (P.n_batch + chunks - 1) / chunks;
+            const uint64_t units = (uint64_t)P.tiles_per_set * chunks;
+            const uint64_t rounds = (units + grid_max - 1) / grid_max;
+            const double cost = (double)rounds * (c + 1.0);
+            if (cost < best) { best = cost; fpu = c; }
+        }
     }
     P.frames_per_unit = std::max(1, std::min(P.n_batch, fpu));
     const uint64_t total = (uint64_t)P.tiles_per_set * ((P.n_batch + P.frames_per_unit - 1) / P.frames_per_unit);
@@ -362,7 +382,7 @@ int launch_rectify_pair(ti_ctx* ctx, Rect4Params& P, int th_index) {
 
 // ---- tables (host, at calibration upload) -----------------------------------------------------------
 void free_pair_tables(CameraSlot& C) {
-    for (int k = 0; k < 2; ++k) {
+    for (int k = 0; k < P4_N_TH; ++k) {
         if (C.d_lut4[k]) cudaFree(C.d_lut4[k]);
         if (C.d_boxes4[k]) cudaFree(C.d_boxes4[k]);
         if (C.d_exc4[k]) cudaFree(C.d_exc4[k]);
@@ -401,7 +421,7 @@ int build_pair_tables(ti_ctx* ctx, CameraSlot& C, const std::vector<uint32_t>& l
     free_pair_tables(C);
     if (C.src_w % 16 != 0) return TI_OK;  // TMA row pitch must be a multiple of 16 bytes
     const int dst_w = C.dst_w, dst_h = C.dst_h;
-    for (int k = 0; k < 2; ++k) {
+    for (int k = 0; k < P4_N_TH; ++k) {
         const int TH = P4_TILE_HEIGHTS[k], RPW = TH / P4_CONSUMER_WARPS;
         const int tx_n = (dst_w + P4_TW - 1) / P4_TW, ty_n = (dst_h + TH - 1) / TH;
         const size_t n_tiles = (size_t)tx_n * ty_n;

@@ -55,6 +55,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     while ((__atomic_load_n(&m->completed, __ATOMIC_ACQUIRE) & 1u) == parity) std::this_thread::yield();
 }
 __device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity) { mbar_wait(bar, parity); }
+__device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity, unsigned) { mbar_wait(bar, parity); }
 __device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
     EmuMbar* m = reinterpret_cast<EmuMbar*>(bar);
     return (__atomic_load_n(&m->completed, __ATOMIC_ACQUIRE) & 1u) != parity;
@@ -116,6 +117,11 @@ __device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity
             : "memory");
         if (!done) __nanosleep(200);
     } while (!done);
+}
+__device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity);
+// Poll with a fixed sleep between probes: for a lone issuer thread whose wait is about one item long.
+__device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity, unsigned ns) {
+    while (!mbar_test(bar, parity)) __nanosleep(ns);
 }
 __device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {  // one non-blocking probe
     uint32_t ok;

@@ -72,8 +72,8 @@ def main() -> None:
 
     if not args.only or "rect" in args.only:
         print("plan", ctx.rectify_plan(0), flush=True)
-        for variant, th, fpu, stages, pf in ((4, 32, 0, 4, 0), (4, 32, 16, 4, 0), (4, 32, 16, 3, 0), (4, 32, 16, 5, 0), (4, 32, 8, 4, 0), (4, 32, 32, 4, 0),
-                                             (4, 16, 0, 4, 0), (4, 16, 16, 6, 0), (3, 32, 16, 2, 0))[:1 if args.one else None]:
+        for variant, th, fpu, stages, pf in ((4, 32, 0, 3, 0), (4, 32, 0, 4, 0), (4, 32, 0, 2, 0), (4, 32, 32, 3, 0), (4, 24, 0, 3, 0), (4, 24, 0, 4, 0),
+                                             (4, 24, 0, 2, 0), (4, 16, 0, 4, 0), (3, 32, 16, 2, 0))[:1 if args.one else None]:
             ctx.set_option(ctx.OPT_MONO_VARIANT, variant)
             ctx.set_option(ctx.OPT_TMA_TILE_H, th)
             ctx.set_option(ctx.OPT_FRAMES_PER_UNIT, fpu)
