@@ -43,9 +43,10 @@ N_CAMERAS = 4  # stereo sources -> 8 streams
 STREAMS = 2 * N_CAMERAS
 PX_PER_SET = STREAMS * W * H
 ALGO_BYTES_PER_PX = 2  # mono8 -> rectified mono8
-# dram__bytes_read.sum + dram__bytes_write.sum of ONE rectify_mono_tma_kernel launch over 64 frame sets, from the
-# `ncu --set full` capture of this bench (profiles/r01_rect_ncu_raw.txt): 615.99 MB + 489.26 MB
-NCU_TRAFFIC_BYTES_PER_FRAME_SET = (615.985408e6 + 489.261312e6) / 64
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE rectify_mono_pair_kernel launch over 64 frame sets, from the
+# `ncu --set full` capture of this bench (profiles/r01_rect_v4_ncu_raw.txt): 687.25 MB + 488.14 MB
+NCU_TRAFFIC_BYTES_PER_FRAME_SET = (687.250688e6 + 488.143616e6) / 64
+KERNEL_BY_VARIANT = {4: "rectify_mono_pair_kernel<32,false>", 3: "rectify_mono_tma_kernel<32,false>", 2: "rectify_mono_kernel", 1: "rectify_tile_kernel<1>"}
 FALLBACK_HBM_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md fallback
 
 
@@ -268,6 +269,9 @@ def run_ours(args) -> None:
     for cam, (mx, my) in enumerate(maps):
         ctx.upload_rectify_map(cam, mx, my, (W, H))
 
+    plan = ctx.rectify_plan(0)
+    if plan["variant"] != 4:
+        raise SystemExit(f"bench: the benchmark rig must run the pair-window kernel, got {plan}")
     B = args.batch
     pool_frames = host_frames(sources, 2)  # two distinct frames per stream, tiled over the batch on device
     d_src, d_dst = [], []
@@ -378,8 +382,8 @@ def run_ours(args) -> None:
             "gpu_launches": launches,
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": NCU_TRAFFIC_BYTES_PER_FRAME_SET * B, "traffic_source": "ncu --set full, profiles/r01_rect_ncu_raw.txt (scaled per frame set)",
-                         "kernel": "rectify_mono_tma_kernel<32,false>", "algorithmic_bytes_per_launch": algo_bytes,
+                         "traffic": NCU_TRAFFIC_BYTES_PER_FRAME_SET * B, "traffic_source": "ncu --set full, profiles/r01_rect_v4_ncu_raw.txt (scaled per frame set)",
+                         "kernel": KERNEL_BY_VARIANT[plan["variant"]], "kernel_plan": plan, "algorithmic_bytes_per_launch": algo_bytes,
                          "peak_source": peak_src, "frac_of_8000_datasheet": achieved / 8000.0,
                          "note": "per-rank launch; duration = max-over-ranks ms_per_step (one launch per step)"},
             "cpu_baseline": cpu_baseline,
