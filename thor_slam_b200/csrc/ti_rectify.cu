@@ -737,6 +737,7 @@ int launch_rectify(ti_ctx* ctx, const RectifyJob* jobs, int n_jobs, int n_batch)
         const size_t stage = 128 + 2 * (size_t)PT.rows_alloc_max * M3_PITCH + 128;
         PT.frames_per_unit = std::max(1, std::min(n_batch, ctx->frames_per_unit));
         PT.stages = std::max(2, std::min(ctx->stages, M3_MAX_STAGES));
+        while (PT.stages > 2 && 256 + (size_t)PT.stages * stage > 220 * 1024) --PT.stages;  // tall source boxes: fewer stages
         const size_t smem = 256 + (size_t)PT.stages * stage;
         const uint64_t total = (uint64_t)PT.tiles_per_set * ((n_batch + PT.frames_per_unit - 1) / PT.frames_per_unit);
         typedef void (*Kern)(const Rect3Params);

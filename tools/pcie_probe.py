@@ -1,0 +1,49 @@
+#!/usr/bin/env python
+"""Host<->device copy ceilings of this box (pinned memory): H2D alone, D2H alone, both at once.
+
+    python tools/pcie_probe.py [--mb 256]
+
+The e2e number of bench.py moves 1 B/px in and 1 B/px out through ``ti_ingest_host``; this is the
+ceiling that path can reach.  Development tool.
+"""
+from __future__ import annotations
+
+import argparse
+import time
+
+import torch
+
+
+def main() -> None:
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--mb", type=int, default=256)
+    ap.add_argument("--iters", type=int, default=10)
+    args = ap.parse_args()
+    n = args.mb << 20
+    h_in = torch.empty(n, dtype=torch.uint8).pin_memory()
+    h_out = torch.empty(n, dtype=torch.uint8).pin_memory()
+    d_a = torch.empty(n, dtype=torch.uint8, device="cuda")
+    d_b = torch.empty(n, dtype=torch.uint8, device="cuda")
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+
+    def run(h2d: bool, d2h: bool) -> float:
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(args.iters):
+            if h2d:
+                with torch.cuda.stream(s1):
+                    d_a.copy_(h_in, non_blocking=True)
+            if d2h:
+                with torch.cuda.stream(s2):
+                    h_out.copy_(d_b, non_blocking=True)
+        torch.cuda.synchronize()
+        return (time.perf_counter() - t0) / args.iters
+
+    for name, a, b in (("H2D alone", True, False), ("D2H alone", False, True), ("H2D + D2H concurrently", True, True)):
+        run(a, b)
+        dt = run(a, b)
+        print(f"{name:26s} {n / dt / 1e9:7.1f} GB/s per direction ({args.mb} MB per copy, {dt * 1e3:.2f} ms)")
+
+
+if __name__ == "__main__":
+    main()
