@@ -507,8 +507,8 @@ def main() -> None:
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=64, help="frame sets per step (per rank)")
-    ap.add_argument("--e2e-batch", type=int, default=32, dest="e2e_batch")
-    ap.add_argument("--chunk", type=int, default=4, help="frame sets per H2D/compute/D2H pipeline stage")
+    ap.add_argument("--e2e-batch", type=int, default=64, dest="e2e_batch")
+    ap.add_argument("--chunk", type=int, default=8, help="frame sets per H2D/compute/D2H pipeline stage")
     ap.add_argument("--cpu-budget", type=float, default=10.0, dest="cpu_budget", help="seconds of CPU work for cpu_baseline")
     ap.add_argument("--ref-sets", type=int, default=8, dest="ref_sets", help="frame sets per step of the reference arm")
     ap.add_argument("--no-cpu", action="store_true", dest="no_cpu")

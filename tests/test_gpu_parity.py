@@ -176,12 +176,13 @@ def test_ingest_fused_matches_single_calls(gpu_backend):
         assert ob.points_close(gx[i], pts)[0] and np.array_equal(gm[i], msk) and int(gc[i]) == cnt
 
 
-def test_ingest_host_pipeline(gpu_backend):
-    """Host buffers in, host buffers out, chunked H2D / kernels / D2H; ragged last chunk."""
+@pytest.mark.parametrize("n,chunk", [(7, 3), (21, 8), (2, 8)])
+def test_ingest_host_pipeline(gpu_backend, n, chunk):
+    """Host buffers in, host buffers out, chunked H2D / kernels / D2H; ramped and ragged chunks."""
     import torch
 
     be = gpu_backend
-    w, h, n = 640, 400, 7
+    w, h = 640, 400
     rng = np.random.default_rng(10)
     s, maps = cases.stereo_maps(w, h, seed=10)
     be.ctx.upload_rectify_map(42, *maps[0], (w, h))
@@ -198,7 +199,7 @@ def test_ingest_host_pipeline(gpu_backend):
     be.ctx.ingest_host([
         StreamSpec(F.KIND_RECTIFY, left, o_l, F.MONO8, F.MONO8, camera=42),
         StreamSpec(F.KIND_BACKPROJECT, depth, xyz, F.DEPTH16, F.XYZ32F, camera=42, mask=mask, count=count),
-    ], chunk=3)
+    ], chunk=chunk)
     for i in range(n):
         assert np.array_equal(o_l[i].numpy(), orc.remap_cv(left[i].numpy(), *maps[0]))
         pts, msk, cnt = ob.backproject(depth_np[i], intr.matrix, m)

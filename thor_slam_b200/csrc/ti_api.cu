@@ -451,7 +451,7 @@ int ti_ingest(ti_ctx* ctx, const ti_stream* streams, int n_streams, int n_batch)
 
 // ---- host-buffer pipeline ----------------------------------------------------------------------
 // Frames arrive in (pinned) host memory; per chunk of `chunk` frame sets: H2D on one stream,
-// kernels on a second, D2H on a third, two chunk slots in flight so the three overlap.
+// kernels on a second, D2H on a third, three chunk slots in flight so the three overlap.
 
 static uint64_t stream_src_bytes(const ti_ctx* ctx, const ti_stream& S) {
     if (S.kind == TI_KIND_RECTIFY) { const CameraSlot& C = ctx->cams[S.camera]; return frame_bytes(S.src_format, C.src_w, C.src_h); }
@@ -525,12 +525,27 @@ int ti_ingest_host(ti_ctx* ctx, const ti_stream* streams, int n_streams, int n_b
     }
     cudaStream_t user_stream = ctx->stream;
     int rc = TI_OK;
-    const int n_chunks = (n_batch + chunk - 1) / chunk;
+    // Chunk schedule: the call returns only when everything has landed, so the first upload and the last
+    // download are not overlapped with anything - keep those chunks small (chunk/4, chunk/2, chunk, ..., chunk/2, chunk/4).
+    std::vector<int> sizes;
+    {
+        int left = n_batch;
+        std::vector<int> tail;
+        for (int ramp = std::max(1, chunk / 4); ramp < chunk && left > 2 * chunk; ramp *= 2) {
+            sizes.push_back(ramp); left -= ramp;
+            tail.push_back(ramp); left -= ramp;
+        }
+        while (left > 0) { const int nb = std::min(chunk, left); sizes.push_back(nb); left -= nb; }
+        sizes.insert(sizes.end(), tail.rbegin(), tail.rend());
+    }
+    const int n_chunks = (int)sizes.size();
+    int b_next = 0;
     for (int c = 0; c < n_chunks && rc == TI_OK; ++c) {
-        auto& h = ctx->hslot[c & 1];
-        const int b0 = c * chunk, nb = std::min(chunk, n_batch - b0);
+        auto& h = ctx->hslot[c % 3];
+        const int b0 = b_next, nb = sizes[c];
+        b_next += nb;
         // the slot's previous D2H must have drained before its buffers are overwritten
-        if (c >= 2) {
+        if (c >= 3) {
             cudaStreamWaitEvent(ctx->s_h2d, h.d2h_done, 0);
             cudaStreamWaitEvent(ctx->s_exec, h.d2h_done, 0);
         }

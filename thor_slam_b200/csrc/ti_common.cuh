@@ -162,7 +162,7 @@ struct ti_ctx {
         std::vector<uint32_t*> d_count;
         std::vector<size_t> cap_src, cap_dst, cap_mask, cap_count;
         cudaEvent_t h2d_done = nullptr, exec_done = nullptr, d2h_done = nullptr;
-    } hslot[2];
+    } hslot[3];  // three chunk slots in flight: upload / kernels / download of consecutive chunks never share buffers
     // NCCL (dlopen)
     void* nccl_comm = nullptr;
     int rank = 0, world = 1;
