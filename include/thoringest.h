@@ -127,12 +127,14 @@ int ti_upload_rectify_map(ti_ctx* ctx, int camera, int dst_w, int dst_h, int src
 int ti_upload_projection(ti_ctx* ctx, int camera, int width, int height, const double k[4],
                          const double body_T_cam[12]);
 
-/* Which remap kernel ti_rectify()/ti_ingest() will run for MONO8/NV12 -> MONO8 on slot `camera`
- * under the current options (diagnostic; tests use it to prove no silent fall-back to a slower
- * kernel).  out[0] = kernel variant (4 pair-window, 3 TMA + shifted copy, 2 thread-staged,
- * 1 generic), out[1] = output tile height, out[2] = source rows staged per tile,
- * out[3] = exception-table entries per (tile, warp) of the pair-window kernel. */
-int ti_rectify_plan(ti_ctx* ctx, int camera, int32_t out[4]);
+/* Which remap kernels ti_rectify()/ti_ingest() will run on slot `camera` under the current options
+ * (diagnostic; tests use it to prove there is no silent fall-back to a slower kernel).
+ * MONO8/NV12 -> MONO8 (and BGR8 -> MONO8 after its gray pre-pass): out[0] = kernel variant (4 pair-window,
+ * 3 TMA + shifted copy, 2 thread-staged, 1 generic), out[1] = output tile height, out[2] = source rows staged
+ * per tile, out[3] = exception entries per (tile, warp) of the pair-window kernel.
+ * BGR8 -> RGB8: out[4] = 5 (3-channel window kernel) or 1 (generic), out[5] = source rows staged per tile.
+ * out[6], out[7] reserved (0). */
+int ti_rectify_plan(ti_ctx* ctx, int camera, int32_t out[8]);
 
 /* u8 dst_h x dst_w mask of slot `camera`: 1 where all four bilinear taps are inside the
  * source image.  Static per calibration.  dst: DEVICE pointer. */

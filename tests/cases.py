@@ -95,6 +95,8 @@ def check_rectify(be, cam: int, mapx, mapy, s: str, d: str, src_w: int, src_h: i
                 assert plan["variant"] == expect_variant, f"slot {cam} would run kernel variant {plan}"
                 if expect_exceptions:
                     assert plan["exceptions_per_warp"] > 0, "this map was chosen to exercise the exception path"
+            if (s, d) == ("bgr8", "rgb8") and expect_variant == 4 and variant == 4:
+                assert be.ctx.rectify_plan(cam)["colour_variant"] == 5, "BGR8 -> RGB8 must run the 3-channel window kernel here"
             dst = be.zeros((n, *F.frame_shape(F.fmt(d), dst_w, dst_h)), np.uint8)
             be.ctx.rectify(cam, be.dev(src), dst, s, d)
             got = be.host(dst)

@@ -40,6 +40,7 @@ static void free_camera(CameraSlot& c) {
         if (c.d_boxes3[k]) cudaFree(c.d_boxes3[k]);
     }
     free_pair_tables(c);
+    free_c3_tables(c);
     c = CameraSlot{};
 }
 
@@ -84,6 +85,7 @@ int ti_destroy(ti_ctx* ctx) {
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
     for (auto& c : ctx->cams) free_camera(c);
+    if (ctx->scratch) cudaFree(ctx->scratch);
     for (auto& h : ctx->hslot) {
         for (void* p : h.d_src) if (p) cudaFree(p);
         for (void* p : h.d_dst) if (p) cudaFree(p);
@@ -169,6 +171,7 @@ int ti_upload_rectify_map(ti_ctx* ctx, int camera, int dst_w, int dst_h, int src
     C.d_lut = nullptr; C.d_boxes = nullptr; C.d_valid = nullptr; C.d_lut2 = nullptr; C.d_boxes2 = nullptr;
     C.has_map = false; C.has_fast_mono = false;
     free_pair_tables(C);
+    free_c3_tables(C);
     for (int k = 0; k < 3; ++k) {
         if (C.d_lut3[k]) cudaFree(C.d_lut3[k]);
         if (C.d_boxes3[k]) cudaFree(C.d_boxes3[k]);
@@ -328,7 +331,10 @@ int ti_upload_rectify_map(ti_ctx* ctx, int camera, int dst_w, int dst_h, int src
         C.tiles3_x[k] = t3x; C.tiles3_y[k] = t3y; C.rows3_alloc[k] = rows_alloc;
         C.has_tma_mono[k] = true;
     }
-    return build_pair_tables(ctx, C, lut, lut_pitch);
+    const int rc_pair = build_pair_tables(ctx, C, lut, lut_pitch);
+    C.h_lut = std::move(lut);
+    C.h_lut_pitch = lut_pitch;
+    return rc_pair;
 }
 
 int ti_upload_projection(ti_ctx* ctx, int camera, int width, int height, const double k[4], const double body_T_cam[12]) {
@@ -350,14 +356,22 @@ int ti_upload_projection(ti_ctx* ctx, int camera, int width, int height, const d
     return TI_OK;
 }
 
-int ti_rectify_plan(ti_ctx* ctx, int camera, int32_t out[4]) {
+int ti_rectify_plan(ti_ctx* ctx, int camera, int32_t out[8]) {
     if (!ctx) return TI_EINVAL;
     if (camera < 0 || camera >= TI_MAX_CAMERAS || !out) return fail(ctx, TI_EINVAL, "ti_rectify_plan: bad argument");
-    const CameraSlot& C = ctx->cams[camera];
+    CameraSlot& C = ctx->cams[camera];
     if (!C.has_map) return fail(ctx, TI_ESTATE, "ti_rectify_plan: camera slot %d has no remap LUT", camera);
     const int th4 = p4_th_index(ctx->tma_tile_h), thk = m3_th_index(ctx->tma_tile_h);
-    out[0] = 1; out[1] = RT_H; out[2] = 0; out[3] = 0;
+    out[0] = 1; out[1] = RT_H; out[2] = 0; out[3] = 0; out[4] = 1; out[5] = 0; out[6] = 0; out[7] = 0;
     if (ctx->force_generic_rectify) return TI_OK;
+    if (ctx->mono_variant == 4 && C.src_w % 16 == 0) {
+        if (!C.c3_tried) {
+            TI_CUDA(ctx, cudaSetDevice(ctx->device));
+            const int rc = build_c3_tables(ctx, C);
+            if (rc != TI_OK) return rc;
+        }
+        if (C.has_c3) { out[4] = 5; out[5] = C.rows5_alloc; }
+    }
     if (ctx->mono_variant == 4 && C.has_pair[th4]) {
         out[0] = 4; out[1] = P4_TILE_HEIGHTS[th4]; out[2] = C.rows4_alloc[th4]; out[3] = C.exc4_per_warp[th4];
     } else if (ctx->mono_variant >= 3 && C.has_tma_mono[thk]) {

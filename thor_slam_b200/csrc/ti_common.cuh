@@ -102,8 +102,25 @@ constexpr int P4_MAX_STAGES = 8;
 constexpr int P4_LUT_ROW_WORDS = 192;  // per tile row: 32 lanes x 2 pairs x {window word, pixel a word, pixel b word}
 constexpr int P4_MAX_EXC = 32;         // exception entries per (tile, warp): one lane each in the per-frame fix-up pass
 
+// 3-channel window path ("c3": BGR8 -> RGB8 rectified): tiles of C3_TW x C3_TH output pixels, one TMA box of
+// 32-bit elements per tile-frame, one 12-byte window per pixel and source row (see ti_rectify_c3.cu).
+constexpr int C3_TW = 128;
+constexpr int C3_TH = 16;
+constexpr int C3_PITCH = 512;          // bytes per staged source row (TMA box of 128 u32 elements)
+constexpr int C3_MAX_ROWS = 64;
+constexpr int C3_CONSUMER_WARPS = 8;
+constexpr int C3_THREADS = (C3_CONSUMER_WARPS + 1) * 32;
+constexpr int C3_MAX_STAGES = 8;
+constexpr int C3_LUT_ROW_WORDS = 256;  // per tile row: 128 pixels x {window word, pixel word}
+
 struct CameraSlot {
     // rectification
+    std::vector<uint32_t> h_lut;                    // host copy of the generic LUT (lazy builds of further tables)
+    int h_lut_pitch = 0;
+    bool c3_tried = false, has_c3 = false;          // built on the first BGR8 -> RGB8 rectify of the slot
+    uint32_t* d_lut5 = nullptr;                     // tiles * C3_TH * C3_LUT_ROW_WORDS
+    TileBox2* d_boxes5 = nullptr;                   // c0 in BYTES of the BGR row (multiple of 16)
+    int tiles5_x = 0, tiles5_y = 0, rows5_alloc = 0;
     bool has_pair[P4_N_TH] = {false, false, false};              // tile height 16, 32, 24
     uint32_t* d_lut4[P4_N_TH] = {nullptr, nullptr, nullptr};     // tiles * TH * P4_LUT_ROW_WORDS
     TileBox2* d_boxes4[P4_N_TH] = {nullptr, nullptr, nullptr};
@@ -155,6 +172,9 @@ struct ti_ctx {
     int frames_per_unit4 = 0;  // same for the pair-window kernel; 0 = chosen per launch (least tail over the persistent grid)
     bool force_generic_rectify = false;  // tests: exercise the generic tiled / direct kernels
     ti::CameraSlot cams[TI_MAX_CAMERAS];
+    // scratch for two-pass paths (BGR -> gray ahead of the mono remap); grown on demand, never visible to the caller
+    void* scratch = nullptr;
+    size_t scratch_cap = 0;
     // host pipeline (ti_ingest_host)
     cudaStream_t s_h2d = nullptr, s_d2h = nullptr, s_exec = nullptr;
     struct HostSlot {
@@ -253,6 +273,9 @@ int launch_rectify(ti_ctx* ctx, const RectifyJob* jobs, int n_jobs, int n_batch)
 // pair-window tables of one camera from its generic LUT (ti_rectify_pair.cu); frees / replaces the old ones
 int build_pair_tables(ti_ctx* ctx, CameraSlot& C, const std::vector<uint32_t>& lut, int lut_pitch);
 void free_pair_tables(CameraSlot& C);
+// 3-channel window tables (ti_rectify_c3.cu), built lazily from CameraSlot::h_lut
+int build_c3_tables(ti_ctx* ctx, CameraSlot& C);
+void free_c3_tables(CameraSlot& C);
 
 struct BackprojectJob {
     const uint16_t* depth;

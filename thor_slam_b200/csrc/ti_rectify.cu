@@ -638,12 +638,59 @@ static int launch_tiled(ti_ctx* ctx, RectParams& P, size_t smem_bytes) {
     return TI_OK;
 }
 
-int launch_rectify(ti_ctx* ctx, const RectifyJob* jobs, int n_jobs, int n_batch) {
+// BGR8 -> MONO8 rectified on a slot that qualifies for a fast mono kernel runs as two fast passes: the exact OpenCV
+// gray conversion (convert_vec_kernel) into library scratch, then the mono remap on the gray frames - identical to
+// cv2.remap(cvtColor(BGR2GRAY)) by construction, and ~4x faster than converting every tap inside the generic kernel.
+static int gray_prepass(ti_ctx* ctx, std::vector<RectifyJob>& jobs, int n_batch) {
+    std::vector<ConvertJob> conv;
+    std::vector<size_t> offs;
+    size_t need = 0;
+    const int th4 = p4_th_index(ctx->tma_tile_h), thk = m3_th_index(ctx->tma_tile_h);
+    for (auto& J : jobs) {
+        if (J.src_fmt != TI_FMT_BGR8 || J.dst_fmt != TI_FMT_MONO8 || ctx->force_generic_rectify || ctx->mono_variant < 3) continue;
+        if (J.camera < 0 || J.camera >= TI_MAX_CAMERAS) continue;
+        const CameraSlot& C = ctx->cams[J.camera];
+        if (!C.has_map || !(C.has_pair[th4] || C.has_tma_mono[thk]) || C.src_w % 16 != 0) continue;
+        if (!J.src || ((uintptr_t)J.src % 16) || (J.src_stride % 16)) continue;
+        const size_t frame = (size_t)C.src_w * C.src_h;  // multiple of 16
+        conv.push_back(ConvertJob{J.src, nullptr, J.src_stride, (uint64_t)frame, C.src_w, C.src_h, TI_FMT_BGR8, TI_FMT_MONO8});
+        offs.push_back(need);
+        need += frame * (size_t)n_batch;
+        J.src = nullptr;  // patched below once the scratch base is known
+        J.src_stride = frame;
+        J.src_fmt = TI_FMT_MONO8;
+    }
+    if (conv.empty()) return TI_OK;
+    if (need > ctx->scratch_cap) {
+        if (ctx->scratch) cudaFree(ctx->scratch);  // synchronises: earlier launches that read it have finished
+        ctx->scratch = nullptr; ctx->scratch_cap = 0;
+        TI_CUDA(ctx, cudaMalloc(&ctx->scratch, need));
+        ctx->scratch_cap = need;
+    }
+    size_t k = 0;
+    for (auto& J : jobs)
+        if (!J.src) {
+            conv[k].dst = static_cast<uint8_t*>(ctx->scratch) + offs[k];
+            J.src = conv[k].dst;
+            ++k;
+        }
+    return launch_convert(ctx, conv.data(), (int)conv.size(), n_batch);
+}
+
+int launch_rectify(ti_ctx* ctx, const RectifyJob* jobs_in, int n_jobs, int n_batch) {
     if (n_jobs <= 0 || n_batch <= 0) return TI_OK;
+    for (int i = 0; i < n_jobs; ++i)
+        if (!jobs_in[i].src || !jobs_in[i].dst) return fail(ctx, TI_EINVAL, "rectify: null src/dst pointer");
+    std::vector<RectifyJob> jobs(jobs_in, jobs_in + n_jobs);
+    {
+        const int rc = gray_prepass(ctx, jobs, n_batch);
+        if (rc != TI_OK) return rc;
+    }
     RectParams P1{}, P3{};  // tiled launches for 1-channel and 3-channel sources
     Rect2Params P2{};       // fast mono launch (v2: thread-staged)
     Rect3Params PT{};       // fast mono launch (v3: TMA-pipelined)
     Rect4Params PP{};       // fast mono launch (v4: pair windows)
+    Rect5Params PC{};       // fast 3-channel launch (BGR8 -> RGB8 windows)
     const int thk = m3_th_index(ctx->tma_tile_h);
     const int th4 = p4_th_index(ctx->tma_tile_h);
     size_t smem1 = 0, smem3 = 0, smem2 = 0;
@@ -669,6 +716,27 @@ int launch_rectify(ti_ctx* ctx, const RectifyJob* jobs, int n_jobs, int n_batch)
                             PT.n_jobs < MAX_RECT_JOBS && !ctx->force_generic_rectify && ctx->mono_variant >= 3;
         const bool pair_ok = mode == DM_MONO && C.has_pair[th4] && ((uintptr_t)J.src % 16 == 0) && (J.src_stride % 16 == 0) &&
                              PP.n_jobs < MAX_PAIR_JOBS && !ctx->force_generic_rectify && ctx->mono_variant == 4;
+        if (mode == DM_BGR_TO_RGB && !ctx->force_generic_rectify && ctx->mono_variant == 4 && C.src_w % 16 == 0 &&
+            ((uintptr_t)J.src % 16 == 0) && (J.src_stride % 16 == 0) && PC.n_jobs < MAX_PAIR_JOBS) {
+            CameraSlot& CM = ctx->cams[J.camera];
+            if (!CM.c3_tried) {
+                const int rc = build_c3_tables(ctx, CM);
+                if (rc != TI_OK) return rc;
+            }
+            if (CM.has_c3) {
+                const int rc = tma_encode_3d(ctx, &PC.map[PC.n_jobs], J.src, 4, 3 * C.src_w / 4, C.src_h, n_batch, (uint64_t)3 * C.src_w,
+                                             J.src_stride, C3_PITCH / 4, CM.rows5_alloc);
+                if (rc != TI_OK) return rc;
+                Rect5JobDev D{};
+                D.lut5 = CM.d_lut5; D.boxes5 = CM.d_boxes5; D.dst = J.dst; D.dst_stride = J.dst_stride;
+                D.dst_w = C.dst_w; D.dst_h = C.dst_h; D.rows_alloc = CM.rows5_alloc;
+                D.tile_begin = PC.tiles_per_set;
+                PC.tiles_per_set += (uint32_t)(CM.tiles5_x * CM.tiles5_y);
+                PC.rows_alloc_max = std::max(PC.rows_alloc_max, D.rows_alloc);
+                PC.job[PC.n_jobs++] = D;
+                continue;
+            }
+        }
         if (pair_ok) {
             const int rc = tma_encode_u8_3d(ctx, &PP.map[PP.n_jobs], J.src, C.src_w, C.src_h, n_batch, (uint64_t)C.src_w,
                                             J.src_stride, P4_PITCH, C.rows4_alloc[th4]);
@@ -727,7 +795,11 @@ int launch_rectify(ti_ctx* ctx, const RectifyJob* jobs, int n_jobs, int n_batch)
     }
     P1.n_batch = P3.n_batch = P2.n_batch = PT.n_batch = n_batch;
     PT.debug = ctx->debug;
-    PP.n_batch = n_batch;
+    PP.n_batch = PC.n_batch = n_batch;
+    if (PC.n_jobs) {
+        const int rc = launch_rectify_c3(ctx, PC);
+        if (rc != TI_OK) return rc;
+    }
     if (PP.n_jobs) {
         const int rc = launch_rectify_pair(ctx, PP, th4);
         if (rc != TI_OK) return rc;

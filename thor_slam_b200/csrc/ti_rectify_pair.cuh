@@ -36,4 +36,28 @@ struct Rect4Params {
 // th_index: index into P4_TILE_HEIGHTS
 int launch_rectify_pair(ti_ctx* ctx, Rect4Params& P, int th_index);
 
+// ---- 3-channel window remap (ti_rectify_c3.cu) --------------------------------------------------------
+struct Rect5JobDev {
+    const uint32_t* lut5;    // tiles x C3_TH x C3_LUT_ROW_WORDS
+    const TileBox2* boxes5;  // tiles
+    uint8_t* dst;
+    uint64_t dst_stride;
+    int dst_w, dst_h;
+    int rows_alloc;
+    uint32_t tile_begin;
+};
+
+struct Rect5Params {
+    TiTensorMap map[MAX_PAIR_JOBS];
+    Rect5JobDev job[MAX_PAIR_JOBS];
+    uint32_t tiles_per_set;
+    int n_jobs;
+    int n_batch;
+    int frames_per_unit;
+    int rows_alloc_max;
+    int stages;
+};
+
+int launch_rectify_c3(ti_ctx* ctx, Rect5Params& P);
+
 }  // namespace ti

@@ -5,9 +5,10 @@
 namespace ti {
 
 #ifdef TI_EMULATE
-int tma_encode_u8_3d(ti_ctx*, TiTensorMap* out, const void* base, int w, int h, int n, uint64_t pitch_y, uint64_t pitch_z,
-                     int box_x, int box_y) {
+int tma_encode_3d(ti_ctx*, TiTensorMap* out, const void* base, int elem_bytes, int w, int h, int n, uint64_t pitch_y,
+                  uint64_t pitch_z, int box_x, int box_y) {
     *out = TiTensorMap{};
+    out->elem = elem_bytes;
     out->base = static_cast<const uint8_t*>(base);
     out->dim[0] = w; out->dim[1] = h; out->dim[2] = n;
     out->stride[0] = 1; out->stride[1] = (int64_t)pitch_y; out->stride[2] = (int64_t)pitch_z;
@@ -33,22 +34,28 @@ static EncodeTiledFn encoder() {
     return fn;
 }
 
-int tma_encode_u8_3d(ti_ctx* ctx, TiTensorMap* out, const void* base, int w, int h, int n, uint64_t pitch_y, uint64_t pitch_z,
-                     int box_x, int box_y) {
+int tma_encode_3d(ti_ctx* ctx, TiTensorMap* out, const void* base, int elem_bytes, int w, int h, int n, uint64_t pitch_y,
+                  uint64_t pitch_z, int box_x, int box_y) {
     EncodeTiledFn fn = encoder();
     if (!fn) return fail(ctx, TI_ECUDA, "cuTensorMapEncodeTiled is not available from this driver");
-    if (((uintptr_t)base % 16) || (pitch_y % 16) || (pitch_z % 16) || (box_x % 16) || box_x > 256 || box_y > 256)
-        return fail(ctx, TI_EINVAL, "tensor map: base/pitches/box must be 16-byte multiples, box <= 256");
+    if ((elem_bytes != 1 && elem_bytes != 4) || ((uintptr_t)base % 16) || (pitch_y % 16) || (pitch_z % 16) ||
+        ((box_x * elem_bytes) % 16) || box_x > 256 || box_y > 256)
+        return fail(ctx, TI_EINVAL, "tensor map: base/pitches/box must be 16-byte multiples, box <= 256 elements");
     const cuuint64_t dims[3] = {(cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)std::max(n, 1)};
     const cuuint64_t strides[2] = {pitch_y, pitch_z ? pitch_z : pitch_y * (uint64_t)h};
     const cuuint32_t box[3] = {(cuuint32_t)box_x, (cuuint32_t)box_y, 1u};
     const cuuint32_t estr[3] = {1u, 1u, 1u};
-    const CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<void*>(base), dims, strides, box, estr,
+    const CUresult r = fn(out, elem_bytes == 4 ? CU_TENSOR_MAP_DATA_TYPE_UINT32 : CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<void*>(base), dims, strides, box, estr,
                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(ctx, TI_ECUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
     return TI_OK;
 }
 #endif
+
+int tma_encode_u8_3d(ti_ctx* ctx, TiTensorMap* out, const void* base, int w, int h, int n, uint64_t pitch_y, uint64_t pitch_z,
+                     int box_x, int box_y) {
+    return tma_encode_3d(ctx, out, base, 1, w, h, n, pitch_y, pitch_z, box_x, box_y);
+}
 
 }  // namespace ti

@@ -16,7 +16,8 @@ struct alignas(64) TiTensorMap {
     int32_t dim[3];     // elements (bytes) per dimension, x fastest
     int64_t stride[3];  // bytes; stride[0] == 1
     int32_t box[3];
-    char pad[128 - 8 - 12 - 24 - 12 - 8];
+    int32_t elem;       // bytes per element (1 or 4); dim / box / coordinates count elements
+    char pad[128 - 8 - 12 - 24 - 12 - 4 - 4];
 };
 static_assert(sizeof(TiTensorMap) == 128, "same size as CUtensorMap");
 #else
@@ -27,6 +28,9 @@ typedef CUtensorMap TiTensorMap;
 // boxes of box_x x box_y x 1; out-of-bounds elements read as zero.
 int tma_encode_u8_3d(ti_ctx* ctx, TiTensorMap* out, const void* base, int w, int h, int n, uint64_t pitch_y,
                      uint64_t pitch_z, int box_x, int box_y);
+// same with elements of `elem_bytes` (1 or 4): w, box_x and the x coordinate of a load count elements, pitches stay bytes
+int tma_encode_3d(ti_ctx* ctx, TiTensorMap* out, const void* base, int elem_bytes, int w, int h, int n, uint64_t pitch_y,
+                  uint64_t pitch_z, int box_x, int box_y);
 
 #if defined(TI_EMULATE)
 // ---- emulation -----------------------------------------------------------------------------------
@@ -63,11 +67,14 @@ __device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
 __device__ __forceinline__ void tma_load_3d(void* smem_dst, const TiTensorMap* map, int x, int y, int z, uint64_t*) {
     uint8_t* d = static_cast<uint8_t*>(smem_dst);
     ti_emu::check_align(smem_dst, 128);
+    const int es = map->elem;
     for (int by = 0; by < map->box[1]; ++by)
         for (int bx = 0; bx < map->box[0]; ++bx) {
             const int gx = x + bx, gy = y + by;
             const bool in = gx >= 0 && gx < map->dim[0] && gy >= 0 && gy < map->dim[1] && z >= 0 && z < map->dim[2];
-            d[by * map->box[0] + bx] = in ? map->base[(int64_t)z * map->stride[2] + (int64_t)gy * map->stride[1] + gx] : 0;
+            for (int e = 0; e < es; ++e)
+                d[((size_t)by * map->box[0] + bx) * es + e] =
+                    in ? map->base[(int64_t)z * map->stride[2] + (int64_t)gy * map->stride[1] + (int64_t)gx * es + e] : 0;
         }
 }
 __device__ __forceinline__ void bulk_load_1d(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t*) {

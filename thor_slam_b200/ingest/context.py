@@ -164,9 +164,10 @@ class IngestContext:
         """Which mono remap kernel slot ``camera`` runs under the current options (``ti_rectify_plan``)."""
         import ctypes
 
-        out = (ctypes.c_int32 * 4)()
+        out = (ctypes.c_int32 * 8)()
         self._check(self.lib.ti_rectify_plan(self._h, camera, out))
-        return {"variant": int(out[0]), "tile_h": int(out[1]), "rows": int(out[2]), "exceptions_per_warp": int(out[3])}
+        return {"variant": int(out[0]), "tile_h": int(out[1]), "rows": int(out[2]), "exceptions_per_warp": int(out[3]),
+                "colour_variant": int(out[4]), "colour_rows": int(out[5])}
 
     def get_valid_mask(self, camera: int, out: Any) -> Any:
         self._check(self.lib.ti_get_valid_mask(self._h, camera, self._ptr(out)))

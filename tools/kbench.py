@@ -104,6 +104,28 @@ def main() -> None:
         # plain device copy of the same bytes = what "1.0" looks like for this traffic
         report("torch copy_ (same bytes)", timeit(lambda: [o.copy_(f) for o, f in zip(outs, frames)], args.iters), 2 * px, px)
 
+    if not args.only or "colour" in args.only:
+        CW, CH, NB, NC = 1920, 1200, max(2, B // 2), 4  # the long-range cameras' colour stereo streams (config 4)
+        csrc = SyntheticCameraSource(SyntheticCameraConfig(name="lr0", resolution=(CW, CH), pixel_format="bgr8", pool=1, enable_rgbd=False))
+        cmaps = stereo_rectify_maps(csrc.get_intrinsics(), csrc.get_extrinsics(), (CW, CH))
+        for cam in range(NC):
+            ctx.upload_rectify_map(16 + cam, *cmaps[cam % 2], (CW, CH))
+        print("plan", ctx.rectify_plan(16), flush=True)
+        cin = [torch.randint(0, 256, (NB, CH, CW, 3), dtype=torch.uint8, device="cuda") for _ in range(NC)]
+        cout = [torch.empty_like(t) for t in cin]
+        gout = [torch.empty((NB, CH, CW), dtype=torch.uint8, device="cuda") for _ in range(NC)]
+        cspecs = [StreamSpec(F.KIND_RECTIFY, cin[i], cout[i], F.BGR8, F.RGB8, camera=16 + i) for i in range(NC)]
+        gspecs = [StreamSpec(F.KIND_RECTIFY, cin[i], gout[i], F.BGR8, F.MONO8, camera=16 + i) for i in range(NC)]
+        cpx = NC * NB * CW * CH
+        report("rectify bgr8->rgb8 1920x1200 (3-channel windows)", timeit(lambda: ctx.ingest(cspecs), args.iters), 6 * cpx, cpx)
+        report("rectify bgr8->mono8 1920x1200 (gray pass + v4)", timeit(lambda: ctx.ingest(gspecs), args.iters), 4 * cpx, cpx)
+        ctx.set_option(ctx.OPT_FORCE_GENERIC_RECTIFY, 1)
+        report("rectify bgr8->rgb8 generic tiled", timeit(lambda: ctx.ingest(cspecs), max(3, args.iters // 4)), 6 * cpx, cpx)
+        report("rectify bgr8->mono8 generic direct", timeit(lambda: ctx.ingest(gspecs), max(3, args.iters // 4)), 4 * cpx, cpx)
+        ctx.set_option(ctx.OPT_FORCE_GENERIC_RECTIFY, 0)
+        report("torch copy_ bgr (6 B/px)", timeit(lambda: [o.copy_(i) for o, i in zip(cout, cin)], args.iters), 6 * cpx, cpx)
+        del cin, cout, gout
+
     if not args.only or "bp" in args.only:
         intr = src.get_intrinsics()[0]
         m = body_T_camera(None, src.get_extrinsics()[0].to_4x4_matrix(), "rdf")
