@@ -638,27 +638,38 @@ static int launch_tiled(ti_ctx* ctx, RectParams& P, size_t smem_bytes) {
     return TI_OK;
 }
 
-// BGR8 -> MONO8 rectified on a slot that qualifies for a fast mono kernel runs as two fast passes: the exact OpenCV
-// gray conversion (convert_vec_kernel) into library scratch, then the mono remap on the gray frames - identical to
-// cv2.remap(cvtColor(BGR2GRAY)) by construction, and ~4x faster than converting every tap inside the generic kernel.
-static int gray_prepass(ti_ctx* ctx, std::vector<RectifyJob>& jobs, int n_batch) {
+// Two-pass paths.  BGR8 -> MONO8 rectified on a slot that qualifies for a fast mono kernel: the exact OpenCV gray
+// conversion (convert_vec_kernel) into library scratch, then the mono remap on the gray frames - identical to
+// cv2.remap(cvtColor(BGR2GRAY)) by construction.  NV12 -> RGB8 rectified: the exact NV12 -> BGR conversion into
+// scratch, then the 3-channel window remap (which swaps to RGB) - remap is per channel, so this equals
+// cv2.remap(cvtColor(YUV2RGB_NV12)).  Both are several times faster than converting every tap inside the generic kernel.
+static int convert_prepass(ti_ctx* ctx, std::vector<RectifyJob>& jobs, int n_batch) {
     std::vector<ConvertJob> conv;
     std::vector<size_t> offs;
     size_t need = 0;
     const int th4 = p4_th_index(ctx->tma_tile_h), thk = m3_th_index(ctx->tma_tile_h);
     for (auto& J : jobs) {
-        if (J.src_fmt != TI_FMT_BGR8 || J.dst_fmt != TI_FMT_MONO8 || ctx->force_generic_rectify || ctx->mono_variant < 3) continue;
-        if (J.camera < 0 || J.camera >= TI_MAX_CAMERAS) continue;
-        const CameraSlot& C = ctx->cams[J.camera];
-        if (!C.has_map || !(C.has_pair[th4] || C.has_tma_mono[thk]) || C.src_w % 16 != 0) continue;
-        if (!J.src || ((uintptr_t)J.src % 16) || (J.src_stride % 16)) continue;
-        const size_t frame = (size_t)C.src_w * C.src_h;  // multiple of 16
-        conv.push_back(ConvertJob{J.src, nullptr, J.src_stride, (uint64_t)frame, C.src_w, C.src_h, TI_FMT_BGR8, TI_FMT_MONO8});
+        if (ctx->force_generic_rectify || J.camera < 0 || J.camera >= TI_MAX_CAMERAS) continue;
+        CameraSlot& C = ctx->cams[J.camera];
+        if (!C.has_map || C.src_w % 16 != 0 || !J.src || ((uintptr_t)J.src % 16) || (J.src_stride % 16)) continue;
+        int mid_fmt = -1;
+        if (J.src_fmt == TI_FMT_BGR8 && J.dst_fmt == TI_FMT_MONO8 && ctx->mono_variant >= 3 && (C.has_pair[th4] || C.has_tma_mono[thk])) {
+            mid_fmt = TI_FMT_MONO8;
+        } else if (J.src_fmt == TI_FMT_NV12 && J.dst_fmt == TI_FMT_RGB8 && ctx->mono_variant == 4 && !((C.src_w | C.src_h) & 1)) {
+            if (!C.c3_tried) {
+                const int rc = build_c3_tables(ctx, C);
+                if (rc != TI_OK) return rc;
+            }
+            if (C.has_c3) mid_fmt = TI_FMT_BGR8;
+        }
+        if (mid_fmt < 0) continue;
+        const size_t frame = (size_t)frame_bytes(mid_fmt, C.src_w, C.src_h);  // multiple of 16 (src_w is)
+        conv.push_back(ConvertJob{J.src, nullptr, J.src_stride, (uint64_t)frame, C.src_w, C.src_h, J.src_fmt, mid_fmt});
         offs.push_back(need);
         need += frame * (size_t)n_batch;
         J.src = nullptr;  // patched below once the scratch base is known
         J.src_stride = frame;
-        J.src_fmt = TI_FMT_MONO8;
+        J.src_fmt = mid_fmt;
     }
     if (conv.empty()) return TI_OK;
     if (need > ctx->scratch_cap) {
@@ -683,7 +694,7 @@ int launch_rectify(ti_ctx* ctx, const RectifyJob* jobs_in, int n_jobs, int n_bat
         if (!jobs_in[i].src || !jobs_in[i].dst) return fail(ctx, TI_EINVAL, "rectify: null src/dst pointer");
     std::vector<RectifyJob> jobs(jobs_in, jobs_in + n_jobs);
     {
-        const int rc = gray_prepass(ctx, jobs, n_batch);
+        const int rc = convert_prepass(ctx, jobs, n_batch);
         if (rc != TI_OK) return rc;
     }
     RectParams P1{}, P3{};  // tiled launches for 1-channel and 3-channel sources
