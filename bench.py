@@ -309,14 +309,7 @@ def run_ours(args) -> None:
     ms_per_step = ms_max / args.steps
     value = world * B * args.steps / (ms_max * 1e-3)
 
-    # parity spot check inside the bench (rank 0, one frame of one stream) - the number is void otherwise
-    if rank == 0:
-        from oracle import rectify as orc
-
-        want = orc.remap_cv(pool_frames[3][1], maps[3][0], maps[3][1])
-        got = d_dst[3][1].cpu().numpy()
-        if not np.array_equal(got, want):
-            raise SystemExit("bench: GPU output differs from cv2.remap - refusing to report a number")
+    got_value_frame = d_dst[3][1].cpu().numpy() if rank == 0 else None  # checked against the oracle in the cpu_baseline leg
 
     # ---- end to end through the host-buffer API ("e2e") -----------------------------------------
     Be = min(B, args.e2e_batch)
@@ -338,11 +331,7 @@ def run_ours(args) -> None:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_value = world * Be * e2e_steps / float(te.item())
     launches_e2e = ctx.launch_count - launches_e2e0
-    if rank == 0:
-        from oracle import rectify as orc
-
-        if not np.array_equal(h_dst[5][0].numpy(), orc.remap_cv(pool_frames[5][0], maps[5][0], maps[5][1])):
-            raise SystemExit("bench: e2e output differs from cv2.remap - refusing to report a number")
+    got_e2e_frame = h_dst[5][0].numpy().copy() if rank == 0 else None
 
     extras: dict = {}
     if args.extras:
@@ -354,6 +343,13 @@ def run_ours(args) -> None:
         import cv2
 
         cv2.setNumThreads(os.cpu_count() or 1)
+        # the oracle runs only in this leg: it is the CPU baseline and, on the same frames, the checker of both GPU numbers
+        from oracle import rectify as orc
+
+        if not np.array_equal(got_value_frame, orc.remap_cv(pool_frames[3][1], maps[3][0], maps[3][1])):
+            raise SystemExit("bench: GPU output differs from cv2.remap - refusing to report a number")
+        if not np.array_equal(got_e2e_frame, orc.remap_cv(pool_frames[5][0], maps[5][0], maps[5][1])):
+            raise SystemExit("bench: e2e output differs from cv2.remap - refusing to report a number")
         cps, done, secs = time_cpu(pool_frames, maps, args.cpu_budget, 4096)
         cpu_baseline = {"value": cps, "unit": "frame-sets/s", "cores": cv2.getNumThreads(), "kind": "port",
                         "sample": f"{done} frame sets of 8 x 1280x800 mono8 in {secs:.1f} s, cv2.remap INTER_LINEAR (OpenCV {cv2.__version__})"}
