@@ -442,6 +442,35 @@ def gen_urdf() -> None:
     (HERE / "urdf.json").write_text(json.dumps(out, indent=1))
 
 
+def gen_pipeline_config() -> None:
+    """scripts/run_pipeline.py:85-163 - PipelineConfig.from_dict on the shipped YAML and on the schema's corner cases."""
+    import dataclasses
+
+    import yaml
+    from scripts import run_pipeline, run_slam
+
+    cases = {
+        "slam_config.yaml": yaml.safe_load((REF / "config" / "slam_config.yaml").read_text()),
+        "empty": {},
+        "deprecated_rgbd_camera_ip": {"cameras": [{"ip": "10.0.0.1"}, {"ip": "10.0.0.2", "stereo": False}], "rgbd_camera_ip": "10.0.0.2"},
+        "enable_rgbd_flags": {"cameras": [{"ip": "a", "enable_rgbd": True, "sensor_type": "mono"},
+                                          {"ip": "b", "resolution": [1920, 1200], "output_resolution": [640, 400]},
+                                          {"ip": "c", "enable_rgbd": True, "rgb_output_resolution": [1280, 720]}],
+                              "fps": 15, "rig_queue_size": 4, "urdf_path": "/tmp/x.urdf"},
+        "nvblox_not_a_list": {"cameras": [{"ip": "a"}], "nvblox_cameras": "a"},
+    }
+    out = {"camera_map_run_pipeline": run_pipeline.CAMERA_MAP, "camera_map_run_slam": run_slam.CAMERA_MAP, "cases": {}}
+    for name, data in cases.items():
+        cfg = run_pipeline.PipelineConfig.from_dict(data)
+        d = dataclasses.asdict(cfg)
+        d["urdf_is_default_brackets"] = d["urdf_path"].endswith("examples/assets/brackets.urdf")
+        if d["urdf_is_default_brackets"]:
+            d["urdf_path"] = "<default>"
+        d["num_cameras"] = cfg.calculate_num_cameras()
+        out["cases"][name] = {"input": data, "config": d}
+    (HERE / "pipeline_config.json").write_text(json.dumps(out, indent=1))
+
+
 def gen_cv_arith() -> None:
     from oracle import rectify
 
@@ -491,6 +520,7 @@ if __name__ == "__main__":
     gen_isaac_adapter()
     gen_rgbd_publisher()
     gen_urdf()
+    gen_pipeline_config()
     gen_cv_arith()
     for f in sorted(HERE.iterdir()):
         print(f"{f.name:28s} {f.stat().st_size:8d} B")

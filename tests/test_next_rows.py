@@ -81,3 +81,71 @@ def test_rectified_camera_info():
     assert li.d == [0.0] * 5 and li.k == np.asarray(p1)[:, :3].flatten().tolist()
     assert li.p[3] == 0.0 and ri.p[3] < 0  # ROS stereo convention: Tx = -fx * baseline on the right camera
     assert np.isclose(ri.p[3], -p2[0, 0] * 0.075, rtol=1e-3)
+
+
+# ---- (f) row 1: rig description (YAML schema) -> sources + URDF poses -> ingest rig ------------------------------
+def test_pipeline_config_matches_reference_from_dict():
+    """Every field and default of scripts/run_pipeline.py:85-163 on the shipped YAML and the schema's corner cases."""
+    import dataclasses
+
+    from thor_slam_b200.ingest.pipeline_config import CAMERA_MAP, PipelineConfig
+
+    g = json.loads((GOLDEN / "pipeline_config.json").read_text())
+    assert CAMERA_MAP == g["camera_map_run_pipeline"] == g["camera_map_run_slam"]
+    for name, case in g["cases"].items():
+        want = dict(case["config"])
+        default_urdf = want.pop("urdf_is_default_brackets")
+        num = want.pop("num_cameras")
+        cfg = PipelineConfig.from_dict(case["input"], default_urdf=__file__)  # any existing file plays the default URDF
+        got = json.loads(json.dumps(dataclasses.asdict(cfg)))  # tuples -> lists, like the golden file
+        if default_urdf:
+            assert got["urdf_path"] == __file__, name
+            got["urdf_path"] = "<default>"
+        assert got == want, name
+        assert cfg.calculate_num_cameras() == num, name
+
+
+def test_rig_description_to_ingested_frames_emulated(emu_backend, tmp_path):
+    """YAML + URDF -> IngestRig: poses come from the URDF (reference Euler order), frames come out rectified,
+    the cloud is in the FLU body frame of that pose."""
+    from oracle import backproject as ob
+    from oracle import conventions as conv
+    from oracle import rectify as orc
+    from thor_slam_b200.ingest.pipeline_config import PipelineConfig, build_ingest_rig
+
+    u = json.loads((GOLDEN / "urdf.json").read_text())
+    joints = "".join(
+        f'<joint name="{j["joint"]}" type="fixed"><parent link="base_link"/><child link="{j["link"]}"/>'
+        f'<origin xyz="{j["xyz"]}" rpy="{j["rpy"]}"/></joint>' for j in u["joints"].values())
+    urdf = tmp_path / "rig.urdf"
+    urdf.write_text(f'<robot name="r"><link name="base_link"/>{joints}</robot>')
+    yaml_path = tmp_path / "slam_config.yaml"
+    yaml_path.write_text(
+        "cameras:\n"
+        '  - ip: "192.168.2.21"\n    stereo: true\n    resolution: [640, 400]\n    output_resolution: [192, 96]\n    sensor_type: "MONO"\n'
+        '  - ip: "192.168.2.25"\n    stereo: true\n    resolution: [192, 96]\n    sensor_type: "MONO"\n    enable_rgbd: true\n'
+        "    rgb_output_resolution: [128, 64]\n"
+        f'urdf_path: "{urdf}"\nrig_queue_size: 3\nnvblox_cameras:\n  - "192.168.2.25"\n')
+    cfg = PipelineConfig.from_yaml(yaml_path)
+    assert cfg.calculate_num_cameras() == 4 and cfg.rig_queue_size == 3 and cfg.nvblox_cameras == ["192.168.2.25"]
+    rig = build_ingest_rig(cfg, context=emu_backend.ctx)
+    assert rig.queue_size == 3 and rig.get_source_names() == ["192.168.2.21", "192.168.2.25"]
+    for ip in rig.get_source_names():
+        assert np.allclose(rig.get_rig_extrinsics(ip).to_4x4_matrix(), np.array(u["matrices"][ip]), rtol=0, atol=1e-15)
+    with rig:
+        sync = rig.get_synchronized_frames(with_clouds=True)
+    for ip in rig.get_source_names():
+        src = rig.get_source(ip)
+        (il, ir), (el, er) = src.get_intrinsics(), src.get_extrinsics()
+        assert (il.width, il.height) == (192, 96)  # output_resolution wins over resolution for the SLAM streams
+        r1, _r2, p1, _p2 = orc.stereo_rectify_cv(il.matrix, il.coeffs, ir.matrix, ir.coeffs, (192, 96), el.to_4x4_matrix(), er.to_4x4_matrix())
+        mapx, mapy = orc.undistort_rectify_map_cv(il.matrix, il.coeffs, r1, p1, (192, 96))
+        left = np.asarray(sync.frame_sets[ip].frames[0].image)
+        assert np.array_equal(left, orc.remap_cv(src._pool[0][0], mapx, mapy))
+    assert set(sync.clouds) == {"192.168.2.25"}  # only the nvblox camera delivers RGB-D
+    src = rig.get_source("192.168.2.25")
+    _ri, di = src.get_rgbd_intrinsics()
+    m = conv.body_T_camera(np.array(u["matrices"]["192.168.2.25"]), src.get_rgbd_extrinsics()[1].to_4x4_matrix(), "rdf")
+    pts, _mask, cnt = ob.backproject(src._rgbd_pool[0][1], di.matrix, m)
+    c = sync.clouds["192.168.2.25"]
+    assert ob.points_close(np.asarray(c["points"]), pts)[0] and int(c["count"]) == cnt
