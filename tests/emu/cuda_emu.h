@@ -11,6 +11,7 @@
 
 #include <atomic>
 #include <barrier>
+#include <chrono>
 #include <cmath>
 #include <cstdint>
 #include <cstdio>
@@ -166,6 +167,7 @@ inline uint32_t __byte_perm(uint32_t x, uint32_t y, uint32_t s) {
 }
 inline int __popc(uint32_t v) { return __builtin_popcount(v); }
 inline uint32_t __ballot_sync(uint32_t, int pred) { return ti_emu::ballot(pred); }
+inline int __any_sync(uint32_t, int pred) { return ti_emu::ballot(pred) != 0u; }
 inline uint32_t __reduce_add_sync(uint32_t, uint32_t v) { return ti_emu::reduce_add(v); }
 inline uint32_t __reduce_or_sync(uint32_t, uint32_t v) { return ti_emu::reduce_or(v); }
 template <typename T>

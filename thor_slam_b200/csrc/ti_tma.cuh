@@ -56,7 +56,18 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) { emu_arrive(bar); }
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t) { emu_arrive(bar); }  // copies already done
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     EmuMbar* m = reinterpret_cast<EmuMbar*>(bar);
-    while ((__atomic_load_n(&m->completed, __ATOMIC_ACQUIRE) & 1u) == parity) std::this_thread::yield();
+    uint64_t spins = 0;
+    while ((__atomic_load_n(&m->completed, __ATOMIC_ACQUIRE) & 1u) == parity) {
+        std::this_thread::yield();
+        if (++spins == (1ull << 24)) {  // a kernel that deadlocks must not hang the test run: say where and stop
+            fprintf(stderr, "EMU: mbarrier wait stuck: block %u thread %u barrier at smem+%ld parity %u completed %u pending %d\n",
+                    ti_emu::tls.bid.x, ti_emu::tls.tid.x, (long)(reinterpret_cast<uint8_t*>(bar) - ti_emu::tls.dyn_smem), parity,
+                    m->completed, (int)m->pending);
+            fflush(stderr);
+            std::this_thread::sleep_for(std::chrono::seconds(2));
+            abort();
+        }
+    }
 }
 __device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity) { mbar_wait(bar, parity); }
 __device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity, unsigned) { mbar_wait(bar, parity); }
