@@ -283,18 +283,14 @@ int launch_rectify_pair(ti_ctx* ctx, Rect4Params& P, int th_index) {
     int per_sm = resident_ctas(kern, P4_THREADS, smem, 3);
     if (ctx->ctas_per_sm > 0) per_sm = ctx->ctas_per_sm;
     const uint64_t grid_max = (uint64_t)ctx->sm_count * per_sm;
-    // frames per unit: a unit costs one LUT expansion (about one frame of work) plus its frames; CTAs walk the
-    // unit list in rounds of `grid_max`, so pick the even split of the batch whose rounds x (frames + 1) is least
+    // frames per unit: every unit costs one LUT fetch + expansion (measured: about one frame of work) and the CTAs of
+    // an SM share its throughput, so what counts is few units - as long as every CTA still gets about four of them
     int fpu = ctx->frames_per_unit4;
     if (fpu <= 0) {
-        double best = 1e30;
-        for (int chunks = (P.n_batch + 31) / 32; chunks <= std::max(1, (P.n_batch + 7) / 8); ++chunks) {
-            const int c = (P.n_batch + chunks - 1) / chunks;
-            const uint64_t units = (uint64_t)P.tiles_per_set * chunks;
-            const uint64_t rounds = (units + grid_max - 1) / grid_max;
-            const double cost = (double)rounds * (c + 1.0);
-            if (cost < best) { best = cost; fpu = c; }
-        }
+        const uint64_t want_units = 4 * grid_max;
+        const int chunks = (int)std::max<uint64_t>(1, std::min<uint64_t>((want_units + P.tiles_per_set - 1) / P.tiles_per_set,
+                                                                        (uint64_t)std::max(1, P.n_batch / 8)));
+        fpu = (P.n_batch + chunks - 1) / chunks;
     }
     P.frames_per_unit = std::max(1, std::min(P.n_batch, fpu));
     const uint64_t total = (uint64_t)P.tiles_per_set * ((P.n_batch + P.frames_per_unit - 1) / P.frames_per_unit);
