@@ -77,7 +77,7 @@ __device__ __forceinline__ void p4_blend(const Taps& T, const uint4& w, uint32_t
 // WHOLE: every pixel of the warp's rows exists and rows start on even addresses (16-bit stores).
 // PREFETCH: software pipeline, the windows of row q+1 are in flight while row q is blended and stored (8 more registers).
 // fixes (warp-uniform): some lane has an exception entry; i_fix: this lane has one, at shared address my_exc =
-// {window word, Wtop, Wbot, row << 16 | column}.  Its window is fetched ahead of the last row's blend so that the
+// {window word, Wtop, Wbot, row * dst_w + column}.  Its window is fetched ahead of the last row's blend so that the
 // latency of the dependent loads hides behind that row; its store follows the row loop's stores (__syncwarp).
 template <int RPW, bool WHOLE, bool PREFETCH>
 __device__ __forceinline__ void p4_rows(const uint4 (&w0)[RPW], const uint4 (&w1)[RPW], const uint2 (&mw)[RPW], p4_addr_t base,
@@ -118,7 +118,7 @@ __device__ __forceinline__ void p4_rows(const uint4 (&w0)[RPW], const uint4 (&w1
         if (i_fix) {
             const uint32_t xt = p4_prmt(X.t0, X.t1, fe.x), xb = p4_prmt(X.b0, X.b1, fe.x);
             const uint32_t r = __dp2a_lo(fe.z, xb, __dp2a_lo(fe.y, xt, 32768u));
-            st_stream_b8(warp_dst + (size_t)(fe.w >> 16) * dst_w + (fe.w & 0xFFFFu), r >> 16);
+            st_stream_b8(warp_dst + fe.w, r >> 16);
         }
     }
 }
@@ -398,7 +398,7 @@ int build_pair_tables(ti_ctx* ctx, CameraSlot& C, const std::vector<uint32_t>& l
                                 m = (off << 16) | sa | ((sa + 1) << 4) | ((uint32_t)sb_rel << 8) | ((uint32_t)(sb_rel + 1) << 12);
                             } else {
                                 // pixel b gets an entry of the warp's exception list: its own window (bytes b.left, b.right
-                                // selected into bytes 0, 1), its weight words, where it goes (row of the warp << 16 | tile column)
+                                // selected into bytes 0, 1), its weight words, where it goes (byte offset from the warp's first row in the tile)
                                 if (ex.size() / 4 >= (size_t)P4_MAX_EXC) { ok = false; break; }
                                 const int wordb = (b.x0 - B.c0) & ~3;
                                 const uint32_t offb = (uint32_t)((b.y0 - B.y0) * P4_PITCH + wordb);
@@ -409,7 +409,7 @@ int build_pair_tables(ti_ctx* ctx, CameraSlot& C, const std::vector<uint32_t>& l
                                 ex.push_back((offb << 16) | sb | ((sb + 1) << 4) | (sb << 8) | ((sb + 1) << 12));
                                 ex.push_back(wt);
                                 ex.push_back(wb);
-                                ex.push_back(((uint32_t)(row % RPW) << 16) | (uint32_t)(p * 64 + 2 * lane + 1));
+                                ex.push_back((uint32_t)(row % RPW) * (uint32_t)dst_w + (uint32_t)(p * 64 + 2 * lane + 1));
                             }
                         }
                 }
