@@ -48,12 +48,12 @@ __device__ __forceinline__ void p4_wait(p4_addr_t bar, uint32_t parity) {
         "{\n"
         ".reg .pred p;\n"
         "WAIT_%=:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"
         "@p bra DONE_%=;\n"
         "bra WAIT_%=;\n"
         "DONE_%=:\n"
         "}\n" ::"r"(bar),
-        "r"(parity)
+        "r"(parity), "r"(20000u)  // suspend-time hint (ns): the warp sleeps until the phase completes instead of re-probing
         : "memory");
 }
 __device__ __forceinline__ void p4_arrive(p4_addr_t bar) {
