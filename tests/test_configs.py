@@ -253,3 +253,40 @@ def test_rotated_maps_gpu(gpu_backend):
     for slot, deg, variant in ((14, 20.0, None), (15, 1.5, 4), (16, 3.0, None)):
         mx, my = _rotated_maps(W, H, deg)
         cases.check_rectify(gpu_backend, slot, mx, my, "mono8", "mono8", W, H, n=2, expect_variant=variant)
+
+
+# ---- randomised maps: scale, shear, roll, barrel distortion, offsets that push the source box over every border --------
+def _random_map(rng: np.random.Generator, w: int, h: int):
+    yy, xx = np.mgrid[0:h, 0:w].astype(np.float64)
+    cx, cy = w / 2 + rng.uniform(-20, 20), h / 2 + rng.uniform(-20, 20)
+    s = rng.uniform(0.8, 1.25)
+    roll = np.deg2rad(rng.uniform(-4, 4))
+    k1 = rng.uniform(-0.25, 0.25)
+    x, y = (xx - cx) / w, (yy - cy) / w
+    r2 = x * x + y * y
+    f = 1 + k1 * r2
+    xd, yd = x * f, y * f
+    c, sn = np.cos(roll), np.sin(roll)
+    mx = (xd * c - yd * sn) * w * s + cx + rng.uniform(-15, 15) + rng.uniform(-0.05, 0.05) * yy
+    my = (xd * sn + yd * c) * w * s * rng.uniform(0.9, 1.1) + cy + rng.uniform(-15, 15)
+    return mx.astype(np.float32), my.astype(np.float32)
+
+
+def _random_maps_case(be, n_maps: int, w: int, h: int, seed: int) -> None:
+    rng = np.random.default_rng(seed)
+    ran_pair = 0
+    for i in range(n_maps):
+        mx, my = _random_map(rng, w, h)
+        cases.check_rectify(be, 18, mx, my, "mono8", "mono8", w, h, n=2, seed=seed + i)
+        ran_pair += be.ctx.rectify_plan(18)["variant"] == 4
+    assert ran_pair >= n_maps // 2, "most of these maps are meant to qualify for the pair-window kernel"
+
+
+def test_random_maps_emulated(emu_backend):
+    _random_maps_case(emu_backend, 3, 256, 64, seed=77)
+
+
+@pytest.mark.gpu
+def test_random_maps_gpu(gpu_backend):
+    _random_maps_case(gpu_backend, 12, 640, 416, seed=78)
+    cases.check_rectify(gpu_backend, 18, *_random_map(np.random.default_rng(5), 1920, 1200), "bgr8", "rgb8", 1920, 1200, n=1)
