@@ -165,6 +165,19 @@ int ti_backproject(ti_ctx* ctx, int camera, const uint16_t* depth, float* xyz, u
                    uint32_t* count, int n_batch, uint64_t depth_frame_stride,
                    uint64_t xyz_frame_stride, uint64_t mask_frame_stride);
 
+/* Depth -> RGB registration constants of slot `camera` (thor_slam/camera/drivers/luxonis.py:1018-1091: depth and
+ * RGB intrinsics of get_rgbd_intrinsics(), rgb_T_depth = inv(rgb extrinsics) * depth extrinsics from
+ * get_rgbd_extrinsics()).  k_* = {fx, fy, cx, cy}; rgb_T_depth: row-major 3x4, metres.  float64 in, rounded once. */
+int ti_upload_registration(ti_ctx* ctx, int camera, int depth_w, int depth_h, const double k_depth[4], int rgb_w,
+                           int rgb_h, const double k_rgb[4], const double rgb_T_depth[12]);
+
+/* One RGB8 colour per depth pixel: back-project with the depth K, move into the RGB camera, project with the RGB K,
+ * take the nearest RGB pixel (round-half-even); (0,0,0) where depth is 0, the point is behind the RGB camera or falls
+ * outside the image.  depth: u16 HxW; rgb: RGB8 of the registered size; colour: u8 HxWx3 (depth size).  Strides in
+ * bytes, 0 = tightly packed.  The lookup nvblox does per voxel (scripts/run_pipeline.py:218-256) done once per pixel. */
+int ti_register_colour(ti_ctx* ctx, int camera, const uint16_t* depth, const uint8_t* rgb, uint8_t* colour, int n_batch,
+                       uint64_t depth_frame_stride, uint64_t rgb_frame_stride, uint64_t colour_frame_stride);
+
 /* Whole frame-set batch in at most one launch per kind: every stream x every frame.
  * This is the call behind CameraRig.get_synchronized_frames() (thor_slam/camera/rig.py:358-415)
  * in the drop-in rig.  streams: HOST array, DEVICE image pointers inside. */

@@ -36,6 +36,41 @@ def backproject(depth_mm: np.ndarray, k: np.ndarray, body_T_cam: np.ndarray) -> 
     return pts, valid.astype(np.uint8), int(valid.sum())
 
 
+def register_colour(depth_mm: np.ndarray, k_depth: np.ndarray, rgb_T_depth: np.ndarray, k_rgb: np.ndarray, rgb: np.ndarray) -> np.ndarray:
+    """One colour per depth pixel (HxWx3 u8): the per-pixel form of the depth / RGB association nvblox makes from the two
+    images the reference publishes (``scripts/run_pipeline.py:218-256``) with the extrinsics of
+    ``drivers/luxonis.py:1068-1091``.  Pinhole on both images' ``K``, nearest RGB pixel (round-half-even), (0,0,0) where
+    depth is 0, the point is behind the RGB camera or outside the image.
+
+    Restated in float32 with one rounding per multiply / add / divide, in the order of
+    ``thor_slam_b200/csrc/ti_register.cu`` - the constants are formed in float64 and rounded once, exactly as
+    ``ti_upload_registration`` does - so the selected pixels are bit-identical, not merely close."""
+    f32 = np.float32
+    h, w = depth_mm.shape
+    rh, rw = rgb.shape[:2]
+    kd, kr = np.asarray(k_depth, np.float64), np.asarray(k_rgb, np.float64)
+    m = np.asarray(rgb_T_depth, np.float64)
+    a = np.stack([m[:3, 0] / kd[0, 0], m[:3, 1] / kd[1, 1], m[:3, 2]], axis=1).astype(f32)  # rows: x, y, z of the RGB frame
+    t = m[:3, 3].astype(f32)
+    cx, cy = f32(kd[0, 2]), f32(kd[1, 2])
+    rfx, rfy, rcx, rcy = f32(kr[0, 0]), f32(kr[1, 1]), f32(kr[0, 2]), f32(kr[1, 2])
+    fu = np.arange(w, dtype=f32)[None, :] - cx
+    fv = np.arange(h, dtype=f32)[:, None] - cy
+    z = depth_mm.astype(f32) * f32(0.001)
+    with np.errstate(all="ignore"):
+        p = [((a[i, 0] * fu + a[i, 1] * fv) + a[i, 2]) * z + t[i] for i in range(3)]
+        ok = (depth_mm > 0) & (p[2] > 0)
+        ur = (p[0] / p[2]) * rfx + rcx
+        vr = (p[1] / p[2]) * rfy + rcy
+        ok &= (ur > -1) & (ur < f32(rw)) & (vr > -1) & (vr < f32(rh))
+        iu = np.rint(np.where(ok, ur, 0)).astype(np.int64)
+        iv = np.rint(np.where(ok, vr, 0)).astype(np.int64)
+    ok &= (iu >= 0) & (iu < rw) & (iv >= 0) & (iv < rh)
+    out = np.zeros((h, w, 3), np.uint8)
+    out[ok] = rgb[iv[ok], iu[ok]]
+    return out
+
+
 def depth_stats(depth_mm: np.ndarray) -> dict:
     valid = depth_mm[depth_mm > 0]
     if valid.size == 0:

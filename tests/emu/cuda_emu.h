@@ -198,6 +198,10 @@ inline uint32_t __dp2a_lo(uint32_t a, uint32_t b, uint32_t c) { return c + (a & 
 inline uint32_t __dp2a_hi(uint32_t a, uint32_t b, uint32_t c) { return c + (a & 0xFFFF) * ((b >> 16) & 0xFF) + (a >> 16) * ((b >> 24) & 0xFF); }
 inline float __fmaf_rn(float a, float b, float c) { return std::fmaf(a, b, c); }
 inline float __fmul_rn(float a, float b) { return a * b; }
+inline float __fadd_rn(float a, float b) { return a + b; }
+inline float __fsub_rn(float a, float b) { return a - b; }
+inline float __fdiv_rn(float a, float b) { return a / b; }
+inline int __float2int_rn(float a) { return (int)std::nearbyintf(a); }
 inline float __uint2float_rn(uint32_t v) { return (float)v; }
 inline float __int2float_rn(int v) { return (float)v; }
 inline uint32_t __funnelshift_r(uint32_t lo, uint32_t hi, uint32_t s) { return (uint32_t)((((uint64_t)hi << 32) | lo) >> (s & 31)); }

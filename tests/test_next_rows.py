@@ -149,3 +149,49 @@ def test_rig_description_to_ingested_frames_emulated(emu_backend, tmp_path):
     pts, _mask, cnt = ob.backproject(src._rgbd_pool[0][1], di.matrix, m)
     c = sync.clouds["192.168.2.25"]
     assert ob.points_close(np.asarray(c["points"]), pts)[0] and int(c["count"]) == cnt
+
+
+# ---- (f) row 3: depth -> RGB registration (one colour per depth pixel) -----------------------------------------------
+def _registration_case(be, dw: int, dh: int, rw: int, rh: int, n: int = 2, seed: int = 21) -> None:
+    from oracle import backproject as ob
+    from thor_slam_b200.camera.synthetic import make_depth, make_image
+
+    rng = np.random.default_rng(seed)
+    src = SyntheticCameraSource(SyntheticCameraConfig(name="oak0", enable_rgbd=True, rgb_resolution=(rw, rh), depth_resolution=(dw, dh),
+                                                      resolution=(dw, dh), pool=1, seed=seed))
+    ri, di = src.get_rgbd_intrinsics()
+    re, de = src.get_rgbd_extrinsics()  # both -> CAM_A (thor_slam/camera/drivers/luxonis.py:1068-1091)
+    rgb_T_depth = np.linalg.inv(re.to_4x4_matrix()) @ de.to_4x4_matrix()
+    be.ctx.upload_registration(50, di.matrix, (dw, dh), ri.matrix, (rw, rh), rgb_T_depth)
+    depth = np.stack([make_depth(rng, dw, dh) for _ in range(n)])
+    depth[0, :2, :] = 1  # 1 mm: far outside the RGB frustum or right at the camera - must not crash, colour (0,0,0) or a border pixel
+    rgb = np.stack([make_image(rng, "bgr8", rw, rh)[..., ::-1].copy() for _ in range(n)])
+    colour = be.zeros((n, dh, dw, 3), np.uint8)
+    be.ctx.register_colour(50, be.dev(depth), be.dev(rgb), colour)
+    got = be.host(colour)
+    for i in range(n):
+        want = ob.register_colour(depth[i], di.matrix, rgb_T_depth, ri.matrix, rgb[i])
+        assert np.array_equal(got[i], want), f"frame {i}: {(got[i] != want).any(axis=-1).sum()} pixels differ"
+        assert not got[i][depth[i] == 0].any(), "no depth, no colour"
+    assert (got.reshape(-1, 3).any(axis=1)).mean() > 0.5, "most valid points of this rig land inside the RGB image"
+    # identical sensors (same K, same size, identity extrinsics): every valid pixel takes the colour at its own position
+    be.ctx.upload_registration(51, di.matrix, (dw, dh), di.matrix, (dw, dh), np.eye(4))
+    same = np.ascontiguousarray(rgb[:, :dh, :dw]) if (rh >= dh and rw >= dw) else make_image(rng, "bgr8", dw, dh)[None].repeat(n, 0)
+    colour2 = be.zeros((n, dh, dw, 3), np.uint8)
+    be.ctx.register_colour(51, be.dev(depth), be.dev(same), colour2)
+    got2 = be.host(colour2)
+    valid = depth > 0
+    assert np.array_equal(got2[valid], same[valid]) and not got2[~valid].any()
+
+
+def test_depth_rgb_registration_emulated(emu_backend):
+    _registration_case(emu_backend, 96, 64, 128, 72)
+
+
+@pytest.mark.gpu
+def test_depth_rgb_registration_gpu(gpu_backend):
+    _registration_case(gpu_backend, 1280, 800, 1920, 1080)
+    _registration_case(gpu_backend, 640, 400, 640, 400, n=3, seed=22)
+    with pytest.raises(RuntimeError):
+        gpu_backend.ctx.register_colour(52, gpu_backend.zeros((1, 8, 8), np.uint16), gpu_backend.zeros((1, 8, 8, 3), np.uint8),
+                                        gpu_backend.zeros((1, 8, 8, 3), np.uint8))  # slot never uploaded

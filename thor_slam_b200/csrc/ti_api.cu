@@ -382,6 +382,37 @@ int ti_rectify_plan(ti_ctx* ctx, int camera, int32_t out[8]) {
     return TI_OK;
 }
 
+int ti_upload_registration(ti_ctx* ctx, int camera, int depth_w, int depth_h, const double k_depth[4], int rgb_w, int rgb_h,
+                           const double k_rgb[4], const double rgb_T_depth[12]) {
+    if (!ctx) return TI_EINVAL;
+    if (camera < 0 || camera >= TI_MAX_CAMERAS) return fail(ctx, TI_EINVAL, "camera slot %d out of range", camera);
+    if (!k_depth || !k_rgb || !rgb_T_depth || depth_w <= 0 || depth_h <= 0 || rgb_w <= 0 || rgb_h <= 0)
+        return fail(ctx, TI_EINVAL, "ti_upload_registration: bad argument");
+    if (k_depth[0] == 0.0 || k_depth[1] == 0.0) return fail(ctx, TI_EINVAL, "ti_upload_registration: zero focal length");
+    CameraSlot& C = ctx->cams[camera];
+    for (int i = 0; i < 3; ++i) {
+        C.reg_a[3 * i + 0] = (float)(rgb_T_depth[4 * i + 0] / k_depth[0]);
+        C.reg_a[3 * i + 1] = (float)(rgb_T_depth[4 * i + 1] / k_depth[1]);
+        C.reg_a[3 * i + 2] = (float)rgb_T_depth[4 * i + 2];
+        C.reg_t[i] = (float)rgb_T_depth[4 * i + 3];
+    }
+    C.reg_k[0] = (float)k_depth[2]; C.reg_k[1] = (float)k_depth[3];
+    C.reg_k[2] = (float)k_rgb[0]; C.reg_k[3] = (float)k_rgb[1]; C.reg_k[4] = (float)k_rgb[2]; C.reg_k[5] = (float)k_rgb[3];
+    C.reg_dw = depth_w; C.reg_dh = depth_h; C.reg_rw = rgb_w; C.reg_rh = rgb_h;
+    C.has_reg = true;
+    return TI_OK;
+}
+
+int ti_register_colour(ti_ctx* ctx, int camera, const uint16_t* depth, const uint8_t* rgb, uint8_t* colour, int n_batch,
+                       uint64_t depth_frame_stride, uint64_t rgb_frame_stride, uint64_t colour_frame_stride) {
+    if (!ctx) return TI_EINVAL;
+    if (camera < 0 || camera >= TI_MAX_CAMERAS || !ctx->cams[camera].has_reg)
+        return fail(ctx, TI_ESTATE, "ti_register_colour: camera slot %d has no registration (call ti_upload_registration)", camera);
+    if (n_batch < 0 || (n_batch > 0 && (!depth || !rgb || !colour))) return fail(ctx, TI_EINVAL, "ti_register_colour: bad argument");
+    TI_CUDA(ctx, cudaSetDevice(ctx->device));
+    return launch_register_colour(ctx, camera, depth, rgb, colour, n_batch, depth_frame_stride, rgb_frame_stride, colour_frame_stride);
+}
+
 int ti_get_valid_mask(ti_ctx* ctx, int camera, uint8_t* dst) {
     if (!ctx) return TI_EINVAL;
     if (camera < 0 || camera >= TI_MAX_CAMERAS || !ctx->cams[camera].has_map)

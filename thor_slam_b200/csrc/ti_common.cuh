@@ -145,6 +145,12 @@ struct CameraSlot {
     TileBox* d_boxes = nullptr;    // tiles_y * tiles_x
     uint8_t* d_valid = nullptr;    // dst_h * dst_w
     size_t tile_smem[2] = {0, 0};  // largest staged box in bytes for 1- and 3-channel sources
+    // depth -> RGB registration (ti_register.cu)
+    bool has_reg = false;
+    int reg_dw = 0, reg_dh = 0, reg_rw = 0, reg_rh = 0;
+    float reg_a[9];  // R_rgb<-depth * diag(1/fx_d, 1/fy_d, 1), row-major
+    float reg_t[3];
+    float reg_k[6];  // cx_d, cy_d, fx_r, fy_r, cx_r, cy_r
     // projection
     bool has_proj = false;
     int proj_w = 0, proj_h = 0;
@@ -286,6 +292,8 @@ struct BackprojectJob {
     int camera;
 };
 int launch_backproject(ti_ctx* ctx, const BackprojectJob* jobs, int n_jobs, int n_batch);
+int launch_register_colour(ti_ctx* ctx, int camera, const uint16_t* depth, const uint8_t* rgb, uint8_t* colour, int n_batch,
+                           uint64_t depth_stride, uint64_t rgb_stride, uint64_t colour_stride);
 
 #if defined(TI_EMULATE)
 __device__ __forceinline__ uint4 ld_stream_u4(const void* p) { return *reinterpret_cast<const uint4*>(ti_emu::check_align(p, 16)); }

@@ -1,0 +1,86 @@
+// Depth -> RGB registration: one colour per depth pixel.
+//
+// The reference hands nvblox a 16UC1 depth image and an rgb8 image that come from different sensors unless
+// depth_align_to_rgb is set (thor_slam/camera/drivers/luxonis.py:1018-1051); get_rgbd_extrinsics() gives
+// depth (CAM_B) -> RGB (CAM_A) (luxonis.py:1068-1091).  This kernel does the lookup nvblox would do per voxel,
+// once per depth pixel:
+//
+//     ray = A * [u - cx_d, v - cy_d, 1]        A = R_rgb<-depth * diag(1/fx_d, 1/fy_d, 1)   (float64 on the host, rounded once)
+//     p   = z * ray + t                         z = d * 0.001
+//     (ur, vr) = (fx_r * p.x / p.z + cx_r, fy_r * p.y / p.z + cy_r),  pinhole on the RGB image's K (no distortion, as nvblox)
+//     colour = rgb[rint(vr)][rint(ur)]          nearest pixel, round-half-even; (0,0,0) when d == 0, p.z <= 0 or outside
+//
+// Every float operation is a separately rounded IEEE fp32 multiply / add / divide (no FMA contraction), in a fixed order,
+// so a float32 numpy restatement (oracle/backproject.py:register_colour) selects bit-identical pixels.
+// Streaming kernel: 2 B/px depth in, 3 B/px colour out, RGB gathers are spatially coherent (L1/L2 hits).
+#include "ti_common.cuh"
+
+namespace ti {
+
+constexpr int RG_THREADS = 256;
+
+struct RegJobDev {
+    const uint16_t* depth;
+    const uint8_t* rgb;
+    uint8_t* colour;
+    uint64_t depth_stride, rgb_stride, colour_stride;
+    float a[9], t[3];
+    float cx, cy, rfx, rfy, rcx, rcy;
+    int dw, dh, rw, rh;
+};
+
+__device__ __forceinline__ uint32_t register_pixel(const RegJobDev& J, const uint8_t* rgb, int u, int v, uint32_t d) {
+    const float fu = __fsub_rn((float)u, J.cx), fv = __fsub_rn((float)v, J.cy);
+    const float z = __fmul_rn((float)d, 0.001f);
+    float p[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        const float r = __fadd_rn(__fadd_rn(__fmul_rn(J.a[3 * i], fu), __fmul_rn(J.a[3 * i + 1], fv)), J.a[3 * i + 2]);
+        p[i] = __fadd_rn(__fmul_rn(r, z), J.t[i]);
+    }
+    if (d == 0 || !(p[2] > 0.f)) return 0u;
+    const float ur = __fadd_rn(__fmul_rn(__fdiv_rn(p[0], p[2]), J.rfx), J.rcx);
+    const float vr = __fadd_rn(__fmul_rn(__fdiv_rn(p[1], p[2]), J.rfy), J.rcy);
+    if (!(ur > -1.f && ur < (float)J.rw && vr > -1.f && vr < (float)J.rh)) return 0u;  // also rejects NaN
+    const int iu = __float2int_rn(ur), iv = __float2int_rn(vr);
+    if (iu < 0 || iu >= J.rw || iv < 0 || iv >= J.rh) return 0u;
+    const uint8_t* s = rgb + ((size_t)iv * J.rw + iu) * 3;
+    return (uint32_t)s[0] | ((uint32_t)s[1] << 8) | ((uint32_t)s[2] << 16);
+}
+
+__global__ void __launch_bounds__(RG_THREADS) register_colour_kernel(const RegJobDev J, int n_batch) {
+    const uint64_t npx = (uint64_t)J.dw * J.dh;
+    const uint64_t total = npx * n_batch;
+    for (uint64_t i = (uint64_t)blockIdx.x * RG_THREADS + threadIdx.x; i < total; i += (uint64_t)gridDim.x * RG_THREADS) {
+        const uint64_t b = i / npx;
+        const uint32_t px = (uint32_t)(i - b * npx);
+        const int v = (int)(px / (uint32_t)J.dw), u = (int)(px - (uint32_t)v * J.dw);
+        const uint16_t* depth = reinterpret_cast<const uint16_t*>(reinterpret_cast<const uint8_t*>(J.depth) + b * J.depth_stride);
+        const uint32_t c = register_pixel(J, J.rgb + b * J.rgb_stride, u, v, depth[px]);
+        uint8_t* o = J.colour + b * J.colour_stride + (size_t)px * 3;
+        o[0] = (uint8_t)c; o[1] = (uint8_t)(c >> 8); o[2] = (uint8_t)(c >> 16);
+    }
+}
+
+int launch_register_colour(ti_ctx* ctx, int camera, const uint16_t* depth, const uint8_t* rgb, uint8_t* colour, int n_batch,
+                           uint64_t depth_stride, uint64_t rgb_stride, uint64_t colour_stride) {
+    if (n_batch <= 0) return TI_OK;
+    const CameraSlot& C = ctx->cams[camera];
+    RegJobDev J{};
+    J.depth = depth; J.rgb = rgb; J.colour = colour;
+    J.depth_stride = depth_stride ? depth_stride : (uint64_t)C.reg_dw * C.reg_dh * 2;
+    J.rgb_stride = rgb_stride ? rgb_stride : (uint64_t)C.reg_rw * C.reg_rh * 3;
+    J.colour_stride = colour_stride ? colour_stride : (uint64_t)C.reg_dw * C.reg_dh * 3;
+    if (J.depth_stride % 2) return fail(ctx, TI_EINVAL, "register_colour: depth frame stride must be even");
+    for (int i = 0; i < 9; ++i) J.a[i] = C.reg_a[i];
+    for (int i = 0; i < 3; ++i) J.t[i] = C.reg_t[i];
+    J.cx = C.reg_k[0]; J.cy = C.reg_k[1]; J.rfx = C.reg_k[2]; J.rfy = C.reg_k[3]; J.rcx = C.reg_k[4]; J.rcy = C.reg_k[5];
+    J.dw = C.reg_dw; J.dh = C.reg_dh; J.rw = C.reg_rw; J.rh = C.reg_rh;
+    const uint64_t total = (uint64_t)J.dw * J.dh * n_batch;
+    const int grid = (int)std::min<uint64_t>((total + RG_THREADS - 1) / RG_THREADS, (uint64_t)ctx->sm_count * 16);
+    TI_LAUNCH(register_colour_kernel, grid, RG_THREADS, 0, ctx->stream, J, n_batch);
+    TI_CHECK_LAUNCH(ctx);
+    return TI_OK;
+}
+
+}  // namespace ti

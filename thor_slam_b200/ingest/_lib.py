@@ -52,6 +52,9 @@ SIGNATURES: dict[str, tuple] = {
     "ti_upload_rectify_map": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "ti_upload_projection": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "ti_rectify_plan": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_int32)]),
+    "ti_upload_registration": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double), C.c_int, C.c_int,
+                                         C.POINTER(C.c_double), C.POINTER(C.c_double)]),
+    "ti_register_colour": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_uint64, C.c_uint64, C.c_uint64]),
     "ti_get_valid_mask": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
     "ti_convert": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_uint64, C.c_uint64]),
     "ti_rectify": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_uint64, C.c_uint64]),

@@ -157,6 +157,25 @@ class IngestContext:
         self._check(self.lib.ti_upload_projection(self._h, camera, int(size[0]), int(size[1]), kk, mm))
         self._cams.setdefault(camera, {}).update(proj=(int(size[0]), int(size[1])))
 
+    def upload_registration(self, camera: int, k_depth: np.ndarray, depth_size: tuple[int, int], k_rgb: np.ndarray,
+                            rgb_size: tuple[int, int], rgb_T_depth: np.ndarray) -> None:
+        """Depth -> RGB registration constants: 3x3 intrinsics of both images, sizes (w, h), 4x4 (or 3x4) ``rgb_T_depth``."""
+        kd, kr = np.asarray(k_depth, dtype=np.float64), np.asarray(k_rgb, dtype=np.float64)
+        m = np.asarray(rgb_T_depth, dtype=np.float64)
+        if kd.shape != (3, 3) or kr.shape != (3, 3) or m.shape not in ((4, 4), (3, 4)):
+            raise ValueError("intrinsics must be 3x3 and rgb_T_depth 4x4 or 3x4")
+        self._check(self.lib.ti_upload_registration(
+            self._h, camera, int(depth_size[0]), int(depth_size[1]), (C.c_double * 4)(kd[0, 0], kd[1, 1], kd[0, 2], kd[1, 2]),
+            int(rgb_size[0]), int(rgb_size[1]), (C.c_double * 4)(kr[0, 0], kr[1, 1], kr[0, 2], kr[1, 2]),
+            (C.c_double * 12)(*m[:3, :4].reshape(-1))))
+
+    def register_colour(self, camera: int, depth: Any, rgb: Any, colour: Any) -> Any:
+        """One RGB8 colour per depth pixel (``ti_register_colour``): ``depth`` [n,H,W] u16, ``rgb`` [n,Hr,Wr,3], ``colour`` [n,H,W,3]."""
+        n = int(depth.shape[0])
+        self._check(self.lib.ti_register_colour(self._h, camera, self._ptr(depth), self._ptr(rgb), self._ptr(colour), n,
+                                                self._batch_stride(depth), self._batch_stride(rgb), self._batch_stride(colour)))
+        return colour
+
     def camera_info(self, camera: int) -> dict:
         return dict(self._cams.get(camera, {}))
 
