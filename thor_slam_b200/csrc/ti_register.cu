@@ -62,6 +62,25 @@ __global__ void __launch_bounds__(RG_THREADS) register_colour_kernel(const RegJo
     }
 }
 
+// 4 consecutive depth pixels per thread: one 64-bit depth load, twelve colour bytes as three 32-bit streaming stores.
+__global__ void __launch_bounds__(RG_THREADS) register_colour_vec_kernel(const RegJobDev J, int n_batch) {
+    const uint32_t quads_per_frame = (uint32_t)J.dw * J.dh / 4;
+    const uint64_t total = (uint64_t)quads_per_frame * n_batch;
+    for (uint64_t i = (uint64_t)blockIdx.x * RG_THREADS + threadIdx.x; i < total; i += (uint64_t)gridDim.x * RG_THREADS) {
+        const uint64_t b = i / quads_per_frame;
+        const uint32_t px = (uint32_t)(i - b * quads_per_frame) * 4;
+        const int v = (int)(px / (uint32_t)J.dw), u = (int)(px - (uint32_t)v * J.dw);  // dw % 4 == 0: the quad stays in one row
+        const uint2 d = ld_stream_u2(reinterpret_cast<const uint8_t*>(J.depth) + b * J.depth_stride + (size_t)px * 2);
+        const uint8_t* rgb = J.rgb + b * J.rgb_stride;
+        const uint32_t c0 = register_pixel(J, rgb, u, v, d.x & 0xFFFFu), c1 = register_pixel(J, rgb, u + 1, v, d.x >> 16);
+        const uint32_t c2 = register_pixel(J, rgb, u + 2, v, d.y & 0xFFFFu), c3 = register_pixel(J, rgb, u + 3, v, d.y >> 16);
+        uint8_t* o = J.colour + b * J.colour_stride + (size_t)px * 3;
+        st_stream_u1(o, c0 | (c1 << 24));
+        st_stream_u1(o + 4, (c1 >> 8) | (c2 << 16));
+        st_stream_u1(o + 8, (c2 >> 16) | (c3 << 8));
+    }
+}
+
 int launch_register_colour(ti_ctx* ctx, int camera, const uint16_t* depth, const uint8_t* rgb, uint8_t* colour, int n_batch,
                            uint64_t depth_stride, uint64_t rgb_stride, uint64_t colour_stride) {
     if (n_batch <= 0) return TI_OK;
@@ -77,6 +96,14 @@ int launch_register_colour(ti_ctx* ctx, int camera, const uint16_t* depth, const
     J.cx = C.reg_k[0]; J.cy = C.reg_k[1]; J.rfx = C.reg_k[2]; J.rfy = C.reg_k[3]; J.rcx = C.reg_k[4]; J.rcy = C.reg_k[5];
     J.dw = C.reg_dw; J.dh = C.reg_dh; J.rw = C.reg_rw; J.rh = C.reg_rh;
     const uint64_t total = (uint64_t)J.dw * J.dh * n_batch;
+    const bool vec = J.dw % 4 == 0 && ((uintptr_t)depth % 8 == 0) && (J.depth_stride % 8 == 0) && ((uintptr_t)colour % 4 == 0) &&
+                     (J.colour_stride % 4 == 0);
+    if (vec) {
+        const int grid = (int)std::min<uint64_t>((total / 4 + RG_THREADS - 1) / RG_THREADS, (uint64_t)ctx->sm_count * 16);
+        TI_LAUNCH(register_colour_vec_kernel, grid, RG_THREADS, 0, ctx->stream, J, n_batch);
+        TI_CHECK_LAUNCH(ctx);
+        return TI_OK;
+    }
     const int grid = (int)std::min<uint64_t>((total + RG_THREADS - 1) / RG_THREADS, (uint64_t)ctx->sm_count * 16);
     TI_LAUNCH(register_colour_kernel, grid, RG_THREADS, 0, ctx->stream, J, n_batch);
     TI_CHECK_LAUNCH(ctx);

@@ -142,6 +142,16 @@ def main() -> None:
         report("backproject depth->xyz+mask+count", timeit(lambda: ctx.ingest(bspecs), args.iters), 15 * dpx, dpx)
         report("torch copy_ xyz (24 B/px traffic)", timeit(lambda: [xyz[i].copy_(xyz[(i + 1) % ND]) for i in range(ND)], args.iters), 24 * dpx, dpx)
         report("torch fill_ xyz (12 B/px, write only)", timeit(lambda: [xyz[i].fill_(1.0) for i in range(ND)], args.iters), 12 * dpx, dpx)
+        rgb_img = torch.randint(0, 256, (B, 1080, 1920, 3), dtype=torch.uint8, device="cuda")
+        colour = torch.empty((B, H, W, 3), dtype=torch.uint8, device="cuda")
+        ri, di = SyntheticCameraSource(SyntheticCameraConfig(name="r", enable_rgbd=True, rgb_resolution=(1920, 1080), depth_resolution=(W, H),
+                                                             pool=1)).get_rgbd_intrinsics()
+        t_rd = np.eye(4)
+        t_rd[0, 3] = -0.0375
+        ctx.upload_registration(0, di.matrix, (W, H), ri.matrix, (1920, 1080), t_rd)
+        report("register depth->rgb colour (depth 2 + colour 3 B/px + the 1080p RGB image once)",
+               timeit(lambda: ctx.register_colour(0, depth[0], rgb_img, colour), args.iters), 5 * B * W * H + B * 1920 * 1080 * 3, B * W * H)
+        del rgb_img, colour
         for per_sm in (2, 3, 4, 6, 8):
             ctx.set_option(ctx.OPT_CTAS_PER_SM, per_sm)
             report(f"backproject ctas/sm={per_sm}", timeit(lambda: ctx.ingest(bspecs), args.iters), 15 * dpx, dpx)
