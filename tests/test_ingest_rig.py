@@ -96,6 +96,11 @@ def run_case(ctx):
                 assert np.array_equal(np.asarray(c["mask"]), mask) and int(c["count"]) == cnt
                 rgb_src = src._rgbd_pool[int(c["rgb"].sequence_num) % 3][0]
                 assert np.array_equal(np.asarray(c["rgb"].image), rgb_src[..., ::-1])
+                ri, _di = src.get_rgbd_intrinsics()
+                re, de = src.get_rgbd_extrinsics()
+                want_col = ob.register_colour(depth, di.matrix, np.linalg.inv(re.to_4x4_matrix()) @ de.to_4x4_matrix(), ri.matrix,
+                                              np.ascontiguousarray(rgb_src[..., ::-1]))
+                assert np.array_equal(np.asarray(c["colours"]), want_col)
     # the consumer saw 6 streams in the reference's global order: sorted source name, then cam_idx
     assert [(c.source_name, c.cam_idx) for c in engine.cameras] == [("oak0", 0), ("oak0", 1), ("oak1", 0), ("oak1", 1), ("oak2", 0), ("oak2", 1)]
     assert [r.encoding for r in engine.history[-1]] == ["rgb8", "rgb8", "mono8", "mono8", "rgb8", "rgb8"]

@@ -104,6 +104,7 @@ class IngestRig(CameraRig):
         self._color_output = F.fmt(color_output)
         self._streams: dict[str, list[_Stream]] = {}
         self._rgbd: dict[str, tuple[_Stream, _Stream]] = {}
+        self._colours: dict[str, Any] = {}
         self._next_camera = 0
         self._copy_stream = None if self._emulated else torch.cuda.Stream(device=self._device)
         self._build_streams()
@@ -183,6 +184,9 @@ class IngestRig(CameraRig):
             rig_pose = cal.rig_extrinsics.get(name)
             m = body_T_camera(None if rig_pose is None else rig_pose.to_4x4_matrix(), de.to_4x4_matrix(), self._rig_frame)
             self._ctx.upload_projection(dep.camera, di.matrix, m, dep.src_size)
+            # depth -> RGB registration: both extrinsics map into the source frame (CAM_A), luxonis.py:1068-1091
+            rgb_T_depth = np.linalg.inv(_re.to_4x4_matrix()) @ de.to_4x4_matrix()
+            self._ctx.upload_registration(dep.camera, di.matrix, dep.src_size, _ri.matrix, _rgb.src_size, rgb_T_depth)
 
     def _on_calibration_changed(self) -> None:
         if hasattr(self, "_streams"):
@@ -253,7 +257,8 @@ class IngestRig(CameraRig):
         """Latest RGB-D pair of ``source_name`` through the ingest stage.
 
         Returns ``{"rgb": CameraFrame(rgb8), "depth": CameraFrame(u16 mm, untouched), "points": DeviceImage
-        HxWx3 f32 body frame, "mask": DeviceImage HxW u8, "count": int tensor}`` or ``None`` when the
+        HxWx3 f32 body frame, "colours": DeviceImage HxWx3 u8 (the RGB pixel each depth pixel projects to),
+        "mask": DeviceImage HxW u8, "count": int tensor}`` or ``None`` when the
         source has no new pair (or is not an RGB-D source / the rig is stopped).
         """
         if not self._running or source_name not in self._rgbd:
@@ -278,6 +283,8 @@ class IngestRig(CameraRig):
             StreamSpec(F.KIND_BACKPROJECT, dep.dev[slot:slot + 1], dep.out[slot:slot + 1], F.DEPTH16, F.XYZ32F, camera=dep.camera,
                        mask=dep.mask[slot:slot + 1], count=dep.count[slot:slot + 1]),
         ])
+        colours = self._colours.setdefault(source_name, self._alloc((2, dep.src_size[1], dep.src_size[0], 3), F.RGB8))
+        self._ctx.register_colour(dep.camera, dep.dev[slot:slot + 1], rgb.out[slot:slot + 1], colours[slot:slot + 1])
         ready = None
         if not self._emulated:
             ready = torch.cuda.Event()
@@ -285,6 +292,7 @@ class IngestRig(CameraRig):
         return {
             "rgb": CameraFrame(DeviceImage(rgb.out[slot], ready), rgb_f.timestamp, rgb_f.sequence_num, rgb_f.camera_name),
             "depth": dep_f,
+            "colours": DeviceImage(colours[slot], ready),
             "points": DeviceImage(dep.out[slot], ready),
             "mask": DeviceImage(dep.mask[slot], ready),
             "count": dep.count[slot],
