@@ -195,3 +195,50 @@ def test_depth_rgb_registration_gpu(gpu_backend):
     with pytest.raises(RuntimeError):
         gpu_backend.ctx.register_colour(52, gpu_backend.zeros((1, 8, 8), np.uint16), gpu_backend.zeros((1, 8, 8, 3), np.uint8),
                                         gpu_backend.zeros((1, 8, 8, 3), np.uint8))  # slot never uploaded
+
+
+# ---- (f) row 4: IMU samples in the convention of the IMU extrinsics -----------------------------------------------------
+def test_imu_sample_rotation_matches_the_extrinsics_convention():
+    from oracle import conventions as conv
+    from thor_slam_b200.ingest.calib import rotate_imu_sample
+
+    rng = np.random.default_rng(8)
+    sample = {"accelerometer": [0.3, -9.7, 1.1], "gyroscope": [0.01, -0.02, 0.5], "timestamp": 12.5}
+    assert rotate_imu_sample(sample, "rdf") is sample and rotate_imu_sample(None, "drb") is None  # reference behaviour: untouched
+    got = rotate_imu_sample(sample, "drb")
+    assert got["timestamp"] == 12.5 and sample["accelerometer"] == [0.3, -9.7, 1.1]  # pass-through, no mutation
+    # x_rdf = y_drb, y_rdf = x_drb, z_rdf = -z_drb (scripts/run_slam.py:254-266)
+    assert got["accelerometer"] == [-9.7, 0.3, -1.1] and got["gyroscope"] == [-0.02, 0.01, -0.5]
+    # a Pro IMU read through (DRB extrinsics, raw sample) and through (RDF extrinsics, rotated sample) is the same world vector
+    rig_pose, t_imu = np.eye(4), np.eye(4)
+    from scipy.spatial.transform import Rotation
+
+    rig_pose[:3, :3] = Rotation.from_rotvec(rng.uniform(-1, 1, 3)).as_matrix()
+    t_imu[:3, :3] = Rotation.from_rotvec(rng.uniform(-0.2, 0.2, 3)).as_matrix()
+    drb_world = conv.imu_world_extrinsics(rig_pose, t_imu, "drb")[:3, :3]
+    for key in ("accelerometer", "gyroscope"):
+        raw_in_imu_axes = np.linalg.inv(t_imu[:3, :3]) @ conv.DRB_TO_RDF[:3, :3].T @ np.asarray(got[key])  # undo: back to what the chip reported
+        np.testing.assert_allclose(raw_in_imu_axes, np.linalg.inv(t_imu[:3, :3]) @ np.asarray(sample[key]), atol=1e-12)
+        np.testing.assert_allclose(drb_world @ np.linalg.inv(t_imu[:3, :3]) @ np.asarray(sample[key]),
+                                   rig_pose[:3, :3] @ conv.DRB_TO_RDF[:3, :3] @ np.asarray(sample[key]), atol=1e-12)
+    assert abs(np.linalg.det(conv.DRB_TO_RDF[:3, :3]) - 1.0) < 1e-15  # proper rotation: the gyro transforms like the accelerometer
+    with pytest.raises(ValueError):
+        rotate_imu_sample(sample, "ulb")
+
+
+def test_ingest_rig_rotates_pro_imu_samples(emu_backend):
+    from thor_slam_b200.ingest.rig import IngestRig
+
+    def make(name):
+        return SyntheticCameraSource(SyntheticCameraConfig(name=name, resolution=(192, 96), pool=1, read_imu=True, seed=3))
+
+    rig_drb = IngestRig([make("pro")], queue_size=2, imu_source="pro", imu_frame="drb", context=emu_backend.ctx)
+    rig_rdf = IngestRig([make("pro")], queue_size=2, imu_source="pro", context=emu_backend.ctx)
+    with rig_drb, rig_rdf:
+        a, b = rig_drb.get_synchronized_frames(), rig_rdf.get_synchronized_frames()
+    assert a.sensor_data is not None and b.sensor_data is not None and a.sensor_timestamp == b.sensor_timestamp
+    for key in ("accelerometer", "gyroscope"):
+        x, y, z = b.sensor_data[key][:3]
+        assert a.sensor_data[key][:3] == [y, x, -z]
+    with pytest.raises(ValueError):
+        IngestRig([make("pro")], imu_source="pro", imu_frame="flu", context=emu_backend.ctx)

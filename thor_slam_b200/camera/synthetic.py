@@ -252,7 +252,7 @@ class SyntheticCameraSource(CameraSource):
             "timestamp": ts,
             "sequence_num": seq,
         }
-        return {"imu": sample}, ts
+        return sample, ts  # the latest packet, flat, like LuxonisCameraSource (luxonis.py:1098-1160)
 
     # -- RGB-D extras (duck-typed like LuxonisCameraSource) -----------------
     @property

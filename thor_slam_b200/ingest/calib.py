@@ -49,6 +49,28 @@ DRB_TO_RDF_MATRIX = np.array(  # OAK-D Pro IMU axes -> camera axes (scripts/run_
 )
 
 
+def rotate_imu_sample(sample: dict | None, imu_frame: str = "rdf") -> dict | None:
+    """IMU sample with its vectors expressed in the camera (RDF) axes.
+
+    The reference folds the OAK-D Pro's DRB -> RDF rotation into the IMU *extrinsics* only
+    (``scripts/run_slam.py:254-276``, ``scripts/run_pipeline.py:543-565``) and publishes the samples themselves as they
+    come (``slam/adapters/isaac_ros.py:284-298``); a consumer that wants samples and extrinsics in one convention needs
+    the same rotation on ``accelerometer`` / ``gyroscope``.  ``DRB_TO_RDF`` is a proper rotation (det +1), so the
+    angular rate transforms like the acceleration.  ``imu_frame="rdf"`` (OAK-D Long Range) returns the sample unchanged;
+    every other key (timestamps, ...) is passed through."""
+    if sample is None or imu_frame == "rdf":
+        return sample
+    if imu_frame != "drb":
+        raise ValueError(f"unknown IMU frame {imu_frame!r} (expected 'drb' or 'rdf')")
+    r = DRB_TO_RDF_MATRIX[:3, :3]
+    out = dict(sample)
+    for key in ("accelerometer", "gyroscope"):
+        v = sample.get(key)
+        if v is not None and len(v) >= 3:
+            out[key] = [float(x) for x in r @ np.asarray(v[:3], dtype=np.float64)] + list(v[3:])
+    return out
+
+
 def distortion_model(coeffs: np.ndarray | Sequence[float]) -> tuple[str, np.ndarray]:
     """(ROS model name, coefficients that take part) - the reference's CameraInfo rule."""
     d = [float(x) for x in np.asarray(coeffs, dtype=np.float64).reshape(-1)]

@@ -37,7 +37,7 @@ from thor_slam_b200.camera.calibration import Extrinsics, IMUExtrinsics
 from thor_slam_b200.camera.frames import CameraFrame, CameraSource, DeviceImage, FrameSet, SynchronizedFrameSet
 from thor_slam_b200.camera.rig import CameraRig
 from thor_slam_b200.ingest import formats as F
-from thor_slam_b200.ingest.calib import body_T_camera, stereo_rectify_maps
+from thor_slam_b200.ingest.calib import body_T_camera, rotate_imu_sample, stereo_rectify_maps
 from thor_slam_b200.ingest.context import IngestContext, StreamSpec
 
 logger = logging.getLogger(__name__)
@@ -86,6 +86,7 @@ class IngestRig(CameraRig):
         rectify: bool = True,
         rig_frame: str = "rdf",
         color_output: str = "rgb8",
+        imu_frame: str = "rdf",
         context: IngestContext | None = None,
     ) -> None:
         """Extra (keyword-only) arguments over the reference constructor:
@@ -93,7 +94,9 @@ class IngestRig(CameraRig):
         ``device``: CUDA device index; ``rectify``: remap SLAM streams (False = conversion only);
         ``rig_frame``: ``"rdf"`` (rig poses in the Luxonis convention, clouds rotated to FLU with
         ``RDF_TO_FLU_MATRIX``) or ``"flu"``; ``color_output``: ``"rgb8"`` (what the reference's adapter
-        publishes for 3-channel frames) or ``"mono8"``; ``context``: share an ``IngestContext``.
+        publishes for 3-channel frames) or ``"mono8"``; ``imu_frame``: axes of the IMU source's samples, ``"drb"``
+        (OAK-D Pro: samples are rotated into the camera's RDF axes, see ``calib.rotate_imu_sample``) or ``"rdf"``
+        (OAK-D Long Range, reference behaviour: untouched); ``context``: share an ``IngestContext``.
         """
         super().__init__(sources, queue_size, rig_extrinsics, imu_extrinsics, imu_source)
         self._ctx = context if context is not None else IngestContext(device)
@@ -102,6 +105,9 @@ class IngestRig(CameraRig):
         self._rectify = rectify
         self._rig_frame = rig_frame
         self._color_output = F.fmt(color_output)
+        if imu_frame not in ("rdf", "drb"):
+            raise ValueError(f"unknown IMU frame {imu_frame!r} (expected 'drb' or 'rdf')")
+        self._imu_frame = imu_frame
         self._streams: dict[str, list[_Stream]] = {}
         self._rgbd: dict[str, tuple[_Stream, _Stream]] = {}
         self._colours: dict[str, Any] = {}
@@ -250,7 +256,8 @@ class IngestRig(CameraRig):
             frames = [CameraFrame(DeviceImage(st.out[slot], ready), fr.timestamp, fr.sequence_num, fr.camera_name)
                       for (st, slot), fr in zip(outputs[name], fs.frames)]
             out_sets[name] = FrameSet(fs.timestamp, frames, fs.source_name, fs.sensor_data, fs.sensor_timestamp)
-        return SynchronizedFrameSet(sync.timestamp, out_sets, sync.max_time_delta, sync.sensor_data, sync.sensor_timestamp)
+        return SynchronizedFrameSet(sync.timestamp, out_sets, sync.max_time_delta, rotate_imu_sample(sync.sensor_data, self._imu_frame),
+                                    sync.sensor_timestamp)
 
     # -- RGB-D (bypasses the synchroniser in the reference too: run_pipeline.py:624-631) --------
     def get_rgbd(self, source_name: str, blocking: bool = False) -> dict | None:
