@@ -79,18 +79,19 @@ __device__ __forceinline__ void p4_blend(const Taps& T, const uint4& w, uint32_t
 // fixes (warp-uniform): some lane has an exception entry; i_fix: this lane has one, at shared address my_exc =
 // {window word, Wtop, Wbot, row * dst_w + column}.  Its window is fetched ahead of the last row's blend so that the
 // latency of the dependent loads hides behind that row; its store follows the row loop's stores (__syncwarp).
-template <int RPW, bool WHOLE, bool PREFETCH>
+template <int RPW, bool WHOLE, bool PREFETCH, bool HALF_LOADS = false>
 __device__ __forceinline__ void p4_rows(const uint4 (&w0)[RPW], const uint4 (&w1)[RPW], const uint2 (&mw)[RPW], p4_addr_t base,
                                         uint8_t* dp, int dst_w, int live_rows, int live_cols, int lane, bool fixes, bool i_fix,
                                         p4_addr_t my_exc) {
-    Taps A = p4_fetch(base, mw[0].x), B = p4_fetch(base, mw[0].y);
+    // HALF_LOADS (bring-up only, wrong pixels): pair 1 reuses pair 0's window - how much of the time is the window loads?
+    Taps A = p4_fetch(base, mw[0].x), B = HALF_LOADS ? A : p4_fetch(base, mw[0].y);
     uint8_t* const warp_dst = dp - 2 * lane;  // (row 0, column 0) of this warp
     uint4 fe = make_uint4(0u, 0u, 0u, 0u);
     Taps X = A;
 #pragma unroll
     for (int q = 0; q < RPW; ++q) {
         Taps An = A, Bn = B;
-        if (PREFETCH && q + 1 < RPW) { An = p4_fetch(base, mw[q + 1].x); Bn = p4_fetch(base, mw[q + 1].y); }
+        if (PREFETCH && q + 1 < RPW) { An = p4_fetch(base, mw[q + 1].x); Bn = HALF_LOADS ? An : p4_fetch(base, mw[q + 1].y); }
         if (q == RPW - 1 && fixes && i_fix) {
             fe = p4_lds128(my_exc);
             X = p4_fetch(base, fe.x);
@@ -247,7 +248,8 @@ __global__ void __launch_bounds__(P4_THREADS, TH == 32 ? 3 : 4) rectify_mono_pai
         for (uint32_t f = 0; f < U.nb; ++f) {
             p4_wait(bar, phase);
             if (!skip_blend) {
-                if (whole) p4_rows<RPW, true, TH == 32>(w0, w1, mw, base, dp, dst_w, live_rows, live_cols, lane, warp_fixes, i_fix, my_exc);
+                if (DEBUG && (P.debug & 8)) p4_rows<RPW, true, TH == 32, true>(w0, w1, mw, base, dp, dst_w, live_rows, live_cols, lane, warp_fixes, i_fix, my_exc);
+                else if (whole) p4_rows<RPW, true, TH == 32>(w0, w1, mw, base, dp, dst_w, live_rows, live_cols, lane, warp_fixes, i_fix, my_exc);
                 else p4_rows<RPW, false, false>(w0, w1, mw, base, dp, dst_w, live_rows, live_cols, lane, warp_fixes, i_fix, my_exc);
             }
             __syncwarp();
@@ -361,7 +363,9 @@ int build_pair_tables(ti_ctx* ctx, CameraSlot& C, const std::vector<uint32_t>& l
                 TileBox2& B = boxes[(size_t)ty * tx_n + tx];
                 B = TileBox2{0, 0, 0, 0, (int16_t)(tx * P4_TW), (int16_t)(ty * TH), 0, 0};
                 if (bx1 <= bx0) continue;
-                const int c0 = bx0 & ~15;  // floor to 16 (-1 -> -16): TMA boxes start on 16-byte columns
+                // floor to 16 (-1 -> -16): a TMA box must start on a 16-byte boundary of global memory - probed on the B200:
+                // starts shifted by 1, 4 or 7 bytes end in "an illegal instruction was encountered"
+                const int c0 = bx0 & ~15;
                 if (bx1 - c0 > P4_PITCH || by1 - by0 > P4_MAX_ROWS) { ok = false; break; }
                 B.c0 = (int16_t)c0; B.y0 = (int16_t)by0; B.nvec = (int16_t)((bx1 - c0 + 15) / 16); B.rows = (int16_t)(by1 - by0);
                 rows_max = std::max(rows_max, by1 - by0);

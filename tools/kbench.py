@@ -90,7 +90,7 @@ def main() -> None:
         if args.one:
             ctx.close()
             return
-        for dbg, what in ((1, "loads only (no blend)"), (2, "blend only (no loads)"), (3, "pipeline only")):
+        for dbg, what in ((1, "loads only (no blend)"), (2, "blend only (no loads)"), (3, "pipeline only"), (8, "half the window loads (wrong pixels)")):
             ctx.set_option(ctx.OPT_DEBUG, dbg)
             report(f"rectify mono v4 DEBUG {what}", timeit(lambda: ctx.ingest(specs), args.iters), 2 * px, px)
         ctx.set_option(ctx.OPT_DEBUG, 0)
