@@ -39,6 +39,7 @@
 #include "ti_rectify_pair.cuh"
 #include "ti_pair_dev.cuh"
 
+#include <cstdlib>
 #include <cstring>
 
 namespace ti {
@@ -79,7 +80,8 @@ __device__ __forceinline__ void p4_blend(const Taps& T, const uint4& w, uint32_t
 // fixes (warp-uniform): some lane has an exception entry; i_fix: this lane has one, at shared address my_exc =
 // {window word, Wtop, Wbot, row * dst_w + column}.  Its window is fetched ahead of the last row's blend so that the
 // latency of the dependent loads hides behind that row; its store follows the row loop's stores (__syncwarp).
-template <int RPW, bool WHOLE, bool PREFETCH, bool HALF_LOADS = false>
+// DSTW > 0: the destination row pitch is this compile-time constant, so row q is an immediate offset from the lane's first-row pointer.
+template <int RPW, bool WHOLE, bool PREFETCH, bool HALF_LOADS = false, int DSTW = 0>
 __device__ __forceinline__ void p4_rows(const uint4 (&w0)[RPW], const uint4 (&w1)[RPW], const uint2 (&mw)[RPW], p4_addr_t base,
                                         uint8_t* dp, int dst_w, int live_rows, int live_cols, int lane, bool fixes, bool i_fix,
                                         p4_addr_t my_exc) {
@@ -100,7 +102,10 @@ __device__ __forceinline__ void p4_rows(const uint4 (&w0)[RPW], const uint4 (&w1
         p4_blend(A, w0[q], mw[q].x, ra0, rb0);
         p4_blend(B, w1[q], mw[q].y, ra1, rb1);
         const uint32_t o0 = __byte_perm(ra0, rb0, 0x0062), o1 = __byte_perm(ra1, rb1, 0x0062);
-        if (WHOLE) {
+        if (WHOLE && DSTW > 0) {
+            st_stream_b16(dp + q * DSTW, o0);
+            st_stream_b16(dp + q * DSTW + 64, o1);
+        } else if (WHOLE) {
             st_stream_b16(dp, o0);
             st_stream_b16(dp + 64, o1);
         } else if (q < live_rows) {
@@ -110,7 +115,7 @@ __device__ __forceinline__ void p4_rows(const uint4 (&w0)[RPW], const uint4 (&w1
             if (c1 < live_cols) st_stream_b8(dp + 64, o1);
             if (c1 + 1 < live_cols) st_stream_b8(dp + 65, o1 >> 8);
         }
-        dp += dst_w;
+        if (!(WHOLE && DSTW > 0)) dp += dst_w;
         if (PREFETCH) { A = An; B = Bn; }
         else if (q + 1 < RPW) { A = p4_fetch(base, mw[q + 1].x); B = p4_fetch(base, mw[q + 1].y); }
     }
@@ -124,7 +129,7 @@ __device__ __forceinline__ void p4_rows(const uint4 (&w0)[RPW], const uint4 (&w1
     }
 }
 
-template <int TH, bool DEBUG>
+template <int TH, bool DEBUG, int DSTW = 0>
 __global__ void __launch_bounds__(P4_THREADS, TH == 32 ? 3 : 4) rectify_mono_pair_kernel(const __grid_constant__ Rect4Params P) {
     TI_DYNAMIC_SMEM(uint8_t, smem);
     constexpr int RPW = TH / P4_CONSUMER_WARPS;  // tile rows per consumer warp
@@ -249,7 +254,7 @@ __global__ void __launch_bounds__(P4_THREADS, TH == 32 ? 3 : 4) rectify_mono_pai
             p4_wait(bar, phase);
             if (!skip_blend) {
                 if (DEBUG && (P.debug & 8)) p4_rows<RPW, true, TH == 32, true>(w0, w1, mw, base, dp, dst_w, live_rows, live_cols, lane, warp_fixes, i_fix, my_exc);
-                else if (whole) p4_rows<RPW, true, TH == 32>(w0, w1, mw, base, dp, dst_w, live_rows, live_cols, lane, warp_fixes, i_fix, my_exc);
+                else if (whole) p4_rows<RPW, true, TH == 32, false, DSTW>(w0, w1, mw, base, dp, dst_w, live_rows, live_cols, lane, warp_fixes, i_fix, my_exc);
                 else p4_rows<RPW, false, false>(w0, w1, mw, base, dp, dst_w, live_rows, live_cols, lane, warp_fixes, i_fix, my_exc);
             }
             __syncwarp();
@@ -271,7 +276,17 @@ int launch_rectify_pair(ti_ctx* ctx, Rect4Params& P, int th_index) {
     static const Kern kernels[2][P4_N_TH] = {
         {rectify_mono_pair_kernel<16, false>, rectify_mono_pair_kernel<32, false>, rectify_mono_pair_kernel<24, false>},
         {rectify_mono_pair_kernel<16, true>, rectify_mono_pair_kernel<32, true>, rectify_mono_pair_kernel<24, true>}};
-    const Kern kern = kernels[ctx->debug ? 1 : 0][th_index];
+    Kern kern = kernels[ctx->debug ? 1 : 0][th_index];
+    // every job of the launch writes rows of the same common pitch: use the kernel whose row stores are immediate offsets
+    static const bool no_dstw = getenv("TI_NO_DSTW") != nullptr;  // A/B switch for measurements
+    if (!ctx->debug && TH == 32 && !no_dstw) {
+        int dw = P.job[0].dst_w;
+        for (int j = 1; j < P.n_jobs; ++j)
+            if (P.job[j].dst_w != dw) dw = 0;
+        if (dw == 1280) kern = rectify_mono_pair_kernel<32, false, 1280>;
+        else if (dw == 640) kern = rectify_mono_pair_kernel<32, false, 640>;
+        else if (dw == 1920) kern = rectify_mono_pair_kernel<32, false, 1920>;
+    }
     // ring depth: as asked, but never so deep that fewer CTAs fit an SM than the register budget allows
     const int want_ctas = TH == 32 ? 3 : 4;  // = the kernel's __launch_bounds__
     int stages = std::max(2, std::min(ctx->stages4, P4_MAX_STAGES));
