@@ -61,6 +61,24 @@ __device__ __forceinline__ void p4_arrive(p4_addr_t bar) {
 }
 #endif
 
+// One arrival per warp on `bar`, after every lane's work: the arriving lane is picked by elect.sync (no thread-index
+// arithmetic in the loop); the emulation lets lane 0 do it.
+__device__ __forceinline__ void p4_warp_arrive(p4_addr_t bar) {
+#ifdef TI_EMULATE
+    __syncwarp();
+    if ((threadIdx.x & 31) == 0) p4_arrive(bar);
+#else
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "bar.warp.sync 0xffffffff;\n"
+        "elect.sync _|p, 0xffffffff;\n"
+        "@p mbarrier.arrive.shared::cta.b64 _, [%0];\n"
+        "}\n" ::"r"(bar)
+        : "memory");
+#endif
+}
+
 // prmt.b32 with the selector taken as it is (CUDA's __byte_perm masks it with 0x7777 first - one more
 // instruction per window row; bit 3 of a nibble only matters in flagged window words, see below)
 __device__ __forceinline__ uint32_t p4_prmt(uint32_t lo, uint32_t hi, uint32_t sel) {

@@ -78,7 +78,7 @@ __device__ __forceinline__ void p4_blend(const Taps& T, const uint4& w, uint32_t
 // WHOLE: every pixel of the warp's rows exists and rows start on even addresses (16-bit stores).
 // PREFETCH: software pipeline, the windows of row q+1 are in flight while row q is blended and stored (8 more registers).
 // fixes (warp-uniform): some lane has an exception entry; i_fix: this lane has one, at shared address my_exc =
-// {window word, Wtop, Wbot, row * dst_w + column}.  Its window is fetched ahead of the last row's blend so that the
+// {window word, Wtop, Wbot, row * dst_w + column - 2 * lane}.  Its window is fetched ahead of the last row's blend so that the
 // latency of the dependent loads hides behind that row; its store follows the row loop's stores (__syncwarp).
 // DSTW > 0: the destination row pitch is this compile-time constant, so row q is an immediate offset from the lane's first-row pointer.
 template <int RPW, bool WHOLE, bool PREFETCH, bool HALF_LOADS = false, int DSTW = 0>
@@ -87,7 +87,7 @@ __device__ __forceinline__ void p4_rows(const uint4 (&w0)[RPW], const uint4 (&w1
                                         p4_addr_t my_exc) {
     // HALF_LOADS (bring-up only, wrong pixels): pair 1 reuses pair 0's window - how much of the time is the window loads?
     Taps A = p4_fetch(base, mw[0].x), B = HALF_LOADS ? A : p4_fetch(base, mw[0].y);
-    uint8_t* const warp_dst = dp - 2 * lane;  // (row 0, column 0) of this warp
+    uint8_t* const lane_dst = dp;  // this lane's first pixel of the warp's first row
     uint4 fe = make_uint4(0u, 0u, 0u, 0u);
     Taps X = A;
 #pragma unroll
@@ -124,7 +124,7 @@ __device__ __forceinline__ void p4_rows(const uint4 (&w0)[RPW], const uint4 (&w1
         if (i_fix) {
             const uint32_t xt = p4_prmt(X.t0, X.t1, fe.x), xb = p4_prmt(X.b0, X.b1, fe.x);
             const uint32_t r = __dp2a_lo(fe.z, xb, __dp2a_lo(fe.y, xt, 32768u));
-            st_stream_b8(warp_dst + fe.w, r >> 16);
+            st_stream_b8(lane_dst + (int32_t)fe.w, r >> 16);  // offset relative to the repairing lane's own first pixel
         }
     }
 }
@@ -216,7 +216,7 @@ __global__ void __launch_bounds__(P4_THREADS, TH == 32 ? 3 : 4) rectify_mono_pai
     const p4_addr_t stage_first = sm0 + 256;
     const bool skip_blend = DEBUG && (P.debug & 1) != 0;
     p4_addr_t base = stage_first, bar = sm0;  // current stage, its `full` barrier (`empty` is 64 bytes further)
-    const p4_addr_t bar_end = sm0 + 8u * (uint32_t)S;
+    int s_left = S;                            // stages until the ring wraps
     uint32_t phase = 0;
     for (uint32_t k = 0; k < units_mine; ++k) {
         const P4Unit U = p4_unit(P, k);
@@ -257,11 +257,10 @@ __global__ void __launch_bounds__(P4_THREADS, TH == 32 ? 3 : 4) rectify_mono_pai
                 else if (whole) p4_rows<RPW, true, TH == 32, false, DSTW>(w0, w1, mw, base, dp, dst_w, live_rows, live_cols, lane, warp_fixes, i_fix, my_exc);
                 else p4_rows<RPW, false, false>(w0, w1, mw, base, dp, dst_w, live_rows, live_cols, lane, warp_fixes, i_fix, my_exc);
             }
-            __syncwarp();
-            if (lane == 0) p4_arrive(bar + 64);
+            p4_warp_arrive(bar + 64);
             dp += dst_stride;
             bar += 8; base += stage_bytes;
-            if (bar == bar_end) { bar = sm0; base = stage_first; phase ^= 1u; }
+            if (--s_left == 0) { s_left = S; bar -= 8u * (uint32_t)S; base -= (uint32_t)S * stage_bytes; phase ^= 1u; }
         }
     }
 }
@@ -417,7 +416,7 @@ int build_pair_tables(ti_ctx* ctx, CameraSlot& C, const std::vector<uint32_t>& l
                                 m = (off << 16) | sa | ((sa + 1) << 4) | ((uint32_t)sb_rel << 8) | ((uint32_t)(sb_rel + 1) << 12);
                             } else {
                                 // pixel b gets an entry of the warp's exception list: its own window (bytes b.left, b.right
-                                // selected into bytes 0, 1), its weight words, where it goes (byte offset from the warp's first row in the tile)
+                                // selected into bytes 0, 1), its weight words, where it goes
                                 if (ex.size() / 4 >= (size_t)P4_MAX_EXC) { ok = false; break; }
                                 const int wordb = (b.x0 - B.c0) & ~3;
                                 const uint32_t offb = (uint32_t)((b.y0 - B.y0) * P4_PITCH + wordb);
@@ -428,7 +427,9 @@ int build_pair_tables(ti_ctx* ctx, CameraSlot& C, const std::vector<uint32_t>& l
                                 ex.push_back((offb << 16) | sb | ((sb + 1) << 4) | (sb << 8) | ((sb + 1) << 12));
                                 ex.push_back(wt);
                                 ex.push_back(wb);
-                                ex.push_back((uint32_t)(row % RPW) * (uint32_t)dst_w + (uint32_t)(p * 64 + 2 * lane + 1));
+                                // destination of the pixel relative to the first pixel of the lane that will repair it (entry i -> lane i)
+                                const int fix_lane = (int)(ex.size() / 4);
+                                ex.push_back((uint32_t)((row % RPW) * dst_w + (p * 64 + 2 * lane + 1) - 2 * fix_lane));
                             }
                         }
                 }
