@@ -136,7 +136,7 @@ __global__ void __launch_bounds__(C3_THREADS, 3) rectify_c3_kernel(const __grid_
     const p4_addr_t sm0 = p4_addr(smem);
     const p4_addr_t stage_first = sm0 + 256;
     p4_addr_t base = stage_first, bar = sm0;  // current stage, its `full` barrier (`empty` is 64 bytes further)
-    const p4_addr_t bar_end = sm0 + 8u * (uint32_t)S;
+    int s_left = S;                            // stages until the ring wraps
     uint32_t phase = 0;
     for (uint32_t k = 0; k < units_mine; ++k) {
         const C3Unit U = c3_unit(P, k);
@@ -188,11 +188,10 @@ __global__ void __launch_bounds__(C3_THREADS, 3) rectify_c3_kernel(const __grid_
                 }
                 rp += (size_t)dst_w * 3;
             }
-            __syncwarp();
-            if (lane == 0) p4_arrive(bar + 64);
+            p4_warp_arrive(bar + 64);
             dp += dst_stride;
             bar += 8; base += stage_bytes;
-            if (bar == bar_end) { bar = sm0; base = stage_first; phase ^= 1u; }
+            if (--s_left == 0) { s_left = S; bar -= 8u * (uint32_t)S; base -= (uint32_t)S * stage_bytes; phase ^= 1u; }
         }
     }
 }
