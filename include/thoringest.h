@@ -103,7 +103,7 @@ typedef enum ti_option {
     TI_OPT_TMA_TILE_H = 4,            /* output tile height of the TMA-pipelined kernel: 16, 24 or 32 (default) */
     TI_OPT_DEBUG = 5,                 /* bring-up switches; 0 in production (non-zero MAY change results) */
     TI_OPT_FRAMES_PER_UNIT = 6,       /* frames of a batch sharing one LUT fetch in the TMA kernels (default 16; pair-window: 0 = automatic) */
-    TI_OPT_STAGES = 7,                /* shared-memory ring depth of the TMA kernels, 2..8 (default 3 pair-window, 2 shifted-copy) */
+    TI_OPT_STAGES = 7,                /* shared-memory ring depth of the TMA kernels, 2..8 (default 6 pair-window, reduced to fit; 2 shifted-copy) */
     TI_OPT_LUT_PREFETCH = 8           /* 1: consumers prefetch the next unit's LUT into a second register set (default 0) */
 } ti_option;
 int ti_set_option(ti_ctx* ctx, int option, int value);

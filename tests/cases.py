@@ -108,7 +108,7 @@ def check_rectify(be, cam: int, mapx, mapy, s: str, d: str, src_w: int, src_h: i
         be.ctx.set_option(be.ctx.OPT_TMA_TILE_H, 32)
         be.ctx.set_option(be.ctx.OPT_FRAMES_PER_UNIT, 16)
         be.ctx.set_option(be.ctx.OPT_FRAMES_PER_UNIT, 0)
-        be.ctx.set_option(be.ctx.OPT_STAGES, 4)
+        be.ctx.set_option(be.ctx.OPT_STAGES, 6)
         be.ctx.set_option(be.ctx.OPT_LUT_PREFETCH, 0)
     mask = be.zeros((dst_h, dst_w), np.uint8)
     be.ctx.get_valid_mask(cam, mask)

@@ -173,7 +173,7 @@ struct ti_ctx {
     int tma_tile_h = 32;    // 16, 24 or 32
     int lut_prefetch = 0;   // 1: consumers prefetch the next unit's LUT into a second register set (costs 16 registers)
     int stages = 2;           // shared-memory ring depth of the TMA-pipelined kernel (2 stages -> 4 CTAs per SM)
-    int stages4 = 4;          // ring depth of the pair-window kernel
+    int stages4 = 6;          // ring depth of the pair-window kernels (reduced per launch until three CTAs fit an SM)
     int frames_per_unit = 16;  // frames of the batch that share one LUT fetch in the TMA-pipelined kernel
     int frames_per_unit4 = 0;  // same for the pair-window kernel; 0 = chosen per launch (least tail over the persistent grid)
     bool force_generic_rectify = false;  // tests: exercise the generic tiled / direct kernels

@@ -72,7 +72,7 @@ def main() -> None:
 
     if not args.only or "rect" in args.only:
         print("plan", ctx.rectify_plan(0), flush=True)
-        for variant, th, fpu, stages, pf in ((4, 32, 0, 3, 0), (4, 32, 0, 4, 0), (4, 32, 0, 2, 0), (4, 32, 32, 3, 0), (4, 24, 0, 3, 0), (4, 24, 0, 4, 0),
+        for variant, th, fpu, stages, pf in ((4, 32, 0, 4, 0), (4, 32, 0, 3, 0), (4, 32, 0, 5, 0), (4, 32, 0, 6, 0), (4, 24, 0, 3, 0), (4, 24, 0, 4, 0),
                                              (4, 24, 0, 2, 0), (4, 16, 0, 4, 0), (3, 32, 16, 2, 0))[:1 if args.one else None]:
             ctx.set_option(ctx.OPT_MONO_VARIANT, variant)
             ctx.set_option(ctx.OPT_TMA_TILE_H, th)
@@ -83,7 +83,7 @@ def main() -> None:
         ctx.set_option(ctx.OPT_CTAS_PER_SM, 0)
         ctx.set_option(ctx.OPT_FRAMES_PER_UNIT, 16)
         ctx.set_option(ctx.OPT_FRAMES_PER_UNIT, 0)
-        ctx.set_option(ctx.OPT_STAGES, 4)
+        ctx.set_option(ctx.OPT_STAGES, 6)
         ctx.set_option(ctx.OPT_LUT_PREFETCH, 0)
         ctx.set_option(ctx.OPT_MONO_VARIANT, 4)
         ctx.set_option(ctx.OPT_TMA_TILE_H, 32)
