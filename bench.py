@@ -44,9 +44,9 @@ STREAMS = 2 * N_CAMERAS
 PX_PER_SET = STREAMS * W * H
 ALGO_BYTES_PER_PX = 2  # mono8 -> rectified mono8
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE rectify_mono_pair_kernel launch over 64 frame sets, from the
-# `ncu --set full` capture of this bench (profiles/r01_rect_v4_ncu_raw.txt): 578.83 MB + 485.25 MB
-NCU_TRAFFIC_BYTES_PER_FRAME_SET = (578.833152e6 + 485.247744e6) / 64
-KERNEL_BY_VARIANT = {4: "rectify_mono_pair_kernel<32,false>", 3: "rectify_mono_tma_kernel<32,false>", 2: "rectify_mono_kernel", 1: "rectify_tile_kernel<1>"}
+# `ncu --set full` capture of this bench (profiles/r01_rect_v4_ncu_raw.txt): 584.93 MB + 485.15 MB
+NCU_TRAFFIC_BYTES_PER_FRAME_SET = (584.931840e6 + 485.148160e6) / 64
+KERNEL_BY_VARIANT = {4: "rectify_mono_pair_kernel<32,false,1280>", 3: "rectify_mono_tma_kernel<32,false>", 2: "rectify_mono_kernel", 1: "rectify_tile_kernel<1>"}
 FALLBACK_HBM_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md fallback
 
 
