@@ -63,6 +63,8 @@ __device__ __forceinline__ uint32_t c3_pixel(p4_addr_t base, uint32_t m, uint32_
     return __byte_perm(__byte_perm(cr, cg, 0x0062), cb, 0x0610);
 }
 
+// DSTW > 0: the destination row pitch in pixels is this compile-time constant (row stores become immediate offsets).
+template <int DSTW>
 __global__ void __launch_bounds__(C3_THREADS, 3) rectify_c3_kernel(const __grid_constant__ Rect5Params P) {
     TI_DYNAMIC_SMEM(uint8_t, smem);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -173,7 +175,11 @@ __global__ void __launch_bounds__(C3_THREADS, 3) rectify_c3_kernel(const __grid_
                 uint32_t px[4];
 #pragma unroll
                 for (int j = 0; j < 4; ++j) px[j] = c3_pixel(base, mw[q][j], wt[q][j], wb[q][j]);
-                if (whole) {
+                if (whole && DSTW > 0) {
+                    c3_st32(dp + q * (DSTW * 3), __byte_perm(px[0], px[1], 0x4210));
+                    c3_st32(dp + q * (DSTW * 3) + 4, __byte_perm(px[1], px[2], 0x5421));
+                    c3_st32(dp + q * (DSTW * 3) + 8, __byte_perm(px[2], px[3], 0x6542));
+                } else if (whole) {
                     c3_st32(rp, __byte_perm(px[0], px[1], 0x4210));
                     c3_st32(rp + 4, __byte_perm(px[1], px[2], 0x5421));
                     c3_st32(rp + 8, __byte_perm(px[2], px[3], 0x6542));
@@ -205,10 +211,20 @@ int launch_rectify_c3(ti_ctx* ctx, Rect5Params& P) {
     P.stages = stages;
     const size_t smem = 256 + (size_t)stages * stage + C3_LUT_BYTES;
     if (smem > 220 * 1024) return fail(ctx, TI_EINVAL, "rectify (3-channel): source boxes of %d rows do not fit shared memory", P.rows_alloc_max);
+    typedef void (*Kern)(const Rect5Params);
+    Kern kern = rectify_c3_kernel<0>;
+    {  // every job of the launch writes rows of the same common pitch: immediate row offsets
+        int dw = P.job[0].dst_w;
+        for (int j = 1; j < P.n_jobs; ++j)
+            if (P.job[j].dst_w != dw) dw = 0;
+        if (dw == 1920) kern = rectify_c3_kernel<1920>;
+        else if (dw == 1280) kern = rectify_c3_kernel<1280>;
+        else if (dw == 640) kern = rectify_c3_kernel<640>;
+    }
 #ifndef TI_EMULATE
-    TI_CUDA(ctx, cudaFuncSetAttribute(rectify_c3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    TI_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 #endif
-    int per_sm = resident_ctas(rectify_c3_kernel, C3_THREADS, smem, 3);
+    int per_sm = resident_ctas(kern, C3_THREADS, smem, 3);
     if (ctx->ctas_per_sm > 0) per_sm = ctx->ctas_per_sm;
     const uint64_t grid_max = (uint64_t)ctx->sm_count * per_sm;
     // frames per unit: every unit costs one LUT fetch + expansion (measured: about one frame of work) and the CTAs of
@@ -223,7 +239,7 @@ int launch_rectify_c3(ti_ctx* ctx, Rect5Params& P) {
     P.frames_per_unit = std::max(1, std::min(P.n_batch, fpu));
     const uint64_t total = (uint64_t)P.tiles_per_set * ((P.n_batch + P.frames_per_unit - 1) / P.frames_per_unit);
     const int grid = (int)std::min<uint64_t>(total, grid_max);
-    TI_LAUNCH(rectify_c3_kernel, grid, C3_THREADS, smem, ctx->stream, P);
+    TI_LAUNCH(kern, grid, C3_THREADS, smem, ctx->stream, P);
     TI_CHECK_LAUNCH(ctx);
     return TI_OK;
 }
