@@ -16,7 +16,11 @@
 //    LUT) line the six bytes up, two PRMT with fixed selectors regroup them as (B0 B1 G0 G1) and (R0 R1 . .), and
 //    each channel is two IDP.2A against the pixel's 16-bit 2-D weights - result 64*(S+512), the channel value is
 //    byte 2.  No pixel depends on a neighbour, so there are no exceptions to fix up;
-//  * a lane owns 4 consecutive pixels = 12 output bytes (R G B order), written as three 32-bit streaming stores.
+//  * for the window loads lane L of a warp takes pixels L, L+32, L+64, L+96 of a tile row: the 32 windows of one load
+//    instruction then cover ~100 consecutive source bytes (<= 32 distinct words: no bank conflicts - with 4 consecutive
+//    pixels per lane the windows are 3 words apart and 57 % of the shared-memory wavefronts were conflict replays);
+//    the results cross a 512-byte per-warp buffer so that for the stores a lane owns 4 consecutive pixels = 12 output
+//    bytes (R G B order), written as three 32-bit streaming stores.
 #include "ti_rectify_pair.cuh"
 #include "ti_pair_dev.cuh"
 
@@ -76,6 +80,7 @@ __global__ void __launch_bounds__(C3_THREADS, 3) rectify_c3_kernel(const __grid_
     uint64_t* lut_empty = lut_full + 1;                  // every consumer warp has expanded its part of the slice
     uint8_t* stage0 = smem + 256;
     uint8_t* lutbuf = stage0 + (size_t)S * stage_bytes;
+    // after the LUT slice: one 512-byte transpose buffer per consumer warp
 
     if (tid == 0) {
         for (int s = 0; s < S; ++s) {
@@ -133,12 +138,13 @@ __global__ void __launch_bounds__(C3_THREADS, 3) rectify_c3_kernel(const __grid_
         return;
     }
     // ---------------------------------------------------- consumers ---------------------------------
-    // Lane L owns pixels 4L .. 4L+3 of each of its warp's C3_RPW tile rows.
+    // Lane L blends pixels L, L+32, L+64, L+96 of each of its warp's C3_RPW tile rows and stores pixels 4L .. 4L+3.
     uint32_t mw[C3_RPW][4], wt[C3_RPW][4], wb[C3_RPW][4];
     const p4_addr_t sm0 = p4_addr(smem);
     const p4_addr_t stage_first = sm0 + 256;
     p4_addr_t base = stage_first, bar = sm0;  // current stage, its `full` barrier (`empty` is 64 bytes further)
     int s_left = S;                            // stages until the ring wraps
+    uint32_t* const tbuf = reinterpret_cast<uint32_t*>(lutbuf + C3_LUT_BYTES) + warp * 128;  // this warp's transpose buffer
     uint32_t phase = 0;
     for (uint32_t k = 0; k < units_mine; ++k) {
         const C3Unit U = c3_unit(P, k);
@@ -173,8 +179,14 @@ __global__ void __launch_bounds__(C3_THREADS, 3) rectify_c3_kernel(const __grid_
 #pragma unroll
             for (int q = 0; q < C3_RPW; ++q) {
                 uint32_t px[4];
+                __syncwarp();  // the previous row's reads of the transpose buffer are done
 #pragma unroll
-                for (int j = 0; j < 4; ++j) px[j] = c3_pixel(base, mw[q][j], wt[q][j], wb[q][j]);
+                for (int j = 0; j < 4; ++j) tbuf[32 * j + lane] = c3_pixel(base, mw[q][j], wt[q][j], wb[q][j]);  // pixel 32j + lane
+                __syncwarp();
+                {
+                    const uint4 t4 = *reinterpret_cast<const uint4*>(tbuf + 4 * lane);  // pixels 4 lane .. 4 lane + 3
+                    px[0] = t4.x; px[1] = t4.y; px[2] = t4.z; px[3] = t4.w;
+                }
                 if (whole && DSTW > 0) {
                     c3_st32(dp + q * (DSTW * 3), __byte_perm(px[0], px[1], 0x4210));
                     c3_st32(dp + q * (DSTW * 3) + 4, __byte_perm(px[1], px[2], 0x5421));
@@ -207,9 +219,10 @@ int launch_rectify_c3(ti_ctx* ctx, Rect5Params& P) {
     if (P.n_jobs == 0 || P.n_batch <= 0) return TI_OK;
     const size_t stage = (size_t)P.rows_alloc_max * C3_PITCH;
     int stages = std::max(2, std::min(ctx->stages4, C3_MAX_STAGES));
-    while (stages > 2 && (256 + (size_t)stages * stage + C3_LUT_BYTES + 1024) * 3 > 228 * 1024) --stages;
+    const size_t tail = C3_LUT_BYTES + (size_t)C3_CONSUMER_WARPS * 512;  // LUT slice + per-warp transpose buffers
+    while (stages > 2 && (256 + (size_t)stages * stage + tail + 1024) * 3 > 228 * 1024) --stages;
     P.stages = stages;
-    const size_t smem = 256 + (size_t)stages * stage + C3_LUT_BYTES;
+    const size_t smem = 256 + (size_t)stages * stage + tail;
     if (smem > 220 * 1024) return fail(ctx, TI_EINVAL, "rectify (3-channel): source boxes of %d rows do not fit shared memory", P.rows_alloc_max);
     typedef void (*Kern)(const Rect5Params);
     Kern kern = rectify_c3_kernel<0>;
@@ -289,7 +302,8 @@ int build_c3_tables(ti_ctx* ctx, CameraSlot& C) {
                     const uint32_t fx = (e >> 22) & 31u, fy = e >> 27;
                     const int bp = 3 * x0 - c0, wordx = bp & ~3, s = bp & 3;
                     const uint32_t off = (uint32_t)((y0 - by0) * C3_PITCH + wordx);
-                    uint32_t* w = lut5.data() + (tile * C3_TH + row) * C3_LUT_ROW_WORDS + (size_t)lu * 2;
+                    // lane (lu % 32) blends pixel lu as its (lu / 32)-th: its eight LUT words are contiguous
+                    uint32_t* w = lut5.data() + (tile * C3_TH + row) * C3_LUT_ROW_WORDS + (size_t)((lu & 31) * 4 + (lu >> 5)) * 2;
                     w[0] = (off << 16) | (uint32_t)(8 * s);
                     w[1] = (32u - fx) | (fy << 6) | ((fx == 0 && fy == 0 ? 1u : 0u) << 11) | (fx << 16);  // see p4_expand
                 }
