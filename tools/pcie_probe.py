@@ -18,31 +18,37 @@ def main() -> None:
     ap = argparse.ArgumentParser()
     ap.add_argument("--mb", type=int, default=256)
     ap.add_argument("--iters", type=int, default=10)
+    ap.add_argument("--pieces", type=int, default=1, help="split every copy into this many back-to-back pieces")
+    ap.add_argument("--streams", type=int, default=1, help="round-robin the pieces of one direction over this many streams")
     args = ap.parse_args()
     n = args.mb << 20
     h_in = torch.empty(n, dtype=torch.uint8).pin_memory()
     h_out = torch.empty(n, dtype=torch.uint8).pin_memory()
     d_a = torch.empty(n, dtype=torch.uint8, device="cuda")
     d_b = torch.empty(n, dtype=torch.uint8, device="cuda")
-    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    up = [torch.cuda.Stream() for _ in range(args.streams)]
+    down = [torch.cuda.Stream() for _ in range(args.streams)]
+    step = n // args.pieces
 
     def run(h2d: bool, d2h: bool) -> float:
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         for _ in range(args.iters):
-            if h2d:
-                with torch.cuda.stream(s1):
-                    d_a.copy_(h_in, non_blocking=True)
-            if d2h:
-                with torch.cuda.stream(s2):
-                    h_out.copy_(d_b, non_blocking=True)
+            for k in range(args.pieces):
+                sl = slice(k * step, (k + 1) * step)
+                if h2d:
+                    with torch.cuda.stream(up[k % args.streams]):
+                        d_a[sl].copy_(h_in[sl], non_blocking=True)
+                if d2h:
+                    with torch.cuda.stream(down[k % args.streams]):
+                        h_out[sl].copy_(d_b[sl], non_blocking=True)
         torch.cuda.synchronize()
         return (time.perf_counter() - t0) / args.iters
 
     for name, a, b in (("H2D alone", True, False), ("D2H alone", False, True), ("H2D + D2H concurrently", True, True)):
         run(a, b)
         dt = run(a, b)
-        print(f"{name:26s} {n / dt / 1e9:7.1f} GB/s per direction ({args.mb} MB per copy, {dt * 1e3:.2f} ms)")
+        print(f"{name:26s} {n / dt / 1e9:7.1f} GB/s per direction ({args.mb} MB in {args.pieces} piece(s) over {args.streams} stream(s), {dt * 1e3:.2f} ms)")
 
 
 if __name__ == "__main__":
