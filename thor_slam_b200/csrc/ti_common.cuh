@@ -222,19 +222,50 @@ void set_global_error(const char* msg);
     } while (0)
 #endif
 
-// Resident CTAs per SM of a persistent kernel (cached per kernel): grids are sized to exactly one wave.
+// Resident CTAs per SM of a persistent kernel: grids are sized to exactly one wave.  The last answer per
+// (kernel, threads, shared memory) is remembered - the query costs microseconds that matter for one-frame-set calls.
 template <typename K>
 inline int resident_ctas(K kernel, int threads, size_t dyn_smem, int fallback) {
 #ifdef TI_EMULATE
     (void)kernel; (void)threads; (void)dyn_smem;
     return fallback > 2 ? 2 : fallback;
 #else
+    struct Memo { const void* k; int threads; size_t smem; int n; };
+    static thread_local Memo memo[8] = {};
+    static thread_local int next = 0;
+    const void* key = reinterpret_cast<const void*>(kernel);
+    for (const Memo& m : memo)
+        if (m.k == key && m.threads == threads && m.smem == dyn_smem) return m.n;
     int n = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, threads, dyn_smem) != cudaSuccess || n <= 0) {
         cudaGetLastError();
         return fallback;
     }
+    memo[next] = Memo{key, threads, dyn_smem, n};
+    next = (next + 1) % 8;
     return n;
+#endif
+}
+
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) only when the kernel needs more than it was last given
+template <typename K>
+inline cudaError_t ensure_dynamic_smem(K kernel, size_t dyn_smem, int device) {
+#ifdef TI_EMULATE
+    (void)kernel; (void)dyn_smem; (void)device;
+    return cudaSuccess;
+#else
+    struct Memo { const void* k; size_t smem; int device; };
+    static thread_local Memo memo[16] = {};
+    const void* key = reinterpret_cast<const void*>(kernel);
+    Memo* slot = nullptr;
+    for (Memo& m : memo) {
+        if (m.k == key && m.device == device) { slot = &m; break; }
+        if (!m.k && !slot) slot = &m;
+    }
+    if (slot && slot->k == key && slot->smem >= dyn_smem) return cudaSuccess;
+    const cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_smem);
+    if (e == cudaSuccess && slot) { slot->k = key; slot->smem = dyn_smem; slot->device = device; }
+    return e;
 #endif
 }
 

@@ -234,9 +234,7 @@ int launch_rectify_c3(ti_ctx* ctx, Rect5Params& P) {
         else if (dw == 1280) kern = rectify_c3_kernel<1280>;
         else if (dw == 640) kern = rectify_c3_kernel<640>;
     }
-#ifndef TI_EMULATE
-    TI_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-#endif
+    TI_CUDA(ctx, ensure_dynamic_smem(kern, smem, ctx->device));
     int per_sm = resident_ctas(kern, C3_THREADS, smem, 3);
     if (ctx->ctas_per_sm > 0) per_sm = ctx->ctas_per_sm;
     const uint64_t grid_max = (uint64_t)ctx->sm_count * per_sm;

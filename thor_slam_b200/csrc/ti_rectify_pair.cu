@@ -293,9 +293,7 @@ int launch_rectify_pair(ti_ctx* ctx, Rect4Params& P, int th_index) {
     P.stages = stages;
     P.debug = ctx->debug;
     const size_t smem = 256 + (size_t)stages * stage + lut_bytes;
-#ifndef TI_EMULATE
-    TI_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-#endif
+    TI_CUDA(ctx, ensure_dynamic_smem(kern, smem, ctx->device));
     int per_sm = resident_ctas(kern, P4_THREADS, smem, 3);
     if (ctx->ctas_per_sm > 0) per_sm = ctx->ctas_per_sm;
     const uint64_t grid_max = (uint64_t)ctx->sm_count * per_sm;

@@ -8,6 +8,7 @@ the C ABI.  Error mapping follows the reference's conventions (SURVEY.md section
 from __future__ import annotations
 
 import ctypes as C
+import math
 from dataclasses import dataclass
 from typing import Any, Sequence
 
@@ -101,8 +102,8 @@ class IngestContext:
     def _batch_stride(x: Any) -> int:
         """Bytes between consecutive frames (dimension 0) of a batched array."""
         if _is_torch(x):
-            return x.stride(0) * x.element_size() if x.dim() > 0 and x.shape[0] > 1 else int(np.prod(x.shape[1:])) * x.element_size()
-        return x.strides[0] if x.ndim > 0 and x.shape[0] > 1 else int(np.prod(x.shape[1:])) * x.itemsize
+            return x.stride(0) * x.element_size() if x.dim() > 0 and x.shape[0] > 1 else math.prod(x.shape[1:]) * x.element_size()
+        return x.strides[0] if x.ndim > 0 and x.shape[0] > 1 else math.prod(x.shape[1:]) * x.itemsize
 
     def set_stream(self, cuda_stream: int | None) -> None:
         """``cuda_stream``: e.g. ``torch.cuda.current_stream().cuda_stream`` (``None``/0: legacy default)."""
