@@ -39,7 +39,6 @@
 #include "ti_rectify_pair.cuh"
 #include "ti_pair_dev.cuh"
 
-#include <cstdlib>
 #include <cstring>
 
 namespace ti {
@@ -277,8 +276,7 @@ int launch_rectify_pair(ti_ctx* ctx, Rect4Params& P, int th_index) {
         {rectify_mono_pair_kernel<16, true>, rectify_mono_pair_kernel<32, true>, rectify_mono_pair_kernel<24, true>}};
     Kern kern = kernels[ctx->debug ? 1 : 0][th_index];
     // every job of the launch writes rows of the same common pitch: use the kernel whose row stores are immediate offsets
-    static const bool no_dstw = getenv("TI_NO_DSTW") != nullptr;  // A/B switch for measurements
-    if (!ctx->debug && TH == 32 && !no_dstw) {
+    if (!ctx->debug && TH == 32) {
         int dw = P.job[0].dst_w;
         for (int j = 1; j < P.n_jobs; ++j)
             if (P.job[j].dst_w != dw) dw = 0;
