@@ -188,6 +188,15 @@ int ti_ingest(ti_ctx* ctx, const ti_stream* streams, int n_streams, int n_batch)
  * time on internal streams; returns after everything has landed in the dst buffers. */
 int ti_ingest_host(ti_ctx* ctx, const ti_stream* streams, int n_streams, int n_batch, int chunk);
 
+/* The same call split in two, for callers that stream batch after batch (a capture loop double-buffering its
+ * host frames): submit enqueues the batch behind whatever was submitted before and returns at once with a
+ * ticket; wait blocks until that batch has landed in its dst buffers.  Uploads of batch k+1 overlap downloads
+ * of batch k.  The host buffers of a batch belong to the library from submit until its wait returns; at most 8
+ * tickets may be outstanding (a ninth submit waits for the oldest).  Same role as above: get_synchronized_frames()
+ * (thor_slam/camera/rig.py:358-415) called in a loop by SlamEngine.process_frame (thor_slam/slam/interface.py). */
+int ti_ingest_host_submit(ti_ctx* ctx, const ti_stream* streams, int n_streams, int n_batch, int chunk, uint64_t* ticket);
+int ti_ingest_host_wait(ti_ctx* ctx, uint64_t ticket);
+
 /* ---- multi-GPU: one process per GPU ------------------------------------------------------ */
 
 /* NCCL is dlopen()ed on first use.  id: 128 bytes, created on rank 0, shipped by the caller

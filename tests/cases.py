@@ -145,3 +145,51 @@ def check_backproject(be, cam: int, w: int, h: int, n: int = 2, seed: int = 2, r
         assert np.array_equal(gm[i], msk)
         assert int(gc[i]) == cnt
         assert not np.any(gx[i][msk == 0]), "invalid pixels must be written as (0,0,0)"
+
+
+def check_host_pipeline(be, cam: int, w: int, h: int, batches: list[int], chunk: int, pinned: bool, submit: bool) -> None:
+    """Host buffers in, host buffers out (``ti_ingest_host`` / ``ti_ingest_host_submit`` + ``_wait``): one rectify and
+    one back-projection stream per batch; with ``submit`` every batch is enqueued before the first wait."""
+    rng = np.random.default_rng(10 + cam)
+    s, maps = stereo_maps(w, h, seed=10)
+    be.ctx.upload_rectify_map(cam, *maps[0], (w, h))
+    intr = s.get_intrinsics()[0]
+    m = conv.body_T_camera(None, s.get_extrinsics()[0].to_4x4_matrix(), "rdf")
+    be.ctx.upload_projection(cam, intr.matrix, m, (w, h))
+
+    def host(a: np.ndarray):
+        if not pinned:
+            return a
+        import torch
+
+        return torch.from_numpy(a).pin_memory()
+
+    def view(x) -> np.ndarray:
+        return x if isinstance(x, np.ndarray) else x.numpy()
+
+    jobs = []
+    for n in batches:
+        left = host(make_batch(rng, "mono8", w, h, n))
+        depth_np = np.stack([make_depth(rng, w, h) for _ in range(n)]) if n else np.zeros((0, h, w), np.uint16)
+        depth = host(depth_np.view(np.int16))
+        out = dict(o_l=host(np.zeros((n, h, w), np.uint8)), xyz=host(np.zeros((n, h, w, 3), np.float32)),
+                   mask=host(np.zeros((n, h, w), np.uint8)), count=host(np.zeros((n,), np.int32)))
+        specs = [
+            StreamSpec(F.KIND_RECTIFY, left, out["o_l"], F.MONO8, F.MONO8, camera=cam),
+            StreamSpec(F.KIND_BACKPROJECT, depth, out["xyz"], F.DEPTH16, F.XYZ32F, camera=cam, mask=out["mask"], count=out["count"]),
+        ]
+        jobs.append((n, left, depth_np, out, specs))
+    if submit:
+        tickets = [be.ctx.ingest_host_submit(j[4], chunk=chunk) for j in jobs]
+        assert all(b > a for a, b in zip(tickets, tickets[1:])) or len(set(tickets)) == 1 == len(tickets)
+        for t in reversed(tickets):  # waiting out of order is allowed
+            be.ctx.ingest_host_wait(t)
+    else:
+        for j in jobs:
+            be.ctx.ingest_host(j[4], chunk=chunk)
+    for n, left, depth_np, out, _ in jobs:
+        for i in range(n):
+            assert np.array_equal(view(out["o_l"])[i], orc.remap_cv(view(left)[i], *maps[0]))
+            pts, msk, cnt = ob.backproject(depth_np[i], intr.matrix, m)
+            assert ob.points_close(view(out["xyz"])[i], pts)[0]
+            assert np.array_equal(view(out["mask"])[i], msk) and int(view(out["count"])[i]) == cnt

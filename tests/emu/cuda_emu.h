@@ -246,6 +246,7 @@ inline cudaError_t emu_props(cudaDeviceProp* p) {
 #define cudaStreamWaitEvent(s, e, f) ti_emu::ok()
 #define cudaEventCreateWithFlags(e, f) (*(e) = nullptr, cudaSuccess)
 #define cudaEventRecord(e, s) ti_emu::ok()
+#define cudaEventSynchronize(e) ti_emu::ok()
 #define cudaEventDestroy(e) ti_emu::ok()
 #define cudaDeviceSynchronize() ti_emu::ok()
 #define cudaGetLastError() ti_emu::ok()

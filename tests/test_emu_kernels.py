@@ -69,6 +69,12 @@ def test_backproject_extremes(emu_backend):
     cases.check_backproject(emu_backend, 6, 64, 16, depth=depth)
 
 
+@pytest.mark.parametrize("submit", [False, True])
+def test_host_pipeline_chunk_schedule(emu_backend, submit):
+    """ti_ingest_host / _submit / _wait: ramped, ragged and empty batches through the three chunk slots."""
+    cases.check_host_pipeline(emu_backend, 44, 64, 32, [13, 0, 2, 7] if submit else [13, 2], 4, pinned=False, submit=submit)
+
+
 def test_errors(emu_backend):
     ctx = emu_backend.ctx
     a = np.zeros((1, 8, 16), np.uint8)

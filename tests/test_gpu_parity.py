@@ -176,35 +176,22 @@ def test_ingest_fused_matches_single_calls(gpu_backend):
         assert ob.points_close(gx[i], pts)[0] and np.array_equal(gm[i], msk) and int(gc[i]) == cnt
 
 
-@pytest.mark.parametrize("n,chunk", [(7, 3), (21, 8), (2, 8)])
+@pytest.mark.parametrize("n,chunk", [(7, 3), (21, 8), (2, 8), (24, 8)])
 def test_ingest_host_pipeline(gpu_backend, n, chunk):
     """Host buffers in, host buffers out, chunked H2D / kernels / D2H; ramped and ragged chunks."""
-    import torch
+    cases.check_host_pipeline(gpu_backend, 42, 640, 400, [n], chunk, pinned=True, submit=False)
 
-    be = gpu_backend
-    w, h = 640, 400
-    rng = np.random.default_rng(10)
-    s, maps = cases.stereo_maps(w, h, seed=10)
-    be.ctx.upload_rectify_map(42, *maps[0], (w, h))
-    intr = s.get_intrinsics()[0]
-    m = conv.body_T_camera(None, s.get_extrinsics()[0].to_4x4_matrix(), "rdf")
-    be.ctx.upload_projection(42, intr.matrix, m, (w, h))
-    left = torch.from_numpy(cases.make_batch(rng, "mono8", w, h, n)).pin_memory()
-    depth_np = np.stack([make_depth(rng, w, h) for _ in range(n)])
-    depth = torch.from_numpy(depth_np.view(np.int16)).pin_memory()
-    o_l = torch.zeros((n, h, w), dtype=torch.uint8).pin_memory()
-    xyz = torch.zeros((n, h, w, 3), dtype=torch.float32).pin_memory()
-    mask = torch.zeros((n, h, w), dtype=torch.uint8).pin_memory()
-    count = torch.zeros((n,), dtype=torch.int32).pin_memory()
-    be.ctx.ingest_host([
-        StreamSpec(F.KIND_RECTIFY, left, o_l, F.MONO8, F.MONO8, camera=42),
-        StreamSpec(F.KIND_BACKPROJECT, depth, xyz, F.DEPTH16, F.XYZ32F, camera=42, mask=mask, count=count),
-    ], chunk=chunk)
-    for i in range(n):
-        assert np.array_equal(o_l[i].numpy(), orc.remap_cv(left[i].numpy(), *maps[0]))
-        pts, msk, cnt = ob.backproject(depth_np[i], intr.matrix, m)
-        assert ob.points_close(xyz[i].numpy(), pts)[0]
-        assert np.array_equal(mask[i].numpy(), msk) and int(count[i]) == cnt
+
+@pytest.mark.parametrize("batches,chunk", [([5, 9, 3], 4), ([2] * 11, 2), ([8, 0, 8], 8)])
+def test_ingest_host_submit_wait(gpu_backend, batches, chunk):
+    """Several batches in flight at once (more than the ticket ring holds in the second case); waits out of order."""
+    cases.check_host_pipeline(gpu_backend, 43, 640, 400, batches, chunk, pinned=True, submit=True)
+
+
+def test_ingest_host_wait_errors(gpu_backend):
+    gpu_backend.ctx.ingest_host_wait(0)  # the ticket of an empty submission
+    with pytest.raises(ValueError):
+        gpu_backend.ctx.ingest_host_wait(1 << 40)
 
 
 def test_errors(gpu_backend):

@@ -95,9 +95,12 @@ int ti_destroy(ti_ctx* ctx) {
         if (h.exec_done) cudaEventDestroy(h.exec_done);
         if (h.d2h_done) cudaEventDestroy(h.d2h_done);
     }
-    if (ctx->s_h2d) cudaStreamDestroy(ctx->s_h2d);
-    if (ctx->s_d2h) cudaStreamDestroy(ctx->s_d2h);
-    if (ctx->s_exec) cudaStreamDestroy(ctx->s_exec);
+    if (ctx->host_ready) {
+        for (auto& ev : ctx->ticket_done) cudaEventDestroy(ev);
+        cudaStreamDestroy(ctx->s_h2d);
+        cudaStreamDestroy(ctx->s_d2h);
+        cudaStreamDestroy(ctx->s_exec);
+    }
     ti_nccl_teardown(ctx);
     delete ctx;
     return TI_OK;
@@ -524,9 +527,10 @@ static int ensure_cap(ti_ctx* ctx, void** p, size_t* cap, size_t need) {
     return TI_OK;
 }
 
-int ti_ingest_host(ti_ctx* ctx, const ti_stream* streams, int n_streams, int n_batch, int chunk) {
-    if (!ctx) return TI_EINVAL;
-    if (n_batch < 0 || n_streams < 0 || (n_streams && !streams)) return fail(ctx, TI_EINVAL, "ti_ingest_host: bad arguments");
+// Enqueues one host-buffer call on the pipeline streams.  Chunks are numbered over the life of the context, so the
+// three buffer slots and their events carry over from one call to the next and consecutive submissions overlap.
+static int host_enqueue(ti_ctx* ctx, const ti_stream* streams, int n_streams, int n_batch, int chunk, bool ramp, const char* who) {
+    if (n_batch < 0 || n_streams < 0 || (n_streams && !streams)) return fail(ctx, TI_EINVAL, "%s: bad arguments", who);
     if (n_batch == 0 || n_streams == 0) return TI_OK;
     if (chunk <= 0) chunk = 1;
     chunk = std::min(chunk, n_batch);
@@ -538,7 +542,7 @@ int ti_ingest_host(ti_ctx* ctx, const ti_stream* streams, int n_streams, int n_b
             return fail(ctx, TI_ESTATE, "stream %d: camera slot %d not uploaded", i, S.camera);
         if (!S.src || !S.dst) return fail(ctx, TI_EINVAL, "stream %d: null src/dst", i);
     }
-    if (!ctx->s_h2d) {
+    if (!ctx->host_ready) {
         TI_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->s_h2d, cudaStreamNonBlocking));
         TI_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->s_d2h, cudaStreamNonBlocking));
         TI_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->s_exec, cudaStreamNonBlocking));
@@ -547,6 +551,8 @@ int ti_ingest_host(ti_ctx* ctx, const ti_stream* streams, int n_streams, int n_b
             TI_CUDA(ctx, cudaEventCreateWithFlags(&h.exec_done, cudaEventDisableTiming));
             TI_CUDA(ctx, cudaEventCreateWithFlags(&h.d2h_done, cudaEventDisableTiming));
         }
+        for (auto& ev : ctx->ticket_done) TI_CUDA(ctx, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        ctx->host_ready = true;
     }
     // device staging: tightly packed frames, `chunk` per stream per slot
     std::vector<uint64_t> sb(n_streams), db(n_streams), mb(n_streams);
@@ -555,42 +561,59 @@ int ti_ingest_host(ti_ctx* ctx, const ti_stream* streams, int n_streams, int n_b
         db[i] = (stream_dst_bytes(ctx, streams[i]) + 15) & ~15ull;
         mb[i] = (stream_mask_bytes(ctx, streams[i]) + 15) & ~15ull;
     }
+    bool grow = false;
     for (auto& h : ctx->hslot) {
-        h.d_src.resize(n_streams, nullptr); h.d_dst.resize(n_streams, nullptr); h.d_mask.resize(n_streams, nullptr);
-        h.d_count.resize(n_streams, nullptr);
-        h.cap_src.resize(n_streams, 0); h.cap_dst.resize(n_streams, 0); h.cap_mask.resize(n_streams, 0); h.cap_count.resize(n_streams, 0);
-        for (int i = 0; i < n_streams; ++i) {
-            int r;
-            if ((r = ensure_cap(ctx, &h.d_src[i], &h.cap_src[i], sb[i] * chunk)) != TI_OK) return r;
-            if ((r = ensure_cap(ctx, &h.d_dst[i], &h.cap_dst[i], db[i] * chunk)) != TI_OK) return r;
-            if ((r = ensure_cap(ctx, &h.d_mask[i], &h.cap_mask[i], mb[i] * chunk)) != TI_OK) return r;
+        if ((int)h.d_src.size() < n_streams) { grow = true; break; }
+        for (int i = 0; i < n_streams && !grow; ++i) {
             const size_t cb = (streams[i].kind == TI_KIND_BACKPROJECT && streams[i].count) ? sizeof(uint32_t) * chunk : 0;
-            if ((r = ensure_cap(ctx, (void**)&h.d_count[i], &h.cap_count[i], cb)) != TI_OK) return r;
+            grow = h.cap_src[i] < sb[i] * chunk || h.cap_dst[i] < db[i] * chunk || h.cap_mask[i] < mb[i] * chunk || h.cap_count[i] < cb;
+        }
+    }
+    if (grow) {
+        // buffers of earlier submissions may still be in flight
+        TI_CUDA(ctx, cudaStreamSynchronize(ctx->s_d2h));
+        TI_CUDA(ctx, cudaStreamSynchronize(ctx->s_exec));
+        TI_CUDA(ctx, cudaStreamSynchronize(ctx->s_h2d));
+        for (auto& h : ctx->hslot) {
+            if ((int)h.d_src.size() < n_streams) {
+                h.d_src.resize(n_streams, nullptr); h.d_dst.resize(n_streams, nullptr); h.d_mask.resize(n_streams, nullptr);
+                h.d_count.resize(n_streams, nullptr);
+                h.cap_src.resize(n_streams, 0); h.cap_dst.resize(n_streams, 0); h.cap_mask.resize(n_streams, 0); h.cap_count.resize(n_streams, 0);
+            }
+            for (int i = 0; i < n_streams; ++i) {
+                int r;
+                if ((r = ensure_cap(ctx, &h.d_src[i], &h.cap_src[i], sb[i] * chunk)) != TI_OK) return r;
+                if ((r = ensure_cap(ctx, &h.d_dst[i], &h.cap_dst[i], db[i] * chunk)) != TI_OK) return r;
+                if ((r = ensure_cap(ctx, &h.d_mask[i], &h.cap_mask[i], mb[i] * chunk)) != TI_OK) return r;
+                const size_t cb = (streams[i].kind == TI_KIND_BACKPROJECT && streams[i].count) ? sizeof(uint32_t) * chunk : 0;
+                if ((r = ensure_cap(ctx, (void**)&h.d_count[i], &h.cap_count[i], cb)) != TI_OK) return r;
+            }
         }
     }
     cudaStream_t user_stream = ctx->stream;
     int rc = TI_OK;
-    // Chunk schedule: the call returns only when everything has landed, so the first upload and the last
-    // download are not overlapped with anything - keep those chunks small (chunk/4, chunk/2, chunk, ..., chunk/2, chunk/4).
+    // Chunk schedule.  A call that returns only when everything has landed has its first upload and its last download
+    // overlapped with nothing - one half-size chunk at either end keeps them short.  (Smaller pieces cost more than
+    // they save: a host<->device copy carries ~15 us of fixed cost, tools/pcie_probe.py.)  Submissions that overlap
+    // their neighbours need no ramp.
     std::vector<int> sizes;
     {
         int left = n_batch;
-        std::vector<int> tail;
-        for (int ramp = std::max(1, chunk / 4); ramp < chunk && left > 2 * chunk; ramp *= 2) {
-            sizes.push_back(ramp); left -= ramp;
-            tail.push_back(ramp); left -= ramp;
-        }
+        const int half = chunk / 2;
+        ramp = ramp && half >= 1 && n_batch >= 3 * chunk;
+        if (ramp) { sizes.push_back(half); left -= 2 * half; }
         while (left > 0) { const int nb = std::min(chunk, left); sizes.push_back(nb); left -= nb; }
-        sizes.insert(sizes.end(), tail.rbegin(), tail.rend());
+        if (ramp) sizes.push_back(half);
     }
     const int n_chunks = (int)sizes.size();
     int b_next = 0;
     for (int c = 0; c < n_chunks && rc == TI_OK; ++c) {
-        auto& h = ctx->hslot[c % 3];
+        const uint64_t g = ctx->host_chunks++;
+        auto& h = ctx->hslot[g % 3];
         const int b0 = b_next, nb = sizes[c];
         b_next += nb;
         // the slot's previous D2H must have drained before its buffers are overwritten
-        if (c >= 3) {
+        if (g >= 3) {
             cudaStreamWaitEvent(ctx->s_h2d, h.d2h_done, 0);
             cudaStreamWaitEvent(ctx->s_exec, h.d2h_done, 0);
         }
@@ -636,13 +659,55 @@ int ti_ingest_host(ti_ctx* ctx, const ti_stream* streams, int n_streams, int n_b
         }
         cudaEventRecord(h.d2h_done, ctx->s_d2h);
     }
+    return rc;
+}
+
+static int host_drain(ti_ctx* ctx, const char* who) {
+    if (!ctx->host_ready) return TI_OK;
     cudaError_t e1 = cudaStreamSynchronize(ctx->s_d2h);
     cudaError_t e2 = cudaStreamSynchronize(ctx->s_exec);
     cudaError_t e3 = cudaStreamSynchronize(ctx->s_h2d);
-    if (rc != TI_OK) return rc;
     cudaError_t e = e1 != cudaSuccess ? e1 : (e2 != cudaSuccess ? e2 : e3);
     if (e == cudaSuccess) e = cudaGetLastError();
-    if (e != cudaSuccess) return fail(ctx, TI_ECUDA, "ti_ingest_host: %s", cudaGetErrorString(e));
+    if (e != cudaSuccess) return fail(ctx, TI_ECUDA, "%s: %s", who, cudaGetErrorString(e));
+    return TI_OK;
+}
+
+int ti_ingest_host(ti_ctx* ctx, const ti_stream* streams, int n_streams, int n_batch, int chunk) {
+    if (!ctx) return TI_EINVAL;
+    const int rc = host_enqueue(ctx, streams, n_streams, n_batch, chunk, /*ramp=*/true, "ti_ingest_host");
+    const int rd = host_drain(ctx, "ti_ingest_host");
+    return rc != TI_OK ? rc : rd;
+}
+
+int ti_ingest_host_submit(ti_ctx* ctx, const ti_stream* streams, int n_streams, int n_batch, int chunk, uint64_t* ticket) {
+    if (!ctx) return TI_EINVAL;
+    if (!ticket) return fail(ctx, TI_EINVAL, "ti_ingest_host_submit: null ticket");
+    constexpr uint64_t kRing = sizeof(ctx->ticket_done) / sizeof(ctx->ticket_done[0]);
+    const uint64_t t = ctx->host_tickets + 1;
+    // the event of ticket t - kRing is about to be reused
+    if (ctx->host_ready && t > kRing) TI_CUDA(ctx, cudaEventSynchronize(ctx->ticket_done[t % kRing]));
+    const int rc = host_enqueue(ctx, streams, n_streams, n_batch, chunk, /*ramp=*/false, "ti_ingest_host_submit");
+    if (rc != TI_OK) { host_drain(ctx, "ti_ingest_host_submit"); return rc; }
+    if (!ctx->host_ready) {  // empty submission before any stream exists: nothing to wait for
+        *ticket = 0;
+        return TI_OK;
+    }
+    TI_CUDA(ctx, cudaEventRecord(ctx->ticket_done[t % kRing], ctx->s_d2h));
+    ctx->host_tickets = t;
+    *ticket = t;
+    return TI_OK;
+}
+
+int ti_ingest_host_wait(ti_ctx* ctx, uint64_t ticket) {
+    if (!ctx) return TI_EINVAL;
+    if (ticket == 0) return TI_OK;
+    if (ticket > ctx->host_tickets) return fail(ctx, TI_EINVAL, "ti_ingest_host_wait: ticket %llu was never issued", (unsigned long long)ticket);
+    constexpr uint64_t kRing = sizeof(ctx->ticket_done) / sizeof(ctx->ticket_done[0]);
+    if (ctx->host_tickets - ticket >= kRing) return TI_OK;  // its event was waited for before being reused
+    cudaError_t e = cudaEventSynchronize(ctx->ticket_done[ticket % kRing]);
+    if (e == cudaSuccess) e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(ctx, TI_ECUDA, "ti_ingest_host_wait: %s", cudaGetErrorString(e));
     return TI_OK;
 }
 

@@ -189,6 +189,10 @@ struct ti_ctx {
         std::vector<size_t> cap_src, cap_dst, cap_mask, cap_count;
         cudaEvent_t h2d_done = nullptr, exec_done = nullptr, d2h_done = nullptr;
     } hslot[3];  // three chunk slots in flight: upload / kernels / download of consecutive chunks never share buffers
+    bool host_ready = false;     // streams and events below exist
+    uint64_t host_chunks = 0;    // chunks enqueued so far; chunk g uses slot g % 3
+    uint64_t host_tickets = 0;   // submissions so far (ti_ingest_host_submit); ticket t completes at ticket_done[t % 8]
+    cudaEvent_t ticket_done[8] = {};
     // NCCL (dlopen)
     void* nccl_comm = nullptr;
     int rank = 0, world = 1;

@@ -250,6 +250,21 @@ class IngestContext:
         arr, n_batch = self._pack(streams, host=True)
         self._check(self.lib.ti_ingest_host(self._h, arr, len(streams), n_batch, chunk))
 
+    def ingest_host_submit(self, streams: Sequence[StreamSpec], chunk: int = 8) -> int:
+        """Enqueue a host-buffer batch behind earlier submissions and return its ticket at once.
+
+        The buffers named in ``streams`` must stay alive and untouched until :meth:`ingest_host_wait` returns for the
+        ticket.  A capture loop that double-buffers its host frames overlaps batch k+1's upload with batch k's download.
+        """
+        arr, n_batch = self._pack(streams, host=True)
+        ticket = C.c_uint64(0)
+        self._check(self.lib.ti_ingest_host_submit(self._h, arr, len(streams), n_batch, chunk, C.byref(ticket)))
+        return int(ticket.value)
+
+    def ingest_host_wait(self, ticket: int) -> None:
+        """Block until the batch submitted under ``ticket`` has landed in its destination buffers."""
+        self._check(self.lib.ti_ingest_host_wait(self._h, ticket))
+
     # -- multi-GPU ---------------------------------------------------------------
     def nccl_unique_id(self) -> bytes:
         buf = C.create_string_buffer(128)

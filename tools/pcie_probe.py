@@ -45,6 +45,26 @@ def main() -> None:
         torch.cuda.synchronize()
         return (time.perf_counter() - t0) / args.iters
 
+    def run_dependent() -> float:
+        """Piece k comes back only after it went up (the shape of ti_ingest_host: upload -> kernel -> download per chunk)."""
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(args.iters):
+            for k in range(args.pieces):
+                sl = slice(k * step, (k + 1) * step)
+                with torch.cuda.stream(up[0]):
+                    d_a[sl].copy_(h_in[sl], non_blocking=True)
+                    ev = torch.cuda.Event()
+                    ev.record()
+                with torch.cuda.stream(down[0]):
+                    down[0].wait_event(ev)
+                    h_out[sl].copy_(d_a[sl], non_blocking=True)
+        torch.cuda.synchronize()
+        return (time.perf_counter() - t0) / args.iters
+
+    run_dependent()
+    dt = run_dependent()
+    print(f"{'up, then down, per piece':26s} {n / dt / 1e9:7.1f} GB/s per direction ({args.mb} MB in {args.pieces} piece(s), {dt * 1e3:.2f} ms)")
     for name, a, b in (("H2D alone", True, False), ("D2H alone", False, True), ("H2D + D2H concurrently", True, True)):
         run(a, b)
         dt = run(a, b)
