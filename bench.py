@@ -318,9 +318,15 @@ def run_ours(args) -> None:
     # memory and reads its own result back into pinned host memory inside the timed region.  The same loop through
     # the blocking call (one batch at a time, nothing overlapped across calls) is reported next to it.
     Be = min(B, args.e2e_batch)
-    h_src = [[torch.from_numpy(np.ascontiguousarray(np.tile(pool_frames[s], ((Be + 1) // 2, 1, 1))[:Be])).pin_memory() for s in range(STREAMS)]
-             for _ in range(2)]
-    h_dst = [[torch.zeros((Be, H, W), dtype=torch.uint8).pin_memory() for _ in range(STREAMS)] for _ in range(2)]
+    from thor_slam_b200.ingest.hostmem import near_gpu
+
+    with near_gpu(local_rank) as place:  # pinned pages on the GPU's own NUMA node (matters with one process per GPU)
+        if args.no_numa:
+            os.sched_setaffinity(0, place.before)
+        h_src = [[torch.from_numpy(np.ascontiguousarray(np.tile(pool_frames[s], ((Be + 1) // 2, 1, 1))[:Be])).pin_memory() for s in range(STREAMS)]
+                 for _ in range(2)]
+        h_dst = [[torch.zeros((Be, H, W), dtype=torch.uint8).pin_memory() for _ in range(STREAMS)] for _ in range(2)]
+    host_cpus = len(place.cpus)
     hspecs = [[StreamSpec(F.KIND_RECTIFY, h_src[k][s], h_dst[k][s], F.MONO8, F.MONO8, camera=s) for s in range(STREAMS)] for k in range(2)]
     e2e_steps = max(4, min(args.steps, 10))
 
@@ -400,7 +406,7 @@ def run_ours(args) -> None:
             "e2e": {"value": e2e_value, "unit": "frame-sets/s", "h2d_bytes_per_step": Be * PX_PER_SET, "d2h_bytes_per_step": Be * PX_PER_SET,
                     "frame_sets_per_step": Be, "steps": e2e_steps, "chunk": args.chunk, "gpu_launches": launches_e2e,
                     "api": "ingest_host_submit / ingest_host_wait, two batches in flight (double-buffered pinned host frames)",
-                    "blocking_call_value": e2e_blocking_value},
+                    "blocking_call_value": e2e_blocking_value, "host_buffers_on_gpu_local_cpus": 0 if args.no_numa else host_cpus},
             "gpu_launches": launches,
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
@@ -534,6 +540,7 @@ def main() -> None:
     ap.add_argument("--cpu-budget", type=float, default=10.0, dest="cpu_budget", help="seconds of CPU work for cpu_baseline")
     ap.add_argument("--ref-sets", type=int, default=8, dest="ref_sets", help="frame sets per step of the reference arm")
     ap.add_argument("--no-cpu", action="store_true", dest="no_cpu")
+    ap.add_argument("--no-numa", action="store_true", dest="no_numa", help="do not place the pinned host buffers on the GPU's NUMA node")
     ap.add_argument("--extras", action="store_true", help="also time config 5 (rectify + back-projection) and the NCCL gather")
     args = ap.parse_args()
     if args.warmup < 3:
