@@ -201,6 +201,8 @@ inline float __fmul_rn(float a, float b) { return a * b; }
 inline float __fadd_rn(float a, float b) { return a + b; }
 inline float __fsub_rn(float a, float b) { return a - b; }
 inline float __fdiv_rn(float a, float b) { return a / b; }
+template <typename T>
+inline T __ldg(const T* p) { return *p; }
 inline int __float2int_rn(float a) { return (int)std::nearbyintf(a); }
 inline float __uint2float_rn(uint32_t v) { return (float)v; }
 inline float __int2float_rn(int v) { return (float)v; }

@@ -174,6 +174,20 @@ def _registration_case(be, dw: int, dh: int, rw: int, rh: int, n: int = 2, seed:
         assert np.array_equal(got[i], want), f"frame {i}: {(got[i] != want).any(axis=-1).sum()} pixels differ"
         assert not got[i][depth[i] == 0].any(), "no depth, no colour"
     assert (got.reshape(-1, 3).any(axis=1)).mean() > 0.5, "most valid points of this rig land inside the RGB image"
+    # a sensor pair looking in very different directions: most points fall behind the RGB camera or outside its image
+    from scipy.spatial.transform import Rotation
+
+    for k, yaw in enumerate((35.0, 100.0, 180.0)):
+        skew = np.eye(4)
+        skew[:3, :3] = Rotation.from_euler("y", yaw, degrees=True).as_matrix()
+        skew[:3, 3] = (0.3, -0.1, 0.2)
+        be.ctx.upload_registration(53, di.matrix, (dw, dh), ri.matrix, (rw, rh), skew)
+        colour3 = be.zeros((1, dh, dw, 3), np.uint8)
+        be.ctx.register_colour(53, be.dev(depth[:1]), be.dev(rgb[:1]), colour3)
+        want = ob.register_colour(depth[0], di.matrix, skew, ri.matrix, rgb[0])
+        assert np.array_equal(be.host(colour3)[0], want), f"yaw {yaw}"
+        if yaw == 180.0:
+            assert not want.any()
     # identical sensors (same K, same size, identity extrinsics): every valid pixel takes the colour at its own position
     be.ctx.upload_registration(51, di.matrix, (dw, dh), di.matrix, (dw, dh), np.eye(4))
     same = np.ascontiguousarray(rgb[:, :dh, :dw]) if (rh >= dh and rw >= dw) else make_image(rng, "bgr8", dw, dh)[None].repeat(n, 0)
