@@ -471,6 +471,8 @@ def run_extras(args, ctx, sources, maps, rank, world, distributed, barrier) -> d
     out = {"config5": {"frame_sets_per_step_per_rank": B, "ms_per_step": ms, "frame_sets_per_sec": world * B / (ms * 1e-3),
                        "hbm_gbs": B * bytes_per_set / (ms * 1e-3) / 1e9, "frac": B * bytes_per_set / (ms * 1e-3) / 1e9 / peak,
                        "algorithmic_bytes_per_frame_set": bytes_per_set}}
+    if not distributed:
+        out.update(run_config34(args, ctx, sources, keep, clouds, peak))
     if distributed:
         from thor_slam_b200.ingest.distributed import CloudGather, PeerCloudBuffer, RawDeviceBuffer
 
@@ -525,6 +527,82 @@ def run_extras(args, ctx, sources, maps, rank, world, distributed, barrier) -> d
             out["config5"]["fused_peer_store"]["matches_local"] = bool(torch.equal(fused[0], clouds))
         barrier()
         peer.close()
+    return out
+
+
+def run_config34(args, ctx, sources, keep5, clouds, peak) -> dict:
+    """BASELINE configs 3 and 4 as whole frame sets, one ``ingest`` call per step (N = 1; kernels only, device-resident).
+
+    Config 3: 4 x (1920x1080 BGR -> rgb8, 1280x800 depth -> body-frame cloud).  Config 4: 2 x "OAK-D Pro" (stereo mono
+    1280x800 rectified, 1280x800 BGR -> rgb8, depth -> cloud) + 2 x "OAK-D LR" (stereo BGR 1920x1200 -> rgb8 rectified,
+    1920x1200 BGR -> rgb8, depth -> cloud).  Algorithmic bytes per SURVEY section 8(d).
+    """
+    import torch
+
+    from thor_slam_b200.camera.synthetic import SyntheticCameraConfig, SyntheticCameraSource
+    from thor_slam_b200.ingest import formats as F
+    from thor_slam_b200.ingest.calib import stereo_rectify_maps
+    from thor_slam_b200.ingest.context import StreamSpec
+
+    stream = torch.cuda.current_stream()
+    steps = max(3, min(args.steps, 10))
+
+    def timed(specs) -> float:
+        for _ in range(3):
+            ctx.ingest(specs)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(steps):
+            ctx.ingest(specs)
+        e1.record(stream)
+        e1.synchronize()
+        return e0.elapsed_time(e1) / steps
+
+    def report(ms: float, n_sets: int, bytes_per_set: int) -> dict:
+        gbs = n_sets * bytes_per_set / (ms * 1e-3) / 1e9
+        return {"frame_sets_per_step": n_sets, "ms_per_step": ms, "frame_sets_per_sec": n_sets / (ms * 1e-3), "hbm_gbs": gbs,
+                "frac": gbs / peak, "algorithmic_bytes_per_frame_set": bytes_per_set}
+
+    def bgr(n, h, w):
+        return torch.randint(0, 256, (n, h, w, 3), dtype=torch.uint8, device="cuda")
+
+    out = {}
+    # ---- config 3 ----
+    B3 = max(2, args.batch // 4)
+    specs = []
+    for i in range(N_CAMERAS):
+        _, _, depth, mask, count = keep5[i]
+        rgb_in = bgr(B3, 1080, 1920)
+        specs.append(StreamSpec(F.KIND_CONVERT, rgb_in, torch.empty_like(rgb_in), F.BGR8, F.RGB8, width=1920, height=1080))
+        specs.append(StreamSpec(F.KIND_BACKPROJECT, depth[:B3], clouds[i][:B3], F.DEPTH16, F.XYZ32F, camera=2 * i, mask=mask[:B3], count=count[:B3]))
+    out["config3"] = report(timed(specs), B3, N_CAMERAS * (1920 * 1080 * 6 + W * H * 15))
+    del specs
+    # ---- config 4 ----
+    B4 = max(2, args.batch // 8)
+    lr = SyntheticCameraSource(SyntheticCameraConfig(name="lr0", resolution=(1920, 1200), pixel_format="bgr8", pool=1, enable_rgbd=False))
+    lr_maps = stereo_rectify_maps(lr.get_intrinsics(), lr.get_extrinsics(), (1920, 1200))
+    for k in range(2):
+        for cam in range(2):
+            ctx.upload_rectify_map(8 + 2 * k + cam, *lr_maps[cam], (1920, 1200))
+    specs = []
+    for i in range(2):  # OAK-D Pro: slots 2i, 2i+1 hold the mono stereo maps, slot 2i the depth projection
+        left, _, depth, mask, count = keep5[i]
+        for cam in range(2):
+            specs.append(StreamSpec(F.KIND_RECTIFY, left[:B4], torch.empty_like(left[:B4]), F.MONO8, F.MONO8, camera=2 * i + cam))
+        rgb_in = bgr(B4, H, W)
+        specs.append(StreamSpec(F.KIND_CONVERT, rgb_in, torch.empty_like(rgb_in), F.BGR8, F.RGB8, width=W, height=H))
+        specs.append(StreamSpec(F.KIND_BACKPROJECT, depth[:B4], clouds[i][:B4], F.DEPTH16, F.XYZ32F, camera=2 * i, mask=mask[:B4], count=count[:B4]))
+    for k in range(2):  # OAK-D LR
+        _, _, depth, mask, count = keep5[2 + k]
+        for cam in range(2):
+            col = bgr(B4, 1200, 1920)
+            specs.append(StreamSpec(F.KIND_RECTIFY, col, torch.empty_like(col), F.BGR8, F.RGB8, camera=8 + 2 * k + cam))
+        rgb_in = bgr(B4, 1200, 1920)
+        specs.append(StreamSpec(F.KIND_CONVERT, rgb_in, torch.empty_like(rgb_in), F.BGR8, F.RGB8, width=1920, height=1200))
+        specs.append(StreamSpec(F.KIND_BACKPROJECT, depth[:B4], clouds[2 + k][:B4], F.DEPTH16, F.XYZ32F, camera=2 * (2 + k), mask=mask[:B4], count=count[:B4]))
+    pro = 2 * W * H * 2 + W * H * 6 + W * H * 15
+    lrb = 2 * 1920 * 1200 * 6 + 1920 * 1200 * 6 + W * H * 15
+    out["config4"] = report(timed(specs), B4, 2 * pro + 2 * lrb)
     return out
 
 
