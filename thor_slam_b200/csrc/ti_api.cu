@@ -348,12 +348,13 @@ int ti_upload_projection(ti_ctx* ctx, int camera, int width, int height, const d
         return fail(ctx, TI_EINVAL, "ti_upload_projection: bad size %dx%d", width, height);
     if (!(k[0] != 0.0) || !(k[1] != 0.0)) return fail(ctx, TI_EINVAL, "ti_upload_projection: fx and fy must be non-zero");
     CameraSlot& C = ctx->cams[camera];
-    const double inv[3] = {1.0 / k[0], 1.0 / k[1], 1.0};
     for (int r = 0; r < 3; ++r) {
-        for (int c = 0; c < 3; ++c) C.ray[3 * r + c] = (float)(body_T_cam[4 * r + c] * inv[c]);
-        C.trans[r] = (float)body_T_cam[4 * r + 3];
+        const double ax = body_T_cam[4 * r + 0] / k[0], ay = body_T_cam[4 * r + 1] / k[1], az = body_T_cam[4 * r + 2];
+        C.proj_au[r] = 1e-3 * ax;
+        C.proj_av[r] = 1e-3 * ay;
+        C.proj_ac[r] = 1e-3 * (az - ax * k[2] - ay * k[3]);
+        C.proj_t[r] = body_T_cam[4 * r + 3];
     }
-    C.cx = (float)k[2]; C.cy = (float)k[3];
     C.proj_w = width; C.proj_h = height;
     C.has_proj = true;
     return TI_OK;

@@ -7,7 +7,7 @@
 // (examples/rgbd_stream.py:121-123,270-276):
 //
 //     z = d * 1e-3 ;  ray = A * [u - cx, v - cy, 1] ,  A = R * diag(1/fx, 1/fy, 1)
-//     p = z * ray + t      (d == 0 -> p = 0, mask = 0)
+//     p = z * ray + t      (d == 0 -> p = 0, mask = 0)        evaluated in double, stored as float
 //
 // HBM-bound streaming kernel: 2 B/px in, 12 + 1 B/px out.  Each thread owns 8 consecutive pixels
 // (one 16-byte depth load, one 8-byte mask store); the 96 B of xyz per thread are transposed
@@ -23,10 +23,11 @@ constexpr int BP_TILE = BP_THREADS * BP_PX_PER_THREAD;  // 2048 px
 constexpr int MAX_BP_JOBS = 16;
 constexpr int BP_LANE_STRIDE = 7;  // float4 slots per lane in the transpose buffer (6 used + 1 pad: conflict-free)
 
+// Constants in double: p = d * (au * u + av * v + ac) + t with d the raw depth in millimetres - the 1e-3, the
+// intrinsics and the principal point are folded in on the host (ti_upload_projection).
 struct BpCam {
-    float a[9];
-    float t[3];
-    float cx, cy;
+    double au[3], av[3], ac[3];
+    double t[3];
     int width, height;
 };
 
@@ -47,17 +48,27 @@ struct BpParams {
     int n_batch;
 };
 
-__device__ __forceinline__ void project(const BpCam& c, float bx, float by, float bz, int u, uint32_t d, float& x,
+// The arithmetic is done in double and rounded to float once per coordinate.  In float the error of a point is about
+// 6e-8 of the LARGEST term, z * ray or t, whatever the size of their sum - a point that lands within a few millimetres of
+// the body origin (z * ray = -t) then misses the 1e-5 relative bar (found by tools/fuzz_convert_backproject.py: 1.08e-5).
+// The kernel moves 15 B/px and stays HBM-bound: ten double-precision operations per pixel are a fraction of the FP64 pipe.
+// Integer -> double conversions run on the narrow conversion pipe, which the three double -> float roundings per pixel already
+// load: the column arrives as a double (first column of the thread + a constant), the depth is made a double by planting its
+// bits in the mantissa of 2^52 and subtracting 2^52 (exact for any 32-bit value).
+__device__ __forceinline__ double u32_as_double(uint32_t v) {
+#if defined(TI_EMULATE) || !defined(TI_BP_MAGIC)
+    return (double)v;
+#else
+    return __hiloint2double(0x43300000, (int)v) - 4503599627370496.0;
+#endif
+}
+__device__ __forceinline__ void project(const BpCam& c, double bx, double by, double bz, double ud, uint32_t d, float& x,
                                         float& y, float& z) {
-    const float du = (float)u - c.cx;
-    const float rx = __fmaf_rn(c.a[0], du, bx);
-    const float ry = __fmaf_rn(c.a[3], du, by);
-    const float rz = __fmaf_rn(c.a[6], du, bz);
-    const float zz = (float)d * 0.001f;
+    const double dd = u32_as_double(d);
     const bool ok = d != 0;
-    x = ok ? __fmaf_rn(zz, rx, c.t[0]) : 0.f;
-    y = ok ? __fmaf_rn(zz, ry, c.t[1]) : 0.f;
-    z = ok ? __fmaf_rn(zz, rz, c.t[2]) : 0.f;
+    x = ok ? (float)fma(dd, fma(c.au[0], ud, bx), c.t[0]) : 0.f;
+    y = ok ? (float)fma(dd, fma(c.au[1], ud, by), c.t[1]) : 0.f;
+    z = ok ? (float)fma(dd, fma(c.au[2], ud, bz), c.t[2]) : 0.f;
 }
 
 __global__ void __launch_bounds__(BP_THREADS) backproject_vec_kernel(const __grid_constant__ BpParams P) {
@@ -108,16 +119,17 @@ __global__ void __launch_bounds__(BP_THREADS) backproject_vec_kernel(const __gri
         if (p0 < npx) {  // width % 8 == 0 -> a thread's 8 pixels never straddle a row or the frame end
             const uint32_t dw[4] = {cur.dv.x, cur.dv.y, cur.dv.z, cur.dv.w};
             const int v = (int)(p0 / (uint32_t)J.cam.width), u0 = (int)(p0 - (uint32_t)v * J.cam.width);
-            const float fv = (float)v - J.cam.cy;
-            const float bx = __fmaf_rn(J.cam.a[1], fv, J.cam.a[2]);
-            const float by = __fmaf_rn(J.cam.a[4], fv, J.cam.a[5]);
-            const float bz = __fmaf_rn(J.cam.a[7], fv, J.cam.a[8]);
+            const double vd = (double)v;
+            const double bx = fma(J.cam.av[0], vd, J.cam.ac[0]);
+            const double by = fma(J.cam.av[1], vd, J.cam.ac[1]);
+            const double bz = fma(J.cam.av[2], vd, J.cam.ac[2]);
+            const double u0d = (double)u0;
             float f[24];
             uint32_t m0 = 0, m1 = 0;
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
                 const uint32_t d = (dw[k >> 1] >> ((k & 1) * 16)) & 0xFFFFu;
-                project(J.cam, bx, by, bz, u0 + k, d, f[3 * k], f[3 * k + 1], f[3 * k + 2]);
+                project(J.cam, bx, by, bz, u0d + (double)k, d, f[3 * k], f[3 * k + 1], f[3 * k + 2]);
                 const uint32_t ok = d != 0 ? 1u : 0u;
                 nvalid += ok;
                 if (k < 4) m0 |= ok << (8 * k); else m1 |= ok << (8 * (k - 4));
@@ -168,10 +180,10 @@ __global__ void __launch_bounds__(BP_THREADS) backproject_scalar_kernel(BpJobDev
             const uint32_t p = (uint32_t)(t - (uint64_t)b * npx);
             const int v = (int)(p / (uint32_t)J.cam.width), u = (int)(p - (uint32_t)v * J.cam.width);
             const uint32_t d = J.depth[(uint64_t)b * (J.depth_stride / 2) + p];
-            const float fv = (float)v - J.cam.cy;
+            const double vd = (double)v;
             float x, y, z;
-            project(J.cam, __fmaf_rn(J.cam.a[1], fv, J.cam.a[2]), __fmaf_rn(J.cam.a[4], fv, J.cam.a[5]),
-                    __fmaf_rn(J.cam.a[7], fv, J.cam.a[8]), u, d, x, y, z);
+            project(J.cam, fma(J.cam.av[0], vd, J.cam.ac[0]), fma(J.cam.av[1], vd, J.cam.ac[1]), fma(J.cam.av[2], vd, J.cam.ac[2]),
+                    (double)u, d, x, y, z);
             float* o = J.xyz + (uint64_t)b * (J.xyz_stride / 4) + (uint64_t)p * 3;
             o[0] = x; o[1] = y; o[2] = z;
             ok = d != 0;
@@ -197,9 +209,8 @@ int launch_backproject(ti_ctx* ctx, const BackprojectJob* jobs, int n_jobs, int 
             BpJobDev D{};
             D.depth = J.depth; D.xyz = J.xyz; D.mask = J.mask; D.count = J.count;
             D.depth_stride = J.depth_stride; D.xyz_stride = J.xyz_stride; D.mask_stride = J.mask_stride;
-            for (int i = 0; i < 9; ++i) D.cam.a[i] = C.ray[i];
-            for (int i = 0; i < 3; ++i) D.cam.t[i] = C.trans[i];
-            D.cam.cx = C.cx; D.cam.cy = C.cy; D.cam.width = C.proj_w; D.cam.height = C.proj_h;
+            for (int i = 0; i < 3; ++i) { D.cam.au[i] = C.proj_au[i]; D.cam.av[i] = C.proj_av[i]; D.cam.ac[i] = C.proj_ac[i]; D.cam.t[i] = C.proj_t[i]; }
+            D.cam.width = C.proj_w; D.cam.height = C.proj_h;
             if (J.depth_stride % 2 || J.xyz_stride % 4)
                 return fail(ctx, TI_EINVAL, "backproject: frame strides must keep element alignment");
             if (J.count) {

@@ -154,9 +154,8 @@ struct CameraSlot {
     // projection
     bool has_proj = false;
     int proj_w = 0, proj_h = 0;
-    float ray[9];  // A = R * diag(1/fx, 1/fy, 1), row-major: p = z * (A * [u-cx, v-cy, 1]) + t
-    float trans[3];
-    float cx = 0.f, cy = 0.f;
+    // p = d_mm * (au * u + av * v + ac) + t : rows of 1e-3 * R * diag(1/fx, 1/fy, 1) with the principal point folded into ac
+    double proj_au[3], proj_av[3], proj_ac[3], proj_t[3];
 };
 
 }  // namespace ti
