@@ -52,19 +52,9 @@ struct BpParams {
 // 6e-8 of the LARGEST term, z * ray or t, whatever the size of their sum - a point that lands within a few millimetres of
 // the body origin (z * ray = -t) then misses the 1e-5 relative bar (found by tools/fuzz_convert_backproject.py: 1.08e-5).
 // The kernel moves 15 B/px and stays HBM-bound: ten double-precision operations per pixel are a fraction of the FP64 pipe.
-// Integer -> double conversions run on the narrow conversion pipe, which the three double -> float roundings per pixel already
-// load: the column arrives as a double (first column of the thread + a constant), the depth is made a double by planting its
-// bits in the mantissa of 2^52 and subtracting 2^52 (exact for any 32-bit value).
-__device__ __forceinline__ double u32_as_double(uint32_t v) {
-#if defined(TI_EMULATE) || !defined(TI_BP_MAGIC)
-    return (double)v;
-#else
-    return __hiloint2double(0x43300000, (int)v) - 4503599627370496.0;
-#endif
-}
 __device__ __forceinline__ void project(const BpCam& c, double bx, double by, double bz, double ud, uint32_t d, float& x,
                                         float& y, float& z) {
-    const double dd = u32_as_double(d);
+    const double dd = (double)d;
     const bool ok = d != 0;
     x = ok ? (float)fma(dd, fma(c.au[0], ud, bx), c.t[0]) : 0.f;
     y = ok ? (float)fma(dd, fma(c.au[1], ud, by), c.t[1]) : 0.f;
