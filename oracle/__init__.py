@@ -26,5 +26,5 @@ PARITY PIN STATUS
   ``thor_slam/requirements.txt:4``) called exactly as the reference calls it,
   next to an independent pure-numpy restatement of the same integer/fp
   arithmetic; the two are checked against each other exhaustively
-  (``tests/test_oracle_self.py``) and frozen as golden fixtures.
+  (``tests/test_oracle_golden.py::test_cv_arithmetic_fixtures``) and frozen as golden fixtures.
 """
