@@ -178,6 +178,35 @@ int ti_upload_registration(ti_ctx* ctx, int camera, int depth_w, int depth_h, co
 int ti_register_colour(ti_ctx* ctx, int camera, const uint16_t* depth, const uint8_t* rgb, uint8_t* colour, int n_batch,
                        uint64_t depth_frame_stride, uint64_t rgb_frame_stride, uint64_t colour_frame_stride);
 
+/* ---- voxel down-sampling of the body-frame cloud ---------------------------------- */
+
+/* Voxel grid of the rig-wide cloud.  voxel_size_m: edge length in metres (nvblox `voxel_size`, launch/thor_nvblox.launch.py:26:
+ * 0.05).  max_depth_mm: depth pixels beyond it are not integrated (`tsdf_integrator_max_integration_distance_m`,
+ * launch/thor_nvblox.launch.py:27-31: 10 m); 0 = no cap. */
+int ti_set_voxel_grid(ti_ctx* ctx, double voxel_size_m, uint32_t max_depth_mm);
+
+typedef struct ti_depth_stream {
+    int32_t camera;              /* calibration slot with a projection (ti_upload_projection)     */
+    int32_t reserved;
+    const uint16_t* depth;       /* DEVICE, u16 millimetres, frame b at depth + b*depth_frame_stride bytes */
+    uint64_t depth_frame_stride; /* 0 = tightly packed                                              */
+} ti_depth_stream;
+
+/* depth frames of n_streams cameras x n_batch frame sets -> ONE list with one u64 record per voxel that at least one valid
+ * pixel (0 < d <= max_depth_mm) of ANY camera of frame set b falls into - the valid-compacted, down-sampled form of the clouds
+ * ti_backproject writes densely (same double-precision back-projection, then k = floor(p_body / voxel_size) per axis):
+ *     record = tag << 56 | (set_base + b) << 45 | (kx + 16384) << 30 | (ky + 16384) << 15 | (kz + 16384)
+ * records: DEVICE u64[capacity], appended in no defined order; *n_records (DEVICE u32, overwritten) = number of distinct
+ * records found - when it exceeds capacity the list was truncated.  set_counts: DEVICE u32[n_batch] (overwritten) or NULL.
+ * tag < 256 (the producing rank in the multi-GPU gather), set_base + n_batch <= 2048.  One call at a time per ctx.
+ * This is the cloud the reference's only cloud type carries (thor_slam/slam/interface.py:134-138, N x 3) before ti_voxel_points. */
+int ti_voxel_cloud(ti_ctx* ctx, const ti_depth_stream* streams, int n_streams, int n_batch, uint32_t set_base, uint32_t tag,
+                   uint64_t* records, uint64_t capacity, uint32_t* n_records, uint32_t* set_counts);
+
+/* Records -> voxel centres, N x 3 f32 metres in the body frame (SlamMap.to_point_cloud, thor_slam/slam/interface.py:134-138).
+ * Converts min(*n_records, max_records) records; xyz: DEVICE f32[max_records * 3]. */
+int ti_voxel_points(ti_ctx* ctx, const uint64_t* records, const uint32_t* n_records, uint64_t max_records, float* xyz);
+
 /* Whole frame-set batch in at most one launch per kind: every stream x every frame.
  * This is the call behind CameraRig.get_synchronized_frames() (thor_slam/camera/rig.py:358-415)
  * in the drop-in rig.  streams: HOST array, DEVICE image pointers inside. */

@@ -13,7 +13,8 @@ from oracle import backproject as ob
 from oracle import conventions as conv
 from oracle import convert as oc
 from oracle import rectify as orc
-from thor_slam_b200.camera.synthetic import SyntheticCameraConfig, SyntheticCameraSource, make_depth, make_image
+from oracle import voxel as ov
+from thor_slam_b200.camera.synthetic import SyntheticCameraConfig, SyntheticCameraSource, make_depth, make_depth_scene, make_image
 from thor_slam_b200.ingest import formats as F
 from thor_slam_b200.ingest.context import StreamSpec
 
@@ -145,6 +146,54 @@ def check_backproject(be, cam: int, w: int, h: int, n: int = 2, seed: int = 2, r
         assert np.array_equal(gm[i], msk)
         assert int(gc[i]) == cnt
         assert not np.any(gx[i][msk == 0]), "invalid pixels must be written as (0,0,0)"
+
+
+def check_voxel(be, cam0: int, sizes: list[tuple[int, int]], n: int = 2, seed: int = 4, voxel: float = 0.05, max_depth_mm: int = 10000,
+                scene: str = "room", set_base: int = 0, tag: int = 0, capacity: int | None = None, depth=None) -> int:
+    """``ti_voxel_cloud`` over ``len(sizes)`` cameras x ``n`` frame sets against ``np.unique`` of the oracle's keys: the SET of
+    records, the total and the per-set counts must be exact; ``ti_voxel_points`` must give the voxel centres bit for bit.
+    Returns the number of records."""
+    rng = np.random.default_rng(seed)
+    cams = []
+    for i, (w, h) in enumerate(sizes):
+        s = SyntheticCameraSource(SyntheticCameraConfig(name=f"oak{i}", resolution=(w, h), pool=1, seed=seed + i))
+        intr, ext = s.get_intrinsics()[0], s.get_extrinsics()[0]
+        m = conv.body_T_camera(random_pose(rng), ext.to_4x4_matrix(), "rdf")
+        be.ctx.upload_projection(cam0 + i, intr.matrix, m, (w, h))
+        if depth is not None:
+            d = depth[i]
+        elif scene == "room":
+            d = np.stack([make_depth_scene(rng, w, h, focal_px=intr.matrix[0, 0]) for _ in range(n)]) if n else np.zeros((0, h, w), np.uint16)
+        else:
+            d = np.stack([make_depth(rng, w, h) for _ in range(n)]) if n else np.zeros((0, h, w), np.uint16)
+        cams.append((d, intr.matrix, m))
+    n = cams[0][0].shape[0]
+    want_sets = [ov.voxel_records([(d[b], k, m) for d, k, m in cams], voxel, max_depth_mm, set_base + b, tag) for b in range(n)]
+    want = np.concatenate(want_sets) if want_sets else np.zeros(0, np.uint64)
+    cap = capacity if capacity is not None else max(len(want) + 7, 1)
+    be.ctx.set_voxel_grid(voxel, max_depth_mm)
+    records = be.dev(np.full(cap, 0x5555555555555555, dtype=np.int64))
+    n_rec = be.dev(np.full(1, 0xDEADBEEF, dtype=np.uint32))  # overwritten, not accumulated
+    counts = be.dev(np.full(max(n, 1), 0xDEADBEEF, dtype=np.uint32))
+    for _ in range(2):  # a second launch reuses the hash set: entries of the first must read as free
+        be.ctx.voxel_cloud([(cam0 + i, be.dev(cams[i][0])) for i in range(len(cams))], records, n_rec, counts, set_base=set_base, tag=tag)
+    got_n = int(be.host(n_rec)[0])
+    assert got_n == len(want), f"{got_n} records, oracle has {len(want)} distinct voxels"
+    got_counts = be.host(counts)
+    for b in range(n):
+        assert int(got_counts[b]) == len(want_sets[b]), f"set {b}: {int(got_counts[b])} vs {len(want_sets[b])}"
+    got = be.host(records).view(np.uint64)
+    if capacity is None:
+        assert np.array_equal(np.sort(got[:got_n]), np.sort(want)), "record sets differ"
+        assert np.all(got[got_n:] == 0x5555555555555555), "wrote past the end of the list"
+        xyz = be.zeros((cap, 3), np.float32)
+        be.ctx.voxel_points(records, n_rec, xyz)
+        assert np.array_equal(be.host(xyz)[:got_n], ov.record_points(got[:got_n], voxel))
+        assert not be.host(xyz)[got_n:].any()
+    else:  # truncated list: everything that was written is a genuine, distinct record
+        assert got_n > cap
+        assert len(np.unique(got)) == cap and np.isin(got, want).all()
+    return got_n
 
 
 def check_host_pipeline(be, cam: int, w: int, h: int, batches: list[int], chunk: int, pinned: bool, submit: bool) -> None:

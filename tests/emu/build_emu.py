@@ -16,7 +16,7 @@ from pathlib import Path
 HERE = Path(__file__).resolve().parent
 CSRC = HERE.parent.parent / "thor_slam_b200" / "csrc"
 OUT_DIR = HERE / "_build"
-SOURCES = ["ti_api.cu", "ti_convert.cu", "ti_rectify.cu", "ti_rectify_pair.cu", "ti_rectify_c3.cu", "ti_backproject.cu", "ti_register.cu", "ti_tma.cu"]
+SOURCES = ["ti_api.cu", "ti_convert.cu", "ti_rectify.cu", "ti_rectify_pair.cu", "ti_rectify_c3.cu", "ti_backproject.cu", "ti_register.cu", "ti_voxel.cu", "ti_tma.cu"]
 CUDA_INC = "/usr/local/cuda/include"
 
 

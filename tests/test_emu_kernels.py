@@ -69,6 +69,26 @@ def test_backproject_extremes(emu_backend):
     cases.check_backproject(emu_backend, 6, 64, 16, depth=depth)
 
 
+@pytest.mark.parametrize("scene", ["room", "noise"])
+def test_voxel_cloud(emu_backend, scene):
+    """Two cameras of different size (vector and scalar load paths, ragged tiles) fused per frame set."""
+    cases.check_voxel(emu_backend, 20, [(128, 64), (100, 45)], n=2, scene=scene)
+
+
+def test_voxel_cloud_edges(emu_backend):
+    depth = np.zeros((3, 32, 64), np.uint16)  # set 0: nothing valid; set 1: all beyond the cap but one pixel; set 2: all one voxel
+    depth[1] = 65535
+    depth[1, 5, 7] = 10000
+    depth[2] = 1
+    cases.check_voxel(emu_backend, 22, [(64, 32)], depth=[depth], set_base=2045, tag=255)
+    cases.check_voxel(emu_backend, 22, [(64, 32)], n=0)
+    cases.check_voxel(emu_backend, 22, [(128, 64)], n=1, scene="noise", capacity=100)  # truncated list, full count
+    with pytest.raises(ValueError):
+        cases.check_voxel(emu_backend, 22, [(64, 32)], n=1, voxel=0.001, max_depth_mm=0)  # 65 m / 1 mm overflows the key fields
+    with pytest.raises(ValueError):
+        cases.check_voxel(emu_backend, 22, [(64, 32)], n=2, set_base=2047)
+
+
 @pytest.mark.parametrize("submit", [False, True])
 def test_host_pipeline_chunk_schedule(emu_backend, submit):
     """ti_ingest_host / _submit / _wait: ramped, ragged and empty batches through the three chunk slots."""

@@ -205,3 +205,30 @@ def test_errors(gpu_backend):
         ctx.convert(a, a.clone(), "mono8", "rgb8", 16, 8)  # unsupported conversion
     with pytest.raises(ValueError):
         ctx.convert(a.cpu(), a.clone(), "mono8", "mono8", 16, 8)  # host tensor on the device API
+
+
+@pytest.mark.parametrize("scene", ["room", "noise"])
+def test_voxel_cloud_config5_full_size(gpu_backend, scene):
+    """BASELINE config 5 frame sets: 4 depth cameras of 1280x800 fused per frame set into one voxel list (0.05 m, 10 m cap)."""
+    n = cases.check_voxel(gpu_backend, 30, [(1280, 800)] * 4, n=2, scene=scene, seed=21)
+    assert n > 0
+
+
+def test_voxel_cloud_small_ragged_and_edges(gpu_backend):
+    cases.check_voxel(gpu_backend, 34, [(128, 64), (100, 45)], n=3, scene="room")
+    cases.check_voxel(gpu_backend, 34, [(128, 64), (100, 45)], n=3, scene="noise", voxel=0.02, max_depth_mm=0)
+    depth = np.zeros((3, 32, 64), np.uint16)
+    depth[1] = 65535
+    depth[1, 5, 7] = 10000
+    depth[2] = 1
+    cases.check_voxel(gpu_backend, 36, [(64, 32)], depth=[depth], set_base=2045, tag=255)
+    cases.check_voxel(gpu_backend, 36, [(64, 32)], n=0)
+    cases.check_voxel(gpu_backend, 36, [(128, 64)], n=1, scene="noise", capacity=100)
+    with pytest.raises(ValueError):
+        cases.check_voxel(gpu_backend, 36, [(64, 32)], n=1, voxel=0.001, max_depth_mm=0)
+
+
+def test_voxel_cloud_many_launches_epoch_wrap(gpu_backend):
+    """More than 255 launches on one table: the epoch byte wraps and the table is cleared."""
+    for i in range(130):  # two launches per check
+        cases.check_voxel(gpu_backend, 37, [(64, 32)], n=1, scene="noise", seed=100 + i)

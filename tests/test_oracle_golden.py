@@ -154,3 +154,33 @@ def test_distortion_model_rule(n, model):
     m, d = orc.select_distortion(np.arange(1, n + 1, dtype=float))
     assert m == model
     assert len(d) == {"rational_polynomial": 8, "plumb_bob": 5, "equidistant": 4}[model]
+
+
+def test_voxel_oracle_fma_route_agrees_with_float64_numpy():
+    """The C restatement (fma, constants folded) against floor(backproject(...) / voxel) in plain float64 numpy: identical keys
+    wherever p / voxel is not within 1e-9 of an integer, and never more than one voxel apart."""
+    from oracle import voxel as ov
+    from tests import cases
+    from thor_slam_b200.camera.synthetic import SyntheticCameraConfig, SyntheticCameraSource, make_depth, make_depth_scene
+
+    rng = np.random.default_rng(7)
+    for w, h, scene in [(320, 200, "room"), (320, 200, "noise"), (101, 57, "noise")]:
+        s = SyntheticCameraSource(SyntheticCameraConfig(name="oak0", resolution=(w, h), pool=1, seed=7))
+        k = s.get_intrinsics()[0].matrix
+        m = cases.conv.body_T_camera(cases.random_pose(rng), s.get_extrinsics()[0].to_4x4_matrix(), "rdf")
+        d = make_depth_scene(rng, w, h) if scene == "room" else make_depth(rng, w, h)
+        keys, valid = ov.voxel_keys(d, k, m, 0.05, 10000)
+        assert np.array_equal(valid, (d > 0) & (d <= 10000))
+        ref, margin = ov.voxel_keys_f64(d, k, m, 0.05)
+        clear = valid & (margin > 1e-9)
+        assert clear.sum() > 0.99 * valid.sum()
+        assert np.array_equal(keys[clear], ref[clear])
+        assert np.abs(keys[valid] - ref[valid]).max() <= 1
+    # identity pose, principal-point pixel: x = y = 0 exactly, z = d mm -> key (0, 0, floor(d / 50))
+    k = np.array([[100.0, 0, 8], [0, 100.0, 4], [0, 0, 1]])
+    d = np.full((8, 16), 1234, np.uint16)
+    keys, _ = ov.voxel_keys(d, k, np.eye(4), 0.05, 0)
+    assert tuple(keys[4, 8]) == (0, 0, 24)
+    rec = ov.pack_records(keys[4:5, 8], set_id=3, tag=2)
+    assert ov.unpack_records(rec)[0][0] == 2 and ov.unpack_records(rec)[1][0] == 3 and tuple(ov.unpack_records(rec)[2][0]) == (0, 0, 24)
+    assert np.allclose(ov.record_points(rec, 0.05), [[0.025, 0.025, 1.225]])

@@ -126,6 +126,33 @@ def make_depth(rng: np.random.Generator, width: int, height: int) -> np.ndarray:
     return d
 
 
+def make_depth_scene(rng: np.random.Generator, width: int, height: int, focal_px: float | None = None, hole_fraction: float = 0.2) -> np.ndarray:
+    """A depth image of SURFACES (``make_depth`` is per-pixel noise, the worst case for any spatial down-sampling): a room
+    seen from inside - floor, ceiling, two side walls, a back wall - with a few boxes in it, multiplicative stereo-like
+    noise of 0.2 %, coherent holes covering about ``hole_fraction`` of the image and a few saturated pixels.
+    Millimetres, 0 = invalid, like ``get_latest_rgbd_frames`` (``drivers/luxonis.py:876-921``)."""
+    f = float(focal_px if focal_px is not None else 0.625 * width)
+    x = (np.arange(width, dtype=np.float64)[None, :] - width / 2) / f
+    y = (np.arange(height, dtype=np.float64)[:, None] - height / 2) / f
+    half_w, up, down, back = rng.uniform(2.0, 3.5), rng.uniform(1.0, 1.8), rng.uniform(0.8, 1.4), rng.uniform(5.0, 9.0)
+    with np.errstate(divide="ignore"):
+        z = np.minimum(np.minimum(half_w / np.abs(x), np.where(y > 0, down / np.abs(y), up / np.abs(y))), back)
+    z = np.broadcast_to(z, (height, width)).copy()
+    for _ in range(int(rng.integers(3, 7))):  # boxes: fronto-parallel faces nearer than the room
+        bw, bh = int(rng.integers(width // 16, width // 4)), int(rng.integers(height // 10, height // 3))
+        u0, v0 = int(rng.integers(0, width - bw)), int(rng.integers(0, height - bh))
+        zb = rng.uniform(0.6, 4.0)
+        z[v0:v0 + bh, u0:u0 + bw] = np.minimum(z[v0:v0 + bh, u0:u0 + bw], zb)
+    z *= 1.0 + 0.002 * rng.standard_normal((height, width))
+    d = np.clip(np.rint(z * 1000.0), 1, 65534).astype(np.uint16)
+    if hole_fraction > 0:
+        coarse = rng.random(((height + 31) // 32, (width + 31) // 32)) < hole_fraction
+        d[np.kron(coarse, np.ones((32, 32), bool))[:height, :width]] = 0
+    hot = rng.integers(0, height * width, size=max(4, height * width // 50000))
+    d.reshape(-1)[hot] = 65535
+    return d
+
+
 class SyntheticCameraSource(CameraSource):
     """Deterministic frames, calibration and clocks for one (stereo or single) camera."""
 

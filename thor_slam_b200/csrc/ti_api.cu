@@ -86,6 +86,7 @@ int ti_destroy(ti_ctx* ctx) {
     cudaDeviceSynchronize();
     for (auto& c : ctx->cams) free_camera(c);
     if (ctx->scratch) cudaFree(ctx->scratch);
+    if (ctx->voxel_table) cudaFree(ctx->voxel_table);
     for (auto& h : ctx->hslot) {
         for (void* p : h.d_src) if (p) cudaFree(p);
         for (void* p : h.d_dst) if (p) cudaFree(p);

@@ -192,6 +192,12 @@ struct ti_ctx {
     uint64_t host_chunks = 0;    // chunks enqueued so far; chunk g uses slot g % 3
     uint64_t host_tickets = 0;   // submissions so far (ti_ingest_host_submit); ticket t completes at ticket_done[t % 8]
     cudaEvent_t ticket_done[8] = {};
+    // voxel down-sampling (ti_voxel.cu)
+    double voxel_size = 0.0;
+    uint32_t voxel_max_depth = 65535;
+    uint64_t* voxel_table = nullptr;  // hash set of the launch in flight; entries carry the epoch of the launch that wrote them
+    uint64_t voxel_slots = 0;
+    uint32_t voxel_epoch = 0;
     // NCCL (dlopen)
     void* nccl_comm = nullptr;
     int rank = 0, world = 1;

@@ -1,0 +1,308 @@
+// depth (u16 mm) of every camera of a frame set -> ONE list of occupied body-frame voxels (SURVEY section 8 (f) row 4,
+// "rig-side voxel down-sampling of the cloud ahead of nvblox", and the N x 3 cloud contract of
+// thor_slam/slam/interface.py:134-138).
+//
+// nvblox integrates at voxel_size = 0.05 m and ignores depth beyond tsdf_integrator_max_integration_distance_m = 10 m
+// (launch/thor_nvblox.launch.py:26-31).  Shipping 12 B for every depth pixel to the fusing rank carries each voxel of
+// a surface ~170 times (a 5 cm voxel at 3 m covers 13 x 13 pixels of a 1280 x 800 / f = 800 px camera).  This kernel
+// emits each occupied voxel of a frame set once:
+//
+//     p   = d * (au * u + av * v + ac) + t          the back-projection of ti_backproject.cu (double, fused multiply-adds,
+//                                                   same constants, RDF->FLU and rig pose folded in)
+//     k   = floor(p / voxel_size)  per axis         computed as floor(d * (au' * u + av' * v + ac') + t') with the constants
+//                                                   pre-multiplied by 1 / voxel_size on the host
+//     valid = d > 0  and  d <= max_depth_mm         examples/rgbd_stream.py:121-123 and the nvblox distance cap
+//     record = tag << 56 | set << 45 | (kx + 16384) << 30 | (ky + 16384) << 15 | (kz + 16384)
+//
+// One record per distinct (set, k) over ALL cameras of the call: the per-frame-set rig-wide fusion.  The order of the list
+// is not defined (records are appended tile by tile); the SET of records and the per-set counts are exact.
+//
+// How duplicates are removed (every stage only ever drops a key that is provably already on its way out):
+//   1. a thread owns 8 consecutive pixels of a row and forwards a key only when it differs from its predecessor's;
+//   2. a direct-mapped cache of 2048 keys in shared memory (one atomic exchange): whoever finds its own key there drops it -
+//      the thread that put it there forwards it.  Keys carry the frame-set number, so the cache is never cleared;
+//   3. an open-addressing hash set in global memory (one 64-bit compare-and-swap per surviving key), whose entries carry
+//      an 8-bit launch epoch so it is never cleared between launches either.  The thread whose CAS installs a key emits it.
+// New keys of a tile are collected in shared memory and appended to the list with one atomic per tile, so the list is
+// written in coalesced runs.  Traffic: 2 B/px of depth in, 8 B per occupied voxel out.
+#include "ti_common.cuh"
+
+namespace ti {
+
+constexpr int VX_THREADS = 256;
+constexpr int VX_TW = 64, VX_TH = 32;  // pixels per tile: 8 threads x 8 px wide, 32 rows
+constexpr int VX_CACHE = 2048;         // direct-mapped key cache per CTA (16 KB)
+constexpr int MAX_VX_JOBS = 16;
+constexpr uint64_t VX_KEY_MASK = (1ull << 56) - 1;
+
+struct VxCam {
+    double au[3], av[3], ac[3], t[3];  // already divided by the voxel size
+    int width, height;
+};
+
+struct VxJobDev {
+    const uint16_t* depth;
+    uint64_t depth_stride;  // bytes between frames
+    VxCam cam;
+    uint32_t tile_begin, tiles_x;
+    uint32_t vec;  // rows are 16-byte aligned: 128-bit loads
+};
+
+struct VxParams {
+    VxJobDev job[MAX_VX_JOBS];
+    uint64_t* table;       // hash set, table_mask + 1 slots
+    uint64_t table_mask;
+    uint64_t epoch;        // << 56
+    uint64_t tag;          // << 56
+    uint64_t* records;
+    uint64_t capacity;
+    uint32_t* n_records;
+    uint32_t* set_counts;
+    uint32_t tiles_per_set, set_base, max_depth;
+    int n_jobs, n_batch;
+};
+
+__device__ __forceinline__ uint64_t vx_mix(uint64_t k) {  // murmur3 finaliser
+    k ^= k >> 33; k *= 0xff51afd7ed558ccdull; k ^= k >> 33; k *= 0xc4ceb9fe1a85ec53ull; k ^= k >> 33;
+    return k;
+}
+
+// floor(x) as an int for |x| < 2^31: add 1.5 * 2^52 rounding towards minus infinity, take the low mantissa word
+// (a plain FP64-pipe add; the double -> int conversion instruction runs at a quarter of that rate)
+__device__ __forceinline__ int vx_floor(double x) {
+#ifdef TI_EMULATE
+    return (int)std::floor(x);
+#else
+    return __double2loint(__dadd_rd(x, 6755399441055744.0));
+#endif
+}
+
+__device__ __forceinline__ double vx_u2d(uint32_t v) {  // exact u32 -> double without the conversion pipe
+#ifdef TI_EMULATE
+    return (double)v;
+#else
+    return __hiloint2double(0x43300000, (int)v) - 4503599627370496.0;
+#endif
+}
+
+#ifdef TI_EMULATE
+__device__ __forceinline__ uint64_t vx_exch(uint64_t* p, uint64_t v) { return __atomic_exchange_n(p, v, __ATOMIC_RELAXED); }
+__device__ __forceinline__ uint64_t vx_cas(uint64_t* p, uint64_t expect, uint64_t v) {
+    __atomic_compare_exchange_n(p, &expect, v, false, __ATOMIC_RELAXED, __ATOMIC_RELAXED);
+    return expect;
+}
+__device__ __forceinline__ uint64_t vx_load(const uint64_t* p) { return __atomic_load_n(p, __ATOMIC_RELAXED); }
+#else
+__device__ __forceinline__ uint64_t vx_exch(uint64_t* p, uint64_t v) {
+    return atomicExch(reinterpret_cast<unsigned long long*>(p), (unsigned long long)v);
+}
+__device__ __forceinline__ uint64_t vx_cas(uint64_t* p, uint64_t expect, uint64_t v) {
+    return atomicCAS(reinterpret_cast<unsigned long long*>(p), (unsigned long long)expect, (unsigned long long)v);
+}
+__device__ __forceinline__ uint64_t vx_load(const uint64_t* p) { return *reinterpret_cast<const volatile uint64_t*>(p); }
+#endif
+
+// true when this thread installed `key` (set number and voxel, 56 bits) in the global hash set
+__device__ __forceinline__ bool vx_insert(const VxParams& P, uint64_t key, uint64_t h) {
+    const uint64_t entry = P.epoch | key;
+    uint64_t slot = (h >> 11) & P.table_mask;
+    uint64_t cur = vx_load(P.table + slot);
+    for (;;) {
+        if (cur == entry) return false;
+        if ((cur >> 56) != (P.epoch >> 56)) {  // left over from an earlier launch: free
+            const uint64_t old = vx_cas(P.table + slot, cur, entry);
+            if (old == cur) return true;
+            cur = old;  // somebody else took the slot meanwhile: look at what they put there
+            continue;
+        }
+        slot = (slot + 1) & P.table_mask;
+        cur = vx_load(P.table + slot);
+    }
+}
+
+__global__ void __launch_bounds__(VX_THREADS) voxel_cloud_kernel(const __grid_constant__ VxParams P) {
+    __shared__ uint64_t cache[VX_CACHE];
+    __shared__ uint64_t stage[VX_TW * VX_TH];
+    __shared__ uint32_t s_n, s_cnt, s_base;
+    for (int i = threadIdx.x; i < VX_CACHE; i += VX_THREADS) cache[i] = ~0ull;  // no key has its top byte set
+    if (threadIdx.x == 0) s_n = 0;
+    __syncthreads();
+    const int tx = threadIdx.x & 7, ty = threadIdx.x >> 3;
+    const uint64_t total = (uint64_t)P.tiles_per_set * P.n_batch;
+    for (uint64_t t = blockIdx.x; t < total; t += gridDim.x) {
+        const uint32_t b = (uint32_t)(t / P.tiles_per_set);
+        const uint32_t r = (uint32_t)(t - (uint64_t)b * P.tiles_per_set);
+        int j = 0;
+        while (j + 1 < P.n_jobs && r >= P.job[j + 1].tile_begin) ++j;
+        const VxJobDev& J = P.job[j];
+        const uint32_t lt = r - J.tile_begin;
+        const int tile_y = (int)(lt / J.tiles_x), tile_x = (int)(lt - (uint32_t)tile_y * J.tiles_x);
+        const int v = tile_y * VX_TH + ty, u0 = tile_x * VX_TW + tx * 8;
+        uint32_t dw[4] = {0u, 0u, 0u, 0u};
+        if (v < J.cam.height && u0 < J.cam.width) {
+            const uint16_t* row = reinterpret_cast<const uint16_t*>(reinterpret_cast<const uint8_t*>(J.depth) + (uint64_t)b * J.depth_stride) +
+                                  (size_t)v * J.cam.width;
+            if (J.vec) {  // width % 8 == 0: the 8 pixels are inside the row
+                const uint4 q = ld_stream_u4(row + u0);
+                dw[0] = q.x; dw[1] = q.y; dw[2] = q.z; dw[3] = q.w;
+            } else {
+                for (int k = 0; k < 8; ++k)
+                    if (u0 + k < J.cam.width) dw[k >> 1] |= (uint32_t)row[u0 + k] << ((k & 1) * 16);
+            }
+        }
+        const double vd = vx_u2d((uint32_t)v);
+        const double bx = fma(J.cam.av[0], vd, J.cam.ac[0]);
+        const double by = fma(J.cam.av[1], vd, J.cam.ac[1]);
+        const double bz = fma(J.cam.av[2], vd, J.cam.ac[2]);
+        const uint64_t set_bits = (uint64_t)(P.set_base + b) << 45;
+        uint64_t prev = ~0ull;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const uint32_t d = (dw[k >> 1] >> ((k & 1) * 16)) & 0xFFFFu;
+            const double ud = vx_u2d((uint32_t)(u0 + k)), dd = vx_u2d(d);
+            const int kx = vx_floor(fma(dd, fma(J.cam.au[0], ud, bx), J.cam.t[0]));
+            const int ky = vx_floor(fma(dd, fma(J.cam.au[1], ud, by), J.cam.t[1]));
+            const int kz = vx_floor(fma(dd, fma(J.cam.au[2], ud, bz), J.cam.t[2]));
+            const uint64_t key = set_bits | ((uint64_t)(uint32_t)(kx + 16384) << 30) | ((uint64_t)(uint32_t)(ky + 16384) << 15) |
+                                 (uint64_t)(uint32_t)(kz + 16384);
+            bool fresh = d != 0 && d <= P.max_depth && key != prev;
+            if (fresh) {
+                prev = key;
+                const uint64_t h = vx_mix(key);
+                fresh = vx_exch(&cache[h & (VX_CACHE - 1)], key) != key && vx_insert(P, key, h);
+            }
+            if (fresh) stage[atomicAdd(&s_n, 1u)] = key;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {  // every append of this tile is in; the next tile's come after the third barrier
+            const uint32_t n = s_n;
+            s_n = 0;
+            s_cnt = n;
+            s_base = n ? atomicAdd(P.n_records, n) : 0u;
+            if (n && P.set_counts) atomicAdd(P.set_counts + b, n);
+        }
+        __syncthreads();
+        const uint32_t n = s_cnt, base = s_base;
+        for (uint32_t i = threadIdx.x; i < n; i += VX_THREADS)
+            if ((uint64_t)base + i < P.capacity) P.records[(uint64_t)base + i] = P.tag | stage[i];
+        __syncthreads();
+    }
+}
+
+// records -> centres of the voxels as N x 3 f32 (the cloud type of SlamMap.to_point_cloud, interface.py:134-138);
+// rows past *n_records are left untouched
+__global__ void __launch_bounds__(256) voxel_points_kernel(const uint64_t* records, const uint32_t* n_records, uint64_t max_records,
+                                                           double voxel, float* xyz) {
+    const uint64_t n = min((uint64_t)*n_records, max_records);
+    for (uint64_t i = (uint64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (uint64_t)gridDim.x * 256) {
+        const uint64_t r = records[i];
+        const int kx = (int)((r >> 30) & 0x7FFF) - 16384, ky = (int)((r >> 15) & 0x7FFF) - 16384, kz = (int)(r & 0x7FFF) - 16384;
+        xyz[3 * i + 0] = (float)(((double)kx + 0.5) * voxel);
+        xyz[3 * i + 1] = (float)(((double)ky + 0.5) * voxel);
+        xyz[3 * i + 2] = (float)(((double)kz + 0.5) * voxel);
+    }
+}
+
+}  // namespace ti
+
+using namespace ti;
+
+extern "C" {
+
+int ti_set_voxel_grid(ti_ctx* ctx, double voxel_size_m, uint32_t max_depth_mm) {
+    if (!ctx) return TI_EINVAL;
+    if (!(voxel_size_m > 0.0) || !(voxel_size_m < 1e6)) return fail(ctx, TI_EINVAL, "ti_set_voxel_grid: voxel size must be positive");
+    ctx->voxel_size = voxel_size_m;
+    ctx->voxel_max_depth = max_depth_mm ? std::min<uint32_t>(max_depth_mm, 65535u) : 65535u;
+    return TI_OK;
+}
+
+int ti_voxel_cloud(ti_ctx* ctx, const ti_depth_stream* streams, int n_streams, int n_batch, uint32_t set_base, uint32_t tag,
+                   uint64_t* records, uint64_t capacity, uint32_t* n_records, uint32_t* set_counts) {
+    if (!ctx) return TI_EINVAL;
+    if (n_streams < 0 || n_batch < 0 || (n_streams > 0 && !streams)) return fail(ctx, TI_EINVAL, "ti_voxel_cloud: bad stream array");
+    if (!n_records || (capacity && !records)) return fail(ctx, TI_EINVAL, "ti_voxel_cloud: null records / n_records");
+    if (!(ctx->voxel_size > 0.0)) return fail(ctx, TI_ESTATE, "ti_voxel_cloud: call ti_set_voxel_grid first");
+    if (n_streams > MAX_VX_JOBS) return fail(ctx, TI_EINVAL, "ti_voxel_cloud: at most %d depth streams per call", MAX_VX_JOBS);
+    if ((uint64_t)set_base + (uint64_t)n_batch > 2048u) return fail(ctx, TI_EINVAL, "ti_voxel_cloud: set_base + n_batch must be <= 2048 (11-bit set field)");
+    if (tag > 255u) return fail(ctx, TI_EINVAL, "ti_voxel_cloud: tag must fit 8 bits");
+    TI_CUDA(ctx, cudaSetDevice(ctx->device));
+    TI_CUDA(ctx, cudaMemsetAsync(n_records, 0, sizeof(uint32_t), ctx->stream));
+    if (set_counts && n_batch) TI_CUDA(ctx, cudaMemsetAsync(set_counts, 0, sizeof(uint32_t) * (size_t)n_batch, ctx->stream));
+    if (n_streams == 0 || n_batch == 0) return TI_OK;
+
+    VxParams P{};
+    const double inv = 1.0 / ctx->voxel_size;
+    uint32_t tiles = 0;
+    uint64_t px = 0;
+    for (int i = 0; i < n_streams; ++i) {
+        const ti_depth_stream& S = streams[i];
+        if (S.camera < 0 || S.camera >= TI_MAX_CAMERAS || !ctx->cams[S.camera].has_proj)
+            return fail(ctx, TI_ESTATE, "ti_voxel_cloud: camera slot %d has no projection (call ti_upload_projection)", S.camera);
+        if (!S.depth) return fail(ctx, TI_EINVAL, "ti_voxel_cloud: stream %d has a null depth pointer", i);
+        const CameraSlot& C = ctx->cams[S.camera];
+        VxJobDev& D = P.job[i];
+        D.depth = S.depth;
+        D.depth_stride = S.depth_frame_stride ? S.depth_frame_stride : (uint64_t)C.proj_w * C.proj_h * 2;
+        if (D.depth_stride % 2 || (uintptr_t)S.depth % 2) return fail(ctx, TI_EINVAL, "ti_voxel_cloud: depth must be 2-byte aligned");
+        double reach = 0.0;  // bound on |p| / voxel over the image, every valid depth
+        for (int r = 0; r < 3; ++r) {
+            D.cam.au[r] = C.proj_au[r] * inv; D.cam.av[r] = C.proj_av[r] * inv; D.cam.ac[r] = C.proj_ac[r] * inv; D.cam.t[r] = C.proj_t[r] * inv;
+            const double ray = fabs(D.cam.au[r]) * C.proj_w + fabs(D.cam.av[r]) * C.proj_h + fabs(D.cam.ac[r]);
+            reach = std::max(reach, ray * ctx->voxel_max_depth + fabs(D.cam.t[r]));
+        }
+        if (!(reach < 16383.0))
+            return fail(ctx, TI_EINVAL, "ti_voxel_cloud: camera slot %d reaches %.0f voxels from the body origin; the 15-bit key fields hold "
+                        "16383 (use a larger voxel or a depth cap)", S.camera, reach);
+        D.cam.width = C.proj_w; D.cam.height = C.proj_h;
+        D.tiles_x = (uint32_t)((C.proj_w + VX_TW - 1) / VX_TW);
+        D.tile_begin = tiles;
+        tiles += D.tiles_x * (uint32_t)((C.proj_h + VX_TH - 1) / VX_TH);
+        D.vec = (C.proj_w % 8 == 0) && ((uintptr_t)S.depth % 16 == 0) && (D.depth_stride % 16 == 0);
+        px += (uint64_t)C.proj_w * C.proj_h;
+    }
+    // hash set: twice the pixels of the launch (every pixel could be its own voxel), a power of two; entries of earlier
+    // launches are recognised by their epoch byte, so it is cleared only when the epoch wraps or the table grows
+    uint64_t slots = 1u << 16;
+    while (slots < 2 * px * (uint64_t)n_batch) slots <<= 1;
+    if (slots > ctx->voxel_slots) {
+        TI_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        if (ctx->voxel_table) cudaFree(ctx->voxel_table);
+        ctx->voxel_table = nullptr; ctx->voxel_slots = 0;
+        TI_CUDA(ctx, cudaMalloc(&ctx->voxel_table, slots * sizeof(uint64_t)));
+        ctx->voxel_slots = slots;
+        ctx->voxel_epoch = 0;
+    }
+    if (ctx->voxel_epoch == 0 || ctx->voxel_epoch >= 255) {
+        TI_CUDA(ctx, cudaMemsetAsync(ctx->voxel_table, 0, ctx->voxel_slots * sizeof(uint64_t), ctx->stream));
+        ctx->voxel_epoch = 0;
+    }
+    ctx->voxel_epoch++;
+    P.table = ctx->voxel_table;
+    P.table_mask = ctx->voxel_slots - 1;
+    P.epoch = (uint64_t)ctx->voxel_epoch << 56;
+    P.tag = (uint64_t)tag << 56;
+    P.records = records; P.capacity = capacity; P.n_records = n_records; P.set_counts = set_counts;
+    P.tiles_per_set = tiles; P.set_base = set_base; P.max_depth = ctx->voxel_max_depth;
+    P.n_jobs = n_streams; P.n_batch = n_batch;
+    const uint64_t total = (uint64_t)tiles * n_batch;
+    const int per_sm = ctx->ctas_per_sm > 0 ? ctx->ctas_per_sm : resident_ctas(voxel_cloud_kernel, VX_THREADS, 0, 4);
+    const int grid = (int)std::min<uint64_t>(total, (uint64_t)ctx->sm_count * per_sm);
+    TI_LAUNCH(voxel_cloud_kernel, grid, VX_THREADS, 0, ctx->stream, P);
+    TI_CHECK_LAUNCH(ctx);
+    return TI_OK;
+}
+
+int ti_voxel_points(ti_ctx* ctx, const uint64_t* records, const uint32_t* n_records, uint64_t max_records, float* xyz) {
+    if (!ctx) return TI_EINVAL;
+    if (!n_records || (max_records && (!records || !xyz))) return fail(ctx, TI_EINVAL, "ti_voxel_points: null argument");
+    if (!(ctx->voxel_size > 0.0)) return fail(ctx, TI_ESTATE, "ti_voxel_points: call ti_set_voxel_grid first");
+    if (max_records == 0) return TI_OK;
+    TI_CUDA(ctx, cudaSetDevice(ctx->device));
+    const int grid = (int)std::min<uint64_t>((max_records + 255) / 256, (uint64_t)ctx->sm_count * 8);
+    TI_LAUNCH(voxel_points_kernel, grid, 256, 0, ctx->stream, records, n_records, max_records, ctx->voxel_size, xyz);
+    TI_CHECK_LAUNCH(ctx);
+    return TI_OK;
+}
+
+}  // extern "C"

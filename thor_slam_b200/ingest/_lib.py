@@ -38,6 +38,12 @@ class TiStream(C.Structure):
     ]
 
 
+class TiDepthStream(C.Structure):
+    """``struct ti_depth_stream``."""
+
+    _fields_ = [("camera", C.c_int32), ("reserved", C.c_int32), ("depth", C.c_void_p), ("depth_frame_stride", C.c_uint64)]
+
+
 # name -> (restype, argtypes); every symbol declared in include/thoringest.h
 SIGNATURES: dict[str, tuple] = {
     "ti_abi_version": (C.c_int, []),
@@ -59,6 +65,10 @@ SIGNATURES: dict[str, tuple] = {
     "ti_convert": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_uint64, C.c_uint64]),
     "ti_rectify": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_uint64, C.c_uint64]),
     "ti_backproject": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_uint64, C.c_uint64, C.c_uint64]),
+    "ti_set_voxel_grid": (C.c_int, [C.c_void_p, C.c_double, C.c_uint32]),
+    "ti_voxel_cloud": (C.c_int, [C.c_void_p, C.POINTER(TiDepthStream), C.c_int, C.c_int, C.c_uint32, C.c_uint32, C.c_void_p, C.c_uint64,
+                                 C.c_void_p, C.c_void_p]),
+    "ti_voxel_points": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]),
     "ti_ingest": (C.c_int, [C.c_void_p, C.POINTER(TiStream), C.c_int, C.c_int]),
     "ti_ingest_host": (C.c_int, [C.c_void_p, C.POINTER(TiStream), C.c_int, C.c_int, C.c_int]),
     "ti_ingest_host_submit": (C.c_int, [C.c_void_p, C.POINTER(TiStream), C.c_int, C.c_int, C.c_int, C.POINTER(C.c_uint64)]),

@@ -15,7 +15,7 @@ from typing import Any, Sequence
 import numpy as np
 
 from thor_slam_b200.ingest import formats as F
-from thor_slam_b200.ingest._lib import TI_EINVAL, TI_OK, IngestLibrary, TiStream, default_library
+from thor_slam_b200.ingest._lib import TI_EINVAL, TI_OK, IngestLibrary, TiDepthStream, TiStream, default_library
 
 
 def _is_torch(x: Any) -> bool:
@@ -264,6 +264,34 @@ class IngestContext:
     def ingest_host_wait(self, ticket: int) -> None:
         """Block until the batch submitted under ``ticket`` has landed in its destination buffers."""
         self._check(self.lib.ti_ingest_host_wait(self._h, ticket))
+
+    # -- voxel down-sampled cloud ------------------------------------------------
+    def set_voxel_grid(self, voxel_size_m: float = 0.05, max_depth_mm: int = 10000) -> None:
+        """Grid of the rig-wide cloud; defaults are nvblox's (``launch/thor_nvblox.launch.py:26-31``). ``max_depth_mm`` 0 = no cap."""
+        self._check(self.lib.ti_set_voxel_grid(self._h, float(voxel_size_m), int(max_depth_mm)))
+        self.voxel_size = float(voxel_size_m)
+
+    def voxel_cloud(self, depth_streams: Sequence[tuple[int, Any]], records: Any, n_records: Any, set_counts: Any = None,
+                    set_base: int = 0, tag: int = 0) -> None:
+        """``ti_voxel_cloud``: ``depth_streams`` = [(camera slot, depth [n_batch, H, W] u16), ...]; ``records``: u64/i64 [capacity];
+        ``n_records``: u32/i32 [1]; ``set_counts``: u32/i32 [n_batch] or ``None``.  One record per occupied voxel per frame set."""
+        arr = (TiDepthStream * max(1, len(depth_streams)))()
+        n_batch = None
+        for i, (cam, depth) in enumerate(depth_streams):
+            nb = int(depth.shape[0])
+            if n_batch is None:
+                n_batch = nb
+            elif nb != n_batch:
+                raise ValueError(f"depth stream {i} carries {nb} frames, earlier streams carry {n_batch}")
+            arr[i].camera, arr[i].depth, arr[i].depth_frame_stride = int(cam), self._ptr(depth), self._batch_stride(depth)
+        capacity = int(records.shape[0]) if records is not None else 0
+        self._check(self.lib.ti_voxel_cloud(self._h, arr, len(depth_streams), n_batch or 0, int(set_base), int(tag), self._ptr(records), capacity,
+                                            self._ptr(n_records), self._ptr(set_counts)))
+
+    def voxel_points(self, records: Any, n_records: Any, xyz: Any) -> Any:
+        """``ti_voxel_points``: voxel centres ``[capacity, 3]`` f32 of the first ``*n_records`` records (``N x 3`` cloud contract)."""
+        self._check(self.lib.ti_voxel_points(self._h, self._ptr(records), self._ptr(n_records), int(xyz.shape[0]), self._ptr(xyz)))
+        return xyz
 
     # -- multi-GPU ---------------------------------------------------------------
     def nccl_unique_id(self) -> bytes:
