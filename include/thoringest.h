@@ -104,7 +104,8 @@ typedef enum ti_option {
     TI_OPT_DEBUG = 5,                 /* bring-up switches; 0 in production (non-zero MAY change results) */
     TI_OPT_FRAMES_PER_UNIT = 6,       /* frames of a batch sharing one LUT fetch in the TMA kernels (default 16; pair-window: 0 = automatic) */
     TI_OPT_STAGES = 7,                /* shared-memory ring depth of the TMA kernels, 2..8 (default 6 pair-window, reduced to fit; 2 shifted-copy) */
-    TI_OPT_LUT_PREFETCH = 8           /* 1: consumers prefetch the next unit's LUT into a second register set (default 0) */
+    TI_OPT_LUT_PREFETCH = 8,          /* 1: consumers prefetch the next unit's LUT into a second register set (default 0) */
+    TI_OPT_PUSH_BLOCKS = 9            /* CTAs of the peer-store copy kernels of ti_cloud_push / ti_inbox_take (default 32) */
 } ti_option;
 int ti_set_option(ti_ctx* ctx, int option, int value);
 int ti_device_sm_count(const ti_ctx* ctx);
@@ -234,9 +235,19 @@ int ti_nccl_unique_id(void* id128);
 int ti_nccl_init(ti_ctx* ctx, const void* id128, int rank, int world);
 /* Gather of per-GPU body-frame clouds to `root` over NVLink: rank r contributes
  * bytes_per_rank[r] bytes from `local` (DEVICE); on root they land back to back in `gathered`
- * (DEVICE, sum of bytes_per_rank) in rank order.  bytes_per_rank: HOST array of `world`. */
+ * (DEVICE, sum of bytes_per_rank) in rank order.  bytes_per_rank: HOST array of `world`.
+ * The exchange runs on the context's own EXCHANGE STREAM: it starts after everything enqueued on the ingest stream so far
+ * (an event), and work enqueued on the ingest stream afterwards - the next batch's kernels - overlaps it.  Nobody may read
+ * `gathered` or overwrite `local` before ti_gather_wait(). */
 int ti_gather_clouds(ti_ctx* ctx, const void* local, void* gathered, const uint64_t* bytes_per_rank,
                      int root);
+/* Wait for the last exchange enqueued by ti_gather_clouds / ti_cloud_push / ti_inbox_take.  on_stream != 0: the ingest
+ * stream waits (device side, returns at once); on_stream == 0: the calling thread blocks. */
+int ti_gather_wait(ti_ctx* ctx, int on_stream);
+/* Sizes of a variable-length gather: every rank contributes *n_local (DEVICE u32, e.g. the n_records of ti_voxel_cloud);
+ * counts (HOST, `world` entries) receives all of them.  All-gather + read-back on the exchange stream; blocks the calling
+ * thread until the counts are there (the ingest stream keeps running what was enqueued meanwhile). */
+int ti_gather_counts(ti_ctx* ctx, const uint32_t* n_local, uint32_t* counts);
 int ti_nccl_barrier(ti_ctx* ctx);
 
 /* Peer-visible cloud buffer: allocated on this GPU, exported as a 64-byte IPC handle, opened
@@ -246,6 +257,26 @@ int ti_peer_alloc(ti_ctx* ctx, uint64_t bytes, void** dev_ptr, void* handle64);
 int ti_peer_open(ti_ctx* ctx, const void* handle64, void** dev_ptr);
 int ti_peer_close(ti_ctx* ctx, void* dev_ptr);
 int ti_peer_free(ti_ctx* ctx, void* dev_ptr);
+
+
+/* ---- the exchange as our own kernels over peer memory (no collective library, no host round trip) --------------------
+ * An INBOX is a peer buffer (ti_peer_alloc on the fusing rank, ti_peer_open elsewhere) of TI_INBOX_HEADER_BYTES + 8 *
+ * capacity bytes: a header {u32 n_records, done, gen, error} followed by u64 records.  Producers append their ti_voxel_cloud
+ * lists with stores that cross NVLink; the root takes one generation at a time.  All calls enqueue on the exchange stream. */
+#define TI_INBOX_HEADER_BYTES 128
+/* Root, once, before the handle is shared: zero the header (generation 0). */
+int ti_inbox_init(ti_ctx* ctx, void* inbox);
+/* Append records[0 .. *n_records) (DEVICE; *n_records is read on the device when the ingest stream reaches this point) to
+ * `inbox` (own or peer-mapped) for generation `gen`: waits on the device until the inbox is at `gen`, reserves the slots with
+ * one system-scope atomic, copies with peer stores, then reports this rank done.  Records past inbox_capacity are dropped
+ * (the header's count still includes them).  `records` may be reused after ti_gather_wait(). */
+int ti_cloud_push(ti_ctx* ctx, const uint64_t* records, const uint32_t* n_records, void* inbox, uint64_t inbox_capacity,
+                  uint32_t gen);
+/* Root: wait on the device until `world` ranks have reported done for the inbox's current generation, copy
+ * min(count, inbox_capacity, dst_capacity) records to dst (DEVICE), write status[0] = count, status[1] = error flag
+ * (DEVICE u32[2]; error != 0: a peer missed its 4 s deadline), empty the inbox and advance its generation. */
+int ti_inbox_take(ti_ctx* ctx, void* inbox, uint64_t inbox_capacity, uint32_t world, uint64_t* dst, uint64_t dst_capacity,
+                  uint32_t* status);
 
 #ifdef __cplusplus
 }

@@ -50,6 +50,14 @@ def _worker(rank: int, world: int, port: int, n_sets: int, out: dict) -> None:
             out["n"] = int(fused.shape[0])
         else:
             assert fused is None
+        # variable-length record lists (the gloo face of gather_records): capacity 64, rank r holds 5 + 9 r records
+        n = 5 + 9 * rank
+        rec = torch.zeros(64, dtype=torch.int64)
+        rec[:n] = torch.arange(n) + 1000 * rank
+        fused, counts = CloudGather(None, rank, world, root=0).gather_records(rec, torch.tensor([n], dtype=torch.int32))
+        assert counts == [5 + 9 * r for r in range(world)]
+        if rank == 0:
+            out["rec_ok"] = bool(torch.equal(fused, torch.cat([torch.arange(5 + 9 * r) + 1000 * r for r in range(world)])))
     finally:
         dist.destroy_process_group()
 
@@ -60,3 +68,4 @@ def test_gloo_world2_gather():
     out = mgr.dict()
     mp.spawn(_worker, args=(world, _free_port(), n_sets, out), nprocs=world, join=True)
     assert out["ok"] and out["n"] == sum(10 + 3 * i for i in range(n_sets))
+    assert out["rec_ok"]

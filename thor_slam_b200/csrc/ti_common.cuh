@@ -201,6 +201,13 @@ struct ti_ctx {
     // NCCL (dlopen)
     void* nccl_comm = nullptr;
     int rank = 0, world = 1;
+    // exchange step on its own stream (ti_nccl.cu)
+    cudaStream_t s_comm = nullptr;
+    cudaEvent_t ev_compute = nullptr, ev_gather = nullptr, ev_counts = nullptr;
+    uint32_t* d_comm_words = nullptr;  // 256 words: gathered counts, push reservations, the barrier's zero
+    uint32_t* h_comm_words = nullptr;  // pinned mirror
+    bool gather_pending = false;
+    int push_blocks = 0;  // CTAs of the peer-store copy kernels (0 = 32)
 };
 
 void ti_nccl_teardown(ti_ctx* ctx);  // ti_nccl.cu

@@ -27,6 +27,7 @@ struct NcclApi {
     ncclResult_t (*Send)(const void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*Recv)(void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllGather)(const void*, void*, size_t, int, ncclComm_t, cudaStream_t) = nullptr;
     const char* (*GetErrorString)(ncclResult_t) = nullptr;
     std::string why;
 };
@@ -56,6 +57,7 @@ NcclApi& nccl() {
     LOAD(Send, "ncclSend")
     LOAD(Recv, "ncclRecv")
     LOAD(AllReduce, "ncclAllReduce")
+    LOAD(AllGather, "ncclAllGather")
     LOAD(GetErrorString, "ncclGetErrorString")
 #undef LOAD
     return api;
@@ -63,6 +65,7 @@ NcclApi& nccl() {
 
 constexpr int NCCL_UINT8 = 1;   // ncclUint8
 constexpr int NCCL_INT32 = 2;   // ncclInt32
+constexpr int NCCL_UINT32 = 3;  // ncclUint32
 constexpr int NCCL_SUM = 0;     // ncclSum
 
 #define TI_NCCL(ctx, expr)                                                                     \
@@ -74,9 +77,36 @@ constexpr int NCCL_SUM = 0;     // ncclSum
 
 }  // namespace
 
+// The exchange step runs on its own stream so that it overlaps the next batch's kernels: the comm
+// stream first waits for what the ingest stream has enqueued so far, and whoever needs the result waits for ev_gather.
+int ti_comm_ready(ti_ctx* ctx) {
+    if (ctx->s_comm) return TI_OK;
+    TI_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->s_comm, cudaStreamNonBlocking));
+    TI_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_compute, cudaEventDisableTiming));
+    TI_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_gather, cudaEventDisableTiming));
+    TI_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_counts, cudaEventDisableTiming));
+    TI_CUDA(ctx, cudaMalloc(&ctx->d_comm_words, 256 * sizeof(uint32_t)));
+    TI_CUDA(ctx, cudaMemset(ctx->d_comm_words, 0, 256 * sizeof(uint32_t)));
+    TI_CUDA(ctx, cudaMallocHost(&ctx->h_comm_words, 256 * sizeof(uint32_t)));
+    return TI_OK;
+}
+
+int ti_comm_follow_compute(ti_ctx* ctx) {
+    TI_CUDA(ctx, cudaEventRecord(ctx->ev_compute, ctx->stream));
+    TI_CUDA(ctx, cudaStreamWaitEvent(ctx->s_comm, ctx->ev_compute, 0));
+    return TI_OK;
+}
+
 void ti_nccl_teardown(ti_ctx* ctx) {
     if (ctx->nccl_comm && nccl().handle) nccl().CommDestroy((ncclComm_t)ctx->nccl_comm);
     ctx->nccl_comm = nullptr;
+    if (ctx->s_comm) {
+        cudaStreamSynchronize(ctx->s_comm);
+        cudaEventDestroy(ctx->ev_compute); cudaEventDestroy(ctx->ev_gather); cudaEventDestroy(ctx->ev_counts);
+        cudaFree(ctx->d_comm_words); cudaFreeHost(ctx->h_comm_words);
+        cudaStreamDestroy(ctx->s_comm);
+        ctx->s_comm = nullptr; ctx->d_comm_words = nullptr; ctx->h_comm_words = nullptr;
+    }
 }
 
 extern "C" {
@@ -119,22 +149,61 @@ int ti_gather_clouds(ti_ctx* ctx, const void* local, void* gathered, const uint6
     TI_CUDA(ctx, cudaSetDevice(ctx->device));
     const uint64_t mine = bytes_per_rank[ctx->rank];
     if (mine && !local) return ti::fail(ctx, TI_EINVAL, "ti_gather_clouds: null local buffer");
+    int rc = ti_comm_ready(ctx);
+    if (rc != TI_OK) return rc;
+    if ((rc = ti_comm_follow_compute(ctx)) != TI_OK) return rc;
     if (ctx->rank == root) {
         uint64_t off = 0;
         for (int r = 0; r < root; ++r) off += bytes_per_rank[r];
         if (mine)  // own slice: device-to-device copy, no NCCL self send
-            TI_CUDA(ctx, cudaMemcpyAsync((uint8_t*)gathered + off, local, mine, cudaMemcpyDeviceToDevice, ctx->stream));
-        TI_NCCL(ctx, a.GroupStart());
+            TI_CUDA(ctx, cudaMemcpyAsync((uint8_t*)gathered + off, local, mine, cudaMemcpyDeviceToDevice, ctx->s_comm));
+        ncclResult_t first = 0;  // the group is always closed, whatever a Recv answers
+        ncclResult_t r0 = a.GroupStart();
+        if (r0 != 0) return ti::fail(ctx, TI_ENCCL, "ncclGroupStart failed: %s", a.GetErrorString(r0));
         off = 0;
         for (int r = 0; r < ctx->world; ++r) {
-            if (r != root && bytes_per_rank[r])
-                TI_NCCL(ctx, a.Recv((uint8_t*)gathered + off, bytes_per_rank[r], NCCL_UINT8, r, comm, ctx->stream));
+            if (r != root && bytes_per_rank[r] && first == 0)
+                first = a.Recv((uint8_t*)gathered + off, bytes_per_rank[r], NCCL_UINT8, r, comm, ctx->s_comm);
             off += bytes_per_rank[r];
         }
-        TI_NCCL(ctx, a.GroupEnd());
+        const ncclResult_t r1 = a.GroupEnd();
+        if (first != 0) return ti::fail(ctx, TI_ENCCL, "ncclRecv failed: %s", a.GetErrorString(first));
+        if (r1 != 0) return ti::fail(ctx, TI_ENCCL, "ncclGroupEnd failed: %s", a.GetErrorString(r1));
     } else if (mine) {
-        TI_NCCL(ctx, a.Send(local, mine, NCCL_UINT8, root, comm, ctx->stream));
+        TI_NCCL(ctx, a.Send(local, mine, NCCL_UINT8, root, comm, ctx->s_comm));
     }
+    TI_CUDA(ctx, cudaEventRecord(ctx->ev_gather, ctx->s_comm));
+    ctx->gather_pending = true;
+    return TI_OK;
+}
+
+int ti_gather_wait(ti_ctx* ctx, int on_stream) {
+    if (!ctx) return TI_EINVAL;
+    if (!ctx->gather_pending) return TI_OK;
+    TI_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (on_stream) {
+        TI_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_gather, 0));
+    } else {
+        TI_CUDA(ctx, cudaEventSynchronize(ctx->ev_gather));
+        ctx->gather_pending = false;
+    }
+    return TI_OK;
+}
+
+int ti_gather_counts(ti_ctx* ctx, const uint32_t* n_local, uint32_t* counts) {
+    if (!ctx) return TI_EINVAL;
+    if (!ctx->nccl_comm) return ti::fail(ctx, TI_ESTATE, "ti_gather_counts: call ti_nccl_init first");
+    if (!n_local || !counts) return ti::fail(ctx, TI_EINVAL, "ti_gather_counts: null argument");
+    if (ctx->world > 256) return ti::fail(ctx, TI_EINVAL, "ti_gather_counts: at most 256 ranks");
+    TI_CUDA(ctx, cudaSetDevice(ctx->device));
+    int rc = ti_comm_ready(ctx);
+    if (rc != TI_OK) return rc;
+    if ((rc = ti_comm_follow_compute(ctx)) != TI_OK) return rc;
+    TI_NCCL(ctx, nccl().AllGather(n_local, ctx->d_comm_words, 1, NCCL_UINT32, (ncclComm_t)ctx->nccl_comm, ctx->s_comm));
+    TI_CUDA(ctx, cudaMemcpyAsync(ctx->h_comm_words, ctx->d_comm_words, sizeof(uint32_t) * ctx->world, cudaMemcpyDeviceToHost, ctx->s_comm));
+    TI_CUDA(ctx, cudaEventRecord(ctx->ev_counts, ctx->s_comm));
+    TI_CUDA(ctx, cudaEventSynchronize(ctx->ev_counts));  // the ingest stream keeps running whatever was enqueued after this call's event
+    for (int r = 0; r < ctx->world; ++r) counts[r] = ctx->h_comm_words[r];
     return TI_OK;
 }
 
@@ -142,11 +211,9 @@ int ti_nccl_barrier(ti_ctx* ctx) {
     if (!ctx) return TI_EINVAL;
     if (!ctx->nccl_comm) return ti::fail(ctx, TI_ESTATE, "ti_nccl_barrier: call ti_nccl_init first");
     TI_CUDA(ctx, cudaSetDevice(ctx->device));
-    static thread_local int* d_flag = nullptr;
-    if (!d_flag) {
-        TI_CUDA(ctx, cudaMalloc(&d_flag, sizeof(int)));
-        TI_CUDA(ctx, cudaMemset(d_flag, 0, sizeof(int)));
-    }
+    const int rc = ti_comm_ready(ctx);
+    if (rc != TI_OK) return rc;
+    int* d_flag = reinterpret_cast<int*>(ctx->d_comm_words + 255);  // stays 0: a sum of zeros
     TI_NCCL(ctx, nccl().AllReduce(d_flag, d_flag, 1, NCCL_INT32, NCCL_SUM, (ncclComm_t)ctx->nccl_comm, ctx->stream));
     TI_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return TI_OK;

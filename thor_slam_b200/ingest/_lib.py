@@ -14,6 +14,7 @@ from pathlib import Path
 
 LIB_PATH = Path(__file__).resolve().parent.parent / "libthoringest.so"
 ABI_VERSION = 1
+INBOX_HEADER_BYTES = 128  # TI_INBOX_HEADER_BYTES
 
 TI_OK, TI_EINVAL, TI_ECUDA, TI_ENCCL, TI_ESTATE, TI_ENOMEM = range(6)
 
@@ -76,7 +77,12 @@ SIGNATURES: dict[str, tuple] = {
     "ti_nccl_unique_id": (C.c_int, [C.c_void_p]),
     "ti_nccl_init": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int]),
     "ti_gather_clouds": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_uint64), C.c_int]),
+    "ti_gather_wait": (C.c_int, [C.c_void_p, C.c_int]),
+    "ti_gather_counts": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_uint32)]),
     "ti_nccl_barrier": (C.c_int, [C.c_void_p]),
+    "ti_inbox_init": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "ti_cloud_push": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32]),
+    "ti_inbox_take": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, C.c_void_p, C.c_uint64, C.c_void_p]),
     "ti_peer_alloc": (C.c_int, [C.c_void_p, C.c_uint64, C.POINTER(C.c_void_p), C.c_void_p]),
     "ti_peer_open": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]),
     "ti_peer_close": (C.c_int, [C.c_void_p, C.c_void_p]),

@@ -310,6 +310,30 @@ class IngestContext:
         arr = (C.c_uint64 * len(bytes_per_rank))(*[int(b) for b in bytes_per_rank])
         self._check(self.lib.ti_gather_clouds(self._h, self._ptr(local), self._ptr(gathered), arr, root))
 
+    def gather_wait(self, on_stream: bool = False) -> None:
+        """Wait for the last exchange (``ti_gather_wait``): the ingest stream waits if ``on_stream``, else this thread blocks."""
+        self._check(self.lib.ti_gather_wait(self._h, 1 if on_stream else 0))
+
+    def gather_counts(self, n_local: Any, world: int) -> list[int]:
+        """All ranks' ``*n_local`` (a device u32) on the host - sizes of a variable-length gather (``ti_gather_counts``)."""
+        out = (C.c_uint32 * world)()
+        self._check(self.lib.ti_gather_counts(self._h, self._ptr(n_local), out))
+        return [int(x) for x in out]
+
+    def inbox_init(self, inbox: int) -> None:
+        self._check(self.lib.ti_inbox_init(self._h, C.c_void_p(inbox)))
+
+    def cloud_push(self, records: Any, n_records: Any, inbox: int, inbox_capacity: int, gen: int) -> None:
+        """Append a ``ti_voxel_cloud`` list to a (peer-mapped) inbox with peer stores on the exchange stream (``ti_cloud_push``)."""
+        self._check(self.lib.ti_cloud_push(self._h, self._ptr(records), self._ptr(n_records), C.c_void_p(inbox), int(inbox_capacity), int(gen)))
+
+    def inbox_take(self, inbox: int, inbox_capacity: int, world: int, dst: Any, status: Any) -> None:
+        """Root: take one generation of an inbox into ``dst`` (u64/i64 [capacity]); ``status`` u32/i32 [2] = (count, error)."""
+        cap = int(dst.shape[0]) if dst is not None else 0
+        self._check(self.lib.ti_inbox_take(self._h, C.c_void_p(inbox), int(inbox_capacity), int(world), self._ptr(dst), cap, self._ptr(status)))
+
+    OPT_PUSH_BLOCKS = 9
+
     def nccl_barrier(self) -> None:
         self._check(self.lib.ti_nccl_barrier(self._h))
 

@@ -6,9 +6,15 @@ is the gather of the per-GPU body-frame point clouds on the fusing rank (SURVEY.
 
 * ``shard_frame_sets``     - frame set ``i`` -> rank ``i % world`` (perfect balance, any batch size);
 * ``exchange_counts``      - tiny all-gather of per-rank byte counts over ``torch.distributed`` (plumbing);
-* ``CloudGather.gather``   - grouped ``ncclSend``/``ncclRecv`` inside ``libthoringest.so`` on the ingest
-                             stream (``ti_gather_clouds``), or ``torch.distributed.gather`` when the process
-                             group is ``gloo`` (CPU tests of the host logic);
+* ``CloudGather.gather``   - grouped ``ncclSend``/``ncclRecv`` inside ``libthoringest.so`` on the library's own
+                             exchange stream (``ti_gather_clouds``: it starts behind the kernels enqueued so far
+                             and overlaps the ones enqueued next), or ``torch.distributed`` send/recv when the
+                             process group is ``gloo`` (CPU tests of the host logic);
+* ``CloudGather.gather_records`` - the same for the variable-length voxel lists of ``ti_voxel_cloud``: the device
+                             counts are all-gathered on the exchange stream (``ti_gather_counts``), no torch collective;
+* ``RecordExchange``       - the exchange as our own kernels: producers append their lists to an inbox in the root's
+                             HBM with peer stores over NVLink, reserving slots with one system-scope atomic
+                             (``ti_cloud_push`` / ``ti_inbox_take``); no collective library and no host round trip;
 * ``PeerCloudBuffer``      - the gather FUSED into the producing kernel: the root allocates the fused
                              cloud buffer, exports a CUDA-IPC handle, every rank maps it and hands its slice
                              to ``ti_backproject`` as the xyz destination, so the kernel's stores go straight
@@ -93,6 +99,7 @@ class CloudGather:
         self.ctx, self.rank, self.world, self.root, self.group = ctx, rank, world, root, group
         self.backend = dist.get_backend(group) if dist.is_initialized() else "none"
         self._nccl_ready = False
+        self._keep: Any = None
 
     def _ensure_nccl(self) -> None:
         if self._nccl_ready:
@@ -103,29 +110,125 @@ class CloudGather:
         self.ctx.nccl_init(uid[0], self.rank, self.world)
         self._nccl_ready = True
 
-    def gather(self, local: torch.Tensor, gathered: torch.Tensor | None = None) -> torch.Tensor | None:
-        """Returns the fused buffer on ``root`` (``None`` elsewhere).  ``local`` may differ in length per rank."""
+    def gather(self, local: torch.Tensor, gathered: torch.Tensor | None = None, wait: bool = True) -> torch.Tensor | None:
+        """Returns the fused buffer on ``root`` (``None`` elsewhere).  ``local`` may differ in length per rank.
+
+        ``wait=False`` (NCCL only) returns as soon as the exchange is enqueued on the library's exchange stream; the caller
+        goes on enqueueing the next batch and calls :meth:`wait` before touching ``gathered`` or overwriting ``local``."""
         nbytes = local.numel() * local.element_size()
         sizes = exchange_counts(nbytes, self.group)
+        return self._gather_sized(local, gathered, sizes, wait)
+
+    def _gather_sized(self, local: torch.Tensor, gathered: torch.Tensor | None, sizes: list[int], wait: bool) -> torch.Tensor | None:
         total = sum(sizes)
+        nbytes = sizes[self.rank]
         if self.backend == "nccl" and local.is_cuda:
             self._ensure_nccl()
             if self.rank == self.root and gathered is None:
                 gathered = torch.empty(total // local.element_size(), dtype=local.dtype, device=local.device)
-            self.ctx.gather_clouds(local.contiguous(), gathered, sizes, self.root)
+            self._keep = local.contiguous()  # the send reads it asynchronously: keep it alive until wait()
+            self.ctx.gather_clouds(self._keep, gathered, sizes, self.root)
+            if wait:
+                self.wait()
             return gathered if self.rank == self.root else None
         # gloo / CPU: host-logic path used by the CPU tests
-        flat = local.contiguous().view(-1)
+        flat = local.contiguous().view(-1)[: nbytes // local.element_size()]
         if self.rank == self.root:
             parts = [torch.empty(s // local.element_size(), dtype=local.dtype) for s in sizes]
             parts[self.root] = flat
             for r in range(self.world):
                 if r != self.root and sizes[r]:
                     dist.recv(parts[r], src=r, group=self.group)
-            return torch.cat(parts) if gathered is None else gathered.view(-1).copy_(torch.cat(parts))
+            return torch.cat(parts) if gathered is None else gathered.view(-1)[: total // local.element_size()].copy_(torch.cat(parts))
         if nbytes:
             dist.send(flat, dst=self.root, group=self.group)
         return None
+
+    def wait(self, on_stream: bool = False) -> None:
+        """Block (or make the ingest stream wait) until the last ``gather(..., wait=False)`` has landed."""
+        if self.backend == "nccl" and self.ctx is not None and self._nccl_ready:
+            self.ctx.gather_wait(on_stream)
+            if not on_stream:
+                self._keep = None
+
+    def gather_records(self, records: torch.Tensor, n_records: torch.Tensor, gathered: torch.Tensor | None = None,
+                       wait: bool = True) -> tuple[torch.Tensor | None, list[int]]:
+        """Variable-length gather of ``ti_voxel_cloud`` lists: rank r contributes ``records[:n_records]`` (a DEVICE count).
+        Returns (fused list on root else ``None``, records per rank)."""
+        if self.backend == "nccl" and records.is_cuda:
+            self._ensure_nccl()
+            counts = self.ctx.gather_counts(n_records, self.world)
+        else:
+            mine = torch.tensor([int(n_records.view(-1)[0].item())], dtype=torch.int64)
+            out = [torch.zeros_like(mine) for _ in range(self.world)]
+            dist.all_gather(out, mine, group=self.group)
+            counts = [int(t.item()) for t in out]
+        cap = int(records.shape[0])
+        counts = [min(c, cap) for c in counts]  # a truncated list still reports its full count
+        sizes = [c * records.element_size() for c in counts]
+        return self._gather_sized(records, gathered, sizes, wait), counts
+
+
+class RecordExchange:
+    """The cloud exchange as the library's own kernels over peer memory (``thor_slam_b200/csrc/ti_push.cu``).
+
+    The root owns ``slots`` inboxes (used round robin, so a producer does not wait for the root to drain the previous round);
+    every rank - the root included - appends its ``ti_voxel_cloud`` list with :meth:`push`; the root collects a round with
+    :meth:`take`.  Everything runs on the library's exchange stream behind an event of the ingest stream."""
+
+    def __init__(self, ctx: IngestContext, rank: int, world: int, capacity: int, root: int = 0, slots: int = 2, group: Any = None) -> None:
+        from thor_slam_b200.ingest._lib import INBOX_HEADER_BYTES
+
+        self.ctx, self.rank, self.world, self.root, self.capacity, self.slots = ctx, rank, world, root, int(capacity), slots
+        self.group = group
+        nbytes = INBOX_HEADER_BYTES + 8 * self.capacity
+        handles: list[Any] = [None] * slots
+        self._owned: list[int] = []
+        self._mapped: list[int] = []
+        if rank == root:
+            for k in range(slots):
+                ptr, h = ctx.peer_alloc(nbytes)
+                ctx.inbox_init(ptr)
+                self._owned.append(ptr)
+                handles[k] = h
+        dist.broadcast_object_list(handles, src=root, group=group)
+        if rank == root:
+            self.inbox = list(self._owned)
+        else:
+            self._mapped = [ctx.peer_open(h) for h in handles]
+            self.inbox = list(self._mapped)
+        self.round = 0
+        self.taken = 0
+
+    def push(self, records: Any, n_records: Any) -> None:
+        """Append this rank's list for the current round; rounds advance with every call."""
+        k = self.round
+        self.ctx.cloud_push(records, n_records, self.inbox[k % self.slots], self.capacity, k // self.slots)
+        self.round += 1
+
+    def take(self, dst: Any, status: Any) -> None:
+        """Root only: the next round's fused list into ``dst`` (u64 [>= capacity]), ``status`` = (count, error flag)."""
+        assert self.rank == self.root
+        k = self.taken
+        self.ctx.inbox_take(self.inbox[k % self.slots], self.capacity, self.world, dst, status)
+        self.taken += 1
+
+    def wait(self, on_stream: bool = False) -> None:
+        self.ctx.gather_wait(on_stream)
+
+    def close(self) -> None:
+        """Collective: nobody may still be storing into the root's inboxes when they are freed."""
+        self.ctx.gather_wait(False)
+        if dist.is_initialized():
+            dist.barrier(group=self.group)
+        for p in self._mapped:
+            self.ctx.peer_close(p)
+        self._mapped = []
+        if dist.is_initialized():
+            dist.barrier(group=self.group)
+        for p in self._owned:
+            self.ctx.peer_free(p)
+        self._owned = []
 
 
 class PeerCloudBuffer:
@@ -168,9 +271,15 @@ class PeerCloudBuffer:
         return torch.as_tensor(obj, device=torch.device("cuda", self.ctx.device))
 
     def close(self) -> None:
+        """Collective: peers unmap first, then the owner frees (a barrier on either side, so no store is in flight)."""
+        self.ctx.sync()
+        if dist.is_initialized():
+            dist.barrier()
         if self._mapped is not None:
             self.ctx.peer_close(self._mapped)
             self._mapped = None
+        if dist.is_initialized():
+            dist.barrier()
         if self._owned is not None:
             self.ctx.peer_free(self._owned)
             self._owned = None
