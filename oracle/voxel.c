@@ -9,7 +9,8 @@
  *
  *     a_u = 1e-3 * R[:,0] / fx,  a_v = 1e-3 * R[:,1] / fy,  a_c = 1e-3 * (R[:,2] - R[:,0]/fx * cx - R[:,1]/fy * cy)
  *     (each then multiplied by 1 / voxel_size, as is t)
- *     k = floor( fma(d, fma(a_u, u, fma(a_v, v, a_c)), t) )          d = depth in millimetres
+ *     k = floor( fma(d, fma(a_u, u, fma(a_v, v, a_c)), t + 16384) ) - 16384      d = depth in millimetres; 16384 = bias of
+ *                                                                                the 15-bit record fields, added before the one rounding
  *     valid = 0 < d <= max_depth_mm                                   examples/rgbd_stream.py:121-123 + the nvblox cap
  *
  * IEEE fma is correctly rounded everywhere, so these keys are bit-identical to the CUDA kernel's; tests also compare them
@@ -28,7 +29,7 @@ void oracle_voxel_constants(const double k[4], const double m[12], double voxel,
         out[r] = (1e-3 * ax) * inv;
         out[3 + r] = (1e-3 * ay) * inv;
         out[6 + r] = (1e-3 * (az - ax * k[2] - ay * k[3])) * inv;
-        out[9 + r] = m[4 * r + 3] * inv;
+        out[9 + r] = m[4 * r + 3] * inv + 16384.0;
     }
 }
 
@@ -44,9 +45,9 @@ int64_t oracle_voxel_keys(const uint16_t* depth, int w, int h, const double k[4]
             const uint32_t d = depth[(int64_t)v * w + u];
             const double dd = (double)d, ud = (double)u;
             int32_t* o = keys + ((int64_t)v * w + u) * 3;
-            o[0] = (int32_t)floor(fma(dd, fma(c[0], ud, bx), c[9]));
-            o[1] = (int32_t)floor(fma(dd, fma(c[1], ud, by), c[10]));
-            o[2] = (int32_t)floor(fma(dd, fma(c[2], ud, bz), c[11]));
+            o[0] = (int32_t)floor(fma(dd, fma(c[0], ud, bx), c[9])) - 16384;
+            o[1] = (int32_t)floor(fma(dd, fma(c[1], ud, by), c[10])) - 16384;
+            o[2] = (int32_t)floor(fma(dd, fma(c[2], ud, bz), c[11])) - 16384;
             const int ok = d != 0 && d <= max_depth_mm;
             valid[(int64_t)v * w + u] = (uint8_t)ok;
             n += ok;

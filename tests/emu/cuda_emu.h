@@ -170,6 +170,11 @@ inline uint32_t __ballot_sync(uint32_t, int pred) { return ti_emu::ballot(pred);
 inline int __any_sync(uint32_t, int pred) { return ti_emu::ballot(pred) != 0u; }
 inline uint32_t __reduce_add_sync(uint32_t, uint32_t v) { return ti_emu::reduce_add(v); }
 inline uint32_t __reduce_or_sync(uint32_t, uint32_t v) { return ti_emu::reduce_or(v); }
+inline uint32_t __reduce_max_sync(uint32_t, uint32_t v) {
+    uint32_t r = 0;
+    for (int i = 0; i < 32; ++i) r = std::max(r, ti_emu::shfl_idx(v, i));
+    return r;
+}
 template <typename T>
 inline T __shfl_sync(uint32_t, T v, int src) {
     static_assert(sizeof(T) == 4, "emu shuffles 32-bit values");
@@ -184,6 +189,12 @@ inline T __shfl_down_sync(uint32_t m, T v, int delta) {
     const int src = (int)ti_emu::lane() + delta;
     T r = __shfl_sync(m, v, src & 31);
     return src < 32 ? r : v;
+}
+template <typename T>
+inline T __shfl_up_sync(uint32_t m, T v, int delta) {
+    const int src = (int)ti_emu::lane() - delta;
+    T r = __shfl_sync(m, v, src & 31);
+    return src >= 0 ? r : v;
 }
 template <typename T>
 inline T __shfl_xor_sync(uint32_t m, T v, int x) { return __shfl_sync(m, v, (int)ti_emu::lane() ^ x); }

@@ -9,8 +9,8 @@
 //
 //     p   = d * (au * u + av * v + ac) + t          the back-projection of ti_backproject.cu (double, fused multiply-adds,
 //                                                   same constants, RDF->FLU and rig pose folded in)
-//     k   = floor(p / voxel_size)  per axis         computed as floor(d * (au' * u + av' * v + ac') + t') with the constants
-//                                                   pre-multiplied by 1 / voxel_size on the host
+//     k   = floor(p / voxel_size)  per axis         computed as floor(d * (au' * u + av' * v + ac') + (t' + 16384)) - 16384 with
+//                                                   the constants pre-multiplied by 1 / voxel_size on the host
 //     valid = d > 0  and  d <= max_depth_mm         examples/rgbd_stream.py:121-123 and the nvblox distance cap
 //     record = tag << 56 | set << 45 | (kx + 16384) << 30 | (ky + 16384) << 15 | (kz + 16384)
 //
@@ -18,25 +18,32 @@
 // is not defined (records are appended tile by tile); the SET of records and the per-set counts are exact.
 //
 // How duplicates are removed (every stage only ever drops a key that is provably already on its way out):
-//   1. a thread owns 8 consecutive pixels of a row and forwards a key only when it differs from its predecessor's;
-//   2. a direct-mapped cache of 2048 keys in shared memory (one atomic exchange): whoever finds its own key there drops it -
-//      the thread that put it there forwards it.  Keys carry the frame-set number, so the cache is never cleared;
-//   3. an open-addressing hash set in global memory (one 64-bit compare-and-swap per surviving key), whose entries carry
-//      an 8-bit launch epoch so it is never cleared between launches either.  The thread whose CAS installs a key emits it.
-// New keys of a tile are collected in shared memory and appended to the list with one atomic per tile, so the list is
-// written in coalesced runs.  Traffic: 2 B/px of depth in, 8 B per occupied voxel out.
+//   1. a lane owns 8 consecutive pixels of a row and forwards a key only when it differs from its predecessor's;
+//   2. a direct-mapped cache of 2048 keys in shared memory (one 64-bit atomic exchange): whoever finds its own key there drops
+//      it - the thread that put it there forwards it.  Keys carry the frame-set number, so the cache is never cleared;
+//   3. an open-addressing hash set in global memory (one load + one 64-bit compare-and-swap per surviving key), whose
+//      entries carry an 8-bit launch epoch so it is never cleared between launches either.  The lane whose CAS installs a key
+//      emits it.  (Slots are fully hashed: keeping the voxels of an 8 x 8 x 8 block together - a few cache lines per
+//      surface patch - was measured 2.2 x slower, the lanes of a warp then hammer the same L2 sectors.)
+// Warps work on their own: a warp takes a 32 x 32 pixel tile, collects the survivors of stage 2 in its slice of shared memory,
+// inserts them 32 at a time (all lanes in flight together: two dependent L2 round trips per tile, not per key), and appends
+// the new ones to the list with one atomic per ~100 records, in coalesced runs.  No block-wide barrier after start-up.
+// Traffic: 2 B/px of depth in, 8 B per occupied voxel out.
 #include "ti_common.cuh"
 
 namespace ti {
 
 constexpr int VX_THREADS = 256;
-constexpr int VX_TW = 64, VX_TH = 32;  // pixels per tile: 8 threads x 8 px wide, 32 rows
+constexpr int VX_WARPS = VX_THREADS / 32;
+constexpr int VX_TW = 32, VX_TH = 32;  // pixels per warp tile: 4 lanes x 8 px wide; 8 lane rows x 4 sub-blocks high
 constexpr int VX_CACHE = 2048;         // direct-mapped key cache per CTA (16 KB)
+static_assert(VX_CACHE == 2048, "the cache index is the top 11 bits of a 32-bit hash");
+constexpr int VX_BUF = 384;            // records per warp in shared memory: confirmed new ones, then pending survivors
+constexpr int VX_FLUSH = 96;           // confirmed records that trigger an append to the global list
 constexpr int MAX_VX_JOBS = 16;
-constexpr uint64_t VX_KEY_MASK = (1ull << 56) - 1;
 
 struct VxCam {
-    double au[3], av[3], ac[3], t[3];  // already divided by the voxel size
+    double au[3], av[3], ac[3], t[3];  // already divided by the voxel size; t also carries the +16384 bias of the key fields
     int width, height;
 };
 
@@ -60,6 +67,7 @@ struct VxParams {
     uint32_t* set_counts;
     uint32_t tiles_per_set, set_base, max_depth;
     int n_jobs, n_batch;
+    int debug;  // bring-up switches (TI_OPT_DEBUG): 1 = no hash-set stage, 2 = no cache stage, 4 = block-local slots (measured slower: same-sector contention)
 };
 
 __device__ __forceinline__ uint64_t vx_mix(uint64_t k) {  // murmur3 finaliser
@@ -103,9 +111,11 @@ __device__ __forceinline__ uint64_t vx_load(const uint64_t* p) { return *reinter
 #endif
 
 // true when this thread installed `key` (set number and voxel, 56 bits) in the global hash set
-__device__ __forceinline__ bool vx_insert(const VxParams& P, uint64_t key, uint64_t h) {
+__device__ __forceinline__ bool vx_insert(const VxParams& P, uint64_t key) {
     const uint64_t entry = P.epoch | key;
-    uint64_t slot = (h >> 11) & P.table_mask;
+    const uint64_t h = vx_mix(key & ~0x00000001C0038007ull);  // the 8 x 8 x 8 block: low three bits of every coordinate cleared ...
+    const uint64_t local = ((key >> 24) & 0x1C0u) | ((key >> 12) & 0x38u) | (key & 7u);  // ... and the position inside it
+    uint64_t slot = ((P.debug & 4) ? (((h >> 20) << 9) | local) : (vx_mix(key) >> 11)) & P.table_mask;
     uint64_t cur = vx_load(P.table + slot);
     for (;;) {
         if (cur == entry) return false;
@@ -120,16 +130,53 @@ __device__ __forceinline__ bool vx_insert(const VxParams& P, uint64_t key, uint6
     }
 }
 
-__global__ void __launch_bounds__(VX_THREADS) voxel_cloud_kernel(const __grid_constant__ VxParams P) {
+__global__ void __launch_bounds__(VX_THREADS, 3) voxel_cloud_kernel(const __grid_constant__ VxParams P) {
     __shared__ uint64_t cache[VX_CACHE];
-    __shared__ uint64_t stage[VX_TW * VX_TH];
-    __shared__ uint32_t s_n, s_cnt, s_base;
+    __shared__ uint64_t wbuf[VX_WARPS][VX_BUF];
     for (int i = threadIdx.x; i < VX_CACHE; i += VX_THREADS) cache[i] = ~0ull;  // no key has its top byte set
-    if (threadIdx.x == 0) s_n = 0;
     __syncthreads();
-    const int tx = threadIdx.x & 7, ty = threadIdx.x >> 3;
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    const int lx = lane & 3, ly = lane >> 2;
+    uint64_t* buf = wbuf[warp];
+    uint32_t n_conf = 0, n_pend = 0, buf_b = 0;  // warp-uniform
+
+    // pending survivors -> hash set, 32 at a time; the ones this warp installed move up behind the confirmed records
+    auto drain = [&]() {
+        __syncwarp();
+        const uint32_t base = n_conf, n = n_pend;
+        uint32_t out = n_conf;
+        for (uint32_t i0 = 0; i0 < n; i0 += 32) {
+            const uint32_t idx = i0 + lane;
+            const bool have = idx < n;
+            const uint64_t key = have ? buf[base + idx] : 0ull;
+            const bool is_new = have && ((P.debug & 1) || vx_insert(P, key));
+            const uint32_t m = __ballot_sync(0xFFFFFFFFu, is_new);
+            __syncwarp();  // every read of this round precedes its writes (which never reach a later round's reads)
+            if (is_new) buf[out + __popc(m & lt_mask)] = key;
+            out += __popc(m);
+        }
+        n_conf = out;
+        n_pend = 0;
+        __syncwarp();
+    };
+    auto flush = [&](uint32_t b) {
+        if (n_conf == 0) return;
+        uint32_t base = 0;
+        if (lane == 0) {
+            base = atomicAdd(P.n_records, n_conf);
+            if (P.set_counts) atomicAdd(P.set_counts + b, n_conf);
+        }
+        base = __shfl_sync(0xFFFFFFFFu, base, 0);
+        for (uint32_t i = lane; i < n_conf; i += 32)
+            if ((uint64_t)base + i < P.capacity) P.records[(uint64_t)base + i] = P.tag | buf[i];
+        n_conf = 0;
+        __syncwarp();
+    };
+
     const uint64_t total = (uint64_t)P.tiles_per_set * P.n_batch;
-    for (uint64_t t = blockIdx.x; t < total; t += gridDim.x) {
+    const uint64_t n_warps = (uint64_t)gridDim.x * VX_WARPS;
+    for (uint64_t t = (uint64_t)blockIdx.x * VX_WARPS + warp; t < total; t += n_warps) {
         const uint32_t b = (uint32_t)(t / P.tiles_per_set);
         const uint32_t r = (uint32_t)(t - (uint64_t)b * P.tiles_per_set);
         int j = 0;
@@ -137,56 +184,82 @@ __global__ void __launch_bounds__(VX_THREADS) voxel_cloud_kernel(const __grid_co
         const VxJobDev& J = P.job[j];
         const uint32_t lt = r - J.tile_begin;
         const int tile_y = (int)(lt / J.tiles_x), tile_x = (int)(lt - (uint32_t)tile_y * J.tiles_x);
-        const int v = tile_y * VX_TH + ty, u0 = tile_x * VX_TW + tx * 8;
-        uint32_t dw[4] = {0u, 0u, 0u, 0u};
-        if (v < J.cam.height && u0 < J.cam.width) {
-            const uint16_t* row = reinterpret_cast<const uint16_t*>(reinterpret_cast<const uint8_t*>(J.depth) + (uint64_t)b * J.depth_stride) +
-                                  (size_t)v * J.cam.width;
-            if (J.vec) {  // width % 8 == 0: the 8 pixels are inside the row
-                const uint4 q = ld_stream_u4(row + u0);
-                dw[0] = q.x; dw[1] = q.y; dw[2] = q.z; dw[3] = q.w;
-            } else {
-                for (int k = 0; k < 8; ++k)
-                    if (u0 + k < J.cam.width) dw[k >> 1] |= (uint32_t)row[u0 + k] << ((k & 1) * 16);
-            }
+        if (b != buf_b) {  // the confirmed records are counted per frame set
+            flush(buf_b);
+            buf_b = b;
         }
-        const double vd = vx_u2d((uint32_t)v);
-        const double bx = fma(J.cam.av[0], vd, J.cam.ac[0]);
-        const double by = fma(J.cam.av[1], vd, J.cam.ac[1]);
-        const double bz = fma(J.cam.av[2], vd, J.cam.ac[2]);
-        const uint64_t set_bits = (uint64_t)(P.set_base + b) << 45;
-        uint64_t prev = ~0ull;
+        const int u0 = tile_x * VX_TW + lx * 8;
+        const uint16_t* frame = reinterpret_cast<const uint16_t*>(reinterpret_cast<const uint8_t*>(J.depth) + (uint64_t)b * J.depth_stride);
+        auto load_sub = [&](int sub) -> uint4 {
+            const int v = tile_y * VX_TH + sub * 8 + ly;
+            if (sub >= 4 || v >= J.cam.height || u0 >= J.cam.width) return make_uint4(0u, 0u, 0u, 0u);
+            const uint16_t* row = frame + (size_t)v * J.cam.width;
+            if (J.vec) return ld_stream_u4(row + u0);  // width % 8 == 0: the 8 pixels are inside the row
+            uint32_t w[4] = {0u, 0u, 0u, 0u};
+            for (int k = 0; k < 8; ++k)
+                if (u0 + k < J.cam.width) w[k >> 1] |= (uint32_t)row[u0 + k] << ((k & 1) * 16);
+            return make_uint4(w[0], w[1], w[2], w[3]);
+        };
+        const uint32_t set_hi = (P.set_base + b) << 13;  // bits 45.. of the record
+        const double ud0 = vx_u2d((uint32_t)u0);
+        uint4 cur = load_sub(0);
+#pragma unroll 1
+        for (int sub = 0; sub < 4; ++sub) {
+            const uint4 nxt = load_sub(sub + 1);  // next sub-block's depth is in flight while this one is processed
+            if (n_conf + n_pend > VX_BUF - 256) {  // room for a sub-block in which every pixel is a new voxel
+                drain();
+                if (n_conf > VX_BUF - 256) flush(b);
+            }
+            const uint32_t dw[4] = {cur.x, cur.y, cur.z, cur.w};
+            const double vd = vx_u2d((uint32_t)(tile_y * VX_TH + sub * 8 + ly));
+            const double bx = fma(J.cam.av[0], vd, J.cam.ac[0]);
+            const double by = fma(J.cam.av[1], vd, J.cam.ac[1]);
+            const double bz = fma(J.cam.av[2], vd, J.cam.ac[2]);
+            // stage 1, branch-free: this lane's run-distinct keys go to column `lane` of the free part of the buffer
+            // (row i = the lane's i-th key), so that stage 2 can walk them row by row
+            uint64_t* col = buf + n_conf + n_pend + lane;
+            uint32_t prev_lo = 0xFFFFFFFFu, prev_hi = 0xFFFFFFFFu, mine = 0;
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            const uint32_t d = (dw[k >> 1] >> ((k & 1) * 16)) & 0xFFFFu;
-            const double ud = vx_u2d((uint32_t)(u0 + k)), dd = vx_u2d(d);
-            const int kx = vx_floor(fma(dd, fma(J.cam.au[0], ud, bx), J.cam.t[0]));
-            const int ky = vx_floor(fma(dd, fma(J.cam.au[1], ud, by), J.cam.t[1]));
-            const int kz = vx_floor(fma(dd, fma(J.cam.au[2], ud, bz), J.cam.t[2]));
-            const uint64_t key = set_bits | ((uint64_t)(uint32_t)(kx + 16384) << 30) | ((uint64_t)(uint32_t)(ky + 16384) << 15) |
-                                 (uint64_t)(uint32_t)(kz + 16384);
-            bool fresh = d != 0 && d <= P.max_depth && key != prev;
-            if (fresh) {
-                prev = key;
-                const uint64_t h = vx_mix(key);
-                fresh = vx_exch(&cache[h & (VX_CACHE - 1)], key) != key && vx_insert(P, key, h);
+            for (int k = 0; k < 8; ++k) {
+                const uint32_t d = (k & 1) ? (dw[k >> 1] >> 16) : (dw[k >> 1] & 0xFFFFu);
+                const double ud = ud0 + (double)k, dd = vx_u2d(d);
+                // t carries the +16384 bias of the key fields: the low word of the rounded-down sum IS the field
+                const uint32_t kx = (uint32_t)vx_floor(fma(dd, fma(J.cam.au[0], ud, bx), J.cam.t[0]));
+                const uint32_t ky = (uint32_t)vx_floor(fma(dd, fma(J.cam.au[1], ud, by), J.cam.t[1]));
+                const uint32_t kz = (uint32_t)vx_floor(fma(dd, fma(J.cam.au[2], ud, bz), J.cam.t[2]));
+                const uint32_t lo = kz | (ky << 15) | (kx << 30), hi = (kx >> 2) | set_hi;
+                const bool keep = (d - 1u) < P.max_depth && (lo != prev_lo || hi != prev_hi);  // 0 < d <= max_depth, new run
+                if (keep) {
+                    col[mine * 32] = ((uint64_t)hi << 32) | lo;
+                    ++mine;
+                    prev_lo = lo; prev_hi = hi;
+                }
             }
-            if (fresh) stage[atomicAdd(&s_n, 1u)] = key;
+            // stage 2, one row at a time: the shared cache; survivors are packed to the front of the same region
+            const uint32_t rows = __reduce_max_sync(0xFFFFFFFFu, mine);
+            uint64_t* pend = buf + n_conf + n_pend;
+            uint32_t out = 0;
+            for (uint32_t i = 0; i < rows; ++i) {
+                bool fresh = i < mine;
+                uint64_t key = 0;
+                if (fresh) {
+                    key = col[i * 32];
+                    // index from the TOP bits of a product: every key bit reaches them (low product bits only see low key bits)
+                    const uint32_t c = ((uint32_t)key ^ ((uint32_t)(key >> 32) * 0x9E3779B1u)) * 0x85EBCA6Bu;
+                    fresh = (P.debug & 2) || vx_exch(&cache[c >> 21], key) != key;
+                }
+                const uint32_t m = __ballot_sync(0xFFFFFFFFu, fresh);  // also orders this row's reads before the writes below
+                if (fresh) pend[out + __popc(m & lt_mask)] = key;      // out + 32 <= (i + 1) * 32: never reaches an unread row
+                out += __popc(m);
+            }
+            n_pend += out;
+            __syncwarp();
+            cur = nxt;
         }
-        __syncthreads();
-        if (threadIdx.x == 0) {  // every append of this tile is in; the next tile's come after the third barrier
-            const uint32_t n = s_n;
-            s_n = 0;
-            s_cnt = n;
-            s_base = n ? atomicAdd(P.n_records, n) : 0u;
-            if (n && P.set_counts) atomicAdd(P.set_counts + b, n);
-        }
-        __syncthreads();
-        const uint32_t n = s_cnt, base = s_base;
-        for (uint32_t i = threadIdx.x; i < n; i += VX_THREADS)
-            if ((uint64_t)base + i < P.capacity) P.records[(uint64_t)base + i] = P.tag | stage[i];
-        __syncthreads();
+        drain();
+        if (n_conf >= VX_FLUSH) flush(b);
     }
+    flush(buf_b);
 }
 
 // records -> centres of the voxels as N x 3 f32 (the cloud type of SlamMap.to_point_cloud, interface.py:134-138);
@@ -247,9 +320,9 @@ int ti_voxel_cloud(ti_ctx* ctx, const ti_depth_stream* streams, int n_streams, i
         if (D.depth_stride % 2 || (uintptr_t)S.depth % 2) return fail(ctx, TI_EINVAL, "ti_voxel_cloud: depth must be 2-byte aligned");
         double reach = 0.0;  // bound on |p| / voxel over the image, every valid depth
         for (int r = 0; r < 3; ++r) {
-            D.cam.au[r] = C.proj_au[r] * inv; D.cam.av[r] = C.proj_av[r] * inv; D.cam.ac[r] = C.proj_ac[r] * inv; D.cam.t[r] = C.proj_t[r] * inv;
+            D.cam.au[r] = C.proj_au[r] * inv; D.cam.av[r] = C.proj_av[r] * inv; D.cam.ac[r] = C.proj_ac[r] * inv; D.cam.t[r] = C.proj_t[r] * inv + 16384.0;
             const double ray = fabs(D.cam.au[r]) * C.proj_w + fabs(D.cam.av[r]) * C.proj_h + fabs(D.cam.ac[r]);
-            reach = std::max(reach, ray * ctx->voxel_max_depth + fabs(D.cam.t[r]));
+            reach = std::max(reach, ray * ctx->voxel_max_depth + fabs(C.proj_t[r] * inv));
         }
         if (!(reach < 16383.0))
             return fail(ctx, TI_EINVAL, "ti_voxel_cloud: camera slot %d reaches %.0f voxels from the body origin; the 15-bit key fields hold "
@@ -263,7 +336,7 @@ int ti_voxel_cloud(ti_ctx* ctx, const ti_depth_stream* streams, int n_streams, i
     }
     // hash set: twice the pixels of the launch (every pixel could be its own voxel), a power of two; entries of earlier
     // launches are recognised by their epoch byte, so it is cleared only when the epoch wraps or the table grows
-    uint64_t slots = 1u << 16;
+    uint64_t slots = 1u << 20;
     while (slots < 2 * px * (uint64_t)n_batch) slots <<= 1;
     if (slots > ctx->voxel_slots) {
         TI_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -285,9 +358,10 @@ int ti_voxel_cloud(ti_ctx* ctx, const ti_depth_stream* streams, int n_streams, i
     P.records = records; P.capacity = capacity; P.n_records = n_records; P.set_counts = set_counts;
     P.tiles_per_set = tiles; P.set_base = set_base; P.max_depth = ctx->voxel_max_depth;
     P.n_jobs = n_streams; P.n_batch = n_batch;
+    P.debug = ctx->debug;
     const uint64_t total = (uint64_t)tiles * n_batch;
     const int per_sm = ctx->ctas_per_sm > 0 ? ctx->ctas_per_sm : resident_ctas(voxel_cloud_kernel, VX_THREADS, 0, 4);
-    const int grid = (int)std::min<uint64_t>(total, (uint64_t)ctx->sm_count * per_sm);
+    const int grid = (int)std::min<uint64_t>((total + VX_WARPS - 1) / VX_WARPS, (uint64_t)ctx->sm_count * per_sm);
     TI_LAUNCH(voxel_cloud_kernel, grid, VX_THREADS, 0, ctx->stream, P);
     TI_CHECK_LAUNCH(ctx);
     return TI_OK;

@@ -18,7 +18,7 @@ import torch
 
 ROOT = Path(__file__).resolve().parent.parent
 sys.path.insert(0, str(ROOT))
-from thor_slam_b200.camera.synthetic import SyntheticCameraConfig, SyntheticCameraSource, make_depth  # noqa: E402
+from thor_slam_b200.camera.synthetic import SyntheticCameraConfig, SyntheticCameraSource, make_depth, make_depth_scene  # noqa: E402
 from thor_slam_b200.ingest import formats as F  # noqa: E402
 from thor_slam_b200.ingest.calib import body_T_camera, stereo_rectify_maps  # noqa: E402
 from thor_slam_b200.ingest.context import IngestContext, StreamSpec  # noqa: E402
@@ -157,6 +157,34 @@ def main() -> None:
             report(f"backproject ctas/sm={per_sm}", timeit(lambda: ctx.ingest(bspecs), args.iters), 15 * dpx, dpx)
         ctx.set_option(ctx.OPT_CTAS_PER_SM, 0)
         del xyz, mask, depth
+
+    if not args.only or "voxel" in args.only:
+        intr = src.get_intrinsics()[0]
+        m = body_T_camera(None, src.get_extrinsics()[0].to_4x4_matrix(), "rdf")
+        ND, VB = 4, max(2, B // 2)
+        for cam in range(ND):
+            ctx.upload_projection(cam, intr.matrix, m, (W, H))
+        ctx.set_voxel_grid(0.05, 10000)
+        vpx = ND * VB * W * H
+        rec = torch.empty(vpx, dtype=torch.int64, device="cuda")
+        nrec = torch.zeros(1, dtype=torch.int32, device="cuda")
+        cnts = torch.zeros(VB, dtype=torch.int32, device="cuda")
+        for scene, gen in (("room", lambda: make_depth_scene(rng, W, H, focal_px=intr.matrix[0, 0])), ("noise", lambda: make_depth(rng, W, H))):
+            d4 = np.stack([gen() for _ in range(4)]).view(np.int16)
+            vdepth = [torch.from_numpy(np.roll(d4, i, axis=0)).cuda().view(torch.uint16).repeat((VB + 3) // 4, 1, 1)[:VB].contiguous() for i in range(ND)]
+            streams = [(i, vdepth[i]) for i in range(ND)]
+            for per_sm, dbg in ((0, 0), (3, 0), (0, 4), (0, 1), (0, 2), (0, 3))[:2 if args.one else None]:
+                if scene == "noise" and dbg in (2, 3):
+                    continue
+                ctx.set_option(ctx.OPT_CTAS_PER_SM, per_sm)
+                ctx.set_option(ctx.OPT_DEBUG, dbg)
+                ms = timeit(lambda: ctx.voxel_cloud(streams, rec, nrec, cnts), 3 if scene == "noise" else args.iters)
+                n = int(nrec.item())
+                report(f"voxel cloud {scene} ctas/sm={per_sm} debug={dbg}: {n} voxels of {vpx} px (x{vpx * 0.8 / max(n, 1):.1f})", ms, 2 * vpx + 8 * n, vpx)
+            ctx.set_option(ctx.OPT_CTAS_PER_SM, 0)
+            ctx.set_option(ctx.OPT_DEBUG, 0)
+            del vdepth
+        del rec
 
     if not args.only or "conv" in args.only:
         CW, CH, NB = 1920, 1080, max(2, B)  # >= 32 frames: 199 MB in, far beyond L2
