@@ -17,9 +17,18 @@ step, far larger than the 126 MB L2, so no step is served from cache).
                 of the rectify kernel / its average duration, against MEASURED_PEAKS.json ``hbm_gbs``.
 * ``cpu_baseline``: the oracle (cv2.remap, all host threads) on a bounded sample, rank 0, N=1 only.
 
-With N > 1 every rank processes its own batch (weak scaling, no data-path collective - config 2 has no
-exchange step); ``extras.config5`` additionally times the 4 x (mono rectify + depth -> cloud) frame set
-and the NCCL gather of the clouds separately.
+* ``sustained``: the same step loop run for >= 1.5 s (the K-step region of a short run lasts milliseconds), with the SM
+                clock sampled through NVML over it.
+* ``configs``  : BASELINE configs 3, 4 and 5 as whole frame sets, one ``ingest`` call per step (N = 1), and config 5 with the
+                voxel down-sampled cloud (``ti_voxel_cloud``) in place of the dense one.
+* ``e2e_rig``  : ``SyntheticCameraSource -> IngestRig.get_synchronized_frames() -> np.asarray(image)`` frame-sets/s and latency,
+                beside the oracle (cv2.remap) driven through the ``CameraRig`` mirror.  N = 1.
+
+With N > 1 every rank processes its own batch (weak scaling, no data-path collective - config 2 has no exchange step) and the
+line carries ``config5``: BASELINE config 5 (4 x (mono rectify + depth -> cloud) per frame set, frame sets sharded over the ranks)
+WITH its one exchange step - the gather of the clouds on rank 0 - overlapped with the next batch's kernels: voxel lists over NCCL
+on the library's exchange stream, the same as peer-store kernels, and the dense clouds of round 1 for comparison; the gathered
+list of the last step is checked against the oracle on rank 0.  ``--strong`` fixes the total at 64 frame sets instead of 16 per rank.
 """
 
 from __future__ import annotations
@@ -185,6 +194,8 @@ def time_cpu(frames, maps, budget_s: float, max_sets: int) -> tuple[float, int, 
 
 # ------------------------------------------------------------------------------------------------
 def run_reference(args) -> None:
+    """The reference-side CPU path on the same workload, same step size, same loop as ``cpu_baseline``: ``args.batch`` frame sets
+    per step, ``--warmup`` full steps untimed, ``--steps`` steps timed, every host thread OpenCV will use."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -193,16 +204,20 @@ def run_reference(args) -> None:
     cores = os.cpu_count() or 1
     cv2.setNumThreads(cores)
     sources, maps = build_rig()
-    sets_per_step = max(1, args.ref_sets)
-    frames = host_frames(sources, min(sets_per_step, 4))
+    B = args.batch
+    frames = host_frames(sources, 2)
+
+    def step() -> None:
+        for b in range(B):
+            cpu_pass([f[b % 2: b % 2 + 1] for f in frames], maps, 1)
+
     for _ in range(args.warmup):
-        cpu_pass([f[:1] for f in frames], maps, 1)
+        step()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        for b in range(sets_per_step):
-            cpu_pass([f[b % f.shape[0]: b % f.shape[0] + 1] for f in frames], maps, 1)
+        step()
     dt = time.perf_counter() - t0
-    value = args.steps * sets_per_step / dt
+    value = args.steps * B / dt
     line = {
         "impl": "reference",
         "metric": "frame_sets_per_sec",
@@ -217,10 +232,11 @@ def run_reference(args) -> None:
         "vs_baseline": None,
         "dtype": "u8",
         "data": "synthetic",
-        "config": workload_config(sets_per_step, args.gpus) | {"note": "CPU path: cv2.remap INTER_LINEAR per stream (oracle port of the reference-side path), all host threads"},
+        "config": workload_config(B, args.gpus),
         "mpix_per_sec": value * PX_PER_SET / 1e6,
         "cpu_baseline": {"value": value, "unit": "frame-sets/s", "cores": cv2.getNumThreads(), "kind": "port",
-                         "sample": f"{args.steps} steps x {sets_per_step} frame sets of 8 x 1280x800 mono8, cv2.remap"},
+                         "sample": f"{args.steps} steps x {B} frame sets of 8 x 1280x800 mono8 in {dt:.1f} s after {args.warmup} warm-up steps, "
+                                   f"cv2.remap INTER_LINEAR per stream (OpenCV {cv2.__version__}; oracle port of the reference-side path)"},
         "e2e": {"value": value, "unit": "frame-sets/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -312,6 +328,29 @@ def run_ours(args) -> None:
 
     got_value_frame = d_dst[3][1].cpu().numpy() if rank == 0 else None  # checked against the oracle in the cpu_baseline leg
 
+    # ---- the same loop, sustained: the K-step region above lasts milliseconds; this one >= args.sustain_s seconds, with the
+    # SM clock sampled over it (one NVML poll per 4 ms) -------------------------------------------
+    sus_steps = int(min(50000, max(args.steps, args.sustain_s / max(ms_per_step * 1e-3, 1e-6))))
+    sampler2 = ClockSampler(local_rank)
+    barrier()
+    if rank == 0:
+        sampler2.start()
+    s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ts_begin = time.perf_counter()
+    s0.record(stream)
+    for _ in range(sus_steps):
+        ctx.ingest(specs)
+    s1.record(stream)
+    barrier()
+    ts_end = time.perf_counter()
+    sus_clocks = sampler2.stop(ts_begin, ts_end) if rank == 0 else None
+    tsus = torch.tensor([s0.elapsed_time(s1)], dtype=torch.float64, device="cuda")
+    if distributed:
+        dist.all_reduce(tsus, op=dist.ReduceOp.MAX)
+    sus_ms = float(tsus.item())
+    sustained = {"steps": sus_steps, "seconds": round(sus_ms * 1e-3, 3), "ms_per_step": sus_ms / sus_steps, "value": world * B * sus_steps / (sus_ms * 1e-3),
+                 "gpu_launches": sus_steps, "clocks": sus_clocks}
+
     # ---- end to end through the host-buffer API ("e2e") -----------------------------------------
     # A capture loop double-buffers its host frames: batch k+1 is submitted before batch k is waited for, so one
     # step's download overlaps the next step's upload.  Every step still uploads its own inputs from pinned host
@@ -363,9 +402,13 @@ def run_ours(args) -> None:
     launches_e2e = (ctx.launch_count - launches_e2e0) * e2e_steps // (e2e_steps + 2)  # the two warm-up steps launch too
     got_e2e_frame = h_dst[(e2e_steps - 1) % 2][5][0].numpy().copy() if rank == 0 else None
 
-    extras: dict = {}
-    if args.extras:
-        extras = run_extras(args, ctx, sources, maps, rank, world, distributed, barrier)
+    peak, peak_src = measured_peak()
+    configs = run_configs(args, ctx, sources, peak) if (world == 1 and not args.no_configs) else None
+    config5 = run_config5_exchange(args, ctx, sources, rank, world, barrier, peak) if (distributed and not args.no_configs) else None
+    pcie = pcie_probe(rank, world, barrier) if not args.no_pcie else None
+    e2e_rig = None
+    if rank == 0 and world == 1 and not args.no_rig:
+        e2e_rig = run_e2e_rig(args)
 
     # ---- CPU baseline (rank 0, N = 1 only) ---------------------------------------------------------
     cpu_baseline = None
@@ -385,7 +428,6 @@ def run_ours(args) -> None:
                         "sample": f"{done} frame sets of 8 x 1280x800 mono8 in {secs:.1f} s, cv2.remap INTER_LINEAR (OpenCV {cv2.__version__})"}
 
     if rank == 0:
-        peak, peak_src = measured_peak()
         algo_bytes = B * PX_PER_SET * ALGO_BYTES_PER_PX
         achieved = algo_bytes / (ms_per_step * 1e-3) / 1e9
         line = {
@@ -413,130 +455,113 @@ def run_ours(args) -> None:
                          "traffic": NCU_TRAFFIC_BYTES_PER_FRAME_SET * B, "traffic_source": "ncu --set full, profiles/r01_rect_v4_ncu_raw.txt (scaled per frame set)",
                          "kernel": KERNEL_BY_VARIANT[plan["variant"]], "kernel_plan": plan, "algorithmic_bytes_per_launch": algo_bytes,
                          "peak_source": peak_src, "frac_of_8000_datasheet": achieved / 8000.0,
+                         "sustained_achieved": algo_bytes / (sustained["ms_per_step"] * 1e-3) / 1e9,
+                         "sustained_frac": algo_bytes / (sustained["ms_per_step"] * 1e-3) / 1e9 / peak,
                          "note": "per-rank launch; duration = max-over-ranks ms_per_step (one launch per step)"},
             "cpu_baseline": cpu_baseline,
+            "sustained": sustained,
         }
-        if extras:
-            line["extras"] = extras
+        for key, val in (("configs", configs), ("config5", config5), ("e2e_rig", e2e_rig), ("pcie", pcie)):
+            if val is not None:
+                line[key] = val
         print(json.dumps(line))
     ctx.close()
     if distributed:
         dist.destroy_process_group()
 
 
-def run_extras(args, ctx, sources, maps, rank, world, distributed, barrier) -> dict:
-    """Config 5 frame sets (4 mono rectify + 4 depth -> cloud) and, for N > 1, the cloud gather."""
+def timed_steps(stream, fn, steps: int, warm: int = 3) -> float:
+    """ms per call of ``fn(k)`` over ``steps`` calls after ``warm`` untimed ones (CUDA events on ``stream``)."""
     import torch
-    import torch.distributed as dist
 
-    from thor_slam_b200.camera.synthetic import make_depth
-    from thor_slam_b200.ingest import formats as F
-    from thor_slam_b200.ingest.calib import body_T_camera
-    from thor_slam_b200.ingest.context import StreamSpec
-
-    B = max(1, args.batch // 4)
-    rng = np.random.default_rng(1337 + rank)
-    specs = []
-    keep = []
-    clouds = torch.empty((N_CAMERAS, B, H, W, 3), dtype=torch.float32, device="cuda")
-    for i, s in enumerate(sources):
-        left = torch.from_numpy(np.stack([s._pool[b % 2][0] for b in range(B)])).cuda()
-        out = torch.empty_like(left)
-        depth = torch.from_numpy(np.stack([make_depth(rng, W, H) for _ in range(2)]).view(np.int16)).cuda().view(torch.uint16)
-        depth = depth.repeat((B + 1) // 2, 1, 1)[:B].contiguous()
-        mask = torch.empty((B, H, W), dtype=torch.uint8, device="cuda")
-        count = torch.zeros((B,), dtype=torch.int32, device="cuda")
-        intr = s.get_intrinsics()[0]
-        ctx.upload_projection(2 * i, intr.matrix, body_T_camera(None, s.get_extrinsics()[0].to_4x4_matrix(), "rdf"), (W, H))
-        specs.append(StreamSpec(F.KIND_RECTIFY, left, out, F.MONO8, F.MONO8, camera=2 * i))
-        specs.append(StreamSpec(F.KIND_BACKPROJECT, depth, clouds[i], F.DEPTH16, F.XYZ32F, camera=2 * i, mask=mask, count=count))
-        keep.append((left, out, depth, mask, count))
-    stream = torch.cuda.current_stream()
-    for _ in range(3):
-        ctx.ingest(specs)
-    barrier()
-    steps = max(3, min(args.steps, 10))
+    for k in range(warm):
+        fn(k)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
-    for _ in range(steps):
-        ctx.ingest(specs)
+    for k in range(steps):
+        fn(warm + k)
     e1.record(stream)
-    barrier()
-    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
-    if distributed:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms = float(t.item()) / steps
-    bytes_per_set = N_CAMERAS * W * H * (2 + 15)
-    peak, _ = measured_peak()
-    out = {"config5": {"frame_sets_per_step_per_rank": B, "ms_per_step": ms, "frame_sets_per_sec": world * B / (ms * 1e-3),
-                       "hbm_gbs": B * bytes_per_set / (ms * 1e-3) / 1e9, "frac": B * bytes_per_set / (ms * 1e-3) / 1e9 / peak,
-                       "algorithmic_bytes_per_frame_set": bytes_per_set}}
-    if not distributed:
-        out.update(run_config34(args, ctx, sources, keep, clouds, peak))
-    if distributed:
-        from thor_slam_b200.ingest.distributed import CloudGather, PeerCloudBuffer, RawDeviceBuffer
-
-        # (a) compute, then ONE grouped ncclSend/ncclRecv gather of the dense clouds on rank 0
-        gat = CloudGather(ctx, rank, world, root=0)
-        nbytes = clouds.numel() * 4
-        gathered = torch.empty((world, *clouds.shape), dtype=torch.float32, device="cuda") if rank == 0 else None
-        for _ in range(2):
-            gat.gather(clouds, gathered)
-        barrier()
-        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        g0.record(stream)
-        for _ in range(steps):
-            gat.gather(clouds, gathered)
-        g1.record(stream)
-        barrier()
-        tg = torch.tensor([g0.elapsed_time(g1)], dtype=torch.float64, device="cuda")
-        dist.all_reduce(tg, op=dist.ReduceOp.MAX)
-        gms = float(tg.item()) / steps
-        out["config5"]["gather_nccl"] = {"ms": gms, "bytes_into_root": nbytes * (world - 1),
-                                         "root_ingress_gbs": nbytes * (world - 1) / (gms * 1e-3) / 1e9,
-                                         "kind": "grouped ncclSend/ncclRecv of dense clouds after the kernel (includes the count all-gather)"}
-        if rank == 0:
-            out["config5"]["gather_nccl"]["matches_local"] = bool(torch.equal(gathered[0], clouds))
-        # (b) gather fused into the kernel: xyz stores go straight into rank 0's buffer over NVLink
-        peer = PeerCloudBuffer(ctx, rank, world, tuple(clouds.shape), root=0)
-        mine = peer.slice_for(rank)
-        fused_specs = []
-        for i in range(len(specs)):
-            sp = specs[i]
-            if sp.kind == F.KIND_BACKPROJECT:
-                cam_i = i // 2
-                dst = RawDeviceBuffer(mine.ptr + cam_i * clouds[0].numel() * 4, tuple(clouds[0].shape), 4)
-                sp = StreamSpec(F.KIND_BACKPROJECT, sp.src, dst, F.DEPTH16, F.XYZ32F, camera=sp.camera, mask=sp.mask, count=sp.count)
-            fused_specs.append(sp)
-        for _ in range(2):
-            ctx.ingest(fused_specs)
-        barrier()
-        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        f0.record(stream)
-        for _ in range(steps):
-            ctx.ingest(fused_specs)
-        f1.record(stream)
-        barrier()
-        tf = torch.tensor([f0.elapsed_time(f1)], dtype=torch.float64, device="cuda")
-        dist.all_reduce(tf, op=dist.ReduceOp.MAX)
-        fms = float(tf.item()) / steps
-        out["config5"]["fused_peer_store"] = {"ms_per_step": fms, "frame_sets_per_sec": world * B / (fms * 1e-3),
-                                              "kind": "back-projection kernels store xyz into rank 0's buffer through CUDA-IPC peer mapping (gather fused into the kernel); barrier only"}
-        if rank == 0:
-            fused = peer.as_tensor()
-            out["config5"]["fused_peer_store"]["matches_local"] = bool(torch.equal(fused[0], clouds))
-        barrier()
-        peer.close()
-    return out
+    e1.synchronize()
+    return e0.elapsed_time(e1) / steps
 
 
-def run_config34(args, ctx, sources, keep5, clouds, peak) -> dict:
-    """BASELINE configs 3 and 4 as whole frame sets, one ``ingest`` call per step (N = 1; kernels only, device-resident).
+class Config5:
+    """BASELINE config 5 frame sets on one rank: 4 cameras x (left mono 1280x800 -> rectified, depth 1280x800 -> cloud).
 
-    Config 3: 4 x (1920x1080 BGR -> rgb8, 1280x800 depth -> body-frame cloud).  Config 4: 2 x "OAK-D Pro" (stereo mono
-    1280x800 rectified, 1280x800 BGR -> rgb8, depth -> cloud) + 2 x "OAK-D LR" (stereo BGR 1920x1200 -> rgb8 rectified,
-    1920x1200 BGR -> rgb8, depth -> cloud).  Algorithmic bytes per SURVEY section 8(d).
-    """
+    Depth is a scene of surfaces (``make_depth_scene``; ``scene="noise"``: the per-pixel noise of SURVEY 8(d)), two distinct
+    frame sets per camera tiled over the batch, seeded per rank so that rank 0 can rebuild every rank's input for the oracle."""
+
+    def __init__(self, ctx, sources, B: int, rank: int, scene: str = "room") -> None:
+        import torch
+
+        from thor_slam_b200.camera.synthetic import make_depth, make_depth_scene
+        from thor_slam_b200.ingest import formats as F
+        from thor_slam_b200.ingest.calib import body_T_camera
+        from thor_slam_b200.ingest.context import StreamSpec
+
+        self.ctx, self.B, self.rank, self.scene = ctx, B, rank, scene
+        self.k, self.m, self.depth_np = [], [], self.host_depth(sources, rank, scene)
+        self.rect_specs, self.dense_specs, self.depth_streams, self.keep = [], [], [], []
+        self.clouds = None
+        for i, s in enumerate(sources):
+            left = torch.from_numpy(np.stack([s._pool[b % 2][0] for b in range(B)])).cuda()
+            out = torch.empty_like(left)
+            depth = torch.from_numpy(self.depth_np[i].view(np.int16)).cuda().view(torch.uint16).repeat((B + 1) // 2, 1, 1)[:B].contiguous()
+            intr = s.get_intrinsics()[0]
+            m = body_T_camera(None, s.get_extrinsics()[0].to_4x4_matrix(), "rdf")
+            ctx.upload_projection(2 * i, intr.matrix, m, (W, H))
+            self.k.append(intr.matrix)
+            self.m.append(m)
+            self.rect_specs.append(StreamSpec(F.KIND_RECTIFY, left, out, F.MONO8, F.MONO8, camera=2 * i))
+            self.depth_streams.append((2 * i, depth))
+            self.keep.append((left, out, depth))
+
+    @staticmethod
+    def host_depth(sources, rank: int, scene: str) -> list[np.ndarray]:
+        """[camera] -> u16 [2, H, W]: the two distinct depth frames of every camera of ``rank``."""
+        from thor_slam_b200.camera.synthetic import make_depth, make_depth_scene
+
+        rng = np.random.default_rng(4242 + rank)
+        out = []
+        for s in sources:
+            f = float(s.get_intrinsics()[0].matrix[0, 0])
+            out.append(np.stack([make_depth_scene(rng, W, H, focal_px=f) if scene == "room" else make_depth(rng, W, H) for _ in range(2)]))
+        return out
+
+    def add_dense(self) -> None:
+        import torch
+
+        from thor_slam_b200.ingest import formats as F
+        from thor_slam_b200.ingest.context import StreamSpec
+
+        B = self.B
+        self.clouds = torch.empty((N_CAMERAS, B, H, W, 3), dtype=torch.float32, device="cuda")
+        self.masks = torch.empty((N_CAMERAS, B, H, W), dtype=torch.uint8, device="cuda")
+        self.counts = torch.zeros((N_CAMERAS, B), dtype=torch.int32, device="cuda")
+        self.dense_specs = list(self.rect_specs)
+        for i, (cam, depth) in enumerate(self.depth_streams):
+            self.dense_specs.append(StreamSpec(F.KIND_BACKPROJECT, depth, self.clouds[i], F.DEPTH16, F.XYZ32F, camera=cam, mask=self.masks[i], count=self.counts[i]))
+
+    def oracle_records(self, rank: int, sources, tag: int, sets: int | None = None) -> np.ndarray:
+        """Sorted records of the first ``sets`` frame sets (default: all) of one step of ``rank`` (set j uses depth frame j % 2)."""
+        from oracle import voxel as ov
+
+        n = self.B if sets is None else min(sets, self.B)
+        depth = self.depth_np if rank == self.rank else self.host_depth(sources, rank, self.scene)
+        base = [ov.voxel_records([(depth[i][j], self.k[i], self.m[i]) for i in range(N_CAMERAS)], 0.05, 10000, set_id=0, tag=tag) for j in range(min(2, n))]
+        parts = [base[j % 2] | (np.uint64(j) << np.uint64(45)) for j in range(n)]
+        return np.sort(np.concatenate(parts))
+
+    @staticmethod
+    def first_sets(records: np.ndarray, sets: int | None) -> np.ndarray:
+        if sets is None:
+            return records
+        return records[((records >> np.uint64(45)) & np.uint64(0x7FF)) < np.uint64(sets)]
+
+
+def run_configs(args, ctx, sources, peak: float) -> dict:
+    """N = 1: BASELINE configs 3, 4, 5 as whole frame sets (kernels only, device-resident, one ``ingest`` call per step) and
+    config 5 with the voxel down-sampled cloud.  Algorithmic bytes per SURVEY section 8(d)."""
     import torch
 
     from thor_slam_b200.camera.synthetic import SyntheticCameraConfig, SyntheticCameraSource
@@ -545,37 +570,55 @@ def run_config34(args, ctx, sources, keep5, clouds, peak) -> dict:
     from thor_slam_b200.ingest.context import StreamSpec
 
     stream = torch.cuda.current_stream()
-    steps = max(3, min(args.steps, 10))
+    steps = max(5, min(args.steps, 20))
 
-    def timed(specs) -> float:
-        for _ in range(3):
-            ctx.ingest(specs)
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(stream)
-        for _ in range(steps):
-            ctx.ingest(specs)
-        e1.record(stream)
-        e1.synchronize()
-        return e0.elapsed_time(e1) / steps
-
-    def report(ms: float, n_sets: int, bytes_per_set: int) -> dict:
+    def report(ms: float, n_sets: int, bytes_per_set: int, **extra) -> dict:
         gbs = n_sets * bytes_per_set / (ms * 1e-3) / 1e9
-        return {"frame_sets_per_step": n_sets, "ms_per_step": ms, "frame_sets_per_sec": n_sets / (ms * 1e-3), "hbm_gbs": gbs,
-                "frac": gbs / peak, "algorithmic_bytes_per_frame_set": bytes_per_set}
+        return {"frame_sets_per_step": n_sets, "ms_per_step": round(ms, 5), "frame_sets_per_sec": round(n_sets / (ms * 1e-3), 1), "hbm_gbs": round(gbs, 1),
+                "frac": round(gbs / peak, 4), "algorithmic_bytes_per_frame_set": bytes_per_set, **extra}
 
     def bgr(n, h, w):
         return torch.randint(0, 256, (n, h, w, 3), dtype=torch.uint8, device="cuda")
 
     out = {}
+    B5 = max(2, args.batch // 4)
+    c5 = Config5(ctx, sources, B5, rank=0, scene="room")
+    c5.add_dense()
+    out["5"] = report(timed_steps(stream, lambda k: ctx.ingest(c5.dense_specs), steps), B5, N_CAMERAS * W * H * (2 + 15),
+                      what="4 x (mono rectify + depth -> dense body-frame cloud + mask + count)")
+    # config 5 with the cloud down-sampled to occupied 0.05 m voxels (nvblox's grid, 10 m cap) instead of 12 B per pixel
+    ctx.set_voxel_grid(0.05, 10000)
+    cap = B5 * 400_000
+    rec = torch.empty(cap, dtype=torch.int64, device="cuda")
+    nrec = torch.zeros(1, dtype=torch.int32, device="cuda")
+
+    def voxel_step(k: int) -> None:
+        ctx.ingest(c5.rect_specs)
+        ctx.voxel_cloud(c5.depth_streams, rec, nrec)
+
+    ms_v = timed_steps(stream, voxel_step, steps)
+    n_vox = int(nrec.item())
+    if n_vox > cap:
+        raise SystemExit(f"bench: voxel list overflow ({n_vox} > {cap})")
+    ms_vk = timed_steps(stream, lambda k: ctx.voxel_cloud(c5.depth_streams, rec, nrec), steps)
+    out["5_voxel"] = report(ms_v, B5, N_CAMERAS * W * H * (2 + 2) + 8 * n_vox // B5,
+                            what="4 x mono rectify + 4 depth frames -> ONE list of occupied voxels per frame set (ti_voxel_cloud)",
+                            scene="room (surfaces)", voxels_per_frame_set=n_vox // B5, valid_pixels_per_voxel=round(0.8 * N_CAMERAS * W * H * B5 / max(n_vox, 1), 1),
+                            cloud_bytes_per_frame_set={"dense_xyz": N_CAMERAS * W * H * 12, "voxel_records": 8 * n_vox // B5},
+                            voxel_kernel_ms=round(ms_vk, 5), voxel_kernel_gpix_per_sec=round(N_CAMERAS * W * H * B5 / (ms_vk * 1e-3) / 1e9, 1))
+    got = np.sort(rec[:n_vox].cpu().numpy().view(np.uint64))  # the checker, outside every timed region
+    if not np.array_equal(got, c5.oracle_records(0, sources, tag=0)):
+        raise SystemExit("bench: voxel records differ from the oracle - refusing to report a number")
+    out["5_voxel"]["oracle_check"] = "record set of one step == np.unique of the oracle's keys"
     # ---- config 3 ----
     B3 = max(2, args.batch // 4)
     specs = []
     for i in range(N_CAMERAS):
-        _, _, depth, mask, count = keep5[i]
         rgb_in = bgr(B3, 1080, 1920)
         specs.append(StreamSpec(F.KIND_CONVERT, rgb_in, torch.empty_like(rgb_in), F.BGR8, F.RGB8, width=1920, height=1080))
-        specs.append(StreamSpec(F.KIND_BACKPROJECT, depth[:B3], clouds[i][:B3], F.DEPTH16, F.XYZ32F, camera=2 * i, mask=mask[:B3], count=count[:B3]))
-    out["config3"] = report(timed(specs), B3, N_CAMERAS * (1920 * 1080 * 6 + W * H * 15))
+        specs.append(c5.dense_specs[N_CAMERAS + i])
+    out["3"] = report(timed_steps(stream, lambda k: ctx.ingest(specs), steps), B3, N_CAMERAS * (1920 * 1080 * 6 + W * H * 15),
+                      what="4 x (1920x1080 BGR -> rgb8 + 1280x800 depth -> cloud)")
     del specs
     # ---- config 4 ----
     B4 = max(2, args.batch // 8)
@@ -586,24 +629,289 @@ def run_config34(args, ctx, sources, keep5, clouds, peak) -> dict:
             ctx.upload_rectify_map(8 + 2 * k + cam, *lr_maps[cam], (1920, 1200))
     specs = []
     for i in range(2):  # OAK-D Pro: slots 2i, 2i+1 hold the mono stereo maps, slot 2i the depth projection
-        left, _, depth, mask, count = keep5[i]
+        left, _, depth = c5.keep[i]
         for cam in range(2):
             specs.append(StreamSpec(F.KIND_RECTIFY, left[:B4], torch.empty_like(left[:B4]), F.MONO8, F.MONO8, camera=2 * i + cam))
         rgb_in = bgr(B4, H, W)
         specs.append(StreamSpec(F.KIND_CONVERT, rgb_in, torch.empty_like(rgb_in), F.BGR8, F.RGB8, width=W, height=H))
-        specs.append(StreamSpec(F.KIND_BACKPROJECT, depth[:B4], clouds[i][:B4], F.DEPTH16, F.XYZ32F, camera=2 * i, mask=mask[:B4], count=count[:B4]))
+        specs.append(StreamSpec(F.KIND_BACKPROJECT, depth[:B4], c5.clouds[i][:B4], F.DEPTH16, F.XYZ32F, camera=2 * i, mask=c5.masks[i][:B4], count=c5.counts[i][:B4]))
     for k in range(2):  # OAK-D LR
-        _, _, depth, mask, count = keep5[2 + k]
+        _, _, depth = c5.keep[2 + k]
         for cam in range(2):
             col = bgr(B4, 1200, 1920)
             specs.append(StreamSpec(F.KIND_RECTIFY, col, torch.empty_like(col), F.BGR8, F.RGB8, camera=8 + 2 * k + cam))
         rgb_in = bgr(B4, 1200, 1920)
         specs.append(StreamSpec(F.KIND_CONVERT, rgb_in, torch.empty_like(rgb_in), F.BGR8, F.RGB8, width=1920, height=1200))
-        specs.append(StreamSpec(F.KIND_BACKPROJECT, depth[:B4], clouds[2 + k][:B4], F.DEPTH16, F.XYZ32F, camera=2 * (2 + k), mask=mask[:B4], count=count[:B4]))
+        specs.append(StreamSpec(F.KIND_BACKPROJECT, depth[:B4], c5.clouds[2 + k][:B4], F.DEPTH16, F.XYZ32F, camera=2 * (2 + k), mask=c5.masks[2 + k][:B4],
+                                count=c5.counts[2 + k][:B4]))
     pro = 2 * W * H * 2 + W * H * 6 + W * H * 15
     lrb = 2 * 1920 * 1200 * 6 + 1920 * 1200 * 6 + W * H * 15
-    out["config4"] = report(timed(specs), B4, 2 * pro + 2 * lrb)
+    out["4"] = report(timed_steps(stream, lambda k: ctx.ingest(specs), steps), B4, 2 * pro + 2 * lrb,
+                      what="2 x OAK-D Pro (2 mono rectify, BGR -> rgb8, depth -> cloud) + 2 x OAK-D LR (2 x 1920x1200 BGR -> rgb8 rectify, BGR -> rgb8, depth -> cloud)")
     return out
+
+
+def run_config5_exchange(args, ctx, sources, rank: int, world: int, barrier, peak: float) -> dict:
+    """N > 1: config 5 WITH its exchange step.  Frame sets are sharded over the ranks (``B`` per rank per step); every step's
+    cloud goes to rank 0 while the next step's kernels run.  Reported: compute only, and compute + exchange overlapped, for
+    (a) voxel lists over NCCL on the exchange stream, (b) voxel lists as peer-store kernels, (c) round 1's dense clouds."""
+    import torch
+    import torch.distributed as dist
+
+    from thor_slam_b200.ingest.distributed import CloudGather, RecordExchange
+
+    stream = torch.cuda.current_stream()
+    B = max(1, 64 // world) if args.strong else max(1, args.batch // 4)
+    steps = max(6, min(args.steps, 30))
+    out: dict = {"frame_sets_per_step_per_rank": B, "scaling": "strong (64 frame sets per step in total)" if args.strong else "weak",
+                 "sharding": f"frame set i -> rank i mod {world}; 4 cameras x (mono rectify + depth) per frame set; clouds gathered on rank 0"}
+
+    def max_ms(ms: float) -> float:
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def fs_per_sec(ms: float) -> float:
+        return round(world * B / (ms * 1e-3), 1)
+
+    ctx.set_voxel_grid(0.05, 10000)
+    gat = CloudGather(ctx, rank, world, root=0)
+    for scene in ("room", "noise"):
+        c5 = Config5(ctx, sources, B, rank, scene)
+        check_sets = None if scene == "room" else 1  # the noise lists are 16 x larger: the oracle checks frame set 0 of every rank
+        cap = B * (400_000 if scene == "room" else 3_400_000)
+        NB = 2
+        rec = [torch.empty(cap, dtype=torch.int64, device="cuda") for _ in range(NB)]
+        nrec = [torch.zeros(1, dtype=torch.int32, device="cuda") for _ in range(NB)]
+
+        def compute(k: int) -> None:
+            ctx.ingest(c5.rect_specs)
+            ctx.voxel_cloud(c5.depth_streams, rec[k % NB], nrec[k % NB], tag=rank)
+
+        res: dict = {}
+        barrier()
+        ms_c = max_ms(timed_steps(stream, compute, steps))
+        n_mine = int(nrec[0].item())
+        if n_mine > cap:
+            raise SystemExit(f"bench: voxel list overflow ({n_mine} > {cap})")
+        res["compute_only"] = {"ms_per_step": round(ms_c, 5), "frame_sets_per_sec": fs_per_sec(ms_c)}
+        res["voxels_per_frame_set"] = n_mine // B
+        res["cloud_bytes_per_frame_set"] = {"dense_xyz": N_CAMERAS * W * H * 12, "voxel_records": 8 * n_mine // B}
+
+        # (a) NCCL on the exchange stream, pipelined: step k's exchange runs under step k + 1's kernels
+        gathered = [torch.empty(world * cap, dtype=torch.int64, device="cuda") if rank == 0 else None for _ in range(NB)]
+        last_counts: list = [None]
+
+        def run_nccl(n: int) -> float:
+            fences = [0] * n
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+
+            def send(j: int) -> None:
+                _, last_counts[0] = gat.records_send(rec[j % NB], gathered[j % NB], wait=False)
+                fences[j] = ctx.exchange_fence()
+
+            for k in range(n):
+                if k >= NB:
+                    ctx.exchange_wait(fences[k - NB], on_stream=True)
+                compute(k)
+                if k >= 1:
+                    send(k - 1)
+                gat.records_begin(nrec[k % NB])
+            send(n - 1)
+            ctx.exchange_wait(fences[n - 1], on_stream=True)  # the timed region ends when the last cloud has landed
+            e1.record(stream)
+            e1.synchronize()
+            return e0.elapsed_time(e1) / n
+
+        run_nccl(3)
+        ms_n = max_ms(run_nccl(steps))
+        per_rank = last_counts[0]
+        res["overlapped_nccl"] = {"ms_per_step": round(ms_n, 5), "frame_sets_per_sec": fs_per_sec(ms_n), "vs_compute_only": round(ms_c / ms_n, 4),
+                                  "bytes_into_root_per_step": 8 * (sum(per_rank) - per_rank[0]),
+                                  "kind": "ti_gather_counts_begin/finish + ti_gather_records (grouped ncclSend/ncclRecv) on the exchange stream"}
+        if rank == 0:  # the checker, outside the timed region: last step's fused list against the oracle, every rank's frames
+            n_tot = sum(per_rank)
+            got = np.sort(Config5.first_sets(gathered[(steps - 1) % NB][:n_tot].cpu().numpy().view(np.uint64), check_sets))
+            want = np.sort(np.concatenate([c5.oracle_records(r, sources, tag=r, sets=check_sets) for r in range(world)]))
+            if not np.array_equal(got, want):
+                raise SystemExit(f"bench: gathered voxel list ({scene}, NCCL) differs from the oracle - refusing to report a number")
+            res["overlapped_nccl"]["oracle_check"] = f"{len(got)} of {n_tot} gathered records ({'all' if check_sets is None else 'frame set 0 of every rank'}) == oracle over all {world} ranks"
+        del gathered
+        barrier()
+
+        # (b) the same exchange as peer-store kernels over NVLink (no collective library, no host round trip)
+        ex = RecordExchange(ctx, rank, world, capacity=world * cap, root=0, slots=2)
+        taken = torch.empty(world * cap, dtype=torch.int64, device="cuda") if rank == 0 else None
+        status = torch.zeros(2, dtype=torch.int32, device="cuda") if rank == 0 else None
+
+        def run_push(n: int) -> float:
+            fences = [0] * n
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            for k in range(n):
+                if k >= NB:
+                    ctx.exchange_wait(fences[k - NB], on_stream=True)
+                compute(k)
+                fences[k] = ex.push(rec[k % NB], nrec[k % NB])
+                if rank == 0:
+                    ex.take(taken, status)
+            ex.wait(on_stream=True)
+            e1.record(stream)
+            e1.synchronize()
+            return e0.elapsed_time(e1) / n
+
+        run_push(4)
+        ms_p = max_ms(run_push(steps))
+        res["overlapped_push"] = {"ms_per_step": round(ms_p, 5), "frame_sets_per_sec": fs_per_sec(ms_p), "vs_compute_only": round(ms_c / ms_p, 4),
+                                  "kind": "ti_cloud_push / ti_inbox_take: reserve with one system-scope atomic, 16-byte peer stores into rank 0's inbox"}
+        if rank == 0:
+            n_tot, err = (int(x) for x in status.cpu().numpy())
+            got = np.sort(Config5.first_sets(taken[:n_tot].cpu().numpy().view(np.uint64), check_sets))
+            want = np.sort(np.concatenate([c5.oracle_records(r, sources, tag=r, sets=check_sets) for r in range(world)]))
+            if err or not np.array_equal(got, want):
+                raise SystemExit(f"bench: gathered voxel list ({scene}, peer stores, error flag {err}) differs from the oracle - refusing to report a number")
+            res["overlapped_push"]["oracle_check"] = f"{len(got)} of {n_tot} records in rank 0's inbox ({'all' if check_sets is None else 'frame set 0 of every rank'}) == oracle over all {world} ranks"
+        ex.close()
+        del taken, rec
+        out[scene] = res
+        if scene == "room":
+            # (c) round 1's exchange for comparison: dense clouds (12 B per pixel, invalid ones included), gathered after the kernels
+            c5.add_dense()
+            barrier()
+            ms_d = max_ms(timed_steps(stream, lambda k: ctx.ingest(c5.dense_specs), steps))
+            dsteps = max(3, steps // 3)
+            gd = torch.empty((world, *c5.clouds.shape), dtype=torch.float32, device="cuda") if rank == 0 else None
+
+            def dense_step(k: int) -> None:
+                ctx.ingest(c5.dense_specs)
+                gat.gather(c5.clouds, gd, wait=False)
+                gat.wait(on_stream=True)
+
+            barrier()
+            ms_dg = max_ms(timed_steps(stream, dense_step, dsteps, warm=2))
+            gat.wait()
+            nbytes = c5.clouds.numel() * 4
+            out["dense"] = {"compute_only": {"ms_per_step": round(ms_d, 5), "frame_sets_per_sec": fs_per_sec(ms_d)},
+                            "with_gather": {"ms_per_step": round(ms_dg, 5), "frame_sets_per_sec": fs_per_sec(ms_dg), "vs_compute_only": round(ms_d / ms_dg, 4),
+                                            "bytes_into_root_per_step": nbytes * (world - 1),
+                                            "kind": "ti_gather_clouds of the dense clouds after every step (the buffer is rewritten by the next step, so nothing overlaps)"}}
+            del gd
+        del c5
+        torch.cuda.empty_cache()
+    return out
+
+
+def run_e2e_rig(args) -> dict:
+    """The drop-in itself: 4 synthetic stereo sources -> ``IngestRig.get_synchronized_frames()`` -> ``np.asarray(frame.image)`` of
+    all 8 rectified frames, one frame set per call, beside the oracle (cv2.remap, all host threads) behind the ``CameraRig``
+    mirror on the same sources.  Host buffers in, host buffers out."""
+    import cv2
+    import torch
+
+    from oracle import rectify as orc
+    from thor_slam_b200.camera.rig import CameraRig
+    from thor_slam_b200.camera.synthetic import make_rig_sources
+    from thor_slam_b200.ingest.calib import stereo_rectify_maps
+    from thor_slam_b200.ingest.rig import IngestRig
+
+    n_sets = 200
+    sources = make_rig_sources(N_CAMERAS, resolution=(W, H), pixel_format="mono8", seed=1337, pool=2)
+    rig = IngestRig(sources, queue_size=10)
+    rig.start()
+    lat = []
+    for _ in range(10):
+        fs = rig.get_synchronized_frames()
+        [np.asarray(f.image) for f in fs.get_all_frames()]
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(n_sets):
+        t1 = time.perf_counter()
+        fs = rig.get_synchronized_frames()
+        imgs = [np.asarray(f.image) for f in fs.get_all_frames()]
+        lat.append(time.perf_counter() - t1)
+    dt = time.perf_counter() - t0
+    last_gpu = imgs[3].copy()
+    last_src = fs  # noqa: F841
+    rig.stop()
+    # the oracle behind the CameraRig mirror, same sources, same frames
+    sources2 = make_rig_sources(N_CAMERAS, resolution=(W, H), pixel_format="mono8", seed=1337, pool=2)
+    maps = []
+    for s in sources2:
+        maps.extend(stereo_rectify_maps(s.get_intrinsics(), s.get_extrinsics(), (W, H)))
+    cv2.setNumThreads(os.cpu_count() or 1)
+    ref = CameraRig(sources2, queue_size=10)
+    ref.start()
+    for _ in range(10):
+        fs2 = ref.get_synchronized_frames()
+        [orc.remap_cv(f.image, *maps[i]) for i, f in enumerate(fs2.get_all_frames())]
+    n_cpu, t0c, lat_c = 0, time.perf_counter(), []
+    while n_cpu < n_sets and time.perf_counter() - t0c < 8.0:
+        t1 = time.perf_counter()
+        fs2 = ref.get_synchronized_frames()
+        outs = [orc.remap_cv(f.image, *maps[i]) for i, f in enumerate(fs2.get_all_frames())]
+        lat_c.append(time.perf_counter() - t1)
+        n_cpu += 1
+    dtc = time.perf_counter() - t0c
+    ref.stop()
+    # same call count on both rigs -> the same source frames: compare one stream of the last frame set of equal index
+    check = None
+    if n_cpu == n_sets:
+        check = bool(np.array_equal(last_gpu, outs[3]))
+        if not check:
+            raise SystemExit("bench: IngestRig output differs from cv2.remap behind the CameraRig mirror")
+    return {"frame_sets_per_sec": round(n_sets / dt, 1), "latency_ms_median": round(float(np.median(lat)) * 1e3, 3), "latency_ms_p95": round(float(np.percentile(lat, 95)) * 1e3, 3),
+            "frame_sets": n_sets, "h2d_bytes_per_frame_set": PX_PER_SET, "d2h_bytes_per_frame_set": PX_PER_SET,
+            "api": "IngestRig.get_synchronized_frames() + np.asarray(frame.image) for all 8 frames, one frame set per call",
+            "cpu_rig": {"frame_sets_per_sec": round(n_cpu / dtc, 1), "latency_ms_median": round(float(np.median(lat_c)) * 1e3, 3), "frame_sets": n_cpu,
+                        "cores": cv2.getNumThreads(), "api": "CameraRig (API mirror).get_synchronized_frames() + cv2.remap per frame (oracle)"},
+            "matches_cpu_rig": check}
+
+
+def pcie_probe(rank: int, world: int, barrier, mb: int = 256, iters: int = 6) -> dict:
+    """Host <-> device copy ceilings with ALL ranks copying at once (pinned buffers near each GPU): what the box gives the
+    e2e path at this N.  GB/s per rank (min over ranks) and summed over ranks."""
+    import torch
+    import torch.distributed as dist
+
+    from thor_slam_b200.ingest.hostmem import near_gpu
+
+    n = mb << 20
+    with near_gpu(torch.cuda.current_device()):
+        h_in = torch.empty(n, dtype=torch.uint8).pin_memory()
+        h_out = torch.empty(n, dtype=torch.uint8).pin_memory()
+    d_a = torch.empty(n, dtype=torch.uint8, device="cuda")
+    d_b = torch.empty(n, dtype=torch.uint8, device="cuda")
+    up, down = torch.cuda.Stream(), torch.cuda.Stream()
+
+    def run(h2d: bool, d2h: bool) -> float:
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(iters):
+            if h2d:
+                with torch.cuda.stream(up):
+                    d_a.copy_(h_in, non_blocking=True)
+            if d2h:
+                with torch.cuda.stream(down):
+                    h_out.copy_(d_b, non_blocking=True)
+        torch.cuda.synchronize()
+        return n * iters / (time.perf_counter() - t0) / 1e9
+
+    res = {}
+    for name, a, b in (("h2d_alone", True, False), ("d2h_alone", False, True), ("both_directions", True, True)):
+        run(a, b)
+        g = run(a, b)
+        t = torch.tensor([g, -g], dtype=torch.float64, device="cuda")
+        s = torch.tensor([g], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MIN)
+            dist.all_reduce(s, op=dist.ReduceOp.SUM)
+        res[name] = {"gbs_per_direction_min_rank": round(float(t[0].item()), 1), "gbs_per_direction_max_rank": round(-float(t[1].item()), 1),
+                     "gbs_per_direction_sum": round(float(s.item()), 1)}
+    res["note"] = f"{mb} MB pinned copies, all {world} rank(s) at once"
+    return res
 
 
 def main() -> None:
@@ -616,10 +924,14 @@ def main() -> None:
     ap.add_argument("--e2e-batch", type=int, default=64, dest="e2e_batch")
     ap.add_argument("--chunk", type=int, default=8, help="frame sets per H2D/compute/D2H pipeline stage")
     ap.add_argument("--cpu-budget", type=float, default=10.0, dest="cpu_budget", help="seconds of CPU work for cpu_baseline")
-    ap.add_argument("--ref-sets", type=int, default=8, dest="ref_sets", help="frame sets per step of the reference arm")
     ap.add_argument("--no-cpu", action="store_true", dest="no_cpu")
     ap.add_argument("--no-numa", action="store_true", dest="no_numa", help="do not place the pinned host buffers on the GPU's NUMA node")
-    ap.add_argument("--extras", action="store_true", help="also time config 5 (rectify + back-projection) and the NCCL gather")
+    ap.add_argument("--no-configs", action="store_true", dest="no_configs", help="skip configs 3/4/5 (N = 1) and config 5 with its exchange (N > 1)")
+    ap.add_argument("--no-rig", action="store_true", dest="no_rig", help="skip the IngestRig end-to-end loop")
+    ap.add_argument("--no-pcie", action="store_true", dest="no_pcie", help="skip the host<->device copy probe")
+    ap.add_argument("--strong", action="store_true", help="config 5 at N > 1: 64 frame sets per step in total instead of 16 per rank")
+    ap.add_argument("--sustain-s", type=float, default=1.5, dest="sustain_s", help="seconds of the sustained loop")
+    ap.add_argument("--extras", action="store_true", help=argparse.SUPPRESS)  # round-1 flag, now the default
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3  # timing rule: at least 3 warm-up steps

@@ -134,7 +134,8 @@ int ti_upload_projection(ti_ctx* ctx, int camera, int width, int height, const d
  * 3 TMA + shifted copy, 2 thread-staged, 1 generic), out[1] = output tile height, out[2] = source rows staged
  * per tile, out[3] = exception entries per (tile, warp) of the pair-window kernel.
  * BGR8 -> RGB8: out[4] = 5 (3-channel window kernel) or 1 (generic), out[5] = source rows staged per tile.
- * out[6], out[7] reserved (0). */
+ * out[6] = output pixels of the pair-window kernel repaired by the per-pixel pass after it (a (tile, warp) holds 32 exceptions;
+ * strongly bent maps - fisheye - have a few more), out[7] reserved (0). */
 int ti_rectify_plan(ti_ctx* ctx, int camera, int32_t out[8]);
 
 /* u8 dst_h x dst_w mask of slot `camera`: 1 where all four bilinear taps are inside the
@@ -248,6 +249,19 @@ int ti_gather_wait(ti_ctx* ctx, int on_stream);
  * counts (HOST, `world` entries) receives all of them.  All-gather + read-back on the exchange stream; blocks the calling
  * thread until the counts are there (the ingest stream keeps running what was enqueued meanwhile). */
 int ti_gather_counts(ti_ctx* ctx, const uint32_t* n_local, uint32_t* counts);
+/* The same in two halves, so that the caller can hand the ingest stream its next batch before it blocks: begin enqueues the
+ * all-gather behind what the ingest stream holds NOW; finish blocks until the counts are on the host.  One outstanding. */
+int ti_gather_counts_begin(ti_ctx* ctx, const uint32_t* n_local);
+int ti_gather_counts_finish(ti_ctx* ctx, uint32_t* counts);
+/* Variable-length gather of ti_voxel_cloud lists sized by ti_gather_counts: rank r contributes records[0 .. counts[r]); on root
+ * they land back to back in `gathered` in rank order.  counts: HOST, `world` entries.  Ordered on the exchange stream behind the
+ * ti_gather_counts_begin that sized it, not behind whatever the ingest stream was given since - this is what lets batch k's
+ * exchange run under batch k + 1's kernels.  Completion: ti_gather_wait / ti_exchange_fence. */
+int ti_gather_records(ti_ctx* ctx, const uint64_t* records, uint64_t* gathered, const uint32_t* counts, int root);
+/* A fence names everything enqueued on the exchange stream so far (ring of 16).  ti_exchange_wait: the ingest stream
+ * (on_stream != 0) or the calling thread waits for it - e.g. before a record buffer handed to an exchange is overwritten. */
+int ti_exchange_fence(ti_ctx* ctx, uint64_t* fence);
+int ti_exchange_wait(ti_ctx* ctx, uint64_t fence, int on_stream);
 int ti_nccl_barrier(ti_ctx* ctx);
 
 /* Peer-visible cloud buffer: allocated on this GPU, exported as a 64-byte IPC handle, opened

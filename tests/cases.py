@@ -68,8 +68,15 @@ def edge_maps(dst_w: int, dst_h: int) -> tuple[np.ndarray, np.ndarray]:
     return (xx * 1.13 - 13.3 + 0.05 * yy).astype(np.float32), (yy * 1.21 - 14.7 - 0.03 * xx).astype(np.float32)
 
 
+def shear_maps(dst_w: int, dst_h: int, shear: float = 0.16) -> tuple[np.ndarray, np.ndarray]:
+    """A map whose source row changes every ``1 / shear`` output pixels: more than 32 exception pairs per (tile, warp) of the
+    pair-window kernel, so its overflow list is exercised (a fisheye camera does the same near the image corners)."""
+    yy, xx = np.mgrid[0:dst_h, 0:dst_w].astype(np.float32)
+    return (xx + 3.3).astype(np.float32), (yy + shear * xx + 0.4).astype(np.float32)
+
+
 def check_rectify(be, cam: int, mapx, mapy, s: str, d: str, src_w: int, src_h: int, n: int = 3, seed: int = 1,
-                  expect_variant: int | None = None, expect_exceptions: bool = False) -> None:
+                  expect_variant: int | None = None, expect_exceptions: bool = False, expect_overflow: bool = False) -> None:
     rng = np.random.default_rng(seed)
     dst_h, dst_w = mapx.shape
     be.ctx.upload_rectify_map(cam, mapx, mapy, (src_w, src_h))
@@ -96,6 +103,8 @@ def check_rectify(be, cam: int, mapx, mapy, s: str, d: str, src_w: int, src_h: i
                 assert plan["variant"] == expect_variant, f"slot {cam} would run kernel variant {plan}"
                 if expect_exceptions:
                     assert plan["exceptions_per_warp"] > 0, "this map was chosen to exercise the exception path"
+                if expect_overflow and th == 32:
+                    assert plan["exceptions_per_warp"] == 32 and plan["overflow_pixels"] > 0, f"this map was chosen to overflow the exception lists: {plan}"
             if (s, d) == ("bgr8", "rgb8") and expect_variant == 4 and variant == 4:
                 assert be.ctx.rectify_plan(cam)["colour_variant"] == 5, "BGR8 -> RGB8 must run the 3-channel window kernel here"
             dst = be.zeros((n, *F.frame_shape(F.fmt(d), dst_w, dst_h)), np.uint8)

@@ -98,29 +98,42 @@ def worker(rank: int, world: int, port: int, out: dict) -> None:
         nrec = [torch.zeros(1, dtype=torch.int32, device="cuda") for _ in range(2)]
         dev_depth = [torch.from_numpy(scene_all[k * world * per + rank * per: k * world * per + (rank + 1) * per].view(np.int16)).cuda().view(torch.uint16)
                      for k in range(rounds)]
-        # (c) NCCL, variable length, asynchronous: round k + 1's kernel is enqueued before round k's exchange is waited for
-        gathered = [torch.zeros(world * cap, dtype=torch.int64, device="cuda") if rank == 0 else None for _ in range(2)]
-        ok_c, counts_k = True, [None, None]
-        ctx.voxel_cloud([(0, dev_depth[0])], rec[0], nrec[0], tag=rank)
+        # (c) NCCL, variable length, pipelined: round k + 1's kernel is enqueued before round k's counts are collected, and
+        #     round k's exchange runs under it
+        gathered = [torch.zeros(world * cap, dtype=torch.int64, device="cuda") if rank == 0 else None for _ in range(rounds)]
+        counts_k: list = [None] * rounds
+        fences = [0] * rounds
+
+        def send(j: int) -> None:
+            _, counts_k[j] = gat.records_send(rec[j % 2], gathered[j], wait=False)
+            fences[j] = ctx.exchange_fence()
+
         for k in range(rounds):
-            _, counts_k[k % 2] = gat.gather_records(rec[k % 2], nrec[k % 2], gathered[k % 2], wait=False)
-            if k + 1 < rounds:
-                ctx.voxel_cloud([(0, dev_depth[k + 1])], rec[(k + 1) % 2], nrec[(k + 1) % 2], tag=rank)
-            gat.wait()
-            if rank == 0:
-                got = np.sort(gathered[k % 2][: sum(counts_k[k % 2])].cpu().numpy().view(np.uint64))
-                ok_c = ok_c and np.array_equal(got, want_round(k))
+            if k >= 2:
+                ctx.exchange_wait(fences[k - 2], on_stream=True)  # rec[k % 2] has left
+            ctx.voxel_cloud([(0, dev_depth[k])], rec[k % 2], nrec[k % 2], tag=rank)
+            if k >= 1:
+                send(k - 1)
+            gat.records_begin(nrec[k % 2])
+        send(rounds - 1)
+        gat.wait()
+        torch.cuda.synchronize()
         if rank == 0:
+            ok_c = True
+            for k in range(rounds):
+                got = np.sort(gathered[k][: sum(counts_k[k])].cpu().numpy().view(np.uint64))
+                ok_c = ok_c and np.array_equal(got, want_round(k))
             out["records_nccl_ok"] = bool(ok_c)
         dist.barrier()
-        # (d) peer-store exchange, two inbox slots, three rounds, nothing waited for until the end of each round's take
+        # (d) peer-store exchange, two inbox slots, three rounds, nothing waited for on the host until the end
         ex = RecordExchange(ctx, rank, world, capacity=world * cap, root=0, slots=2)
         taken = [torch.zeros(world * cap, dtype=torch.int64, device="cuda") for _ in range(rounds)] if rank == 0 else None
         status = [torch.zeros(2, dtype=torch.int32, device="cuda") for _ in range(rounds)] if rank == 0 else None
         for k in range(rounds):
-            ex.wait(on_stream=True)  # rec[k % 2] was pushed two rounds ago: that copy must have left before it is overwritten
+            if k >= 2:
+                ctx.exchange_wait(fences[k - 2], on_stream=True)  # rec[k % 2] was pushed two rounds ago
             ctx.voxel_cloud([(0, dev_depth[k])], rec[k % 2], nrec[k % 2], tag=rank)
-            ex.push(rec[k % 2], nrec[k % 2])
+            fences[k] = ex.push(rec[k % 2], nrec[k % 2])
             if rank == 0:
                 ex.take(taken[k], status[k])
         ex.wait()

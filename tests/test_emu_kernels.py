@@ -36,6 +36,13 @@ def test_rectify_border(emu_backend, s, d):
     cases.check_rectify(emu_backend, 1, mx, my, s, d, 160, 64, expect_variant=4, expect_exceptions=True)
 
 
+def test_rectify_overflowing_exception_lists(emu_backend):
+    """More than 32 exception pairs in a (tile, warp): the pair-window kernel keeps the slot, the surplus pixels are repaired
+    by the per-pixel pass after it."""
+    mx, my = cases.shear_maps(256, 64)
+    cases.check_rectify(emu_backend, 9, mx, my, "mono8", "mono8", 272, 112, n=2, expect_variant=4, expect_overflow=True)
+
+
 def test_rectify_resize_and_ragged(emu_backend):
     yy, xx = np.mgrid[0:51, 0:99].astype(np.float32)
     cases.check_rectify(emu_backend, 2, xx * 1.1 + 0.3, yy * 1.05 + 0.7, "mono8", "mono8", 110, 60)  # direct kernel

@@ -61,7 +61,13 @@ def test_rectify_full_size_mono(gpu_backend, distortion):
     """BASELINE config 2 stream shape, every distortion model the reference's CameraInfo rule knows."""
     _, maps = cases.stereo_maps(1280, 800, seed=11, distortion=distortion)
     for cam, (mx, my) in enumerate(maps):
-        cases.check_rectify(gpu_backend, 8 + cam, mx, my, "mono8", "mono8", 1280, 800, n=3)
+        # no silent fall-back: every distortion model of the reference's CameraInfo rule runs the pair-window kernel
+        cases.check_rectify(gpu_backend, 8 + cam, mx, my, "mono8", "mono8", 1280, 800, n=3, expect_variant=4)
+
+
+def test_rectify_overflowing_exception_lists(gpu_backend):
+    mx, my = cases.shear_maps(1280, 800)
+    cases.check_rectify(gpu_backend, 12, mx, my, "mono8", "mono8", 1296, 1024, n=2, expect_variant=4, expect_overflow=True)
 
 
 def test_rectify_full_size_colour(gpu_backend):

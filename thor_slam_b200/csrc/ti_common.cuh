@@ -128,6 +128,8 @@ struct CameraSlot {
     int tiles4_x[P4_N_TH] = {0, 0, 0}, tiles4_y[P4_N_TH] = {0, 0, 0};
     int rows4_alloc[P4_N_TH] = {0, 0, 0};
     int exc4_per_warp[P4_N_TH] = {0, 0, 0};
+    uint32_t* d_over4[P4_N_TH] = {nullptr, nullptr, nullptr};    // output pixels whose (tile, warp) exception list was full
+    int n_over4[P4_N_TH] = {0, 0, 0};
     bool has_tma_mono[3] = {false, false, false};   // tile height 16, 32, 24 (index = M3_TH_INDEX)
     uint32_t* d_lut3[3] = {nullptr, nullptr, nullptr};
     TileBox2* d_boxes3[3] = {nullptr, nullptr, nullptr};
@@ -206,7 +208,9 @@ struct ti_ctx {
     cudaEvent_t ev_compute = nullptr, ev_gather = nullptr, ev_counts = nullptr;
     uint32_t* d_comm_words = nullptr;  // 256 words: gathered counts, push reservations, the barrier's zero
     uint32_t* h_comm_words = nullptr;  // pinned mirror
-    bool gather_pending = false;
+    bool gather_pending = false, counts_pending = false;
+    cudaEvent_t ev_fence[16] = {};  // ti_exchange_fence ring
+    uint64_t fences = 0;
     int push_blocks = 0;  // CTAs of the peer-store copy kernels (0 = 32)
 };
 

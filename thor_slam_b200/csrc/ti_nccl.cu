@@ -103,6 +103,8 @@ void ti_nccl_teardown(ti_ctx* ctx) {
     if (ctx->s_comm) {
         cudaStreamSynchronize(ctx->s_comm);
         cudaEventDestroy(ctx->ev_compute); cudaEventDestroy(ctx->ev_gather); cudaEventDestroy(ctx->ev_counts);
+        for (auto& ev : ctx->ev_fence) { if (ev) cudaEventDestroy(ev); ev = nullptr; }
+        ctx->counts_pending = false; ctx->gather_pending = false;
         cudaFree(ctx->d_comm_words); cudaFreeHost(ctx->h_comm_words);
         cudaStreamDestroy(ctx->s_comm);
         ctx->s_comm = nullptr; ctx->d_comm_words = nullptr; ctx->h_comm_words = nullptr;
@@ -139,7 +141,7 @@ int ti_nccl_init(ti_ctx* ctx, const void* id128, int rank, int world) {
     return TI_OK;
 }
 
-int ti_gather_clouds(ti_ctx* ctx, const void* local, void* gathered, const uint64_t* bytes_per_rank, int root) {
+static int gather_on_comm_stream(ti_ctx* ctx, const void* local, void* gathered, const uint64_t* bytes_per_rank, int root, bool follow) {
     if (!ctx) return TI_EINVAL;
     if (!ctx->nccl_comm) return ti::fail(ctx, TI_ESTATE, "ti_gather_clouds: call ti_nccl_init first");
     if (!bytes_per_rank || root < 0 || root >= ctx->world) return ti::fail(ctx, TI_EINVAL, "ti_gather_clouds: bad arguments");
@@ -151,7 +153,7 @@ int ti_gather_clouds(ti_ctx* ctx, const void* local, void* gathered, const uint6
     if (mine && !local) return ti::fail(ctx, TI_EINVAL, "ti_gather_clouds: null local buffer");
     int rc = ti_comm_ready(ctx);
     if (rc != TI_OK) return rc;
-    if ((rc = ti_comm_follow_compute(ctx)) != TI_OK) return rc;
+    if (follow && (rc = ti_comm_follow_compute(ctx)) != TI_OK) return rc;
     if (ctx->rank == root) {
         uint64_t off = 0;
         for (int r = 0; r < root; ++r) off += bytes_per_rank[r];
@@ -177,6 +179,49 @@ int ti_gather_clouds(ti_ctx* ctx, const void* local, void* gathered, const uint6
     return TI_OK;
 }
 
+int ti_gather_clouds(ti_ctx* ctx, const void* local, void* gathered, const uint64_t* bytes_per_rank, int root) {
+    return gather_on_comm_stream(ctx, local, gathered, bytes_per_rank, root, /*follow=*/true);
+}
+
+int ti_gather_records(ti_ctx* ctx, const uint64_t* records, uint64_t* gathered, const uint32_t* counts, int root) {
+    if (!ctx) return TI_EINVAL;
+    if (!counts) return ti::fail(ctx, TI_EINVAL, "ti_gather_records: null counts");
+    if (ctx->world > 256) return ti::fail(ctx, TI_EINVAL, "ti_gather_records: at most 256 ranks");
+    uint64_t bytes[256];
+    for (int r = 0; r < ctx->world; ++r) bytes[r] = (uint64_t)counts[r] * sizeof(uint64_t);
+    // ordered on the exchange stream behind the ti_gather_counts_begin that sized it - NOT behind what the ingest stream
+    // has been given since (the next batch's kernels)
+    return gather_on_comm_stream(ctx, records, gathered, bytes, root, /*follow=*/false);
+}
+
+int ti_exchange_fence(ti_ctx* ctx, uint64_t* fence) {
+    if (!ctx) return TI_EINVAL;
+    if (!fence) return ti::fail(ctx, TI_EINVAL, "ti_exchange_fence: null fence");
+    TI_CUDA(ctx, cudaSetDevice(ctx->device));
+    const int rc = ti_comm_ready(ctx);
+    if (rc != TI_OK) return rc;
+    constexpr uint64_t kRing = sizeof(ctx->ev_fence) / sizeof(ctx->ev_fence[0]);
+    const uint64_t f = ctx->fences + 1;
+    if (!ctx->ev_fence[f % kRing]) TI_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_fence[f % kRing], cudaEventDisableTiming));
+    TI_CUDA(ctx, cudaEventRecord(ctx->ev_fence[f % kRing], ctx->s_comm));
+    ctx->fences = f;
+    *fence = f;
+    return TI_OK;
+}
+
+int ti_exchange_wait(ti_ctx* ctx, uint64_t fence, int on_stream) {
+    if (!ctx) return TI_EINVAL;
+    if (fence == 0) return TI_OK;
+    constexpr uint64_t kRing = sizeof(ctx->ev_fence) / sizeof(ctx->ev_fence[0]);
+    if (fence > ctx->fences) return ti::fail(ctx, TI_EINVAL, "ti_exchange_wait: fence %llu was never issued", (unsigned long long)fence);
+    if (ctx->fences - fence >= kRing)
+        return ti::fail(ctx, TI_EINVAL, "ti_exchange_wait: fence %llu is more than %d fences old", (unsigned long long)fence, (int)kRing);
+    TI_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (on_stream) TI_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_fence[fence % kRing], 0));
+    else TI_CUDA(ctx, cudaEventSynchronize(ctx->ev_fence[fence % kRing]));
+    return TI_OK;
+}
+
 int ti_gather_wait(ti_ctx* ctx, int on_stream) {
     if (!ctx) return TI_EINVAL;
     if (!ctx->gather_pending) return TI_OK;
@@ -190,11 +235,12 @@ int ti_gather_wait(ti_ctx* ctx, int on_stream) {
     return TI_OK;
 }
 
-int ti_gather_counts(ti_ctx* ctx, const uint32_t* n_local, uint32_t* counts) {
+int ti_gather_counts_begin(ti_ctx* ctx, const uint32_t* n_local) {
     if (!ctx) return TI_EINVAL;
-    if (!ctx->nccl_comm) return ti::fail(ctx, TI_ESTATE, "ti_gather_counts: call ti_nccl_init first");
-    if (!n_local || !counts) return ti::fail(ctx, TI_EINVAL, "ti_gather_counts: null argument");
-    if (ctx->world > 256) return ti::fail(ctx, TI_EINVAL, "ti_gather_counts: at most 256 ranks");
+    if (!ctx->nccl_comm) return ti::fail(ctx, TI_ESTATE, "ti_gather_counts_begin: call ti_nccl_init first");
+    if (!n_local) return ti::fail(ctx, TI_EINVAL, "ti_gather_counts_begin: null argument");
+    if (ctx->world > 128) return ti::fail(ctx, TI_EINVAL, "ti_gather_counts_begin: at most 128 ranks");
+    if (ctx->counts_pending) return ti::fail(ctx, TI_ESTATE, "ti_gather_counts_begin: the previous counts were not collected (ti_gather_counts_finish)");
     TI_CUDA(ctx, cudaSetDevice(ctx->device));
     int rc = ti_comm_ready(ctx);
     if (rc != TI_OK) return rc;
@@ -202,9 +248,24 @@ int ti_gather_counts(ti_ctx* ctx, const uint32_t* n_local, uint32_t* counts) {
     TI_NCCL(ctx, nccl().AllGather(n_local, ctx->d_comm_words, 1, NCCL_UINT32, (ncclComm_t)ctx->nccl_comm, ctx->s_comm));
     TI_CUDA(ctx, cudaMemcpyAsync(ctx->h_comm_words, ctx->d_comm_words, sizeof(uint32_t) * ctx->world, cudaMemcpyDeviceToHost, ctx->s_comm));
     TI_CUDA(ctx, cudaEventRecord(ctx->ev_counts, ctx->s_comm));
-    TI_CUDA(ctx, cudaEventSynchronize(ctx->ev_counts));  // the ingest stream keeps running whatever was enqueued after this call's event
-    for (int r = 0; r < ctx->world; ++r) counts[r] = ctx->h_comm_words[r];
+    ctx->counts_pending = true;
     return TI_OK;
+}
+
+int ti_gather_counts_finish(ti_ctx* ctx, uint32_t* counts) {
+    if (!ctx) return TI_EINVAL;
+    if (!counts) return ti::fail(ctx, TI_EINVAL, "ti_gather_counts_finish: null argument");
+    if (!ctx->counts_pending) return ti::fail(ctx, TI_ESTATE, "ti_gather_counts_finish: no ti_gather_counts_begin is outstanding");
+    TI_CUDA(ctx, cudaSetDevice(ctx->device));
+    TI_CUDA(ctx, cudaEventSynchronize(ctx->ev_counts));  // the ingest stream keeps running what it was given meanwhile
+    for (int r = 0; r < ctx->world; ++r) counts[r] = ctx->h_comm_words[r];
+    ctx->counts_pending = false;
+    return TI_OK;
+}
+
+int ti_gather_counts(ti_ctx* ctx, const uint32_t* n_local, uint32_t* counts) {
+    const int rc = ti_gather_counts_begin(ctx, n_local);
+    return rc != TI_OK ? rc : ti_gather_counts_finish(ctx, counts);
 }
 
 int ti_nccl_barrier(ti_ctx* ctx) {

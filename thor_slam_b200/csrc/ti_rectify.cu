@@ -598,6 +598,29 @@ __global__ void __launch_bounds__(256) rectify_direct_kernel(DirectJob J, int n_
     }
 }
 
+// The overflow pixels of a pair-window slot (ti_rectify_pair.cu): one thread per listed pixel and frame, taps from global
+// memory through the generic LUT - the arithmetic of rectify_direct_kernel<DM_MONO>.
+__global__ void __launch_bounds__(256) rectify_points_kernel(DirectJob J, const uint32_t* __restrict__ pts, int n_pts, int n_batch) {
+    const uint64_t total = (uint64_t)n_pts * n_batch;
+    for (uint64_t t = (uint64_t)blockIdx.x * 256 + threadIdx.x; t < total; t += (uint64_t)gridDim.x * 256) {
+        const uint64_t b = t / (uint32_t)n_pts;
+        const uint32_t p = pts[t - b * (uint32_t)n_pts];
+        const int v = (int)(p / (uint32_t)J.dst_w), u = (int)(p - (uint32_t)v * J.dst_w);
+        const uint32_t ek = J.lut[(size_t)v * J.lut_pitch + u];
+        uint8_t* dst = J.dst + b * J.dst_stride + p;
+        if (ek == LUT_OUTSIDE) { *dst = 0; continue; }
+        const int sx = (int)(ek & LUT_COORD_MASK) - 1, sy = (int)((ek >> LUT_COORD_BITS) & LUT_COORD_MASK) - 1;
+        const uint32_t fx = (ek >> 22) & 31u, fy = ek >> 27;
+        const uint8_t* src = J.src + b * J.src_stride;
+        uint32_t t00[3], t01[3], t10[3], t11[3];
+        fetch<DM_MONO>(J, src, sx, sy, t00);
+        fetch<DM_MONO>(J, src, sx + 1, sy, t01);
+        fetch<DM_MONO>(J, src, sx, sy + 1, t10);
+        fetch<DM_MONO>(J, src, sx + 1, sy + 1, t11);
+        *dst = (uint8_t)bilinear_u8(t00[0], t01[0], t10[0], t11[0], fx, fy);
+    }
+}
+
 static int direct_mode(int s, int d) {
     if ((s == TI_FMT_MONO8 || s == TI_FMT_NV12) && d == TI_FMT_MONO8) return DM_MONO;
     if (s == TI_FMT_BGR8 && d == TI_FMT_RGB8) return DM_BGR_TO_RGB;
@@ -702,6 +725,7 @@ int launch_rectify(ti_ctx* ctx, const RectifyJob* jobs_in, int n_jobs, int n_bat
     Rect3Params PT{};       // fast mono launch (v3: TMA-pipelined)
     Rect4Params PP{};       // fast mono launch (v4: pair windows)
     Rect5Params PC{};       // fast 3-channel launch (BGR8 -> RGB8 windows)
+    std::vector<DirectJob> pair_overflow;  // pair-window jobs whose slot has an overflow list (mode = camera slot)
     const int thk = m3_th_index(ctx->tma_tile_h);
     const int th4 = p4_th_index(ctx->tma_tile_h);
     size_t smem1 = 0, smem3 = 0, smem2 = 0;
@@ -760,6 +784,8 @@ int launch_rectify(ti_ctx* ctx, const RectifyJob* jobs_in, int n_jobs, int n_bat
             PP.rows_alloc_max = std::max(PP.rows_alloc_max, D.rows_alloc);
             PP.exc_max = std::max(PP.exc_max, D.exc_per_warp);
             PP.job[PP.n_jobs++] = D;
+            if (C.n_over4[th4] > 0)
+                pair_overflow.push_back(DirectJob{J.src, J.dst, J.src_stride, J.dst_stride, C.d_lut, lut_pitch, C.dst_w, C.dst_h, C.src_w, C.src_h, J.camera});
             continue;
         }
         if (tma_ok) {
@@ -814,6 +840,15 @@ int launch_rectify(ti_ctx* ctx, const RectifyJob* jobs_in, int n_jobs, int n_bat
     if (PP.n_jobs) {
         const int rc = launch_rectify_pair(ctx, PP, th4);
         if (rc != TI_OK) return rc;
+        for (const DirectJob& D : pair_overflow) {  // slots with more exceptions in some (tile, warp) than its list holds
+            const CameraSlot& C = ctx->cams[D.mode];  // mode carries the slot here
+            DirectJob K = D;
+            K.mode = DM_MONO;
+            const uint64_t total = (uint64_t)C.n_over4[th4] * n_batch;
+            const int grid = (int)std::min<uint64_t>((total + 255) / 256, (uint64_t)ctx->sm_count * 8);
+            TI_LAUNCH(rectify_points_kernel, grid, 256, 0, ctx->stream, K, C.d_over4[th4], C.n_over4[th4], n_batch);
+            TI_CHECK_LAUNCH(ctx);
+        }
     }
     if (PT.n_jobs) {
         const int TH = M3_TILE_HEIGHTS[thk];

@@ -24,9 +24,9 @@
 //    exception list for the tile (window word, the two weight words, destination column / row),
 //    blends that single pixel from its own window and overwrites the byte (ordered behind the row
 //    loop's stores by __syncwarp).  The cost per frame is flat - one short pass whatever the number
-//    of exceptions - so the eight warps that share a stage stay in step.  Cameras with more than
-//    P4_MAX_EXC exceptions in one (tile, warp), or with source boxes wider than P4_PITCH, keep
-//    using the v3 / v2 kernels.
+//    of exceptions - so the eight warps that share a stage stay in step.  The 33rd and further exceptions of a
+//    (tile, warp) go to the slot's overflow list and are repaired after the kernel (rectify_points_kernel,
+//    ti_rectify.cu); only cameras with source boxes wider than P4_PITCH keep using the v3 / v2 kernels.
 //  * The LUT is 6 bytes per output pixel in memory (per pair: the window word and one word per pixel
 //    holding 32-fx, fy, fx and the fx = fy = 0 flag); a tile's 24 KB slice is prefetched into shared
 //    memory by a 1-D bulk copy one unit ahead (unit = tile x up to frames_per_unit frames of the
@@ -318,7 +318,8 @@ void free_pair_tables(CameraSlot& C) {
         if (C.d_lut4[k]) cudaFree(C.d_lut4[k]);
         if (C.d_boxes4[k]) cudaFree(C.d_boxes4[k]);
         if (C.d_exc4[k]) cudaFree(C.d_exc4[k]);
-        C.d_lut4[k] = nullptr; C.d_boxes4[k] = nullptr; C.d_exc4[k] = nullptr;
+        if (C.d_over4[k]) cudaFree(C.d_over4[k]);
+        C.d_lut4[k] = nullptr; C.d_boxes4[k] = nullptr; C.d_exc4[k] = nullptr; C.d_over4[k] = nullptr; C.n_over4[k] = 0;
         C.has_pair[k] = false; C.exc4_per_warp[k] = 0; C.rows4_alloc[k] = 0;
     }
 }
@@ -385,6 +386,7 @@ int build_pair_tables(ti_ctx* ctx, CameraSlot& C, const std::vector<uint32_t>& l
 
         std::vector<uint32_t> lut4(n_tiles * TH * P4_LUT_ROW_WORDS, 0u);
         std::vector<std::vector<uint32_t>> exc(n_tiles * P4_CONSUMER_WARPS);  // 4 words per entry
+        std::vector<uint32_t> over;  // output pixels (v * dst_w + u) whose warp list was full
         for (int ty = 0; ty < ty_n && ok; ++ty)
             for (int tx = 0; tx < tx_n && ok; ++tx) {
                 const size_t tile = (size_t)ty * tx_n + tx;
@@ -413,7 +415,16 @@ int build_pair_tables(ti_ctx* ctx, CameraSlot& C, const std::vector<uint32_t>& l
                             } else {
                                 // pixel b gets an entry of the warp's exception list: its own window (bytes b.left, b.right
                                 // selected into bytes 0, 1), its weight words, where it goes
-                                if (ex.size() / 4 >= (size_t)P4_MAX_EXC) { ok = false; break; }
+                                if (ex.size() / 4 >= (size_t)P4_MAX_EXC) {
+                                    // the warp's list is full (a strongly bent map: a fisheye4 camera at 1280 x 800 has up to 42 such
+                                    // pairs in one (tile, warp)): the pixel joins the slot's OVERFLOW list, repaired after the kernel by
+                                    // one thread per pixel and frame from the generic LUT (rectify_points_kernel) - a handful of pixels
+                                    // per frame, so every reference camera model stays on this kernel
+                                    m = (off << 16) | sa | ((sa + 1) << 4) | (sa << 8) | ((sa + 1) << 12);
+                                    over.push_back((uint32_t)v * (uint32_t)dst_w + (uint32_t)(ua + 1));
+                                    if (over.size() > (size_t)dst_w * dst_h / 32) { ok = false; break; }  // beyond ~3 % the per-pixel pass costs more than v3
+                                    continue;
+                                }
                                 const int wordb = (b.x0 - B.c0) & ~3;
                                 const uint32_t offb = (uint32_t)((b.y0 - B.y0) * P4_PITCH + wordb);
                                 const uint32_t sb = (uint32_t)(b.x0 - B.c0 - wordb);
@@ -444,6 +455,11 @@ int build_pair_tables(ti_ctx* ctx, CameraSlot& C, const std::vector<uint32_t>& l
         TI_CUDA(ctx, cudaMemcpy(C.d_lut4[k], lut4.data(), lut4.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
         TI_CUDA(ctx, cudaMemcpy(C.d_boxes4[k], boxes.data(), boxes.size() * sizeof(TileBox2), cudaMemcpyHostToDevice));
         TI_CUDA(ctx, cudaMemcpy(C.d_exc4[k], exc_flat.data(), exc_flat.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+        if (!over.empty()) {
+            TI_CUDA(ctx, cudaMalloc(&C.d_over4[k], over.size() * sizeof(uint32_t)));
+            TI_CUDA(ctx, cudaMemcpy(C.d_over4[k], over.data(), over.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+        }
+        C.n_over4[k] = (int)over.size();
         C.tiles4_x[k] = tx_n; C.tiles4_y[k] = ty_n; C.rows4_alloc[k] = rows_alloc; C.exc4_per_warp[k] = epw;
         C.has_pair[k] = true;
     }

@@ -79,6 +79,11 @@ SIGNATURES: dict[str, tuple] = {
     "ti_gather_clouds": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_uint64), C.c_int]),
     "ti_gather_wait": (C.c_int, [C.c_void_p, C.c_int]),
     "ti_gather_counts": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_uint32)]),
+    "ti_gather_counts_begin": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "ti_gather_counts_finish": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint32)]),
+    "ti_gather_records": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_uint32), C.c_int]),
+    "ti_exchange_fence": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64)]),
+    "ti_exchange_wait": (C.c_int, [C.c_void_p, C.c_uint64, C.c_int]),
     "ti_nccl_barrier": (C.c_int, [C.c_void_p]),
     "ti_inbox_init": (C.c_int, [C.c_void_p, C.c_void_p]),
     "ti_cloud_push": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32]),

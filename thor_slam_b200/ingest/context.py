@@ -187,7 +187,7 @@ class IngestContext:
         out = (ctypes.c_int32 * 8)()
         self._check(self.lib.ti_rectify_plan(self._h, camera, out))
         return {"variant": int(out[0]), "tile_h": int(out[1]), "rows": int(out[2]), "exceptions_per_warp": int(out[3]),
-                "colour_variant": int(out[4]), "colour_rows": int(out[5])}
+                "colour_variant": int(out[4]), "colour_rows": int(out[5]), "overflow_pixels": int(out[6])}
 
     def get_valid_mask(self, camera: int, out: Any) -> Any:
         self._check(self.lib.ti_get_valid_mask(self._h, camera, self._ptr(out)))
@@ -319,6 +319,27 @@ class IngestContext:
         out = (C.c_uint32 * world)()
         self._check(self.lib.ti_gather_counts(self._h, self._ptr(n_local), out))
         return [int(x) for x in out]
+
+    def gather_counts_begin(self, n_local: Any) -> None:
+        self._check(self.lib.ti_gather_counts_begin(self._h, self._ptr(n_local)))
+
+    def gather_counts_finish(self, world: int) -> list[int]:
+        out = (C.c_uint32 * world)()
+        self._check(self.lib.ti_gather_counts_finish(self._h, out))
+        return [int(x) for x in out]
+
+    def gather_records(self, records: Any, gathered: Any, counts: Sequence[int], root: int = 0) -> None:
+        """Variable-length gather of voxel lists sized by ``gather_counts*`` (``ti_gather_records``), on the exchange stream."""
+        arr = (C.c_uint32 * len(counts))(*[int(c) for c in counts])
+        self._check(self.lib.ti_gather_records(self._h, self._ptr(records), self._ptr(gathered), arr, root))
+
+    def exchange_fence(self) -> int:
+        f = C.c_uint64(0)
+        self._check(self.lib.ti_exchange_fence(self._h, C.byref(f)))
+        return int(f.value)
+
+    def exchange_wait(self, fence: int, on_stream: bool = False) -> None:
+        self._check(self.lib.ti_exchange_wait(self._h, int(fence), 1 if on_stream else 0))
 
     def inbox_init(self, inbox: int) -> None:
         self._check(self.lib.ti_inbox_init(self._h, C.c_void_p(inbox)))

@@ -100,6 +100,7 @@ class CloudGather:
         self.backend = dist.get_backend(group) if dist.is_initialized() else "none"
         self._nccl_ready = False
         self._keep: Any = None
+        self._pending_counts: list[int] | None = None
 
     def _ensure_nccl(self) -> None:
         if self._nccl_ready:
@@ -154,17 +155,37 @@ class CloudGather:
     def gather_records(self, records: torch.Tensor, n_records: torch.Tensor, gathered: torch.Tensor | None = None,
                        wait: bool = True) -> tuple[torch.Tensor | None, list[int]]:
         """Variable-length gather of ``ti_voxel_cloud`` lists: rank r contributes ``records[:n_records]`` (a DEVICE count).
-        Returns (fused list on root else ``None``, records per rank)."""
-        if self.backend == "nccl" and records.is_cuda:
+        Returns (fused list on root else ``None``, records per rank).  = :meth:`records_begin` + :meth:`records_send`."""
+        self.records_begin(n_records)
+        return self.records_send(records, gathered, wait)
+
+    def records_begin(self, n_records: torch.Tensor) -> None:
+        """First half: all-gather the device counts on the exchange stream, behind what the ingest stream holds now.  A pipelined
+        caller enqueues its next batch between this call and :meth:`records_send`, which blocks for the counts."""
+        if self.backend == "nccl" and n_records.is_cuda:
             self._ensure_nccl()
-            counts = self.ctx.gather_counts(n_records, self.world)
+            self.ctx.gather_counts_begin(n_records)
+            self._pending_counts = None
         else:
             mine = torch.tensor([int(n_records.view(-1)[0].item())], dtype=torch.int64)
             out = [torch.zeros_like(mine) for _ in range(self.world)]
             dist.all_gather(out, mine, group=self.group)
-            counts = [int(t.item()) for t in out]
+            self._pending_counts = [int(t.item()) for t in out]
+
+    def records_send(self, records: torch.Tensor, gathered: torch.Tensor | None = None, wait: bool = True) -> tuple[torch.Tensor | None, list[int]]:
+        """Second half: collect the counts, then the grouped send / receive of exactly that many records per rank."""
         cap = int(records.shape[0])
-        counts = [min(c, cap) for c in counts]  # a truncated list still reports its full count
+        if self._pending_counts is None:
+            counts = [min(c, cap) for c in self.ctx.gather_counts_finish(self.world)]  # a truncated list still reports its full count
+            total = sum(counts)
+            if self.rank == self.root and gathered is None:
+                gathered = torch.empty(total, dtype=records.dtype, device=records.device)
+            self._keep = records
+            self.ctx.gather_records(records, gathered, counts, self.root)
+            if wait:
+                self.wait()
+            return (gathered if self.rank == self.root else None), counts
+        counts = [min(c, cap) for c in self._pending_counts]
         sizes = [c * records.element_size() for c in counts]
         return self._gather_sized(records, gathered, sizes, wait), counts
 
@@ -200,11 +221,13 @@ class RecordExchange:
         self.round = 0
         self.taken = 0
 
-    def push(self, records: Any, n_records: Any) -> None:
-        """Append this rank's list for the current round; rounds advance with every call."""
+    def push(self, records: Any, n_records: Any) -> int:
+        """Append this rank's list for the current round; rounds advance with every call.  Returns a fence: once it has
+        passed (``ctx.exchange_wait(fence, on_stream=True)``), ``records`` may be overwritten."""
         k = self.round
         self.ctx.cloud_push(records, n_records, self.inbox[k % self.slots], self.capacity, k // self.slots)
         self.round += 1
+        return self.ctx.exchange_fence()
 
     def take(self, dst: Any, status: Any) -> None:
         """Root only: the next round's fused list into ``dst`` (u64 [>= capacity]), ``status`` = (count, error flag)."""
