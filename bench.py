@@ -271,6 +271,7 @@ def run_ours(args) -> None:
     distributed = world > 1
     if distributed:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # stdout carries the one JSON line and nothing else
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     def barrier() -> None:
@@ -756,8 +757,8 @@ def run_config5_exchange(args, ctx, sources, rank: int, world: int, barrier, pea
                     ctx.exchange_wait(fences[k - NB], on_stream=True)
                 compute(k)
                 fences[k] = ex.push(rec[k % NB], nrec[k % NB])
-                if rank == 0:
-                    ex.take(taken, status)
+                if rank == 0:  # the fusing rank consumes a round in place while the other inbox fills; the last one is copied out for the oracle
+                    ex.take(taken if k == n - 1 else None, status)
             ex.wait(on_stream=True)
             e1.record(stream)
             e1.synchronize()

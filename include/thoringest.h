@@ -105,7 +105,7 @@ typedef enum ti_option {
     TI_OPT_FRAMES_PER_UNIT = 6,       /* frames of a batch sharing one LUT fetch in the TMA kernels (default 16; pair-window: 0 = automatic) */
     TI_OPT_STAGES = 7,                /* shared-memory ring depth of the TMA kernels, 2..8 (default 6 pair-window, reduced to fit; 2 shifted-copy) */
     TI_OPT_LUT_PREFETCH = 8,          /* 1: consumers prefetch the next unit's LUT into a second register set (default 0) */
-    TI_OPT_PUSH_BLOCKS = 9            /* CTAs of the peer-store copy kernels of ti_cloud_push / ti_inbox_take (default 32) */
+    TI_OPT_PUSH_BLOCKS = 9            /* CTAs of the peer-store copy kernels of ti_cloud_push / ti_inbox_take (default: one per SM) */
 } ti_option;
 int ti_set_option(ti_ctx* ctx, int option, int value);
 int ti_device_sm_count(const ti_ctx* ctx);
@@ -287,8 +287,9 @@ int ti_inbox_init(ti_ctx* ctx, void* inbox);
 int ti_cloud_push(ti_ctx* ctx, const uint64_t* records, const uint32_t* n_records, void* inbox, uint64_t inbox_capacity,
                   uint32_t gen);
 /* Root: wait on the device until `world` ranks have reported done for the inbox's current generation, copy
- * min(count, inbox_capacity, dst_capacity) records to dst (DEVICE), write status[0] = count, status[1] = error flag
- * (DEVICE u32[2]; error != 0: a peer missed its 4 s deadline), empty the inbox and advance its generation. */
+ * min(count, inbox_capacity, dst_capacity) records to dst (DEVICE; dst_capacity 0: no copy - the caller consumed the inbox in
+ * place while it was the other slot's turn), write status[0] = count, status[1] = error flag (DEVICE u32[2]; error != 0: a
+ * peer missed its 4 s deadline), empty the inbox and advance its generation. */
 int ti_inbox_take(ti_ctx* ctx, void* inbox, uint64_t inbox_capacity, uint32_t world, uint64_t* dst, uint64_t dst_capacity,
                   uint32_t* status);
 

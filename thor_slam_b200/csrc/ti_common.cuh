@@ -211,7 +211,7 @@ struct ti_ctx {
     bool gather_pending = false, counts_pending = false;
     cudaEvent_t ev_fence[16] = {};  // ti_exchange_fence ring
     uint64_t fences = 0;
-    int push_blocks = 0;  // CTAs of the peer-store copy kernels (0 = 32)
+    int push_blocks = 0;  // CTAs of the peer-store copy kernels (0 = one per SM)
 };
 
 void ti_nccl_teardown(ti_ctx* ctx);  // ti_nccl.cu

@@ -81,7 +81,9 @@ constexpr int NCCL_SUM = 0;     // ncclSum
 // stream first waits for what the ingest stream has enqueued so far, and whoever needs the result waits for ev_gather.
 int ti_comm_ready(ti_ctx* ctx) {
     if (ctx->s_comm) return TI_OK;
-    TI_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->s_comm, cudaStreamNonBlocking));
+    int prio_low = 0, prio_high = 0;  // the exchange stream's (small) kernels go first whenever an SM has room
+    TI_CUDA(ctx, cudaDeviceGetStreamPriorityRange(&prio_low, &prio_high));
+    TI_CUDA(ctx, cudaStreamCreateWithPriority(&ctx->s_comm, cudaStreamNonBlocking, prio_high));
     TI_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_compute, cudaEventDisableTiming));
     TI_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_gather, cudaEventDisableTiming));
     TI_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_counts, cudaEventDisableTiming));

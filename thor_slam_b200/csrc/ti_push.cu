@@ -22,7 +22,9 @@
 namespace ti {
 
 constexpr uint64_t TI_PUSH_TIMEOUT_NS = 4000000000ull;  // 4 s
-constexpr int PUSH_THREADS = 256;
+constexpr int PUSH_THREADS = 64;   // small CTAs of <= 32 registers per thread: they fit beside the resident CTAs of the persistent
+                                    // ingest kernels (which leave ~3 K registers and no shared memory to spare per SM), so the
+                                    // copies really run UNDER the next batch's kernels instead of queueing behind them
 
 struct InboxHdr {
     uint32_t n_records;  // slots reserved so far in this generation (may exceed the capacity: the list was truncated)
@@ -66,7 +68,7 @@ __global__ void push_reserve_kernel(InboxHdr* hdr, const uint32_t* n_local, uint
     words[1] = (uint64_t)base >= capacity ? 0u : (uint32_t)min((uint64_t)n, capacity - base);
 }
 
-__global__ void __launch_bounds__(PUSH_THREADS) push_copy_kernel(InboxHdr* hdr, const uint64_t* __restrict__ local, uint32_t* words) {
+__global__ void __launch_bounds__(PUSH_THREADS, 32) push_copy_kernel(InboxHdr* hdr, const uint64_t* __restrict__ local, uint32_t* words) {
     uint64_t* remote = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(hdr) + TI_INBOX_HEADER_BYTES);
     const uint32_t base = words[0], n = words[1];
     // 16-byte stores where source and destination line up (base even), 8-byte otherwise
@@ -106,7 +108,7 @@ __global__ void inbox_wait_kernel(InboxHdr* hdr, uint32_t world, uint32_t* statu
     status[1] = ld_acquire_sys(&hdr->error);
 }
 
-__global__ void __launch_bounds__(PUSH_THREADS) inbox_copy_kernel(const InboxHdr* hdr, uint64_t capacity, const uint32_t* status, uint64_t* dst,
+__global__ void __launch_bounds__(PUSH_THREADS, 32) inbox_copy_kernel(const InboxHdr* hdr, uint64_t capacity, const uint32_t* status, uint64_t* dst,
                                                                   uint64_t dst_capacity) {
     const uint64_t* src = reinterpret_cast<const uint64_t*>(reinterpret_cast<const uint8_t*>(hdr) + TI_INBOX_HEADER_BYTES);
     const uint64_t n = min(min((uint64_t)status[0], capacity), dst_capacity);
@@ -152,7 +154,7 @@ int ti_cloud_push(ti_ctx* ctx, const uint64_t* records, const uint32_t* n_record
     uint32_t* words = ctx->d_comm_words + 128;
     push_reserve_kernel<<<1, 32, 0, ctx->s_comm>>>(hdr, n_records, gen, inbox_capacity, words);
     TI_CHECK_LAUNCH(ctx);
-    push_copy_kernel<<<ctx->push_blocks > 0 ? ctx->push_blocks : 32, PUSH_THREADS, 0, ctx->s_comm>>>(hdr, records, words);
+    push_copy_kernel<<<ctx->push_blocks > 0 ? ctx->push_blocks : 2 * ctx->sm_count, PUSH_THREADS, 0, ctx->s_comm>>>(hdr, records, words);
     TI_CHECK_LAUNCH(ctx);
     TI_CUDA(ctx, cudaEventRecord(ctx->ev_gather, ctx->s_comm));
     ctx->gather_pending = true;
@@ -169,7 +171,7 @@ int ti_inbox_take(ti_ctx* ctx, void* inbox, uint64_t inbox_capacity, uint32_t wo
     inbox_wait_kernel<<<1, 32, 0, ctx->s_comm>>>(hdr, world, status);
     TI_CHECK_LAUNCH(ctx);
     if (dst_capacity) {
-        inbox_copy_kernel<<<ctx->push_blocks > 0 ? ctx->push_blocks : 32, PUSH_THREADS, 0, ctx->s_comm>>>(hdr, inbox_capacity, status, dst, dst_capacity);
+        inbox_copy_kernel<<<ctx->push_blocks > 0 ? ctx->push_blocks : 2 * ctx->sm_count, PUSH_THREADS, 0, ctx->s_comm>>>(hdr, inbox_capacity, status, dst, dst_capacity);
         TI_CHECK_LAUNCH(ctx);
     }
     inbox_release_kernel<<<1, 32, 0, ctx->s_comm>>>(hdr);
