@@ -58,6 +58,12 @@ ALGO_BYTES_PER_PX = 2  # mono8 -> rectified mono8
 NCU_TRAFFIC_BYTES_PER_FRAME_SET = (584.931840e6 + 485.148160e6) / 64
 KERNEL_BY_VARIANT = {4: "rectify_mono_pair_kernel<32,false,1280>", 3: "rectify_mono_tma_kernel<32,false>", 2: "rectify_mono_kernel", 1: "rectify_tile_kernel<1>"}
 FALLBACK_HBM_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md fallback
+_JSON_OUT = sys.stdout
+
+
+def emit(line: dict) -> None:
+    _JSON_OUT.write(json.dumps(line) + "\n")
+    _JSON_OUT.flush()
 
 
 def measured_peak() -> tuple[float, str]:
@@ -240,7 +246,7 @@ def run_reference(args) -> None:
         "e2e": {"value": value, "unit": "frame-sets/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 def workload_config(batch: int, gpus: int) -> dict:
@@ -328,6 +334,17 @@ def run_ours(args) -> None:
     value = world * B * args.steps / (ms_max * 1e-3)
 
     got_value_frame = d_dst[3][1].cpu().numpy() if rank == 0 else None  # checked against the oracle in the cpu_baseline leg
+
+    if args.only_config5 and distributed:  # a second pass (e.g. --strong): the headline K steps above, then config 5 and nothing else
+        c5 = run_config5_exchange(args, ctx, sources, rank, world, barrier, measured_peak()[0])
+        if rank == 0:
+            emit({"metric": "frame_sets_per_sec", "value": value, "unit": "frame-sets/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                  "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+                  "config": workload_config(B, world), "gpu_launches": launches, "clocks": clocks, "config5": c5,
+                  "note": "--only-config5 pass: no e2e / sustained / roofline blocks"})
+        ctx.close()
+        dist.destroy_process_group()
+        return
 
     # ---- the same loop, sustained: the K-step region above lasts milliseconds; this one >= args.sustain_s seconds, with the
     # SM clock sampled over it (one NVML poll per 4 ms) -------------------------------------------
@@ -465,7 +482,7 @@ def run_ours(args) -> None:
         for key, val in (("configs", configs), ("config5", config5), ("e2e_rig", e2e_rig), ("pcie", pcie)):
             if val is not None:
                 line[key] = val
-        print(json.dumps(line))
+        emit(line)
     ctx.close()
     if distributed:
         dist.destroy_process_group()
@@ -916,6 +933,12 @@ def pcie_probe(rank: int, world: int, barrier, mb: int = 256, iters: int = 6) ->
 
 
 def main() -> None:
+    # stdout carries the one JSON line and nothing else: whatever a library prints there (NCCL announces its version on the
+    # first communicator) goes to stderr instead; the line itself is written to the saved descriptor
+    global _JSON_OUT
+    sys.stdout.flush()
+    _JSON_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=400)
@@ -930,6 +953,7 @@ def main() -> None:
     ap.add_argument("--no-configs", action="store_true", dest="no_configs", help="skip configs 3/4/5 (N = 1) and config 5 with its exchange (N > 1)")
     ap.add_argument("--no-rig", action="store_true", dest="no_rig", help="skip the IngestRig end-to-end loop")
     ap.add_argument("--no-pcie", action="store_true", dest="no_pcie", help="skip the host<->device copy probe")
+    ap.add_argument("--only-config5", action="store_true", dest="only_config5", help="N > 1: skip the e2e loops and the sustained loop (a second, --strong pass)")
     ap.add_argument("--strong", action="store_true", help="config 5 at N > 1: 64 frame sets per step in total instead of 16 per rank")
     ap.add_argument("--sustain-s", type=float, default=1.5, dest="sustain_s", help="seconds of the sustained loop")
     ap.add_argument("--extras", action="store_true", help=argparse.SUPPRESS)  # round-1 flag, now the default
