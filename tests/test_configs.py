@@ -235,11 +235,18 @@ def _rotated_maps(w: int, h: int, deg: float):
 
 
 def test_rotated_map_overflows_the_exception_table_emulated(emu_backend):
-    """20 degrees of roll: almost every pixel pair straddles two source rows -> more than 32 exceptions per
-    (tile, warp) -> the slot is not eligible for the pair-window kernel; the plan says so and the result is exact."""
+    """20 degrees of roll: a third of the pixel pairs straddle two source rows.  With 32-row tiles the surplus over the 32
+    exceptions a (tile, warp) holds exceeds 3 % of the image -> the slot leaves the pair-window kernel, and the plan says so.
+    With 16-row tiles it stays, with full exception lists and an overflow list - and with exception entries whose
+    destination offset is -1 (the pixel left of the repairing lane's first one), which an all-ones "unused" marker once
+    swallowed: the result must be exact on every variant."""
     mx, my = _rotated_maps(256, 96, 20.0)
     emu_backend.ctx.upload_rectify_map(12, mx, my, (256, 96))
     assert emu_backend.ctx.rectify_plan(12)["variant"] < 4
+    emu_backend.ctx.set_option(emu_backend.ctx.OPT_TMA_TILE_H, 16)
+    plan16 = emu_backend.ctx.rectify_plan(12)
+    emu_backend.ctx.set_option(emu_backend.ctx.OPT_TMA_TILE_H, 32)
+    assert plan16["variant"] == 4 and plan16["exceptions_per_warp"] == 32 and plan16["overflow_pixels"] > 0, plan16
     cases.check_rectify(emu_backend, 12, mx, my, "mono8", "mono8", 256, 96, n=2)
 
 

@@ -59,15 +59,24 @@ class DeviceImage:
     ``dtype``, ``ndim`` and ``__array__`` make it acceptable wherever the
     reference's consumers expect ``CameraFrame.image`` (they only look at
     ``len(img.shape)`` and hand the array to OpenCV - isaac_ros.py:351-358).
-    The device->host copy happens at most once and only on demand.
+
+    LIFETIME.  The reference hands out fresh arrays (``getCvFrame()`` copies); here the pixels live in a ring slot of the rig
+    that produced them and stay valid for ``queue_size`` further polls of that rig - the window in which the reference's
+    queue would still hold the frame.  ``np.asarray(image)`` is a zero-copy view of the slot's pinned host mirror (the
+    device -> host copy was enqueued when the frame set left the rig); ``np.array(image)`` / ``image.copy()`` /
+    ``image.tensor.clone()`` give pixels of unlimited lifetime.  Touching a frame whose slot has since been re-used raises
+    ``RuntimeError`` instead of returning somebody else's pixels.
     """
 
-    __slots__ = ("tensor", "_host", "_ready")
+    __slots__ = ("tensor", "_host", "_ready", "_mirror", "_mirror_ready", "_guard")
 
-    def __init__(self, tensor: Any, ready_event: Any = None) -> None:
+    def __init__(self, tensor: Any, ready_event: Any = None, host_mirror: Any = None, mirror_event: Any = None, guard: Any = None) -> None:
         self.tensor = tensor
         self._host: np.ndarray | None = None
         self._ready = ready_event
+        self._mirror = host_mirror        # pinned host tensor the rig is copying `tensor` into (or None)
+        self._mirror_ready = mirror_event
+        self._guard = guard               # callable -> bool: the slot still holds this frame
 
     @property
     def shape(self) -> tuple[int, ...]:
@@ -81,26 +90,54 @@ class DeviceImage:
     def dtype(self) -> np.dtype:
         return np.dtype(str(self.tensor.dtype).replace("torch.", ""))
 
+    def _check_alive(self) -> None:
+        if self._guard is not None and not self._guard():
+            raise RuntimeError("this frame's ring slot has been re-used (frames stay valid for queue_size polls of their rig); "
+                               "copy frames you keep longer: np.array(image) or image.tensor.clone()")
+
     def wait(self) -> None:
+        """Block until the pixels are in ``tensor`` (device side)."""
         if self._ready is not None:
             self._ready.synchronize()
             self._ready = None
 
     def numpy(self) -> np.ndarray:
         if self._host is None:
-            self.wait()
-            self._host = self.tensor.cpu().numpy()
+            self._check_alive()
+            if self._mirror is not None:
+                if self._mirror_ready is not None:
+                    self._mirror_ready.synchronize()
+                    self._mirror_ready = None
+                self._check_alive()
+                m = self._mirror
+                self._host = m.view(torch_int16()).numpy().view(np.uint16) if str(m.dtype) == "torch.uint16" else m.numpy()
+            else:
+                self.wait()
+                self._host = self.tensor.cpu().numpy()
+        elif self._mirror is not None:
+            self._check_alive()
         return self._host
+
+    def copy(self) -> np.ndarray:
+        return np.array(self.numpy(), copy=True)
 
     def __array__(self, dtype: Any = None, copy: Any = None) -> np.ndarray:
         arr = self.numpy()
-        return arr if dtype is None else arr.astype(dtype, copy=False)
+        if dtype is not None:
+            arr = arr.astype(dtype, copy=False)
+        return np.array(arr, copy=True) if copy else arr
 
     def __len__(self) -> int:
         return self.shape[0]
 
     def __getitem__(self, idx: Any) -> Any:
         return self.numpy()[idx]
+
+
+def torch_int16() -> Any:
+    import torch
+
+    return torch.int16
 
 
 @dataclass

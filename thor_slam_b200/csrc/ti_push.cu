@@ -68,15 +68,23 @@ __global__ void push_reserve_kernel(InboxHdr* hdr, const uint32_t* n_local, uint
     words[1] = (uint64_t)base >= capacity ? 0u : (uint32_t)min((uint64_t)n, capacity - base);
 }
 
-__global__ void __launch_bounds__(PUSH_THREADS, 32) push_copy_kernel(InboxHdr* hdr, const uint64_t* __restrict__ local, uint32_t* words) {
+__global__ void __launch_bounds__(PUSH_THREADS, 24) push_copy_kernel(InboxHdr* hdr, const uint64_t* __restrict__ local, uint32_t* words) {
     uint64_t* remote = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(hdr) + TI_INBOX_HEADER_BYTES);
     const uint32_t base = words[0], n = words[1];
-    // 16-byte stores where source and destination line up (base even), 8-byte otherwise
+    // 16-byte stores where source and destination line up (base even), 8-byte otherwise.  Four independent 16-byte loads are
+    // in flight per thread before the first store: the few small CTAs that fit beside the ingest kernels have to cover the
+    // NVLink round trip with bytes in flight, not with thread count.
     const uint64_t tid = (uint64_t)blockIdx.x * PUSH_THREADS + threadIdx.x, nth = (uint64_t)gridDim.x * PUSH_THREADS;
     if ((base & 1u) == 0) {
         const uint4* s4 = reinterpret_cast<const uint4*>(local);
         uint4* d4 = reinterpret_cast<uint4*>(remote + base);
-        for (uint64_t i = tid; i < n / 2; i += nth) d4[i] = s4[i];
+        const uint64_t n4 = n / 2;
+        uint64_t i = tid;
+        for (; i + 3 * nth < n4; i += 4 * nth) {
+            const uint4 a = s4[i], b = s4[i + nth], c = s4[i + 2 * nth], d = s4[i + 3 * nth];
+            d4[i] = a; d4[i + nth] = b; d4[i + 2 * nth] = c; d4[i + 3 * nth] = d;
+        }
+        for (; i < n4; i += nth) d4[i] = s4[i];
         if (tid == 0 && (n & 1u)) remote[base + n - 1] = local[n - 1];
     } else {
         for (uint64_t i = tid; i < n; i += nth) remote[base + i] = local[i];

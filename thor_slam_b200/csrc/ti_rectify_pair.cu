@@ -241,10 +241,11 @@ __global__ void __launch_bounds__(P4_THREADS, TH == 32 ? 3 : 4) rectify_mono_pai
                 p4_expand(e2.y, w1[q].z, w1[q].w);
             }
         }
-        // this lane's exception entry (if any): entries are dense from 0, an unused one has all bits set in its last word
+        // this lane's exception entry (if any): entries are dense from 0, an unused one has P4_EXC_UNUSED in its last word (NOT all
+        // ones: -1 is a legitimate destination offset - the pixel left of the repairing lane's first one)
         const p4_addr_t my_exc = sm0 + 256u + (uint32_t)S * stage_bytes + LUT_BYTES + (k & 1u) * exc_buf_bytes +
                                  (uint32_t)(warp * J.exc_per_warp + lane) * 16u;
-        const bool i_fix = lane < J.exc_per_warp && p4_lds<12>(my_exc) != 0xFFFFFFFFu;
+        const bool i_fix = lane < J.exc_per_warp && p4_lds<12>(my_exc) != P4_EXC_UNUSED;
         const bool warp_fixes = __ballot_sync(0xFFFFFFFFu, i_fix) != 0u;  // warp-uniform
         __syncwarp();  // every lane's reads of the LUT slice are ordered before the release below
         if (lane == 0) mbar_arrive(lut_empty);
@@ -445,7 +446,7 @@ int build_pair_tables(ti_ctx* ctx, CameraSlot& C, const std::vector<uint32_t>& l
         size_t e_max = 0;
         for (const auto& e : exc) e_max = std::max(e_max, e.size() / 4);
         const int epw = (int)e_max;
-        std::vector<uint32_t> exc_flat(std::max<size_t>(4, n_tiles * P4_CONSUMER_WARPS * epw * 4), 0xFFFFFFFFu);  // unused entries: all ones
+        std::vector<uint32_t> exc_flat(std::max<size_t>(4, n_tiles * P4_CONSUMER_WARPS * epw * 4), P4_EXC_UNUSED);
         for (size_t i = 0; i < exc.size(); ++i)
             if (!exc[i].empty()) std::memcpy(exc_flat.data() + i * epw * 4, exc[i].data(), exc[i].size() * sizeof(uint32_t));
 

@@ -144,16 +144,23 @@ def stereo_rectification(
 
 
 def stereo_rectify_maps(
-    intrinsics: Sequence[Intrinsics], extrinsics: Sequence[Extrinsics], size: tuple[int, int]
-) -> list[tuple[np.ndarray, np.ndarray]]:
-    """Remap maps of a source: ``[left, right]`` for a stereo pair, ``[undistort-only]`` for a single camera."""
+    intrinsics: Sequence[Intrinsics], extrinsics: Sequence[Extrinsics], size: tuple[int, int], with_rp: bool = False
+):
+    """Remap maps of a source: ``[left, right]`` for a stereo pair, ``[undistort-only]`` for a single camera.
+
+    ``with_rp``: also return, per stream, ``{"R": 3x3, "P": 3x4}`` - what a rectified ``CameraInfo`` carries (for a single camera
+    ``R = I`` and ``P = [K | 0]``: undistortion only)."""
     if len(intrinsics) == 2:
         r1, r2, p1, p2 = stereo_rectification(intrinsics[0], intrinsics[1], extrinsics[0], extrinsics[1], size)
-        return [
+        maps = [
             undistort_rectify_map(intrinsics[0].matrix, intrinsics[0].coeffs, r1, p1, size),
             undistort_rectify_map(intrinsics[1].matrix, intrinsics[1].coeffs, r2, p2, size),
         ]
-    return [undistort_rectify_map(i.matrix, i.coeffs, None, None, size) for i in intrinsics]
+        rp = [{"R": np.asarray(r1, np.float64), "P": np.asarray(p1, np.float64)}, {"R": np.asarray(r2, np.float64), "P": np.asarray(p2, np.float64)}]
+    else:
+        maps = [undistort_rectify_map(i.matrix, i.coeffs, None, None, size) for i in intrinsics]
+        rp = [{"R": np.eye(3), "P": np.hstack([np.asarray(i.matrix, np.float64), np.zeros((3, 1))])} for i in intrinsics]
+    return (maps, rp) if with_rp else maps
 
 
 def body_T_camera(rig_T_source: np.ndarray | None, source_T_camera: np.ndarray, rig_frame: str = "rdf") -> np.ndarray:

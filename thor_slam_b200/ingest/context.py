@@ -245,6 +245,15 @@ class IngestContext:
         arr, n_batch = self._pack(streams, host=False)
         self._check(self.lib.ti_ingest(self._h, arr, len(streams), n_batch))
 
+    def prepare(self, streams: Sequence[StreamSpec]) -> tuple[Any, int, int, tuple]:
+        """Pack a stream list once; ``ingest_prepared`` then costs one foreign call (the live rig replays the same few slot
+        combinations for ever).  The buffers named in ``streams`` are kept alive by the returned object."""
+        arr, n_batch = self._pack(streams, host=False)
+        return arr, len(streams), n_batch, tuple(streams)
+
+    def ingest_prepared(self, prepared: tuple[Any, int, int, tuple]) -> None:
+        self._check(self.lib.ti_ingest(self._h, prepared[0], prepared[1], prepared[2]))
+
     def ingest_host(self, streams: Sequence[StreamSpec], chunk: int = 8) -> None:
         """Same with (pinned) host buffers: H2D, kernels and D2H pipelined ``chunk`` frame sets at a time."""
         arr, n_batch = self._pack(streams, host=True)

@@ -20,20 +20,31 @@ What changes relative to the reference (BASELINE.json north_star, "subsystems th
 * calibration: ``Intrinsics`` / ``Extrinsics`` (``camera/types.py``) are turned once into remap LUTs
   and 3x4 body transforms on the device (re-done on ``load_rig_extrinsics``).
 
-``CameraFrame.image`` of a returned frame is a :class:`DeviceImage` (ndarray-compatible, lazy device
--> host copy); ``SynchronizedFrameSet.clouds`` maps source name -> ``{"points", "mask", "count"}``.
+``CameraFrame.image`` of a returned frame is a :class:`DeviceImage` (ndarray-compatible; the device -> host copy into the slot's
+pinned mirror is enqueued before the frame set leaves the rig, ``np.asarray(image)`` only waits for it);
+``SynchronizedFrameSet.clouds`` maps source name -> ``{"points", "mask", "count"}``.
+
+Slot discipline (what replaces the reference's "every frame is a fresh array"): a slot's device input is re-staged only after
+the ingest kernels that read it have finished (an event per slot), its outputs stay valid for ``queue_size`` polls, and a
+:class:`DeviceImage` refuses to hand out pixels of a slot that has been re-used (``frames.py``).
+
+Calibration of what is returned: with ``rectify=True`` the pixels are rectified and undistorted, so the matching calibration
+is ``rectified_intrinsics(name)`` / ``rectification(name)`` (``D = 0``, ``K = P[:3,:3]``, ``R``, ``P`` - what a consumer
+publishes with ``rectified_images:=true``); ``calibration`` keeps describing the raw cameras, as in the reference.
 """
 
 from __future__ import annotations
 
 import logging
+import os
+from concurrent.futures import ThreadPoolExecutor
 from dataclasses import dataclass, field
 from typing import Any, Sequence
 
 import numpy as np
 import torch
 
-from thor_slam_b200.camera.calibration import Extrinsics, IMUExtrinsics
+from thor_slam_b200.camera.calibration import Extrinsics, IMUExtrinsics, Intrinsics
 from thor_slam_b200.camera.frames import CameraFrame, CameraSource, DeviceImage, FrameSet, SynchronizedFrameSet
 from thor_slam_b200.camera.rig import CameraRig
 from thor_slam_b200.ingest import formats as F
@@ -61,8 +72,10 @@ class _Stream:
     host: Any = None      # [queue_size, ...] pinned
     dev: Any = None       # [queue_size, ...] device
     out: Any = None       # [queue_size, ...] device, ingest output
+    out_host: Any = None  # [queue_size, ...] pinned mirror of `out`
     mask: Any = None
     count: Any = None
+    gen: list = field(default_factory=list)        # per slot: how many times it has been staged
 
 
 @dataclass
@@ -71,6 +84,8 @@ class _SlotFrameSet(FrameSet):
 
     slot: int = -1
     uploaded: Any = field(default=None, repr=False)  # event: H2D of this slot finished
+    gen: int = 0                                      # staging generation of the slot when this entry was made
+    result: Any = field(default=None, repr=False)    # (ready event, mirror event): the slot has been ingested already
 
 
 class IngestRig(CameraRig):
@@ -113,6 +128,11 @@ class IngestRig(CameraRig):
         self._colours: dict[str, Any] = {}
         self._next_camera = 0
         self._copy_stream = None if self._emulated else torch.cuda.Stream(device=self._device)
+        self._down_stream = None if self._emulated else torch.cuda.Stream(device=self._device)
+        self._slot_ingested: dict[tuple[str, int], Any] = {}   # (source, slot) -> event: the kernels that read the slot are done
+        self._prepared: dict[tuple, Any] = {}                  # slots of a frame set -> packed ti_stream array
+        self._pool = ThreadPoolExecutor(max_workers=max(2, min(8, (os.cpu_count() or 2) // 2)), thread_name_prefix="thor-stage")
+        self._rect: dict[str, list[dict]] = {}                 # per source, per stream: {"R", "P"} of the rectification
         self._build_streams()
         self._upload_calibration()
 
@@ -158,6 +178,8 @@ class IngestRig(CameraRig):
         st.host = self._alloc((slots, *F.frame_shape(st.src_format, w, h)), st.src_format, pinned=True)
         st.dev = self._alloc((slots, *F.frame_shape(st.src_format, w, h)), st.src_format)
         st.out = self._alloc((slots, *F.frame_shape(st.dst_format, dw, dh)), st.dst_format)
+        st.out_host = self._alloc((slots, *F.frame_shape(st.dst_format, dw, dh)), st.dst_format, pinned=True)
+        st.gen = [0] * slots
         if st.kind == F.KIND_BACKPROJECT:
             st.mask = self._alloc((slots, dh, dw), F.MONO8)
             st.count = torch.zeros((slots,), dtype=torch.int32, device=self._device)
@@ -180,9 +202,11 @@ class IngestRig(CameraRig):
             intr, extr = cal.intrinsics[name], cal.extrinsics[name]
             if self._rectify:
                 size = streams[0].src_size
-                maps = stereo_rectify_maps(intr, extr, size)
+                maps, rp = stereo_rectify_maps(intr, extr, size, with_rp=True)
+                self._rect[name] = rp
                 for st, (mx, my) in zip(streams, maps):
                     self._ctx.upload_rectify_map(st.camera, mx, my, st.src_size)
+                self._prepared.clear()
         for name, (_rgb, dep) in self._rgbd.items():
             src = self.sources[name]
             _ri, di = src.get_rgbd_intrinsics()
@@ -199,7 +223,8 @@ class IngestRig(CameraRig):
             self._upload_calibration()
 
     # -- frame-set assembly: pinned ring + async upload -------------------------------
-    def _stage(self, st: _Stream, slot: int, image: np.ndarray) -> None:
+    def _stage_host(self, st: _Stream, slot: int, image: np.ndarray) -> None:
+        """CPU half of staging (runs on the pool): one copy of the driver's frame into the slot's pinned buffer."""
         host = st.host[slot]
         src = torch.from_numpy(np.ascontiguousarray(image))
         if src.dtype != host.dtype:
@@ -207,57 +232,115 @@ class IngestRig(CameraRig):
         if tuple(src.shape) != tuple(host.shape):
             raise ValueError(f"{st.source}[{st.index}]: frame shape {tuple(src.shape)} does not match the calibrated {tuple(host.shape)}")
         host.copy_(src)
+
+    def _stage_upload(self, st: _Stream, slot: int) -> None:
+        """GPU half: pinned slot -> device slot on the copy stream, behind the kernels that still read the device slot."""
+        st.gen[slot] += 1
         if self._emulated:
-            st.dev[slot].copy_(host)
-        else:
-            with torch.cuda.stream(self._copy_stream):
-                st.dev[slot].copy_(host, non_blocking=True)
+            st.dev[slot].copy_(st.host[slot])
+            return
+        with torch.cuda.stream(self._copy_stream):
+            st.dev[slot].copy_(st.host[slot], non_blocking=True)
+
+    def _stage(self, st: _Stream, slot: int, image: np.ndarray) -> None:
+        self._stage_host(st, slot, image)
+        self._stage_upload(st, slot)
+
+    def _wait_slot_free(self, name: str, slot: int) -> None:
+        """Before a slot is re-staged: the ingest kernels that read its device buffer (and the download of its outputs) are done."""
+        ev = self._slot_ingested.pop((name, slot), None)
+        if ev is not None and not self._emulated:
+            ready, mirror = ev
+            self._copy_stream.wait_event(ready)  # write-after-read on st.dev[slot]
+            mirror.synchronize()                 # the pinned input / output mirrors of the slot are host-visible state
 
     def _wrap_frames(self, name: str, frames: list) -> FrameSet:
         streams = self._streams[name]
         slot = self._frame_queues[name].next_slot()
-        staged = []
+        self._wait_slot_free(name, slot)
         for st, fr in zip(streams, frames):
             if st.host is None:
                 self._resolve_format(st, fr.image)
-            self._stage(st, slot, np.asarray(fr.image))
+        jobs = [self._pool.submit(self._stage_host, st, slot, np.asarray(fr.image)) for st, fr in zip(streams, frames)]
+        staged = []
+        for st, fr, job in zip(streams, frames, jobs):
+            job.result()  # the upload of stream i runs while the pool still copies stream i + 1
+            self._stage_upload(st, slot)
             view = st.host[slot].numpy() if st.host.dtype != torch.uint16 else st.host[slot].view(torch.int16).numpy().view(np.uint16)
             staged.append(CameraFrame(view, fr.timestamp, fr.sequence_num, fr.camera_name))
         ev = None
         if not self._emulated:
             ev = torch.cuda.Event()
             ev.record(self._copy_stream)
-        return _SlotFrameSet(timestamp=staged[0].timestamp, frames=staged, source_name=name, slot=slot, uploaded=ev)
+        return _SlotFrameSet(timestamp=staged[0].timestamp, frames=staged, source_name=name, slot=slot, uploaded=ev, gen=streams[0].gen[slot])
 
     # -- the ingest stage itself ------------------------------------------------------
     def _finish(self, sync: SynchronizedFrameSet) -> SynchronizedFrameSet:
-        specs: list[StreamSpec] = []
-        outputs: dict[str, list[tuple[_Stream, int]]] = {}
-        if not self._emulated:
-            cur = torch.cuda.current_stream(self._device)
-            self._ctx.set_stream(cur.cuda_stream)
+        todo: list[tuple[str, Any]] = []
         for name, fs in sync.frame_sets.items():
-            slot = getattr(fs, "slot", -1)
-            if slot < 0:
+            if getattr(fs, "slot", -1) < 0:
                 return sync  # not one of ours (e.g. injected by a test): pass through untouched
-            if fs.uploaded is not None:
-                torch.cuda.current_stream(self._device).wait_event(fs.uploaded)
-            for st in self._streams[name]:
-                specs.append(StreamSpec(st.kind, st.dev[slot:slot + 1], st.out[slot:slot + 1], st.src_format, st.dst_format,
-                                        camera=st.camera, width=st.src_size[0], height=st.src_size[1]))
-                outputs.setdefault(name, []).append((st, slot))
-        self._ctx.ingest(specs)
-        ready = None
-        if not self._emulated:
-            ready = torch.cuda.Event()
-            ready.record(torch.cuda.current_stream(self._device))
+            if fs.result is None:  # nothing is popped from the queues: a frame set can be matched twice, it is ingested once
+                todo.append((name, fs))
+        if todo:
+            key = tuple((name, fs.slot) for name, fs in todo)
+            prep = self._prepared.get(key)
+            if prep is None:
+                specs = [StreamSpec(st.kind, st.dev[fs.slot:fs.slot + 1], st.out[fs.slot:fs.slot + 1], st.src_format, st.dst_format,
+                                    camera=st.camera, width=st.src_size[0], height=st.src_size[1])
+                         for name, fs in todo for st in self._streams[name]]
+                prep = self._prepared[key] = self._ctx.prepare(specs)
+            ready = mirror = None
+            if not self._emulated:
+                cur = torch.cuda.current_stream(self._device)
+                self._ctx.set_stream(cur.cuda_stream)
+                for _, fs in todo:
+                    if fs.uploaded is not None:
+                        cur.wait_event(fs.uploaded)
+            self._ctx.ingest_prepared(prep)
+            if not self._emulated:
+                ready = torch.cuda.Event()
+                ready.record(cur)
+                self._down_stream.wait_event(ready)
+                with torch.cuda.stream(self._down_stream):  # outputs -> pinned mirrors, under whatever the caller does next
+                    for name, fs in todo:
+                        for st in self._streams[name]:
+                            st.out_host[fs.slot].copy_(st.out[fs.slot], non_blocking=True)
+                mirror = torch.cuda.Event()
+                mirror.record(self._down_stream)
+            else:
+                for name, fs in todo:
+                    for st in self._streams[name]:
+                        st.out_host[fs.slot].copy_(st.out[fs.slot])
+            for name, fs in todo:
+                fs.result = (ready, mirror)
+                self._slot_ingested[(name, fs.slot)] = (ready, mirror)
         out_sets: dict[str, FrameSet] = {}
         for name, fs in sync.frame_sets.items():
-            frames = [CameraFrame(DeviceImage(st.out[slot], ready), fr.timestamp, fr.sequence_num, fr.camera_name)
-                      for (st, slot), fr in zip(outputs[name], fs.frames)]
+            ready, mirror = fs.result
+            frames = []
+            for st, fr in zip(self._streams[name], fs.frames):
+                guard = (lambda st=st, slot=fs.slot, gen=fs.gen: st.gen[slot] == gen)
+                frames.append(CameraFrame(DeviceImage(st.out[fs.slot], ready, st.out_host[fs.slot], mirror, guard), fr.timestamp, fr.sequence_num, fr.camera_name))
             out_sets[name] = FrameSet(fs.timestamp, frames, fs.source_name, fs.sensor_data, fs.sensor_timestamp)
         return SynchronizedFrameSet(sync.timestamp, out_sets, sync.max_time_delta, rotate_imu_sample(sync.sensor_data, self._imu_frame),
                                     sync.sensor_timestamp)
+
+    # -- calibration of the RETURNED pixels ----------------------------------------------------------
+    def rectification(self, source_name: str) -> list[dict] | None:
+        """Per stream of ``source_name``: ``{"R": 3x3, "P": 3x4}`` of the stereo rectification the returned pixels went through
+        (``cv2.stereoRectify`` with ``CALIB_ZERO_DISPARITY``, ``alpha=0``), or ``None`` with ``rectify=False``."""
+        return self._rect.get(source_name) if self._rectify else None
+
+    def rectified_intrinsics(self, source_name: str) -> list[Intrinsics]:
+        """``Intrinsics`` that describe what ``get_synchronized_frames()`` returns: ``K = P[:3,:3]`` and no distortion when the rig
+        rectifies (``CameraInfo`` with ``D = 0``, ``R``, ``P`` and ``rectified_images:=true`` - the rectified counterpart of
+        ``isaac_ros.py:364-411``), the raw intrinsics otherwise."""
+        raw = self._calibration.intrinsics[source_name]
+        if not self._rectify:
+            return list(raw)
+        return [Intrinsics(width=it.width, height=it.height, matrix=np.array(rp["P"])[:3, :3].copy(), coeffs=np.zeros(5))
+                for it, rp in zip(raw, self._rect[source_name])]
 
     # -- RGB-D (bypasses the synchroniser in the reference too: run_pipeline.py:624-631) --------
     def get_rgbd(self, source_name: str, blocking: bool = False) -> dict | None:
@@ -277,6 +360,7 @@ class IngestRig(CameraRig):
         rgb_f, dep_f = pair
         rgb, dep = self._rgbd[source_name]
         slot = int(rgb_f.sequence_num) % 2
+        self._wait_slot_free(source_name + "/rgbd", slot)
         self._stage(rgb, slot, np.asarray(rgb_f.image))
         self._stage(dep, slot, np.asarray(dep_f.image))
         if not self._emulated:
@@ -296,6 +380,7 @@ class IngestRig(CameraRig):
         if not self._emulated:
             ready = torch.cuda.Event()
             ready.record(torch.cuda.current_stream(self._device))
+            self._slot_ingested[(source_name + "/rgbd", slot)] = (ready, ready)
         return {
             "rgb": CameraFrame(DeviceImage(rgb.out[slot], ready), rgb_f.timestamp, rgb_f.sequence_num, rgb_f.camera_name),
             "depth": dep_f,
@@ -323,5 +408,6 @@ class IngestRig(CameraRig):
 
     def stop(self) -> None:
         super().stop()
+        self._slot_ingested.clear()
         if not self._emulated:
             torch.cuda.synchronize(self._device)
