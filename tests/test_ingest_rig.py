@@ -142,3 +142,72 @@ def oracle_maps_size(src, w, h):
     (il, ir), (el, er) = src.get_intrinsics(), src.get_extrinsics()
     r1, r2, p1, p2 = orc.stereo_rectify_cv(il.matrix, il.coeffs, ir.matrix, ir.coeffs, (w, h), el.to_4x4_matrix(), er.to_4x4_matrix())
     return [orc.undistort_rectify_map_cv(il.matrix, il.coeffs, r1, p1, (w, h)), orc.undistort_rectify_map_cv(ir.matrix, ir.coeffs, r2, p2, (w, h))]
+
+
+def _lifetime_case(ctx) -> None:
+    """Slot discipline of the pinned ring: frames stay valid for ``queue_size`` polls, a re-used slot is refused, copies live
+    for ever, a frame set matched twice is ingested once, and the rig hands out the calibration of the pixels it returns."""
+    src = SyntheticCameraSource(SyntheticCameraConfig(name="oak0", resolution=(W, H), pixel_format="mono8", seed=31, pool=3))
+    maps = oracle_maps(src)
+    q = 3
+    rig = IngestRig([SyntheticCameraSource(SyntheticCameraConfig(name="oak0", resolution=(W, H), pixel_format="mono8", seed=31, pool=3))],
+                    queue_size=q, context=ctx)
+    with rig:
+        first = rig.get_synchronized_frames()
+        img0 = first.frame_sets["oak0"].frames[0].image
+        kept = np.array(img0)          # a copy: unlimited lifetime
+        view = np.asarray(img0)        # a view of the slot's pinned mirror
+        assert np.array_equal(view, orc.remap_cv(src._pool[0][0], *maps[0]))
+        launches0 = ctx.launch_count
+        for _ in range(q - 1):         # the slot is still the queue's: the view stays what it was
+            rig.get_synchronized_frames()
+            assert np.array_equal(np.asarray(img0), kept)
+        assert ctx.launch_count - launches0 == q - 1, "one ingest launch per NEW frame set"
+        rig.get_synchronized_frames()  # poll number queue_size: the first slot is staged again
+        with pytest.raises(RuntimeError, match="re-used"):
+            np.asarray(img0)
+        late = first.frame_sets["oak0"].frames[1].image  # never touched before the slot went: refused as well
+        with pytest.raises(RuntimeError, match="re-used"):
+            np.asarray(late)
+        assert np.array_equal(kept, orc.remap_cv(src._pool[0][0], *maps[0]))
+        # calibration of the returned (rectified) pixels vs the raw cameras
+        raw, rect = rig.calibration.intrinsics["oak0"], rig.rectified_intrinsics("oak0")
+        (il, ir), (el, er) = src.get_intrinsics(), src.get_extrinsics()
+        r1, r2, p1, p2 = orc.stereo_rectify_cv(il.matrix, il.coeffs, ir.matrix, ir.coeffs, (W, H), el.to_4x4_matrix(), er.to_4x4_matrix())
+        assert np.array_equal(raw[0].matrix, il.matrix) and np.any(raw[0].coeffs != 0)
+        assert np.allclose(rect[0].matrix, p1[:3, :3]) and np.allclose(rect[1].matrix, p2[:3, :3]) and not np.any(rect[0].coeffs)
+        rp = rig.rectification("oak0")
+        assert np.allclose(rp[0]["R"], r1) and np.allclose(rp[1]["P"], p2)
+    plain = IngestRig([SyntheticCameraSource(SyntheticCameraConfig(name="oak0", resolution=(W, H), pixel_format="mono8", seed=31, pool=3))],
+                      queue_size=q, context=ctx, rectify=False)
+    assert plain.rectification("oak0") is None and np.array_equal(plain.rectified_intrinsics("oak0")[0].matrix, il.matrix)
+
+
+def test_ring_slot_lifetime_emulated(emu_backend):
+    _lifetime_case(emu_backend.ctx)
+
+
+@pytest.mark.gpu
+def test_ring_slot_lifetime_gpu(gpu_backend):
+    _lifetime_case(gpu_backend.ctx)
+
+
+@pytest.mark.gpu
+def test_config1_through_rig_gpu_full_size(gpu_backend):
+    """BASELINE config 1 at its own size on the GPU: one OAK-D, 640x400 mono + 640x400 depth through the rig."""
+    src = SyntheticCameraSource(SyntheticCameraConfig(name="oak0", resolution=(640, 400), enable_rgbd=True, rgb_resolution=(640, 400),
+                                                      depth_resolution=(640, 400), pool=2))
+    rig = IngestRig([src], queue_size=4, context=gpu_backend.ctx)
+    maps = oracle_maps_size(src, 640, 400)
+    with rig:
+        for step in range(5):
+            sync = rig.get_synchronized_frames(with_clouds=True)
+            for cam in range(2):
+                got = np.asarray(sync.frame_sets["oak0"].frames[cam].image)
+                assert np.array_equal(got, orc.remap_cv(src._pool[step % 2][cam], *maps[cam])), (step, cam)
+            c = sync.clouds["oak0"]
+            _ri, di = src.get_rgbd_intrinsics()
+            m = conv.body_T_camera(np.eye(4), src.get_rgbd_extrinsics()[1].to_4x4_matrix(), "rdf")
+            pts, mask, cnt = ob.backproject(np.asarray(c["depth"].image), di.matrix, m)
+            assert ob.points_close(np.asarray(c["points"]), pts)[0] and int(c["count"]) == cnt
+            assert np.array_equal(np.asarray(c["mask"]), mask)

@@ -161,6 +161,14 @@ struct CameraSlot {
     double proj_au[3], proj_av[3], proj_ac[3], proj_t[3];
 };
 
+// remembered TMA descriptors (ti_tma.cu): key = everything cuTensorMapEncodeTiled is given
+struct TmaKey {
+    const void* base;
+    uint64_t pitch_y, pitch_z;
+    int elem_bytes, w, h, n, box_x, box_y;
+};
+struct TmaBlob { unsigned char bytes[128]; };
+
 }  // namespace ti
 
 struct ti_ctx {
@@ -195,6 +203,7 @@ struct ti_ctx {
     uint64_t host_chunks = 0;    // chunks enqueued so far; chunk g uses slot g % 3
     uint64_t host_tickets = 0;   // submissions so far (ti_ingest_host_submit); ticket t completes at ticket_done[t % 8]
     cudaEvent_t ticket_done[8] = {};
+    std::vector<std::pair<ti::TmaKey, ti::TmaBlob>> tma_cache;
     // voxel down-sampling (ti_voxel.cu)
     double voxel_size = 0.0;
     uint32_t voxel_max_depth = 65535;

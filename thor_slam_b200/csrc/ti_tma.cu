@@ -2,6 +2,10 @@
 // (cuTensorMapEncodeTiled is fetched with cudaGetDriverEntryPoint, so libcuda is not linked).
 #include "ti_tma.cuh"
 
+#include <string.h>
+
+#include <utility>
+
 namespace ti {
 
 #ifdef TI_EMULATE
@@ -36,6 +40,21 @@ static EncodeTiledFn encoder() {
 
 int tma_encode_3d(ti_ctx* ctx, TiTensorMap* out, const void* base, int elem_bytes, int w, int h, int n, uint64_t pitch_y,
                   uint64_t pitch_z, int box_x, int box_y) {
+    // A live rig replays the same few (ring slot, batch) combinations for ever: descriptors are remembered per context
+    // (an encode costs ~1.5 us of driver time, eight of them were a third of a one-frame-set call).
+    static_assert(sizeof(TiTensorMap) == sizeof(TmaBlob), "a tensor map is 128 bytes");
+    TmaKey key;
+    memset(&key, 0, sizeof key);  // padding bytes take part in the comparison
+    key.base = base; key.pitch_y = pitch_y; key.pitch_z = pitch_z; key.elem_bytes = elem_bytes; key.w = w; key.h = h; key.n = n; key.box_x = box_x; key.box_y = box_y;
+    if (ctx) {
+        auto& cache = ctx->tma_cache;
+        for (auto it = cache.begin(); it != cache.end(); ++it)
+            if (memcmp(&it->first, &key, sizeof key) == 0) {
+                memcpy(out, &it->second, sizeof(TiTensorMap));
+                if (it != cache.begin()) std::iter_swap(it, it - 1);  // drift towards the front: hot entries are found first
+                return TI_OK;
+            }
+    }
     EncodeTiledFn fn = encoder();
     if (!fn) return fail(ctx, TI_ECUDA, "cuTensorMapEncodeTiled is not available from this driver");
     if ((elem_bytes != 1 && elem_bytes != 4) || ((uintptr_t)base % 16) || (pitch_y % 16) || (pitch_z % 16) ||
@@ -49,6 +68,12 @@ int tma_encode_3d(ti_ctx* ctx, TiTensorMap* out, const void* base, int elem_byte
                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(ctx, TI_ECUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+    if (ctx) {
+        if (ctx->tma_cache.size() >= 512) ctx->tma_cache.erase(ctx->tma_cache.begin() + 256, ctx->tma_cache.end());  // cold half
+        TmaBlob blob;
+        memcpy(&blob, out, sizeof blob);
+        ctx->tma_cache.emplace_back(key, blob);
+    }
     return TI_OK;
 }
 #endif
