@@ -88,6 +88,8 @@ def main() -> None:
         ctx.set_option(ctx.OPT_MONO_VARIANT, 4)
         ctx.set_option(ctx.OPT_TMA_TILE_H, 32)
         if args.one:
+            prep = ctx.prepare(specs)  # what the live rig does: the stream array packed once, one foreign call per frame set
+            report("  same, prepared stream array (ingest_prepared)", timeit(lambda: ctx.ingest_prepared(prep), args.iters), 2 * px, px)
             ctx.close()
             return
         for dbg, what in ((1, "loads only (no blend)"), (2, "blend only (no loads)"), (3, "pipeline only"), (8, "half the window loads (wrong pixels)")):
