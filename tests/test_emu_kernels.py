@@ -43,6 +43,21 @@ def test_rectify_overflowing_exception_lists(emu_backend):
     cases.check_rectify(emu_backend, 9, mx, my, "mono8", "mono8", 272, 112, n=2, expect_variant=4, expect_overflow=True)
 
 
+@pytest.mark.parametrize("s,d", [("bgr8", "mono8"), ("nv12", "rgb8")])
+def test_rectify_two_pass_in_chunks(emu_backend, s, d):
+    """The two-pass conversions cut the batch into chunks whose scratch stays in the L2: a 1 KB budget makes every frame its
+    own chunk (5 frames -> 5 convert + 5 remap launches), the bytes must not care."""
+    _, maps = cases.stereo_maps(192, 96)
+    ctx = emu_backend.ctx
+    ctx.set_option(ctx.OPT_L2_SCRATCH_KB, 1)
+    try:
+        launches0 = ctx.launch_count
+        cases.check_rectify(emu_backend, 0, *maps[0], s, d, 192, 96, n=5, expect_variant=4)
+        assert ctx.launch_count - launches0 >= 10
+    finally:
+        ctx.set_option(ctx.OPT_L2_SCRATCH_KB, 0)
+
+
 def test_rectify_resize_and_ragged(emu_backend):
     yy, xx = np.mgrid[0:51, 0:99].astype(np.float32)
     cases.check_rectify(emu_backend, 2, xx * 1.1 + 0.3, yy * 1.05 + 0.7, "mono8", "mono8", 110, 60)  # direct kernel

@@ -191,6 +191,7 @@ struct ti_ctx {
     // scratch for two-pass paths (BGR -> gray ahead of the mono remap); grown on demand, never visible to the caller
     void* scratch = nullptr;
     size_t scratch_cap = 0;
+    int l2_scratch_kb = 40 * 1024;  // two-pass rectify: scratch per chunk of the batch (kept inside the L2)
     // host pipeline (ti_ingest_host)
     cudaStream_t s_h2d = nullptr, s_d2h = nullptr, s_exec = nullptr;
     struct HostSlot {

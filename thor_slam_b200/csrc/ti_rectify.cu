@@ -666,60 +666,97 @@ static int launch_tiled(ti_ctx* ctx, RectParams& P, size_t smem_bytes) {
 // cv2.remap(cvtColor(BGR2GRAY)) by construction.  NV12 -> RGB8 rectified: the exact NV12 -> BGR conversion into
 // scratch, then the 3-channel window remap (which swaps to RGB) - remap is per channel, so this equals
 // cv2.remap(cvtColor(YUV2RGB_NV12)).  Both are several times faster than converting every tap inside the generic kernel.
-static int convert_prepass(ti_ctx* ctx, std::vector<RectifyJob>& jobs, int n_batch) {
-    std::vector<ConvertJob> conv;
-    std::vector<size_t> offs;
-    size_t need = 0;
-    const int th4 = p4_th_index(ctx->tma_tile_h), thk = m3_th_index(ctx->tma_tile_h);
-    for (auto& J : jobs) {
-        if (ctx->force_generic_rectify || J.camera < 0 || J.camera >= TI_MAX_CAMERAS) continue;
-        CameraSlot& C = ctx->cams[J.camera];
-        if (!C.has_map || C.src_w % 16 != 0 || !J.src || ((uintptr_t)J.src % 16) || (J.src_stride % 16)) continue;
-        int mid_fmt = -1;
-        if (J.src_fmt == TI_FMT_BGR8 && J.dst_fmt == TI_FMT_MONO8 && ctx->mono_variant >= 3 && (C.has_pair[th4] || C.has_tma_mono[thk])) {
-            mid_fmt = TI_FMT_MONO8;
-        } else if (J.src_fmt == TI_FMT_NV12 && J.dst_fmt == TI_FMT_RGB8 && ctx->mono_variant == 4 && !((C.src_w | C.src_h) & 1)) {
-            if (!C.c3_tried) {
-                const int rc = build_c3_tables(ctx, C);
-                if (rc != TI_OK) return rc;
-            }
-            if (C.has_c3) mid_fmt = TI_FMT_BGR8;
+//
+// The intermediate frames never need to reach DRAM: the batch is cut into chunks whose scratch fits the L2 (126 MB, of which
+// 40 MB are budgeted by default, TI_OPT_L2_SCRATCH_KB), every chunk is converted and remapped before the next one overwrites the same scratch
+// lines, so the second pass reads what the first just wrote from L2 and DRAM sees the algorithmic bytes only (source once,
+// result once).  mid_fmt_of() says which jobs take this route; `two_pass` holds them with their scratch offsets.
+
+struct TwoPassJob {
+    RectifyJob job;     // as given by the caller
+    int mid_fmt;
+    size_t mid_frame;   // bytes of one intermediate frame (multiple of 16)
+};
+
+static int mid_fmt_of(ti_ctx* ctx, const RectifyJob& J, int th4, int thk, int* mid) {
+    *mid = -1;
+    if (ctx->force_generic_rectify || J.camera < 0 || J.camera >= TI_MAX_CAMERAS) return TI_OK;
+    CameraSlot& C = ctx->cams[J.camera];
+    if (!C.has_map || C.src_w % 16 != 0 || !J.src || ((uintptr_t)J.src % 16) || (J.src_stride % 16)) return TI_OK;
+    if (J.src_fmt == TI_FMT_BGR8 && J.dst_fmt == TI_FMT_MONO8 && ctx->mono_variant >= 3 && (C.has_pair[th4] || C.has_tma_mono[thk])) {
+        *mid = TI_FMT_MONO8;
+    } else if (J.src_fmt == TI_FMT_NV12 && J.dst_fmt == TI_FMT_RGB8 && ctx->mono_variant == 4 && !((C.src_w | C.src_h) & 1)) {
+        if (!C.c3_tried) {
+            const int rc = build_c3_tables(ctx, C);
+            if (rc != TI_OK) return rc;
         }
-        if (mid_fmt < 0) continue;
-        const size_t frame = (size_t)frame_bytes(mid_fmt, C.src_w, C.src_h);  // multiple of 16 (src_w is)
-        conv.push_back(ConvertJob{J.src, nullptr, J.src_stride, (uint64_t)frame, C.src_w, C.src_h, J.src_fmt, mid_fmt});
-        offs.push_back(need);
-        need += frame * (size_t)n_batch;
-        J.src = nullptr;  // patched below once the scratch base is known
-        J.src_stride = frame;
-        J.src_fmt = mid_fmt;
+        if (C.has_c3) *mid = TI_FMT_BGR8;
     }
-    if (conv.empty()) return TI_OK;
+    return TI_OK;
+}
+
+static int launch_rectify_direct(ti_ctx* ctx, const RectifyJob* jobs_in, int n_jobs, int n_batch);
+
+int launch_rectify(ti_ctx* ctx, const RectifyJob* jobs_in, int n_jobs, int n_batch) {
+    if (n_jobs <= 0 || n_batch <= 0) return TI_OK;
+    for (int i = 0; i < n_jobs; ++i)
+        if (!jobs_in[i].src || !jobs_in[i].dst) return fail(ctx, TI_EINVAL, "rectify: null src/dst pointer");
+    const int th4 = p4_th_index(ctx->tma_tile_h), thk = m3_th_index(ctx->tma_tile_h);
+    std::vector<RectifyJob> single;
+    std::vector<TwoPassJob> two_pass;
+    size_t mid_per_frame_set = 0;
+    for (int i = 0; i < n_jobs; ++i) {
+        int mid = -1;
+        const int rc = mid_fmt_of(ctx, jobs_in[i], th4, thk, &mid);
+        if (rc != TI_OK) return rc;
+        if (mid < 0) { single.push_back(jobs_in[i]); continue; }
+        const CameraSlot& C = ctx->cams[jobs_in[i].camera];
+        const size_t frame = (size_t)frame_bytes(mid, C.src_w, C.src_h);  // multiple of 16 (src_w is)
+        two_pass.push_back(TwoPassJob{jobs_in[i], mid, frame});
+        mid_per_frame_set += frame;
+    }
+    if (!single.empty()) {
+        const int rc = launch_rectify_direct(ctx, single.data(), (int)single.size(), n_batch);
+        if (rc != TI_OK) return rc;
+    }
+    if (two_pass.empty()) return TI_OK;
+    const int chunk = (int)std::max<size_t>(1, std::min<size_t>((size_t)n_batch, ((size_t)ctx->l2_scratch_kb << 10) / mid_per_frame_set));
+    const size_t need = mid_per_frame_set * (size_t)chunk;
     if (need > ctx->scratch_cap) {
         if (ctx->scratch) cudaFree(ctx->scratch);  // synchronises: earlier launches that read it have finished
         ctx->scratch = nullptr; ctx->scratch_cap = 0;
         TI_CUDA(ctx, cudaMalloc(&ctx->scratch, need));
         ctx->scratch_cap = need;
     }
-    size_t k = 0;
-    for (auto& J : jobs)
-        if (!J.src) {
-            conv[k].dst = static_cast<uint8_t*>(ctx->scratch) + offs[k];
-            J.src = conv[k].dst;
-            ++k;
+    std::vector<ConvertJob> conv(two_pass.size());
+    std::vector<RectifyJob> second(two_pass.size());
+    for (int b0 = 0; b0 < n_batch; b0 += chunk) {
+        const int nb = std::min(chunk, n_batch - b0);
+        size_t off = 0;
+        for (size_t i = 0; i < two_pass.size(); ++i) {
+            const TwoPassJob& T = two_pass[i];
+            const CameraSlot& C = ctx->cams[T.job.camera];
+            uint8_t* mid = static_cast<uint8_t*>(ctx->scratch) + off;
+            off += T.mid_frame * (size_t)chunk;
+            conv[i] = ConvertJob{T.job.src + (uint64_t)b0 * T.job.src_stride, mid, T.job.src_stride, (uint64_t)T.mid_frame, C.src_w, C.src_h,
+                                 T.job.src_fmt, T.mid_fmt};
+            second[i] = RectifyJob{mid, T.job.dst + (uint64_t)b0 * T.job.dst_stride, (uint64_t)T.mid_frame, T.job.dst_stride, T.job.camera,
+                                   T.mid_fmt, T.job.dst_fmt};
         }
-    return launch_convert(ctx, conv.data(), (int)conv.size(), n_batch);
-}
-
-int launch_rectify(ti_ctx* ctx, const RectifyJob* jobs_in, int n_jobs, int n_batch) {
-    if (n_jobs <= 0 || n_batch <= 0) return TI_OK;
-    for (int i = 0; i < n_jobs; ++i)
-        if (!jobs_in[i].src || !jobs_in[i].dst) return fail(ctx, TI_EINVAL, "rectify: null src/dst pointer");
-    std::vector<RectifyJob> jobs(jobs_in, jobs_in + n_jobs);
-    {
-        const int rc = convert_prepass(ctx, jobs, n_batch);
+        for (size_t i = 0; i < conv.size(); i += TI_MAX_STREAMS) {  // launch_convert takes TI_MAX_STREAMS jobs at a time
+            const int rc = launch_convert(ctx, conv.data() + i, (int)std::min<size_t>(TI_MAX_STREAMS, conv.size() - i), nb);
+            if (rc != TI_OK) return rc;
+        }
+        const int rc = launch_rectify_direct(ctx, second.data(), (int)second.size(), nb);
         if (rc != TI_OK) return rc;
     }
+    return TI_OK;
+}
+
+// Everything that is one pass over the source: routes every job to the fastest kernel its slot qualifies for.
+static int launch_rectify_direct(ti_ctx* ctx, const RectifyJob* jobs_in, int n_jobs, int n_batch) {
+    if (n_jobs <= 0 || n_batch <= 0) return TI_OK;
+    std::vector<RectifyJob> jobs(jobs_in, jobs_in + n_jobs);
     RectParams P1{}, P3{};  // tiled launches for 1-channel and 3-channel sources
     Rect2Params P2{};       // fast mono launch (v2: thread-staged)
     Rect3Params PT{};       // fast mono launch (v3: TMA-pipelined)

@@ -363,6 +363,7 @@ class IngestContext:
         self._check(self.lib.ti_inbox_take(self._h, C.c_void_p(inbox), int(inbox_capacity), int(world), self._ptr(dst), cap, self._ptr(status)))
 
     OPT_PUSH_BLOCKS = 9
+    OPT_L2_SCRATCH_KB = 10
 
     def nccl_barrier(self) -> None:
         self._check(self.lib.ti_nccl_barrier(self._h))
