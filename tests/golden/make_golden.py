@@ -414,6 +414,104 @@ def gen_rgbd_publisher() -> None:
     (HERE / "rgbd_publisher.json").write_text(json.dumps(meta, indent=1))
 
 
+class _FakeCalib:
+    """What ``dai.CalibrationHandler`` answers, with the conventions the driver relies on: intrinsics are given at the
+    resolution asked for (DepthAI scales the stored matrix), distortion has 14 coefficients, extrinsics are 4x4 with the
+    translation in CENTIMETRES (``drivers/luxonis.py:675-726``)."""
+
+    def __init__(self, sockets: dict, k_native: dict, native: dict, dist: dict, to_a_cm: dict, imu_to_a_cm: np.ndarray) -> None:
+        self.sockets, self.k_native, self.native, self.dist, self.to_a_cm, self.imu_to_a_cm = sockets, k_native, native, dist, to_a_cm, imu_to_a_cm
+        self.calls: list = []
+
+    def _name(self, sock) -> str:
+        return next(n for n, s in self.sockets.items() if s is sock)
+
+    def getCameraIntrinsics(self, sock, w, h):
+        n = self._name(sock)
+        self.calls.append(("intrinsics", n, int(w), int(h)))
+        k = self.k_native[n].copy()
+        nw, nh = self.native[n]
+        k[0] *= w / nw
+        k[1] *= h / nh
+        return k.tolist()
+
+    def getDistortionCoefficients(self, sock):
+        return self.dist[self._name(sock)].tolist()
+
+    def getCameraExtrinsics(self, src, dst):
+        a, b = self._name(src), self._name(dst)
+        assert b == "CAM_A", "the driver only ever asks for X -> CAM_A"
+        self.calls.append(("extrinsics", a, b))
+        return self.to_a_cm[a].tolist()
+
+    def getImuToCameraExtrinsics(self, sock):
+        assert self._name(sock) == "CAM_A"
+        return self.imu_to_a_cm.tolist()
+
+
+def gen_luxonis_calibration() -> None:
+    """Rows a4 / a5 of SURVEY section 8: the driver's own calibration getters (``drivers/luxonis.py:596-726,974-1091``) run on
+    a fake ``_calib_data`` - sensor-resolution K scaled to the output, centimetres to metres, which socket is the reference."""
+    import depthai as dai  # the MagicMock installed above: sockets are stable attribute objects
+    from thor_slam.camera.drivers import luxonis as lux
+
+    rng = np.random.default_rng(77)
+    sockets = {"CAM_A": dai.CameraBoardSocket.CAM_A, "CAM_B": dai.CameraBoardSocket.CAM_B, "CAM_C": dai.CameraBoardSocket.CAM_C}
+    native = {"CAM_A": (1920, 1200), "CAM_B": (1280, 800), "CAM_C": (1280, 800)}
+    k_native, dist, to_a = {}, {}, {}
+    for n, (w, h) in native.items():
+        f = 0.62 * w * (1 + rng.uniform(-0.01, 0.01))
+        k_native[n] = np.array([[f, 0, w / 2 + rng.uniform(-8, 8)], [0, f * (1 + rng.uniform(-0.002, 0.002)), h / 2 + rng.uniform(-8, 8)], [0, 0, 1.0]])
+        dist[n] = rng.uniform(-0.05, 0.05, size=14)
+    from scipy.spatial.transform import Rotation
+
+    for n, tx in (("CAM_B", -3.75), ("CAM_C", 3.75)):
+        m = np.eye(4)
+        m[:3, :3] = Rotation.from_rotvec(rng.uniform(-0.01, 0.01, 3)).as_matrix()
+        m[:3, 3] = [tx, rng.uniform(-0.05, 0.05), rng.uniform(-0.05, 0.05)]  # centimetres
+        to_a[n] = m
+    imu = np.eye(4)
+    imu[:3, :3] = Rotation.from_rotvec(rng.uniform(-0.2, 0.2, 3)).as_matrix()
+    imu[:3, 3] = [0.7, -1.3, 0.4]  # centimetres
+    calib = _FakeCalib(sockets, k_native, native, dist, to_a, imu)
+
+    def source(stereo: bool, out_res, rgbd) -> "lux.LuxonisCameraSource":
+        s = lux.LuxonisCameraSource.__new__(lux.LuxonisCameraSource)  # no device: the getters only need cfg + _calib_data
+        s.cfg = lux.LuxonisCameraConfig(ip="192.168.2.21", fps=30, stereo=stereo, mono_sensor_resolution=lux.LuxonisResolution(1280, 800),
+                                        output_resolution=lux.LuxonisResolution(*out_res), rgbd_camera_config=rgbd)
+        s._calib_data, s._intrinsics, s._extrinsics = calib, None, None
+        return s
+
+    def intr(i) -> dict:
+        return {"width": i.width, "height": i.height, "matrix": np.asarray(i.matrix).tolist(), "coeffs": np.asarray(i.coeffs).tolist()}
+
+    cases = {}
+    for tag, out_res in (("stereo_native", (1280, 800)), ("stereo_half", (640, 400)), ("stereo_anisotropic", (640, 480))):
+        s = source(True, out_res, None)
+        cases[tag] = {"output_resolution": list(out_res), "intrinsics": [intr(i) for i in s.get_intrinsics()],
+                      "extrinsics": [e.to_4x4_matrix().tolist() for e in s.get_extrinsics()],
+                      "sensor_extrinsics": s.get_sensor_extrinsics().to_4x4_matrix().tolist()}
+    s = source(False, (1280, 800), None)
+    cases["single"] = {"output_resolution": [1280, 800], "intrinsics": [intr(i) for i in s.get_intrinsics()],
+                       "extrinsics": [e.to_4x4_matrix().tolist() for e in s.get_extrinsics()]}
+    for tag, aligned, rgb_out, depth_out in (("rgbd_aligned", True, (1280, 800), (1280, 800)), ("rgbd_not_aligned", False, (1280, 720), (640, 400)),
+                                              ("rgbd_aligned_mismatched", True, (1280, 800), (640, 400))):
+        rgbd = lux.LuxonisRGBDCameraConfig(enable_rgbd=True, rgb_sensor_resolution=lux.LuxonisResolution(1920, 1200),
+                                           rgb_output_resolution=lux.LuxonisResolution(*rgb_out),
+                                           depth_output_resolution=lux.LuxonisResolution(*depth_out), depth_align_to_rgb=aligned)
+        s = source(True, (640, 400), rgbd)
+        ri, di = s.get_rgbd_intrinsics()
+        re, de = s.get_rgbd_extrinsics()
+        cases[tag] = {"depth_align_to_rgb": aligned, "rgb_sensor_resolution": [1920, 1200], "rgb_output_resolution": list(rgb_out),
+                      "depth_output_resolution": list(depth_out), "rgb_intrinsics": intr(ri), "depth_intrinsics": intr(di),
+                      "rgb_extrinsics": re.to_4x4_matrix().tolist(), "depth_extrinsics": de.to_4x4_matrix().tolist()}
+    meta = {"what": "outputs of thor_slam.camera.drivers.luxonis.LuxonisCameraSource calibration getters on a fake CalibrationHandler",
+            "native_resolution": {k: list(v) for k, v in native.items()}, "k_native": {k: v.tolist() for k, v in k_native.items()},
+            "distortion": {k: v.tolist() for k, v in dist.items()}, "to_cam_a_cm": {k: v.tolist() for k, v in to_a.items()},
+            "imu_to_cam_a_cm": imu.tolist(), "mono_sensor_resolution": [1280, 800], "cases": cases}
+    (HERE / "luxonis_calibration.json").write_text(json.dumps(meta, indent=1))
+
+
 def gen_urdf() -> None:
     from scripts import run_slam
     from thor_slam.camera import utils as ref_utils
@@ -519,6 +617,7 @@ if __name__ == "__main__":
     gen_calibration()
     gen_isaac_adapter()
     gen_rgbd_publisher()
+    gen_luxonis_calibration()
     gen_urdf()
     gen_pipeline_config()
     gen_cv_arith()

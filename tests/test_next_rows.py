@@ -256,3 +256,73 @@ def test_ingest_rig_rotates_pro_imu_samples(emu_backend):
         assert a.sensor_data[key][:3] == [y, x, -z]
     with pytest.raises(ValueError):
         IngestRig([make("pro")], imu_source="pro", imu_frame="flu", context=emu_backend.ctx)
+
+
+class _RecordedCalib:
+    """The fake ``CalibrationHandler`` of ``tests/golden/make_golden.py``, rebuilt from what the golden file recorded."""
+
+    def __init__(self, g: dict) -> None:
+        self.g = g
+
+    def getCameraIntrinsics(self, sock, w, h):
+        k = np.array(self.g["k_native"][sock])
+        nw, nh = self.g["native_resolution"][sock]
+        k[0] *= w / nw
+        k[1] *= h / nh
+        return k.tolist()
+
+    def getDistortionCoefficients(self, sock):
+        return self.g["distortion"][sock]
+
+    def getCameraExtrinsics(self, src, dst):
+        assert dst == "CAM_A"
+        return self.g["to_cam_a_cm"][src]
+
+    def getImuToCameraExtrinsics(self, sock):
+        return self.g["imu_to_cam_a_cm"]
+
+
+def test_luxonis_calibration_conventions_match_the_driver():
+    """sensor -> output scaling, cm -> m, CAM_A as the reference, RGB-D intrinsics rules - against the
+    outputs of the reference driver's own getters (``tests/golden/luxonis_calibration.json``)."""
+    import json
+
+    from thor_slam_b200.camera import luxonis_calib as lc
+
+    g = json.loads((GOLDEN / "luxonis_calibration.json").read_text())
+    calib = _RecordedCalib(g)
+    mono = g["mono_sensor_resolution"]
+
+    def same_intr(got, want) -> None:
+        assert (got.width, got.height) == (want["width"], want["height"])
+        assert np.array_equal(got.matrix, np.array(want["matrix"])) and np.array_equal(got.coeffs, np.array(want["coeffs"]))
+
+    for tag in ("stereo_native", "stereo_half", "stereo_anisotropic"):
+        c = g["cases"][tag]
+        for got, want in zip(lc.slam_intrinsics(calib, True, mono, c["output_resolution"]), c["intrinsics"], strict=True):
+            same_intr(got, want)
+        for got, want in zip(lc.slam_extrinsics(calib, True), c["extrinsics"], strict=True):
+            assert np.array_equal(got.to_4x4_matrix(), np.array(want))
+        assert np.array_equal(lc.sensor_extrinsics(calib).to_4x4_matrix(), np.array(c["sensor_extrinsics"]))
+    c = g["cases"]["single"]
+    same_intr(lc.slam_intrinsics(calib, False, mono, c["output_resolution"])[0], c["intrinsics"][0])
+    assert np.array_equal(lc.slam_extrinsics(calib, False)[0].to_4x4_matrix(), np.eye(4)) and c["extrinsics"] == [np.eye(4).tolist()]
+    for tag in ("rgbd_aligned", "rgbd_not_aligned", "rgbd_aligned_mismatched"):
+        c = g["cases"][tag]
+        ri, di = lc.rgbd_intrinsics(calib, c["rgb_sensor_resolution"], c["rgb_output_resolution"], c["depth_output_resolution"], mono, c["depth_align_to_rgb"])
+        same_intr(ri, c["rgb_intrinsics"])
+        same_intr(di, c["depth_intrinsics"])
+        re, de = lc.rgbd_extrinsics(calib)
+        assert np.array_equal(re.to_4x4_matrix(), np.array(c["rgb_extrinsics"])) and np.array_equal(de.to_4x4_matrix(), np.array(c["depth_extrinsics"]))
+    # the conventions themselves, spelled out: 3.75 cm of baseline is 0.0375 m, left is at -x of CAM_A
+    left = lc.slam_extrinsics(calib, True)[0]
+    assert left.translation[0] == g["to_cam_a_cm"]["CAM_B"][0][3] / 100.0 < 0
+    half = lc.slam_intrinsics(calib, True, mono, (640, 400))[0].matrix
+    full = lc.slam_intrinsics(calib, True, mono, (1280, 800))[0].matrix
+    assert np.allclose(half[:2], full[:2] / 2)
+
+    class _NoImu(_RecordedCalib):
+        def getImuToCameraExtrinsics(self, sock):
+            raise RuntimeError("no IMU extrinsics")
+
+    assert np.array_equal(lc.sensor_extrinsics(_NoImu(g)).to_4x4_matrix(), np.eye(4))
