@@ -35,7 +35,8 @@ extern "C" {
 #define TI_ABI_VERSION 1
 #define TI_MAX_CAMERAS 64 /* calibration slots per context                     */
 #define TI_MAX_STREAMS 32 /* streams of one kind per ti_ingest() call          */
-#define TI_MAX_DIM 2046   /* max source width/height addressable by the packed remap LUT */
+#define TI_MAX_DIM 8190   /* max source width/height of a remap slot (the driver's largest sensor mode is 4224 x 3136,
+                             thor_slam/camera/drivers/luxonis.py:36-44) */
 
 typedef struct ti_ctx ti_ctx;
 

@@ -73,6 +73,17 @@ def test_rectify_odd_output_width_on_fast_kernels(emu_backend):
     cases.check_rectify(emu_backend, 7, xx * 0.8 + 1.5, yy * 1.2 + 0.25, "mono8", "mono8", 112, 60)
 
 
+def test_rectify_beyond_2046_pixels(emu_backend):
+    """Source coordinates above the 11-bit limit of round 1's packed LUT (the driver lists 4000 x 3000 and 4224 x 3136 sensor
+    modes, luxonis.py:36-44): a 2560-wide strip, mono and colour."""
+    yy, xx = np.mgrid[0:40, 0:2560].astype(np.float32)
+    mx, my = (xx * 0.998 + 2.3 + 0.01 * yy).astype(np.float32), (yy * 1.02 + 0.4 + 0.0007 * xx).astype(np.float32)
+    cases.check_rectify(emu_backend, 14, mx, my, "mono8", "mono8", 2560, 48, n=1, expect_variant=4)
+    cases.check_rectify(emu_backend, 14, mx, my, "bgr8", "rgb8", 2560, 48, n=1, expect_variant=4)
+    with pytest.raises(ValueError):
+        emu_backend.ctx.upload_rectify_map(14, mx, my, (8200, 48))
+
+
 def test_rectify_all_outside(emu_backend):
     mx = np.full((32, 128), -50.0, np.float32)
     cases.check_rectify(emu_backend, 4, mx, mx.copy(), "mono8", "mono8", 128, 32)

@@ -77,6 +77,14 @@ def test_rectify_full_size_colour(gpu_backend):
     cases.check_rectify(gpu_backend, 10, *maps[0], "nv12", "rgb8", 1920, 1200, n=1)
 
 
+def test_rectify_largest_sensor_mode(gpu_backend):
+    """4224 x 3136, the largest sensor mode the reference's driver lists (luxonis.py:36-44): BGR8 -> RGB8 and mono rectify on
+    the window kernels, bit-exact."""
+    _, maps = cases.stereo_maps(4224, 3136, seed=7)
+    cases.check_rectify(gpu_backend, 13, *maps[0], "bgr8", "rgb8", 4224, 3136, n=1, expect_variant=4)
+    cases.check_rectify(gpu_backend, 13, *maps[1], "mono8", "mono8", 4224, 3136, n=2, expect_variant=4)
+
+
 def test_rectify_resize_ragged_outside(gpu_backend):
     yy, xx = np.mgrid[0:51, 0:99].astype(np.float32)
     cases.check_rectify(gpu_backend, 2, xx * 1.1 + 0.3, yy * 1.05 + 0.7, "mono8", "mono8", 110, 60)

@@ -186,7 +186,7 @@ int ti_upload_rectify_map(ti_ctx* ctx, int camera, int dst_w, int dst_h, int src
 
     const int tiles_x = (dst_w + RT_W - 1) / RT_W, tiles_y = (dst_h + RT_H - 1) / RT_H;
     const int lut_pitch = tiles_x * RT_W, lut_rows = tiles_y * RT_H;
-    std::vector<uint32_t> lut((size_t)lut_pitch * lut_rows, LUT_OUTSIDE);
+    std::vector<lut_t> lut((size_t)lut_pitch * lut_rows, LUT_OUTSIDE);
     std::vector<uint8_t> valid((size_t)dst_w * dst_h, 0);
     std::vector<TileBox> boxes((size_t)tiles_x * tiles_y);
     for (auto& b : boxes) { b.x0 = 32767; b.y0 = 32767; b.x1 = -32768; b.y1 = -32768; }
@@ -198,8 +198,7 @@ int ti_upload_rectify_map(ti_ctx* ctx, int camera, int dst_w, int dst_h, int src
             const int ix = round_half_even(mx * 32.0f), iy = round_half_even(my * 32.0f);
             const int x0 = ix >> 5, y0 = iy >> 5;  // arithmetic shift = floor
             if (x0 < -1 || x0 > src_w - 1 || y0 < -1 || y0 > src_h - 1) continue;  // all four taps outside
-            lut[(size_t)v * lut_pitch + u] = (uint32_t)(x0 + 1) | ((uint32_t)(y0 + 1) << LUT_COORD_BITS) |
-                                             ((uint32_t)(ix & 31) << 22) | ((uint32_t)(iy & 31) << 27);
+            lut[(size_t)v * lut_pitch + u] = lut_pack(x0, y0, (uint32_t)(ix & 31), (uint32_t)(iy & 31));
             valid[(size_t)v * dst_w + u] = (x0 >= 0 && x0 + 1 <= src_w - 1 && y0 >= 0 && y0 + 1 <= src_h - 1) ? 1 : 0;
             TileBox& b = boxes[(size_t)(v / RT_H) * tiles_x + (u / RT_W)];
             b.x0 = std::min<int16_t>(b.x0, (int16_t)x0); b.y0 = std::min<int16_t>(b.y0, (int16_t)y0);
@@ -215,10 +214,10 @@ int ti_upload_rectify_map(ti_ctx* ctx, int camera, int dst_w, int dst_h, int src
         smem1 = std::max(smem1, (size_t)rows * p1);
         smem3 = std::max(smem3, (size_t)rows * p3);
     }
-    TI_CUDA(ctx, cudaMalloc(&C.d_lut, lut.size() * sizeof(uint32_t)));
+    TI_CUDA(ctx, cudaMalloc(&C.d_lut, lut.size() * sizeof(lut_t)));
     TI_CUDA(ctx, cudaMalloc(&C.d_boxes, boxes.size() * sizeof(TileBox)));
     TI_CUDA(ctx, cudaMalloc(&C.d_valid, valid.size()));
-    TI_CUDA(ctx, cudaMemcpy(C.d_lut, lut.data(), lut.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    TI_CUDA(ctx, cudaMemcpy(C.d_lut, lut.data(), lut.size() * sizeof(lut_t), cudaMemcpyHostToDevice));
     TI_CUDA(ctx, cudaMemcpy(C.d_boxes, boxes.data(), boxes.size() * sizeof(TileBox), cudaMemcpyHostToDevice));
     TI_CUDA(ctx, cudaMemcpy(C.d_valid, valid.data(), valid.size(), cudaMemcpyHostToDevice));
     C.dst_w = dst_w; C.dst_h = dst_h; C.src_w = src_w; C.src_h = src_h;
@@ -244,9 +243,9 @@ int ti_upload_rectify_map(ti_ctx* ctx, int camera, int dst_w, int dst_h, int src
                 int bx0 = 1 << 20, by0 = 1 << 20, bx1 = -(1 << 20), by1 = -(1 << 20);
                 for (int v = ty * M2_TH; v < std::min(dst_h, (ty + 1) * M2_TH); ++v)
                     for (int u = tx * M2_TW; u < std::min(dst_w, (tx + 1) * M2_TW); ++u) {
-                        const uint32_t e = lut[(size_t)v * lut_pitch + u];
+                        const lut_t e = lut[(size_t)v * lut_pitch + u];
                         if (e == LUT_OUTSIDE) continue;
-                        const int x0 = (int)(e & LUT_COORD_MASK) - 1, y0 = (int)((e >> LUT_COORD_BITS) & LUT_COORD_MASK) - 1;
+                        const int x0 = lut_x0(e), y0 = lut_y0(e);
                         bx0 = std::min(bx0, x0); by0 = std::min(by0, y0);
                         bx1 = std::max(bx1, x0 + 2); by1 = std::max(by1, y0 + 2);
                     }
@@ -262,10 +261,10 @@ int ti_upload_rectify_map(ti_ctx* ctx, int camera, int dst_w, int dst_h, int src
                 uint32_t* tl = lut2.data() + ((size_t)ty * t2x + tx) * M2_TW * M2_TH;
                 for (int v = ty * M2_TH; v < std::min(dst_h, (ty + 1) * M2_TH); ++v)
                     for (int u = tx * M2_TW; u < std::min(dst_w, (tx + 1) * M2_TW); ++u) {
-                        const uint32_t e = lut[(size_t)v * lut_pitch + u];
+                        const lut_t e = lut[(size_t)v * lut_pitch + u];
                         if (e == LUT_OUTSIDE) continue;
-                        const int x0 = (int)(e & LUT_COORD_MASK) - 1, y0 = (int)((e >> LUT_COORD_BITS) & LUT_COORD_MASK) - 1;
-                        const uint32_t fx = (e >> 22) & 31u, fy = e >> 27;
+                        const int x0 = lut_x0(e), y0 = lut_y0(e);
+                        const uint32_t fx = lut_fx(e), fy = lut_fy(e);
                         const int rel = x0 - c0;
                         const int off = M2_ZERO_BYTES + (y0 - by0) * M2_ROW_BYTES + ((rel & 1) ? M2_COPY_BYTES + rel - 1 : rel);
                         const int lu = u - tx * M2_TW;  // lane (lu % 32) owns pixels lu, lu+32, lu+64, lu+96: stored as its uint4
@@ -294,9 +293,9 @@ int ti_upload_rectify_map(ti_ctx* ctx, int camera, int dst_w, int dst_h, int src
         auto for_tile = [&](int tx, int ty, auto&& fn) {
             for (int v = ty * TH; v < std::min(dst_h, (ty + 1) * TH); ++v)
                 for (int u = tx * M3_TW; u < std::min(dst_w, (tx + 1) * M3_TW); ++u) {
-                    const uint32_t e = lut[(size_t)v * lut_pitch + u];
+                    const lut_t e = lut[(size_t)v * lut_pitch + u];
                     if (e == LUT_OUTSIDE) continue;
-                    fn(u, v, (int)(e & LUT_COORD_MASK) - 1, (int)((e >> LUT_COORD_BITS) & LUT_COORD_MASK) - 1, (e >> 22) & 31u, e >> 27);
+                    fn(u, v, lut_x0(e), lut_y0(e), lut_fx(e), lut_fy(e));
                 }
         };
         for (int ty = 0; ty < t3y && ok; ++ty)

@@ -28,16 +28,25 @@
 namespace ti {
 
 // ---------------------------------------------------------------------------------------------
-// Remap LUT encoding.  One u32 per OUTPUT pixel, row-major:
-//   bits  0..10  x0 + 1   (x0 = floor(mapx) after 1/32-px quantisation; -1 <= x0 <= src_w-1)
-//   bits 11..21  y0 + 1
-//   bits 22..26  fx       (5-bit fractional part, units of 1/32 px)
-//   bits 27..31  fy
-// A pixel none of whose four taps touches the source image is LUT_OUTSIDE (x0+1 == 2047).
+// Remap LUT encoding (the GENERIC table: what the fast tile-relative tables are built from on the host, and what the
+// fall-back kernels read).  One u64 per OUTPUT pixel, row-major:
+//   bits  0..15  x0 + 1   (x0 = floor(mapx) after 1/32-px quantisation; -1 <= x0 <= src_w-1)
+//   bits 16..31  y0 + 1
+//   bits 32..36  fx       (5-bit fractional part, units of 1/32 px)
+//   bits 37..41  fy
+// A pixel none of whose four taps touches the source image is LUT_OUTSIDE.  (Round 1 packed this into 32 bits with 11-bit
+// coordinates, which capped images at 2046 px; the 4000 x 3000 and 4224 x 3136 sensor modes of the reference's driver -
+// thor_slam/camera/drivers/luxonis.py:36-44 - need 13.)
 // ---------------------------------------------------------------------------------------------
-constexpr uint32_t LUT_OUTSIDE = 0xFFFFFFFFu;
-constexpr int LUT_COORD_BITS = 11;
-constexpr uint32_t LUT_COORD_MASK = (1u << LUT_COORD_BITS) - 1u;
+typedef uint64_t lut_t;
+constexpr lut_t LUT_OUTSIDE = ~0ull;
+__host__ __device__ inline lut_t lut_pack(int x0, int y0, uint32_t fx, uint32_t fy) {
+    return (lut_t)(uint32_t)(x0 + 1) | ((lut_t)(uint32_t)(y0 + 1) << 16) | ((lut_t)fx << 32) | ((lut_t)fy << 37);
+}
+__host__ __device__ inline int lut_x0(lut_t e) { return (int)(e & 0xFFFFu) - 1; }
+__host__ __device__ inline int lut_y0(lut_t e) { return (int)((e >> 16) & 0xFFFFu) - 1; }
+__host__ __device__ inline uint32_t lut_fx(lut_t e) { return (uint32_t)(e >> 32) & 31u; }
+__host__ __device__ inline uint32_t lut_fy(lut_t e) { return (uint32_t)(e >> 37) & 31u; }
 
 // Rectify tile: one CTA produces RT_W x RT_H output pixels from a source box staged in smem.
 constexpr int RT_W = 128;
@@ -116,7 +125,7 @@ constexpr int C3_LUT_ROW_WORDS = 256;  // per tile row: 128 pixels x {window wor
 
 struct CameraSlot {
     // rectification
-    std::vector<uint32_t> h_lut;                    // host copy of the generic LUT (lazy builds of further tables)
+    std::vector<lut_t> h_lut;                       // host copy of the generic LUT (lazy builds of further tables)
     int h_lut_pitch = 0;
     bool c3_tried = false, has_c3 = false;          // built on the first BGR8 -> RGB8 rectify of the slot
     uint32_t* d_lut5 = nullptr;                     // tiles * C3_TH * C3_LUT_ROW_WORDS
@@ -144,7 +153,7 @@ struct CameraSlot {
     int rows2_max = 0;
     int dst_w = 0, dst_h = 0, src_w = 0, src_h = 0;
     int tiles_x = 0, tiles_y = 0;
-    uint32_t* d_lut = nullptr;     // dst_h * dst_w
+    lut_t* d_lut = nullptr;        // dst_h * dst_w
     TileBox* d_boxes = nullptr;    // tiles_y * tiles_x
     uint8_t* d_valid = nullptr;    // dst_h * dst_w
     size_t tile_smem[2] = {0, 0};  // largest staged box in bytes for 1- and 3-channel sources
@@ -339,7 +348,7 @@ struct RectifyJob {
 };
 int launch_rectify(ti_ctx* ctx, const RectifyJob* jobs, int n_jobs, int n_batch);
 // pair-window tables of one camera from its generic LUT (ti_rectify_pair.cu); frees / replaces the old ones
-int build_pair_tables(ti_ctx* ctx, CameraSlot& C, const std::vector<uint32_t>& lut, int lut_pitch);
+int build_pair_tables(ti_ctx* ctx, CameraSlot& C, const std::vector<lut_t>& lut, int lut_pitch);
 void free_pair_tables(CameraSlot& C);
 // 3-channel window tables (ti_rectify_c3.cu), built lazily from CameraSlot::h_lut
 int build_c3_tables(ti_ctx* ctx, CameraSlot& C);

@@ -29,7 +29,7 @@ struct RectJobDev {
     const uint8_t* src;
     uint8_t* dst;
     uint64_t src_stride, dst_stride;
-    const uint32_t* lut;  // padded: lut_rows x lut_pitch
+    const lut_t* lut;  // padded: lut_rows x lut_pitch
     const TileBox* boxes;
     int lut_pitch;
     int tiles_x, tiles_y;
@@ -75,9 +75,14 @@ __global__ void __launch_bounds__(RT_THREADS) rectify_tile_kernel(const __grid_c
         const int u = tx * RT_W + lx, v = ty * RT_H + ly;
 
         // (1) LUT entries of this thread's 8 pixels (LUT is padded to whole tiles: no guards)
-        const uint32_t* lp = J.lut + (size_t)v * J.lut_pitch + u;
-        const uint4 l0 = ld_keep_u4(lp), l1 = ld_keep_u4(lp + 4);
-        const uint32_t e[8] = {l0.x, l0.y, l0.z, l0.w, l1.x, l1.y, l1.z, l1.w};
+        const lut_t* lp = J.lut + (size_t)v * J.lut_pitch + u;
+        lut_t e[8];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {  // 64-bit entries: two per 128-bit load
+            const uint4 l = ld_keep_u4(lp + 2 * q);
+            e[2 * q] = (lut_t)l.x | ((lut_t)l.y << 32);
+            e[2 * q + 1] = (lut_t)l.z | ((lut_t)l.w << 32);
+        }
 
         // (2) stage the source box
         const int c0 = (box.x0 * C) & ~15;               // first staged byte column (may be negative)
@@ -108,10 +113,10 @@ __global__ void __launch_bounds__(RT_THREADS) rectify_tile_kernel(const __grid_c
             for (int c = 0; c < C; ++c) o[c][0] = o[c][1] = 0u;
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
-                const uint32_t ek = e[k];
+                const lut_t ek = e[k];
                 if (ek == LUT_OUTSIDE) continue;
-                const int sx = (int)(ek & LUT_COORD_MASK) - 1, sy = (int)((ek >> LUT_COORD_BITS) & LUT_COORD_MASK) - 1;
-                const uint32_t fx = (ek >> 22) & 31u, fy = ek >> 27;
+                const int sx = lut_x0(ek), sy = lut_y0(ek);
+                const uint32_t fx = lut_fx(ek), fy = lut_fy(ek);
                 const uint8_t* s = smem + (sy - box.y0) * pitch + (sx * C - c0);
 #pragma unroll
                 for (int c = 0; c < C; ++c) {
@@ -546,7 +551,7 @@ struct DirectJob {
     const uint8_t* src;
     uint8_t* dst;
     uint64_t src_stride, dst_stride;
-    const uint32_t* lut;
+    const lut_t* lut;
     int lut_pitch;
     int dst_w, dst_h, src_w, src_h;
     int mode;
@@ -580,14 +585,14 @@ __global__ void __launch_bounds__(256) rectify_direct_kernel(DirectJob J, int n_
         const uint64_t b = t / npx;
         const uint32_t p = (uint32_t)(t - b * npx);
         const int v = (int)(p / (uint32_t)J.dst_w), u = (int)(p - (uint32_t)v * J.dst_w);
-        const uint32_t ek = J.lut[(size_t)v * J.lut_pitch + u];
+        const lut_t ek = J.lut[(size_t)v * J.lut_pitch + u];
         uint8_t* dst = J.dst + b * J.dst_stride + (size_t)p * C;
         if (ek == LUT_OUTSIDE) {
             for (int c = 0; c < C; ++c) dst[c] = 0;
             continue;
         }
-        const int sx = (int)(ek & LUT_COORD_MASK) - 1, sy = (int)((ek >> LUT_COORD_BITS) & LUT_COORD_MASK) - 1;
-        const uint32_t fx = (ek >> 22) & 31u, fy = ek >> 27;
+        const int sx = lut_x0(ek), sy = lut_y0(ek);
+        const uint32_t fx = lut_fx(ek), fy = lut_fy(ek);
         const uint8_t* src = J.src + b * J.src_stride;
         uint32_t t00[3], t01[3], t10[3], t11[3];
         fetch<MODE>(J, src, sx, sy, t00);
@@ -606,11 +611,11 @@ __global__ void __launch_bounds__(256) rectify_points_kernel(DirectJob J, const 
         const uint64_t b = t / (uint32_t)n_pts;
         const uint32_t p = pts[t - b * (uint32_t)n_pts];
         const int v = (int)(p / (uint32_t)J.dst_w), u = (int)(p - (uint32_t)v * J.dst_w);
-        const uint32_t ek = J.lut[(size_t)v * J.lut_pitch + u];
+        const lut_t ek = J.lut[(size_t)v * J.lut_pitch + u];
         uint8_t* dst = J.dst + b * J.dst_stride + p;
         if (ek == LUT_OUTSIDE) { *dst = 0; continue; }
-        const int sx = (int)(ek & LUT_COORD_MASK) - 1, sy = (int)((ek >> LUT_COORD_BITS) & LUT_COORD_MASK) - 1;
-        const uint32_t fx = (ek >> 22) & 31u, fy = ek >> 27;
+        const int sx = lut_x0(ek), sy = lut_y0(ek);
+        const uint32_t fx = lut_fx(ek), fy = lut_fy(ek);
         const uint8_t* src = J.src + b * J.src_stride;
         uint32_t t00[3], t01[3], t10[3], t11[3];
         fetch<DM_MONO>(J, src, sx, sy, t00);

@@ -270,7 +270,7 @@ int build_c3_tables(ti_ctx* ctx, CameraSlot& C) {
     const int dst_w = C.dst_w, dst_h = C.dst_h, lut_pitch = C.h_lut_pitch;
     const int tx_n = (dst_w + C3_TW - 1) / C3_TW, ty_n = (dst_h + C3_TH - 1) / C3_TH;
     const size_t n_tiles = (size_t)tx_n * ty_n;
-    auto entry = [&](int u, int v) -> uint32_t { return (u < dst_w && v < dst_h) ? C.h_lut[(size_t)v * lut_pitch + u] : LUT_OUTSIDE; };
+    auto entry = [&](int u, int v) -> lut_t { return (u < dst_w && v < dst_h) ? C.h_lut[(size_t)v * lut_pitch + u] : LUT_OUTSIDE; };
     std::vector<TileBox2> boxes(n_tiles);
     std::vector<uint32_t> lut5(n_tiles * C3_TH * C3_LUT_ROW_WORDS, 0u);
     int rows_max = 0;
@@ -279,9 +279,9 @@ int build_c3_tables(ti_ctx* ctx, CameraSlot& C) {
             int bx0 = 1 << 20, by0 = 1 << 20, bx1 = -(1 << 20), by1 = -(1 << 20);
             for (int v = ty * C3_TH; v < std::min(dst_h, (ty + 1) * C3_TH); ++v)
                 for (int u = tx * C3_TW; u < std::min(dst_w, (tx + 1) * C3_TW); ++u) {
-                    const uint32_t e = entry(u, v);
+                    const lut_t e = entry(u, v);
                     if (e == LUT_OUTSIDE) continue;
-                    const int x0 = (int)(e & LUT_COORD_MASK) - 1, y0 = (int)((e >> LUT_COORD_BITS) & LUT_COORD_MASK) - 1;
+                    const int x0 = lut_x0(e), y0 = lut_y0(e);
                     bx0 = std::min(bx0, x0); by0 = std::min(by0, y0); bx1 = std::max(bx1, x0 + 2); by1 = std::max(by1, y0 + 2);
                 }
             const size_t tile = (size_t)ty * tx_n + tx;
@@ -294,10 +294,10 @@ int build_c3_tables(ti_ctx* ctx, CameraSlot& C) {
             rows_max = std::max(rows_max, by1 - by0);
             for (int row = 0; row < C3_TH; ++row)
                 for (int lu = 0; lu < C3_TW; ++lu) {
-                    const uint32_t e = entry(tx * C3_TW + lu, ty * C3_TH + row);
+                    const lut_t e = entry(tx * C3_TW + lu, ty * C3_TH + row);
                     if (e == LUT_OUTSIDE) continue;  // {0, 0}: zero weights
-                    const int x0 = (int)(e & LUT_COORD_MASK) - 1, y0 = (int)((e >> LUT_COORD_BITS) & LUT_COORD_MASK) - 1;
-                    const uint32_t fx = (e >> 22) & 31u, fy = e >> 27;
+                    const int x0 = lut_x0(e), y0 = lut_y0(e);
+                    const uint32_t fx = lut_fx(e), fy = lut_fy(e);
                     const int bp = 3 * x0 - c0, wordx = bp & ~3, s = bp & 3;
                     const uint32_t off = (uint32_t)((y0 - by0) * C3_PITCH + wordx);
                     // lane (lu % 32) blends pixel lu as its (lu / 32)-th: its eight LUT words are contiguous

@@ -331,12 +331,12 @@ struct Px {  // one output pixel decoded from the generic LUT
     int x0, y0;
     uint32_t fx, fy;
 };
-inline Px decode(uint32_t e) {
+inline Px decode(lut_t e) {
     Px p{};
     p.in = e != LUT_OUTSIDE;
     if (p.in) {
-        p.x0 = (int)(e & LUT_COORD_MASK) - 1; p.y0 = (int)((e >> LUT_COORD_BITS) & LUT_COORD_MASK) - 1;
-        p.fx = (e >> 22) & 31u; p.fy = e >> 27;
+        p.x0 = lut_x0(e); p.y0 = lut_y0(e);
+        p.fx = lut_fx(e); p.fy = lut_fy(e);
     }
     return p;
 }
@@ -351,7 +351,7 @@ inline uint32_t pixel_word(const Px& p) {  // see p4_expand
 }
 }  // namespace
 
-int build_pair_tables(ti_ctx* ctx, CameraSlot& C, const std::vector<uint32_t>& lut, int lut_pitch) {
+int build_pair_tables(ti_ctx* ctx, CameraSlot& C, const std::vector<lut_t>& lut, int lut_pitch) {
     free_pair_tables(C);
     if (C.src_w % 16 != 0) return TI_OK;  // TMA row pitch must be a multiple of 16 bytes
     const int dst_w = C.dst_w, dst_h = C.dst_h;
@@ -360,7 +360,7 @@ int build_pair_tables(ti_ctx* ctx, CameraSlot& C, const std::vector<uint32_t>& l
         const int tx_n = (dst_w + P4_TW - 1) / P4_TW, ty_n = (dst_h + TH - 1) / TH;
         const size_t n_tiles = (size_t)tx_n * ty_n;
         std::vector<TileBox2> boxes(n_tiles);
-        auto entry = [&](int u, int v) -> uint32_t { return (u < dst_w && v < dst_h) ? lut[(size_t)v * lut_pitch + u] : LUT_OUTSIDE; };
+        auto entry = [&](int u, int v) -> lut_t { return (u < dst_w && v < dst_h) ? lut[(size_t)v * lut_pitch + u] : LUT_OUTSIDE; };
         bool ok = true;
         int rows_max = 0;
         for (int ty = 0; ty < ty_n && ok; ++ty)
