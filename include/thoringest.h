@@ -211,6 +211,16 @@ int ti_voxel_cloud(ti_ctx* ctx, const ti_depth_stream* streams, int n_streams, i
  * Converts min(*n_records, max_records) records; xyz: DEVICE f32[max_records * 3]. */
 int ti_voxel_points(ti_ctx* ctx, const uint64_t* records, const uint32_t* n_records, uint64_t max_records, float* xyz);
 
+/* ti_backproject and ti_register_colour in ONE pass over the depth image ("fused into the
+ * back-projection kernel"): xyz + mask + count as ti_backproject, plus colour (u8 HxWx3, depth size) as ti_register_colour
+ * would give it - bit-identical selection - without reading the depth a second time.  rgb: RGB8 of the registered size.
+ * Strides in bytes; rgb / colour strides 0 = tightly packed.  Needs ti_upload_projection and ti_upload_registration of the
+ * same depth size on `camera`. */
+int ti_backproject_colour(ti_ctx* ctx, int camera, const uint16_t* depth, const uint8_t* rgb, float* xyz, uint8_t* mask,
+                          uint32_t* count, uint8_t* colour, int n_batch, uint64_t depth_frame_stride,
+                          uint64_t rgb_frame_stride, uint64_t xyz_frame_stride, uint64_t mask_frame_stride,
+                          uint64_t colour_frame_stride);
+
 /* Whole frame-set batch in at most one launch per kind: every stream x every frame.
  * This is the call behind CameraRig.get_synchronized_frames() (thor_slam/camera/rig.py:358-415)
  * in the drop-in rig.  streams: HOST array, DEVICE image pointers inside. */

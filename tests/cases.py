@@ -157,6 +157,45 @@ def check_backproject(be, cam: int, w: int, h: int, n: int = 2, seed: int = 2, r
         assert not np.any(gx[i][msk == 0]), "invalid pixels must be written as (0,0,0)"
 
 
+def check_backproject_colour(be, cam: int, w: int, h: int, rw: int, rh: int, n: int = 2, seed: int = 6, on_half_pixels: bool = False) -> None:
+    """``ti_backproject_colour``: the cloud / mask / count of ``ti_backproject`` AND the colours of ``ti_register_colour`` from one
+    pass over the depth image.  ``on_half_pixels``: an RGB camera identical to the depth camera but for half a pixel of
+    principal point - every projection lands exactly on x.5, the worst case for the reciprocal fast path's guard band."""
+    rng = np.random.default_rng(seed)
+    s = SyntheticCameraSource(SyntheticCameraConfig(name="oak0", resolution=(w, h), enable_rgbd=True, rgb_resolution=(rw, rh), depth_resolution=(w, h),
+                                                    pool=1, seed=seed))
+    ri, di = s.get_rgbd_intrinsics()
+    re, de = s.get_rgbd_extrinsics()
+    k_rgb, rgb_T_depth = ri.matrix, np.linalg.inv(re.to_4x4_matrix()) @ de.to_4x4_matrix()
+    if on_half_pixels:
+        assert (rw, rh) == (w, h)
+        k_rgb = di.matrix.copy()
+        k_rgb[0, 2] += 0.5
+        k_rgb[1, 2] += 0.5
+        rgb_T_depth = np.eye(4)
+    m = conv.body_T_camera(random_pose(rng), de.to_4x4_matrix(), "rdf")
+    be.ctx.upload_projection(cam, di.matrix, m, (w, h))
+    be.ctx.upload_registration(cam, di.matrix, (w, h), k_rgb, (rw, rh), rgb_T_depth)
+    depth = np.stack([make_depth_scene(rng, w, h) if i % 2 else make_depth(rng, w, h) for i in range(n)])
+    rgb = rng.integers(0, 256, size=(n, rh, rw, 3), dtype=np.uint8)
+    xyz, mask = be.zeros((n, h, w, 3), np.float32), be.zeros((n, h, w), np.uint8)
+    count = be.dev(np.full(n, 0xDEADBEEF, dtype=np.uint32))
+    colour = be.dev(np.full((n, h, w, 3), 0x77, dtype=np.uint8))
+    be.ctx.backproject_colour(cam, be.dev(depth), be.dev(rgb), xyz, colour, mask, count)
+    gx, gm, gc, gcol = be.host(xyz), be.host(mask), be.host(count), be.host(colour)
+    for i in range(n):
+        pts, msk, cnt = ob.backproject(depth[i], di.matrix, m)
+        ok, worst = ob.points_close(gx[i], pts, POINT_RTOL, POINT_FLOOR)
+        assert ok, f"points off by {worst:.3e}"
+        assert np.array_equal(gm[i], msk) and int(gc[i]) == cnt
+        want = ob.register_colour(depth[i], di.matrix, rgb_T_depth, k_rgb, rgb[i])
+        assert np.array_equal(gcol[i], want), f"frame {i}: {(gcol[i] != want).any(axis=-1).sum()} colours differ"
+    # and the stand-alone kernel agrees with the fused one
+    alone = be.dev(np.zeros((n, h, w, 3), np.uint8))
+    be.ctx.register_colour(cam, be.dev(depth), be.dev(rgb), alone)
+    assert np.array_equal(be.host(alone), gcol)
+
+
 def check_voxel(be, cam0: int, sizes: list[tuple[int, int]], n: int = 2, seed: int = 4, voxel: float = 0.05, max_depth_mm: int = 10000,
                 scene: str = "room", set_base: int = 0, tag: int = 0, capacity: int | None = None, depth=None) -> int:
     """``ti_voxel_cloud`` over ``len(sizes)`` cameras x ``n`` frame sets against ``np.unique`` of the oracle's keys: the SET of

@@ -102,6 +102,12 @@ def test_backproject_extremes(emu_backend):
     cases.check_backproject(emu_backend, 6, 64, 16, depth=depth)
 
 
+def test_backproject_with_fused_colour(emu_backend):
+    cases.check_backproject_colour(emu_backend, 7, 64, 40, 96, 54)
+    cases.check_backproject_colour(emu_backend, 7, 64, 40, 64, 40, on_half_pixels=True)
+    cases.check_backproject_colour(emu_backend, 7, 50, 22, 70, 30)  # unaligned width: scalar kernel + stand-alone registration
+
+
 @pytest.mark.parametrize("scene", ["room", "noise"])
 def test_voxel_cloud(emu_backend, scene):
     """Two cameras of different size (vector and scalar load paths, ragged tiles) fused per frame set."""

@@ -246,3 +246,12 @@ def test_voxel_cloud_many_launches_epoch_wrap(gpu_backend):
     """More than 255 launches on one table: the epoch byte wraps and the table is cleared."""
     for i in range(130):  # two launches per check
         cases.check_voxel(gpu_backend, 37, [(64, 32)], n=1, scene="noise", seed=100 + i)
+
+
+def test_backproject_with_fused_colour(gpu_backend):
+    """Fused depth -> xyz + mask + count + colour: the reciprocal fast path with its guard band must select
+    the very pixels the float32 oracle (IEEE divisions) selects - full size, a small ragged size, and the all-on-x.5 worst case."""
+    cases.check_backproject_colour(gpu_backend, 40, 1280, 800, 1920, 1080, n=3)
+    cases.check_backproject_colour(gpu_backend, 41, 64, 40, 96, 54)
+    cases.check_backproject_colour(gpu_backend, 42, 640, 400, 640, 400, on_half_pixels=True)
+    cases.check_backproject_colour(gpu_backend, 43, 50, 22, 70, 30)

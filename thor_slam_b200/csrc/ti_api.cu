@@ -458,6 +458,18 @@ int ti_backproject(ti_ctx* ctx, int camera, const uint16_t* depth, float* xyz, u
     return launch_backproject(ctx, &J, 1, n_batch);
 }
 
+int ti_backproject_colour(ti_ctx* ctx, int camera, const uint16_t* depth, const uint8_t* rgb, float* xyz, uint8_t* mask, uint32_t* count,
+                          uint8_t* colour, int n_batch, uint64_t depth_frame_stride, uint64_t rgb_frame_stride, uint64_t xyz_frame_stride,
+                          uint64_t mask_frame_stride, uint64_t colour_frame_stride) {
+    if (!ctx) return TI_EINVAL;
+    if (n_batch < 0) return fail(ctx, TI_EINVAL, "n_batch must be >= 0");
+    if (n_batch > 0 && (!rgb || !colour)) return fail(ctx, TI_EINVAL, "ti_backproject_colour: null rgb / colour pointer");
+    TI_CUDA(ctx, cudaSetDevice(ctx->device));
+    BackprojectJob J{depth, xyz, mask, count, depth_frame_stride, xyz_frame_stride, mask_frame_stride, camera};
+    J.rgb = rgb; J.colour = colour; J.rgb_stride = rgb_frame_stride; J.colour_stride = colour_frame_stride;
+    return launch_backproject(ctx, &J, 1, n_batch);
+}
+
 static int split_streams(ti_ctx* ctx, const ti_stream* streams, int n_streams, std::vector<ConvertJob>& cv,
                          std::vector<RectifyJob>& rc, std::vector<BackprojectJob>& bp) {
     if (n_streams < 0 || (n_streams > 0 && !streams)) return fail(ctx, TI_EINVAL, "ti_ingest: bad stream array");

@@ -31,6 +31,14 @@ struct BpCam {
     int width, height;
 };
 
+// depth -> RGB registration constants of a job (ti_register.cu has the stand-alone kernel and the arithmetic's rationale)
+struct BpReg {
+    float a[9], t[3];
+    float cx, cy, rfx, rfy, rcx, rcy;
+    float guard;  // half-width of the band around x.5 inside which the reciprocal fast path hands over to the IEEE division
+    int rw, rh;
+};
+
 struct BpJobDev {
     const uint16_t* depth;
     float* xyz;
@@ -39,6 +47,11 @@ struct BpJobDev {
     uint64_t depth_stride, xyz_stride, mask_stride;
     BpCam cam;
     uint32_t tile_begin;  // prefix of tiles per frame set
+    // fused colour lookup (backproject_vec_kernel<true> only)
+    const uint8_t* rgb;
+    uint8_t* colour;
+    uint64_t rgb_stride, colour_stride;
+    BpReg reg;
 };
 
 struct BpParams {
@@ -61,6 +74,44 @@ __device__ __forceinline__ void project(const BpCam& c, double bx, double by, do
     z = ok ? (float)fma(dd, fma(c.au[2], ud, bz), c.t[2]) : 0.f;
 }
 
+// The colour of one depth pixel: the selection of register_pixel (ti_register.cu) - same float32 operations, each rounded
+// on its own, so the float32 oracle picks the same RGB pixel - with the two IEEE divisions taken off the common path:
+// q' = p.x * rcp(p.z) is within 2.4e-7 relative of fl(p.x / p.z), so u' = q' * fx + cx is within `guard` (a few 1e-3 px,
+// bound derived in DESIGN.md) of the reference value; rint() of the two can only differ when u' lies within `guard` of a
+// half-integer, and exactly those pixels (well under 1 %) are redone with the division.
+__device__ __forceinline__ uint32_t bp_colour(const BpReg& R, const uint8_t* rgb, int u, int v, uint32_t d) {
+    const float fu = __fsub_rn((float)u, R.cx), fv = __fsub_rn((float)v, R.cy);
+    const float z = __fmul_rn((float)d, 0.001f);
+    float p[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        const float r = __fadd_rn(__fadd_rn(__fmul_rn(R.a[3 * i], fu), __fmul_rn(R.a[3 * i + 1], fv)), R.a[3 * i + 2]);
+        p[i] = __fadd_rn(__fmul_rn(r, z), R.t[i]);
+    }
+    if (d == 0 || !(p[2] > 0.f)) return 0u;
+#ifdef TI_EMULATE
+    const float inv = 1.0f / p[2];
+#else
+    float inv;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv) : "f"(p[2]));
+#endif
+    float ur = __fadd_rn(__fmul_rn(__fmul_rn(p[0], inv), R.rfx), R.rcx);
+    float vr = __fadd_rn(__fmul_rn(__fmul_rn(p[1], inv), R.rfy), R.rcy);
+    // far outside: rejected on either path (the relative error of the fast path cannot bring such a value back inside)
+    if (!(ur > -2.f && ur < (float)R.rw + 1.f && vr > -2.f && vr < (float)R.rh + 1.f)) return 0u;
+    const float du = fabsf(__fsub_rn(__fsub_rn(ur, floorf(ur)), 0.5f)), dv = fabsf(__fsub_rn(__fsub_rn(vr, floorf(vr)), 0.5f));
+    if (du < R.guard || dv < R.guard) {  // too close to a rounding boundary to trust the reciprocal: the reference's own operations
+        ur = __fadd_rn(__fmul_rn(__fdiv_rn(p[0], p[2]), R.rfx), R.rcx);
+        vr = __fadd_rn(__fmul_rn(__fdiv_rn(p[1], p[2]), R.rfy), R.rcy);
+    }
+    if (!(ur > -1.f && ur < (float)R.rw && vr > -1.f && vr < (float)R.rh)) return 0u;
+    const int iu = __float2int_rn(ur), iv = __float2int_rn(vr);
+    if (iu < 0 || iu >= R.rw || iv < 0 || iv >= R.rh) return 0u;
+    const uint8_t* s = rgb + ((size_t)iv * R.rw + iu) * 3;
+    return (uint32_t)__ldg(s) | ((uint32_t)__ldg(s + 1) << 8) | ((uint32_t)__ldg(s + 2) << 16);
+}
+
+template <bool COLOUR>
 __global__ void __launch_bounds__(BP_THREADS) backproject_vec_kernel(const __grid_constant__ BpParams P) {
     __shared__ float4 xbuf[BP_THREADS / 32][32 * BP_LANE_STRIDE];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -125,6 +176,16 @@ __global__ void __launch_bounds__(BP_THREADS) backproject_vec_kernel(const __gri
                 if (k < 4) m0 |= ok << (8 * k); else m1 |= ok << (8 * (k - 4));
             }
             if (J.mask) st_stream_u2(J.mask + (uint64_t)cur.b * J.mask_stride + p0, make_uint2(m0, m1));
+            if (COLOUR) {  // 8 pixels x RGB = 24 bytes = three 64-bit stores (p0 is a multiple of 8)
+                const uint8_t* rgb = J.rgb + (uint64_t)cur.b * J.rgb_stride;
+                uint32_t c[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) c[k] = bp_colour(J.reg, rgb, u0 + k, v, (dw[k >> 1] >> ((k & 1) * 16)) & 0xFFFFu);
+                uint8_t* o = J.colour + (uint64_t)cur.b * J.colour_stride + (size_t)p0 * 3;
+                st_stream_u2(o, make_uint2(c[0] | (c[1] << 24), (c[1] >> 8) | (c[2] << 16)));
+                st_stream_u2(o + 8, make_uint2((c[2] >> 16) | (c[3] << 8), c[4] | (c[5] << 24)));
+                st_stream_u2(o + 16, make_uint2((c[5] >> 8) | (c[6] << 16), (c[6] >> 16) | (c[7] << 8)));
+            }
 #pragma unroll
             for (int q = 0; q < 6; ++q)
                 xbuf[warp][lane * BP_LANE_STRIDE + q] = make_float4(f[4 * q], f[4 * q + 1], f[4 * q + 2], f[4 * q + 3]);
@@ -185,55 +246,83 @@ __global__ void __launch_bounds__(BP_THREADS) backproject_scalar_kernel(BpJobDev
 
 int launch_backproject(ti_ctx* ctx, const BackprojectJob* jobs, int n_jobs, int n_batch) {
     if (n_jobs <= 0 || n_batch <= 0) return TI_OK;
-    int done = 0;
-    while (done < n_jobs) {
-        BpParams P{};
-        int nv = 0;
-        uint32_t tiles = 0;
-        for (; done < n_jobs && nv < MAX_BP_JOBS; ++done) {
-            const BackprojectJob& J = jobs[done];
-            if (J.camera < 0 || J.camera >= TI_MAX_CAMERAS || !ctx->cams[J.camera].has_proj)
-                return fail(ctx, TI_ESTATE, "backproject: camera slot %d has no projection (call ti_upload_projection)", J.camera);
-            if (!J.depth || !J.xyz) return fail(ctx, TI_EINVAL, "backproject: null depth/xyz pointer");
-            const CameraSlot& C = ctx->cams[J.camera];
-            BpJobDev D{};
-            D.depth = J.depth; D.xyz = J.xyz; D.mask = J.mask; D.count = J.count;
-            D.depth_stride = J.depth_stride; D.xyz_stride = J.xyz_stride; D.mask_stride = J.mask_stride;
-            for (int i = 0; i < 3; ++i) { D.cam.au[i] = C.proj_au[i]; D.cam.av[i] = C.proj_av[i]; D.cam.ac[i] = C.proj_ac[i]; D.cam.t[i] = C.proj_t[i]; }
-            D.cam.width = C.proj_w; D.cam.height = C.proj_h;
-            if (J.depth_stride % 2 || J.xyz_stride % 4)
-                return fail(ctx, TI_EINVAL, "backproject: frame strides must keep element alignment");
-            if (J.count) {
+    // two passes over the job list: plain jobs share launches of <false>, jobs with a colour output share launches of <true>
+    for (int want_colour = 0; want_colour < 2; ++want_colour) {
+        int done = 0;
+        while (done < n_jobs) {
+            BpParams P{};
+            int nv = 0;
+            uint32_t tiles = 0;
+            for (; done < n_jobs && nv < MAX_BP_JOBS; ++done) {
+                const BackprojectJob& J = jobs[done];
+                if ((J.colour != nullptr) != (want_colour != 0)) continue;
+                if (J.camera < 0 || J.camera >= TI_MAX_CAMERAS || !ctx->cams[J.camera].has_proj)
+                    return fail(ctx, TI_ESTATE, "backproject: camera slot %d has no projection (call ti_upload_projection)", J.camera);
+                if (!J.depth || !J.xyz) return fail(ctx, TI_EINVAL, "backproject: null depth/xyz pointer");
+                const CameraSlot& C = ctx->cams[J.camera];
+                BpJobDev D{};
+                D.depth = J.depth; D.xyz = J.xyz; D.mask = J.mask; D.count = J.count;
+                D.depth_stride = J.depth_stride; D.xyz_stride = J.xyz_stride; D.mask_stride = J.mask_stride;
+                for (int i = 0; i < 3; ++i) { D.cam.au[i] = C.proj_au[i]; D.cam.av[i] = C.proj_av[i]; D.cam.ac[i] = C.proj_ac[i]; D.cam.t[i] = C.proj_t[i]; }
+                D.cam.width = C.proj_w; D.cam.height = C.proj_h;
+                if (J.depth_stride % 2 || J.xyz_stride % 4)
+                    return fail(ctx, TI_EINVAL, "backproject: frame strides must keep element alignment");
+                if (J.colour) {
+                    if (!C.has_reg) return fail(ctx, TI_ESTATE, "backproject: camera slot %d has no registration (call ti_upload_registration)", J.camera);
+                    if (!J.rgb) return fail(ctx, TI_EINVAL, "backproject: a colour output needs the RGB image");
+                    if (C.reg_dw != C.proj_w || C.reg_dh != C.proj_h)
+                        return fail(ctx, TI_EINVAL, "backproject: registration (%dx%d) and projection (%dx%d) of slot %d describe different depth images",
+                                    C.reg_dw, C.reg_dh, C.proj_w, C.proj_h, J.camera);
+                    D.rgb = J.rgb; D.colour = J.colour;
+                    D.rgb_stride = J.rgb_stride ? J.rgb_stride : (uint64_t)C.reg_rw * C.reg_rh * 3;
+                    D.colour_stride = J.colour_stride ? J.colour_stride : (uint64_t)C.proj_w * C.proj_h * 3;
+                    for (int i = 0; i < 9; ++i) D.reg.a[i] = C.reg_a[i];
+                    for (int i = 0; i < 3; ++i) D.reg.t[i] = C.reg_t[i];
+                    D.reg.cx = C.reg_k[0]; D.reg.cy = C.reg_k[1]; D.reg.rfx = C.reg_k[2]; D.reg.rfy = C.reg_k[3]; D.reg.rcx = C.reg_k[4]; D.reg.rcy = C.reg_k[5];
+                    D.reg.rw = C.reg_rw; D.reg.rh = C.reg_rh;
+                    // |u' - u| <= 3.6e-7 * |u - cx| + 2 * ulp(u) / 2: 1.7e-3 px for images up to 4096 px; twice that as the band
+                    D.reg.guard = std::max(4e-3f, 1e-6f * (float)std::max(C.reg_rw, C.reg_rh));
+                }
+                if (J.count) {
 #ifndef TI_EMULATE
-                TI_CUDA(ctx, cudaMemsetAsync(J.count, 0, sizeof(uint32_t) * (size_t)n_batch, ctx->stream));
+                    TI_CUDA(ctx, cudaMemsetAsync(J.count, 0, sizeof(uint32_t) * (size_t)n_batch, ctx->stream));
 #else
-                for (int b = 0; b < n_batch; ++b) J.count[b] = 0;
+                    for (int b = 0; b < n_batch; ++b) J.count[b] = 0;
 #endif
+                }
+                const bool aligned = (C.proj_w % 8 == 0) && ((uintptr_t)J.depth % 16 == 0) && ((uintptr_t)J.xyz % 16 == 0) &&
+                                     (J.depth_stride % 16 == 0) && (J.xyz_stride % 16 == 0) &&
+                                     (!J.mask || (((uintptr_t)J.mask | J.mask_stride) % 8 == 0)) &&
+                                     (!J.colour || (((uintptr_t)J.colour | D.colour_stride) % 8 == 0));
+                if (!aligned) {
+                    const uint64_t total = (uint64_t)C.proj_w * C.proj_h * n_batch;
+                    const int grid = (int)std::min<uint64_t>((total + BP_THREADS - 1) / BP_THREADS, (uint64_t)ctx->sm_count * 8);
+                    TI_LAUNCH(backproject_scalar_kernel, grid, BP_THREADS, 0, ctx->stream, D, n_batch);
+                    TI_CHECK_LAUNCH(ctx);
+                    if (J.colour) {  // any size / alignment: the stand-alone registration kernel after it
+                        const int rc = launch_register_colour(ctx, J.camera, J.depth, J.rgb, J.colour, n_batch, J.depth_stride, J.rgb_stride, J.colour_stride);
+                        if (rc != TI_OK) return rc;
+                    }
+                    continue;
+                }
+                D.tile_begin = tiles;
+                tiles += (uint32_t)(((uint64_t)C.proj_w * C.proj_h + BP_TILE - 1) / BP_TILE);
+                P.job[nv++] = D;
             }
-            const bool aligned = (C.proj_w % 8 == 0) && ((uintptr_t)J.depth % 16 == 0) && ((uintptr_t)J.xyz % 16 == 0) &&
-                                 (J.depth_stride % 16 == 0) && (J.xyz_stride % 16 == 0) &&
-                                 (!J.mask || (((uintptr_t)J.mask | J.mask_stride) % 8 == 0));
-            if (!aligned) {
-                const uint64_t total = (uint64_t)C.proj_w * C.proj_h * n_batch;
-                const int grid = (int)std::min<uint64_t>((total + BP_THREADS - 1) / BP_THREADS, (uint64_t)ctx->sm_count * 8);
-                TI_LAUNCH(backproject_scalar_kernel, grid, BP_THREADS, 0, ctx->stream, D, n_batch);
-                TI_CHECK_LAUNCH(ctx);
-                continue;
-            }
-            D.tile_begin = tiles;
-            tiles += (uint32_t)(((uint64_t)C.proj_w * C.proj_h + BP_TILE - 1) / BP_TILE);
-            P.job[nv++] = D;
+            if (nv == 0) continue;
+            P.tiles_per_set = tiles;
+            P.n_jobs = nv;
+            P.n_batch = n_batch;
+            const uint64_t total = (uint64_t)tiles * n_batch;
+            // two resident CTAs per SM measured best for the plain kernel (fewer concurrent DRAM streams; the register prefetch hides
+            // latency); the colour kernel waits on gathers and takes what fits
+            const int fit = want_colour ? resident_ctas(backproject_vec_kernel<true>, BP_THREADS, 0, 3)
+                                        : std::min(2, resident_ctas(backproject_vec_kernel<false>, BP_THREADS, 0, 4));
+            const int grid = (int)std::min<uint64_t>(total, (uint64_t)ctx->sm_count * (ctx->ctas_per_sm > 0 ? ctx->ctas_per_sm : fit));
+            if (want_colour) TI_LAUNCH(backproject_vec_kernel<true>, grid, BP_THREADS, 0, ctx->stream, P);
+            else TI_LAUNCH(backproject_vec_kernel<false>, grid, BP_THREADS, 0, ctx->stream, P);
+            TI_CHECK_LAUNCH(ctx);
         }
-        if (nv == 0) continue;
-        P.tiles_per_set = tiles;
-        P.n_jobs = nv;
-        P.n_batch = n_batch;
-        const uint64_t total = (uint64_t)tiles * n_batch;
-        // two resident CTAs per SM measured best (fewer concurrent DRAM streams; the register prefetch hides latency)
-        static const int per_sm = std::min(2, resident_ctas(backproject_vec_kernel, BP_THREADS, 0, 4));
-        const int grid = (int)std::min<uint64_t>(total, (uint64_t)ctx->sm_count * (ctx->ctas_per_sm > 0 ? ctx->ctas_per_sm : per_sm));
-        TI_LAUNCH(backproject_vec_kernel, grid, BP_THREADS, 0, ctx->stream, P);
-        TI_CHECK_LAUNCH(ctx);
     }
     return TI_OK;
 }

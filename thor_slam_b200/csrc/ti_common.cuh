@@ -361,6 +361,10 @@ struct BackprojectJob {
     uint32_t* count;
     uint64_t depth_stride, xyz_stride, mask_stride;
     int camera;
+    // fused depth -> RGB registration (both NULL: none): one RGB8 colour per depth pixel from `rgb` (the slot's registration)
+    const uint8_t* rgb = nullptr;
+    uint8_t* colour = nullptr;
+    uint64_t rgb_stride = 0, colour_stride = 0;
 };
 int launch_backproject(ti_ctx* ctx, const BackprojectJob* jobs, int n_jobs, int n_batch);
 int launch_register_colour(ti_ctx* ctx, int camera, const uint16_t* depth, const uint8_t* rgb, uint8_t* colour, int n_batch,

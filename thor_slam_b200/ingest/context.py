@@ -220,6 +220,16 @@ class IngestContext:
         )
         return xyz
 
+    def backproject_colour(self, camera: int, depth: Any, rgb: Any, xyz: Any, colour: Any, mask: Any = None, count: Any = None) -> Any:
+        """``ti_backproject_colour``: clouds + mask + count + one RGB8 colour per depth pixel in one pass over the depth image."""
+        n = int(depth.shape[0])
+        self._check(
+            self.lib.ti_backproject_colour(self._h, camera, self._ptr(depth), self._ptr(rgb), self._ptr(xyz), self._ptr(mask), self._ptr(count),
+                                           self._ptr(colour), n, self._batch_stride(depth), self._batch_stride(rgb), self._batch_stride(xyz),
+                                           self._batch_stride(mask) if mask is not None else 0, self._batch_stride(colour))
+        )
+        return xyz
+
     def _pack(self, streams: Sequence[StreamSpec], host: bool) -> tuple[Any, int]:
         arr = (TiStream * len(streams))()
         n_batch = None

@@ -369,11 +369,11 @@ class IngestRig(CameraRig):
             self._ctx.set_stream(cur.cuda_stream)
         self._ctx.ingest([
             StreamSpec(F.KIND_CONVERT, rgb.dev[slot:slot + 1], rgb.out[slot:slot + 1], F.BGR8, F.RGB8, width=rgb.src_size[0], height=rgb.src_size[1]),
-            StreamSpec(F.KIND_BACKPROJECT, dep.dev[slot:slot + 1], dep.out[slot:slot + 1], F.DEPTH16, F.XYZ32F, camera=dep.camera,
-                       mask=dep.mask[slot:slot + 1], count=dep.count[slot:slot + 1]),
         ])
         colours = self._colours.setdefault(source_name, self._alloc((2, dep.src_size[1], dep.src_size[0], 3), F.RGB8))
-        self._ctx.register_colour(dep.camera, dep.dev[slot:slot + 1], rgb.out[slot:slot + 1], colours[slot:slot + 1])
+        # cloud + mask + count + the colour of every depth pixel in one pass over the depth image (ti_backproject_colour)
+        self._ctx.backproject_colour(dep.camera, dep.dev[slot:slot + 1], rgb.out[slot:slot + 1], dep.out[slot:slot + 1], colours[slot:slot + 1],
+                                     dep.mask[slot:slot + 1], dep.count[slot:slot + 1])
         ready = None
         if not self._emulated:
             ready = torch.cuda.Event()

@@ -120,7 +120,21 @@ def main() -> None:
         gspecs = [StreamSpec(F.KIND_RECTIFY, cin[i], gout[i], F.BGR8, F.MONO8, camera=16 + i) for i in range(NC)]
         cpx = NC * NB * CW * CH
         report("rectify bgr8->rgb8 1920x1200 (3-channel windows)", timeit(lambda: ctx.ingest(cspecs), args.iters), 6 * cpx, cpx)
-        report("rectify bgr8->mono8 1920x1200 (gray pass + v4)", timeit(lambda: ctx.ingest(gspecs), args.iters), 4 * cpx, cpx)
+        report("rectify bgr8->mono8 1920x1200 (gray pass + v4, L2-sized chunks)", timeit(lambda: ctx.ingest(gspecs), args.iters), 4 * cpx, cpx)
+        ctx.set_option(ctx.OPT_L2_SCRATCH_KB, 4 << 20)
+        report("  the same with the whole batch as one chunk (round 1)", timeit(lambda: ctx.ingest(gspecs), args.iters), 4 * cpx, cpx)
+        ctx.set_option(ctx.OPT_L2_SCRATCH_KB, 0)
+        nvin = [torch.randint(0, 256, (NB, CH * 3 // 2, CW), dtype=torch.uint8, device="cuda") for _ in range(NC)]
+        nspecs = [StreamSpec(F.KIND_RECTIFY, nvin[i], cout[i], F.NV12, F.RGB8, camera=16 + i) for i in range(NC)]
+        report("rectify nv12->rgb8 1920x1200 (bgr pass + 3-channel windows, L2-sized chunks)", timeit(lambda: ctx.ingest(nspecs), args.iters), 4.5 * cpx, cpx)
+        ctx.set_option(ctx.OPT_L2_SCRATCH_KB, 4 << 20)
+        report("  the same with the whole batch as one chunk (round 1)", timeit(lambda: ctx.ingest(nspecs), args.iters), 4.5 * cpx, cpx)
+        ctx.set_option(ctx.OPT_L2_SCRATCH_KB, 0)
+        for kb in (8 << 10, 16 << 10, 24 << 10, 64 << 10):
+            ctx.set_option(ctx.OPT_L2_SCRATCH_KB, kb)
+            report(f"  bgr8->mono8, {kb >> 10} MB of scratch per chunk", timeit(lambda: ctx.ingest(gspecs), args.iters), 4 * cpx, cpx)
+        ctx.set_option(ctx.OPT_L2_SCRATCH_KB, 0)
+        del nvin
         ctx.set_option(ctx.OPT_FORCE_GENERIC_RECTIFY, 1)
         report("rectify bgr8->rgb8 generic tiled", timeit(lambda: ctx.ingest(cspecs), max(3, args.iters // 4)), 6 * cpx, cpx)
         report("rectify bgr8->mono8 generic direct", timeit(lambda: ctx.ingest(gspecs), max(3, args.iters // 4)), 4 * cpx, cpx)
@@ -153,7 +167,13 @@ def main() -> None:
         ctx.upload_registration(0, di.matrix, (W, H), ri.matrix, (1920, 1080), t_rd)
         report("register depth->rgb colour (depth 2 + colour 3 B/px + the 1080p RGB image once)",
                timeit(lambda: ctx.register_colour(0, depth[0], rgb_img, colour), args.iters), 5 * B * W * H + B * 1920 * 1080 * 3, B * W * H)
-        del rgb_img, colour
+        xyz1 = torch.empty((B, H, W, 3), dtype=torch.float32, device="cuda")
+        report("backproject + colour fused (2 in + 12 + 1 + 3 out = 18 B/px; the RGB image read on top)",
+               timeit(lambda: ctx.backproject_colour(0, depth[0], rgb_img, xyz1, colour, mask[0], cnt[0]), args.iters), 18 * B * W * H, B * W * H)
+        report("  the same as two kernels (backproject, then register colour)",
+               timeit(lambda: (ctx.backproject(0, depth[0], xyz1, mask[0], cnt[0]), ctx.register_colour(0, depth[0], rgb_img, colour)), args.iters),
+               18 * B * W * H, B * W * H)
+        del rgb_img, colour, xyz1
         for per_sm in (2, 3, 4, 6, 8):
             ctx.set_option(ctx.OPT_CTAS_PER_SM, per_sm)
             report(f"backproject ctas/sm={per_sm}", timeit(lambda: ctx.ingest(bspecs), args.iters), 15 * dpx, dpx)
