@@ -106,7 +106,7 @@ typedef enum ti_option {
     TI_OPT_FRAMES_PER_UNIT = 6,       /* frames of a batch sharing one LUT fetch in the TMA kernels (default 16; pair-window: 0 = automatic) */
     TI_OPT_STAGES = 7,                /* shared-memory ring depth of the TMA kernels, 2..8 (default 6 pair-window, reduced to fit; 2 shifted-copy) */
     TI_OPT_LUT_PREFETCH = 8,          /* 1: consumers prefetch the next unit's LUT into a second register set (default 0) */
-    TI_OPT_L2_SCRATCH_KB = 10,        /* two-pass rectify (BGR8 -> MONO8, NV12 -> RGB8): KB of intermediate frames per chunk of the batch (default 40960) */
+    TI_OPT_L2_SCRATCH_KB = 10,        /* two-pass rectify (BGR8 -> MONO8, NV12 -> RGB8): KB of intermediate frames per chunk of the batch (default 0: one chunk) */
     TI_OPT_PUSH_BLOCKS = 9            /* CTAs of the peer-store copy kernels of ti_cloud_push / ti_inbox_take (default: one per SM) */
 } ti_option;
 int ti_set_option(ti_ctx* ctx, int option, int value);

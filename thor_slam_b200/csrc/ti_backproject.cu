@@ -14,6 +14,7 @@
 // through a warp-private shared-memory buffer so every global store instruction writes 512
 // contiguous bytes; counts are reduced with redux.sync and one atomic per warp.
 #include "ti_common.cuh"
+#include "ti_register.cuh"
 
 namespace ti {
 
@@ -31,14 +32,6 @@ struct BpCam {
     int width, height;
 };
 
-// depth -> RGB registration constants of a job (ti_register.cu has the stand-alone kernel and the arithmetic's rationale)
-struct BpReg {
-    float a[9], t[3];
-    float cx, cy, rfx, rfy, rcx, rcy;
-    float guard;  // half-width of the band around x.5 inside which the reciprocal fast path hands over to the IEEE division
-    int rw, rh;
-};
-
 struct BpJobDev {
     const uint16_t* depth;
     float* xyz;
@@ -51,7 +44,7 @@ struct BpJobDev {
     const uint8_t* rgb;
     uint8_t* colour;
     uint64_t rgb_stride, colour_stride;
-    BpReg reg;
+    RegConst reg;
 };
 
 struct BpParams {
@@ -74,45 +67,8 @@ __device__ __forceinline__ void project(const BpCam& c, double bx, double by, do
     z = ok ? (float)fma(dd, fma(c.au[2], ud, bz), c.t[2]) : 0.f;
 }
 
-// The colour of one depth pixel: the selection of register_pixel (ti_register.cu) - same float32 operations, each rounded
-// on its own, so the float32 oracle picks the same RGB pixel - with the two IEEE divisions taken off the common path:
-// q' = p.x * rcp(p.z) is within 2.4e-7 relative of fl(p.x / p.z), so u' = q' * fx + cx is within `guard` (a few 1e-3 px,
-// bound derived in DESIGN.md) of the reference value; rint() of the two can only differ when u' lies within `guard` of a
-// half-integer, and exactly those pixels (well under 1 %) are redone with the division.
-__device__ __forceinline__ uint32_t bp_colour(const BpReg& R, const uint8_t* rgb, int u, int v, uint32_t d) {
-    const float fu = __fsub_rn((float)u, R.cx), fv = __fsub_rn((float)v, R.cy);
-    const float z = __fmul_rn((float)d, 0.001f);
-    float p[3];
-#pragma unroll
-    for (int i = 0; i < 3; ++i) {
-        const float r = __fadd_rn(__fadd_rn(__fmul_rn(R.a[3 * i], fu), __fmul_rn(R.a[3 * i + 1], fv)), R.a[3 * i + 2]);
-        p[i] = __fadd_rn(__fmul_rn(r, z), R.t[i]);
-    }
-    if (d == 0 || !(p[2] > 0.f)) return 0u;
-#ifdef TI_EMULATE
-    const float inv = 1.0f / p[2];
-#else
-    float inv;
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv) : "f"(p[2]));
-#endif
-    float ur = __fadd_rn(__fmul_rn(__fmul_rn(p[0], inv), R.rfx), R.rcx);
-    float vr = __fadd_rn(__fmul_rn(__fmul_rn(p[1], inv), R.rfy), R.rcy);
-    // far outside: rejected on either path (the relative error of the fast path cannot bring such a value back inside)
-    if (!(ur > -2.f && ur < (float)R.rw + 1.f && vr > -2.f && vr < (float)R.rh + 1.f)) return 0u;
-    const float du = fabsf(__fsub_rn(__fsub_rn(ur, floorf(ur)), 0.5f)), dv = fabsf(__fsub_rn(__fsub_rn(vr, floorf(vr)), 0.5f));
-    if (du < R.guard || dv < R.guard) {  // too close to a rounding boundary to trust the reciprocal: the reference's own operations
-        ur = __fadd_rn(__fmul_rn(__fdiv_rn(p[0], p[2]), R.rfx), R.rcx);
-        vr = __fadd_rn(__fmul_rn(__fdiv_rn(p[1], p[2]), R.rfy), R.rcy);
-    }
-    if (!(ur > -1.f && ur < (float)R.rw && vr > -1.f && vr < (float)R.rh)) return 0u;
-    const int iu = __float2int_rn(ur), iv = __float2int_rn(vr);
-    if (iu < 0 || iu >= R.rw || iv < 0 || iv >= R.rh) return 0u;
-    const uint8_t* s = rgb + ((size_t)iv * R.rw + iu) * 3;
-    return (uint32_t)__ldg(s) | ((uint32_t)__ldg(s + 1) << 8) | ((uint32_t)__ldg(s + 2) << 16);
-}
-
 template <bool COLOUR>
-__global__ void __launch_bounds__(BP_THREADS) backproject_vec_kernel(const __grid_constant__ BpParams P) {
+__global__ void __launch_bounds__(BP_THREADS, COLOUR ? 4 : 1) backproject_vec_kernel(const __grid_constant__ BpParams P) {
     __shared__ float4 xbuf[BP_THREADS / 32][32 * BP_LANE_STRIDE];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     // Every CTA owns a CONTIGUOUS run of tiles (decoded incrementally: no divisions per 8 pixels), so a
@@ -178,9 +134,16 @@ __global__ void __launch_bounds__(BP_THREADS) backproject_vec_kernel(const __gri
             if (J.mask) st_stream_u2(J.mask + (uint64_t)cur.b * J.mask_stride + p0, make_uint2(m0, m1));
             if (COLOUR) {  // 8 pixels x RGB = 24 bytes = three 64-bit stores (p0 is a multiple of 8)
                 const uint8_t* rgb = J.rgb + (uint64_t)cur.b * J.rgb_stride;
+                int idx[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) idx[k] = reg_pixel_index(J.reg, u0 + k, v, (dw[k >> 1] >> ((k & 1) * 16)) & 0xFFFFu);
                 uint32_t c[8];
 #pragma unroll
-                for (int k = 0; k < 8; ++k) c[k] = bp_colour(J.reg, rgb, u0 + k, v, (dw[k >> 1] >> ((k & 1) * 16)) & 0xFFFFu);
+                for (int k = 0; k < 8; ++k) {  // the gathers of all 8 pixels are in flight together (no control flow between them)
+                    const uint8_t* s = rgb + (size_t)max(idx[k], 0) * 3;
+                    const uint32_t px = (uint32_t)__ldg(s) | ((uint32_t)__ldg(s + 1) << 8) | ((uint32_t)__ldg(s + 2) << 16);
+                    c[k] = idx[k] >= 0 ? px : 0u;
+                }
                 uint8_t* o = J.colour + (uint64_t)cur.b * J.colour_stride + (size_t)p0 * 3;
                 st_stream_u2(o, make_uint2(c[0] | (c[1] << 24), (c[1] >> 8) | (c[2] << 16)));
                 st_stream_u2(o + 8, make_uint2((c[2] >> 16) | (c[3] << 8), c[4] | (c[5] << 24)));
@@ -276,12 +239,7 @@ int launch_backproject(ti_ctx* ctx, const BackprojectJob* jobs, int n_jobs, int 
                     D.rgb = J.rgb; D.colour = J.colour;
                     D.rgb_stride = J.rgb_stride ? J.rgb_stride : (uint64_t)C.reg_rw * C.reg_rh * 3;
                     D.colour_stride = J.colour_stride ? J.colour_stride : (uint64_t)C.proj_w * C.proj_h * 3;
-                    for (int i = 0; i < 9; ++i) D.reg.a[i] = C.reg_a[i];
-                    for (int i = 0; i < 3; ++i) D.reg.t[i] = C.reg_t[i];
-                    D.reg.cx = C.reg_k[0]; D.reg.cy = C.reg_k[1]; D.reg.rfx = C.reg_k[2]; D.reg.rfy = C.reg_k[3]; D.reg.rcx = C.reg_k[4]; D.reg.rcy = C.reg_k[5];
-                    D.reg.rw = C.reg_rw; D.reg.rh = C.reg_rh;
-                    // |u' - u| <= 3.6e-7 * |u - cx| + 2 * ulp(u) / 2: 1.7e-3 px for images up to 4096 px; twice that as the band
-                    D.reg.guard = std::max(4e-3f, 1e-6f * (float)std::max(C.reg_rw, C.reg_rh));
+                    D.reg = reg_constants(C);
                 }
                 if (J.count) {
 #ifndef TI_EMULATE

@@ -672,10 +672,11 @@ static int launch_tiled(ti_ctx* ctx, RectParams& P, size_t smem_bytes) {
 // scratch, then the 3-channel window remap (which swaps to RGB) - remap is per channel, so this equals
 // cv2.remap(cvtColor(YUV2RGB_NV12)).  Both are several times faster than converting every tap inside the generic kernel.
 //
-// The intermediate frames never need to reach DRAM: the batch is cut into chunks whose scratch fits the L2 (126 MB, of which
-// 40 MB are budgeted by default, TI_OPT_L2_SCRATCH_KB), every chunk is converted and remapped before the next one overwrites the same scratch
-// lines, so the second pass reads what the first just wrote from L2 and DRAM sees the algorithmic bytes only (source once,
-// result once).  mid_fmt_of() says which jobs take this route; `two_pass` holds them with their scratch offsets.
+// TI_OPT_L2_SCRATCH_KB > 0 cuts the batch into chunks whose scratch fits that budget, every chunk converted and remapped
+// before the next one overwrites the same scratch lines, so that the second pass reads what the first just wrote from the L2.
+// Measured on the B200 (profiles/r02_summary.md): 40 MB chunks 0.39 of peak against 0.49 for the whole batch in one chunk
+// (BGR8 -> MONO8, 4 x 1920 x 1200 x 16) - the smaller launches lose more than the saved re-read gains - so the default is one
+// chunk.  mid_fmt_of() says which jobs take the two-pass route; `two_pass` holds them with their scratch offsets.
 
 struct TwoPassJob {
     RectifyJob job;     // as given by the caller
@@ -725,7 +726,8 @@ int launch_rectify(ti_ctx* ctx, const RectifyJob* jobs_in, int n_jobs, int n_bat
         if (rc != TI_OK) return rc;
     }
     if (two_pass.empty()) return TI_OK;
-    const int chunk = (int)std::max<size_t>(1, std::min<size_t>((size_t)n_batch, ((size_t)ctx->l2_scratch_kb << 10) / mid_per_frame_set));
+    const int chunk = ctx->l2_scratch_kb <= 0 ? n_batch
+                                              : (int)std::max<size_t>(1, std::min<size_t>((size_t)n_batch, ((size_t)ctx->l2_scratch_kb << 10) / mid_per_frame_set));
     const size_t need = mid_per_frame_set * (size_t)chunk;
     if (need > ctx->scratch_cap) {
         if (ctx->scratch) cudaFree(ctx->scratch);  // synchronises: earlier launches that read it have finished
