@@ -68,7 +68,7 @@ __device__ __forceinline__ void project(const BpCam& c, double bx, double by, do
 }
 
 template <bool COLOUR>
-__global__ void __launch_bounds__(BP_THREADS, COLOUR ? 4 : 1) backproject_vec_kernel(const __grid_constant__ BpParams P) {
+__global__ void __launch_bounds__(BP_THREADS, 4) backproject_vec_kernel(const __grid_constant__ BpParams P) {
     __shared__ float4 xbuf[BP_THREADS / 32][32 * BP_LANE_STRIDE];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     // Every CTA owns a CONTIGUOUS run of tiles (decoded incrementally: no divisions per 8 pixels), so a

@@ -262,7 +262,7 @@ template <int MODE, int UNROLL>
 static int launch_mode(ti_ctx* ctx, const ConvertParams& P, uint32_t units) {
     const uint64_t total = (uint64_t)units * P.n_batch;
     const uint64_t want = (total + (uint64_t)CV_THREADS * UNROLL - 1) / ((uint64_t)CV_THREADS * UNROLL);
-    static const int per_sm = resident_ctas(convert_vec_kernel<MODE, UNROLL>, CV_THREADS, 0, 4);
+    const int per_sm = resident_ctas(convert_vec_kernel<MODE, UNROLL>, CV_THREADS, 0, 4);  // memoised per thread and kernel
     const int grid = (int)std::max<uint64_t>(1, std::min<uint64_t>(want, (uint64_t)ctx->sm_count * per_sm));
     TI_LAUNCH((convert_vec_kernel<MODE, UNROLL>), grid, CV_THREADS, 0, ctx->stream, P);
     TI_CHECK_LAUNCH(ctx);

@@ -651,14 +651,7 @@ template <int C>
 static int launch_tiled(ti_ctx* ctx, RectParams& P, size_t smem_bytes) {
     const uint64_t total = (uint64_t)P.tiles_per_set * P.n_batch;
     if (total == 0) return TI_OK;
-#ifndef TI_EMULATE
-    static size_t configured[2] = {0, 0};
-    size_t& cfg = configured[C == 1 ? 0 : 1];
-    if (smem_bytes > 48 * 1024 && smem_bytes > cfg) {
-        TI_CUDA(ctx, cudaFuncSetAttribute(rectify_tile_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RT_MAX_SMEM));
-        cfg = RT_MAX_SMEM;
-    }
-#endif
+    if (smem_bytes > 48 * 1024) TI_CUDA(ctx, ensure_dynamic_smem(rectify_tile_kernel<C>, RT_MAX_SMEM, ctx->device));  // per device, not per process
     const int per_sm = resident_ctas(rectify_tile_kernel<C>, RT_THREADS, smem_bytes, 4);
     const int grid = (int)std::min<uint64_t>(total, (uint64_t)ctx->sm_count * per_sm);
     TI_LAUNCH(rectify_tile_kernel<C>, grid, RT_THREADS, smem_bytes, ctx->stream, P);
@@ -908,9 +901,7 @@ static int launch_rectify_direct(ti_ctx* ctx, const RectifyJob* jobs_in, int n_j
                                            {rectify_mono_tma_kernel<24, false>, rectify_mono_tma_kernel<24, true>}};
         const Kern kern = kernels[thk][ctx->lut_prefetch ? 1 : 0];
         (void)TH;
-#ifndef TI_EMULATE
-        TI_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-#endif
+        TI_CUDA(ctx, ensure_dynamic_smem(kern, smem, ctx->device));
         int per_sm = resident_ctas(kern, M3_THREADS, smem, 3);
         if (ctx->ctas_per_sm > 0) per_sm = ctx->ctas_per_sm;
         const int grid = (int)std::min<uint64_t>(total, (uint64_t)ctx->sm_count * per_sm);
@@ -919,14 +910,7 @@ static int launch_rectify_direct(ti_ctx* ctx, const RectifyJob* jobs_in, int n_j
     }
     if (P2.n_jobs) {
         const uint64_t total = (uint64_t)P2.tiles_per_set * n_batch;
-#ifndef TI_EMULATE
-        static bool configured = false;
-        if (!configured) {
-            TI_CUDA(ctx, cudaFuncSetAttribute(rectify_mono_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                              M2_ZERO_BYTES + M2_MAX_ROWS * M2_ROW_BYTES));
-            configured = true;
-        }
-#endif
+        TI_CUDA(ctx, ensure_dynamic_smem(rectify_mono_kernel, M2_ZERO_BYTES + M2_MAX_ROWS * M2_ROW_BYTES, ctx->device));
         int per_sm = resident_ctas(rectify_mono_kernel, M2_THREADS, smem2, 4);
         if (ctx->ctas_per_sm > 0) per_sm = ctx->ctas_per_sm;
         const int grid = (int)std::min<uint64_t>(total, (uint64_t)ctx->sm_count * per_sm);
