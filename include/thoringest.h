@@ -107,6 +107,7 @@ typedef enum ti_option {
     TI_OPT_STAGES = 7,                /* shared-memory ring depth of the TMA kernels, 2..8 (default 6 pair-window, reduced to fit; 2 shifted-copy) */
     TI_OPT_LUT_PREFETCH = 8,          /* 1: consumers prefetch the next unit's LUT into a second register set (default 0) */
     TI_OPT_L2_SCRATCH_KB = 10,        /* two-pass rectify (BGR8 -> MONO8, NV12 -> RGB8): KB of intermediate frames per chunk of the batch (default 0: one chunk) */
+    TI_OPT_PUSH_TMA = 11,             /* peer copy of ti_cloud_push: 1 = TMA bulk copies issued by one lane per CTA (default), 0 = 16-byte stores */
     TI_OPT_PUSH_BLOCKS = 9            /* CTAs of the peer-store copy kernels of ti_cloud_push / ti_inbox_take (default: one per SM) */
 } ti_option;
 int ti_set_option(ti_ctx* ctx, int option, int value);
@@ -295,8 +296,10 @@ int ti_inbox_init(ti_ctx* ctx, void* inbox);
 /* Append records[0 .. *n_records) (DEVICE; *n_records is read on the device when the ingest stream reaches this point) to
  * `inbox` (own or peer-mapped) for generation `gen`: waits on the device until the inbox is at `gen`, reserves the slots with
  * one system-scope atomic, copies with peer stores, then reports this rank done.  Records past inbox_capacity are dropped
- * (the header's count still includes them).  `records` may be reused after ti_gather_wait(). */
-int ti_cloud_push(ti_ctx* ctx, const uint64_t* records, const uint32_t* n_records, void* inbox, uint64_t inbox_capacity,
+ * (the header's count still includes them).  Every rank's run starts 16-byte aligned: an odd list is padded with ONE zero
+ * record (written at records[*n_records], so the buffer needs a spare slot; 0 is not a valid record) - consumers skip
+ * zero records.  `records` may be reused after ti_gather_wait() / the fence taken behind this call. */
+int ti_cloud_push(ti_ctx* ctx, uint64_t* records, const uint32_t* n_records, void* inbox, uint64_t inbox_capacity,
                   uint32_t gen);
 /* Root: wait on the device until `world` ranks have reported done for the inbox's current generation, copy
  * min(count, inbox_capacity, dst_capacity) records to dst (DEVICE; dst_capacity 0: no copy - the caller consumed the inbox in

@@ -125,27 +125,36 @@ def worker(rank: int, world: int, port: int, out: dict) -> None:
                 ok_c = ok_c and np.array_equal(got, want_round(k))
             out["records_nccl_ok"] = bool(ok_c)
         dist.barrier()
-        # (d) peer-store exchange, two inbox slots, three rounds, nothing waited for on the host until the end
-        ex = RecordExchange(ctx, rank, world, capacity=world * cap, root=0, slots=2)
-        taken = [torch.zeros(world * cap, dtype=torch.int64, device="cuda") for _ in range(rounds)] if rank == 0 else None
-        status = [torch.zeros(2, dtype=torch.int32, device="cuda") for _ in range(rounds)] if rank == 0 else None
-        for k in range(rounds):
-            if k >= 2:
-                ctx.exchange_wait(fences[k - 2], on_stream=True)  # rec[k % 2] was pushed two rounds ago
-            ctx.voxel_cloud([(0, dev_depth[k])], rec[k % 2], nrec[k % 2], tag=rank)
-            fences[k] = ex.push(rec[k % 2], nrec[k % 2])
-            if rank == 0:
-                ex.take(taken[k], status[k])
-        ex.wait()
-        torch.cuda.synchronize()
-        if rank == 0:
-            ok_d = True
+        # (d) peer-store exchange, two inbox slots, three rounds, nothing waited for on the host until the end; once with the
+        #     TMA bulk-copy kernel, once with the 16-byte-store kernel
+        for use_tma in (1, 0):
+            ctx.set_option(ctx.OPT_PUSH_TMA, use_tma)
+            ex = RecordExchange(ctx, rank, world, capacity=world * cap, root=0, slots=2)
+            taken = [torch.zeros(world * cap, dtype=torch.int64, device="cuda") for _ in range(rounds)] if rank == 0 else None
+            status = [torch.zeros(2, dtype=torch.int32, device="cuda") for _ in range(rounds)] if rank == 0 else None
+            own = []
             for k in range(rounds):
-                n, err = (int(x) for x in status[k].cpu().numpy())
-                got = np.sort(taken[k][:n].cpu().numpy().view(np.uint64))
-                ok_d = ok_d and err == 0 and np.array_equal(got, want_round(k))
-            out["records_push_ok"] = bool(ok_d)
-        ex.close()
+                if k >= 2:
+                    ctx.exchange_wait(fences[k - 2], on_stream=True)  # rec[k % 2] was pushed two rounds ago
+                ctx.voxel_cloud([(0, dev_depth[k])], rec[k % 2], nrec[k % 2], tag=rank)
+                if rank == 0:
+                    own.append((rec[k % 2].clone(), nrec[k % 2].clone()))  # the root's own list stays local
+                fences[k] = ex.push(rec[k % 2], nrec[k % 2])
+                if rank == 0:
+                    ex.take(taken[k], status[k])
+            ex.wait()
+            torch.cuda.synchronize()
+            if rank == 0:
+                ok_d = True
+                for k in range(rounds):
+                    n, err = (int(x) for x in status[k].cpu().numpy())
+                    got = taken[k][:n].cpu().numpy().view(np.uint64)
+                    mine = own[k][0][: int(own[k][1].item())].cpu().numpy().view(np.uint64)
+                    got = np.sort(np.concatenate([got[got != 0], mine]))  # zero records pad odd lists to 16 bytes
+                    ok_d = ok_d and err == 0 and np.array_equal(got, want_round(k))
+                out["records_push_tma_ok" if use_tma else "records_push_ok"] = bool(ok_d)
+            ex.close()
+        ctx.set_option(ctx.OPT_PUSH_TMA, 1)
         ctx.close()
     finally:
         dist.destroy_process_group()

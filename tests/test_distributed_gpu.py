@@ -19,4 +19,4 @@ def test_two_gpu_gather_and_peer_store():
 
     out = run_two_ranks()
     assert out.get("gather_ok") and out.get("peer_ok"), out
-    assert out.get("records_nccl_ok") and out.get("records_push_ok"), out
+    assert out.get("records_nccl_ok") and out.get("records_push_ok") and out.get("records_push_tma_ok"), out

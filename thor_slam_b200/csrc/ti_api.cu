@@ -136,6 +136,7 @@ int ti_set_option(ti_ctx* ctx, int option, int value) {
         case TI_OPT_DEBUG: ctx->debug = value; return TI_OK;
         case TI_OPT_LUT_PREFETCH: ctx->lut_prefetch = value != 0; return TI_OK;
         case TI_OPT_PUSH_BLOCKS: ctx->push_blocks = value > 0 ? value : 0; return TI_OK;
+        case TI_OPT_PUSH_TMA: ctx->push_tma = value != 0; return TI_OK;
         case TI_OPT_L2_SCRATCH_KB: ctx->l2_scratch_kb = value > 0 ? value : 0; return TI_OK;
         case TI_OPT_STAGES:
             if (value < 2 || value > M3_MAX_STAGES) return fail(ctx, TI_EINVAL, "stages must be in [2,%d]", M3_MAX_STAGES);

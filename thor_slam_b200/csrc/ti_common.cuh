@@ -233,6 +233,7 @@ struct ti_ctx {
     cudaEvent_t ev_fence[16] = {};  // ti_exchange_fence ring
     uint64_t fences = 0;
     int push_blocks = 0;  // CTAs of the peer-store copy kernels (0 = one per SM)
+    int push_tma = 1;     // 1: the peer copy is issued as TMA bulk copies by one lane per CTA; 0: 16-byte stores by small CTAs
 };
 
 void ti_nccl_teardown(ti_ctx* ctx);  // ti_nccl.cu

@@ -18,6 +18,7 @@
 // Every spin has a deadline (TI_PUSH_TIMEOUT_NS): a missing peer turns into header.error / a TI_ECUDA from ti_inbox_take's
 // caller-visible status word, never into a hung GPU.
 #include "ti_common.cuh"
+#include "ti_tma.cuh"
 
 namespace ti {
 
@@ -51,7 +52,7 @@ __device__ __forceinline__ uint64_t now_ns() {
 }
 
 // words: [0] base, [1] n to copy, [2] blocks finished (self-resetting), [3] sticky error
-__global__ void push_reserve_kernel(InboxHdr* hdr, const uint32_t* n_local, uint32_t gen, uint64_t capacity, uint32_t* words) {
+__global__ void push_reserve_kernel(InboxHdr* hdr, uint64_t* records, const uint32_t* n_local, uint32_t gen, uint64_t capacity, uint32_t* words) {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     const uint64_t t0 = now_ns();
     while (ld_acquire_sys(&hdr->gen) != gen) {
@@ -62,10 +63,13 @@ __global__ void push_reserve_kernel(InboxHdr* hdr, const uint32_t* n_local, uint
         }
         __nanosleep(500);
     }
-    const uint32_t n = *n_local;
+    // Every rank reserves an EVEN number of slots, so every rank's run starts 16-byte aligned in the inbox (bulk copies need
+    // that); an odd list is padded with one zero record - no voxel encodes as 0 (key fields are biased, |k| < 16383).
+    uint32_t n = *n_local;
+    if (n & 1u) { records[n] = 0ull; ++n; }
     const uint32_t base = atomicAdd_system(&hdr->n_records, n);
     words[0] = base;
-    words[1] = (uint64_t)base >= capacity ? 0u : (uint32_t)min((uint64_t)n, capacity - base);
+    words[1] = (uint64_t)base >= capacity ? 0u : (uint32_t)min((unsigned long long)n, (unsigned long long)((capacity & ~1ull) - base));
 }
 
 __global__ void __launch_bounds__(PUSH_THREADS, 24) push_copy_kernel(InboxHdr* hdr, const uint64_t* __restrict__ local, uint32_t* words) {
@@ -97,6 +101,65 @@ __global__ void __launch_bounds__(PUSH_THREADS, 24) push_copy_kernel(InboxHdr* h
             words[2] = 0;
             __threadfence_system();
             if (words[3] == 0) atomicAdd_system(&hdr->done, 1u);  // a rank whose reservation timed out never reports done
+        }
+    }
+}
+
+// The same copy driven by the TMA unit: ONE warp per CTA, one lane issuing bulk copies local HBM -> shared memory -> the root's
+// HBM (cp.async.bulk both ways), three 4 KB stages in flight.  It costs the SM no load/store instructions and a handful of issue
+// slots, so the next batch's kernels - which share the SM - keep their pace; its 12 KB of shared memory fit beside the voxel
+// kernel's CTAs (not beside the rectify kernel's, which fill the SM: the copy then waits for that kernel's last CTAs).
+constexpr int TPC_STAGE_BYTES = 4096;
+constexpr int TPC_STAGES = 3;
+
+__device__ __forceinline__ void bulk_store_1d(void* gdst, const void* smem_src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(smem_src)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
+__global__ void __launch_bounds__(32) push_copy_tma_kernel(InboxHdr* hdr, const uint64_t* __restrict__ local, uint32_t* words) {
+    __shared__ __align__(128) uint8_t buf[TPC_STAGES][TPC_STAGE_BYTES];
+    __shared__ __align__(8) uint64_t full[TPC_STAGES];
+    if (threadIdx.x == 0) {
+        uint8_t* remote = reinterpret_cast<uint8_t*>(hdr) + TI_INBOX_HEADER_BYTES + (uint64_t)words[0] * 8u;  // base is even: 16-byte aligned
+        const uint8_t* src = reinterpret_cast<const uint8_t*>(local);
+        const uint64_t bytes = (uint64_t)words[1] * 8u;                                                    // a multiple of 16
+        const uint64_t n_chunks = (bytes + TPC_STAGE_BYTES - 1) / TPC_STAGE_BYTES;
+        for (int s = 0; s < TPC_STAGES; ++s) mbar_init(full + s, 1);
+        mbar_fence_init();
+        auto chunk_bytes = [&](uint64_t c) { return (uint32_t)min((uint64_t)TPC_STAGE_BYTES, bytes - c * TPC_STAGE_BYTES); };
+        // chunks blockIdx.x, blockIdx.x + gridDim.x, ... ; load i + STAGES - 1 is requested before store i is issued
+        uint64_t c_load = blockIdx.x, c_store = blockIdx.x;
+        uint32_t i_load = 0, i_store = 0;
+        for (; i_load < TPC_STAGES - 1 && c_load < n_chunks; ++i_load, c_load += gridDim.x) {
+            const uint32_t nb = chunk_bytes(c_load);
+            mbar_arrive_expect_tx(full + i_load % TPC_STAGES, nb);
+            bulk_load_1d(buf[i_load % TPC_STAGES], src + c_load * TPC_STAGE_BYTES, nb, full + i_load % TPC_STAGES);
+        }
+        for (; c_store < n_chunks; ++i_store, c_store += gridDim.x) {
+            if (c_load < n_chunks) {
+                const int s = i_load % TPC_STAGES;  // last read by store i_load - STAGES: at most STAGES - 2 younger stores may still be reading
+                bulk_wait_read<TPC_STAGES - 2>();
+                const uint32_t nb = chunk_bytes(c_load);
+                mbar_arrive_expect_tx(full + s, nb);
+                bulk_load_1d(buf[s], src + c_load * TPC_STAGE_BYTES, nb, full + s);
+                ++i_load; c_load += gridDim.x;
+            }
+            const int s = i_store % TPC_STAGES;
+            mbar_wait(full + s, (i_store / TPC_STAGES) & 1u);
+            bulk_store_1d(remote + c_store * TPC_STAGE_BYTES, buf[s], chunk_bytes(c_store));
+            bulk_commit();
+        }
+        bulk_wait_all();  // every store of this CTA has been performed
+        __threadfence_system();
+        const uint32_t finished = atomicAdd(&words[2], 1u) + 1;
+        if (finished == gridDim.x) {
+            words[2] = 0;
+            __threadfence_system();
+            if (words[3] == 0) atomicAdd_system(&hdr->done, 1u);
         }
     }
 }
@@ -150,7 +213,7 @@ int ti_inbox_init(ti_ctx* ctx, void* inbox) {
     return TI_OK;
 }
 
-int ti_cloud_push(ti_ctx* ctx, const uint64_t* records, const uint32_t* n_records, void* inbox, uint64_t inbox_capacity, uint32_t gen) {
+int ti_cloud_push(ti_ctx* ctx, uint64_t* records, const uint32_t* n_records, void* inbox, uint64_t inbox_capacity, uint32_t gen) {
     if (!ctx) return TI_EINVAL;
     if (!records || !n_records || !inbox) return fail(ctx, TI_EINVAL, "ti_cloud_push: null argument");
     if ((uintptr_t)records % 16 || (uintptr_t)inbox % 16) return fail(ctx, TI_EINVAL, "ti_cloud_push: buffers must be 16-byte aligned");
@@ -160,9 +223,10 @@ int ti_cloud_push(ti_ctx* ctx, const uint64_t* records, const uint32_t* n_record
     if ((rc = ti_comm_follow_compute(ctx)) != TI_OK) return rc;
     InboxHdr* hdr = reinterpret_cast<InboxHdr*>(inbox);
     uint32_t* words = ctx->d_comm_words + 128;
-    push_reserve_kernel<<<1, 32, 0, ctx->s_comm>>>(hdr, n_records, gen, inbox_capacity, words);
+    push_reserve_kernel<<<1, 32, 0, ctx->s_comm>>>(hdr, records, n_records, gen, inbox_capacity, words);
     TI_CHECK_LAUNCH(ctx);
-    push_copy_kernel<<<ctx->push_blocks > 0 ? ctx->push_blocks : 2 * ctx->sm_count, PUSH_THREADS, 0, ctx->s_comm>>>(hdr, records, words);
+    if (ctx->push_tma) push_copy_tma_kernel<<<ctx->push_blocks > 0 ? ctx->push_blocks : ctx->sm_count, 32, 0, ctx->s_comm>>>(hdr, records, words);
+    else push_copy_kernel<<<ctx->push_blocks > 0 ? ctx->push_blocks : 2 * ctx->sm_count, PUSH_THREADS, 0, ctx->s_comm>>>(hdr, records, words);
     TI_CHECK_LAUNCH(ctx);
     TI_CUDA(ctx, cudaEventRecord(ctx->ev_gather, ctx->s_comm));
     ctx->gather_pending = true;

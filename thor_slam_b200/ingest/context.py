@@ -374,6 +374,7 @@ class IngestContext:
 
     OPT_PUSH_BLOCKS = 9
     OPT_L2_SCRATCH_KB = 10
+    OPT_PUSH_TMA = 11
 
     def nccl_barrier(self) -> None:
         self._check(self.lib.ti_nccl_barrier(self._h))

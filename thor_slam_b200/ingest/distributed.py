@@ -194,8 +194,10 @@ class RecordExchange:
     """The cloud exchange as the library's own kernels over peer memory (``thor_slam_b200/csrc/ti_push.cu``).
 
     The root owns ``slots`` inboxes (used round robin, so a producer does not wait for the root to drain the previous round);
-    every rank - the root included - appends its ``ti_voxel_cloud`` list with :meth:`push`; the root collects a round with
-    :meth:`take`.  Everything runs on the library's exchange stream behind an event of the ingest stream."""
+    every OTHER rank appends its ``ti_voxel_cloud`` list with :meth:`push` (on the root the call only takes a fence: its own
+    list is already where the fusion runs); the root collects a round with :meth:`take`.  A round's cloud is therefore the
+    inbox plus the root's own list.  Everything runs on the library's exchange stream behind an event of the ingest stream.
+    Runs of different ranks start 16-byte aligned in the inbox: odd lists are padded with one zero record - skip zeros."""
 
     def __init__(self, ctx: IngestContext, rank: int, world: int, capacity: int, root: int = 0, slots: int = 2, group: Any = None) -> None:
         from thor_slam_b200.ingest._lib import INBOX_HEADER_BYTES
@@ -225,7 +227,8 @@ class RecordExchange:
         """Append this rank's list for the current round; rounds advance with every call.  Returns a fence: once it has
         passed (``ctx.exchange_wait(fence, on_stream=True)``), ``records`` may be overwritten."""
         k = self.round
-        self.ctx.cloud_push(records, n_records, self.inbox[k % self.slots], self.capacity, k // self.slots)
+        if self.rank != self.root:
+            self.ctx.cloud_push(records, n_records, self.inbox[k % self.slots], self.capacity, k // self.slots)
         self.round += 1
         return self.ctx.exchange_fence()
 
@@ -233,7 +236,7 @@ class RecordExchange:
         """Root only: the next round's fused list into ``dst`` (u64 [>= capacity]), ``status`` = (count, error flag)."""
         assert self.rank == self.root
         k = self.taken
-        self.ctx.inbox_take(self.inbox[k % self.slots], self.capacity, self.world, dst, status)
+        self.ctx.inbox_take(self.inbox[k % self.slots], self.capacity, self.world - 1, dst, status)
         self.taken += 1
 
     def wait(self, on_stream: bool = False) -> None:
