@@ -108,6 +108,7 @@ constexpr int P4_MAX_ROWS = 96;
 constexpr int P4_CONSUMER_WARPS = 8;
 constexpr int P4_THREADS = (P4_CONSUMER_WARPS + 1) * 32;  // consumers + TMA issuer
 constexpr int P4_MAX_STAGES = 8;
+constexpr int P4_SMEM_HEADROOM_KB = 20;  // shared memory per SM the window kernels leave to co-resident exchange kernels
 constexpr int P4_LUT_ROW_WORDS = 192;  // per tile row: 32 lanes x 2 pairs x {window word, pixel a word, pixel b word}
 constexpr uint32_t P4_EXC_UNUSED = 0x80000000u;  // last word of an unused exception entry (no destination offset is -2^31)
 constexpr int P4_MAX_EXC = 32;         // exception entries per (tile, warp): one lane each in the per-frame fix-up pass

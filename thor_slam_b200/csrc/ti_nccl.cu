@@ -7,6 +7,7 @@
 //    output straight into the root GPU's memory through NVLink - the gather is then fused into
 //    the producing kernel (its `dst` simply is a peer pointer) and only a barrier remains.
 #include <dlfcn.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "ti_common.cuh"
@@ -83,7 +84,8 @@ int ti_comm_ready(ti_ctx* ctx) {
     if (ctx->s_comm) return TI_OK;
     int prio_low = 0, prio_high = 0;  // the exchange stream's (small) kernels go first whenever an SM has room
     TI_CUDA(ctx, cudaDeviceGetStreamPriorityRange(&prio_low, &prio_high));
-    TI_CUDA(ctx, cudaStreamCreateWithPriority(&ctx->s_comm, cudaStreamNonBlocking, prio_high));
+    const char* prio_env = getenv("TI_EXCHANGE_PRIORITY");  // bring-up: "0" = default priority
+    TI_CUDA(ctx, cudaStreamCreateWithPriority(&ctx->s_comm, cudaStreamNonBlocking, (prio_env && prio_env[0] == '0') ? prio_low : prio_high));
     TI_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_compute, cudaEventDisableTiming));
     TI_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_gather, cudaEventDisableTiming));
     TI_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_counts, cudaEventDisableTiming));

@@ -17,6 +17,8 @@
 //
 // Every spin has a deadline (TI_PUSH_TIMEOUT_NS): a missing peer turns into header.error / a TI_ECUDA from ti_inbox_take's
 // caller-visible status word, never into a hung GPU.
+#include <stdlib.h>
+
 #include "ti_common.cuh"
 #include "ti_tma.cuh"
 
@@ -52,7 +54,7 @@ __device__ __forceinline__ uint64_t now_ns() {
 }
 
 // words: [0] base, [1] n to copy, [2] blocks finished (self-resetting), [3] sticky error
-__global__ void push_reserve_kernel(InboxHdr* hdr, uint64_t* records, const uint32_t* n_local, uint32_t gen, uint64_t capacity, uint32_t* words) {
+__global__ void push_reserve_kernel(InboxHdr* hdr, uint64_t* records, const uint32_t* n_local, uint32_t gen, uint64_t capacity, uint32_t* words, int debug) {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     const uint64_t t0 = now_ns();
     while (ld_acquire_sys(&hdr->gen) != gen) {
@@ -65,7 +67,7 @@ __global__ void push_reserve_kernel(InboxHdr* hdr, uint64_t* records, const uint
     }
     // Every rank reserves an EVEN number of slots, so every rank's run starts 16-byte aligned in the inbox (bulk copies need
     // that); an odd list is padded with one zero record - no voxel encodes as 0 (key fields are biased, |k| < 16383).
-    uint32_t n = *n_local;
+    uint32_t n = (debug & 16) ? 0u : *n_local;  // bring-up switch 16: the whole protocol, no payload
     if (n & 1u) { records[n] = 0ull; ++n; }
     const uint32_t base = atomicAdd_system(&hdr->n_records, n);
     words[0] = base;
@@ -203,6 +205,11 @@ using namespace ti;
 int ti_comm_ready(ti_ctx* ctx);           // ti_nccl.cu
 int ti_comm_follow_compute(ti_ctx* ctx);  // ti_nccl.cu
 
+static int push_debug() {  // bring-up switches, TI_PUSH_DEBUG: 16 = the whole protocol without payload, 32 = no kernels at all
+    static const int v = getenv("TI_PUSH_DEBUG") ? atoi(getenv("TI_PUSH_DEBUG")) : 0;
+    return v;
+}
+
 extern "C" {
 
 int ti_inbox_init(ti_ctx* ctx, void* inbox) {
@@ -223,7 +230,12 @@ int ti_cloud_push(ti_ctx* ctx, uint64_t* records, const uint32_t* n_records, voi
     if ((rc = ti_comm_follow_compute(ctx)) != TI_OK) return rc;
     InboxHdr* hdr = reinterpret_cast<InboxHdr*>(inbox);
     uint32_t* words = ctx->d_comm_words + 128;
-    push_reserve_kernel<<<1, 32, 0, ctx->s_comm>>>(hdr, records, n_records, gen, inbox_capacity, words);
+    if (push_debug() & 32) {  // bring-up: no kernels at all on the exchange stream
+        TI_CUDA(ctx, cudaEventRecord(ctx->ev_gather, ctx->s_comm));
+        ctx->gather_pending = true;
+        return TI_OK;
+    }
+    push_reserve_kernel<<<1, 32, 0, ctx->s_comm>>>(hdr, records, n_records, gen, inbox_capacity, words, push_debug());
     TI_CHECK_LAUNCH(ctx);
     if (ctx->push_tma) push_copy_tma_kernel<<<ctx->push_blocks > 0 ? ctx->push_blocks : ctx->sm_count, 32, 0, ctx->s_comm>>>(hdr, records, words);
     else push_copy_kernel<<<ctx->push_blocks > 0 ? ctx->push_blocks : 2 * ctx->sm_count, PUSH_THREADS, 0, ctx->s_comm>>>(hdr, records, words);
@@ -240,6 +252,11 @@ int ti_inbox_take(ti_ctx* ctx, void* inbox, uint64_t inbox_capacity, uint32_t wo
     int rc = ti_comm_ready(ctx);
     if (rc != TI_OK) return rc;
     InboxHdr* hdr = reinterpret_cast<InboxHdr*>(inbox);
+    if (push_debug() & 32) {
+        TI_CUDA(ctx, cudaEventRecord(ctx->ev_gather, ctx->s_comm));
+        ctx->gather_pending = true;
+        return TI_OK;
+    }
     inbox_wait_kernel<<<1, 32, 0, ctx->s_comm>>>(hdr, world, status);
     TI_CHECK_LAUNCH(ctx);
     if (dst_capacity) {

@@ -220,7 +220,11 @@ int launch_rectify_c3(ti_ctx* ctx, Rect5Params& P) {
     const size_t stage = (size_t)P.rows_alloc_max * C3_PITCH;
     int stages = std::max(2, std::min(ctx->stages4, C3_MAX_STAGES));
     const size_t tail = C3_LUT_BYTES + (size_t)C3_CONSUMER_WARPS * 512;  // LUT slice + per-warp transpose buffers
-    while (stages > 2 && (256 + (size_t)stages * stage + tail + 1024) * 3 > 228 * 1024) --stages;
+    // ... and never so deep that the SM has no shared memory left for anybody else: the exchange kernels (ti_push.cu: a 12 KB TMA
+    // copy CTA, one-warp flag kernels, each with its 1 KB of system shared memory) run BESIDE this kernel's resident CTAs.  When
+    // they did not fit, whichever came first displaced a CTA of this persistent grid, which then started late and stretched the
+    // kernel by a third (measured: 14 us per step on the fusing rank).  Ring depth beyond four stages buys nothing (round 1).
+    while (stages > 2 && (256 + (size_t)stages * stage + tail + 1024) * 3 > (228 - P4_SMEM_HEADROOM_KB) * 1024) --stages;
     P.stages = stages;
     const size_t smem = 256 + (size_t)stages * stage + tail;
     if (smem > 220 * 1024) return fail(ctx, TI_EINVAL, "rectify (3-channel): source boxes of %d rows do not fit shared memory", P.rows_alloc_max);

@@ -288,7 +288,11 @@ int launch_rectify_pair(ti_ctx* ctx, Rect4Params& P, int th_index) {
     // ring depth: as asked, but never so deep that fewer CTAs fit an SM than the register budget allows
     const int want_ctas = TH == 32 ? 3 : 4;  // = the kernel's __launch_bounds__
     int stages = std::max(2, std::min(ctx->stages4, P4_MAX_STAGES));
-    while (stages > 2 && (256 + (size_t)stages * stage + lut_bytes + 1024) * want_ctas > 228 * 1024) --stages;
+    // ... and never so deep that the SM has no shared memory left for anybody else: the exchange kernels (ti_push.cu: a 12 KB TMA
+    // copy CTA, one-warp flag kernels, each with its 1 KB of system shared memory) run BESIDE this kernel's resident CTAs.  When
+    // they did not fit, whichever came first displaced a CTA of this persistent grid, which then started late and stretched the
+    // kernel by a third (measured: 14 us per step on the fusing rank).  Ring depth beyond four stages buys nothing (round 1).
+    while (stages > 2 && (256 + (size_t)stages * stage + lut_bytes + 1024) * want_ctas > (228 - P4_SMEM_HEADROOM_KB) * 1024) --stages;
     P.stages = stages;
     P.debug = ctx->debug;
     const size_t smem = 256 + (size_t)stages * stage + lut_bytes;
