@@ -212,6 +212,12 @@ int ti_voxel_cloud(ti_ctx* ctx, const ti_depth_stream* streams, int n_streams, i
  * Converts min(*n_records, max_records) records; xyz: DEVICE f32[max_records * 3]. */
 int ti_voxel_points(ti_ctx* ctx, const uint64_t* records, const uint32_t* n_records, uint64_t max_records, float* xyz);
 
+/* The viewer's depth statistics (examples/rgbd_stream.py:270-276: valid count, mean, min, max of depth > 0), one pass over
+ * n_batch depth frames: stats[b] = six u32 {count, min, max, 0, sum low word, sum high word} (DEVICE; min is 0xFFFFFFFF for a
+ * frame without a valid pixel; mean = sum / count is the caller's division).  depth_frame_stride 0 = tightly packed. */
+int ti_depth_stats(ti_ctx* ctx, const uint16_t* depth, int width, int height, int n_batch, uint64_t depth_frame_stride,
+                   uint32_t* stats);
+
 /* ti_backproject and ti_register_colour in ONE pass over the depth image ("fused into the
  * back-projection kernel"): xyz + mask + count as ti_backproject, plus colour (u8 HxWx3, depth size) as ti_register_colour
  * would give it - bit-identical selection - without reading the depth a second time.  rgb: RGB8 of the registered size.

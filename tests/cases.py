@@ -157,6 +157,27 @@ def check_backproject(be, cam: int, w: int, h: int, n: int = 2, seed: int = 2, r
         assert not np.any(gx[i][msk == 0]), "invalid pixels must be written as (0,0,0)"
 
 
+def check_depth_stats(be, w: int, h: int, n: int = 3, seed: int = 8) -> None:
+    """``ti_depth_stats`` against ``oracle.backproject.depth_stats`` (examples/rgbd_stream.py:270-276): exact integers."""
+    rng = np.random.default_rng(seed)
+    depth = np.stack([make_depth(rng, w, h) for _ in range(n)])
+    depth[0] = 0                       # nothing valid
+    if n > 1:
+        depth[1, h // 2:, :] = 65535   # saturated half
+    stats = be.dev(np.full((n, 6), 0xDEADBEEF, dtype=np.uint32))
+    be.ctx.depth_stats(be.dev(depth), stats)
+    got = be.host(stats)
+    for i in range(n):
+        want = ob.depth_stats(depth[i])
+        total = int(got[i, 4]) | (int(got[i, 5]) << 32)
+        assert int(got[i, 0]) == want["count"], (i, got[i], want)
+        if want["count"]:
+            assert int(got[i, 1]) == want["min"] and int(got[i, 2]) == want["max"]
+            assert total == int(depth[i].astype(np.uint64).sum()) and abs(total / want["count"] - want["mean"]) < 1e-6
+        else:
+            assert int(got[i, 1]) == 0xFFFFFFFF and total == 0
+
+
 def check_backproject_colour(be, cam: int, w: int, h: int, rw: int, rh: int, n: int = 2, seed: int = 6, on_half_pixels: bool = False) -> None:
     """``ti_backproject_colour``: the cloud / mask / count of ``ti_backproject`` AND the colours of ``ti_register_colour`` from one
     pass over the depth image.  ``on_half_pixels``: an RGB camera identical to the depth camera but for half a pixel of

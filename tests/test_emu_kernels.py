@@ -102,6 +102,11 @@ def test_backproject_extremes(emu_backend):
     cases.check_backproject(emu_backend, 6, 64, 16, depth=depth)
 
 
+@pytest.mark.parametrize("w,h", [(64, 40), (50, 22)])
+def test_depth_stats(emu_backend, w, h):
+    cases.check_depth_stats(emu_backend, w, h)
+
+
 def test_backproject_with_fused_colour(emu_backend):
     cases.check_backproject_colour(emu_backend, 7, 64, 40, 96, 54)
     cases.check_backproject_colour(emu_backend, 7, 64, 40, 64, 40, on_half_pixels=True)

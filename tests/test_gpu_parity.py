@@ -255,3 +255,8 @@ def test_backproject_with_fused_colour(gpu_backend):
     cases.check_backproject_colour(gpu_backend, 41, 64, 40, 96, 54)
     cases.check_backproject_colour(gpu_backend, 42, 640, 400, 640, 400, on_half_pixels=True)
     cases.check_backproject_colour(gpu_backend, 43, 50, 22, 70, 30)
+
+
+@pytest.mark.parametrize("w,h", [(1280, 800), (50, 22)])
+def test_depth_stats(gpu_backend, w, h):
+    cases.check_depth_stats(gpu_backend, w, h, n=4)

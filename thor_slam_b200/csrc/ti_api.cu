@@ -459,6 +459,14 @@ int ti_backproject(ti_ctx* ctx, int camera, const uint16_t* depth, float* xyz, u
     return launch_backproject(ctx, &J, 1, n_batch);
 }
 
+int ti_depth_stats(ti_ctx* ctx, const uint16_t* depth, int width, int height, int n_batch, uint64_t depth_frame_stride, uint32_t* stats) {
+    if (!ctx) return TI_EINVAL;
+    if (n_batch < 0 || width <= 0 || height <= 0 || (n_batch > 0 && (!depth || !stats))) return fail(ctx, TI_EINVAL, "ti_depth_stats: bad argument");
+    if (depth_frame_stride % 2 || (uintptr_t)depth % 2) return fail(ctx, TI_EINVAL, "ti_depth_stats: depth must be 2-byte aligned");
+    TI_CUDA(ctx, cudaSetDevice(ctx->device));
+    return launch_depth_stats(ctx, depth, width, height, n_batch, depth_frame_stride, stats);
+}
+
 int ti_backproject_colour(ti_ctx* ctx, int camera, const uint16_t* depth, const uint8_t* rgb, float* xyz, uint8_t* mask, uint32_t* count,
                           uint8_t* colour, int n_batch, uint64_t depth_frame_stride, uint64_t rgb_frame_stride, uint64_t xyz_frame_stride,
                           uint64_t mask_frame_stride, uint64_t colour_frame_stride) {

@@ -207,6 +207,73 @@ __global__ void __launch_bounds__(BP_THREADS) backproject_scalar_kernel(BpJobDev
     }
 }
 
+// valid count / min / max / sum of a depth frame (examples/rgbd_stream.py:270-276 prints count, mean, min, max of depth > 0):
+// out[b] = {count, min, max, 0, sum lo, sum hi} as six u32; 128-bit loads, warp reductions, one set of atomics per warp.
+__global__ void __launch_bounds__(256) depth_stats_kernel(const uint16_t* __restrict__ depth, uint64_t stride_bytes, uint32_t npx, int n_batch,
+                                                          uint32_t* __restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    for (int b = blockIdx.y; b < n_batch; b += gridDim.y) {
+        const uint16_t* d = reinterpret_cast<const uint16_t*>(reinterpret_cast<const uint8_t*>(depth) + (uint64_t)b * stride_bytes);
+        uint32_t cnt = 0, mn = 0xFFFFFFFFu, mx = 0;
+        uint64_t sum = 0;
+        for (uint32_t i = (blockIdx.x * 256 + threadIdx.x) * 8; i < npx; i += gridDim.x * 256 * 8) {
+            uint32_t w[4] = {0u, 0u, 0u, 0u};
+            if (i + 8 <= npx && (((uintptr_t)(d + i)) & 15) == 0) {
+                const uint4 q = ld_stream_u4(d + i);
+                w[0] = q.x; w[1] = q.y; w[2] = q.z; w[3] = q.w;
+            } else {
+                for (uint32_t k = 0; k < 8 && i + k < npx; ++k) w[k >> 1] |= (uint32_t)d[i + k] << ((k & 1) * 16);
+            }
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const uint32_t v = (w[k >> 1] >> ((k & 1) * 16)) & 0xFFFFu;
+                if (v) { ++cnt; sum += v; mn = min(mn, v); mx = max(mx, v); }
+            }
+        }
+#ifdef TI_EMULATE
+        uint32_t wc = __reduce_add_sync(0xFFFFFFFFu, cnt), wlo = 0, whi = 0, wmn = mn, wmx = mx;
+        for (int o = 16; o; o >>= 1) { wmn = min(wmn, __shfl_xor_sync(0xFFFFFFFFu, wmn, o)); wmx = max(wmx, __shfl_xor_sync(0xFFFFFFFFu, wmx, o)); }
+        uint64_t ws = 0;
+        for (int l = 0; l < 32; ++l) ws += ((uint64_t)__shfl_sync(0xFFFFFFFFu, (uint32_t)(sum >> 32), l) << 32) | __shfl_sync(0xFFFFFFFFu, (uint32_t)sum, l);
+        wlo = (uint32_t)ws; whi = (uint32_t)(ws >> 32);
+#else
+        const uint32_t wc = __reduce_add_sync(0xFFFFFFFFu, cnt), wmn = __reduce_min_sync(0xFFFFFFFFu, mn), wmx = __reduce_max_sync(0xFFFFFFFFu, mx);
+        uint64_t ws = sum;
+        for (int o = 16; o; o >>= 1) ws += __shfl_xor_sync(0xFFFFFFFFu, ws, o);
+        const uint32_t wlo = (uint32_t)ws, whi = (uint32_t)(ws >> 32);
+#endif
+        if (lane == 0 && wc) {
+            uint32_t* o = out + (size_t)b * 6;
+            atomicAdd(o, wc);
+            atomicMin(o + 1, wmn);
+            atomicMax(o + 2, wmx);
+#ifdef TI_EMULATE
+            uint64_t* s64 = reinterpret_cast<uint64_t*>(o + 4);
+            __atomic_fetch_add(s64, ((uint64_t)whi << 32) | wlo, __ATOMIC_RELAXED);
+#else
+            atomicAdd(reinterpret_cast<unsigned long long*>(o + 4), ((unsigned long long)whi << 32) | wlo);
+#endif
+        }
+    }
+}
+
+int launch_depth_stats(ti_ctx* ctx, const uint16_t* depth, int width, int height, int n_batch, uint64_t stride, uint32_t* out) {
+    if (n_batch <= 0) return TI_OK;
+    const uint32_t npx = (uint32_t)width * (uint32_t)height;
+    // {0, 0xFFFFFFFF, 0, 0, 0, 0} per frame: min starts at all ones (an empty frame is reported as count 0, min 0 by the caller's view below)
+    std::vector<uint32_t> init((size_t)n_batch * 6, 0u);
+    for (int b = 0; b < n_batch; ++b) init[(size_t)b * 6 + 1] = 0xFFFFFFFFu;
+    TI_CUDA(ctx, cudaMemcpyAsync(out, init.data(), init.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+#ifndef TI_EMULATE
+    TI_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // `init` is pageable host memory: the copy must have left it
+#endif
+    const int gx = (int)std::min<uint32_t>((npx / 8 + 255) / 256 + 1, (uint32_t)ctx->sm_count * 4);
+    dim3 grid((unsigned)gx, (unsigned)std::min(n_batch, 64));
+    TI_LAUNCH(depth_stats_kernel, grid, 256, 0, ctx->stream, depth, stride ? stride : (uint64_t)npx * 2, npx, n_batch, out);
+    TI_CHECK_LAUNCH(ctx);
+    return TI_OK;
+}
+
 int launch_backproject(ti_ctx* ctx, const BackprojectJob* jobs, int n_jobs, int n_batch) {
     if (n_jobs <= 0 || n_batch <= 0) return TI_OK;
     // two passes over the job list: plain jobs share launches of <false>, jobs with a colour output share launches of <true>

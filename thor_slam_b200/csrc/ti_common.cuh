@@ -370,6 +370,7 @@ struct BackprojectJob {
     uint64_t rgb_stride = 0, colour_stride = 0;
 };
 int launch_backproject(ti_ctx* ctx, const BackprojectJob* jobs, int n_jobs, int n_batch);
+int launch_depth_stats(ti_ctx* ctx, const uint16_t* depth, int width, int height, int n_batch, uint64_t stride, uint32_t* out);
 int launch_register_colour(ti_ctx* ctx, int camera, const uint16_t* depth, const uint8_t* rgb, uint8_t* colour, int n_batch,
                            uint64_t depth_stride, uint64_t rgb_stride, uint64_t colour_stride);
 

@@ -215,10 +215,10 @@ __global__ void __launch_bounds__(VX_THREADS, 3) voxel_cloud_kernel(const __grid
             const double bx = fma(J.cam.av[0], vd, J.cam.ac[0]);
             const double by = fma(J.cam.av[1], vd, J.cam.ac[1]);
             const double bz = fma(J.cam.av[2], vd, J.cam.ac[2]);
-            // stage 1, branch-free: this lane's run-distinct keys go to column `lane` of the free part of the buffer
-            // (row i = the lane's i-th key), so that stage 2 can walk them row by row
-            uint64_t* col = buf + n_conf + n_pend + lane;
-            uint32_t prev_lo = 0xFFFFFFFFu, prev_hi = 0xFFFFFFFFu, mine = 0;
+            // stage 1: the warp's run-distinct keys of this sub-block, appended densely behind the pending ones (one ballot per
+            // pixel column: stage 2 then walks ceil(n / 32) full rows instead of max-over-lanes sparse ones)
+            uint64_t* pend = buf + n_conf + n_pend;
+            uint32_t prev_lo = 0xFFFFFFFFu, prev_hi = 0xFFFFFFFFu, n_sub = 0;
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
                 const uint32_t d = (k & 1) ? (dw[k >> 1] >> 16) : (dw[k >> 1] & 0xFFFFu);
@@ -229,27 +229,27 @@ __global__ void __launch_bounds__(VX_THREADS, 3) voxel_cloud_kernel(const __grid
                 const uint32_t kz = (uint32_t)vx_floor(fma(dd, fma(J.cam.au[2], ud, bz), J.cam.t[2]));
                 const uint32_t lo = kz | (ky << 15) | (kx << 30), hi = (kx >> 2) | set_hi;
                 const bool keep = (d - 1u) < P.max_depth && (lo != prev_lo || hi != prev_hi);  // 0 < d <= max_depth, new run
+                const uint32_t m = __ballot_sync(0xFFFFFFFFu, keep);
                 if (keep) {
-                    col[mine * 32] = ((uint64_t)hi << 32) | lo;
-                    ++mine;
+                    pend[n_sub + __popc(m & lt_mask)] = ((uint64_t)hi << 32) | lo;
                     prev_lo = lo; prev_hi = hi;
                 }
+                n_sub += __popc(m);
             }
-            // stage 2, one row at a time: the shared cache; survivors are packed to the front of the same region
-            const uint32_t rows = __reduce_max_sync(0xFFFFFFFFu, mine);
-            uint64_t* pend = buf + n_conf + n_pend;
+            __syncwarp();
+            // stage 2, 32 keys at a time: the shared cache; survivors are packed to the front of the same region
             uint32_t out = 0;
-            for (uint32_t i = 0; i < rows; ++i) {
-                bool fresh = i < mine;
+            for (uint32_t i0 = 0; i0 < n_sub; i0 += 32) {
+                bool fresh = i0 + lane < n_sub;
                 uint64_t key = 0;
                 if (fresh) {
-                    key = col[i * 32];
+                    key = pend[i0 + lane];
                     // index from the TOP bits of a product: every key bit reaches them (low product bits only see low key bits)
                     const uint32_t c = ((uint32_t)key ^ ((uint32_t)(key >> 32) * 0x9E3779B1u)) * 0x85EBCA6Bu;
                     fresh = (P.debug & 2) || vx_exch(&cache[c >> 21], key) != key;
                 }
                 const uint32_t m = __ballot_sync(0xFFFFFFFFu, fresh);  // also orders this row's reads before the writes below
-                if (fresh) pend[out + __popc(m & lt_mask)] = key;      // out + 32 <= (i + 1) * 32: never reaches an unread row
+                if (fresh) pend[out + __popc(m & lt_mask)] = key;      // out <= i0: never reaches an unread row
                 out += __popc(m);
             }
             n_pend += out;

@@ -66,6 +66,7 @@ SIGNATURES: dict[str, tuple] = {
     "ti_convert": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_uint64, C.c_uint64]),
     "ti_rectify": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_uint64, C.c_uint64]),
     "ti_backproject": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_uint64, C.c_uint64, C.c_uint64]),
+    "ti_depth_stats": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_uint64, C.c_void_p]),
     "ti_backproject_colour": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
                                         C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64]),
     "ti_set_voxel_grid": (C.c_int, [C.c_void_p, C.c_double, C.c_uint32]),

@@ -220,6 +220,12 @@ class IngestContext:
         )
         return xyz
 
+    def depth_stats(self, depth: Any, stats: Any) -> Any:
+        """``ti_depth_stats``: ``depth`` [n, H, W] u16 -> ``stats`` [n, 6] u32/i32 = (count, min, max, 0, sum lo, sum hi) of depth > 0."""
+        n, h, w = (int(x) for x in depth.shape)
+        self._check(self.lib.ti_depth_stats(self._h, self._ptr(depth), w, h, n, self._batch_stride(depth), self._ptr(stats)))
+        return stats
+
     def backproject_colour(self, camera: int, depth: Any, rgb: Any, xyz: Any, colour: Any, mask: Any = None, count: Any = None) -> Any:
         """``ti_backproject_colour``: clouds + mask + count + one RGB8 colour per depth pixel in one pass over the depth image."""
         n = int(depth.shape[0])
