@@ -202,7 +202,8 @@ typedef struct ti_depth_stream {
  * ti_backproject writes densely (same double-precision back-projection, then k = floor(p_body / voxel_size) per axis):
  *     record = tag << 56 | (set_base + b) << 45 | (kx + 16384) << 30 | (ky + 16384) << 15 | (kz + 16384)
  * records: DEVICE u64[capacity], appended in no defined order; *n_records (DEVICE u32, overwritten) = number of distinct
- * records found - when it exceeds capacity the list was truncated.  set_counts: DEVICE u32[n_batch] (overwritten) or NULL.
+ * records found - when it exceeds capacity the list was truncated (and the count is then only a lower bound: the kernel stops
+ * extending a list that has grown past twice its capacity).  set_counts: DEVICE u32[n_batch] (overwritten) or NULL.
  * tag < 256 (the producing rank in the multi-GPU gather), set_base + n_batch <= 2048.  One call at a time per ctx.
  * This is the cloud the reference's only cloud type carries (thor_slam/slam/interface.py:134-138, N x 3) before ti_voxel_points. */
 int ti_voxel_cloud(ti_ctx* ctx, const ti_depth_stream* streams, int n_streams, int n_batch, uint32_t set_base, uint32_t tag,

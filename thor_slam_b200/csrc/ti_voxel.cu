@@ -59,6 +59,7 @@ struct VxParams {
     VxJobDev job[MAX_VX_JOBS];
     uint64_t* table;       // hash set, table_mask + 1 slots
     uint64_t table_mask;
+    uint32_t region_mask, region_shift;  // frame set s starts probing in region (s - set_base) & region_mask of 1 << region_shift slots
     uint64_t epoch;        // << 56
     uint64_t tag;          // << 56
     uint64_t* records;
@@ -113,11 +114,20 @@ __device__ __forceinline__ uint64_t vx_load(const uint64_t* p) { return *reinter
 // true when this thread installed `key` (set number and voxel, 56 bits) in the global hash set
 __device__ __forceinline__ bool vx_insert(const VxParams& P, uint64_t key) {
     const uint64_t entry = P.epoch | key;
-    const uint64_t h = vx_mix(key & ~0x00000001C0038007ull);  // the 8 x 8 x 8 block: low three bits of every coordinate cleared ...
-    const uint64_t local = ((key >> 24) & 0x1C0u) | ((key >> 12) & 0x38u) | (key & 7u);  // ... and the position inside it
-    uint64_t slot = ((P.debug & 4) ? (((h >> 20) << 9) | local) : (vx_mix(key) >> 11)) & P.table_mask;
+    // Home slot: the frame set picks a REGION of the table, the hash a slot inside it.  Tiles are handed out in frame-set order,
+    // so at any moment the whole grid works on one or two frame sets and their regions (a few MB) stay in the L2; with slots
+    // hashed over the whole table every probe was a DRAM sector (ncu: 390 MB read for 131 MB of depth).  Probing runs on past
+    // the end of a region, so a frame set with more voxels than its share just borrows from its neighbour.
+    const uint64_t set = (key >> 45) & 0x7FFu;
+    uint64_t slot;
+    if (P.debug & 4) {
+        const uint64_t h = vx_mix(key & ~0x00000001C0038007ull);  // bring-up: 8 x 8 x 8 blocks kept together (measured slower)
+        slot = (((h >> 20) << 9) | ((key >> 24) & 0x1C0u) | ((key >> 12) & 0x38u) | (key & 7u)) & P.table_mask;
+    } else {
+        slot = (((set - P.set_base) & P.region_mask) << P.region_shift) | ((vx_mix(key) >> 11) & ((1ull << P.region_shift) - 1));
+    }
     uint64_t cur = vx_load(P.table + slot);
-    for (;;) {
+    for (uint32_t probes = 0; probes < 2048u; ++probes) {
         if (cur == entry) return false;
         if ((cur >> 56) != (P.epoch >> 56)) {  // left over from an earlier launch: free
             const uint64_t old = vx_cas(P.table + slot, cur, entry);
@@ -128,6 +138,7 @@ __device__ __forceinline__ bool vx_insert(const VxParams& P, uint64_t key) {
         slot = (slot + 1) & P.table_mask;
         cur = vx_load(P.table + slot);
     }
+    return false;  // 2048 probes: the table (2 x capacity slots) is as good as full - the list overflowed long ago, *n_records says so
 }
 
 __global__ void __launch_bounds__(VX_THREADS, 3) voxel_cloud_kernel(const __grid_constant__ VxParams P) {
@@ -184,6 +195,9 @@ __global__ void __launch_bounds__(VX_THREADS, 3) voxel_cloud_kernel(const __grid
         const VxJobDev& J = P.job[j];
         const uint32_t lt = r - J.tile_begin;
         const int tile_y = (int)(lt / J.tiles_x), tile_x = (int)(lt - (uint32_t)tile_y * J.tiles_x);
+        // a list far beyond its capacity (the caller sized it wrong; *n_records will say so) stops being extended: the hash set
+        // holds 2 x capacity slots and must not be driven to full
+        if (*reinterpret_cast<const volatile uint32_t*>(P.n_records) > 2 * P.capacity && P.capacity) continue;
         if (b != buf_b) {  // the confirmed records are counted per frame set
             flush(buf_b);
             buf_b = b;
@@ -334,10 +348,13 @@ int ti_voxel_cloud(ti_ctx* ctx, const ti_depth_stream* streams, int n_streams, i
         D.vec = (C.proj_w % 8 == 0) && ((uintptr_t)S.depth % 16 == 0) && (D.depth_stride % 16 == 0);
         px += (uint64_t)C.proj_w * C.proj_h;
     }
-    // hash set: twice the pixels of the launch (every pixel could be its own voxel), a power of two; entries of earlier
-    // launches are recognised by their epoch byte, so it is cleared only when the epoch wraps or the table grows
-    uint64_t slots = 1u << 20;
-    while (slots < 2 * px * (uint64_t)n_batch) slots <<= 1;
+    // hash set: twice the records the caller's list can take (a list that overflows is reported through *n_records; the
+    // table then fills up harmlessly), at most twice the pixels of the launch (every pixel its own voxel), a power of two;
+    // entries of earlier launches are recognised by their epoch byte, so it is cleared only when the epoch wraps or the
+    // table grows
+    uint64_t slots = 1u << 16;
+    const uint64_t want = 2 * std::min<uint64_t>(std::max<uint64_t>(capacity, 1), px * (uint64_t)n_batch);
+    while (slots < want) slots <<= 1;
     if (slots > ctx->voxel_slots) {
         TI_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
         if (ctx->voxel_table) cudaFree(ctx->voxel_table);
@@ -353,6 +370,14 @@ int ti_voxel_cloud(ti_ctx* ctx, const ti_depth_stream* streams, int n_streams, i
     ctx->voxel_epoch++;
     P.table = ctx->voxel_table;
     P.table_mask = ctx->voxel_slots - 1;
+    {
+        uint32_t regions = 1;
+        while ((int)regions < n_batch && (ctx->voxel_slots / (regions * 2)) >= 4096) regions <<= 1;
+        uint32_t shift = 0;
+        while ((ctx->voxel_slots >> (shift + 1)) >= regions) ++shift;  // 1 << shift = slots / regions
+        P.region_mask = regions - 1;
+        P.region_shift = shift;
+    }
     P.epoch = (uint64_t)ctx->voxel_epoch << 56;
     P.tag = (uint64_t)tag << 56;
     P.records = records; P.capacity = capacity; P.n_records = n_records; P.set_counts = set_counts;
