@@ -54,8 +54,8 @@ STREAMS = 2 * N_CAMERAS
 PX_PER_SET = STREAMS * W * H
 ALGO_BYTES_PER_PX = 2  # mono8 -> rectified mono8
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE rectify_mono_pair_kernel launch over 64 frame sets, from the
-# `ncu --set full` capture of this bench (profiles/r01_rect_v4_ncu_raw.txt): 584.93 MB + 485.15 MB
-NCU_TRAFFIC_BYTES_PER_FRAME_SET = (584.931840e6 + 485.148160e6) / 64
+# `ncu --set full` capture of round 2 (profiles/r02_ncu_rect_pair.txt, tools/profile_r02.sh): 574.73 MB + 482.23 MB = 1.008 x algorithmic
+NCU_TRAFFIC_BYTES_PER_FRAME_SET = (574.733824e6 + 482.234112e6) / 64
 KERNEL_BY_VARIANT = {4: "rectify_mono_pair_kernel<32,false,1280>", 3: "rectify_mono_tma_kernel<32,false>", 2: "rectify_mono_kernel", 1: "rectify_tile_kernel<1>"}
 FALLBACK_HBM_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md fallback
 _JSON_OUT = sys.stdout
@@ -470,7 +470,7 @@ def run_ours(args) -> None:
             "gpu_launches": launches,
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": NCU_TRAFFIC_BYTES_PER_FRAME_SET * B, "traffic_source": "ncu --set full, profiles/r01_rect_v4_ncu_raw.txt (scaled per frame set)",
+                         "traffic": NCU_TRAFFIC_BYTES_PER_FRAME_SET * B, "traffic_source": "ncu --set full, profiles/r02_ncu_rect_pair.txt (scaled per frame set)",
                          "kernel": KERNEL_BY_VARIANT[plan["variant"]], "kernel_plan": plan, "algorithmic_bytes_per_launch": algo_bytes,
                          "peak_source": peak_src, "frac_of_8000_datasheet": achieved / 8000.0,
                          "sustained_achieved": algo_bytes / (sustained["ms_per_step"] * 1e-3) / 1e9,

@@ -123,6 +123,8 @@ __device__ __forceinline__ bool vx_insert(const VxParams& P, uint64_t key) {
     if (P.debug & 4) {
         const uint64_t h = vx_mix(key & ~0x00000001C0038007ull);  // bring-up: 8 x 8 x 8 blocks kept together (measured slower)
         slot = (((h >> 20) << 9) | ((key >> 24) & 0x1C0u) | ((key >> 12) & 0x38u) | (key & 7u)) & P.table_mask;
+    } else if (P.debug & 8) {
+        slot = (vx_mix(key) >> 11) & P.table_mask;  // bring-up: hashed over the whole table
     } else {
         slot = (((set - P.set_base) & P.region_mask) << P.region_shift) | ((vx_mix(key) >> 11) & ((1ull << P.region_shift) - 1));
     }

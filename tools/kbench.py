@@ -195,7 +195,7 @@ def main() -> None:
             d4 = np.stack([gen() for _ in range(4)]).view(np.int16)
             vdepth = [torch.from_numpy(np.roll(d4, i, axis=0)).cuda().view(torch.uint16).repeat((VB + 3) // 4, 1, 1)[:VB].contiguous() for i in range(ND)]
             streams = [(i, vdepth[i]) for i in range(ND)]
-            for per_sm, dbg in ((0, 0), (3, 0), (0, 4), (0, 1), (0, 2), (0, 3))[:2 if args.one else None]:
+            for per_sm, dbg in ((0, 0), (0, 8), (0, 0), (0, 8), (0, 4), (0, 1), (0, 2), (0, 3))[:4 if args.one else None]:
                 if scene == "noise" and dbg in (2, 3):
                     continue
                 ctx.set_option(ctx.OPT_CTAS_PER_SM, per_sm)
