@@ -66,6 +66,7 @@ def main() -> None:
     rng = np.random.default_rng(args.seed)
     convs = [("mono8", "mono8")] * 5 + [("bgr8", "rgb8")] * 2 + [("bgr8", "mono8"), ("nv12", "mono8"), ("nv12", "rgb8")]
     plans: collections.Counter = collections.Counter()
+    overflow: list[int] = []
     t0 = time.time()
     for i in range(args.cases):
         s, d = convs[int(rng.integers(len(convs)))]
@@ -73,8 +74,8 @@ def main() -> None:
         dst_w = int(rng.integers(33, 2048 if big else (300 if args.emu else 700)))
         dst_h = int(rng.integers(9, 1300 if big else (70 if args.emu else 300)))
         ratio = rng.choice([1.0, 1.0, 0.5, 2.0, 1.5])
-        src_w = min(2046, max(16, int(dst_w * ratio) + int(rng.integers(-5, 6))))  # the library takes sizes up to 2046
-        src_h = min(2046, max(8, int(dst_h * ratio) + int(rng.integers(-5, 6))))
+        src_w = min(4224, max(16, int(dst_w * ratio) + int(rng.integers(-5, 6))))  # up to the driver's largest sensor mode (the library takes 8190)
+        src_h = min(3136, max(8, int(dst_h * ratio) + int(rng.integers(-5, 6))))
         if rng.random() < 0.8:
             src_w = max(16, src_w & ~15)  # the TMA kernels need a 16-byte row pitch (every sensor mode has one)
         if s == "nv12":
@@ -88,7 +89,10 @@ def main() -> None:
             raise SystemExit(1)
         p = ctx.rectify_plan(20)
         plans[(s, d, p["variant"] if d == "mono8" else p["colour_variant"])] += 1
+        if p["overflow_pixels"]:
+            overflow.append(p["overflow_pixels"])
     print(f"{args.cases} cases, every variant bit-exact against cv2.remap, {time.time() - t0:.0f} s")
+    print(f"  {len(overflow)} slots ran the pair-window kernel WITH an overflow list (up to {max(overflow, default=0)} pixels repaired after the kernel)")
     for k, v in sorted(plans.items()):
         print(f"  {k[0]:>5s} -> {k[1]:<5s} default kernel variant {k[2]}: {v} cases")
 
