@@ -334,10 +334,12 @@ int ti_voxel_cloud(ti_ctx* ctx, const ti_depth_stream* streams, int n_streams, i
         D.depth = S.depth;
         D.depth_stride = S.depth_frame_stride ? S.depth_frame_stride : (uint64_t)C.proj_w * C.proj_h * 2;
         if (D.depth_stride % 2 || (uintptr_t)S.depth % 2) return fail(ctx, TI_EINVAL, "ti_voxel_cloud: depth must be 2-byte aligned");
-        double reach = 0.0;  // bound on |p| / voxel over the image, every valid depth
+        double reach = 0.0;  // max |p| / voxel over the image and every valid depth: the ray is linear in (u, v), so a corner has it
         for (int r = 0; r < 3; ++r) {
             D.cam.au[r] = C.proj_au[r] * inv; D.cam.av[r] = C.proj_av[r] * inv; D.cam.ac[r] = C.proj_ac[r] * inv; D.cam.t[r] = C.proj_t[r] * inv + 16384.0;
-            const double ray = fabs(D.cam.au[r]) * C.proj_w + fabs(D.cam.av[r]) * C.proj_h + fabs(D.cam.ac[r]);
+            double ray = 0.0;
+            for (int corner = 0; corner < 4; ++corner)
+                ray = std::max(ray, fabs(D.cam.au[r] * ((corner & 1) ? C.proj_w - 1 : 0) + D.cam.av[r] * ((corner & 2) ? C.proj_h - 1 : 0) + D.cam.ac[r]));
             reach = std::max(reach, ray * ctx->voxel_max_depth + fabs(C.proj_t[r] * inv));
         }
         if (!(reach < 16383.0))

@@ -49,7 +49,7 @@ def main() -> None:
         ctx.set_stream(torch.cuda.current_stream().cuda_stream)
         be = Backend("gpu", ctx)
     rng = np.random.default_rng(args.seed)
-    t0, n_vox, n_col, records = time.time(), 0, 0, 0
+    t0, n_vox, n_col, records, n_refused = time.time(), 0, 0, 0, 0
     top = 160 if args.emu else 900
     for i in range(args.cases):
         kind = i % 3
@@ -67,10 +67,14 @@ def main() -> None:
                 cases.check_backproject_colour(be, 44, w, h, int(rng.integers(16, 2 * top)), int(rng.integers(8, top)), n=int(rng.integers(1, 3)), seed=args.seed * 1000 + i)
                 cases.check_depth_stats(be, w, h, n=2, seed=args.seed * 1000 + i)
                 n_col += 1
+        except ValueError as e:  # a 2 cm grid, no depth cap, a wide camera far from the origin: the library says the 15-bit fields do not reach
+            if "key fields" not in str(e):
+                raise
+            n_refused += 1
         except AssertionError as e:
             print(f"case {i} (kind {kind}): MISMATCH {e}", flush=True)
             raise SystemExit(1)
-    print(f"{n_vox} voxel-cloud cases ({records} records, every set exact), {n_col} fused colour + depth-stats cases: all match the oracle, {time.time() - t0:.0f} s")
+    print(f"{n_vox} voxel-cloud cases ({records} records, every set exact), {n_col} fused colour + depth-stats cases: all match the oracle ({n_refused} grids refused as out of key range), {time.time() - t0:.0f} s")
 
 
 if __name__ == "__main__":
