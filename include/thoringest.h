@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define TI_ABI_VERSION 1
+#define TI_ABI_VERSION 2 /* round 2: voxel clouds, the exchange stream, peer inboxes, fused colour, depth statistics */
 #define TI_MAX_CAMERAS 64 /* calibration slots per context                     */
 #define TI_MAX_STREAMS 32 /* streams of one kind per ti_ingest() call          */
 #define TI_MAX_DIM 8190   /* max source width/height of a remap slot (the driver's largest sensor mode is 4224 x 3136,

@@ -13,7 +13,7 @@ import ctypes as C
 from pathlib import Path
 
 LIB_PATH = Path(__file__).resolve().parent.parent / "libthoringest.so"
-ABI_VERSION = 1
+ABI_VERSION = 2
 INBOX_HEADER_BYTES = 128  # TI_INBOX_HEADER_BYTES
 
 TI_OK, TI_EINVAL, TI_ECUDA, TI_ENCCL, TI_ESTATE, TI_ENOMEM = range(6)
