@@ -138,7 +138,8 @@ int ti_upload_projection(ti_ctx* ctx, int camera, int width, int height, const d
  * per tile, out[3] = exception entries per (tile, warp) of the pair-window kernel.
  * BGR8 -> RGB8: out[4] = 5 (3-channel window kernel) or 1 (generic), out[5] = source rows staged per tile.
  * out[6] = output pixels of the pair-window kernel repaired by the per-pixel pass after it (a (tile, warp) holds 32 exceptions;
- * strongly bent maps - fisheye - have a few more), out[7] reserved (0). */
+ * strongly bent maps - fisheye - have a few more), out[7] = bytes per staged source row of the pair-window kernel (192, or
+ * 320 for maps whose tiles span more source pixels, e.g. a 2 x downscale). */
 int ti_rectify_plan(ti_ctx* ctx, int camera, int32_t out[8]);
 
 /* u8 dst_h x dst_w mask of slot `camera`: 1 where all four bilinear taps are inside the

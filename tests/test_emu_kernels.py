@@ -73,6 +73,21 @@ def test_rectify_odd_output_width_on_fast_kernels(emu_backend):
     cases.check_rectify(emu_backend, 7, xx * 0.8 + 1.5, yy * 1.2 + 0.25, "mono8", "mono8", 112, 60)
 
 
+def test_rectify_downscale_runs_the_wide_pitch_kernel(emu_backend):
+    """A 2 x downscale map (the output_resolution of config/slam_config.yaml:7,26 done on the host): 128 output pixels sample 256
+    source pixels, more than the 192-byte rows of the standard boxes - the slot plans the pair-window kernel with 320-byte rows."""
+    yy, xx = np.mgrid[0:64, 0:160].astype(np.float32)
+    mx, my = (xx * 2.0 + 0.25 + 0.004 * yy).astype(np.float32), (yy * 2.0 + 0.75 - 0.003 * xx).astype(np.float32)
+    emu_backend.ctx.upload_rectify_map(15, mx, my, (320, 128))
+    plan = emu_backend.ctx.rectify_plan(15)
+    assert plan["variant"] == 4 and plan["pitch"] == 320, plan
+    cases.check_rectify(emu_backend, 15, mx, my, "mono8", "mono8", 320, 128, n=2, expect_variant=4)
+    cases.check_rectify(emu_backend, 15, mx, my, "nv12", "mono8", 320, 128, n=2, expect_variant=4)
+    cases.check_rectify(emu_backend, 15, mx, my, "bgr8", "mono8", 320, 128, n=1, expect_variant=4)
+    cases.check_rectify(emu_backend, 15, mx, my, "bgr8", "rgb8", 320, 128, n=2, expect_variant=4)  # asserts the 3-channel window kernel (1024-byte rows)
+    cases.check_rectify(emu_backend, 15, mx, my, "nv12", "rgb8", 320, 128, n=1, expect_variant=4)
+
+
 def test_rectify_beyond_2046_pixels(emu_backend):
     """Source coordinates above the 11-bit limit of round 1's packed LUT (the driver lists 4000 x 3000 and 4224 x 3136 sensor
     modes, luxonis.py:36-44): a 2560-wide strip, mono and colour."""

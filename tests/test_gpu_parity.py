@@ -89,7 +89,11 @@ def test_rectify_resize_ragged_outside(gpu_backend):
     yy, xx = np.mgrid[0:51, 0:99].astype(np.float32)
     cases.check_rectify(gpu_backend, 2, xx * 1.1 + 0.3, yy * 1.05 + 0.7, "mono8", "mono8", 110, 60)
     yy, xx = np.mgrid[0:400, 0:640].astype(np.float32)
-    cases.check_rectify(gpu_backend, 3, xx * 2.0 + 0.25, yy * 2.0 + 0.75, "mono8", "mono8", 1280, 800)  # 2x downscale (slam_config.yaml:7)
+    cases.check_rectify(gpu_backend, 3, xx * 2.0 + 0.25, yy * 2.0 + 0.75, "mono8", "mono8", 1280, 800, expect_variant=4)  # 2x downscale (slam_config.yaml:7)
+    assert gpu_backend.ctx.rectify_plan(3)["pitch"] == 320, "the 2 x downscale map must run the wide-pitch pair-window kernel"
+    cases.check_rectify(gpu_backend, 3, xx * 2.0 + 0.25, yy * 2.0 + 0.75, "bgr8", "rgb8", 1280, 800, n=2, expect_variant=4)  # colour: 1024-byte rows
+    yy, xx = np.mgrid[0:600, 0:960].astype(np.float32)
+    cases.check_rectify(gpu_backend, 5, xx * 2.0 + 0.6, yy * 2.0 + 0.3, "bgr8", "rgb8", 1920, 1200, n=2, expect_variant=4)  # the LR colour stereo stream, halved
     mx = np.full((32, 128), -50.0, np.float32)
     cases.check_rectify(gpu_backend, 4, mx, mx.copy(), "mono8", "mono8", 128, 32)
 

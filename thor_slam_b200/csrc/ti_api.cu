@@ -380,7 +380,7 @@ int ti_rectify_plan(ti_ctx* ctx, int camera, int32_t out[8]) {
         if (C.has_c3) { out[4] = 5; out[5] = C.rows5_alloc; }
     }
     if (ctx->mono_variant == 4 && C.has_pair[th4]) {
-        out[0] = 4; out[1] = P4_TILE_HEIGHTS[th4]; out[2] = C.rows4_alloc[th4]; out[3] = C.exc4_per_warp[th4]; out[6] = C.n_over4[th4];
+        out[0] = 4; out[1] = P4_TILE_HEIGHTS[th4]; out[2] = C.rows4_alloc[th4]; out[3] = C.exc4_per_warp[th4]; out[6] = C.n_over4[th4]; out[7] = C.pitch4[th4];
     } else if (ctx->mono_variant >= 3 && C.has_tma_mono[thk]) {
         out[0] = 3; out[1] = M3_TILE_HEIGHTS[thk]; out[2] = C.rows3_alloc[thk];
     } else if (ctx->mono_variant >= 2 && C.has_fast_mono) {

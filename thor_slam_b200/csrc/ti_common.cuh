@@ -104,6 +104,8 @@ constexpr int P4_N_TH = 3;
 constexpr int P4_TILE_HEIGHTS[P4_N_TH] = {16, 32, 24};
 inline int p4_th_index(int th) { return th == 16 ? 0 : (th == 24 ? 2 : 1); }
 constexpr int P4_PITCH = 192;        // = 16 banks (mod 32): a lane group crossing into the next source row stays conflict-free
+constexpr int P4_PITCH_WIDE = 320;   // same residue; for maps whose 128-pixel tiles span up to 320 source bytes (a 2 x downscale:
+                                     // config/slam_config.yaml's output_resolution done on the host instead of on the camera)
 constexpr int P4_MAX_ROWS = 96;
 constexpr int P4_CONSUMER_WARPS = 8;
 constexpr int P4_THREADS = (P4_CONSUMER_WARPS + 1) * 32;  // consumers + TMA issuer
@@ -118,6 +120,7 @@ constexpr int P4_MAX_EXC = 32;         // exception entries per (tile, warp): on
 constexpr int C3_TW = 128;
 constexpr int C3_TH = 16;
 constexpr int C3_PITCH = 512;          // bytes per staged source row (TMA box of 128 u32 elements)
+constexpr int C3_PITCH_WIDE = 1024;    // 256 u32 elements, the most a TMA box dimension holds: maps that sample up to ~2.5 x as many source pixels
 constexpr int C3_MAX_ROWS = 64;
 constexpr int C3_CONSUMER_WARPS = 8;
 constexpr int C3_THREADS = (C3_CONSUMER_WARPS + 1) * 32;
@@ -131,13 +134,14 @@ struct CameraSlot {
     bool c3_tried = false, has_c3 = false;          // built on the first BGR8 -> RGB8 rectify of the slot
     uint32_t* d_lut5 = nullptr;                     // tiles * C3_TH * C3_LUT_ROW_WORDS
     TileBox2* d_boxes5 = nullptr;                   // c0 in BYTES of the BGR row (multiple of 16)
-    int tiles5_x = 0, tiles5_y = 0, rows5_alloc = 0;
+    int tiles5_x = 0, tiles5_y = 0, rows5_alloc = 0, pitch5 = 0;
     bool has_pair[P4_N_TH] = {false, false, false};              // tile height 16, 32, 24
     uint32_t* d_lut4[P4_N_TH] = {nullptr, nullptr, nullptr};     // tiles * TH * P4_LUT_ROW_WORDS
     TileBox2* d_boxes4[P4_N_TH] = {nullptr, nullptr, nullptr};
     uint32_t* d_exc4[P4_N_TH] = {nullptr, nullptr, nullptr};     // tiles * P4_CONSUMER_WARPS * exc4_per_warp entries of 4 words
     int tiles4_x[P4_N_TH] = {0, 0, 0}, tiles4_y[P4_N_TH] = {0, 0, 0};
     int rows4_alloc[P4_N_TH] = {0, 0, 0};
+    int pitch4[P4_N_TH] = {0, 0, 0};                             // P4_PITCH or P4_PITCH_WIDE: bytes per staged source row
     int exc4_per_warp[P4_N_TH] = {0, 0, 0};
     uint32_t* d_over4[P4_N_TH] = {nullptr, nullptr, nullptr};    // output pixels whose (tile, warp) exception list was full
     int n_over4[P4_N_TH] = {0, 0, 0};

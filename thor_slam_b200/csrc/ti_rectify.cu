@@ -761,7 +761,8 @@ static int launch_rectify_direct(ti_ctx* ctx, const RectifyJob* jobs_in, int n_j
     Rect2Params P2{};       // fast mono launch (v2: thread-staged)
     Rect3Params PT{};       // fast mono launch (v3: TMA-pipelined)
     Rect4Params PP{};       // fast mono launch (v4: pair windows)
-    Rect5Params PC{};       // fast 3-channel launch (BGR8 -> RGB8 windows)
+    Rect4Params PW{};       // the same for slots with wide source boxes (P4_PITCH_WIDE)
+    Rect5Params PC{}, PCW{};  // fast 3-channel launches (BGR8 -> RGB8 windows): standard and wide source boxes
     std::vector<DirectJob> pair_overflow;  // pair-window jobs whose slot has an overflow list (mode = camera slot)
     const int thk = m3_th_index(ctx->tma_tile_h);
     const int th4 = p4_th_index(ctx->tma_tile_h);
@@ -787,43 +788,52 @@ static int launch_rectify_direct(ti_ctx* ctx, const RectifyJob* jobs_in, int n_j
         const bool tma_ok = mode == DM_MONO && C.has_tma_mono[thk] && ((uintptr_t)J.src % 16 == 0) && (J.src_stride % 16 == 0) &&
                             PT.n_jobs < MAX_RECT_JOBS && !ctx->force_generic_rectify && ctx->mono_variant >= 3;
         const bool pair_ok = mode == DM_MONO && C.has_pair[th4] && ((uintptr_t)J.src % 16 == 0) && (J.src_stride % 16 == 0) &&
-                             PP.n_jobs < MAX_PAIR_JOBS && !ctx->force_generic_rectify && ctx->mono_variant == 4;
+                             !ctx->force_generic_rectify && ctx->mono_variant == 4;
         if (mode == DM_BGR_TO_RGB && !ctx->force_generic_rectify && ctx->mono_variant == 4 && C.src_w % 16 == 0 &&
-            ((uintptr_t)J.src % 16 == 0) && (J.src_stride % 16 == 0) && PC.n_jobs < MAX_PAIR_JOBS) {
+            ((uintptr_t)J.src % 16 == 0) && (J.src_stride % 16 == 0)) {
             CameraSlot& CM = ctx->cams[J.camera];
             if (!CM.c3_tried) {
                 const int rc = build_c3_tables(ctx, CM);
                 if (rc != TI_OK) return rc;
             }
-            if (CM.has_c3) {
-                const int rc = tma_encode_3d(ctx, &PC.map[PC.n_jobs], J.src, 4, 3 * C.src_w / 4, C.src_h, n_batch, (uint64_t)3 * C.src_w,
-                                             J.src_stride, C3_PITCH / 4, CM.rows5_alloc);
+            Rect5Params& QC = CM.pitch5 == C3_PITCH_WIDE ? PCW : PC;  // jobs of a launch stage rows of one pitch
+            if (CM.has_c3 && QC.n_jobs < MAX_PAIR_JOBS) {
+                const int rc = tma_encode_3d(ctx, &QC.map[QC.n_jobs], J.src, 4, 3 * C.src_w / 4, C.src_h, n_batch, (uint64_t)3 * C.src_w,
+                                             J.src_stride, CM.pitch5 / 4, CM.rows5_alloc);
                 if (rc != TI_OK) return rc;
                 Rect5JobDev D{};
                 D.lut5 = CM.d_lut5; D.boxes5 = CM.d_boxes5; D.dst = J.dst; D.dst_stride = J.dst_stride;
                 D.dst_w = C.dst_w; D.dst_h = C.dst_h; D.rows_alloc = CM.rows5_alloc;
-                D.tile_begin = PC.tiles_per_set;
-                PC.tiles_per_set += (uint32_t)(CM.tiles5_x * CM.tiles5_y);
-                PC.rows_alloc_max = std::max(PC.rows_alloc_max, D.rows_alloc);
-                PC.job[PC.n_jobs++] = D;
+                D.tile_begin = QC.tiles_per_set;
+                QC.tiles_per_set += (uint32_t)(CM.tiles5_x * CM.tiles5_y);
+                QC.rows_alloc_max = std::max(QC.rows_alloc_max, D.rows_alloc);
+                QC.pitch = CM.pitch5;
+                QC.job[QC.n_jobs++] = D;
                 continue;
             }
         }
         if (pair_ok) {
-            const int rc = tma_encode_u8_3d(ctx, &PP.map[PP.n_jobs], J.src, C.src_w, C.src_h, n_batch, (uint64_t)C.src_w,
-                                            J.src_stride, P4_PITCH, C.rows4_alloc[th4]);
-            if (rc != TI_OK) return rc;
-            Rect4JobDev D{};
-            D.lut4 = C.d_lut4[th4]; D.boxes4 = C.d_boxes4[th4]; D.exc4 = C.d_exc4[th4]; D.dst = J.dst; D.dst_stride = J.dst_stride;
-            D.dst_w = C.dst_w; D.dst_h = C.dst_h; D.rows_alloc = C.rows4_alloc[th4]; D.exc_per_warp = C.exc4_per_warp[th4];
-            D.tile_begin = PP.tiles_per_set;
-            PP.tiles_per_set += (uint32_t)(C.tiles4_x[th4] * C.tiles4_y[th4]);
-            PP.rows_alloc_max = std::max(PP.rows_alloc_max, D.rows_alloc);
-            PP.exc_max = std::max(PP.exc_max, D.exc_per_warp);
-            PP.job[PP.n_jobs++] = D;
-            if (C.n_over4[th4] > 0)
-                pair_overflow.push_back(DirectJob{J.src, J.dst, J.src_stride, J.dst_stride, C.d_lut, lut_pitch, C.dst_w, C.dst_h, C.src_w, C.src_h, J.camera});
-            continue;
+            const bool wide_slot = C.pitch4[th4] == P4_PITCH_WIDE;
+            Rect4Params& Q = wide_slot ? PW : PP;  // jobs of a launch stage rows of one pitch
+            if (Q.n_jobs < MAX_PAIR_JOBS) {
+                const int rc = wide_slot ? tma_encode_3d(ctx, &Q.map[Q.n_jobs], J.src, 4, C.src_w / 4, C.src_h, n_batch, (uint64_t)C.src_w, J.src_stride,
+                                                         P4_PITCH_WIDE / 4, C.rows4_alloc[th4])
+                                         : tma_encode_u8_3d(ctx, &Q.map[Q.n_jobs], J.src, C.src_w, C.src_h, n_batch, (uint64_t)C.src_w, J.src_stride,
+                                                            P4_PITCH, C.rows4_alloc[th4]);
+                if (rc != TI_OK) return rc;
+                Rect4JobDev D{};
+                D.lut4 = C.d_lut4[th4]; D.boxes4 = C.d_boxes4[th4]; D.exc4 = C.d_exc4[th4]; D.dst = J.dst; D.dst_stride = J.dst_stride;
+                D.dst_w = C.dst_w; D.dst_h = C.dst_h; D.rows_alloc = C.rows4_alloc[th4]; D.exc_per_warp = C.exc4_per_warp[th4];
+                D.tile_begin = Q.tiles_per_set;
+                Q.tiles_per_set += (uint32_t)(C.tiles4_x[th4] * C.tiles4_y[th4]);
+                Q.rows_alloc_max = std::max(Q.rows_alloc_max, D.rows_alloc);
+                Q.exc_max = std::max(Q.exc_max, D.exc_per_warp);
+                Q.pitch = C.pitch4[th4];
+                Q.job[Q.n_jobs++] = D;
+                if (C.n_over4[th4] > 0)
+                    pair_overflow.push_back(DirectJob{J.src, J.dst, J.src_stride, J.dst_stride, C.d_lut, lut_pitch, C.dst_w, C.dst_h, C.src_w, C.src_h, J.camera});
+                continue;
+            }
         }
         if (tma_ok) {
             const int rc = tma_encode_u8_3d(ctx, &PT.map[PT.n_jobs], J.src, C.src_w, C.src_h, n_batch, (uint64_t)C.src_w,
@@ -869,13 +879,21 @@ static int launch_rectify_direct(ti_ctx* ctx, const RectifyJob* jobs_in, int n_j
     }
     P1.n_batch = P3.n_batch = P2.n_batch = PT.n_batch = n_batch;
     PT.debug = ctx->debug;
-    PP.n_batch = PC.n_batch = n_batch;
+    PP.n_batch = PW.n_batch = PC.n_batch = PCW.n_batch = n_batch;
     if (PC.n_jobs) {
         const int rc = launch_rectify_c3(ctx, PC);
         if (rc != TI_OK) return rc;
     }
-    if (PP.n_jobs) {
-        const int rc = launch_rectify_pair(ctx, PP, th4);
+    if (PCW.n_jobs) {
+        const int rc = launch_rectify_c3(ctx, PCW);
+        if (rc != TI_OK) return rc;
+    }
+    if (PW.n_jobs) {
+        const int rc = launch_rectify_pair(ctx, PW, th4);
+        if (rc != TI_OK) return rc;
+    }
+    if (PP.n_jobs || PW.n_jobs) {
+        const int rc = PP.n_jobs ? launch_rectify_pair(ctx, PP, th4) : TI_OK;
         if (rc != TI_OK) return rc;
         for (const DirectJob& D : pair_overflow) {  // slots with more exceptions in some (tile, warp) than its list holds
             const CameraSlot& C = ctx->cams[D.mode];  // mode carries the slot here

@@ -53,10 +53,11 @@ __device__ __forceinline__ void c3_st32(void* p, uint32_t v) {
 }
 
 // one output pixel: window word m (offset << 16 | 8 * byte alignment), weights wt / wb -> (R, G, B, .) in bytes 0..2
+template <int PITCH>
 __device__ __forceinline__ uint32_t c3_pixel(p4_addr_t base, uint32_t m, uint32_t wt, uint32_t wb) {
     const p4_addr_t a = base + (m >> 16);
     const uint32_t t0 = p4_lds<0>(a), t1 = p4_lds<4>(a), t2 = p4_lds<8>(a);
-    const uint32_t b0 = p4_lds<C3_PITCH>(a), b1 = p4_lds<C3_PITCH + 4>(a), b2 = p4_lds<C3_PITCH + 8>(a);
+    const uint32_t b0 = p4_lds<PITCH>(a), b1 = p4_lds<PITCH + 4>(a), b2 = p4_lds<PITCH + 8>(a);
     const uint32_t ta = __funnelshift_r(t0, t1, m), tb = __funnelshift_r(t1, t2, m);  // bytes B0 G0 R0 B1 | G1 R1 . .
     const uint32_t ba = __funnelshift_r(b0, b1, m), bb = __funnelshift_r(b1, b2, m);
     const uint32_t tx = __byte_perm(ta, tb, 0x4130), ty = __byte_perm(ta, tb, 0x5252);  // (B0 B1 G0 G1), (R0 R1 R0 R1)
@@ -68,11 +69,11 @@ __device__ __forceinline__ uint32_t c3_pixel(p4_addr_t base, uint32_t m, uint32_
 }
 
 // DSTW > 0: the destination row pitch in pixels is this compile-time constant (row stores become immediate offsets).
-template <int DSTW>
+template <int DSTW, int PITCH = C3_PITCH>
 __global__ void __launch_bounds__(C3_THREADS, 3) rectify_c3_kernel(const __grid_constant__ Rect5Params P) {
     TI_DYNAMIC_SMEM(uint8_t, smem);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const uint32_t stage_bytes = (uint32_t)P.rows_alloc_max * C3_PITCH;
+    const uint32_t stage_bytes = (uint32_t)P.rows_alloc_max * PITCH;
     const int S = P.stages;
     uint64_t* full = reinterpret_cast<uint64_t*>(smem);  // [S] box landed
     uint64_t* empty = full + C3_MAX_STAGES;              // [S] consumers done
@@ -121,7 +122,7 @@ __global__ void __launch_bounds__(C3_THREADS, 3) rectify_c3_kernel(const __grid_
             const Rect5JobDev& J = P.job[cur.j];
             const int c0 = (int16_t)(cur.box.x & 0xFFFF), y0 = (int16_t)(cur.box.x >> 16);
             const int rows = (int16_t)(cur.box.y >> 16);
-            const uint32_t tx = rows > 0 ? (uint32_t)J.rows_alloc * C3_PITCH : 0u;
+            const uint32_t tx = rows > 0 ? (uint32_t)J.rows_alloc * PITCH : 0u;
             bool lut_pending = k + 1 < units_mine;  // the next unit's LUT slice still has to be requested
             for (uint32_t f = 0; f < cur.nb; ++f) {
                 uint8_t* sb = stage0 + (size_t)s * stage_bytes;
@@ -181,7 +182,7 @@ __global__ void __launch_bounds__(C3_THREADS, 3) rectify_c3_kernel(const __grid_
                 uint32_t px[4];
                 __syncwarp();  // the previous row's reads of the transpose buffer are done
 #pragma unroll
-                for (int j = 0; j < 4; ++j) tbuf[32 * j + lane] = c3_pixel(base, mw[q][j], wt[q][j], wb[q][j]);  // pixel 32j + lane
+                for (int j = 0; j < 4; ++j) tbuf[32 * j + lane] = c3_pixel<PITCH>(base, mw[q][j], wt[q][j], wb[q][j]);  // pixel 32j + lane
                 __syncwarp();
                 {
                     const uint4 t4 = *reinterpret_cast<const uint4*>(tbuf + 4 * lane);  // pixels 4 lane .. 4 lane + 3
@@ -217,7 +218,7 @@ __global__ void __launch_bounds__(C3_THREADS, 3) rectify_c3_kernel(const __grid_
 // ---- launcher ------------------------------------------------------------------------------------
 int launch_rectify_c3(ti_ctx* ctx, Rect5Params& P) {
     if (P.n_jobs == 0 || P.n_batch <= 0) return TI_OK;
-    const size_t stage = (size_t)P.rows_alloc_max * C3_PITCH;
+    const size_t stage = (size_t)P.rows_alloc_max * P.pitch;
     int stages = std::max(2, std::min(ctx->stages4, C3_MAX_STAGES));
     const size_t tail = C3_LUT_BYTES + (size_t)C3_CONSUMER_WARPS * 512;  // LUT slice + per-warp transpose buffers
     // ... and never so deep that the SM has no shared memory left for anybody else: the exchange kernels (ti_push.cu: a 12 KB TMA
@@ -229,8 +230,9 @@ int launch_rectify_c3(ti_ctx* ctx, Rect5Params& P) {
     const size_t smem = 256 + (size_t)stages * stage + tail;
     if (smem > 220 * 1024) return fail(ctx, TI_EINVAL, "rectify (3-channel): source boxes of %d rows do not fit shared memory", P.rows_alloc_max);
     typedef void (*Kern)(const Rect5Params);
-    Kern kern = rectify_c3_kernel<0>;
-    {  // every job of the launch writes rows of the same common pitch: immediate row offsets
+    const bool wide = P.pitch == C3_PITCH_WIDE;
+    Kern kern = wide ? (Kern)rectify_c3_kernel<0, C3_PITCH_WIDE> : (Kern)rectify_c3_kernel<0>;
+    if (!wide) {  // every job of the launch writes rows of the same common pitch: immediate row offsets
         int dw = P.job[0].dst_w;
         for (int j = 1; j < P.n_jobs; ++j)
             if (P.job[j].dst_w != dw) dw = 0;
@@ -278,6 +280,21 @@ int build_c3_tables(ti_ctx* ctx, CameraSlot& C) {
     std::vector<TileBox2> boxes(n_tiles);
     std::vector<uint32_t> lut5(n_tiles * C3_TH * C3_LUT_ROW_WORDS, 0u);
     int rows_max = 0;
+    // bytes per staged source row: the widest tile decides (a 2 x downscale map needs the wide boxes)
+    int span_max = 0;
+    for (int ty = 0; ty < ty_n; ++ty)
+        for (int tx = 0; tx < tx_n; ++tx) {
+            int bx0 = 1 << 20, bx1 = -(1 << 20);
+            for (int v = ty * C3_TH; v < std::min(dst_h, (ty + 1) * C3_TH); ++v)
+                for (int u = tx * C3_TW; u < std::min(dst_w, (tx + 1) * C3_TW); ++u) {
+                    const lut_t e = entry(u, v);
+                    if (e == LUT_OUTSIDE) continue;
+                    bx0 = std::min(bx0, lut_x0(e)); bx1 = std::max(bx1, lut_x0(e) + 2);
+                }
+            if (bx1 > bx0) span_max = std::max(span_max, 3 * bx1 - ((3 * bx0) & ~15));
+        }
+    if (span_max > C3_PITCH_WIDE) return TI_OK;  // not eligible: generic kernels
+    const int pitch = span_max > C3_PITCH ? C3_PITCH_WIDE : C3_PITCH;
     for (int ty = 0; ty < ty_n; ++ty)
         for (int tx = 0; tx < tx_n; ++tx) {
             int bx0 = 1 << 20, by0 = 1 << 20, bx1 = -(1 << 20), by1 = -(1 << 20);
@@ -293,7 +310,7 @@ int build_c3_tables(ti_ctx* ctx, CameraSlot& C) {
             B = TileBox2{0, 0, 0, 0, (int16_t)(tx * C3_TW), (int16_t)(ty * C3_TH), 0, 0};
             if (bx1 <= bx0) continue;
             const int c0 = (3 * bx0) & ~15;  // byte column of the box start (floor to 16: -3 -> -16)
-            if (3 * bx1 - c0 > C3_PITCH || by1 - by0 > C3_MAX_ROWS) return TI_OK;  // not eligible: generic kernels
+            if (3 * bx1 - c0 > pitch || by1 - by0 > C3_MAX_ROWS) return TI_OK;  // not eligible: generic kernels
             B.c0 = (int16_t)c0; B.y0 = (int16_t)by0; B.nvec = (int16_t)((3 * bx1 - c0 + 15) / 16); B.rows = (int16_t)(by1 - by0);
             rows_max = std::max(rows_max, by1 - by0);
             for (int row = 0; row < C3_TH; ++row)
@@ -303,7 +320,7 @@ int build_c3_tables(ti_ctx* ctx, CameraSlot& C) {
                     const int x0 = lut_x0(e), y0 = lut_y0(e);
                     const uint32_t fx = lut_fx(e), fy = lut_fy(e);
                     const int bp = 3 * x0 - c0, wordx = bp & ~3, s = bp & 3;
-                    const uint32_t off = (uint32_t)((y0 - by0) * C3_PITCH + wordx);
+                    const uint32_t off = (uint32_t)((y0 - by0) * pitch + wordx);
                     // lane (lu % 32) blends pixel lu as its (lu / 32)-th: its eight LUT words are contiguous
                     uint32_t* w = lut5.data() + (tile * C3_TH + row) * C3_LUT_ROW_WORDS + (size_t)((lu & 31) * 4 + (lu >> 5)) * 2;
                     w[0] = (off << 16) | (uint32_t)(8 * s);
@@ -315,7 +332,7 @@ int build_c3_tables(ti_ctx* ctx, CameraSlot& C) {
     TI_CUDA(ctx, cudaMalloc(&C.d_boxes5, boxes.size() * sizeof(TileBox2)));
     TI_CUDA(ctx, cudaMemcpy(C.d_lut5, lut5.data(), lut5.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
     TI_CUDA(ctx, cudaMemcpy(C.d_boxes5, boxes.data(), boxes.size() * sizeof(TileBox2), cudaMemcpyHostToDevice));
-    C.tiles5_x = tx_n; C.tiles5_y = ty_n; C.rows5_alloc = rows_alloc;
+    C.tiles5_x = tx_n; C.tiles5_y = ty_n; C.rows5_alloc = rows_alloc; C.pitch5 = pitch;
     C.has_c3 = true;
     return TI_OK;
 }

@@ -26,7 +26,10 @@
 //    loop's stores by __syncwarp).  The cost per frame is flat - one short pass whatever the number
 //    of exceptions - so the eight warps that share a stage stay in step.  The 33rd and further exceptions of a
 //    (tile, warp) go to the slot's overflow list and are repaired after the kernel (rectify_points_kernel,
-//    ti_rectify.cu); only cameras with source boxes wider than P4_PITCH keep using the v3 / v2 kernels.
+//    ti_rectify.cu); only cameras with source boxes wider than P4_PITCH_WIDE keep using the v3 / v2 kernels.
+//  * Slots whose tiles span more than P4_PITCH source bytes (a 2 x downscale map: 128 output pixels sample 256 source pixels)
+//    run the PITCH = P4_PITCH_WIDE instantiation: the box is loaded as 80 32-bit elements per row (a TMA box dimension holds at
+//    most 256 elements), everything else is the same code.
 //  * The LUT is 6 bytes per output pixel in memory (per pair: the window word and one word per pixel
 //    holding 32-fx, fy, fx and the fx = fy = 0 flag); a tile's 24 KB slice is prefetched into shared
 //    memory by a 1-D bulk copy one unit ahead (unit = tile x up to frames_per_unit frames of the
@@ -59,10 +62,11 @@ __device__ __forceinline__ P4Unit p4_unit(const Rect4Params& P, uint32_t k) {
     return U;
 }
 
+template <int PITCH>
 __device__ __forceinline__ Taps p4_fetch(p4_addr_t base, uint32_t window_word) {
     const p4_addr_t a = base + (window_word >> 16);
     Taps T;
-    T.t0 = p4_lds<0>(a); T.t1 = p4_lds<4>(a); T.b0 = p4_lds<P4_PITCH>(a); T.b1 = p4_lds<P4_PITCH + 4>(a);
+    T.t0 = p4_lds<0>(a); T.t1 = p4_lds<4>(a); T.b0 = p4_lds<PITCH>(a); T.b1 = p4_lds<PITCH + 4>(a);
     return T;
 }
 
@@ -80,22 +84,22 @@ __device__ __forceinline__ void p4_blend(const Taps& T, const uint4& w, uint32_t
 // {window word, Wtop, Wbot, row * dst_w + column - 2 * lane}.  Its window is fetched ahead of the last row's blend so that the
 // latency of the dependent loads hides behind that row; its store follows the row loop's stores (__syncwarp).
 // DSTW > 0: the destination row pitch is this compile-time constant, so row q is an immediate offset from the lane's first-row pointer.
-template <int RPW, bool WHOLE, bool PREFETCH, bool HALF_LOADS = false, int DSTW = 0>
+template <int RPW, bool WHOLE, bool PREFETCH, bool HALF_LOADS = false, int DSTW = 0, int PITCH = P4_PITCH>
 __device__ __forceinline__ void p4_rows(const uint4 (&w0)[RPW], const uint4 (&w1)[RPW], const uint2 (&mw)[RPW], p4_addr_t base,
                                         uint8_t* dp, int dst_w, int live_rows, int live_cols, int lane, bool fixes, bool i_fix,
                                         p4_addr_t my_exc) {
     // HALF_LOADS (bring-up only, wrong pixels): pair 1 reuses pair 0's window - how much of the time is the window loads?
-    Taps A = p4_fetch(base, mw[0].x), B = HALF_LOADS ? A : p4_fetch(base, mw[0].y);
+    Taps A = p4_fetch<PITCH>(base, mw[0].x), B = HALF_LOADS ? A : p4_fetch<PITCH>(base, mw[0].y);
     uint8_t* const lane_dst = dp;  // this lane's first pixel of the warp's first row
     uint4 fe = make_uint4(0u, 0u, 0u, 0u);
     Taps X = A;
 #pragma unroll
     for (int q = 0; q < RPW; ++q) {
         Taps An = A, Bn = B;
-        if (PREFETCH && q + 1 < RPW) { An = p4_fetch(base, mw[q + 1].x); Bn = HALF_LOADS ? An : p4_fetch(base, mw[q + 1].y); }
+        if (PREFETCH && q + 1 < RPW) { An = p4_fetch<PITCH>(base, mw[q + 1].x); Bn = HALF_LOADS ? An : p4_fetch<PITCH>(base, mw[q + 1].y); }
         if (q == RPW - 1 && fixes && i_fix) {
             fe = p4_lds128(my_exc);
-            X = p4_fetch(base, fe.x);
+            X = p4_fetch<PITCH>(base, fe.x);
         }
         uint32_t ra0, rb0, ra1, rb1;
         p4_blend(A, w0[q], mw[q].x, ra0, rb0);
@@ -116,7 +120,7 @@ __device__ __forceinline__ void p4_rows(const uint4 (&w0)[RPW], const uint4 (&w1
         }
         if (!(WHOLE && DSTW > 0)) dp += dst_w;
         if (PREFETCH) { A = An; B = Bn; }
-        else if (q + 1 < RPW) { A = p4_fetch(base, mw[q + 1].x); B = p4_fetch(base, mw[q + 1].y); }
+        else if (q + 1 < RPW) { A = p4_fetch<PITCH>(base, mw[q + 1].x); B = p4_fetch<PITCH>(base, mw[q + 1].y); }
     }
     if (fixes) {
         __syncwarp();  // the fix-up stores land behind the row loop's stores to the same bytes
@@ -128,13 +132,13 @@ __device__ __forceinline__ void p4_rows(const uint4 (&w0)[RPW], const uint4 (&w1
     }
 }
 
-template <int TH, bool DEBUG, int DSTW = 0>
+template <int TH, bool DEBUG, int DSTW = 0, int PITCH = P4_PITCH>
 __global__ void __launch_bounds__(P4_THREADS, TH == 32 ? 3 : 4) rectify_mono_pair_kernel(const __grid_constant__ Rect4Params P) {
     TI_DYNAMIC_SMEM(uint8_t, smem);
     constexpr int RPW = TH / P4_CONSUMER_WARPS;  // tile rows per consumer warp
     constexpr uint32_t LUT_BYTES = (uint32_t)TH * P4_LUT_ROW_WORDS * 4u;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const uint32_t stage_bytes = (uint32_t)P.rows_alloc_max * P4_PITCH;  // rows_alloc is a multiple of 8: 128-byte granular
+    const uint32_t stage_bytes = (uint32_t)P.rows_alloc_max * PITCH;  // rows_alloc is a multiple of 8: 128-byte granular
     const uint32_t exc_buf_bytes = (uint32_t)P.exc_max * (P4_CONSUMER_WARPS * 16);
     const int S = P.stages;
     uint64_t* full = reinterpret_cast<uint64_t*>(smem);  // [S] box landed
@@ -187,13 +191,13 @@ __global__ void __launch_bounds__(P4_THREADS, TH == 32 ? 3 : 4) rectify_mono_pai
             const Rect4JobDev& J = P.job[cur.j];
             const int c0 = (int16_t)(cur.box.x & 0xFFFF), y0 = (int16_t)(cur.box.x >> 16);
             const int rows = (int16_t)(cur.box.y >> 16);
-            const uint32_t tx = rows > 0 ? (uint32_t)J.rows_alloc * P4_PITCH : 0u;
+            const uint32_t tx = rows > 0 ? (uint32_t)J.rows_alloc * PITCH : 0u;
             bool lut_pending = k + 1 < units_mine;  // the next unit's LUT slice still has to be requested
             for (uint32_t f = 0; f < cur.nb; ++f) {
                 const uint32_t b = cur.b0 + f;
                 uint8_t* sb = stage0 + (size_t)s * stage_bytes;
                 mbar_wait_sleep(empty + s, phase, 300);  // consumers have released the stage's previous item
-                if (rows > 0 && !(DEBUG && (P.debug & 2))) tma_load_3d(sb, &P.map[cur.j], c0, y0, (int)b, full + s);  // one box: P4_PITCH x rows_alloc bytes
+                if (rows > 0 && !(DEBUG && (P.debug & 2))) tma_load_3d(sb, &P.map[cur.j], PITCH == P4_PITCH ? c0 : c0 / 4, y0, (int)b, full + s);  // one box: PITCH x rows_alloc bytes (wide: 32-bit elements)
                 mbar_arrive_expect_tx(full + s, (DEBUG && (P.debug & 2)) ? 0u : tx);
                 if (++s == S) { s = 0; phase ^= 1u; }
                 // the LUT buffer is free again once all consumer warps hold unit k in registers
@@ -253,9 +257,9 @@ __global__ void __launch_bounds__(P4_THREADS, TH == 32 ? 3 : 4) rectify_mono_pai
         for (uint32_t f = 0; f < U.nb; ++f) {
             p4_wait(bar, phase);
             if (!skip_blend) {
-                if (DEBUG && (P.debug & 8)) p4_rows<RPW, true, TH == 32, true>(w0, w1, mw, base, dp, dst_w, live_rows, live_cols, lane, warp_fixes, i_fix, my_exc);
-                else if (whole) p4_rows<RPW, true, TH == 32, false, DSTW>(w0, w1, mw, base, dp, dst_w, live_rows, live_cols, lane, warp_fixes, i_fix, my_exc);
-                else p4_rows<RPW, false, false>(w0, w1, mw, base, dp, dst_w, live_rows, live_cols, lane, warp_fixes, i_fix, my_exc);
+                if (DEBUG && (P.debug & 8)) p4_rows<RPW, true, TH == 32, true, 0, PITCH>(w0, w1, mw, base, dp, dst_w, live_rows, live_cols, lane, warp_fixes, i_fix, my_exc);
+                else if (whole) p4_rows<RPW, true, TH == 32, false, DSTW, PITCH>(w0, w1, mw, base, dp, dst_w, live_rows, live_cols, lane, warp_fixes, i_fix, my_exc);
+                else p4_rows<RPW, false, false, false, 0, PITCH>(w0, w1, mw, base, dp, dst_w, live_rows, live_cols, lane, warp_fixes, i_fix, my_exc);
             }
             p4_warp_arrive(bar + 64);
             dp += dst_stride;
@@ -269,15 +273,18 @@ __global__ void __launch_bounds__(P4_THREADS, TH == 32 ? 3 : 4) rectify_mono_pai
 int launch_rectify_pair(ti_ctx* ctx, Rect4Params& P, int th_index) {
     if (P.n_jobs == 0 || P.n_batch <= 0) return TI_OK;
     const int TH = P4_TILE_HEIGHTS[th_index];
-    const size_t stage = (size_t)P.rows_alloc_max * P4_PITCH;
+    const size_t stage = (size_t)P.rows_alloc_max * P.pitch;
     const size_t lut_bytes = (size_t)TH * P4_LUT_ROW_WORDS * 4 + 2 * (size_t)P.exc_max * (P4_CONSUMER_WARPS * 16);
     typedef void (*Kern)(const Rect4Params);
     static const Kern kernels[2][P4_N_TH] = {
         {rectify_mono_pair_kernel<16, false>, rectify_mono_pair_kernel<32, false>, rectify_mono_pair_kernel<24, false>},
         {rectify_mono_pair_kernel<16, true>, rectify_mono_pair_kernel<32, true>, rectify_mono_pair_kernel<24, true>}};
-    Kern kern = kernels[ctx->debug ? 1 : 0][th_index];
+    static const Kern kernels_wide[P4_N_TH] = {rectify_mono_pair_kernel<16, false, 0, P4_PITCH_WIDE>, rectify_mono_pair_kernel<32, false, 0, P4_PITCH_WIDE>,
+                                               rectify_mono_pair_kernel<24, false, 0, P4_PITCH_WIDE>};
+    const bool wide = P.pitch == P4_PITCH_WIDE;
+    Kern kern = wide ? kernels_wide[th_index] : kernels[ctx->debug ? 1 : 0][th_index];
     // every job of the launch writes rows of the same common pitch: use the kernel whose row stores are immediate offsets
-    if (!ctx->debug && TH == 32) {
+    if (!ctx->debug && TH == 32 && !wide) {
         int dw = P.job[0].dst_w;
         for (int j = 1; j < P.n_jobs; ++j)
             if (P.job[j].dst_w != dw) dw = 0;
@@ -366,7 +373,7 @@ int build_pair_tables(ti_ctx* ctx, CameraSlot& C, const std::vector<lut_t>& lut,
         std::vector<TileBox2> boxes(n_tiles);
         auto entry = [&](int u, int v) -> lut_t { return (u < dst_w && v < dst_h) ? lut[(size_t)v * lut_pitch + u] : LUT_OUTSIDE; };
         bool ok = true;
-        int rows_max = 0;
+        int rows_max = 0, span_max = 0;
         for (int ty = 0; ty < ty_n && ok; ++ty)
             for (int tx = 0; tx < tx_n && ok; ++tx) {
                 int bx0 = 1 << 20, by0 = 1 << 20, bx1 = -(1 << 20), by1 = -(1 << 20);
@@ -382,12 +389,14 @@ int build_pair_tables(ti_ctx* ctx, CameraSlot& C, const std::vector<lut_t>& lut,
                 // floor to 16 (-1 -> -16): a TMA box must start on a 16-byte boundary of global memory - probed on the B200:
                 // starts shifted by 1, 4 or 7 bytes end in "an illegal instruction was encountered"
                 const int c0 = bx0 & ~15;
-                if (bx1 - c0 > P4_PITCH || by1 - by0 > P4_MAX_ROWS) { ok = false; break; }
+                if (bx1 - c0 > P4_PITCH_WIDE || by1 - by0 > P4_MAX_ROWS) { ok = false; break; }
+                span_max = std::max(span_max, bx1 - c0);
                 B.c0 = (int16_t)c0; B.y0 = (int16_t)by0; B.nvec = (int16_t)((bx1 - c0 + 15) / 16); B.rows = (int16_t)(by1 - by0);
                 rows_max = std::max(rows_max, by1 - by0);
             }
         if (!ok) continue;
         const int rows_alloc = std::max(8, (rows_max + 7) / 8 * 8);
+        const int pitch = span_max > P4_PITCH ? P4_PITCH_WIDE : P4_PITCH;  // staged bytes per source row
 
         std::vector<uint32_t> lut4(n_tiles * TH * P4_LUT_ROW_WORDS, 0u);
         std::vector<std::vector<uint32_t>> exc(n_tiles * P4_CONSUMER_WARPS);  // 4 words per entry
@@ -411,7 +420,7 @@ int build_pair_tables(ti_ctx* ctx, CameraSlot& C, const std::vector<lut_t>& lut,
                             if (!a.in && !b.in) continue;
                             const Px& anchor = a.in ? a : b;  // the window is placed for pixel a (for b when a has no tap inside)
                             const int wordx = (anchor.x0 - B.c0) & ~3;
-                            const uint32_t off = (uint32_t)((anchor.y0 - B.y0) * P4_PITCH + wordx);
+                            const uint32_t off = (uint32_t)((anchor.y0 - B.y0) * pitch + wordx);
                             const uint32_t sa = a.in ? (uint32_t)(a.x0 - B.c0 - wordx) : 0u;
                             const int sb_rel = b.in ? b.x0 - B.c0 - wordx : (int)sa;
                             const bool b_fits = !b.in || (b.y0 == anchor.y0 && sb_rel >= 0 && sb_rel <= 6);
@@ -431,7 +440,7 @@ int build_pair_tables(ti_ctx* ctx, CameraSlot& C, const std::vector<lut_t>& lut,
                                     continue;
                                 }
                                 const int wordb = (b.x0 - B.c0) & ~3;
-                                const uint32_t offb = (uint32_t)((b.y0 - B.y0) * P4_PITCH + wordb);
+                                const uint32_t offb = (uint32_t)((b.y0 - B.y0) * pitch + wordb);
                                 const uint32_t sb = (uint32_t)(b.x0 - B.c0 - wordb);
                                 m = (off << 16) | sa | ((sa + 1) << 4) | (sa << 8) | ((sa + 1) << 12);  // b reads a's bytes: harmless
                                 uint32_t wt, wb;
@@ -465,7 +474,7 @@ int build_pair_tables(ti_ctx* ctx, CameraSlot& C, const std::vector<lut_t>& lut,
             TI_CUDA(ctx, cudaMemcpy(C.d_over4[k], over.data(), over.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
         }
         C.n_over4[k] = (int)over.size();
-        C.tiles4_x[k] = tx_n; C.tiles4_y[k] = ty_n; C.rows4_alloc[k] = rows_alloc; C.exc4_per_warp[k] = epw;
+        C.tiles4_x[k] = tx_n; C.tiles4_y[k] = ty_n; C.rows4_alloc[k] = rows_alloc; C.pitch4[k] = pitch; C.exc4_per_warp[k] = epw;
         C.has_pair[k] = true;
     }
     return TI_OK;

@@ -28,6 +28,7 @@ struct Rect4Params {
     int n_batch;
     int frames_per_unit;
     int rows_alloc_max;  // launch-wide stage geometry
+    int pitch;           // P4_PITCH or P4_PITCH_WIDE: every job of a launch stages rows of this pitch
     int exc_max;         // largest exc_per_warp of the launch
     int stages;
     int debug;           // bring-up switches (TI_OPT_DEBUG): 1 = consumers skip the blend, 2 = issuer skips the loads; 0 in production
@@ -55,6 +56,7 @@ struct Rect5Params {
     int n_batch;
     int frames_per_unit;
     int rows_alloc_max;
+    int pitch;  // C3_PITCH or C3_PITCH_WIDE
     int stages;
 };
 

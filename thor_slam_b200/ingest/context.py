@@ -187,7 +187,7 @@ class IngestContext:
         out = (ctypes.c_int32 * 8)()
         self._check(self.lib.ti_rectify_plan(self._h, camera, out))
         return {"variant": int(out[0]), "tile_h": int(out[1]), "rows": int(out[2]), "exceptions_per_warp": int(out[3]),
-                "colour_variant": int(out[4]), "colour_rows": int(out[5]), "overflow_pixels": int(out[6])}
+                "colour_variant": int(out[4]), "colour_rows": int(out[5]), "overflow_pixels": int(out[6]), "pitch": int(out[7])}
 
     def get_valid_mask(self, camera: int, out: Any) -> Any:
         self._check(self.lib.ti_get_valid_mask(self._h, camera, self._ptr(out)))

@@ -106,6 +106,34 @@ def main() -> None:
         # plain device copy of the same bytes = what "1.0" looks like for this traffic
         report("torch copy_ (same bytes)", timeit(lambda: [o.copy_(f) for o, f in zip(outs, frames)], args.iters), 2 * px, px)
 
+    if not args.only or "downscale" in args.only:
+        # the 2 x downscale of config/slam_config.yaml's output_resolution done on the host: 1280x800 -> 640x400 (8 mono streams) and
+        # 1920x1200 -> 960x600 BGR -> RGB (4 colour streams); algorithmic bytes = source read + result written
+        yy, xx = np.mgrid[0:400, 0:640].astype(np.float32)
+        for cam in range(NS):
+            ctx.upload_rectify_map(24 + cam, xx * 2.0 + 0.25 + 0.002 * yy, yy * 2.0 + 0.75 - 0.002 * xx, (W, H))
+        print("plan", ctx.rectify_plan(24), flush=True)
+        douts = [torch.empty((B, 400, 640), dtype=torch.uint8, device="cuda") for _ in range(NS)]
+        dspecs = [StreamSpec(F.KIND_RECTIFY, frames[s], douts[s], F.MONO8, F.MONO8, camera=24 + s) for s in range(NS)]
+        report("rectify mono 1280x800 -> 640x400 (wide-pitch pair windows)", timeit(lambda: ctx.ingest(dspecs), args.iters), 1.25 * px, px)
+        ctx.set_option(ctx.OPT_MONO_VARIANT, 3)
+        report("  the same on the round-1 route (v3 / v2)", timeit(lambda: ctx.ingest(dspecs), args.iters), 1.25 * px, px)
+        ctx.set_option(ctx.OPT_MONO_VARIANT, 4)
+        CW, CH, NB, NC = 1920, 1200, max(2, B // 2), 4
+        yy, xx = np.mgrid[0:600, 0:960].astype(np.float32)
+        for cam in range(NC):
+            ctx.upload_rectify_map(32 + cam, xx * 2.0 + 0.6 + 0.002 * yy, yy * 2.0 + 0.3 - 0.002 * xx, (CW, CH))
+        print("plan", ctx.rectify_plan(32), flush=True)
+        cin = [torch.randint(0, 256, (NB, CH, CW, 3), dtype=torch.uint8, device="cuda") for _ in range(NC)]
+        cout = [torch.empty((NB, 600, 960, 3), dtype=torch.uint8, device="cuda") for _ in range(NC)]
+        cspecs = [StreamSpec(F.KIND_RECTIFY, cin[i], cout[i], F.BGR8, F.RGB8, camera=32 + i) for i in range(NC)]
+        cpx = NC * NB * CW * CH
+        report("rectify bgr8->rgb8 1920x1200 -> 960x600 (wide-pitch 3-channel windows)", timeit(lambda: ctx.ingest(cspecs), args.iters), 3.75 * cpx, cpx)
+        ctx.set_option(ctx.OPT_FORCE_GENERIC_RECTIFY, 1)
+        report("  the same on the round-1 route (generic tiled)", timeit(lambda: ctx.ingest(cspecs), max(3, args.iters // 4)), 3.75 * cpx, cpx)
+        ctx.set_option(ctx.OPT_FORCE_GENERIC_RECTIFY, 0)
+        del cin, cout, douts
+
     if not args.only or "colour" in args.only:
         CW, CH, NB, NC = 1920, 1200, max(2, B // 2), 4  # the long-range cameras' colour stereo streams (config 4)
         csrc = SyntheticCameraSource(SyntheticCameraConfig(name="lr0", resolution=(CW, CH), pixel_format="bgr8", pool=1, enable_rgbd=False))
