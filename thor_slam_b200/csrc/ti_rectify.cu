@@ -603,13 +603,28 @@ __global__ void __launch_bounds__(256) rectify_direct_kernel(DirectJob J, int n_
     }
 }
 
-// The overflow pixels of a pair-window slot (ti_rectify_pair.cu): one thread per listed pixel and frame, taps from global
-// memory through the generic LUT - the arithmetic of rectify_direct_kernel<DM_MONO>.
-__global__ void __launch_bounds__(256) rectify_points_kernel(DirectJob J, const uint32_t* __restrict__ pts, int n_pts, int n_batch) {
-    const uint64_t total = (uint64_t)n_pts * n_batch;
+// The overflow pixels of pair-window slots (ti_rectify_pair.cu): one thread per listed pixel and frame, taps from global
+// memory through the generic LUT - the arithmetic of rectify_direct_kernel<DM_MONO>.  ONE launch for all jobs of a call
+// (eight launches of a few thousand threads each cost a fisheye rig 40 us per call).
+constexpr int MAX_POINT_JOBS = 16;
+struct PointsParams {
+    DirectJob job[MAX_POINT_JOBS];
+    const uint32_t* pts[MAX_POINT_JOBS];
+    uint32_t begin[MAX_POINT_JOBS + 1];  // prefix sum of points per frame over the jobs
+    int n_jobs;
+    int n_batch;
+};
+
+__global__ void __launch_bounds__(256) rectify_points_kernel(const __grid_constant__ PointsParams P) {
+    const uint32_t per_frame = P.begin[P.n_jobs];
+    const uint64_t total = (uint64_t)per_frame * P.n_batch;
     for (uint64_t t = (uint64_t)blockIdx.x * 256 + threadIdx.x; t < total; t += (uint64_t)gridDim.x * 256) {
-        const uint64_t b = t / (uint32_t)n_pts;
-        const uint32_t p = pts[t - b * (uint32_t)n_pts];
+        const uint64_t b = t / per_frame;
+        const uint32_t r = (uint32_t)(t - b * per_frame);
+        int j = 0;
+        while (j + 1 < P.n_jobs && r >= P.begin[j + 1]) ++j;
+        const DirectJob& J = P.job[j];
+        const uint32_t p = P.pts[j][r - P.begin[j]];
         const int v = (int)(p / (uint32_t)J.dst_w), u = (int)(p - (uint32_t)v * J.dst_w);
         const lut_t ek = J.lut[(size_t)v * J.lut_pitch + u];
         uint8_t* dst = J.dst + b * J.dst_stride + p;
@@ -895,13 +910,20 @@ static int launch_rectify_direct(ti_ctx* ctx, const RectifyJob* jobs_in, int n_j
     if (PP.n_jobs || PW.n_jobs) {
         const int rc = PP.n_jobs ? launch_rectify_pair(ctx, PP, th4) : TI_OK;
         if (rc != TI_OK) return rc;
-        for (const DirectJob& D : pair_overflow) {  // slots with more exceptions in some (tile, warp) than its list holds
-            const CameraSlot& C = ctx->cams[D.mode];  // mode carries the slot here
-            DirectJob K = D;
-            K.mode = DM_MONO;
-            const uint64_t total = (uint64_t)C.n_over4[th4] * n_batch;
+        for (size_t i0 = 0; i0 < pair_overflow.size(); i0 += MAX_POINT_JOBS) {  // slots with more exceptions in some (tile, warp) than its list holds
+            PointsParams Q{};
+            for (size_t i = i0; i < std::min(pair_overflow.size(), i0 + MAX_POINT_JOBS); ++i) {
+                const CameraSlot& C = ctx->cams[pair_overflow[i].mode];  // mode carries the slot here
+                Q.job[Q.n_jobs] = pair_overflow[i];
+                Q.job[Q.n_jobs].mode = DM_MONO;
+                Q.pts[Q.n_jobs] = C.d_over4[th4];
+                Q.begin[Q.n_jobs + 1] = Q.begin[Q.n_jobs] + (uint32_t)C.n_over4[th4];
+                ++Q.n_jobs;
+            }
+            Q.n_batch = n_batch;
+            const uint64_t total = (uint64_t)Q.begin[Q.n_jobs] * n_batch;
             const int grid = (int)std::min<uint64_t>((total + 255) / 256, (uint64_t)ctx->sm_count * 8);
-            TI_LAUNCH(rectify_points_kernel, grid, 256, 0, ctx->stream, K, C.d_over4[th4], C.n_over4[th4], n_batch);
+            TI_LAUNCH(rectify_points_kernel, grid, 256, 0, ctx->stream, Q);
             TI_CHECK_LAUNCH(ctx);
         }
     }

@@ -119,6 +119,16 @@ def main() -> None:
         ctx.set_option(ctx.OPT_MONO_VARIANT, 3)
         report("  the same on the round-1 route (v3 / v2)", timeit(lambda: ctx.ingest(dspecs), args.iters), 1.25 * px, px)
         ctx.set_option(ctx.OPT_MONO_VARIANT, 4)
+        # every distortion model of the reference's CameraInfo rule (isaac_ros.py:370-383) at the headline shape
+        for model in ("fisheye4", "plumb_bob5", "none"):
+            fsrc = SyntheticCameraSource(SyntheticCameraConfig(name="f0", resolution=(W, H), pool=1, enable_rgbd=False, distortion=model, seed=11))
+            fmaps = stereo_rectify_maps(fsrc.get_intrinsics(), fsrc.get_extrinsics(), (W, H))
+            for cam in range(NS):
+                ctx.upload_rectify_map(40 + cam, *fmaps[cam % 2], (W, H))
+            fspecs = [StreamSpec(F.KIND_RECTIFY, frames[s], outs[s], F.MONO8, F.MONO8, camera=40 + s) for s in range(NS)]
+            pl = ctx.rectify_plan(40)
+            report(f"rectify mono 1280x800 {model}: variant {pl['variant']}, {pl['exceptions_per_warp']} exc/warp, {pl['overflow_pixels']} overflow px",
+                   timeit(lambda: ctx.ingest(fspecs), args.iters), 2 * px, px)
         CW, CH, NB, NC = 1920, 1200, max(2, B // 2), 4
         yy, xx = np.mgrid[0:600, 0:960].astype(np.float32)
         for cam in range(NC):
