@@ -421,31 +421,11 @@ def run_ours(args) -> None:
     got_e2e_frame = h_dst[(e2e_steps - 1) % 2][5][0].numpy().copy() if rank == 0 else None
 
     peak, peak_src = measured_peak()
-    configs = run_configs(args, ctx, sources, peak) if (world == 1 and not args.no_configs) else None
-    config5 = run_config5_exchange(args, ctx, sources, rank, world, barrier, peak) if (distributed and not args.no_configs) else None
     pcie = pcie_probe(rank, world, barrier) if not args.no_pcie else None
-    e2e_rig = None
-    if rank == 0 and world == 1 and not args.no_rig:
-        e2e_rig = run_e2e_rig(args)
+    configs = run_configs(args, ctx, sources, peak) if (world == 1 and not args.no_configs) else None
 
-    # ---- CPU baseline (rank 0, N = 1 only) ---------------------------------------------------------
-    cpu_baseline = None
-    if rank == 0 and world == 1 and not args.no_cpu:
-        import cv2
-
-        cv2.setNumThreads(os.cpu_count() or 1)
-        # the oracle runs only in this leg: it is the CPU baseline and, on the same frames, the checker of both GPU numbers
-        from oracle import rectify as orc
-
-        if not np.array_equal(got_value_frame, orc.remap_cv(pool_frames[3][1], maps[3][0], maps[3][1])):
-            raise SystemExit("bench: GPU output differs from cv2.remap - refusing to report a number")
-        if not np.array_equal(got_e2e_frame, orc.remap_cv(pool_frames[5][0], maps[5][0], maps[5][1])):
-            raise SystemExit("bench: e2e output differs from cv2.remap - refusing to report a number")
-        cps, done, secs = time_cpu(pool_frames, maps, args.cpu_budget, 4096)
-        cpu_baseline = {"value": cps, "unit": "frame-sets/s", "cores": cv2.getNumThreads(), "kind": "port",
-                        "sample": f"{done} frame sets of 8 x 1280x800 mono8 in {secs:.1f} s, cv2.remap INTER_LINEAR (OpenCV {cv2.__version__})"}
-
-    if rank == 0:
+    def headline(extra: dict) -> dict:
+        """The JSON line from what has been measured so far (used at the end, and by the watchdog below)."""
         algo_bytes = B * PX_PER_SET * ALGO_BYTES_PER_PX
         achieved = algo_bytes / (ms_per_step * 1e-3) / 1e9
         line = {
@@ -476,12 +456,60 @@ def run_ours(args) -> None:
                          "sustained_achieved": algo_bytes / (sustained["ms_per_step"] * 1e-3) / 1e9,
                          "sustained_frac": algo_bytes / (sustained["ms_per_step"] * 1e-3) / 1e9 / peak,
                          "note": "per-rank launch; duration = max-over-ranks ms_per_step (one launch per step)"},
-            "cpu_baseline": cpu_baseline,
+            "cpu_baseline": None,
             "sustained": sustained,
         }
-        for key, val in (("configs", configs), ("config5", config5), ("e2e_rig", e2e_rig), ("pcie", pcie)):
+        for key, val in extra.items():
             if val is not None:
                 line[key] = val
+        return line
+
+    # Config 5 with its exchange is the one part of this run in which ranks wait for one another on the device.  Whatever happens
+    # there - an exception on one rank, a peer that never answers - the line with everything measured so far still goes out:
+    # a watchdog prints it (rank 0) and ends the process, so the driver never waits for a number that exists already.
+    config5 = None
+    if distributed and not args.no_configs:
+        def bail(reason: str) -> None:
+            if rank == 0:
+                emit(headline({"pcie": pcie, "config5": {"error": reason}}))
+            os._exit(0)
+
+        watchdog = threading.Timer(args.c5_timeout, bail, args=(f"config 5 did not finish within {args.c5_timeout:.0f} s",))
+        watchdog.daemon = True
+        watchdog.start()
+        try:
+            config5 = run_config5_exchange(args, ctx, sources, rank, world, barrier, peak)
+        except SystemExit:
+            raise  # a parity failure: no number may be printed
+        except Exception as exc:  # noqa: BLE001 - anything else: keep the headline, say what happened
+            print(f"[bench] rank {rank}: config 5 failed: {exc!r}", file=sys.stderr, flush=True)
+            watchdog.cancel()
+            bail(f"rank {rank}: {exc!r}")
+        watchdog.cancel()
+    e2e_rig = None
+    if rank == 0 and world == 1 and not args.no_rig:
+        e2e_rig = run_e2e_rig(args)
+
+    # ---- CPU baseline (rank 0, N = 1 only) ---------------------------------------------------------
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        import cv2
+
+        cv2.setNumThreads(os.cpu_count() or 1)
+        # the oracle runs only in this leg: it is the CPU baseline and, on the same frames, the checker of both GPU numbers
+        from oracle import rectify as orc
+
+        if not np.array_equal(got_value_frame, orc.remap_cv(pool_frames[3][1], maps[3][0], maps[3][1])):
+            raise SystemExit("bench: GPU output differs from cv2.remap - refusing to report a number")
+        if not np.array_equal(got_e2e_frame, orc.remap_cv(pool_frames[5][0], maps[5][0], maps[5][1])):
+            raise SystemExit("bench: e2e output differs from cv2.remap - refusing to report a number")
+        cps, done, secs = time_cpu(pool_frames, maps, args.cpu_budget, 4096)
+        cpu_baseline = {"value": cps, "unit": "frame-sets/s", "cores": cv2.getNumThreads(), "kind": "port",
+                        "sample": f"{done} frame sets of 8 x 1280x800 mono8 in {secs:.1f} s, cv2.remap INTER_LINEAR (OpenCV {cv2.__version__})"}
+
+    if rank == 0:
+        line = headline({"configs": configs, "config5": config5, "e2e_rig": e2e_rig, "pcie": pcie})
+        line["cpu_baseline"] = cpu_baseline
         emit(line)
     ctx.close()
     if distributed:
@@ -678,6 +706,8 @@ def run_config5_exchange(args, ctx, sources, rank: int, world: int, barrier, pea
 
     from thor_slam_b200.ingest.distributed import CloudGather, RecordExchange
 
+    if os.environ.get("TI_BENCH_FAIL_RANK") == str(rank):  # test hook of the watchdog in run_ours
+        raise RuntimeError("injected failure (TI_BENCH_FAIL_RANK)")
     stream = torch.cuda.current_stream()
     B = max(1, 64 // world) if args.strong else (args.c5_batch or max(1, args.batch // 4))
     steps = max(6, min(args.steps, 30))
@@ -970,6 +1000,7 @@ def main() -> None:
     ap.add_argument("--only-config5", action="store_true", dest="only_config5", help="N > 1: skip the e2e loops and the sustained loop (a second, --strong pass)")
     ap.add_argument("--c5-batch", type=int, default=0, dest="c5_batch", help="config 5: frame sets per rank per step (default batch / 4)")
     ap.add_argument("--c5-scenes", default="room,noise", dest="c5_scenes")
+    ap.add_argument("--c5-timeout", type=float, default=240.0, dest="c5_timeout", help="seconds after which an N > 1 run prints its line without config 5")
     ap.add_argument("--strong", action="store_true", help="config 5 at N > 1: 64 frame sets per step in total instead of 16 per rank")
     ap.add_argument("--sustain-s", type=float, default=1.5, dest="sustain_s", help="seconds of the sustained loop")
     ap.add_argument("--extras", action="store_true", help=argparse.SUPPRESS)  # round-1 flag, now the default

@@ -58,6 +58,21 @@ def test_rectify_two_pass_in_chunks(emu_backend, s, d):
         ctx.set_option(ctx.OPT_L2_SCRATCH_KB, 0)
 
 
+def test_more_two_pass_streams_than_one_conversion_launch_takes(emu_backend):
+    """34 BGR8 -> MONO8 rectify streams in one ti_ingest call: the gray pre-pass is chunked by TI_MAX_STREAMS (32) and the remap by
+    the 16 jobs a window-kernel launch takes - round 1 failed here with 'too many convert streams'."""
+    _, maps = cases.stereo_maps(192, 96)
+    ctx = emu_backend.ctx
+    ctx.upload_rectify_map(0, *maps[0], (192, 96))
+    rng = np.random.default_rng(3)
+    src = cases.make_batch(rng, "bgr8", 192, 96, 1)
+    want = cases.orc.remap_cv(np.ascontiguousarray(cases.oracle_convert(src[0], "bgr8", "mono8")), *maps[0])
+    outs = [np.zeros((1, 96, 192), np.uint8) for _ in range(34)]
+    ctx.ingest([StreamSpec(F.KIND_RECTIFY, src, o, F.BGR8, F.MONO8, camera=0) for o in outs])
+    for o in outs:
+        assert np.array_equal(o[0], want)
+
+
 def test_rectify_resize_and_ragged(emu_backend):
     yy, xx = np.mgrid[0:51, 0:99].astype(np.float32)
     cases.check_rectify(emu_backend, 2, xx * 1.1 + 0.3, yy * 1.05 + 0.7, "mono8", "mono8", 110, 60)  # direct kernel
