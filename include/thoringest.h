@@ -301,14 +301,15 @@ int ti_peer_free(ti_ctx* ctx, void* dev_ptr);
 #define TI_INBOX_HEADER_BYTES 128
 /* Root, once, before the handle is shared: zero the header (generation 0). */
 int ti_inbox_init(ti_ctx* ctx, void* inbox);
-/* Append records[0 .. *n_records) (DEVICE; *n_records is read on the device when the ingest stream reaches this point) to
+/* Append records[0 .. min(*n_records, records_capacity)) (DEVICE; *n_records is read on the device when the ingest stream reaches
+ * this point - a truncated ti_voxel_cloud list reports more records than records_capacity holds) to
  * `inbox` (own or peer-mapped) for generation `gen`: waits on the device until the inbox is at `gen`, reserves the slots with
  * one system-scope atomic, copies with peer stores, then reports this rank done.  Records past inbox_capacity are dropped
  * (the header's count still includes them).  Every rank's run starts 16-byte aligned: an odd list is padded with ONE zero
- * record (written at records[*n_records], so the buffer needs a spare slot; 0 is not a valid record) - consumers skip
- * zero records.  `records` may be reused after ti_gather_wait() / the fence taken behind this call. */
-int ti_cloud_push(ti_ctx* ctx, uint64_t* records, const uint32_t* n_records, void* inbox, uint64_t inbox_capacity,
-                  uint32_t gen);
+ * record (written into the list's spare slot; a list that fills its buffer to an odd count leaves its last record behind; 0 is
+ * not a valid record) - consumers skip zero records.  `records` may be reused after ti_gather_wait() / the fence taken behind this call. */
+int ti_cloud_push(ti_ctx* ctx, uint64_t* records, const uint32_t* n_records, uint64_t records_capacity, void* inbox,
+                  uint64_t inbox_capacity, uint32_t gen);
 /* Root: wait on the device until `world` ranks have reported done for the inbox's current generation, copy
  * min(count, inbox_capacity, dst_capacity) records to dst (DEVICE; dst_capacity 0: no copy - the caller consumed the inbox in
  * place while it was the other slot's turn), write status[0] = count, status[1] = error flag (DEVICE u32[2]; error != 0: a

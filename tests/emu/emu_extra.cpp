@@ -17,7 +17,7 @@ int ti_gather_records(ti_ctx* c, const uint64_t*, uint64_t*, const uint32_t*, in
 int ti_exchange_fence(ti_ctx* c, uint64_t*) { return ti::fail(c, TI_ENCCL, "no exchange stream in emulation"); }
 int ti_exchange_wait(ti_ctx* c, uint64_t, int) { return ti::fail(c, TI_ENCCL, "no exchange stream in emulation"); }
 int ti_inbox_init(ti_ctx* c, void*) { return ti::fail(c, TI_ECUDA, "no peer memory in emulation"); }
-int ti_cloud_push(ti_ctx* c, uint64_t*, const uint32_t*, void*, uint64_t, uint32_t) { return ti::fail(c, TI_ECUDA, "no peer memory in emulation"); }
+int ti_cloud_push(ti_ctx* c, uint64_t*, const uint32_t*, uint64_t, void*, uint64_t, uint32_t) { return ti::fail(c, TI_ECUDA, "no peer memory in emulation"); }
 int ti_inbox_take(ti_ctx* c, void*, uint64_t, uint32_t, uint64_t*, uint64_t, uint32_t*) { return ti::fail(c, TI_ECUDA, "no peer memory in emulation"); }
 int ti_nccl_barrier(ti_ctx* c) { return ti::fail(c, TI_ENCCL, "no NCCL in emulation"); }
 int ti_peer_alloc(ti_ctx* c, uint64_t, void**, void*) { return ti::fail(c, TI_ECUDA, "no peer memory in emulation"); }

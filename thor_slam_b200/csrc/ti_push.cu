@@ -54,7 +54,8 @@ __device__ __forceinline__ uint64_t now_ns() {
 }
 
 // words: [0] base, [1] n to copy, [2] blocks finished (self-resetting), [3] sticky error
-__global__ void push_reserve_kernel(InboxHdr* hdr, uint64_t* records, const uint32_t* n_local, uint32_t gen, uint64_t capacity, uint32_t* words, int debug) {
+__global__ void push_reserve_kernel(InboxHdr* hdr, uint64_t* records, const uint32_t* n_local, uint64_t records_capacity, uint32_t gen,
+                                    uint64_t capacity, uint32_t* words, int debug) {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     const uint64_t t0 = now_ns();
     while (ld_acquire_sys(&hdr->gen) != gen) {
@@ -68,7 +69,11 @@ __global__ void push_reserve_kernel(InboxHdr* hdr, uint64_t* records, const uint
     // Every rank reserves an EVEN number of slots, so every rank's run starts 16-byte aligned in the inbox (bulk copies need
     // that); an odd list is padded with one zero record - no voxel encodes as 0 (key fields are biased, |k| < 16383).
     uint32_t n = (debug & 16) ? 0u : *n_local;  // bring-up switch 16: the whole protocol, no payload
-    if (n & 1u) { records[n] = 0ull; ++n; }
+    if ((uint64_t)n > records_capacity) n = (uint32_t)records_capacity;  // a truncated list reports more than it holds (ti_voxel_cloud)
+    if (n & 1u) {
+        if ((uint64_t)n < records_capacity) { records[n] = 0ull; ++n; }  // the spare slot takes the pad
+        else --n;                                                         // a full, odd list: its last record stays behind
+    }
     const uint32_t base = atomicAdd_system(&hdr->n_records, n);
     words[0] = base;
     words[1] = (uint64_t)base >= capacity ? 0u : (uint32_t)min((unsigned long long)n, (unsigned long long)((capacity & ~1ull) - base));
@@ -220,7 +225,8 @@ int ti_inbox_init(ti_ctx* ctx, void* inbox) {
     return TI_OK;
 }
 
-int ti_cloud_push(ti_ctx* ctx, uint64_t* records, const uint32_t* n_records, void* inbox, uint64_t inbox_capacity, uint32_t gen) {
+int ti_cloud_push(ti_ctx* ctx, uint64_t* records, const uint32_t* n_records, uint64_t records_capacity, void* inbox, uint64_t inbox_capacity,
+                  uint32_t gen) {
     if (!ctx) return TI_EINVAL;
     if (!records || !n_records || !inbox) return fail(ctx, TI_EINVAL, "ti_cloud_push: null argument");
     if ((uintptr_t)records % 16 || (uintptr_t)inbox % 16) return fail(ctx, TI_EINVAL, "ti_cloud_push: buffers must be 16-byte aligned");
@@ -235,7 +241,7 @@ int ti_cloud_push(ti_ctx* ctx, uint64_t* records, const uint32_t* n_records, voi
         ctx->gather_pending = true;
         return TI_OK;
     }
-    push_reserve_kernel<<<1, 32, 0, ctx->s_comm>>>(hdr, records, n_records, gen, inbox_capacity, words, push_debug());
+    push_reserve_kernel<<<1, 32, 0, ctx->s_comm>>>(hdr, records, n_records, records_capacity, gen, inbox_capacity, words, push_debug());
     TI_CHECK_LAUNCH(ctx);
     if (ctx->push_tma) push_copy_tma_kernel<<<ctx->push_blocks > 0 ? ctx->push_blocks : ctx->sm_count, 32, 0, ctx->s_comm>>>(hdr, records, words);
     else push_copy_kernel<<<ctx->push_blocks > 0 ? ctx->push_blocks : 2 * ctx->sm_count, PUSH_THREADS, 0, ctx->s_comm>>>(hdr, records, words);

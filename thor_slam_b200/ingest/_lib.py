@@ -89,7 +89,7 @@ SIGNATURES: dict[str, tuple] = {
     "ti_exchange_wait": (C.c_int, [C.c_void_p, C.c_uint64, C.c_int]),
     "ti_nccl_barrier": (C.c_int, [C.c_void_p]),
     "ti_inbox_init": (C.c_int, [C.c_void_p, C.c_void_p]),
-    "ti_cloud_push": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32]),
+    "ti_cloud_push": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.c_uint32]),
     "ti_inbox_take": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, C.c_void_p, C.c_uint64, C.c_void_p]),
     "ti_peer_alloc": (C.c_int, [C.c_void_p, C.c_uint64, C.POINTER(C.c_void_p), C.c_void_p]),
     "ti_peer_open": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]),

@@ -371,7 +371,7 @@ class IngestContext:
 
     def cloud_push(self, records: Any, n_records: Any, inbox: int, inbox_capacity: int, gen: int) -> None:
         """Append a ``ti_voxel_cloud`` list to a (peer-mapped) inbox with peer stores on the exchange stream (``ti_cloud_push``)."""
-        self._check(self.lib.ti_cloud_push(self._h, self._ptr(records), self._ptr(n_records), C.c_void_p(inbox), int(inbox_capacity), int(gen)))
+        self._check(self.lib.ti_cloud_push(self._h, self._ptr(records), self._ptr(n_records), int(records.shape[0]), C.c_void_p(inbox), int(inbox_capacity), int(gen)))
 
     def inbox_take(self, inbox: int, inbox_capacity: int, world: int, dst: Any, status: Any) -> None:
         """Root: take one generation of an inbox into ``dst`` (u64/i64 [capacity]); ``status`` u32/i32 [2] = (count, error)."""
