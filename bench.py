@@ -290,6 +290,10 @@ def run_ours(args) -> None:
     ctx.set_stream(stream.cuda_stream)
 
     sources, maps = build_rig()
+    if os.environ.get("TI_BENCH_QUAD"):  # bring-up: the pair-window kernel's layout / exception capacity (TI_OPT_RECTIFY_QUAD)
+        ctx.set_option(ctx.OPT_RECTIFY_QUAD, int(os.environ["TI_BENCH_QUAD"]))
+    if os.environ.get("TI_BENCH_STAGES"):
+        ctx.set_option(ctx.OPT_STAGES, int(os.environ["TI_BENCH_STAGES"]))
     for cam, (mx, my) in enumerate(maps):
         ctx.upload_rectify_map(cam, mx, my, (W, H))
 

@@ -108,6 +108,7 @@ typedef enum ti_option {
     TI_OPT_LUT_PREFETCH = 8,          /* 1: consumers prefetch the next unit's LUT into a second register set (default 0) */
     TI_OPT_L2_SCRATCH_KB = 10,        /* two-pass rectify (BGR8 -> MONO8, NV12 -> RGB8): KB of intermediate frames per chunk of the batch (default 0: one chunk) */
     TI_OPT_PUSH_TMA = 11,             /* peer copy of ti_cloud_push: 1 = TMA bulk copies issued by one lane per CTA (default), 0 = 16-byte stores */
+    TI_OPT_RECTIFY_QUAD = 12,         /* pair-window kernel: 1 = maps uploaded from now on try the quad layout (4 pixels per lane and window) first (default), 0 = pairs; 2..32 = quad with that many exception entries per (tile, warp) (default 24) */
     TI_OPT_PUSH_BLOCKS = 9            /* CTAs of the peer-store copy kernels of ti_cloud_push / ti_inbox_take (default: one per SM) */
 } ti_option;
 int ti_set_option(ti_ctx* ctx, int option, int value);
@@ -139,7 +140,8 @@ int ti_upload_projection(ti_ctx* ctx, int camera, int width, int height, const d
  * BGR8 -> RGB8: out[4] = 5 (3-channel window kernel) or 1 (generic), out[5] = source rows staged per tile.
  * out[6] = output pixels of the pair-window kernel repaired by the per-pixel pass after it (a (tile, warp) holds 32 exceptions;
  * strongly bent maps - fisheye - have a few more), out[7] = bytes per staged source row of the pair-window kernel (192, or
- * 320 for maps whose tiles span more source pixels, e.g. a 2 x downscale). */
+ * 320 for maps whose tiles span more source pixels, e.g. a 2 x downscale) in its low 16 bits, | 0x10000 when the slot runs the
+ * kernel's quad layout (four output pixels per lane and window instead of two). */
 int ti_rectify_plan(ti_ctx* ctx, int camera, int32_t out[8]);
 
 /* u8 dst_h x dst_w mask of slot `camera`: 1 where all four bilinear taps are inside the

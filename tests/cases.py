@@ -113,7 +113,23 @@ def check_rectify(be, cam: int, mapx, mapy, s: str, d: str, src_w: int, src_h: i
             for i in range(n):
                 assert np.array_equal(got[i], wants[i]), (
                     f"rectify {s}->{d} variant={variant} th={th} frame {i}: {(got[i] != wants[i]).sum()} bytes differ")
+        if mono:
+            # the pair-window kernel's other layout (two pixels per window: what maps fall back to when four per window overflow)
+            be.ctx.set_option(be.ctx.OPT_MONO_VARIANT, 4)
+            be.ctx.set_option(be.ctx.OPT_TMA_TILE_H, 32)
+            be.ctx.set_option(be.ctx.OPT_FRAMES_PER_UNIT, 0)
+            be.ctx.set_option(be.ctx.OPT_RECTIFY_QUAD, 0)
+            be.ctx.upload_rectify_map(cam, mapx, mapy, (src_w, src_h))
+            assert be.ctx.rectify_plan(cam)["pixels_per_window"] in (0, 2)
+            dst = be.zeros((n, *F.frame_shape(F.fmt(d), dst_w, dst_h)), np.uint8)
+            be.ctx.rectify(cam, be.dev(src), dst, s, d)
+            got = be.host(dst)
+            for i in range(n):
+                assert np.array_equal(got[i], wants[i]), f"rectify {s}->{d} pair layout frame {i}: {(got[i] != wants[i]).sum()} bytes differ"
     finally:
+        be.ctx.set_option(be.ctx.OPT_RECTIFY_QUAD, 1)
+        if mono:
+            be.ctx.upload_rectify_map(cam, mapx, mapy, (src_w, src_h))  # the slot is left in the default layout
         be.ctx.set_option(be.ctx.OPT_MONO_VARIANT, 4)
         be.ctx.set_option(be.ctx.OPT_TMA_TILE_H, 32)
         be.ctx.set_option(be.ctx.OPT_FRAMES_PER_UNIT, 16)

@@ -55,7 +55,9 @@ def test_config2_eight_mono_streams_one_launch(gpu_backend):
             outs.append(out)
     launches0 = be.ctx.launch_count
     be.ctx.ingest(specs)
-    assert be.ctx.launch_count - launches0 == 1, "8 streams x n frame sets must be ONE kernel launch"
+    # ... plus ONE per-pixel launch for all slots whose exception lists overflowed (a few hundred pixels per frame set)
+    repairs = int(any(be.ctx.rectify_plan(slot)["overflow_pixels"] > 0 for slot in range(8)))
+    assert be.ctx.launch_count - launches0 == 1 + repairs, "8 streams x n frame sets must be ONE remap kernel launch"
     for s, out in enumerate(outs):
         got = be.host(out)
         for b in range(n):

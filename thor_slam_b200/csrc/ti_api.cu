@@ -137,6 +137,10 @@ int ti_set_option(ti_ctx* ctx, int option, int value) {
         case TI_OPT_LUT_PREFETCH: ctx->lut_prefetch = value != 0; return TI_OK;
         case TI_OPT_PUSH_BLOCKS: ctx->push_blocks = value > 0 ? value : 0; return TI_OK;
         case TI_OPT_PUSH_TMA: ctx->push_tma = value != 0; return TI_OK;
+        case TI_OPT_RECTIFY_QUAD:
+            ctx->rectify_quad = value != 0;
+            ctx->quad_exc_cap = value >= 2 ? std::min(value, (int)ti::P4_MAX_EXC) : (int)ti::P4_MAX_EXC_QUAD;
+            return TI_OK;
         case TI_OPT_L2_SCRATCH_KB: ctx->l2_scratch_kb = value > 0 ? value : 0; return TI_OK;
         case TI_OPT_STAGES:
             if (value < 2 || value > M3_MAX_STAGES) return fail(ctx, TI_EINVAL, "stages must be in [2,%d]", M3_MAX_STAGES);
@@ -380,7 +384,8 @@ int ti_rectify_plan(ti_ctx* ctx, int camera, int32_t out[8]) {
         if (C.has_c3) { out[4] = 5; out[5] = C.rows5_alloc; }
     }
     if (ctx->mono_variant == 4 && C.has_pair[th4]) {
-        out[0] = 4; out[1] = P4_TILE_HEIGHTS[th4]; out[2] = C.rows4_alloc[th4]; out[3] = C.exc4_per_warp[th4]; out[6] = C.n_over4[th4]; out[7] = C.pitch4[th4];
+        out[0] = 4; out[1] = P4_TILE_HEIGHTS[th4]; out[2] = C.rows4_alloc[th4]; out[3] = C.exc4_per_warp[th4]; out[6] = C.n_over4[th4];
+        out[7] = C.pitch4[th4] | (C.quad4[th4] ? 0x10000 : 0);
     } else if (ctx->mono_variant >= 3 && C.has_tma_mono[thk]) {
         out[0] = 3; out[1] = M3_TILE_HEIGHTS[thk]; out[2] = C.rows3_alloc[thk];
     } else if (ctx->mono_variant >= 2 && C.has_fast_mono) {

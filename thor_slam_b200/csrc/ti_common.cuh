@@ -114,6 +114,8 @@ constexpr int P4_SMEM_HEADROOM_KB = 20;  // shared memory per SM the window kern
 constexpr int P4_LUT_ROW_WORDS = 192;  // per tile row: 32 lanes x 2 pairs x {window word, pixel a word, pixel b word}
 constexpr uint32_t P4_EXC_UNUSED = 0x80000000u;  // last word of an unused exception entry (no destination offset is -2^31)
 constexpr int P4_MAX_EXC = 32;         // exception entries per (tile, warp): one lane each in the per-frame fix-up pass
+constexpr int P4_MAX_EXC_QUAD = 24;    // the same in the quad layout: 2 x 24 x 8 x 16 bytes of tables leave room for a 5-stage ring of 40-row boxes
+                                       // beside three CTAs per SM (measured on the bench rig: 4 stages 0.765 of the copy peak, 5 stages 0.81)
 
 // 3-channel window path ("c3": BGR8 -> RGB8 rectified): tiles of C3_TW x C3_TH output pixels, one TMA box of
 // 32-bit elements per tile-frame, one 12-byte window per pixel and source row (see ti_rectify_c3.cu).
@@ -141,7 +143,8 @@ struct CameraSlot {
     uint32_t* d_exc4[P4_N_TH] = {nullptr, nullptr, nullptr};     // tiles * P4_CONSUMER_WARPS * exc4_per_warp entries of 4 words
     int tiles4_x[P4_N_TH] = {0, 0, 0}, tiles4_y[P4_N_TH] = {0, 0, 0};
     int rows4_alloc[P4_N_TH] = {0, 0, 0};
-    int pitch4[P4_N_TH] = {0, 0, 0};                             // P4_PITCH or P4_PITCH_WIDE: bytes per staged source row
+    int pitch4[P4_N_TH] = {0, 0, 0};
+    bool quad4[P4_N_TH] = {false, false, false};                 // quad layout: a lane owns 4 consecutive pixels that share ONE 8-byte window per source row                             // P4_PITCH or P4_PITCH_WIDE: bytes per staged source row
     int exc4_per_warp[P4_N_TH] = {0, 0, 0};
     uint32_t* d_over4[P4_N_TH] = {nullptr, nullptr, nullptr};    // output pixels whose (tile, warp) exception list was full
     int n_over4[P4_N_TH] = {0, 0, 0};
@@ -205,6 +208,8 @@ struct ti_ctx {
     // scratch for two-pass paths (BGR -> gray ahead of the mono remap); grown on demand, never visible to the caller
     void* scratch = nullptr;
     size_t scratch_cap = 0;
+    bool rectify_quad = true;  // calibration upload tries the quad layout of the pair-window kernel first
+    int quad_exc_cap = ti::P4_MAX_EXC_QUAD;  // TI_OPT_RECTIFY_QUAD values 2..32 set it (bring-up: ring depth against overflow pixels)
     int l2_scratch_kb = 0;  // two-pass rectify: scratch per chunk of the batch; 0 = the whole batch in one chunk (chunks that fit the
                             // L2 were measured SLOWER: 0.39 vs 0.49 of peak for BGR8 -> MONO8 - small launches cost more than the re-read)
     // host pipeline (ti_ingest_host)
@@ -387,6 +392,7 @@ __device__ __forceinline__ void st_stream_u1(void* p, uint32_t v) { *reinterpret
 __device__ __forceinline__ uint4 ld_keep_u4(const void* p) { return *reinterpret_cast<const uint4*>(ti_emu::check_align(p, 16)); }
 __device__ __forceinline__ void st_stream_b8(void* p, uint32_t v) { *reinterpret_cast<uint8_t*>(p) = (uint8_t)v; }
 __device__ __forceinline__ void st_stream_b16(void* p, uint32_t v) { *reinterpret_cast<uint16_t*>(ti_emu::check_align(p, 2)) = (uint16_t)v; }
+__device__ __forceinline__ void st_stream_b32(void* p, uint32_t v) { *reinterpret_cast<uint32_t*>(ti_emu::check_align(p, 4)) = v; }
 #elif defined(__CUDACC__)
 // ---- device helpers ------------------------------------------------------------------------
 // L2 eviction policies (createpolicy is not volatile: the compiler hoists / CSEs it).
@@ -436,6 +442,9 @@ __device__ __forceinline__ void st_stream_b8(void* p, uint32_t v) {  // .cs = st
 }
 __device__ __forceinline__ void st_stream_b16(void* p, uint32_t v) {
     asm volatile("st.global.cs.u16 [%0], %1;" ::"l"(p), "h"((unsigned short)v) : "memory");
+}
+__device__ __forceinline__ void st_stream_b32(void* p, uint32_t v) {
+    asm volatile("st.global.cs.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 // LUT reads: re-used by every frame of the batch -> prefer to keep in L2.
 __device__ __forceinline__ uint4 ld_keep_u4(const void* p) {

@@ -30,6 +30,13 @@
 //  * Slots whose tiles span more than P4_PITCH source bytes (a 2 x downscale map: 128 output pixels sample 256 source pixels)
 //    run the PITCH = P4_PITCH_WIDE instantiation: the box is loaded as 80 32-bit elements per row (a TMA box dimension holds at
 //    most 256 elements), everything else is the same code.
+//  * QUAD layout (round 2; the default where a map allows it): a lane owns FOUR consecutive output pixels whose taps all lie in
+//    one 8-byte window per source row (at scale ~1 the four pixels span 4-5 source bytes; the window starts at the 4-byte word
+//    of the leftmost) - half the window loads of the pair layout and one 32-bit store per row instead of two 16-bit ones.  The
+//    LUT slot of a lane is the same six words {window word + selector of pixels 0-1, pixel 0, pixel 1, selector of pixels 2-3,
+//    pixel 2, pixel 3}; pixels that do not fit (another source row, further right) are exceptions like pixel b above - three
+//    times as many as with pairs, which the flat fix-up pass does not care about.  Slots with more than the lists hold fall
+//    back to the pair layout.
 //  * The LUT is 6 bytes per output pixel in memory (per pair: the window word and one word per pixel
 //    holding 32-fx, fy, fx and the fx = fy = 0 flag); a tile's 24 KB slice is prefetched into shared
 //    memory by a 1-D bulk copy one unit ahead (unit = tile x up to frames_per_unit frames of the
@@ -84,19 +91,20 @@ __device__ __forceinline__ void p4_blend(const Taps& T, const uint4& w, uint32_t
 // {window word, Wtop, Wbot, row * dst_w + column - 2 * lane}.  Its window is fetched ahead of the last row's blend so that the
 // latency of the dependent loads hides behind that row; its store follows the row loop's stores (__syncwarp).
 // DSTW > 0: the destination row pitch is this compile-time constant, so row q is an immediate offset from the lane's first-row pointer.
-template <int RPW, bool WHOLE, bool PREFETCH, bool HALF_LOADS = false, int DSTW = 0, int PITCH = P4_PITCH>
+template <int RPW, bool WHOLE, bool PREFETCH, bool HALF_LOADS = false, int DSTW = 0, int PITCH = P4_PITCH, bool QUAD = false>
 __device__ __forceinline__ void p4_rows(const uint4 (&w0)[RPW], const uint4 (&w1)[RPW], const uint2 (&mw)[RPW], p4_addr_t base,
                                         uint8_t* dp, int dst_w, int live_rows, int live_cols, int lane, bool fixes, bool i_fix,
                                         p4_addr_t my_exc) {
     // HALF_LOADS (bring-up only, wrong pixels): pair 1 reuses pair 0's window - how much of the time is the window loads?
-    Taps A = p4_fetch<PITCH>(base, mw[0].x), B = HALF_LOADS ? A : p4_fetch<PITCH>(base, mw[0].y);
+    // QUAD: pixels 2-3 of the lane read pixel 0-1's window (mw[q].y is only their selector)
+    Taps A = p4_fetch<PITCH>(base, mw[0].x), B = (HALF_LOADS || QUAD) ? A : p4_fetch<PITCH>(base, mw[0].y);
     uint8_t* const lane_dst = dp;  // this lane's first pixel of the warp's first row
     uint4 fe = make_uint4(0u, 0u, 0u, 0u);
     Taps X = A;
 #pragma unroll
     for (int q = 0; q < RPW; ++q) {
         Taps An = A, Bn = B;
-        if (PREFETCH && q + 1 < RPW) { An = p4_fetch<PITCH>(base, mw[q + 1].x); Bn = HALF_LOADS ? An : p4_fetch<PITCH>(base, mw[q + 1].y); }
+        if (PREFETCH && q + 1 < RPW) { An = p4_fetch<PITCH>(base, mw[q + 1].x); Bn = (HALF_LOADS || QUAD) ? An : p4_fetch<PITCH>(base, mw[q + 1].y); }
         if (q == RPW - 1 && fixes && i_fix) {
             fe = p4_lds128(my_exc);
             X = p4_fetch<PITCH>(base, fe.x);
@@ -105,7 +113,20 @@ __device__ __forceinline__ void p4_rows(const uint4 (&w0)[RPW], const uint4 (&w1
         p4_blend(A, w0[q], mw[q].x, ra0, rb0);
         p4_blend(B, w1[q], mw[q].y, ra1, rb1);
         const uint32_t o0 = __byte_perm(ra0, rb0, 0x0062), o1 = __byte_perm(ra1, rb1, 0x0062);
-        if (WHOLE && DSTW > 0) {
+        if (QUAD) {
+            const uint32_t o = __byte_perm(o0, o1, 0x5410);  // the lane's four pixels
+            if (WHOLE && DSTW > 0) {
+                st_stream_b32(dp + q * DSTW, o);
+            } else if (WHOLE) {
+                st_stream_b32(dp, o);
+            } else if (q < live_rows) {
+                const int c = 4 * lane;
+                if (c < live_cols) st_stream_b8(dp, o);
+                if (c + 1 < live_cols) st_stream_b8(dp + 1, o >> 8);
+                if (c + 2 < live_cols) st_stream_b8(dp + 2, o >> 16);
+                if (c + 3 < live_cols) st_stream_b8(dp + 3, o >> 24);
+            }
+        } else if (WHOLE && DSTW > 0) {
             st_stream_b16(dp + q * DSTW, o0);
             st_stream_b16(dp + q * DSTW + 64, o1);
         } else if (WHOLE) {
@@ -120,7 +141,7 @@ __device__ __forceinline__ void p4_rows(const uint4 (&w0)[RPW], const uint4 (&w1
         }
         if (!(WHOLE && DSTW > 0)) dp += dst_w;
         if (PREFETCH) { A = An; B = Bn; }
-        else if (q + 1 < RPW) { A = p4_fetch<PITCH>(base, mw[q + 1].x); B = p4_fetch<PITCH>(base, mw[q + 1].y); }
+        else if (q + 1 < RPW) { A = p4_fetch<PITCH>(base, mw[q + 1].x); B = QUAD ? A : p4_fetch<PITCH>(base, mw[q + 1].y); }
     }
     if (fixes) {
         __syncwarp();  // the fix-up stores land behind the row loop's stores to the same bytes
@@ -132,7 +153,7 @@ __device__ __forceinline__ void p4_rows(const uint4 (&w0)[RPW], const uint4 (&w1
     }
 }
 
-template <int TH, bool DEBUG, int DSTW = 0, int PITCH = P4_PITCH>
+template <int TH, bool DEBUG, int DSTW = 0, int PITCH = P4_PITCH, bool QUAD = false>
 __global__ void __launch_bounds__(P4_THREADS, TH == 32 ? 3 : 4) rectify_mono_pair_kernel(const __grid_constant__ Rect4Params P) {
     TI_DYNAMIC_SMEM(uint8_t, smem);
     constexpr int RPW = TH / P4_CONSUMER_WARPS;  // tile rows per consumer warp
@@ -228,9 +249,9 @@ __global__ void __launch_bounds__(P4_THREADS, TH == 32 ? 3 : 4) rectify_mono_pai
         const int u0 = (int16_t)(box.z & 0xFFFF), v0 = (int16_t)(box.z >> 16) + warp * RPW;
         const int dst_w = J.dst_w, live_rows = J.dst_h - v0, live_cols = J.dst_w - u0;
         const uint64_t dst_stride = J.dst_stride;
-        uint8_t* dp = J.dst + (uint64_t)U.b0 * dst_stride + (size_t)v0 * dst_w + u0 + 2 * lane;
+        uint8_t* dp = J.dst + (uint64_t)U.b0 * dst_stride + (size_t)v0 * dst_w + u0 + (QUAD ? 4 : 2) * lane;
         const bool whole = live_rows >= RPW && live_cols >= P4_TW &&
-                           ((((uint64_t)(uintptr_t)J.dst | dst_stride | (uint64_t)dst_w) & 1ull) == 0);  // warp-uniform
+                           ((((uint64_t)(uintptr_t)J.dst | dst_stride | (uint64_t)dst_w) & (QUAD ? 3ull : 1ull)) == 0);  // warp-uniform: aligned row stores
         // expand this lane's part of the unit's LUT slice into weight registers
         mbar_wait(lut_full, k & 1u);
         {
@@ -257,9 +278,9 @@ __global__ void __launch_bounds__(P4_THREADS, TH == 32 ? 3 : 4) rectify_mono_pai
         for (uint32_t f = 0; f < U.nb; ++f) {
             p4_wait(bar, phase);
             if (!skip_blend) {
-                if (DEBUG && (P.debug & 8)) p4_rows<RPW, true, TH == 32, true, 0, PITCH>(w0, w1, mw, base, dp, dst_w, live_rows, live_cols, lane, warp_fixes, i_fix, my_exc);
-                else if (whole) p4_rows<RPW, true, TH == 32, false, DSTW, PITCH>(w0, w1, mw, base, dp, dst_w, live_rows, live_cols, lane, warp_fixes, i_fix, my_exc);
-                else p4_rows<RPW, false, false, false, 0, PITCH>(w0, w1, mw, base, dp, dst_w, live_rows, live_cols, lane, warp_fixes, i_fix, my_exc);
+                if (DEBUG && (P.debug & 8)) p4_rows<RPW, true, TH == 32, true, 0, PITCH, QUAD>(w0, w1, mw, base, dp, dst_w, live_rows, live_cols, lane, warp_fixes, i_fix, my_exc);
+                else if (whole) p4_rows<RPW, true, TH == 32, false, DSTW, PITCH, QUAD>(w0, w1, mw, base, dp, dst_w, live_rows, live_cols, lane, warp_fixes, i_fix, my_exc);
+                else p4_rows<RPW, false, false, false, 0, PITCH, QUAD>(w0, w1, mw, base, dp, dst_w, live_rows, live_cols, lane, warp_fixes, i_fix, my_exc);
             }
             p4_warp_arrive(bar + 64);
             dp += dst_stride;
@@ -284,10 +305,17 @@ int launch_rectify_pair(ti_ctx* ctx, Rect4Params& P, int th_index) {
     const bool wide = P.pitch == P4_PITCH_WIDE;
     Kern kern = wide ? kernels_wide[th_index] : kernels[ctx->debug ? 1 : 0][th_index];
     // every job of the launch writes rows of the same common pitch: use the kernel whose row stores are immediate offsets
-    if (!ctx->debug && TH == 32 && !wide) {
-        int dw = P.job[0].dst_w;
-        for (int j = 1; j < P.n_jobs; ++j)
-            if (P.job[j].dst_w != dw) dw = 0;
+    int dw = P.job[0].dst_w;
+    for (int j = 1; j < P.n_jobs; ++j)
+        if (P.job[j].dst_w != dw) dw = 0;
+    if (P.quad) {
+        if (TH != 32 || wide) return fail(ctx, TI_ESTATE, "rectify: the quad layout exists for 32-row tiles of the standard pitch only");
+        kern = ctx->debug  ? (Kern)rectify_mono_pair_kernel<32, true, 0, P4_PITCH, true>
+             : dw == 1280 ? (Kern)rectify_mono_pair_kernel<32, false, 1280, P4_PITCH, true>
+             : dw == 640  ? (Kern)rectify_mono_pair_kernel<32, false, 640, P4_PITCH, true>
+             : dw == 1920 ? (Kern)rectify_mono_pair_kernel<32, false, 1920, P4_PITCH, true>
+                          : (Kern)rectify_mono_pair_kernel<32, false, 0, P4_PITCH, true>;
+    } else if (!ctx->debug && TH == 32 && !wide) {
         if (dw == 1280) kern = rectify_mono_pair_kernel<32, false, 1280>;
         else if (dw == 640) kern = rectify_mono_pair_kernel<32, false, 640>;
         else if (dw == 1920) kern = rectify_mono_pair_kernel<32, false, 1920>;
@@ -332,7 +360,7 @@ void free_pair_tables(CameraSlot& C) {
         if (C.d_exc4[k]) cudaFree(C.d_exc4[k]);
         if (C.d_over4[k]) cudaFree(C.d_over4[k]);
         C.d_lut4[k] = nullptr; C.d_boxes4[k] = nullptr; C.d_exc4[k] = nullptr; C.d_over4[k] = nullptr; C.n_over4[k] = 0;
-        C.has_pair[k] = false; C.exc4_per_warp[k] = 0; C.rows4_alloc[k] = 0;
+        C.has_pair[k] = false; C.quad4[k] = false; C.exc4_per_warp[k] = 0; C.rows4_alloc[k] = 0;
     }
 }
 
@@ -398,63 +426,123 @@ int build_pair_tables(ti_ctx* ctx, CameraSlot& C, const std::vector<lut_t>& lut,
         const int rows_alloc = std::max(8, (rows_max + 7) / 8 * 8);
         const int pitch = span_max > P4_PITCH ? P4_PITCH_WIDE : P4_PITCH;  // staged bytes per source row
 
-        std::vector<uint32_t> lut4(n_tiles * TH * P4_LUT_ROW_WORDS, 0u);
-        std::vector<std::vector<uint32_t>> exc(n_tiles * P4_CONSUMER_WARPS);  // 4 words per entry
-        std::vector<uint32_t> over;  // output pixels (v * dst_w + u) whose warp list was full
-        for (int ty = 0; ty < ty_n && ok; ++ty)
-            for (int tx = 0; tx < tx_n && ok; ++tx) {
-                const size_t tile = (size_t)ty * tx_n + tx;
-                const TileBox2& B = boxes[tile];
-                for (int row = 0; row < TH && ok; ++row) {
-                    uint32_t* rw = lut4.data() + (tile * TH + row) * P4_LUT_ROW_WORDS;
-                    std::vector<uint32_t>& ex = exc[tile * P4_CONSUMER_WARPS + row / RPW];
-                    for (int lane = 0; lane < 32 && ok; ++lane)
-                        for (int p = 0; p < 2; ++p) {
-                            const int ua = tx * P4_TW + p * 64 + 2 * lane, v = ty * TH + row;
-                            const Px a = decode(entry(ua, v)), b = decode(entry(ua + 1, v));
-                            uint32_t* w = rw + (lane * 2 + p) * 3;  // {window word, pixel a, pixel b}
-                            w[1] = pixel_word(a);
-                            w[2] = pixel_word(b);
-                            uint32_t& m = w[0];
-                            m = 0x3210u;
-                            if (!a.in && !b.in) continue;
-                            const Px& anchor = a.in ? a : b;  // the window is placed for pixel a (for b when a has no tap inside)
-                            const int wordx = (anchor.x0 - B.c0) & ~3;
-                            const uint32_t off = (uint32_t)((anchor.y0 - B.y0) * pitch + wordx);
-                            const uint32_t sa = a.in ? (uint32_t)(a.x0 - B.c0 - wordx) : 0u;
-                            const int sb_rel = b.in ? b.x0 - B.c0 - wordx : (int)sa;
-                            const bool b_fits = !b.in || (b.y0 == anchor.y0 && sb_rel >= 0 && sb_rel <= 6);
-                            if (b_fits) {
-                                m = (off << 16) | sa | ((sa + 1) << 4) | ((uint32_t)sb_rel << 8) | ((uint32_t)(sb_rel + 1) << 12);
-                            } else {
-                                // pixel b gets an entry of the warp's exception list: its own window (bytes b.left, b.right
-                                // selected into bytes 0, 1), its weight words, where it goes
-                                if (ex.size() / 4 >= (size_t)P4_MAX_EXC) {
-                                    // the warp's list is full (a strongly bent map: a fisheye4 camera at 1280 x 800 has up to 42 such
-                                    // pairs in one (tile, warp)): the pixel joins the slot's OVERFLOW list, repaired after the kernel by
-                                    // one thread per pixel and frame from the generic LUT (rectify_points_kernel) - a handful of pixels
-                                    // per frame, so every reference camera model stays on this kernel
-                                    m = (off << 16) | sa | ((sa + 1) << 4) | (sa << 8) | ((sa + 1) << 12);
-                                    over.push_back((uint32_t)v * (uint32_t)dst_w + (uint32_t)(ua + 1));
-                                    if (over.size() > (size_t)dst_w * dst_h / 32) { ok = false; break; }  // beyond ~3 % the per-pixel pass costs more than v3
-                                    continue;
-                                }
-                                const int wordb = (b.x0 - B.c0) & ~3;
-                                const uint32_t offb = (uint32_t)((b.y0 - B.y0) * pitch + wordb);
-                                const uint32_t sb = (uint32_t)(b.x0 - B.c0 - wordb);
-                                m = (off << 16) | sa | ((sa + 1) << 4) | (sa << 8) | ((sa + 1) << 12);  // b reads a's bytes: harmless
-                                uint32_t wt, wb;
-                                host_expand(pixel_word(b), wt, wb);
-                                ex.push_back((offb << 16) | sb | ((sb + 1) << 4) | (sb << 8) | ((sb + 1) << 12));
-                                ex.push_back(wt);
-                                ex.push_back(wb);
-                                // destination of the pixel relative to the first pixel of the lane that will repair it (entry i -> lane i)
-                                const int fix_lane = (int)(ex.size() / 4);
-                                ex.push_back((uint32_t)((row % RPW) * dst_w + (p * 64 + 2 * lane + 1) - 2 * fix_lane));
-                            }
-                        }
-                }
+        std::vector<uint32_t> lut4;
+        std::vector<std::vector<uint32_t>> exc;  // per (tile, warp): 4 words per entry
+        std::vector<uint32_t> over;              // output pixels (v * dst_w + u) whose warp list was full
+        // One exception: pixel `q` at output column `col` of tile row `row` gets an entry of its warp's list - its own window (bytes
+        // left, right selected into bytes 0, 1), its weight words, where it goes.  A full list (a strongly bent map: a fisheye4 camera
+        // at 1280 x 800 has up to 42 such pixels in one (tile, warp) with pairs) sends the pixel to the slot's OVERFLOW list, repaired
+        // after the kernel by one thread per pixel and frame from the generic LUT (rectify_points_kernel) - a handful of pixels per
+        // frame, so every reference camera model stays on this kernel.  False: beyond ~3 % the per-pixel pass costs more than v3.
+        auto exception = [&](std::vector<uint32_t>& ex, const TileBox2& B, const Px& q, int row, int col, int v, int u, int lane_px) -> bool {
+            if (ex.size() / 4 >= (size_t)(lane_px == 4 ? ctx->quad_exc_cap : P4_MAX_EXC)) {
+                over.push_back((uint32_t)v * (uint32_t)dst_w + (uint32_t)u);
+                return over.size() <= (size_t)dst_w * dst_h / 32;
             }
+            const int wordq = (q.x0 - B.c0) & ~3;
+            const uint32_t offq = (uint32_t)((q.y0 - B.y0) * pitch + wordq);
+            const uint32_t sq = (uint32_t)(q.x0 - B.c0 - wordq);
+            uint32_t wt, wb;
+            host_expand(pixel_word(q), wt, wb);
+            ex.push_back((offq << 16) | sq | ((sq + 1) << 4) | (sq << 8) | ((sq + 1) << 12));
+            ex.push_back(wt);
+            ex.push_back(wb);
+            // destination of the pixel relative to the first pixel of the lane that will repair it (entry i -> lane i)
+            const int fix_lane = (int)(ex.size() / 4);
+            ex.push_back((uint32_t)((row % RPW) * dst_w + col - lane_px * fix_lane));
+            return true;
+        };
+        // pair layout: lane L owns pixels (2L, 2L+1) and (64+2L, 65+2L) of a tile row, a window per pair
+        auto fill_pairs = [&]() -> bool {
+            lut4.assign(n_tiles * TH * P4_LUT_ROW_WORDS, 0u);
+            exc.assign(n_tiles * P4_CONSUMER_WARPS, std::vector<uint32_t>());
+            over.clear();
+            for (int ty = 0; ty < ty_n; ++ty)
+                for (int tx = 0; tx < tx_n; ++tx) {
+                    const size_t tile = (size_t)ty * tx_n + tx;
+                    const TileBox2& B = boxes[tile];
+                    for (int row = 0; row < TH; ++row) {
+                        uint32_t* rw = lut4.data() + (tile * TH + row) * P4_LUT_ROW_WORDS;
+                        std::vector<uint32_t>& ex = exc[tile * P4_CONSUMER_WARPS + row / RPW];
+                        for (int lane = 0; lane < 32; ++lane)
+                            for (int p = 0; p < 2; ++p) {
+                                const int ua = tx * P4_TW + p * 64 + 2 * lane, v = ty * TH + row;
+                                const Px a = decode(entry(ua, v)), b = decode(entry(ua + 1, v));
+                                uint32_t* w = rw + (lane * 2 + p) * 3;  // {window word, pixel a, pixel b}
+                                w[1] = pixel_word(a);
+                                w[2] = pixel_word(b);
+                                uint32_t& m = w[0];
+                                m = 0x3210u;
+                                if (!a.in && !b.in) continue;
+                                const Px& anchor = a.in ? a : b;  // the window is placed for pixel a (for b when a has no tap inside)
+                                const int wordx = (anchor.x0 - B.c0) & ~3;
+                                const uint32_t off = (uint32_t)((anchor.y0 - B.y0) * pitch + wordx);
+                                const uint32_t sa = a.in ? (uint32_t)(a.x0 - B.c0 - wordx) : 0u;
+                                const int sb_rel = b.in ? b.x0 - B.c0 - wordx : (int)sa;
+                                const bool b_fits = !b.in || (b.y0 == anchor.y0 && sb_rel >= 0 && sb_rel <= 6);
+                                if (b_fits) {
+                                    m = (off << 16) | sa | ((sa + 1) << 4) | ((uint32_t)sb_rel << 8) | ((uint32_t)(sb_rel + 1) << 12);
+                                } else {
+                                    m = (off << 16) | sa | ((sa + 1) << 4) | (sa << 8) | ((sa + 1) << 12);  // b reads a's bytes: harmless
+                                    if (!exception(ex, B, b, row, p * 64 + 2 * lane + 1, v, ua + 1, 2)) return false;
+                                }
+                            }
+                    }
+                }
+            return true;
+        };
+        // quad layout: lane L owns pixels 4L .. 4L+3 of a tile row, ONE window for the four (the slot's second window word only carries
+        // the byte selector of pixels 2-3).  The window is placed for the source row most of the four read (ties: the leftmost pixel's)
+        // at the 4-byte word of that row's leftmost tap; whoever reads another row or lies beyond byte 6 is an exception.
+        auto fill_quads = [&]() -> bool {
+            lut4.assign(n_tiles * TH * P4_LUT_ROW_WORDS, 0u);
+            exc.assign(n_tiles * P4_CONSUMER_WARPS, std::vector<uint32_t>());
+            over.clear();
+            for (int ty = 0; ty < ty_n; ++ty)
+                for (int tx = 0; tx < tx_n; ++tx) {
+                    const size_t tile = (size_t)ty * tx_n + tx;
+                    const TileBox2& B = boxes[tile];
+                    for (int row = 0; row < TH; ++row) {
+                        uint32_t* rw = lut4.data() + (tile * TH + row) * P4_LUT_ROW_WORDS;
+                        std::vector<uint32_t>& ex = exc[tile * P4_CONSUMER_WARPS + row / RPW];
+                        for (int lane = 0; lane < 32; ++lane) {
+                            const int u0 = tx * P4_TW + 4 * lane, v = ty * TH + row;
+                            Px q[4];
+                            for (int i = 0; i < 4; ++i) q[i] = decode(entry(u0 + i, v));
+                            uint32_t* w = rw + lane * 6;  // {window word + selector 0-1, pixel 0, pixel 1, selector 2-3, pixel 2, pixel 3}
+                            w[0] = w[3] = 0x3210u;
+                            w[1] = pixel_word(q[0]); w[2] = pixel_word(q[1]); w[4] = pixel_word(q[2]); w[5] = pixel_word(q[3]);
+                            int best = -1, best_n = 0;
+                            for (int i = 0; i < 4; ++i) {
+                                if (!q[i].in) continue;
+                                int n = 0;
+                                for (int j = 0; j < 4; ++j) n += q[j].in && q[j].y0 == q[i].y0;
+                                if (n > best_n) { best_n = n; best = i; }
+                            }
+                            if (best < 0) continue;
+                            const int wy = q[best].y0;
+                            int xmin = 1 << 20;
+                            for (int i = 0; i < 4; ++i)
+                                if (q[i].in && q[i].y0 == wy) xmin = std::min(xmin, q[i].x0);
+                            const int wordx = (xmin - B.c0) & ~3;
+                            const uint32_t off = (uint32_t)((wy - B.y0) * pitch + wordx);
+                            uint32_t sel[4];
+                            for (int i = 0; i < 4; ++i) {
+                                const int rel = q[i].in ? q[i].x0 - B.c0 - wordx : 0;
+                                const bool fits = !q[i].in || (q[i].y0 == wy && rel >= 0 && rel <= 6);
+                                sel[i] = fits ? (uint32_t)rel : 0u;  // an exception reads bytes 0, 1 of the window: harmless
+                                if (!fits && !exception(ex, B, q[i], row, 4 * lane + i, v, u0 + i, 4)) return false;
+                            }
+                            w[0] = (off << 16) | sel[0] | ((sel[0] + 1) << 4) | (sel[1] << 8) | ((sel[1] + 1) << 12);
+                            w[3] = sel[2] | ((sel[2] + 1) << 4) | (sel[3] << 8) | ((sel[3] + 1) << 12);
+                        }
+                    }
+                }
+            return true;
+        };
+        bool quad = false;
+        if (TH == 32 && pitch == P4_PITCH && ctx->rectify_quad) quad = fill_quads();
+        if (!quad) ok = fill_pairs();
         if (!ok) continue;
         size_t e_max = 0;
         for (const auto& e : exc) e_max = std::max(e_max, e.size() / 4);
@@ -474,7 +562,7 @@ int build_pair_tables(ti_ctx* ctx, CameraSlot& C, const std::vector<lut_t>& lut,
             TI_CUDA(ctx, cudaMemcpy(C.d_over4[k], over.data(), over.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
         }
         C.n_over4[k] = (int)over.size();
-        C.tiles4_x[k] = tx_n; C.tiles4_y[k] = ty_n; C.rows4_alloc[k] = rows_alloc; C.pitch4[k] = pitch; C.exc4_per_warp[k] = epw;
+        C.tiles4_x[k] = tx_n; C.tiles4_y[k] = ty_n; C.rows4_alloc[k] = rows_alloc; C.pitch4[k] = pitch; C.quad4[k] = quad; C.exc4_per_warp[k] = epw;
         C.has_pair[k] = true;
     }
     return TI_OK;

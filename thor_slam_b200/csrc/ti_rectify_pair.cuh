@@ -29,6 +29,7 @@ struct Rect4Params {
     int frames_per_unit;
     int rows_alloc_max;  // launch-wide stage geometry
     int pitch;           // P4_PITCH or P4_PITCH_WIDE: every job of a launch stages rows of this pitch
+    int quad;            // 1: every job of the launch uses the quad layout (4 consecutive pixels per lane, one window per row)
     int exc_max;         // largest exc_per_warp of the launch
     int stages;
     int debug;           // bring-up switches (TI_OPT_DEBUG): 1 = consumers skip the blend, 2 = issuer skips the loads; 0 in production

@@ -187,7 +187,8 @@ class IngestContext:
         out = (ctypes.c_int32 * 8)()
         self._check(self.lib.ti_rectify_plan(self._h, camera, out))
         return {"variant": int(out[0]), "tile_h": int(out[1]), "rows": int(out[2]), "exceptions_per_warp": int(out[3]),
-                "colour_variant": int(out[4]), "colour_rows": int(out[5]), "overflow_pixels": int(out[6]), "pitch": int(out[7])}
+                "colour_variant": int(out[4]), "colour_rows": int(out[5]), "overflow_pixels": int(out[6]), "pitch": int(out[7]) & 0xFFFF,
+                "pixels_per_window": (4 if int(out[7]) >> 16 else 2) if int(out[0]) == 4 else 0}
 
     def get_valid_mask(self, camera: int, out: Any) -> Any:
         self._check(self.lib.ti_get_valid_mask(self._h, camera, self._ptr(out)))
@@ -381,6 +382,7 @@ class IngestContext:
     OPT_PUSH_BLOCKS = 9
     OPT_L2_SCRATCH_KB = 10
     OPT_PUSH_TMA = 11
+    OPT_RECTIFY_QUAD = 12
 
     def nccl_barrier(self) -> None:
         self._check(self.lib.ti_nccl_barrier(self._h))

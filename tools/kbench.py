@@ -106,6 +106,19 @@ def main() -> None:
         # plain device copy of the same bytes = what "1.0" looks like for this traffic
         report("torch copy_ (same bytes)", timeit(lambda: [o.copy_(f) for o, f in zip(outs, frames)], args.iters), 2 * px, px)
 
+    if not args.only or "quad" in args.only:
+        # the pair-window kernel's two layouts on the same maps (the layout is chosen when the map is uploaded)
+        for quad in (1, 0, 1):
+            ctx.set_option(ctx.OPT_RECTIFY_QUAD, quad)
+            for cam in range(NS):
+                ctx.upload_rectify_map(cam, *maps[cam % 2], (W, H))
+            print("plan", ctx.rectify_plan(0), ctx.rectify_plan(1), flush=True)
+            for stages in (3, 4, 5, 6):
+                ctx.set_option(ctx.OPT_STAGES, stages)
+                report(f"rectify mono v4 quad={quad} S={stages}", timeit(lambda: ctx.ingest(specs), args.iters), 2 * px, px)
+            ctx.set_option(ctx.OPT_STAGES, 6)
+        ctx.set_option(ctx.OPT_RECTIFY_QUAD, 1)
+
     if not args.only or "downscale" in args.only:
         # the 2 x downscale of config/slam_config.yaml's output_resolution done on the host: 1280x800 -> 640x400 (8 mono streams) and
         # 1920x1200 -> 960x600 BGR -> RGB (4 colour streams); algorithmic bytes = source read + result written
