@@ -126,7 +126,7 @@ __global__ void __launch_bounds__(C3_THREADS, 3) rectify_c3_kernel(const __grid_
             bool lut_pending = k + 1 < units_mine;  // the next unit's LUT slice still has to be requested
             for (uint32_t f = 0; f < cur.nb; ++f) {
                 uint8_t* sb = stage0 + (size_t)s * stage_bytes;
-                mbar_wait_sleep(empty + s, phase, 300);  // consumers have released the stage's previous item
+                mbar_wait_hint(empty + s, phase, 20000);  // consumers have released the stage's previous item (suspended in hardware, no polling)
                 if (rows > 0) tma_load_3d(sb, &P.map[cur.j], c0 / 4, y0, (int)(cur.b0 + f), full + s);  // 128 u32 x rows_alloc
                 mbar_arrive_expect_tx(full + s, tx);
                 if (++s == S) { s = 0; phase ^= 1u; }

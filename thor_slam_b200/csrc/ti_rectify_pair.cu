@@ -91,7 +91,7 @@ __device__ __forceinline__ void p4_blend(const Taps& T, const uint4& w, uint32_t
 // {window word, Wtop, Wbot, row * dst_w + column - 2 * lane}.  Its window is fetched ahead of the last row's blend so that the
 // latency of the dependent loads hides behind that row; its store follows the row loop's stores (__syncwarp).
 // DSTW > 0: the destination row pitch is this compile-time constant, so row q is an immediate offset from the lane's first-row pointer.
-template <int RPW, bool WHOLE, bool PREFETCH, bool HALF_LOADS = false, int DSTW = 0, int PITCH = P4_PITCH, bool QUAD = false>
+template <int RPW, bool WHOLE, bool PREFETCH, bool HALF_LOADS = false, int DSTW = 0, int PITCH = P4_PITCH, bool QUAD = false, int FIXQ = RPW - 1>
 __device__ __forceinline__ void p4_rows(const uint4 (&w0)[RPW], const uint4 (&w1)[RPW], const uint2 (&mw)[RPW], p4_addr_t base,
                                         uint8_t* dp, int dst_w, int live_rows, int live_cols, int lane, bool fixes, bool i_fix,
                                         p4_addr_t my_exc) {
@@ -105,7 +105,7 @@ __device__ __forceinline__ void p4_rows(const uint4 (&w0)[RPW], const uint4 (&w1
     for (int q = 0; q < RPW; ++q) {
         Taps An = A, Bn = B;
         if (PREFETCH && q + 1 < RPW) { An = p4_fetch<PITCH>(base, mw[q + 1].x); Bn = (HALF_LOADS || QUAD) ? An : p4_fetch<PITCH>(base, mw[q + 1].y); }
-        if (q == RPW - 1 && fixes && i_fix) {
+        if (q == FIXQ && fixes && i_fix) {
             fe = p4_lds128(my_exc);
             X = p4_fetch<PITCH>(base, fe.x);
         }
@@ -217,7 +217,9 @@ __global__ void __launch_bounds__(P4_THREADS, TH == 32 ? 3 : 4) rectify_mono_pai
             for (uint32_t f = 0; f < cur.nb; ++f) {
                 const uint32_t b = cur.b0 + f;
                 uint8_t* sb = stage0 + (size_t)s * stage_bytes;
-                mbar_wait_sleep(empty + s, phase, 300);  // consumers have released the stage's previous item
+                // consumers have released the stage's previous item.  Suspended in hardware: polling every 300 ns cost 8 % of the
+                // kernel's issued instructions (ncu, profiles/r02_ncu_rect_quad.txt) - 1 % of its time
+                mbar_wait_hint(empty + s, phase, 20000);
                 if (rows > 0 && !(DEBUG && (P.debug & 2))) tma_load_3d(sb, &P.map[cur.j], PITCH == P4_PITCH ? c0 : c0 / 4, y0, (int)b, full + s);  // one box: PITCH x rows_alloc bytes (wide: 32-bit elements)
                 mbar_arrive_expect_tx(full + s, (DEBUG && (P.debug & 2)) ? 0u : tx);
                 if (++s == S) { s = 0; phase ^= 1u; }
@@ -279,7 +281,7 @@ __global__ void __launch_bounds__(P4_THREADS, TH == 32 ? 3 : 4) rectify_mono_pai
             p4_wait(bar, phase);
             if (!skip_blend) {
                 if (DEBUG && (P.debug & 8)) p4_rows<RPW, true, TH == 32, true, 0, PITCH, QUAD>(w0, w1, mw, base, dp, dst_w, live_rows, live_cols, lane, warp_fixes, i_fix, my_exc);
-                else if (whole) p4_rows<RPW, true, TH == 32, false, DSTW, PITCH, QUAD>(w0, w1, mw, base, dp, dst_w, live_rows, live_cols, lane, warp_fixes, i_fix, my_exc);
+                else if (whole) p4_rows<RPW, true, TH == 32, false, DSTW, PITCH, QUAD, QUAD ? RPW - 3 : RPW - 1>(w0, w1, mw, base, dp, dst_w, live_rows, live_cols, lane, warp_fixes, i_fix, my_exc);
                 else p4_rows<RPW, false, false, false, 0, PITCH, QUAD>(w0, w1, mw, base, dp, dst_w, live_rows, live_cols, lane, warp_fixes, i_fix, my_exc);
             }
             p4_warp_arrive(bar + 64);

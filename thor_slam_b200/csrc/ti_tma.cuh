@@ -71,6 +71,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 }
 __device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity) { mbar_wait(bar, parity); }
 __device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity, unsigned) { mbar_wait(bar, parity); }
+__device__ __forceinline__ void mbar_wait_hint(uint64_t* bar, uint32_t parity, unsigned) { mbar_wait(bar, parity); }
 __device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
     EmuMbar* m = reinterpret_cast<EmuMbar*>(bar);
     return (__atomic_load_n(&m->completed, __ATOMIC_ACQUIRE) & 1u) != parity;
@@ -135,6 +136,20 @@ __device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity
             : "memory");
         if (!done) __nanosleep(200);
     } while (!done);
+}
+// The hardware suspends the thread until the phase completes or `ns` have passed: no probe instructions in between.
+__device__ __forceinline__ void mbar_wait_hint(uint64_t* bar, uint32_t parity, unsigned ns) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, 20000;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
 }
 __device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity);
 // Poll with a fixed sleep between probes: for a lone issuer thread whose wait is about one item long.
