@@ -103,7 +103,9 @@ constexpr int P4_TW = 128;
 constexpr int P4_N_TH = 3;
 constexpr int P4_TILE_HEIGHTS[P4_N_TH] = {16, 32, 24};
 inline int p4_th_index(int th) { return th == 16 ? 0 : (th == 24 ? 2 : 1); }
-constexpr int P4_PITCH = 192;        // = 16 banks (mod 32): a lane group crossing into the next source row stays conflict-free
+constexpr int P4_PITCH = 192;        // = 16 banks (mod 32): a lane group of the pair layout (32 windows = 16 words) crossing into the next source row stays
+                                     // conflict-free.  The quad layout's 32 windows span 32 words and do collide (ncu: 1.6 wavefronts per window load); a
+                                     // 256-byte pitch removes that but costs a ring stage - measured equal (profiles/r02_summary.md)
 constexpr int P4_PITCH_WIDE = 320;   // same residue; for maps whose 128-pixel tiles span up to 320 source bytes (a 2 x downscale:
                                      // config/slam_config.yaml's output_resolution done on the host instead of on the camera)
 constexpr int P4_MAX_ROWS = 96;

@@ -18,6 +18,7 @@
 #include "ti_pixel.cuh"
 #include "ti_tma.cuh"
 #include "ti_rectify_pair.cuh"
+#include <deque>
 
 namespace ti {
 
@@ -775,9 +776,7 @@ static int launch_rectify_direct(ti_ctx* ctx, const RectifyJob* jobs_in, int n_j
     RectParams P1{}, P3{};  // tiled launches for 1-channel and 3-channel sources
     Rect2Params P2{};       // fast mono launch (v2: thread-staged)
     Rect3Params PT{};       // fast mono launch (v3: TMA-pipelined)
-    Rect4Params PP{};       // fast mono launch (v4: pair windows)
-    Rect4Params PW{};       // the same for slots with wide source boxes (P4_PITCH_WIDE)
-    Rect4Params PQ{};       // the same for slots in the quad layout (four pixels per lane and window)
+    std::deque<Rect4Params> pair_groups;  // fast mono launches (v4: pair / quad windows), one per (staged row pitch, layout)
     Rect5Params PC{}, PCW{};  // fast 3-channel launches (BGR8 -> RGB8 windows): standard and wide source boxes
     std::vector<DirectJob> pair_overflow;  // pair-window jobs whose slot has an overflow list (mode = camera slot)
     const int thk = m3_th_index(ctx->tma_tile_h);
@@ -829,13 +828,24 @@ static int launch_rectify_direct(ti_ctx* ctx, const RectifyJob* jobs_in, int n_j
             }
         }
         if (pair_ok) {
+            // jobs of a launch stage rows of one pitch, in one layout
             const bool wide_slot = C.pitch4[th4] == P4_PITCH_WIDE;
-            Rect4Params& Q = wide_slot ? PW : C.quad4[th4] ? PQ : PP;  // jobs of a launch stage rows of one pitch, in one layout
-            if (Q.n_jobs < MAX_PAIR_JOBS) {
+            Rect4Params* Qp = nullptr;
+            for (Rect4Params& G : pair_groups)
+                if (G.pitch == C.pitch4[th4] && G.quad == (C.quad4[th4] ? 1 : 0) && G.n_jobs < MAX_PAIR_JOBS) Qp = &G;
+            if (!Qp) {
+                pair_groups.emplace_back();
+                Qp = &pair_groups.back();
+                *Qp = Rect4Params{};
+                Qp->pitch = C.pitch4[th4];
+                Qp->quad = C.quad4[th4] ? 1 : 0;
+            }
+            Rect4Params& Q = *Qp;
+            {
                 const int rc = wide_slot ? tma_encode_3d(ctx, &Q.map[Q.n_jobs], J.src, 4, C.src_w / 4, C.src_h, n_batch, (uint64_t)C.src_w, J.src_stride,
                                                          P4_PITCH_WIDE / 4, C.rows4_alloc[th4])
                                          : tma_encode_u8_3d(ctx, &Q.map[Q.n_jobs], J.src, C.src_w, C.src_h, n_batch, (uint64_t)C.src_w, J.src_stride,
-                                                            P4_PITCH, C.rows4_alloc[th4]);
+                                                            C.pitch4[th4], C.rows4_alloc[th4]);
                 if (rc != TI_OK) return rc;
                 Rect4JobDev D{};
                 D.lut4 = C.d_lut4[th4]; D.boxes4 = C.d_boxes4[th4]; D.exc4 = C.d_exc4[th4]; D.dst = J.dst; D.dst_stride = J.dst_stride;
@@ -844,8 +854,6 @@ static int launch_rectify_direct(ti_ctx* ctx, const RectifyJob* jobs_in, int n_j
                 Q.tiles_per_set += (uint32_t)(C.tiles4_x[th4] * C.tiles4_y[th4]);
                 Q.rows_alloc_max = std::max(Q.rows_alloc_max, D.rows_alloc);
                 Q.exc_max = std::max(Q.exc_max, D.exc_per_warp);
-                Q.pitch = C.pitch4[th4];
-                Q.quad = C.quad4[th4] ? 1 : 0;
                 Q.job[Q.n_jobs++] = D;
                 if (C.n_over4[th4] > 0)
                     pair_overflow.push_back(DirectJob{J.src, J.dst, J.src_stride, J.dst_stride, C.d_lut, lut_pitch, C.dst_w, C.dst_h, C.src_w, C.src_h, J.camera});
@@ -896,7 +904,7 @@ static int launch_rectify_direct(ti_ctx* ctx, const RectifyJob* jobs_in, int n_j
     }
     P1.n_batch = P3.n_batch = P2.n_batch = PT.n_batch = n_batch;
     PT.debug = ctx->debug;
-    PP.n_batch = PW.n_batch = PQ.n_batch = PC.n_batch = PCW.n_batch = n_batch;
+    PC.n_batch = PCW.n_batch = n_batch;
     if (PC.n_jobs) {
         const int rc = launch_rectify_c3(ctx, PC);
         if (rc != TI_OK) return rc;
@@ -905,17 +913,12 @@ static int launch_rectify_direct(ti_ctx* ctx, const RectifyJob* jobs_in, int n_j
         const int rc = launch_rectify_c3(ctx, PCW);
         if (rc != TI_OK) return rc;
     }
-    if (PW.n_jobs) {
-        const int rc = launch_rectify_pair(ctx, PW, th4);
-        if (rc != TI_OK) return rc;
-    }
-    if (PQ.n_jobs) {
-        const int rc = launch_rectify_pair(ctx, PQ, th4);
-        if (rc != TI_OK) return rc;
-    }
-    if (PP.n_jobs || PW.n_jobs || PQ.n_jobs) {
-        const int rc = PP.n_jobs ? launch_rectify_pair(ctx, PP, th4) : TI_OK;
-        if (rc != TI_OK) return rc;
+    if (!pair_groups.empty()) {
+        for (Rect4Params& G : pair_groups) {
+            G.n_batch = n_batch;
+            const int rc = launch_rectify_pair(ctx, G, th4);
+            if (rc != TI_OK) return rc;
+        }
         for (size_t i0 = 0; i0 < pair_overflow.size(); i0 += MAX_POINT_JOBS) {  // slots with more exceptions in some (tile, warp) than its list holds
             PointsParams Q{};
             for (size_t i = i0; i < std::min(pair_overflow.size(), i0 + MAX_POINT_JOBS); ++i) {

@@ -159,7 +159,7 @@ __global__ void __launch_bounds__(P4_THREADS, TH == 32 ? 3 : 4) rectify_mono_pai
     constexpr int RPW = TH / P4_CONSUMER_WARPS;  // tile rows per consumer warp
     constexpr uint32_t LUT_BYTES = (uint32_t)TH * P4_LUT_ROW_WORDS * 4u;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const uint32_t stage_bytes = (uint32_t)P.rows_alloc_max * PITCH;  // rows_alloc is a multiple of 8: 128-byte granular
+    const uint32_t stage_bytes = (uint32_t)P.rows_alloc_max * PITCH;  // rows_alloc is even: 128-byte granular for both pitches
     const uint32_t exc_buf_bytes = (uint32_t)P.exc_max * (P4_CONSUMER_WARPS * 16);
     const int S = P.stages;
     uint64_t* full = reinterpret_cast<uint64_t*>(smem);  // [S] box landed
@@ -425,7 +425,7 @@ int build_pair_tables(ti_ctx* ctx, CameraSlot& C, const std::vector<lut_t>& lut,
                 rows_max = std::max(rows_max, by1 - by0);
             }
         if (!ok) continue;
-        const int rows_alloc = std::max(8, (rows_max + 7) / 8 * 8);
+        const int rows_alloc = std::max(8, (rows_max + 1) / 2 * 2);  // a stage (rows x 192 or 320 bytes) must be a multiple of 128 bytes
         const int pitch = span_max > P4_PITCH ? P4_PITCH_WIDE : P4_PITCH;  // staged bytes per source row
 
         std::vector<uint32_t> lut4;
