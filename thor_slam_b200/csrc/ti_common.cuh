@@ -116,7 +116,6 @@ constexpr int P4_SMEM_HEADROOM_KB = 20;  // shared memory per SM the window kern
 constexpr int P4_LUT_ROW_WORDS = 192;  // per tile row: 32 lanes x 2 pairs x {window word, pixel a word, pixel b word}
 constexpr uint32_t P4_EXC_UNUSED = 0x80000000u;  // last word of an unused exception entry (no destination offset is -2^31)
 constexpr int P4_MAX_EXC = 32;         // exception entries per (tile, warp): one lane each in the per-frame fix-up pass
-constexpr int P4_EXC_BIAS = 128;       // added to an entry's destination offset (>= -4 * 31) so that the kernel adds it unsigned
 constexpr int P4_MAX_EXC_QUAD = 24;    // the same in the quad layout: 2 x 24 x 8 x 16 bytes of tables leave room for a 5-stage ring of 40-row boxes
                                        // beside three CTAs per SM (measured on the bench rig: 4 stages 0.765 of the copy peak, 5 stages 0.81)
 

@@ -50,7 +50,6 @@
 #include "ti_pair_dev.cuh"
 
 #include <cstring>
-#include <type_traits>
 
 namespace ti {
 
@@ -89,7 +88,7 @@ __device__ __forceinline__ void p4_blend(const Taps& T, const uint4& w, uint32_t
 // WHOLE: every pixel of the warp's rows exists and rows start on even addresses (16-bit stores).
 // PREFETCH: software pipeline, the windows of row q+1 are in flight while row q is blended and stored (8 more registers).
 // fixes (warp-uniform): some lane has an exception entry; i_fix: this lane has one, at shared address my_exc =
-// {window word, Wtop, Wbot, row * dst_w + column - 2 * lane + P4_EXC_BIAS}.  Its window is fetched ahead of the last row's blend so that the
+// {window word, Wtop, Wbot, row * dst_w + column - 2 * lane}.  Its window is fetched ahead of the last row's blend so that the
 // latency of the dependent loads hides behind that row; its store follows the row loop's stores (__syncwarp).
 // DSTW > 0: the destination row pitch is this compile-time constant, so row q is an immediate offset from the lane's first-row pointer.
 template <int RPW, bool WHOLE, bool PREFETCH, bool HALF_LOADS = false, int DSTW = 0, int PITCH = P4_PITCH, bool QUAD = false, int FIXQ = RPW - 1>
@@ -100,13 +99,13 @@ __device__ __forceinline__ void p4_rows(const uint4 (&w0)[RPW], const uint4 (&w1
     // QUAD: pixels 2-3 of the lane read pixel 0-1's window (mw[q].y is only their selector)
     Taps A = p4_fetch<PITCH>(base, mw[0].x), B = (HALF_LOADS || QUAD) ? A : p4_fetch<PITCH>(base, mw[0].y);
     uint8_t* const lane_dst = dp;  // this lane's first pixel of the warp's first row
-    uint4 fe;
-    Taps X;
+    uint4 fe = make_uint4(0u, 0u, 0u, 0u);
+    Taps X = A;
 #pragma unroll
     for (int q = 0; q < RPW; ++q) {
         Taps An = A, Bn = B;
         if (PREFETCH && q + 1 < RPW) { An = p4_fetch<PITCH>(base, mw[q + 1].x); Bn = (HALF_LOADS || QUAD) ? An : p4_fetch<PITCH>(base, mw[q + 1].y); }
-        if (q == FIXQ && fixes) {  // warp-uniform; every lane reads a USED entry (my_exc is clamped to the last one), only i_fix lanes store
+        if (q == FIXQ && fixes && i_fix) {
             fe = p4_lds128(my_exc);
             X = p4_fetch<PITCH>(base, fe.x);
         }
@@ -149,7 +148,7 @@ __device__ __forceinline__ void p4_rows(const uint4 (&w0)[RPW], const uint4 (&w1
         if (i_fix) {
             const uint32_t xt = p4_prmt(X.t0, X.t1, fe.x), xb = p4_prmt(X.b0, X.b1, fe.x);
             const uint32_t r = __dp2a_lo(fe.z, xb, __dp2a_lo(fe.y, xt, 32768u));
-            st_stream_b8(lane_dst + (size_t)fe.w - P4_EXC_BIAS, r >> 16);  // offset (+ bias: never negative) relative to the repairing lane's own first pixel
+            st_stream_b8(lane_dst + (int32_t)fe.w, r >> 16);  // offset relative to the repairing lane's own first pixel
         }
     }
 }
@@ -160,7 +159,7 @@ __global__ void __launch_bounds__(P4_THREADS, TH == 32 ? 3 : 4) rectify_mono_pai
     constexpr int RPW = TH / P4_CONSUMER_WARPS;  // tile rows per consumer warp
     constexpr uint32_t LUT_BYTES = (uint32_t)TH * P4_LUT_ROW_WORDS * 4u;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const uint32_t stage_bytes = P.stage_bytes;  // rows_alloc_max x PITCH; rows_alloc is even: 128-byte granular for both pitches
+    const uint32_t stage_bytes = (uint32_t)P.rows_alloc_max * PITCH;  // rows_alloc is even: 128-byte granular for both pitches
     const uint32_t exc_buf_bytes = (uint32_t)P.exc_max * (P4_CONSUMER_WARPS * 16);
     const int S = P.stages;
     uint64_t* full = reinterpret_cast<uint64_t*>(smem);  // [S] box landed
@@ -242,7 +241,8 @@ __global__ void __launch_bounds__(P4_THREADS, TH == 32 ? 3 : 4) rectify_mono_pai
     const p4_addr_t sm0 = p4_addr(smem);
     const p4_addr_t stage_first = sm0 + 256;
     const bool skip_blend = DEBUG && (P.debug & 1) != 0;
-    int stage = 0;  // current stage of the ring: its box is at stage_first + stage * stage_bytes, its `full` barrier at sm0 + 8 * stage (`empty` 64 bytes further)
+    p4_addr_t base = stage_first, bar = sm0;  // current stage, its `full` barrier (`empty` is 64 bytes further)
+    int s_left = S;                            // stages until the ring wraps
     uint32_t phase = 0;
     for (uint32_t k = 0; k < units_mine; ++k) {
         const P4Unit U = p4_unit(P, k);
@@ -269,36 +269,25 @@ __global__ void __launch_bounds__(P4_THREADS, TH == 32 ? 3 : 4) rectify_mono_pai
             }
         }
         // this lane's exception entry (if any): entries are dense from 0, an unused one has P4_EXC_UNUSED in its last word (NOT all
-        // ones: -1 is a legitimate destination offset - the pixel left of the repairing lane's first one).  Lanes without one read
-        // the warp's last used entry (a broadcast) so that the fetch needs no predicates; only lanes with one store.
-        const p4_addr_t exc0 = sm0 + 256u + (uint32_t)S * stage_bytes + LUT_BYTES + (k & 1u) * exc_buf_bytes + (uint32_t)(warp * J.exc_per_warp) * 16u;
-        const bool i_fix = lane < J.exc_per_warp && p4_lds<12>(exc0 + (uint32_t)lane * 16u) != P4_EXC_UNUSED;
-        const int n_fix = __popc(__ballot_sync(0xFFFFFFFFu, i_fix));
-        const bool warp_fixes = n_fix != 0;  // warp-uniform
-        const p4_addr_t my_exc = exc0 + (uint32_t)min(lane, max(n_fix, 1) - 1) * 16u;
+        // ones: -1 is a legitimate destination offset - the pixel left of the repairing lane's first one)
+        const p4_addr_t my_exc = sm0 + 256u + (uint32_t)S * stage_bytes + LUT_BYTES + (k & 1u) * exc_buf_bytes +
+                                 (uint32_t)(warp * J.exc_per_warp + lane) * 16u;
+        const bool i_fix = lane < J.exc_per_warp && p4_lds<12>(my_exc) != P4_EXC_UNUSED;
+        const bool warp_fixes = __ballot_sync(0xFFFFFFFFu, i_fix) != 0u;  // warp-uniform
         __syncwarp();  // every lane's reads of the LUT slice are ordered before the release below
         if (lane == 0) mbar_arrive(lut_empty);
 
-        // one frame: wait for its box, blend, release the stage, step to the next stage of the ring
-        auto frame = [&](auto whole_tag) {
-            constexpr bool WHOLE = decltype(whole_tag)::value;
-            const p4_addr_t bar = sm0 + 8u * (uint32_t)stage, base = stage_first + (uint32_t)stage * stage_bytes;
+        for (uint32_t f = 0; f < U.nb; ++f) {
             p4_wait(bar, phase);
             if (!skip_blend) {
                 if (DEBUG && (P.debug & 8)) p4_rows<RPW, true, TH == 32, true, 0, PITCH, QUAD>(w0, w1, mw, base, dp, dst_w, live_rows, live_cols, lane, warp_fixes, i_fix, my_exc);
-                else if (WHOLE) p4_rows<RPW, true, TH == 32, false, DSTW, PITCH, QUAD, QUAD ? RPW - 3 : RPW - 1>(w0, w1, mw, base, dp, dst_w, live_rows, live_cols, lane, warp_fixes, i_fix, my_exc);
+                else if (whole) p4_rows<RPW, true, TH == 32, false, DSTW, PITCH, QUAD, QUAD ? RPW - 3 : RPW - 1>(w0, w1, mw, base, dp, dst_w, live_rows, live_cols, lane, warp_fixes, i_fix, my_exc);
                 else p4_rows<RPW, false, false, false, 0, PITCH, QUAD>(w0, w1, mw, base, dp, dst_w, live_rows, live_cols, lane, warp_fixes, i_fix, my_exc);
             }
             p4_warp_arrive(bar + 64);
-            dp += DSTW > 0 ? P.dst_stride : dst_stride;
-            if (++stage == S) { stage = 0; phase ^= 1u; }
-        };
-        if (whole) {
-#pragma unroll 1
-            for (uint32_t f = 0; f < U.nb; ++f) frame(std::true_type{});
-        } else {
-#pragma unroll 1
-            for (uint32_t f = 0; f < U.nb; ++f) frame(std::false_type{});
+            dp += dst_stride;
+            bar += 8; base += stage_bytes;
+            if (--s_left == 0) { s_left = S; bar -= 8u * (uint32_t)S; base -= (uint32_t)S * stage_bytes; phase ^= 1u; }
         }
     }
 }
@@ -320,8 +309,7 @@ int launch_rectify_pair(ti_ctx* ctx, Rect4Params& P, int th_index) {
     // every job of the launch writes rows of the same common pitch: use the kernel whose row stores are immediate offsets
     int dw = P.job[0].dst_w;
     for (int j = 1; j < P.n_jobs; ++j)
-        if (P.job[j].dst_w != dw || P.job[j].dst_stride != P.job[0].dst_stride) dw = 0;
-    P.dst_stride = P.job[0].dst_stride;
+        if (P.job[j].dst_w != dw) dw = 0;
     if (P.quad) {
         if (TH != 32 || wide) return fail(ctx, TI_ESTATE, "rectify: the quad layout exists for 32-row tiles of the standard pitch only");
         kern = ctx->debug  ? (Kern)rectify_mono_pair_kernel<32, true, 0, P4_PITCH, true>
@@ -343,7 +331,6 @@ int launch_rectify_pair(ti_ctx* ctx, Rect4Params& P, int th_index) {
     // kernel by a third (measured: 14 us per step on the fusing rank).  Ring depth beyond four stages buys nothing (round 1).
     while (stages > 2 && (256 + (size_t)stages * stage + lut_bytes + 1024) * want_ctas > (228 - P4_SMEM_HEADROOM_KB) * 1024) --stages;
     P.stages = stages;
-    P.stage_bytes = (uint32_t)stage;
     P.debug = ctx->debug;
     const size_t smem = 256 + (size_t)stages * stage + lut_bytes;
     TI_CUDA(ctx, ensure_dynamic_smem(kern, smem, ctx->device));
@@ -464,7 +451,7 @@ int build_pair_tables(ti_ctx* ctx, CameraSlot& C, const std::vector<lut_t>& lut,
             ex.push_back(wb);
             // destination of the pixel relative to the first pixel of the lane that will repair it (entry i -> lane i)
             const int fix_lane = (int)(ex.size() / 4);
-            ex.push_back((uint32_t)((row % RPW) * dst_w + col - lane_px * fix_lane + P4_EXC_BIAS));
+            ex.push_back((uint32_t)((row % RPW) * dst_w + col - lane_px * fix_lane));
             return true;
         };
         // pair layout: lane L owns pixels (2L, 2L+1) and (64+2L, 65+2L) of a tile row, a window per pair

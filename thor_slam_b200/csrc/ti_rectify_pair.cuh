@@ -32,8 +32,6 @@ struct Rect4Params {
     int quad;            // 1: every job of the launch uses the quad layout (4 consecutive pixels per lane, one window per row)
     int exc_max;         // largest exc_per_warp of the launch
     int stages;
-    uint32_t stage_bytes;   // rows_alloc_max x pitch (launcher)
-    uint64_t dst_stride;    // DSTW > 0 kernels: the frame stride every job of the launch shares (launcher checks)
     int debug;           // bring-up switches (TI_OPT_DEBUG): 1 = consumers skip the blend, 2 = issuer skips the loads; 0 in production
 };
 
