@@ -543,9 +543,10 @@ int build_pair_tables(ti_ctx* ctx, CameraSlot& C, const std::vector<lut_t>& lut,
             return true;
         };
         // Quads where nearly all their exceptions fit the lists: a strongly bent map (fisheye4 at 1280 x 800: 22 000 overflow pixels with
-        // quads, a few hundred with pairs) is faster with pairs (measured 0.46 against 0.54 of the copy peak).
+        // quads, a few hundred with pairs) is faster with pairs (measured 0.46 against 0.57 of the copy peak).  The per-pixel pass costs
+        // about 9 ps per overflow pixel and frame, quads save about 3.6 ns per 1 MPix frame: break-even near 0.6 % of the image.
         bool quad = false;
-        if (TH == 32 && pitch == P4_PITCH && ctx->rectify_quad) quad = fill_quads() && over.size() <= (size_t)dst_w * dst_h / 512;
+        if (TH == 32 && pitch == P4_PITCH && ctx->rectify_quad) quad = fill_quads() && over.size() <= (size_t)dst_w * dst_h / 256;
         if (!quad) ok = fill_pairs();
         if (!ok) continue;
         size_t e_max = 0;
