@@ -53,10 +53,10 @@ N_CAMERAS = 4  # stereo sources -> 8 streams
 STREAMS = 2 * N_CAMERAS
 PX_PER_SET = STREAMS * W * H
 ALGO_BYTES_PER_PX = 2  # mono8 -> rectified mono8
-# dram__bytes_read.sum + dram__bytes_write.sum of ONE rectify_mono_pair_kernel launch over 64 frame sets, from the
-# `ncu --set full` capture of round 2 (profiles/r02_ncu_rect_pair.txt, tools/profile_r02.sh): 574.73 MB + 482.23 MB = 1.008 x algorithmic
-NCU_TRAFFIC_BYTES_PER_FRAME_SET = (574.733824e6 + 482.234112e6) / 64
-KERNEL_BY_VARIANT = {4: "rectify_mono_pair_kernel<32,false,1280>", 3: "rectify_mono_tma_kernel<32,false>", 2: "rectify_mono_kernel", 1: "rectify_tile_kernel<1>"}
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE rectify_mono_pair_kernel launch (quad layout) over 64 frame sets of this rig,
+# from the `ncu --set full` capture of round 2 (profiles/r02_ncu_rect_quad.txt): 577.31 MB + 479.36 MB = 1.008 x algorithmic
+NCU_TRAFFIC_BYTES_PER_FRAME_SET = (577.310720e6 + 479.360000e6) / 64
+KERNEL_BY_VARIANT = {4: "rectify_mono_pair_kernel<32,false,1280,192,QUAD>", 3: "rectify_mono_tma_kernel<32,false>", 2: "rectify_mono_kernel", 1: "rectify_tile_kernel<1>"}
 FALLBACK_HBM_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md fallback
 _JSON_OUT = sys.stdout
 
@@ -359,11 +359,13 @@ def run_ours(args) -> None:
         sampler2.start()
     s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ts_begin = time.perf_counter()
+    sus_launches0 = ctx.launch_count
     s0.record(stream)
     for _ in range(sus_steps):
         ctx.ingest(specs)
     s1.record(stream)
     barrier()
+    sus_launches = ctx.launch_count - sus_launches0
     ts_end = time.perf_counter()
     sus_clocks = sampler2.stop(ts_begin, ts_end) if rank == 0 else None
     tsus = torch.tensor([s0.elapsed_time(s1)], dtype=torch.float64, device="cuda")
@@ -371,7 +373,7 @@ def run_ours(args) -> None:
         dist.all_reduce(tsus, op=dist.ReduceOp.MAX)
     sus_ms = float(tsus.item())
     sustained = {"steps": sus_steps, "seconds": round(sus_ms * 1e-3, 3), "ms_per_step": sus_ms / sus_steps, "value": world * B * sus_steps / (sus_ms * 1e-3),
-                 "gpu_launches": sus_steps, "clocks": sus_clocks}
+                 "gpu_launches": sus_launches, "clocks": sus_clocks}
 
     # ---- end to end through the host-buffer API ("e2e") -----------------------------------------
     # A capture loop double-buffers its host frames: batch k+1 is submitted before batch k is waited for, so one
@@ -454,12 +456,12 @@ def run_ours(args) -> None:
             "gpu_launches": launches,
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": NCU_TRAFFIC_BYTES_PER_FRAME_SET * B, "traffic_source": "ncu --set full, profiles/r02_ncu_rect_pair.txt (scaled per frame set)",
-                         "kernel": KERNEL_BY_VARIANT[plan["variant"]], "kernel_plan": plan, "algorithmic_bytes_per_launch": algo_bytes,
+                         "traffic": NCU_TRAFFIC_BYTES_PER_FRAME_SET * B, "traffic_source": "ncu --set full, profiles/r02_ncu_rect_quad.txt (scaled per frame set)",
+                         "kernel": KERNEL_BY_VARIANT[plan["variant"]].replace("QUAD", "true" if plan.get("pixels_per_window") == 4 else "false"), "kernel_plan": plan, "algorithmic_bytes_per_launch": algo_bytes,
                          "peak_source": peak_src, "frac_of_8000_datasheet": achieved / 8000.0,
                          "sustained_achieved": algo_bytes / (sustained["ms_per_step"] * 1e-3) / 1e9,
                          "sustained_frac": algo_bytes / (sustained["ms_per_step"] * 1e-3) / 1e9 / peak,
-                         "note": "per-rank launch; duration = max-over-ranks ms_per_step (one launch per step)"},
+                         "note": "per-rank launches; duration = max-over-ranks ms_per_step (per step: ONE remap launch for the 8 streams + one per-pixel repair launch for the ~1 650 pixels per frame set whose exception lists overflowed; the repair pass is inside the timed step)"},
             "cpu_baseline": None,
             "sustained": sustained,
         }
@@ -777,12 +779,14 @@ def run_config5_exchange(args, ctx, sources, rank: int, world: int, barrier, pea
             e1.synchronize()
             return e0.elapsed_time(e1) / n
 
-        run_nccl(3)
+        run_nccl(3)  # CloudGather asks the library for NCCL's shared-memory headroom (TI_OPT_SMEM_HEADROOM_KB 36: one ring stage less)
         ms_n = max_ms(run_nccl(steps))
+        ctx.set_option(ctx.OPT_SMEM_HEADROOM_KB, ctx.SMEM_HEADROOM_DEFAULT_KB)  # the variants below run beside the library's own kernels only
+        gat._headroom_set = False
         per_rank = last_counts[0]
         res["overlapped_nccl"] = {"ms_per_step": round(ms_n, 5), "frame_sets_per_sec": fs_per_sec(ms_n), "vs_compute_only": round(ms_c / ms_n, 4),
                                   "bytes_into_root_per_step": 8 * (sum(per_rank) - per_rank[0]),
-                                  "kind": "ti_gather_counts_begin/finish + ti_gather_records (grouped ncclSend/ncclRecv) on the exchange stream"}
+                                  "kind": "ti_gather_counts_begin/finish + ti_gather_records (grouped ncclSend/ncclRecv) on the exchange stream; remap grids leave 36 KB of shared memory per SM to NCCL"}
         if rank == 0:  # the checker, outside the timed region: last step's fused list against the oracle, every rank's frames
             n_tot = sum(per_rank)
             got = np.sort(Config5.first_sets(gathered[(steps - 1) % NB][:n_tot].cpu().numpy().view(np.uint64), check_sets))

@@ -137,6 +137,7 @@ int ti_set_option(ti_ctx* ctx, int option, int value) {
         case TI_OPT_LUT_PREFETCH: ctx->lut_prefetch = value != 0; return TI_OK;
         case TI_OPT_PUSH_BLOCKS: ctx->push_blocks = value > 0 ? value : 0; return TI_OK;
         case TI_OPT_PUSH_TMA: ctx->push_tma = value != 0; return TI_OK;
+        case TI_OPT_SMEM_HEADROOM_KB: ctx->smem_headroom_kb = std::max(0, std::min(value, 128)); return TI_OK;
         case TI_OPT_RECTIFY_QUAD:
             ctx->rectify_quad = value != 0;
             ctx->quad_exc_cap = value >= 2 ? std::min(value, (int)ti::P4_MAX_EXC) : (int)ti::P4_MAX_EXC_QUAD;

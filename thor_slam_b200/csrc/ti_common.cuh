@@ -113,6 +113,9 @@ constexpr int P4_CONSUMER_WARPS = 8;
 constexpr int P4_THREADS = (P4_CONSUMER_WARPS + 1) * 32;  // consumers + TMA issuer
 constexpr int P4_MAX_STAGES = 8;
 constexpr int P4_SMEM_HEADROOM_KB = 20;  // shared memory per SM the window kernels leave to co-resident exchange kernels
+constexpr int P4_SMEM_HEADROOM_NCCL_KB = 36;  // ... what a host that overlaps NCCL with ingest should ask for (TI_OPT_SMEM_HEADROOM_KB): NCCL's send/recv CTAs need more than
+                                              // the library's own 12 KB copy CTAs (measured at N = 8: with 23 KB left NCCL waited for a whole persistent grid
+                                              // to drain - 0.40 of the job without exchange; with 34 KB left 0.80)
 constexpr int P4_LUT_ROW_WORDS = 192;  // per tile row: 32 lanes x 2 pairs x {window word, pixel a word, pixel b word}
 constexpr uint32_t P4_EXC_UNUSED = 0x80000000u;  // last word of an unused exception entry (no destination offset is -2^31)
 constexpr int P4_MAX_EXC = 32;         // exception entries per (tile, warp): one lane each in the per-frame fix-up pass
@@ -210,6 +213,7 @@ struct ti_ctx {
     // scratch for two-pass paths (BGR -> gray ahead of the mono remap); grown on demand, never visible to the caller
     void* scratch = nullptr;
     size_t scratch_cap = 0;
+    int smem_headroom_kb = ti::P4_SMEM_HEADROOM_KB;  // TI_OPT_SMEM_HEADROOM_KB: shared memory per SM the persistent window kernels leave free
     bool rectify_quad = true;  // calibration upload tries the quad layout of the pair-window kernel first
     int quad_exc_cap = ti::P4_MAX_EXC_QUAD;  // TI_OPT_RECTIFY_QUAD values 2..32 set it (bring-up: ring depth against overflow pixels)
     int l2_scratch_kb = 0;  // two-pass rectify: scratch per chunk of the batch; 0 = the whole batch in one chunk (chunks that fit the

@@ -225,7 +225,7 @@ int launch_rectify_c3(ti_ctx* ctx, Rect5Params& P) {
     // copy CTA, one-warp flag kernels, each with its 1 KB of system shared memory) run BESIDE this kernel's resident CTAs.  When
     // they did not fit, whichever came first displaced a CTA of this persistent grid, which then started late and stretched the
     // kernel by a third (measured: 14 us per step on the fusing rank).  Ring depth beyond four stages buys nothing (round 1).
-    while (stages > 2 && (256 + (size_t)stages * stage + tail + 1024) * 3 > (228 - P4_SMEM_HEADROOM_KB) * 1024) --stages;
+    while (stages > 2 && (256 + (size_t)stages * stage + tail + 1024) * 3 > (228 - ctx->smem_headroom_kb) * 1024) --stages;
     P.stages = stages;
     const size_t smem = 256 + (size_t)stages * stage + tail;
     if (smem > 220 * 1024) return fail(ctx, TI_EINVAL, "rectify (3-channel): source boxes of %d rows do not fit shared memory", P.rows_alloc_max);

@@ -383,6 +383,9 @@ class IngestContext:
     OPT_L2_SCRATCH_KB = 10
     OPT_PUSH_TMA = 11
     OPT_RECTIFY_QUAD = 12
+    OPT_SMEM_HEADROOM_KB = 13
+    SMEM_HEADROOM_DEFAULT_KB = 20
+    SMEM_HEADROOM_NCCL_KB = 36
 
     def nccl_barrier(self) -> None:
         self._check(self.lib.ti_nccl_barrier(self._h))
