@@ -239,6 +239,33 @@ def _rotated_maps(w: int, h: int, deg: float):
     return ((xx - cx) * c - (yy - cy) * s + cx).astype(np.float32), ((xx - cx) * s + (yy - cy) * c + cy).astype(np.float32)
 
 
+def test_layout_choice_of_the_pair_window_kernel_emulated(emu_backend):
+    """The layout of a slot is decided when its map is uploaded: four pixels per window where nearly all exceptions fit the lists
+    (a mildly rotated stereo map), two where they do not (a sheared map that changes source row every six pixels), two when the host
+    asks for pairs; the exception capacity follows TI_OPT_RECTIFY_QUAD.  Every choice gives the same bytes (check_rectify runs both)."""
+    ctx = emu_backend.ctx
+    mx, my = _rotated_maps(256, 96, 1.5)
+    try:
+        ctx.upload_rectify_map(21, mx, my, (256, 96))
+        plan = ctx.rectify_plan(21)
+        assert plan["variant"] == 4 and plan["pixels_per_window"] == 4 and 0 < plan["exceptions_per_warp"] <= 24, plan
+        ctx.set_option(ctx.OPT_RECTIFY_QUAD, 8)  # quads, at most 8 exception entries per (tile, warp): the rest overflows
+        ctx.upload_rectify_map(21, mx, my, (256, 96))
+        plan8 = ctx.rectify_plan(21)
+        assert plan8["pixels_per_window"] == 2 or (plan8["exceptions_per_warp"] <= 8 and plan8["overflow_pixels"] > plan["overflow_pixels"]), plan8
+        ctx.set_option(ctx.OPT_RECTIFY_QUAD, 0)
+        ctx.upload_rectify_map(21, mx, my, (256, 96))
+        assert ctx.rectify_plan(21)["pixels_per_window"] == 2
+        ctx.set_option(ctx.OPT_RECTIFY_QUAD, 1)
+        sx, sy = cases.shear_maps(256, 96)
+        ctx.upload_rectify_map(21, sx, sy, (256 + 16, 160))
+        plan_s = ctx.rectify_plan(21)
+        assert plan_s["variant"] < 4 or plan_s["pixels_per_window"] == 2, plan_s
+    finally:
+        ctx.set_option(ctx.OPT_RECTIFY_QUAD, 1)
+    cases.check_rectify(emu_backend, 21, mx, my, "mono8", "mono8", 256, 96, n=2, expect_variant=4)
+
+
 def test_rotated_map_overflows_the_exception_table_emulated(emu_backend):
     """20 degrees of roll: a third of the pixel pairs straddle two source rows.  With 32-row tiles the surplus over the 32
     exceptions a (tile, warp) holds exceeds 3 % of the image -> the slot leaves the pair-window kernel, and the plan says so.
