@@ -252,6 +252,12 @@ int ti_ingest_host(ti_ctx* ctx, const ti_stream* streams, int n_streams, int n_b
 int ti_ingest_host_submit(ti_ctx* ctx, const ti_stream* streams, int n_streams, int n_batch, int chunk, uint64_t* ticket);
 int ti_ingest_host_wait(ti_ctx* ctx, uint64_t ticket);
 
+/* Plumbing for hosts that stage frames themselves (the drop-in rig: one pinned slot per stream and queue entry): one asynchronous
+ * copy of `bytes` between any two of {pinned host, device} buffers on `cuda_stream` (a cudaStream_t; NULL = the context's stream).
+ * Replaces nothing of the reference - its frames never leave the host (thor_slam/camera/rig.py:297-356) - and exists because a
+ * framework's stream context switch costs 40 us per copy where this call costs 2. */
+int ti_copy_async(ti_ctx* ctx, void* dst, const void* src, uint64_t bytes, void* cuda_stream);
+
 /* ---- multi-GPU: one process per GPU ------------------------------------------------------ */
 
 /* NCCL is dlopen()ed on first use.  id: 128 bytes, created on rank 0, shipped by the caller

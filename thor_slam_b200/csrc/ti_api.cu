@@ -741,4 +741,13 @@ int ti_ingest_host_wait(ti_ctx* ctx, uint64_t ticket) {
     return TI_OK;
 }
 
+int ti_copy_async(ti_ctx* ctx, void* dst, const void* src, uint64_t bytes, void* cuda_stream) {
+    if (!ctx) return TI_EINVAL;
+    if (bytes == 0) return TI_OK;
+    if (!dst || !src) return fail(ctx, TI_EINVAL, "ti_copy_async: null buffer");
+    TI_CUDA(ctx, cudaSetDevice(ctx->device));
+    TI_CUDA(ctx, cudaMemcpyAsync(dst, src, (size_t)bytes, cudaMemcpyDefault, cuda_stream ? (cudaStream_t)cuda_stream : ctx->stream));
+    return TI_OK;
+}
+
 }  // extern "C"

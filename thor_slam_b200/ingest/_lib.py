@@ -77,6 +77,7 @@ SIGNATURES: dict[str, tuple] = {
     "ti_ingest_host": (C.c_int, [C.c_void_p, C.POINTER(TiStream), C.c_int, C.c_int, C.c_int]),
     "ti_ingest_host_submit": (C.c_int, [C.c_void_p, C.POINTER(TiStream), C.c_int, C.c_int, C.c_int, C.POINTER(C.c_uint64)]),
     "ti_ingest_host_wait": (C.c_int, [C.c_void_p, C.c_uint64]),
+    "ti_copy_async": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]),
     "ti_nccl_unique_id": (C.c_int, [C.c_void_p]),
     "ti_nccl_init": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int]),
     "ti_gather_clouds": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_uint64), C.c_int]),

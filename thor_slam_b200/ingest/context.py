@@ -291,6 +291,27 @@ class IngestContext:
         """Block until the batch submitted under ``ticket`` has landed in its destination buffers."""
         self._check(self.lib.ti_ingest_host_wait(self._h, ticket))
 
+    def copy_async(self, dst: Any, src: Any, stream: int | None = None) -> None:
+        """One asynchronous copy between pinned-host / device tensors of equal byte size on CUDA stream ``stream`` (a raw handle;
+        None = the context's stream) - ``ti_copy_async``, the rig's staging copies without a framework stream switch."""
+        nbytes = src.numel() * src.element_size()
+        if dst.numel() * dst.element_size() != nbytes:
+            raise ValueError("copy_async: source and destination differ in size")
+        self._check(self.lib.ti_copy_async(self._h, C.c_void_p(self._ptr(dst, host_ok=True)), C.c_void_p(self._ptr(src, host_ok=True)), nbytes,
+                                           C.c_void_p(stream) if stream else None))
+
+    def copy_plan(self, dst: Any, src: Any) -> tuple[int, int, int]:
+        """(dst address, src address, bytes) of a copy that will be issued many times: :meth:`copy_planned` then costs one foreign call."""
+        nbytes = src.numel() * src.element_size()
+        if dst.numel() * dst.element_size() != nbytes:
+            raise ValueError("copy_plan: source and destination differ in size")
+        return int(self._ptr(dst, host_ok=True)), int(self._ptr(src, host_ok=True)), int(nbytes)
+
+    def copy_planned(self, plan: tuple[int, int, int], stream: int | None = None) -> None:
+        rc = self.lib.ti_copy_async(self._h, plan[0], plan[1], plan[2], stream)
+        if rc != TI_OK:
+            self._check(rc)
+
     # -- voxel down-sampled cloud ------------------------------------------------
     def set_voxel_grid(self, voxel_size_m: float = 0.05, max_depth_mm: int = 10000) -> None:
         """Grid of the rig-wide cloud; defaults are nvblox's (``launch/thor_nvblox.launch.py:26-31``). ``max_depth_mm`` 0 = no cap."""

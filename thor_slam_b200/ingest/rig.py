@@ -74,6 +74,8 @@ class _Stream:
     mask: Any = None
     count: Any = None
     gen: list = field(default_factory=list)        # per slot: how many times it has been staged
+    up_plan: list = field(default_factory=list)    # per slot: (device address, pinned address, bytes) of the upload
+    down_plan: list = field(default_factory=list)  # per slot: the download of the ingest output into its pinned mirror
 
 
 @dataclass
@@ -127,6 +129,8 @@ class IngestRig(CameraRig):
         self._next_camera = 0
         self._copy_stream = None if self._emulated else torch.cuda.Stream(device=self._device)
         self._down_stream = None if self._emulated else torch.cuda.Stream(device=self._device)
+        self._copy_handle = None if self._emulated else self._copy_stream.cuda_stream   # raw cudaStream_t of the two
+        self._down_handle = None if self._emulated else self._down_stream.cuda_stream
         self._slot_ingested: dict[tuple[str, int], Any] = {}   # (source, slot) -> event: the kernels that read the slot are done
         self._prepared: dict[tuple, Any] = {}                  # slots of a frame set -> packed ti_stream array
         self._rect: dict[str, list[dict]] = {}                 # per source, per stream: {"R", "P"} of the rectification
@@ -177,6 +181,9 @@ class IngestRig(CameraRig):
         st.out = self._alloc((slots, *F.frame_shape(st.dst_format, dw, dh)), st.dst_format)
         st.out_host = self._alloc((slots, *F.frame_shape(st.dst_format, dw, dh)), st.dst_format, pinned=True)
         st.gen = [0] * slots
+        # the staging copies of every slot, resolved once: (dst address, src address, bytes)
+        st.up_plan = [self._ctx.copy_plan(st.dev[i], st.host[i]) for i in range(slots)]
+        st.down_plan = [self._ctx.copy_plan(st.out_host[i], st.out[i]) for i in range(slots)]
         if st.kind == F.KIND_BACKPROJECT:
             st.mask = self._alloc((slots, dh, dw), F.MONO8)
             st.count = torch.zeros((slots,), dtype=torch.int32, device=self._device)
@@ -238,8 +245,9 @@ class IngestRig(CameraRig):
         if self._emulated:
             st.dev[slot].copy_(st.host[slot])
             return
-        with torch.cuda.stream(self._copy_stream):
-            st.dev[slot].copy_(st.host[slot], non_blocking=True)
+        # through the library on the copy stream's raw handle: a torch stream context + copy_ costs 40 us per frame (measured,
+        # tools/rig_profile.py), this call 2
+        self._ctx.copy_planned(st.up_plan[slot], self._copy_handle)
 
     def _stage(self, st: _Stream, slot: int, image: np.ndarray) -> None:
         self._stage_host(st, slot, image)
@@ -300,10 +308,9 @@ class IngestRig(CameraRig):
                 ready = torch.cuda.Event()
                 ready.record(cur)
                 self._down_stream.wait_event(ready)
-                with torch.cuda.stream(self._down_stream):  # outputs -> pinned mirrors, under whatever the caller does next
-                    for name, fs in todo:
-                        for st in self._streams[name]:
-                            st.out_host[fs.slot].copy_(st.out[fs.slot], non_blocking=True)
+                for name, fs in todo:  # outputs -> pinned mirrors on the download stream, under whatever the caller does next
+                    for st in self._streams[name]:
+                        self._ctx.copy_planned(st.down_plan[fs.slot], self._down_handle)
                 mirror = torch.cuda.Event()
                 mirror.record(self._down_stream)
             else:
