@@ -59,7 +59,7 @@ def test_config2_eight_mono_streams_one_launch(gpu_backend):
     plans = [be.ctx.rectify_plan(slot) for slot in range(8)]
     repairs = int(any(p["overflow_pixels"] > 0 for p in plans))
     layouts = len({(p["pitch"], p["pixels_per_window"]) for p in plans})  # slots of one layout share a launch; this rig has one
-    assert layouts == 1, plans
+    assert layouts == 1 and plans[0]["pixels_per_window"] == 4, plans  # the headline rig runs the quad layout
     assert be.ctx.launch_count - launches0 == 1 + repairs, "8 streams x n frame sets must be ONE remap kernel launch"
     for s, out in enumerate(outs):
         got = be.host(out)
