@@ -180,3 +180,22 @@ def test_errors(emu_backend):
         ctx.upload_rectify_map(99, np.zeros((4, 4), np.float32), np.zeros((4, 4), np.float32), (4, 4))
     with pytest.raises(ValueError):
         ctx.convert(np.zeros((1, 9, 6), np.uint8), np.zeros((1, 6, 6, 3), np.uint8), "nv12", "rgb8", 5, 6)  # odd NV12
+
+
+def test_copy_async_and_plans(emu_backend):
+    """ti_copy_async (the rig's staging copies): whole buffers, pre-resolved plans, size mismatch, empty copy."""
+    import torch
+
+    ctx = emu_backend.ctx
+    src = torch.arange(4096, dtype=torch.uint8).reshape(4, 1024)
+    dst = torch.zeros_like(src)
+    ctx.copy_async(dst[1], src[2])
+    assert torch.equal(dst[1], src[2]) and not dst[0].any()
+    plan = ctx.copy_plan(dst[3], src[0])
+    ctx.copy_planned(plan)
+    assert torch.equal(dst[3], src[0])
+    ctx.copy_async(dst[0, :0], src[0, :0])  # nothing to copy: accepted
+    with pytest.raises(ValueError):
+        ctx.copy_async(dst[0], src[0, :512])
+    with pytest.raises(ValueError):
+        ctx.copy_plan(dst, src[0])
