@@ -779,14 +779,12 @@ def run_config5_exchange(args, ctx, sources, rank: int, world: int, barrier, pea
             e1.synchronize()
             return e0.elapsed_time(e1) / n
 
-        run_nccl(3)  # CloudGather asks the library for NCCL's shared-memory headroom (TI_OPT_SMEM_HEADROOM_KB 36: one ring stage less)
+        run_nccl(3)
         ms_n = max_ms(run_nccl(steps))
-        ctx.set_option(ctx.OPT_SMEM_HEADROOM_KB, ctx.SMEM_HEADROOM_DEFAULT_KB)  # the variants below run beside the library's own kernels only
-        gat._headroom_set = False
         per_rank = last_counts[0]
         res["overlapped_nccl"] = {"ms_per_step": round(ms_n, 5), "frame_sets_per_sec": fs_per_sec(ms_n), "vs_compute_only": round(ms_c / ms_n, 4),
                                   "bytes_into_root_per_step": 8 * (sum(per_rank) - per_rank[0]),
-                                  "kind": "ti_gather_counts_begin/finish + ti_gather_records (grouped ncclSend/ncclRecv) on the exchange stream; remap grids leave 36 KB of shared memory per SM to NCCL"}
+                                  "kind": "ti_gather_counts_begin/finish + ti_gather_records (grouped ncclSend/ncclRecv) on the exchange stream"}
         if rank == 0:  # the checker, outside the timed region: last step's fused list against the oracle, every rank's frames
             n_tot = sum(per_rank)
             got = np.sort(Config5.first_sets(gathered[(steps - 1) % NB][:n_tot].cpu().numpy().view(np.uint64), check_sets))

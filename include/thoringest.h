@@ -109,7 +109,7 @@ typedef enum ti_option {
     TI_OPT_L2_SCRATCH_KB = 10,        /* two-pass rectify (BGR8 -> MONO8, NV12 -> RGB8): KB of intermediate frames per chunk of the batch (default 0: one chunk) */
     TI_OPT_PUSH_TMA = 11,             /* peer copy of ti_cloud_push: 1 = TMA bulk copies issued by one lane per CTA (default), 0 = 16-byte stores */
     TI_OPT_RECTIFY_QUAD = 12,         /* pair-window kernel: 1 = maps uploaded from now on try the quad layout (4 pixels per lane and window) first (default), 0 = pairs; 2..32 = quad with that many exception entries per (tile, warp) (default 24) */
-    TI_OPT_SMEM_HEADROOM_KB = 13,     /* KB of shared memory per SM the persistent remap kernels leave to kernels running beside them (default 20: the library's own exchange kernels; 36 for NCCL overlapped with ingest) */
+    TI_OPT_SMEM_HEADROOM_KB = 13,     /* KB of shared memory per SM the persistent remap kernels leave to kernels running beside them (default 20: room for the library's own exchange kernels) */
     TI_OPT_PUSH_BLOCKS = 9            /* CTAs of the peer-store copy kernels of ti_cloud_push / ti_inbox_take (default: one per SM) */
 } ti_option;
 int ti_set_option(ti_ctx* ctx, int option, int value);

@@ -113,9 +113,8 @@ constexpr int P4_CONSUMER_WARPS = 8;
 constexpr int P4_THREADS = (P4_CONSUMER_WARPS + 1) * 32;  // consumers + TMA issuer
 constexpr int P4_MAX_STAGES = 8;
 constexpr int P4_SMEM_HEADROOM_KB = 20;  // shared memory per SM the window kernels leave to co-resident exchange kernels
-constexpr int P4_SMEM_HEADROOM_NCCL_KB = 36;  // ... what a host that overlaps NCCL with ingest should ask for (TI_OPT_SMEM_HEADROOM_KB): NCCL's send/recv CTAs need more than
-                                              // the library's own 12 KB copy CTAs (measured at N = 8: with 23 KB left NCCL waited for a whole persistent grid
-                                              // to drain - 0.40 of the job without exchange; with 34 KB left 0.80)
+constexpr int P4_SMEM_HEADROOM_NCCL_KB = 36;  // what a host may ask for instead (TI_OPT_SMEM_HEADROOM_KB) when other libraries' CTAs run beside the remap grids.
+                                              // Measured for NCCL's send/recv at N = 4 and 8: no help (0.34-0.40 of the job without exchange either way), so nothing sets it
 constexpr int P4_LUT_ROW_WORDS = 192;  // per tile row: 32 lanes x 2 pairs x {window word, pixel a word, pixel b word}
 constexpr uint32_t P4_EXC_UNUSED = 0x80000000u;  // last word of an unused exception entry (no destination offset is -2^31)
 constexpr int P4_MAX_EXC = 32;         // exception entries per (tile, warp): one lane each in the per-frame fix-up pass

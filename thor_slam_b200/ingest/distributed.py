@@ -101,7 +101,6 @@ class CloudGather:
         self._nccl_ready = False
         self._keep: Any = None
         self._pending_counts: list[int] | None = None
-        self._headroom_set = False
 
     def _ensure_nccl(self) -> None:
         if self._nccl_ready:
@@ -165,11 +164,6 @@ class CloudGather:
         caller enqueues its next batch between this call and :meth:`records_send`, which blocks for the counts."""
         if self.backend == "nccl" and n_records.is_cuda:
             self._ensure_nccl()
-            if not self._headroom_set:
-                # NCCL's CTAs run beside the persistent remap grids of the next batch: leave them their shared memory (measured at
-                # N = 8: without it NCCL waits for a whole grid to drain, 0.40 instead of 0.80 of the job without exchange)
-                self.ctx.set_option(self.ctx.OPT_SMEM_HEADROOM_KB, self.ctx.SMEM_HEADROOM_NCCL_KB)
-                self._headroom_set = True
             self.ctx.gather_counts_begin(n_records)
             self._pending_counts = None
         else:
