@@ -88,12 +88,12 @@ def main() -> None:
             print(f"case {i}: {s}->{d} dst {dst_w}x{dst_h} src {src_w}x{src_h} n={n}: MISMATCH {e}", flush=True)
             raise SystemExit(1)
         p = ctx.rectify_plan(20)
-        plans[(s, d, p["variant"] if d == "mono8" else p["colour_variant"])] += 1
+        plans[(s, d, (f"{p['variant']} ({p['pixels_per_window']} px/window)" if p["variant"] == 4 else p["variant"]) if d == "mono8" else p["colour_variant"])] += 1
         if p["overflow_pixels"]:
             overflow.append(p["overflow_pixels"])
     print(f"{args.cases} cases, every variant bit-exact against cv2.remap, {time.time() - t0:.0f} s")
     print(f"  {len(overflow)} slots ran the pair-window kernel WITH an overflow list (up to {max(overflow, default=0)} pixels repaired after the kernel)")
-    for k, v in sorted(plans.items()):
+    for k, v in sorted(plans.items(), key=str):
         print(f"  {k[0]:>5s} -> {k[1]:<5s} default kernel variant {k[2]}: {v} cases")
 
 
