@@ -264,6 +264,13 @@ def test_layout_choice_of_the_pair_window_kernel_emulated(emu_backend):
     finally:
         ctx.set_option(ctx.OPT_RECTIFY_QUAD, 1)
     cases.check_rectify(emu_backend, 21, mx, my, "mono8", "mono8", 256, 96, n=2, expect_variant=4)
+    # the ring depth follows the shared memory the host asks the remap grids to leave free; the bytes do not
+    try:
+        for kb in (0, 36, 128):
+            ctx.set_option(ctx.OPT_SMEM_HEADROOM_KB, kb)
+            cases.check_rectify(emu_backend, 21, mx, my, "mono8", "mono8", 256, 96, n=2, expect_variant=4)
+    finally:
+        ctx.set_option(ctx.OPT_SMEM_HEADROOM_KB, ctx.SMEM_HEADROOM_DEFAULT_KB)
 
 
 def test_rotated_map_overflows_the_exception_table_emulated(emu_backend):
